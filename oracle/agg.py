@@ -1,0 +1,177 @@
+"""Per-record taxon aggregation: LCA*, hybrid and MRTL (oracle; test infrastructure only).
+
+Literal restatement of /root/reference/src/agg/mod.rs:27-44 (count, filter),
+src/tree/mod.rs:29-101 (Tree::new/create/collapse/aggregate), src/tree/lca.rs:34-40 (LCA*),
+src/tree/mix.rs:43-64 (hybrid), src/rmq/rtl.rs:28-57 (MRTL) and the record loop of
+src/commands/taxa2agg.rs:159-181.
+
+Where the reference picks among equal maxima by HashMap/HashSet iteration order
+(tree/mix.rs:52-55, rmq/rtl.rs:52-55; acknowledged by its own tests at tree/mix.rs:79 and
+rmq/rtl.rs:89-91) the functions here return the SET of every answer the reference can give.
+f32 arithmetic is done with numpy.float32 exactly where the reference uses f32.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from .taxonomy import Taxonomy, UnknownTaxon
+
+f32 = np.float32
+
+
+class EmptyInput(Exception):
+    pass
+
+
+def count(ids: Iterable[int]) -> Dict[int, np.float32]:
+    """agg/mod.rs:27-36 with the unscored parser (taxa2agg.rs:150-152): 1.0 per occurrence."""
+    c: Dict[int, np.float32] = {}
+    for t in ids:
+        c[t] = f32(c.get(t, f32(0.0)) + f32(1.0))
+    return c
+
+
+def filter_counts(c: Dict[int, np.float32], lower_bound: float) -> Dict[int, np.float32]:
+    """agg/mod.rs:39-44."""
+    lb = f32(lower_bound)
+    return {t: v for t, v in c.items() if v >= lb}
+
+
+class _Tree:
+    __slots__ = ("root", "value", "children")
+
+    def __init__(self, root: int, value, children: List["_Tree"]):
+        self.root = root
+        self.value = value
+        self.children = children
+
+
+def _tree_new(tax: Taxonomy, taxons: Dict[int, np.float32]) -> _Tree:
+    """tree/mod.rs:29-67."""
+    tree: Dict[int, Set[int]] = {}
+    queue = list(taxons.keys())
+    qi = 0
+    while qi < len(queue):
+        tid = queue[qi]
+        qi += 1
+        parent = tax.parent(tid)             # :37 UnknownTaxon
+        if tid == parent:
+            continue
+        if parent not in tree:
+            queue.append(parent)
+        tree.setdefault(parent, set()).add(tid)
+
+    def create(root: int) -> _Tree:
+        return _Tree(root, taxons.get(root, f32(0.0)),
+                     [create(c) for c in sorted(tree.get(root, ()))])
+
+    import sys
+    sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+    return create(tax.root)
+
+
+def _collapse(t: _Tree) -> _Tree:
+    """tree/mod.rs:71-86 with combine = Add::add."""
+    value = t.value
+    new = t
+    while len(new.children) == 1:
+        new = new.children[0]
+        value = f32(value + new.value)
+    return _Tree(new.root, value, [_collapse(c) for c in new.children])
+
+
+def _aggregate(t: _Tree) -> _Tree:
+    """tree/mod.rs:90-101."""
+    children = [_aggregate(c) for c in t.children]
+    value = t.value
+    for c in children:
+        value = f32(value + c.value)
+    return _Tree(t.root, value, children)
+
+
+def lca_star(tax: Taxonomy, taxons: Dict[int, np.float32]) -> int:
+    """tree/lca.rs:34-40.  Deterministic."""
+    if not taxons:
+        raise EmptyInput()
+    return _collapse(_tree_new(tax, taxons)).root
+
+
+def hybrid(tax: Taxonomy, taxons: Dict[int, np.float32], factor: float) -> Set[int]:
+    """tree/mix.rs:43-64.  Returns every answer reachable through tied maxima."""
+    if not taxons:
+        raise EmptyInput()
+    fac = f32(factor)
+    subtree = _aggregate(_collapse(_tree_new(tax, taxons)))
+    results: Set[int] = set()
+
+    def descend(base: _Tree):
+        while True:
+            if not base.children:
+                results.add(base.root)
+                return
+            m = max(c.value for c in base.children)
+            if f32(m / base.value) < fac:     # :57 f32 division then compare
+                results.add(base.root)
+                return
+            tied = [c for c in base.children if c.value == m]
+            if len(tied) == 1:
+                base = tied[0]
+                continue
+            for c in tied:
+                descend(c)
+            return
+
+    descend(subtree)
+    return results
+
+
+def mrtl(tax: Taxonomy, taxons: Dict[int, np.float32]) -> Set[int]:
+    """rmq/rtl.rs:39-57.  Returns the set of arg-maxima."""
+    rtl: Dict[int, np.float32] = {}
+    for taxon, cnt in taxons.items():
+        c = cnt
+        nxt = taxon
+        while True:
+            # ancestors[next]; ancestors[root] = None (:31-33)
+            if nxt == tax.root:
+                break
+            if nxt >= len(tax.parents) or tax.parents[nxt] is None:
+                break
+            anc = tax.parents[nxt]
+            c = f32(c + taxons.get(anc, f32(0.0)))
+            nxt = anc
+        if nxt != tax.root:
+            raise UnknownTaxon(nxt)           # :47-49
+        rtl[taxon] = c
+    if not rtl:
+        raise EmptyInput()
+    m = max(rtl.values())
+    return {t for t, v in rtl.items() if v == m}
+
+
+LCA_STAR, HYBRID, MRTL = 0, 1, 2
+
+
+def taxa2agg_record(tax: Taxonomy, snapping: Sequence[Optional[int]], ids: Sequence[int],
+                    strategy: int, factor: float = 0.25, lower_bound: float = 0.0) -> Set[int]:
+    """taxa2agg.rs:159-181 for one record: the set of ids the reference may print."""
+    counts = filter_counts(count(t for t in ids if t != 0), lower_bound)   # :169-170
+    if not counts:
+        return {1}                                                        # :174-175 literal "1"
+    if strategy == LCA_STAR:
+        res = {lca_star(tax, counts)}
+    elif strategy == HYBRID:
+        res = hybrid(tax, counts, factor)
+    elif strategy == MRTL:
+        res = mrtl(tax, counts)
+    else:
+        raise ValueError("unknown strategy")
+    out = set()
+    for a in res:
+        s = snapping[a]
+        if s is None:
+            raise UnknownTaxon(a)   # `.unwrap()` panic in the reference (:178)
+        out.add(s)
+    return out

@@ -1,0 +1,260 @@
+"""Pins the oracle against every in-scope known-answer vector the reference holds
+(SURVEY Appendix E): unit tests and doc-comment examples, cited per test."""
+import itertools
+
+import pytest
+
+from oracle import agg, fasta, fstv2, lookup, pipeline, seedextend, taxonomy, translate
+
+# /root/reference/src/fixtures.rs:4-21
+FIXTURE = [
+    (1, "root", 0, 1, True),
+    (2, "Bacteria", 1, 1, True),
+    (10239, "Viruses", 1, 1, True),
+    (12884, "Viroids", 1, 1, True),
+    (185751, "Pospiviroidae", 19, 12884, True),
+    (185752, "Avsunviroidae", 19, 12884, True),
+]
+
+
+@pytest.fixture(scope="module")
+def tax():
+    return taxonomy.Taxonomy(FIXTURE)
+
+
+def cagg(ids):
+    return agg.count(ids)
+
+
+# ---- dna/mod.rs:114-135
+def test_strand_from():
+    assert translate.strand("ACGT*TCGA") == list("ACGTNTCGA")
+
+
+def test_strand_reversed():
+    assert translate.reversed_strand(list("TGCANACGT")) == list("ACGTNTGCA")
+
+
+def test_strand_frames():
+    s = list("ACGT")
+    assert s[0:] == list("ACGT") and s[1:] == list("CGT") and s[2:] == list("GT")
+    # frame() of a too-short strand is empty (dna/mod.rs:92-98)
+    assert translate.translate_frame(1, False, list("AC"), 3) == ""
+
+
+# ---- dna/translation.rs:205-232
+def test_translate_codon():
+    aas, starts = translate.get_table(1)
+    assert translate.translate_codon(aas, starts, False, "T", "T", "G") == "L"
+    assert translate.translate_codon(aas, starts, True, "T", "T", "G") == "M"
+
+
+def test_translation_table_parsing():
+    for i in range(1, 24):
+        if i in (7, 8, 17, 18, 19, 20):
+            with pytest.raises(translate.UnknownTable):
+                translate.get_table(i)
+        else:
+            aas, starts = translate.get_table(i)
+            assert len(aas) == 64 and len(starts) == 64
+
+
+# ---- commands/translate.rs:21-40 (doc example)
+def test_translate_doc_example():
+    out = pipeline.translate_text(">header1\nGATTACAAA\n", frames=["1", "1R"])
+    assert out == ">header1\nDYK\n>header1\nFVI\n"
+    out = pipeline.translate_text(">header1\nGATTACAAA\n", frames=["1", "1R"], append_name=True)
+    assert out == ">header1|1\nDYK\n>header1|1R\nFVI\n"
+
+
+def test_translate_all_frames_shapes():
+    # a 150-nt read gives 50/49/49/50/49/49 aa
+    recs = translate.translate_record("ACGT" * 37 + "AC")
+    assert [len(p) for _, p in recs] == [50, 49, 49, 50, 49, 49]
+    assert [n for n, _ in recs] == ["1", "2", "3", "1R", "2R", "3R"]
+    # N anywhere in a codon -> '-'
+    assert translate.translate_record("ACNGGG", frames=["1"])[0][1] == "-G"
+    # lowercase is N (dna/mod.rs:34-44)
+    assert translate.translate_record("acgGGG", frames=["1"])[0][1] == "-G"
+
+
+# ---- commands/prot2kmer.rs:21-35, prot2kmer2lca.rs:32-59 (shape)
+def test_kmers_doc_example():
+    pep = "DAIGDVAKAYKKAG*S"
+    kmers = [pep[i:i + 9] for i in range(len(pep) - 8)]
+    assert kmers == ["DAIGDVAKA", "AIGDVAKAY", "IGDVAKAYK", "GDVAKAYKK", "DVAKAYKKA",
+                     "VAKAYKKAG", "AKAYKKAG*", "KAYKKAG*S"]
+    vals = [571525, 571525, 6920, 6920, 1, 6920]
+    idx = lookup.DictIndex({k.encode(): v for k, v in zip(kmers, vals)})
+    text = ">header1\n" + pep + "\n"
+    assert pipeline.prot2kmer2lca_text(text, idx) == \
+        ">header1\n571525\n571525\n6920\n6920\n1\n6920\n"
+    assert pipeline.prot2kmer2lca_text(text, idx, one_on_one=True) == \
+        ">header1\n571525\n571525\n6920\n6920\n1\n6920\n0\n0\n"
+    # short peptides vanish entirely (prot2kmer2lca.rs:172)
+    assert pipeline.prot2kmer2lca_text(">a\nDAIGDVAK\n>b\n", idx, one_on_one=True) == ""
+
+
+# ---- commands/prot2tryp.rs:22-36, prot2tryp2lca.rs:30-40 (shape)
+TRYP_IN = "AYKKAGVSGHVWQSDGITNCLLRGLTRVKEAVANRDSGNGYINKVYYWTVDKRATTRDALDAGVDGIMTNYPDVITDVLN"
+TRYP_OUT = ["AYK", "K", "AGVSGHVWQSDGITNCLLR", "GLTR", "VK", "EAVANR", "DSGNGYINK", "VYYWTVDK",
+            "R", "ATTR", "DALDAGVDGIMTNYPDVITDVLN"]
+
+
+def test_tryptic_doc_example():
+    assert lookup.tryptic_digest_regex(TRYP_IN) == TRYP_OUT
+    assert lookup.tryptic_digest(TRYP_IN) == TRYP_OUT
+    kept = lookup.tryptic_filter(TRYP_OUT)
+    assert kept == ["AGVSGHVWQSDGITNCLLR", "EAVANR", "DSGNGYINK", "VYYWTVDK",
+                    "DALDAGVDGIMTNYPDVITDVLN"]
+    idx = lookup.DictIndex({b"AGVSGHVWQSDGITNCLLR": 571525, b"EAVANR": 1, b"DSGNGYINK": 571525,
+                            b"VYYWTVDK": 6920})
+    assert pipeline.prot2tryp2lca_text(">header1\n" + TRYP_IN + "\n", idx) == \
+        ">header1\n571525\n1\n571525\n6920\n"
+
+
+def test_tryptic_closed_form_matches_regex():
+    import random
+    rnd = random.Random(7)
+    for _ in range(20000):
+        s = "".join(rnd.choice("KRPA*G") for _ in range(rnd.randint(0, 24)))
+        assert lookup.tryptic_digest(s) == lookup.tryptic_digest_regex(s), s
+
+
+# ---- commands/seedextend.rs:26-50 (doc example)
+def test_seedextend_doc_example():
+    inp = {
+        "header1|1": [9606, 9606, 2759, 9606, 9606, 9606, 9606, 9606, 9606, 9606, 8287],
+        "header1|2": [2026807, 888268, 186802, 1598, 1883],
+        "header1|3": [1883],
+        "header1|1R": [27342, 2759, 155619, 1133106, 38033, 2],
+        "header1|2R": [],
+        "header1|3R": [2951],
+    }
+    text = "".join(fasta.write_record(h, [str(x) for x in v], "\n") for h, v in inp.items())
+    out = pipeline.seedextend_text(text)
+    exp = ">header1|1\n" + "".join(f"{x}\n" for x in inp["header1|1"]) + \
+        ">header1|2\n>header1|3\n>header1|1R\n>header1|2R\n>header1|3R\n"
+    assert out == exp
+
+
+def test_seedextend_quirks():
+    # SURVEY Appendix A.4 observed consequences of the verbatim machine
+    assert seedextend.seedextend([0, 5, 5, 5], 2, 1) == [5, 5]
+    assert seedextend.seedextend([0, 5, 5], 2, 1) == []
+    assert seedextend.seedextend([0, 0, 5, 5, 5], 2, 1) == [5, 5, 5]
+    assert seedextend.seedextend([7, 7, 7, 0, 1, 1], 3, 1) == [7, 7, 7, 0, 1, 1]
+    assert seedextend.seedextend([5, 5, 0, 6, 6], 2, 0) == [5, 5, 6, 6]
+    assert seedextend.seedextend([5, 5, 0, 6, 6], 2, 1) == [5, 5, 0, 6, 6]
+    assert seedextend.seedextend([], 2, 0) == []
+
+
+# ---- commands/uniq.rs:22-40, fastq2fasta.rs:26-54
+def test_uniq_doc_example():
+    text = ">header1/1\n147206\n240495\n>header1/2\n1883\n1\n1883\n1883\n"
+    assert pipeline.uniq_text(text, "/") == ">header1\n147206\n240495\n1883\n1\n1883\n1883\n"
+
+
+def test_fastq2fasta_doc_example():
+    a = "@header1/1\nGATAAACAAAACACTCATCC\n+\nAAAAAAAAAAAAAAAAAAAA\n@header2/1\nACCC\n+\nAAAA\n"
+    b = "@header1/2\nGGGTTT\n+\nAAAAAA\n@header2/2\nTTT\n+\nAAA\n"
+    assert fasta.fastq2fasta([a, b]) == \
+        ">header1/1\nGATAAACAAAACACTCATCC\n>header1/2\nGGGTTT\n>header2/1\nACCC\n>header2/2\nTTT\n"
+
+
+# ---- commands/buildindex.rs:20-28
+def test_index_round_trip():
+    data = fstv2.build([(b"AAAAA", 2759), (b"BBBBBB", 9153)])
+    f = fstv2.Fst(data)
+    assert list(f.stream()) == [(b"AAAAA", 2759), (b"BBBBBB", 9153)]
+    # SURVEY Appendix B self-consistent known answer (55 bytes)
+    assert data.hex() == ("0200000000000000" "0000000000000000" "0010ad" "ededed" "0010b1"
+                          "f1f1f1f1" "c123c70a0108424112" "02" "0200000000000000"
+                          "2600000000000000")
+
+
+# ---- taxon.rs:417-429
+def test_taxon_parsing():
+    assert taxonomy.parse_taxon("1\tFelis catus\tspecies\t4\t\x01") == \
+        (1, "Felis catus", taxonomy.RANKS.index("species"), 4, True)
+    assert taxonomy.parse_taxon("1\tFelis catus\tspecies\t4\t\x00")[4] is False
+    for bad in ["hello world", "a\tFelis catus\tspecies\t4\t\x01", "1\tFelis catus\tspecies\tb\t\x01",
+                "1\tFelis catus\tspecies\t4\tz", "1\tFelis catus\tnorank\t4\t\x01"]:
+        with pytest.raises(taxonomy.TaxonError):
+            taxonomy.parse_taxon(bad)
+
+
+def test_taxon_list_and_root(tax):
+    # taxon.rs:449-464
+    assert tax.root == 1
+    assert tax.parents[185751] == 12884 and tax.parents[1] == 1 and tax.parents[3] is None
+    snap = tax.snapping(False)
+    assert snap[185751] == 185751 and snap[1] == 1 and snap[3] is None
+
+
+# ---- agg/mod.rs:82-118 over the in-scope aggregators
+def test_empty_singleton_unknown(tax):
+    with pytest.raises(agg.EmptyInput):
+        agg.lca_star(tax, {})
+    with pytest.raises(agg.EmptyInput):
+        agg.hybrid(tax, {}, 0.5)
+    with pytest.raises(agg.EmptyInput):
+        agg.mrtl(tax, {})
+    for t in FIXTURE:
+        c = cagg([t[0]])
+        assert agg.lca_star(tax, c) == t[0]
+        for f in (0.0, 0.5, 1.0):
+            assert agg.hybrid(tax, c, f) == {t[0]}
+        assert agg.mrtl(tax, c) == {t[0]}
+    for ids in ([5], [1, 2, 5, 1]):
+        for fn in (lambda c: agg.lca_star(tax, c), lambda c: agg.hybrid(tax, c, 0.5),
+                   lambda c: agg.mrtl(tax, c)):
+            with pytest.raises(taxonomy.UnknownTaxon) as e:
+                fn(cagg(ids))
+            assert e.value.tid == 5
+
+
+# ---- tree/lca.rs:51-77
+def test_lca_star_vectors(tax):
+    L = lambda ids: agg.lca_star(tax, cagg(ids))
+    assert L([12884, 185752]) == 185752 and L([185752, 12884]) == 185752
+    assert L([1, 2]) == 2 and L([2, 1]) == 2
+    assert L([2, 10239]) == 1 and L([10239, 2]) == 1
+    assert L([185751, 185752]) == 12884 and L([185752, 185751]) == 12884
+    for p in itertools.permutations([12884, 185751, 185752]):
+        assert L(list(p)) == 12884
+
+
+# ---- tree/mix.rs:75-97
+def test_hybrid_vectors(tax):
+    H = lambda ids, f: agg.hybrid(tax, cagg(ids), f)
+    assert H([12884, 185751], 0.0) == {185751}
+    assert H([12884, 185751, 185752, 185752], 0.0) == {185752}
+    # the reference's own test accepts either child (tree/mix.rs:79): the tie set is both
+    assert H([1, 1, 10239, 10239, 12884, 185751, 185752], 0.0) == {185751, 185752}
+    assert H([12884, 185751], 1.0) == {185751}
+    assert H([12884, 185751, 185752, 185752], 1.0) == {12884}
+    assert H([1, 1, 10239, 10239, 10239, 12884, 185751, 185752], 1.0) == {1}
+    assert H([12884, 185751], 0.66) == {185751}
+    assert H([1, 12884, 12884, 185751], 0.66) == {185751}
+    assert H([1, 12884, 10239, 185751, 185751, 185752], 0.66) == {12884}
+
+
+# ---- rmq/rtl.rs:69-92
+def test_mrtl_vectors(tax):
+    M = lambda ids: agg.mrtl(tax, cagg(ids))
+    assert M([1]) == {1}
+    assert M([1, 12884]) == {12884}
+    assert M([1, 12884, 185751]) == {185751}
+    assert M([1, 1, 1, 185751, 1, 1]) == {185751}
+    assert M([1, 1, 185752, 185751, 185751, 1]) == {185751}
+    assert M([1, 1, 185752, 185751, 1]) == {185751, 185752}
+
+
+# ---- commands/taxa2agg.rs:159-181
+def test_taxa2agg_record_loop(tax):
+    out = pipeline.taxa2agg_sets(">a\n185751\n0\n185751\n12884\n>b\n0\n0\n>c\n", tax, agg.LCA_STAR)
+    assert out == [("a", {185751}), ("b", {1}), ("c", {1})]
+    # lower bound drops singletons (agg/mod.rs:39-44)
+    out = pipeline.taxa2agg_sets(">a\n185751\n185751\n185752\n", tax, agg.LCA_STAR, lower_bound=2)
+    assert out == [("a", {185751})]
