@@ -1,0 +1,215 @@
+/*
+ * umgap_gpu.h -- C ABI of libumgap_gpu.so, the B200 (sm_100a) implementation of UMGAP's
+ * per-read classification hot path.
+ *
+ * The reference (unipept/umgap, Rust) has no FFI seam of its own; its boundary is the
+ * process (argv + FASTA streams + an `fst` index file + a taxonomy TSV).  Each entry point
+ * below replaces the body of one reference command loop, taking the *parsed* form of that
+ * command's stdin and producing the parsed form of its stdout.  The reference interface each
+ * one replaces is cited as file:line relative to the reference repository.  A Rust `-sys`
+ * crate binds these symbols one to one.
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative umgap_status on failure; the
+ *     message for the calling thread is available from umgap_last_error().
+ *   - Pointers are caller-owned HOST memory unless the parameter name ends in `_dev`
+ *     (device memory on the handle's GPU).  No torch / C++ types cross the boundary.
+ *   - Offsets arrays have n+1 entries (CSR style): item i spans [off[i], off[i+1]).
+ *   - Handles are opaque; one in-flight call per handle, several handles may coexist.
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with UMGAP_ERR_CUDA.
+ */
+#ifndef UMGAP_GPU_H
+#define UMGAP_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMGAP_ABI_VERSION 1
+
+typedef enum umgap_status {
+    UMGAP_OK = 0,
+    UMGAP_ERR_INVALID = -1,       /* bad argument / invalid invocation (reference: exit 1)   */
+    UMGAP_ERR_IO = -2,            /* file could not be read / malformed file                 */
+    UMGAP_ERR_CUDA = -3,          /* CUDA runtime failure or no device                       */
+    UMGAP_ERR_UNKNOWN_TAXON = -4, /* "Unknown Taxon ID: <id>" (tree/mod.rs:37, rmq/rtl.rs:47) */
+    UMGAP_ERR_CAPACITY = -5,      /* value / key outside what the device table can encode    */
+    UMGAP_ERR_NOMEM = -6
+} umgap_status;
+
+/* Result markers in uint32 outputs. */
+#define UMGAP_MISS 0xFFFFFFFFu   /* k-mer absent from the index (before -o mapping)          */
+#define UMGAP_ABSENT 0xFFFFFFFFu /* classify: group produced no record at all (every frame
+                                    shorter than k, prot2kmer2lca.rs:172)                    */
+
+typedef struct umgap_index umgap_index;       /* GPU-resident key -> taxon table            */
+typedef struct umgap_taxonomy umgap_taxonomy; /* GPU-resident tree: ancestor matrix etc.    */
+
+/* Aggregation strategies of `taxa2agg -a` (taxa2agg.rs:111-139, 186-221). */
+enum { UMGAP_AGG_LCA_STAR = 0, UMGAP_AGG_HYBRID = 1, UMGAP_AGG_MRTL = 2 };
+
+/* ---- errors / device ------------------------------------------------------------------ */
+const char* umgap_last_error(void);
+int umgap_abi_version(void);
+int umgap_device_count(void); /* number of CUDA devices, or negative status */
+
+/* ---- index: replaces fst::Map::{from_path,from_bytes} + Map::get ------------------------
+ * call sites prot2kmer2lca.rs:109-114,176; prot2tryp2lca.rs:89-94,130.                      */
+
+/* Streams an `fst` 0.3.x (format v2) Map file once and builds the device table.
+ * k > 0: fixed-length k-mer table (keys of any other length in the file can never be
+ * queried by prot2kmer2lca -k and are skipped; k <= 9).  k == 0: variable-length peptide
+ * table for prot2tryp2lca.  load_factor in (0,1]; <= 0 selects the default (0.70).           */
+int umgap_index_load_fst(const char* path, int k, int device, double load_factor,
+                         umgap_index** out);
+
+/* Same table from explicit pairs.  keys: concatenated key bytes, key i spans
+ * [key_off[i], key_off[i+1]); key_off may be NULL when k > 0 (then key i = keys[i*k..]). */
+int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
+                           uint64_t n, int k, int device, double load_factor, umgap_index** out);
+
+void umgap_index_free(umgap_index* idx);
+
+typedef struct umgap_index_info {
+    uint64_t n_keys;        /* distinct keys resident                                      */
+    uint64_t n_buckets;     /* 32-byte buckets                                             */
+    uint64_t bytes;         /* device bytes of the table                                   */
+    uint64_t n_skipped;     /* file keys skipped (length != k)                             */
+    uint64_t n_flagged;     /* buckets whose overflow flag is set                          */
+    uint64_t n_displaced;   /* keys stored outside their home bucket                       */
+    uint64_t max_probe;     /* longest probe sequence of any resident key (buckets)        */
+    int k;                  /* 0 = variable-length table                                   */
+    int device;
+    int alphabet_size;      /* distinct residue bytes seen in keys                         */
+} umgap_index_info;
+int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info);
+
+/* ---- taxonomy: replaces taxon::read_taxa_file + TaxonTree::new + TaxonList::new +
+ * TaxonTree::snapping (taxon.rs:89-128, 135-163, 224-247, 251-301; taxa2agg.rs:103-109). */
+int umgap_taxonomy_load(const char* tsv_path, int device, umgap_taxonomy** out);
+/* rank[i]: index into the reference's Rank enum (rank.rs:9-44), 0 = "no rank". */
+int umgap_taxonomy_from_arrays(const uint64_t* ids, const uint64_t* parents, const uint8_t* rank,
+                               const uint8_t* valid, uint64_t n, int device,
+                               umgap_taxonomy** out);
+void umgap_taxonomy_free(umgap_taxonomy* tax);
+typedef struct umgap_taxonomy_info {
+    uint64_t n_taxa;
+    uint64_t max_id;
+    uint64_t root;
+    uint32_t max_depth; /* depth of the deepest taxon (root = 0) */
+    int device;
+} umgap_taxonomy_info;
+int umgap_taxonomy_get_info(const umgap_taxonomy* tax, umgap_taxonomy_info* info);
+
+/* ---- translate: replaces the record loop of translate.rs:114-133 (+ dna/mod.rs:23-103,
+ * dna/translation.rs:125-144).  frames_mask bit i selects frame i in the reference order
+ * 1,2,3,1R,2R,3R (translate.rs:83-90).  Output: one peptide per (read, selected frame) in
+ * that order; aa_off has nreads*popcount(frames_mask)+1 entries.  aa_out must hold
+ * umgap_translate_bound() bytes.  Unknown table -> UMGAP_ERR_INVALID ("Unknown table").   */
+uint64_t umgap_translate_bound(uint64_t total_nt, uint64_t nreads, uint8_t frames_mask);
+int umgap_translate(int device, const uint8_t* nt, const uint64_t* read_off, uint64_t nreads,
+                    int table, int methionine, uint8_t frames_mask, uint8_t* aa_out,
+                    uint64_t* aa_off);
+
+/* ---- prot2kmer2lca: replaces the per-record body of stream_prot2kmer2lca
+ * (prot2kmer2lca.rs:168-185).  Peptides shorter than k produce NO record: kept[i] = 0 and an
+ * empty span (the reference drops the header too, :172).  With one_on_one (-o) a miss is
+ * written as 0, otherwise it is omitted (:115,176).  taxa_out must hold
+ * umgap_kmer_lookup_bound() entries; taxa_off has npeps+1 entries.                          */
+uint64_t umgap_kmer_lookup_bound(uint64_t total_aa, uint64_t npeps);
+int umgap_kmer_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t* pep_off,
+                      uint64_t npeps, int one_on_one, uint32_t* taxa_out, uint64_t* taxa_off,
+                      uint8_t* kept);
+
+/* ---- prot2tryp2lca: replaces prot2tryp2lca.rs:105-134 for the default cleavage pattern
+ * ([KR])([^P]).  Each input item is one physical LINE of a record (the reader is
+ * unwrap=false, :100,109); rec_of_line is not needed: the caller concatenates per record.
+ * keep / drop: NUL-terminated residue sets ("" = none).                                    */
+uint64_t umgap_tryp_lookup_bound(uint64_t total_aa, uint64_t nlines);
+int umgap_tryp_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t* line_off,
+                      uint64_t nlines, int minlen, int maxlen, const char* keep,
+                      const char* drop, int one_on_one, uint32_t* taxa_out, uint64_t* taxa_off);
+
+/* ---- seedextend (unranked): replaces seedextend.rs:92-149,167-176.  out holds at most
+ * rec_off[nrecs] entries; out_off has nrecs+1 entries.                                     */
+int umgap_seedextend(int device, const uint32_t* taxa, const uint64_t* rec_off, uint64_t nrecs,
+                     int min_seed_size, int max_gap_size, uint32_t* out, uint64_t* out_off);
+
+/* ---- taxa2agg: replaces the record loop of taxa2agg.rs:159-181 with the aggregators
+ * tree::lca (tree/lca.rs:34-40), tree::mix (tree/mix.rs:43-64) and rmq::rtl
+ * (rmq/rtl.rs:39-57), unscored input.  taxon_out[i] is the snapped aggregate of record i
+ * ("1" for an empty record, :174-175).  Ties in hybrid / MRTL, which the reference breaks
+ * by hash iteration order, are broken deterministically.                    */
+int umgap_aggregate(const umgap_taxonomy* tax, const uint32_t* taxa, const uint64_t* rec_off,
+                    uint64_t nrecs, int strategy, float factor, float lower_bound,
+                    int ranked_only, uint32_t* taxon_out);
+
+/* ---- fused path: translate -a | prot2kmer2lca [-o] | [seedextend] | uniq -d | taxa2agg
+ * (scripts/umgap-analyse.sh:276-311) without materialising text between the stages.       */
+typedef struct umgap_pipeline_opts {
+    int table;          /* translate -t, default 1                                        */
+    int methionine;     /* translate -m                                                   */
+    int one_on_one;     /* prot2kmer2lca -o                                               */
+    int seedextend;     /* 0: stage absent (tryptic presets), 1: present                  */
+    int min_seed_size;  /* seedextend -s, default 2                                       */
+    int max_gap_size;   /* seedextend -g, default 0                                       */
+    int strategy;       /* UMGAP_AGG_*                                                    */
+    float factor;       /* taxa2agg -f, default 0.25                                      */
+    float lower_bound;  /* taxa2agg -l, default 0                                         */
+    int ranked_only;    /* taxa2agg -r                                                    */
+} umgap_pipeline_opts;
+void umgap_pipeline_opts_default(umgap_pipeline_opts* o);
+
+/* Reads r in [group_off[g], group_off[g+1]) are the records `uniq -d` joins (uniq.rs:56-84):
+ * for paired-end input two consecutive reads.  taxon_out has ngroups entries; a group none
+ * of whose frames reaches k residues yields UMGAP_ABSENT (no record in the reference).
+ * n_lookups (optional) receives the number of k-mer lookups performed.                      */
+int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
+                         const umgap_pipeline_opts* opts, const uint8_t* nt,
+                         const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
+                         uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups);
+
+/* Device-resident variant: all arrays already in HBM on idx's device; runs asynchronously on
+ * `stream` (a cudaStream_t, NULL = default stream) using the handle's cached workspace.
+ * total_nt = read_off[nreads] must be supplied by the caller (no device->host sync inside). */
+int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
+                             const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                             const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
+                             const uint64_t* group_off_dev, uint64_t ngroups,
+                             uint32_t* taxon_out_dev, void* stream);
+
+/* Stage kernels on device-resident data, used by the benchmark to time the lookup kernel in
+ * isolation: ids_dev receives 2*total_nt entries (position-major, both strands).           */
+int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts* opts,
+                               const uint8_t* nt_dev, const uint64_t* read_off_dev,
+                               uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
+                               void* stream);
+
+/* ---- benchmark / test aids (synthetic data of SURVEY 8(d); not part of the reference) ---- */
+typedef struct umgap_synth_spec {
+    uint64_t seed;
+    uint64_t n_proteins;   /* proteins of protein_len residues each                        */
+    uint32_t protein_len;  /* index keys = all 9-mers of all proteins                      */
+    uint32_t home_pct;     /* % of k-mers valued with the protein's own taxon              */
+    uint32_t ancestor_pct; /* % valued with a random ancestor; rest: unrelated taxon       */
+} umgap_synth_spec;
+/* Builds the table on the device from the counter-based proteome (no host copy). */
+int umgap_index_build_synthetic(const umgap_synth_spec* spec, const umgap_taxonomy* tax,
+                                int device, double load_factor, umgap_index** out);
+/* Fills nt_dev with npairs*2 reads of read_len nucleotides drawn from the same proteome
+ * (hit_pct % of pairs) or uniformly at random.                                              */
+int umgap_synth_reads_dev(const umgap_synth_spec* spec, uint64_t read_seed, uint64_t first_pair,
+                          uint64_t npairs, uint32_t read_len, uint32_t hit_pct,
+                          uint8_t* nt_dev, void* stream);
+/* Random 32-byte-sector gather over the index' own table memory: the measured denominator
+ * of the "random-sector roofline".  Returns sectors/second in *rate.                       */
+int umgap_randsector_bench(const umgap_index* idx, uint64_t n_gathers, int iters, double* rate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMGAP_GPU_H */

@@ -1,0 +1,330 @@
+"""GPU parity: every C-ABI stage and the fused path against the CPU oracle, bit-exact.
+
+Runs on the B200 box only (`-m gpu`).  Hybrid / MRTL answers are compared against the oracle's
+admissible SET (the reference breaks ties by hash iteration order): equality
+whenever the set is a singleton, membership otherwise.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import agg as oagg
+from oracle import fstv2, lookup as olookup, pipeline as opipe, seedextend as ose, translate as otr
+from oracle.taxonomy import Taxonomy as OTaxonomy
+
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import umgap_b200.capi as c
+    if c.device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return c
+
+
+@pytest.fixture(scope="module")
+def world(capi):
+    taxa = datagen.make_taxonomy(400, seed=11)
+    otax = OTaxonomy(taxa)
+    proteins = datagen.make_proteome(120, seed=12)
+    index = datagen.make_index(proteins, otax, seed=13)
+    gtax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(taxa))
+    keys = sorted(index)
+    gidx = capi.Index.from_pairs(keys, [index[k] for k in keys], k=9)
+    return dict(taxa=taxa, otax=otax, proteins=proteins, index=index, gtax=gtax, gidx=gidx)
+
+
+def _random_reads(rng, n, maxlen=200):
+    out = []
+    for i in range(n):
+        L = rng.choice([0, 1, 2, 3, 5, 26, 27, 28, 29, 30, 31, 32, 33, 100, 150, 151, 152, maxlen, 300, 701])
+        s = "".join(rng.choice("ACGTACGTACGTNacgtRY*") for _ in range(L))
+        out.append(s)
+    return out
+
+
+def test_translate_all_tables_and_frames(capi):
+    rng = random.Random(5)
+    reads = _random_reads(rng, 60)
+    nt, off = capi.pack_strings([r.encode() for r in reads])
+    for table in (1, 2, 4, 11, 23):
+        for meth in (False, True):
+            for mask in (0x3F, 0x01, 0x28, 0x15):
+                aa, aa_off = capi.translate(nt, off, table, meth, mask)
+                frames = [f for i, f in enumerate(otr.FRAME_NAMES) if mask >> i & 1]
+                j = 0
+                for r in reads:
+                    for name, pep in otr.translate_record(r, table, meth, frames):
+                        got = bytes(aa[int(aa_off[j]):int(aa_off[j + 1])]).decode()
+                        assert got == pep, (table, meth, mask, r, name)
+                        j += 1
+                assert j == len(aa_off) - 1
+
+
+def test_translate_known_answers(capi):
+    # translate.rs:21-40 (GATTACAAA -> DYK / FVI) and dna/translation.rs:205-209 (TTG -> L, -m M)
+    nt, off = capi.pack_strings([b"GATTACAAA", b"TTG"])
+    aa, aa_off = capi.translate(nt, off, 1, False, 0x09)
+    peps = [bytes(aa[int(aa_off[i]):int(aa_off[i + 1])]) for i in range(4)]
+    assert peps[0] == b"DYK" and peps[1] == b"FVI" and peps[2] == b"L"
+    aa, aa_off = capi.translate(nt, off, 1, True, 0x01)
+    assert bytes(aa[int(aa_off[1]):int(aa_off[2])]) == b"M"
+    with pytest.raises(capi.UmgapError) as e:
+        capi.translate(nt, off, 7, False, 0x3F)
+    assert "Unknown table" in str(e.value)
+
+
+def test_kmer_lookup_matches_oracle(capi, world):
+    rng = random.Random(6)
+    peps = []
+    for p in world["proteins"][:40]:
+        s = list(p)
+        for _ in range(3):
+            s[rng.randrange(len(s))] = rng.choice("*-Xa")
+        peps.append("".join(s))
+    peps += ["", "ACD", "ACDEFGHI", "ACDEFGHIK", world["proteins"][0][:9], world["proteins"][1][5:30]]
+    oidx = olookup.DictIndex(world["index"])
+    aa, off = capi.pack_strings([p.encode() for p in peps])
+    for one in (True, False):
+        taxa, toff, kept = capi.kmer_lookup(world["gidx"], aa, off, one)
+        expect = {h: ids for h, ids in olookup.prot2kmer2lca([(str(i), [p]) for i, p in enumerate(peps)], oidx, 9, one)}
+        hits = 0
+        for i, p in enumerate(peps):
+            got = [int(x) for x in taxa[int(toff[i]):int(toff[i + 1])]]
+            if str(i) in expect:
+                assert kept[i] == 1
+                assert got == expect[str(i)], (one, p)
+                hits += sum(1 for g in got if g)
+            else:
+                assert kept[i] == 0 and got == []
+        assert hits > 500
+
+
+def test_index_build_stats_and_misses(capi, world):
+    info = world["gidx"].info()
+    assert info.n_keys == len(world["index"])
+    assert info.k == 9 and info.n_buckets >= 1 << 17
+    # keys absent from the index are misses, also when they share 8 of 9 residues with a key
+    rng = random.Random(7)
+    keys = list(world["index"])
+    probes = []
+    for key in rng.sample(keys, 300):
+        s = bytearray(key)
+        s[rng.randrange(9)] = ord(rng.choice(datagen.AAS))
+        probes.append(bytes(s))
+    aa, off = capi.pack_strings(probes)
+    taxa, toff, _ = capi.kmer_lookup(world["gidx"], aa, off, True)
+    for i, p in enumerate(probes):
+        assert int(taxa[int(toff[i])]) == world["index"].get(p, 0)
+
+
+def test_dense_table_overflow_levels(capi):
+    # a load factor of 1.0 forces displaced keys, flagged buckets and overflow levels
+    rng = random.Random(8)
+    n = 700000
+    keys = set()
+    while len(keys) < n:
+        keys.add(bytes(rng.choice(b"ACDEFGHIKLMNPQRSTVWY") for _ in range(9)))
+    keys = sorted(keys)
+    vals = [(i * 2654435761) % 1000003 + 1 for i in range(n)]
+    idx = capi.Index.from_pairs(keys, vals, k=9, load_factor=1.0)
+    info = idx.info()
+    assert info.n_keys == n and info.n_displaced > 0 and info.n_flagged > 0
+    sample = rng.sample(range(n), 20000)
+    probes = [keys[i] for i in sample]
+    misses = []
+    while len(misses) < 5000:
+        m = bytes(rng.choice(b"ACDEFGHIKLMNPQRSTVWY") for _ in range(9))
+        if m not in set(probes):
+            misses.append(m)
+    keyset = set(keys)
+    aa, off = capi.pack_strings(probes + misses)
+    taxa, toff, _ = capi.kmer_lookup(idx, aa, off, True)
+    for j, i in enumerate(sample):
+        assert int(taxa[j]) == vals[i]
+    for j, m in enumerate(misses):
+        if m not in keyset:
+            assert int(taxa[len(probes) + j]) == 0
+    idx.close()
+
+
+def test_fst_loader_roundtrip(capi, world, tmp_path):
+    items = sorted(world["index"].items())[:20000]
+    extra = [(b"AAAAA", 2759), (b"BBBBBB", 9153)]  # buildindex.rs:20-28 keys (other lengths: skipped)
+    data = fstv2.build(sorted(items + extra))
+    path = tmp_path / "nine.fst"
+    path.write_bytes(data)
+    idx = capi.Index.load_fst(str(path), k=9)
+    info = idx.info()
+    assert info.n_keys == len(items) and info.n_skipped == 2
+    rng = random.Random(9)
+    probe = [k for k, _ in rng.sample(items, 3000)]
+    aa, off = capi.pack_strings(probe)
+    taxa, toff, _ = capi.kmer_lookup(idx, aa, off, True)
+    d = dict(items)
+    assert [int(x) for x in taxa] == [d[k] for k in probe]
+    idx.close()
+    with pytest.raises(capi.UmgapError):
+        capi.Index.load_fst(str(tmp_path / "missing.fst"), k=9)
+
+
+def _random_id_lists(rng, n):
+    out = []
+    for _ in range(n):
+        L = rng.choice([0, 1, 2, 3, 5, 8, 13, 42, 42, 42, 90])
+        pool = [0, 0, 0] + [rng.randrange(1, 6) for _ in range(3)]
+        ids, cur = [], 0
+        for _ in range(L):
+            if rng.random() < 0.45:
+                cur = rng.choice(pool)
+            ids.append(cur)
+        out.append(ids)
+    return out
+
+
+def test_seedextend_matches_oracle(capi):
+    rng = random.Random(10)
+    recs = _random_id_lists(rng, 600)
+    recs += [[0, 5, 5, 5], [0, 5, 5], [0, 0, 5, 5, 5], [7, 7, 7, 0, 1, 1], [5, 5, 0, 6, 6],
+             [9606, 9606, 2759, 9606, 9606, 9606, 9606, 9606, 9606, 9606, 8287]]
+    flat = np.array([x for r in recs for x in r], dtype=np.uint32)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in recs])
+    for s in (2, 3, 4):
+        for g in (0, 1, 2):
+            out, ooff = capi.seedextend(flat, off, s, g)
+            for i, r in enumerate(recs):
+                got = [int(x) for x in out[int(ooff[i]):int(ooff[i + 1])]]
+                assert got == ose.seedextend(r, s, g), (s, g, r)
+
+
+def _check_agg(capi, world, recs, strategy, factor, lb, ranked):
+    otax = world["otax"]
+    flat = np.array([x for r in recs for x in r], dtype=np.uint32)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in recs])
+    got = capi.aggregate(world["gtax"], flat, off, strategy, factor, lb, ranked)
+    snapping = otax.snapping(ranked)
+    singles = 0
+    for i, r in enumerate(recs):
+        want = oagg.taxa2agg_record(otax, snapping, r, strategy, factor, lb)
+        assert int(got[i]) in want, (strategy, factor, lb, ranked, r, int(got[i]), want)
+        singles += len(want) == 1
+    return singles
+
+
+def test_aggregate_matches_oracle(capi, world):
+    rng = random.Random(14)
+    otax = world["otax"]
+    ids = [t[0] for t in otax.by_id if t is not None]
+    recs = [[], [0, 0], [ids[3]], [ids[3]] * 5]
+    for _ in range(500):
+        home = rng.choice(ids)
+        path = otax.root_path(home)
+        L = rng.choice([1, 2, 3, 6, 12, 40, 120, 496])
+        r = []
+        for _ in range(L):
+            u = rng.random()
+            r.append(0 if u < 0.2 else home if u < 0.6 else rng.choice(path) if u < 0.85 else rng.choice(ids))
+        recs.append(r)
+    recs.append([rng.choice(ids) for _ in range(3000)])      # beyond the shared-memory list
+    recs.append([rng.choice(ids[:40]) for _ in range(1500)])
+    total = 0
+    for strategy in (capi.AGG_LCA_STAR, capi.AGG_HYBRID, capi.AGG_MRTL):
+        for factor in ((0.25, 0.0, 0.5, 1.0, 0.66) if strategy == capi.AGG_HYBRID else (0.25,)):
+            for lb in (0.0, 1.0, 2.0, 5.0):
+                for ranked in (False, True):
+                    total += _check_agg(capi, world, recs, strategy, factor, lb, ranked)
+    assert total > 1000
+
+
+def test_aggregate_reference_fixture(capi):
+    # the 6-taxon tree of src/fixtures.rs:4-21 and the vectors of tree/lca.rs:51-77,
+    # tree/mix.rs:75-97, rmq/rtl.rs:69-92
+    taxa = [(1, "root", 0, 1, True), (2, "Bacteria", 1, 1, True), (10239, "Viruses", 1, 1, True),
+            (12884, "Viroids", 1, 1, True), (185751, "Pospiviroidae", 19, 12884, True),
+            (185752, "Avsunviroidae", 19, 12884, True)]
+    gtax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(taxa))
+
+    def run(ids, strategy, factor=0.25):
+        flat = np.array(ids, dtype=np.uint32)
+        return int(capi.aggregate(gtax, flat, np.array([0, len(ids)], dtype=np.uint64), strategy, factor)[0])
+
+    assert run([12884, 185751], capi.AGG_LCA_STAR) == 185751          # same path -> deeper
+    assert run([185751, 185752], capi.AGG_LCA_STAR) == 12884          # fork -> parent
+    assert run([12884, 185751, 185752], capi.AGG_LCA_STAR) == 12884
+    assert run([1, 185751, 185752, 2], capi.AGG_LCA_STAR) == 1
+    assert run([12884, 185751, 185751, 185752], capi.AGG_HYBRID, 0.0) == 185751
+    assert run([12884, 185751, 185751, 185752], capi.AGG_HYBRID, 1.0) == 12884
+    assert run([1, 12884, 12884, 185751, 2], capi.AGG_MRTL) == 185751
+    assert run([1, 1, 1, 185751, 1, 1], capi.AGG_MRTL) == 185751
+    assert run([], capi.AGG_MRTL) == 1
+    with pytest.raises(capi.UmgapError) as e:
+        run([5], capi.AGG_LCA_STAR)                                   # agg/mod.rs:104-118
+    assert "Unknown Taxon ID: 5" in str(e.value)
+
+
+@pytest.mark.parametrize("strategy,factor,lb,seed_opts", [
+    (0, 0.25, 0.0, (1, 2, 0)), (1, 0.25, 0.0, (1, 3, 0)), (2, 0.25, 1.0, (1, 2, 1)),
+    (1, 0.25, 1.0, (1, 3, 1)), (0, 0.25, 2.0, (1, 3, 1)), (2, 0.25, 5.0, (0, 0, 0)),
+    (1, 0.5, 0.0, (1, 4, 2)),
+])
+def test_classify_reads_matches_oracle_pipeline(capi, world, strategy, factor, lb, seed_opts):
+    use_se, s, g = seed_opts
+    reads = datagen.make_reads(world["proteins"], 120, seed=21 + strategy)
+    # ragged extras: short reads (dropped records), an N-rich read, a long read, a triple group
+    reads += [("s0/1", "ACGT"), ("s0/2", "ACGTACGTACGTACGTACGTACGTAC"), ("s1/1", "ACG" * 9), ("s1/2", "N" * 40),
+              ("e0/1", ""), ("e0/2", "")]
+    long_src = world["proteins"][3]
+    long_nt = "".join(datagen.CODONS.get(a, ["GCT"])[0] for a in long_src)
+    reads += [("L0/1", long_nt), ("L0/2", datagen.revcomp(long_nt))]
+    # six long reads joined into one group: more kept ids than the shared-memory list holds
+    reads += [(f"M0/{i}", long_nt if i % 2 else datagen.revcomp(long_nt)) for i in range(1, 7)]
+    oidx = olookup.DictIndex(world["index"])
+    want = opipe.classify_reads(reads, oidx, world["otax"], use_seedextend=bool(use_se), min_seed_size=s,
+                                max_gap_size=g, strategy=strategy, factor=factor, lower_bound=lb)
+    want = dict(want)
+    # groups exactly as `uniq -d /` would form them from the headers
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    heads = [h.split("/")[0] for h, _ in reads]
+    goff = [0]
+    for i in range(1, len(reads) + 1):
+        if i == len(reads) or heads[i] != heads[i - 1]:
+            goff.append(i)
+    opts = capi.default_opts(seedextend=use_se, min_seed_size=s, max_gap_size=g, strategy=strategy,
+                             factor=factor, lower_bound=lb)
+    got, nlook = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, np.array(goff, dtype=np.uint64))
+    assert nlook == sum(2 * (len(r[1]) - 26) for r in reads if len(r[1]) >= 27)
+    non_root = 0
+    for gi in range(len(goff) - 1):
+        h = heads[goff[gi]]
+        if h not in want:
+            assert int(got[gi]) == capi.ABSENT, h
+            continue
+        assert int(got[gi]) in want[h], (h, int(got[gi]), want[h])
+        non_root += int(got[gi]) != 1
+    assert non_root > 40
+    assert "e0" not in want and "s0" not in want and "s1" in want and "L0" in want and "M0" in want
+
+
+def test_classify_dev_entry_matches_host_entry(capi, world):
+    torch = pytest.importorskip("torch")
+    reads = datagen.make_reads(world["proteins"], 300, seed=33)
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
+    opts = capi.default_opts(min_seed_size=3, strategy=capi.AGG_HYBRID)
+    host, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, goff)
+    d_nt = torch.from_numpy(nt).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_goff = torch.from_numpy(goff.astype(np.int64)).cuda()
+    d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
+    capi.classify_reads_dev(world["gidx"], world["gtax"], opts, d_nt.data_ptr(), d_off.data_ptr(), len(reads),
+                            int(off[-1]), d_goff.data_ptr(), len(goff) - 1, d_out.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), host)

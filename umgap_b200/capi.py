@@ -1,0 +1,351 @@
+"""ctypes binding of ``libumgap_gpu.so`` (the C ABI declared in ``include/umgap_gpu.h``).
+
+This is the thin host-side mirror the tests and ``bench.py`` use; it holds no algorithm.  Every
+compute call goes to the CUDA library and raises :class:`UmgapError` when the library reports a
+failure -- there is no CPU fallback here or anywhere else in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libumgap_gpu.so")
+
+MISS = 0xFFFFFFFF
+ABSENT = 0xFFFFFFFF
+AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
+
+# every symbol include/umgap_gpu.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "umgap_last_error", "umgap_abi_version", "umgap_device_count",
+    "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
+    "umgap_taxonomy_load", "umgap_taxonomy_from_arrays", "umgap_taxonomy_free",
+    "umgap_taxonomy_get_info",
+    "umgap_translate_bound", "umgap_translate",
+    "umgap_kmer_lookup_bound", "umgap_kmer_lookup",
+    "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
+    "umgap_seedextend", "umgap_aggregate",
+    "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
+    "umgap_translate_lookup_dev",
+    "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
+]
+
+
+class UmgapError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("n_keys", C.c_uint64), ("n_buckets", C.c_uint64), ("bytes", C.c_uint64),
+                ("n_skipped", C.c_uint64), ("n_flagged", C.c_uint64), ("n_displaced", C.c_uint64),
+                ("max_probe", C.c_uint64), ("k", C.c_int), ("device", C.c_int),
+                ("alphabet_size", C.c_int)]
+
+
+class TaxonomyInfo(C.Structure):
+    _fields_ = [("n_taxa", C.c_uint64), ("max_id", C.c_uint64), ("root", C.c_uint64),
+                ("max_depth", C.c_uint32), ("device", C.c_int)]
+
+
+class PipelineOpts(C.Structure):
+    _fields_ = [("table", C.c_int), ("methionine", C.c_int), ("one_on_one", C.c_int),
+                ("seedextend", C.c_int), ("min_seed_size", C.c_int), ("max_gap_size", C.c_int),
+                ("strategy", C.c_int), ("factor", C.c_float), ("lower_bound", C.c_float),
+                ("ranked_only", C.c_int)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_proteins", C.c_uint64), ("protein_len", C.c_uint32),
+                ("home_pct", C.c_uint32), ("ancestor_pct", C.c_uint32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UmgapError(-3, f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); "
+                             "umgap_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.umgap_last_error.restype = C.c_char_p
+    lib.umgap_translate_bound.restype = C.c_uint64
+    lib.umgap_translate_bound.argtypes = [C.c_uint64, C.c_uint64, C.c_uint8]
+    lib.umgap_kmer_lookup_bound.restype = C.c_uint64
+    lib.umgap_kmer_lookup_bound.argtypes = [C.c_uint64, C.c_uint64]
+    lib.umgap_tryp_lookup_bound.restype = C.c_uint64
+    lib.umgap_tryp_lookup_bound.argtypes = [C.c_uint64, C.c_uint64]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise UmgapError(rc, load_library().umgap_last_error().decode("utf-8", "replace"))
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(x, dtype) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def device_count() -> int:
+    return load_library().umgap_device_count()
+
+
+class Taxonomy:
+    """GPU-resident taxonomy (taxon.rs TaxonList/TaxonTree + snapping)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_arrays(cls, ids, parents, ranks, valid, device: int = 0) -> "Taxonomy":
+        ids = _arr(ids, np.uint64)
+        parents = _arr(parents, np.uint64)
+        ranks = _arr(ranks, np.uint8)
+        valid = _arr(valid, np.uint8)
+        h = C.c_void_p()
+        _check(load_library().umgap_taxonomy_from_arrays(_p(ids), _p(parents), _p(ranks), _p(valid),
+                                                         C.c_uint64(len(ids)), C.c_int(device),
+                                                         C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "Taxonomy":
+        h = C.c_void_p()
+        _check(load_library().umgap_taxonomy_load(path.encode(), C.c_int(device), C.byref(h)))
+        return cls(h)
+
+    def info(self) -> TaxonomyInfo:
+        i = TaxonomyInfo()
+        _check(load_library().umgap_taxonomy_get_info(self._h, C.byref(i)))
+        return i
+
+    def close(self):
+        if self._h:
+            load_library().umgap_taxonomy_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    """GPU-resident key -> taxon table (fst::Map replacement)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_pairs(cls, keys: Sequence[bytes], values, k: int = 9, device: int = 0,
+                   load_factor: float = 0.0) -> "Index":
+        lens = np.fromiter((len(x) for x in keys), dtype=np.uint64, count=len(keys))
+        off = np.zeros(len(keys) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        blob = np.frombuffer(b"".join(keys) or b"\0", dtype=np.uint8)
+        return cls.from_blob(blob, off, values, k, device, load_factor)
+
+    @classmethod
+    def from_blob(cls, blob: np.ndarray, off: Optional[np.ndarray], values, k: int = 9,
+                  device: int = 0, load_factor: float = 0.0) -> "Index":
+        blob = _arr(blob, np.uint8)
+        values = _arr(values, np.uint64)
+        off = None if off is None else _arr(off, np.uint64)
+        h = C.c_void_p()
+        _check(load_library().umgap_index_from_pairs(_p(blob), _p(off), _p(values),
+                                                     C.c_uint64(len(values)), C.c_int(k),
+                                                     C.c_int(device), C.c_double(load_factor),
+                                                     C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load_fst(cls, path: str, k: int = 9, device: int = 0, load_factor: float = 0.0) -> "Index":
+        h = C.c_void_p()
+        _check(load_library().umgap_index_load_fst(path.encode(), C.c_int(k), C.c_int(device),
+                                                   C.c_double(load_factor), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_synthetic(cls, spec: SynthSpec, tax: Taxonomy, device: int = 0,
+                        load_factor: float = 0.0) -> "Index":
+        h = C.c_void_p()
+        _check(load_library().umgap_index_build_synthetic(C.byref(spec), tax._h, C.c_int(device),
+                                                          C.c_double(load_factor), C.byref(h)))
+        return cls(h)
+
+    def info(self) -> IndexInfo:
+        i = IndexInfo()
+        _check(load_library().umgap_index_get_info(self._h, C.byref(i)))
+        return i
+
+    def randsector_rate(self, n_gathers: int, iters: int = 5) -> float:
+        r = C.c_double()
+        _check(load_library().umgap_randsector_bench(self._h, C.c_uint64(n_gathers), C.c_int(iters),
+                                                     C.byref(r)))
+        return r.value
+
+    def close(self):
+        if self._h:
+            load_library().umgap_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_opts(**kw) -> PipelineOpts:
+    o = PipelineOpts()
+    load_library().umgap_pipeline_opts_default(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _offsets(lengths) -> np.ndarray:
+    off = np.zeros(len(lengths) + 1, dtype=np.uint64)
+    np.cumsum(np.asarray(lengths, dtype=np.uint64), out=off[1:])
+    return off
+
+
+def pack_strings(items: Sequence[bytes]):
+    """Concatenates byte strings -> (uint8 blob, uint64 offsets)."""
+    off = _offsets([len(x) for x in items])
+    blob = np.frombuffer(b"".join(items) or b"\0", dtype=np.uint8).copy()
+    return blob, off
+
+
+def translate(nt: np.ndarray, read_off: np.ndarray, table: int = 1, methionine: bool = False,
+              frames_mask: int = 0x3F, device: int = 0):
+    """umgap_translate: returns (aa blob, aa offsets) with one peptide per (read, frame)."""
+    lib = load_library()
+    nt = _arr(nt, np.uint8)
+    read_off = _arr(read_off, np.uint64)
+    nreads = len(read_off) - 1
+    nframes = bin(frames_mask & 0x3F).count("1")
+    bound = lib.umgap_translate_bound(C.c_uint64(int(read_off[-1])), C.c_uint64(nreads),
+                                      C.c_uint8(frames_mask))
+    aa = np.zeros(max(int(bound), 1), dtype=np.uint8)
+    aa_off = np.zeros(nreads * nframes + 1, dtype=np.uint64)
+    _check(lib.umgap_translate(C.c_int(device), _p(nt), _p(read_off), C.c_uint64(nreads),
+                               C.c_int(table), C.c_int(int(methionine)), C.c_uint8(frames_mask),
+                               _p(aa), _p(aa_off)))
+    return aa[: int(aa_off[-1])], aa_off
+
+
+def kmer_lookup(index: Index, aa: np.ndarray, pep_off: np.ndarray, one_on_one: bool):
+    """umgap_kmer_lookup: returns (taxa, taxa offsets, kept flags)."""
+    lib = load_library()
+    aa = _arr(aa, np.uint8)
+    pep_off = _arr(pep_off, np.uint64)
+    npeps = len(pep_off) - 1
+    bound = lib.umgap_kmer_lookup_bound(C.c_uint64(int(pep_off[-1])), C.c_uint64(npeps))
+    taxa = np.zeros(max(int(bound), 1), dtype=np.uint32)
+    taxa_off = np.zeros(npeps + 1, dtype=np.uint64)
+    kept = np.zeros(max(npeps, 1), dtype=np.uint8)
+    _check(lib.umgap_kmer_lookup(index._h, _p(aa), _p(pep_off), C.c_uint64(npeps),
+                                 C.c_int(int(one_on_one)), _p(taxa), _p(taxa_off), _p(kept)))
+    return taxa[: int(taxa_off[-1])], taxa_off, kept[:npeps]
+
+
+def tryp_lookup(index: Index, aa: np.ndarray, line_off: np.ndarray, minlen: int = 5,
+                maxlen: int = 50, keep: str = "", drop: str = "", one_on_one: bool = False):
+    lib = load_library()
+    aa = _arr(aa, np.uint8)
+    line_off = _arr(line_off, np.uint64)
+    nlines = len(line_off) - 1
+    bound = lib.umgap_tryp_lookup_bound(C.c_uint64(int(line_off[-1])), C.c_uint64(nlines))
+    taxa = np.zeros(max(int(bound), 1), dtype=np.uint32)
+    taxa_off = np.zeros(nlines + 1, dtype=np.uint64)
+    _check(lib.umgap_tryp_lookup(index._h, _p(aa), _p(line_off), C.c_uint64(nlines),
+                                 C.c_int(minlen), C.c_int(maxlen), keep.encode(), drop.encode(),
+                                 C.c_int(int(one_on_one)), _p(taxa), _p(taxa_off)))
+    return taxa[: int(taxa_off[-1])], taxa_off
+
+
+def seedextend(taxa: np.ndarray, rec_off: np.ndarray, min_seed_size: int = 2,
+               max_gap_size: int = 0, device: int = 0):
+    lib = load_library()
+    taxa = _arr(taxa, np.uint32)
+    rec_off = _arr(rec_off, np.uint64)
+    nrecs = len(rec_off) - 1
+    out = np.zeros(max(len(taxa), 1), dtype=np.uint32)
+    out_off = np.zeros(nrecs + 1, dtype=np.uint64)
+    _check(lib.umgap_seedextend(C.c_int(device), _p(taxa), _p(rec_off), C.c_uint64(nrecs),
+                                C.c_int(min_seed_size), C.c_int(max_gap_size), _p(out),
+                                _p(out_off)))
+    return out[: int(out_off[-1])], out_off
+
+
+def aggregate(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, strategy: int,
+              factor: float = 0.25, lower_bound: float = 0.0, ranked_only: bool = False):
+    lib = load_library()
+    taxa = _arr(taxa, np.uint32)
+    rec_off = _arr(rec_off, np.uint64)
+    nrecs = len(rec_off) - 1
+    out = np.zeros(max(nrecs, 1), dtype=np.uint32)
+    _check(lib.umgap_aggregate(tax._h, _p(taxa), _p(rec_off), C.c_uint64(nrecs), C.c_int(strategy),
+                               C.c_float(factor), C.c_float(lower_bound),
+                               C.c_int(int(ranked_only)), _p(out)))
+    return out[:nrecs]
+
+
+def classify_reads(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarray,
+                   read_off: np.ndarray, group_off: np.ndarray):
+    """umgap_classify_reads (host buffers): returns (taxon per group, number of lookups)."""
+    lib = load_library()
+    nt = _arr(nt, np.uint8)
+    read_off = _arr(read_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    nl = C.c_uint64()
+    _check(lib.umgap_classify_reads(index._h, tax._h, C.byref(opts), _p(nt), _p(read_off),
+                                    C.c_uint64(len(read_off) - 1), _p(group_off),
+                                    C.c_uint64(ngroups), _p(out), C.byref(nl)))
+    return out[:ngroups], nl.value
+
+
+def classify_reads_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, nt_ptr: int,
+                       read_off_ptr: int, nreads: int, total_nt: int, group_off_ptr: int,
+                       ngroups: int, out_ptr: int, stream: int = 0) -> None:
+    """Device-resident variant; pointers are raw device addresses (e.g. torch .data_ptr())."""
+    _check(load_library().umgap_classify_reads_dev(
+        index._h, tax._h, C.byref(opts), C.c_void_p(nt_ptr), C.c_void_p(read_off_ptr),
+        C.c_uint64(nreads), C.c_uint64(total_nt), C.c_void_p(group_off_ptr), C.c_uint64(ngroups),
+        C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def translate_lookup_dev(index: Index, opts: PipelineOpts, nt_ptr: int, read_off_ptr: int,
+                         nreads: int, total_nt: int, ids_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_translate_lookup_dev(
+        index._h, C.byref(opts), C.c_void_p(nt_ptr), C.c_void_p(read_off_ptr), C.c_uint64(nreads),
+        C.c_uint64(total_nt), C.c_void_p(ids_ptr), C.c_void_p(stream)))
+
+
+def synth_reads_dev(spec: SynthSpec, read_seed: int, first_pair: int, npairs: int, read_len: int,
+                    hit_pct: int, nt_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_synth_reads_dev(
+        C.byref(spec), C.c_uint64(read_seed), C.c_uint64(first_pair), C.c_uint64(npairs),
+        C.c_uint32(read_len), C.c_uint32(hit_pct), C.c_void_p(nt_ptr), C.c_void_p(stream)))

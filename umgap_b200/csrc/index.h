@@ -1,0 +1,100 @@
+// Host-side handles behind the opaque C types of include/umgap_gpu.h.
+#pragma once
+#include "common.h"
+#include "table.cuh"
+
+namespace umgap {
+
+// Device view of the taxonomy.  Taxa are renumbered in PREORDER ("dense" index): the subtree
+// of x is the contiguous index range [x, last[x]], so "a is an ancestor-or-self of b" is
+// a <= b <= last[a], the induced tree of a sorted taxon list is laid out in DFS order, and the
+// LCA of a set is the LCA of its smallest and largest member.  anc[x*stride + d] is the
+// ancestor of x at depth d (root = depth 0, x itself at depth[x]); replaces the parent walks of
+// tree/mod.rs:29-48 and rmq/rtl.rs:41-50.
+struct TaxView {
+    const uint32_t* dense_of;    // taxon id -> dense index, kNoTaxon when unknown   [max_id+1]
+    const uint32_t* id_of;       // dense -> taxon id                                [n]
+    const uint32_t* last;        // dense -> last dense index of its subtree         [n]
+    const uint32_t* parent;      // dense -> dense parent (root: itself)             [n]
+    const uint8_t* depth;        // dense -> depth                                   [n]
+    const uint32_t* anc;         // ancestor matrix                                  [n*stride]
+    const uint32_t* snap_valid;  // dense -> taxon id after snapping (taxon.rs:294-301)
+    const uint32_t* snap_ranked; // same with ranked_only
+    uint32_t n;
+    uint32_t max_id;
+    uint32_t stride;             // max_depth+1 rounded up to a multiple of 8
+};
+constexpr uint32_t kNoTaxon = 0xFFFFFFFFu;
+
+}  // namespace umgap
+
+struct umgap_taxonomy {
+    int device = 0;
+    umgap::TaxView view{};
+    std::vector<void*> dev_allocs;
+    // host copies (error reporting, synthetic generators, tests)
+    std::vector<uint64_t> ids, parents;  // as given
+    std::vector<uint32_t> h_dense_of, h_id_of, h_parent;
+    std::vector<uint8_t> h_depth;
+    uint64_t root = 0, max_id = 0;
+    uint32_t max_depth = 0;
+};
+
+struct umgap_index {
+    int device = 0;
+    int k = 9;  // 0: variable-length (tryptic) table
+    int nlevels = 0;
+    uint64_t* level_dev[umgap::kMaxLevels] = {};
+    uint64_t level_nb[umgap::kMaxLevels] = {};
+    uint8_t code_of_byte[256];  // 0xFF = byte not in the index alphabet
+    int alphabet_size = 0;
+    uint64_t n_keys = 0, n_skipped = 0, n_flagged = 0, n_displaced = 0, max_probe = 0;
+    uint64_t bytes = 0;
+    // variable-length table (k == 0), see tryptic.cu
+    void* var_table = nullptr;
+    mutable umgap::Workspace ws;
+
+    umgap::TableView view() const {
+        umgap::TableView v{};
+        for (int i = 0; i < nlevels; ++i) {
+            v.level[i] = reinterpret_cast<const ulonglong4*>(level_dev[i]);
+            v.nb[i] = level_nb[i];
+        }
+        v.nlevels = nlevels;
+        v.k = k;
+        return v;
+    }
+};
+
+namespace umgap {
+
+// Incremental builder used by the FST loader, from_pairs and the synthetic generator.
+struct TableBuilder {
+    umgap_index* idx = nullptr;
+    uint64_t expected = 0;
+    uint64_t* ovf_keys = nullptr;  // device
+    uint32_t* ovf_vals = nullptr;
+    unsigned long long* counters = nullptr;  // device: [0] overflow count, [1] dups, [2] displaced,
+                                             // [3] max probe, [4] inserted
+    uint64_t ovf_cap = 0;
+    const TaxView* lca_view = nullptr;  // non-null: duplicate keys combine by LCA of the values
+
+    void begin(umgap_index* idx, uint64_t expected_keys, double load_factor);
+    // keys: packed 45-bit keys on the device; vals on the device
+    void insert_dev(const uint64_t* keys_dev, const uint32_t* vals_dev, uint64_t n,
+                    cudaStream_t stream = nullptr);
+    void finish();  // builds the overflow levels, fills stats; throws on duplicates unless LCA mode
+    void abort();
+    // byte -> code for the index alphabet, assigning a new code on first sight
+    int code_for(uint8_t byte);
+};
+
+// FST v2 stream reader (fst_stream.cpp): calls `sink(key, len, value)` for every key in order.
+struct FstSink {
+    virtual void on_key(const uint8_t* key, size_t len, uint64_t value) = 0;
+    virtual ~FstSink() {}
+};
+void fst_stream_file(const char* path, FstSink& sink, uint64_t* n_keys_footer);
+uint64_t fst_file_len(const char* path);  // number of keys recorded in the footer
+
+}  // namespace umgap

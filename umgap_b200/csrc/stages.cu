@@ -1,0 +1,327 @@
+// Per-command entry points: one reference command loop each, host buffers in and out.
+//   umgap_translate    translate.rs:114-133       umgap_kmer_lookup  prot2kmer2lca.rs:168-185
+//   umgap_seedextend   seedextend.rs:92-176       umgap_aggregate    taxa2agg.rs:159-181
+#include <algorithm>
+
+#include "index.h"
+#include "warp_agg.cuh"
+
+namespace umgap {
+
+struct AsciiLut {
+    uint8_t v[72];
+};
+void make_ascii_lut_public(int table, int methionine, uint8_t* out65);  // pipeline.cu
+
+__device__ __forceinline__ uint32_t nt_code2(uint8_t c) {
+    return c == 'T' ? 0u : c == 'C' ? 1u : c == 'A' ? 2u : c == 'G' ? 3u : 4u;
+}
+
+// One warp per read; every lane translates whole codons of the selected frames.  Peptide j of
+// read r starts at aa_off[r*nframes + j] (offsets are computed on the host from the read
+// lengths: frame f of an n-nt read has max(n-f,0)/3 residues).
+__global__ void __launch_bounds__(256)
+translate_kernel(AsciiLut lut, const uint8_t* __restrict__ nt, const uint64_t* __restrict__ read_off,
+                 uint64_t nreads, uint32_t frames_mask, int nframes,
+                 const uint64_t* __restrict__ aa_off, uint8_t* __restrict__ aa) {
+    __shared__ uint8_t s_lut[72];
+    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < nreads; r += nwarps) {
+        const uint64_t off = read_off[r];
+        const uint32_t n = (uint32_t)(read_off[r + 1] - off);
+        int slot = 0;
+        for (int fr = 0; fr < 6; ++fr) {
+            if (!(frames_mask >> fr & 1)) continue;
+            const uint32_t f = fr % 3;
+            const bool rev = fr >= 3;
+            const uint32_t plen = n >= f ? (n - f) / 3 : 0;
+            uint8_t* out = aa + aa_off[r * nframes + slot];
+            ++slot;
+            for (uint32_t j = lane; j < plen; j += 32) {
+                uint32_t a, b, c;
+                if (!rev) {
+                    const uint8_t* p = nt + off + f + 3 * j;
+                    a = nt_code2(p[0]);
+                    b = nt_code2(p[1]);
+                    c = nt_code2(p[2]);
+                } else {  // reverse strand position i is the complement of forward n-1-i
+                    const uint8_t* p = nt + off + (n - 1 - f - 3 * j);
+                    a = nt_code2(p[0]);
+                    b = nt_code2(*(p - 1));
+                    c = nt_code2(*(p - 2));
+                    if (!((a | b | c) & 4u)) {
+                        a ^= 2u;
+                        b ^= 2u;
+                        c ^= 2u;
+                    }
+                }
+                out[j] = s_lut[((a | b | c) & 4u) ? 64 : 16 * a + 4 * b + c];
+            }
+        }
+    }
+}
+
+// One warp per peptide; lanes stride the k-mer start positions.  out has one entry per
+// position (UMGAP_MISS for a miss); the host applies -o / compaction.
+__global__ void __launch_bounds__(256)
+kmer_lookup_kernel(TableView t, const uint8_t* __restrict__ code_of_byte,
+                   const uint8_t* __restrict__ aa, const uint64_t* __restrict__ pep_off,
+                   uint64_t npeps, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out) {
+    __shared__ uint8_t s_code[256];
+    s_code[threadIdx.x & 255] = code_of_byte[threadIdx.x & 255];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int k = t.k;
+    for (uint64_t p = warp; p < npeps; p += nwarps) {
+        const uint64_t off = pep_off[p];
+        const uint64_t len = pep_off[p + 1] - off;
+        if (len < (uint64_t)k) continue;
+        const uint64_t cnt = len - k + 1;
+        uint32_t* o = out + out_off[p];
+        for (uint64_t i = lane; i < cnt; i += 32) {
+            uint64_t key = 0;
+            uint32_t bad = 0;
+            for (int j = 0; j < k; ++j) {
+                const uint32_t c = s_code[aa[off + i + j]];
+                bad |= c;
+                key = (key << 5) | (c & 31u);
+            }
+            o[i] = table_lookup(t, (bad & 0x80u) ? kInvalidKey : key);
+        }
+    }
+}
+
+// One lane per record.
+__global__ void __launch_bounds__(128)
+seedextend_kernel(const uint32_t* __restrict__ taxa, const uint64_t* __restrict__ rec_off,
+                  uint64_t nrecs, uint32_t min_seed, uint32_t max_gap, uint32_t* __restrict__ out,
+                  uint32_t* __restrict__ out_len) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrecs; r += stride) {
+        const uint64_t off = rec_off[r];
+        const uint32_t cnt = (uint32_t)(rec_off[r + 1] - off);
+        uint32_t* o = out + off;
+        uint32_t m = 0;
+        seedextend_stream(taxa + off, 1, cnt, true, min_seed, max_gap,
+                          [&](uint32_t v) { o[m++] = v; });
+        out_len[r] = m;
+    }
+}
+
+constexpr int kStageAggWarps = 4;
+constexpr uint32_t kStageAggCap = 512;
+
+// One warp per record; small records aggregate in shared memory, larger ones in their slice of
+// a global scratch buffer (3 words per input id).
+__global__ void __launch_bounds__(kStageAggWarps * 32)
+aggregate_kernel(TaxView tv, AggParams ap, const uint32_t* __restrict__ taxa,
+                 const uint64_t* __restrict__ rec_off, uint64_t nrecs, uint32_t* __restrict__ scratch,
+                 uint32_t* __restrict__ out, unsigned int* err) {
+    __shared__ uint32_t s_a[kStageAggWarps][kStageAggCap];
+    __shared__ uint32_t s_p[kStageAggWarps][kStageAggCap + 1];
+    __shared__ uint32_t s_l[kStageAggWarps][kStageAggCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kStageAggWarps;
+    for (uint64_t r = (uint64_t)blockIdx.x * kStageAggWarps + warp; r < nrecs; r += nwarps) {
+        const uint64_t off = rec_off[r];
+        const uint64_t cnt = rec_off[r + 1] - off;
+        uint32_t *A, *P, *L;
+        if (cnt <= kStageAggCap) {
+            A = s_a[warp];
+            P = s_p[warp];
+            L = s_l[warp];
+        } else {  // slice [3*off + r, 3*(off+cnt) + r + 1): cnt + (cnt+1) + cnt words
+            A = scratch + 3 * off + r;
+            P = A + cnt;
+            L = P + cnt + 1;
+        }
+        // drop zeros (taxa2agg.rs:169), order is irrelevant to the aggregators
+        uint32_t n = 0;
+        for (uint64_t base = 0; base < cnt; base += 32) {
+            const uint64_t i = base + lane;
+            const uint32_t v = i < cnt ? taxa[off + i] : 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+            if (v != 0) A[n + __popc(m & ((1u << lane) - 1))] = v;
+            n += __popc(m);
+        }
+        __syncwarp();
+        uint32_t bad = 0;
+        uint32_t res = warp_aggregate(tv, A, P, L, n, ap, lane, &bad);
+        bad = __reduce_max_sync(0xffffffffu, bad);
+        if (res == kAggUnknown) {
+            if (lane == 0 && atomicCAS(&err[0], 0u, 1u) == 0u) err[1] = bad;
+            res = UMGAP_ABSENT;
+        }
+        if (lane == 0) out[r] = res;
+        __syncwarp();
+    }
+}
+
+static unsigned grid_for(uint64_t items, unsigned per_block, unsigned max_blocks = 148u * 32) {
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ceil_div(items, per_block), max_blocks));
+}
+
+}  // namespace umgap
+
+using namespace umgap;
+
+extern "C" {
+
+uint64_t umgap_translate_bound(uint64_t total_nt, uint64_t nreads, uint8_t frames_mask) {
+    (void)nreads;
+    return ceil_div(total_nt, 3) * (uint64_t)__builtin_popcount(frames_mask & 0x3F) + 1;
+}
+
+int umgap_translate(int device, const uint8_t* nt, const uint64_t* read_off, uint64_t nreads,
+                    int table, int methionine, uint8_t frames_mask, uint8_t* aa_out,
+                    uint64_t* aa_off) {
+    return guarded([&] {
+        if (!read_off || !aa_off || (nreads && (!nt || !aa_out))) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        AsciiLut lut{};
+        make_ascii_lut_public(table, methionine, lut.v);
+        frames_mask &= 0x3F;
+        const int nframes = __builtin_popcount(frames_mask);
+        uint64_t o = 0;
+        for (uint64_t r = 0; r < nreads; ++r) {
+            const uint64_t n = read_off[r + 1] - read_off[r];
+            int slot = 0;
+            for (int fr = 0; fr < 6; ++fr) {
+                if (!(frames_mask >> fr & 1)) continue;
+                const uint64_t f = fr % 3;
+                aa_off[r * nframes + slot++] = o;
+                o += n >= f ? (n - f) / 3 : 0;
+            }
+        }
+        aa_off[nreads * nframes] = o;
+        if (!nreads || !nframes || !o) return;
+        use_device(device);
+        const uint64_t total_nt = read_off[nreads];
+        DevBuf<uint8_t> d_nt(total_nt + 1), d_aa(o);
+        DevBuf<uint64_t> d_roff(nreads + 1), d_aoff(nreads * nframes + 1);
+        UMGAP_CUDA(cudaMemcpy(d_nt.p, nt, total_nt, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_roff.p, read_off, (nreads + 1) * 8, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_aoff.p, aa_off, (nreads * nframes + 1) * 8, cudaMemcpyHostToDevice));
+        translate_kernel<<<grid_for(nreads, 8), 256>>>(lut, d_nt.p, d_roff.p, nreads, frames_mask,
+                                                       nframes, d_aoff.p, d_aa.p);
+        UMGAP_CUDA(cudaGetLastError());
+        UMGAP_CUDA(cudaMemcpy(aa_out, d_aa.p, o, cudaMemcpyDeviceToHost));
+    });
+}
+
+uint64_t umgap_kmer_lookup_bound(uint64_t total_aa, uint64_t npeps) {
+    (void)npeps;
+    return total_aa + 1;
+}
+
+int umgap_kmer_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t* pep_off,
+                      uint64_t npeps, int one_on_one, uint32_t* taxa_out, uint64_t* taxa_off,
+                      uint8_t* kept) {
+    return guarded([&] {
+        if (!idx || !pep_off || !taxa_off || (npeps && (!aa || !taxa_out)))
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->k <= 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "index is not a fixed-length k-mer table");
+        const uint64_t k = idx->k;
+        uint64_t o = 0;
+        for (uint64_t p = 0; p < npeps; ++p) {
+            const uint64_t len = pep_off[p + 1] - pep_off[p];
+            taxa_off[p] = o;
+            const bool keep = len >= k;  // prot2kmer2lca.rs:172
+            if (kept) kept[p] = keep;
+            if (keep) o += len - k + 1;
+        }
+        taxa_off[npeps] = o;
+        if (!o) return;
+        use_device(idx->device);
+        const uint64_t total_aa = pep_off[npeps];
+        DevBuf<uint8_t> d_aa(total_aa + 1), d_code(256);
+        DevBuf<uint64_t> d_poff(npeps + 1), d_ooff(npeps + 1);
+        DevBuf<uint32_t> d_out(o);
+        UMGAP_CUDA(cudaMemcpy(d_aa.p, aa, total_aa, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_code.p, idx->code_of_byte, 256, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_poff.p, pep_off, (npeps + 1) * 8, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_ooff.p, taxa_off, (npeps + 1) * 8, cudaMemcpyHostToDevice));
+        kmer_lookup_kernel<<<grid_for(npeps, 8), 256>>>(idx->view(), d_code.p, d_aa.p, d_poff.p, npeps,
+                                                        d_ooff.p, d_out.p);
+        UMGAP_CUDA(cudaGetLastError());
+        UMGAP_CUDA(cudaMemcpy(taxa_out, d_out.p, o * 4, cudaMemcpyDeviceToHost));
+        if (one_on_one) {  // miss -> 0 (prot2kmer2lca.rs:115)
+            for (uint64_t i = 0; i < o; ++i)
+                if (taxa_out[i] == UMGAP_MISS) taxa_out[i] = 0;
+        } else {  // miss -> omitted (:176)
+            uint64_t w = 0;
+            for (uint64_t p = 0; p < npeps; ++p) {
+                const uint64_t b = taxa_off[p], e = taxa_off[p + 1];
+                taxa_off[p] = w;
+                for (uint64_t i = b; i < e; ++i)
+                    if (taxa_out[i] != UMGAP_MISS) taxa_out[w++] = taxa_out[i];
+            }
+            taxa_off[npeps] = w;
+        }
+    });
+}
+
+int umgap_seedextend(int device, const uint32_t* taxa, const uint64_t* rec_off, uint64_t nrecs,
+                     int min_seed_size, int max_gap_size, uint32_t* out, uint64_t* out_off) {
+    return guarded([&] {
+        if (!rec_off || !out_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (min_seed_size < 0 || max_gap_size < 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "negative size");
+        const uint64_t total = rec_off[nrecs];
+        for (uint64_t i = 0; i <= nrecs; ++i) out_off[i] = 0;
+        if (!nrecs) return;
+        if (total && (!taxa || !out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(device);
+        DevBuf<uint32_t> d_in(total + 1), d_out(total + 1), d_len(nrecs);
+        DevBuf<uint64_t> d_off(nrecs + 1);
+        if (total) UMGAP_CUDA(cudaMemcpy(d_in.p, taxa, total * 4, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_off.p, rec_off, (nrecs + 1) * 8, cudaMemcpyHostToDevice));
+        seedextend_kernel<<<grid_for(nrecs, 128), 128>>>(d_in.p, d_off.p, nrecs, (uint32_t)min_seed_size,
+                                                         (uint32_t)max_gap_size, d_out.p, d_len.p);
+        UMGAP_CUDA(cudaGetLastError());
+        std::vector<uint32_t> len(nrecs), tmp(total + 1);
+        UMGAP_CUDA(cudaMemcpy(len.data(), d_len.p, nrecs * 4, cudaMemcpyDeviceToHost));
+        if (total) UMGAP_CUDA(cudaMemcpy(tmp.data(), d_out.p, total * 4, cudaMemcpyDeviceToHost));
+        uint64_t w = 0;
+        for (uint64_t r = 0; r < nrecs; ++r) {
+            out_off[r] = w;
+            memcpy(out + w, tmp.data() + rec_off[r], (size_t)len[r] * 4);
+            w += len[r];
+        }
+        out_off[nrecs] = w;
+    });
+}
+
+int umgap_aggregate(const umgap_taxonomy* tax, const uint32_t* taxa, const uint64_t* rec_off,
+                    uint64_t nrecs, int strategy, float factor, float lower_bound, int ranked_only,
+                    uint32_t* taxon_out) {
+    return guarded([&] {
+        if (!tax || !rec_off || (nrecs && !taxon_out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (strategy < UMGAP_AGG_LCA_STAR || strategy > UMGAP_AGG_MRTL)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", strategy);
+        if (!nrecs) return;
+        const uint64_t total = rec_off[nrecs];
+        if (total && !taxa) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(tax->device);
+        DevBuf<uint32_t> d_in(total + 1), d_scratch(3 * total + nrecs + 8), d_out(nrecs);
+        DevBuf<uint64_t> d_off(nrecs + 1);
+        DevBuf<unsigned int> d_err(2);
+        if (total) UMGAP_CUDA(cudaMemcpy(d_in.p, taxa, total * 4, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_off.p, rec_off, (nrecs + 1) * 8, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemset(d_err.p, 0, 8));
+        AggParams ap{strategy, factor, lower_bound, ranked_only};
+        aggregate_kernel<<<grid_for(nrecs, kStageAggWarps), kStageAggWarps * 32>>>(
+            tax->view, ap, d_in.p, d_off.p, nrecs, d_scratch.p, d_out.p, d_err.p);
+        UMGAP_CUDA(cudaGetLastError());
+        unsigned int he[2];
+        UMGAP_CUDA(cudaMemcpy(he, d_err.p, 8, cudaMemcpyDeviceToHost));
+        UMGAP_CUDA(cudaMemcpy(taxon_out, d_out.p, nrecs * 4, cudaMemcpyDeviceToHost));
+        if (he[0]) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", he[1]);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// Construction of the device k-mer table (see table.cuh for the layout) and the random-sector
+// gather microbenchmark that measures the roofline denominator on the table's own memory.
+#include <algorithm>
+
+#include "index.h"
+#include "taxdev.cuh"
+
+namespace umgap {
+
+enum { C_OVF = 0, C_DUP = 1, C_DISPLACED = 2, C_MAXPROBE = 3, C_INSERTED = 4, C_BADVAL = 5, C_N = 8 };
+
+__global__ void fill_empty_kernel(ulonglong2* p, uint64_t n16) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        p[i] = make_ulonglong2(kEmptySlot, kEmptySlot);
+}
+
+// One thread per key.  Slots are claimed with 64-bit CAS in slot order, so two threads carrying
+// the same key always meet in the same slot (duplicates are detected, never stored twice).
+template <bool LCA>
+__global__ void insert_kernel(uint64_t* __restrict__ buckets, uint64_t nb,
+                              const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                              uint64_t n, int level, uint64_t* __restrict__ ovf_keys,
+                              uint32_t* __restrict__ ovf_vals, uint64_t ovf_cap,
+                              unsigned long long* __restrict__ counters, TaxView tv) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        const uint32_t val = vals[i];
+        if (key == kInvalidKey) continue;
+        if (val == kNoValue) {
+            atomicAdd(&counters[C_BADVAL], 1ull);
+            continue;
+        }
+        const uint64_t h = mix45(key);
+        const uint32_t tag = (uint32_t)h & kTagMask;
+        uint64_t b = home_bucket(h, nb);
+        bool done = false;
+        for (int d = 0; d < kMaxDisp && !done; ++d) {
+            unsigned long long* s = reinterpret_cast<unsigned long long*>(buckets + 4 * b);
+            const uint32_t want = ((uint32_t)d << 28) | tag;
+            const uint64_t entry = ((uint64_t)val << 32) | want;
+            for (int j = 0; j < 4 && !done; ++j) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s + j);
+                for (;;) {
+                    if (cur == kEmptySlot) {
+                        const unsigned long long prev = atomicCAS(s + j, kEmptySlot, entry);
+                        if (prev == kEmptySlot) {
+                            atomicAdd(&counters[C_INSERTED], 1ull);
+                            if (d) atomicAdd(&counters[C_DISPLACED], 1ull);
+                            atomicMax(&counters[C_MAXPROBE],
+                                      (unsigned long long)(level * kMaxDisp + d + 1));
+                            done = true;
+                            break;
+                        }
+                        cur = prev;
+                        continue;
+                    }
+                    if (((uint32_t)cur & ~kFlagBit) == want) {  // the same key is resident
+                        if (!LCA) {
+                            atomicAdd(&counters[C_DUP], 1ull);
+                            done = true;
+                            break;
+                        }
+                        const uint32_t old = (uint32_t)(cur >> 32);
+                        const uint32_t merged = lca_ids(tv, old, val);
+                        if (merged == old) {
+                            done = true;
+                            break;
+                        }
+                        const unsigned long long desired =
+                            (cur & 0xFFFFFFFFull) | ((unsigned long long)merged << 32);
+                        const unsigned long long prev = atomicCAS(s + j, cur, desired);
+                        if (prev == cur) {
+                            done = true;
+                            break;
+                        }
+                        cur = prev;
+                        continue;
+                    }
+                    break;  // occupied by another key
+                }
+            }
+            if (!done) {
+                if (!((uint32_t)(*reinterpret_cast<volatile unsigned long long*>(s)) & kFlagBit))
+                    atomicOr(s, (unsigned long long)kFlagBit);
+                b = (b + 1 == nb) ? 0 : b + 1;
+            }
+        }
+        if (!done) {
+            const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
+            if (o < ovf_cap) {
+                ovf_keys[o] = key;
+                ovf_vals[o] = val;
+            }
+        }
+    }
+}
+
+__global__ void count_flagged_kernel(const uint64_t* __restrict__ buckets, uint64_t nb,
+                                     unsigned long long* out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) {
+        const uint64_t s0 = buckets[4 * i];
+        local += (s0 != kEmptySlot) && ((uint32_t)s0 & kFlagBit);
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+static void alloc_level(umgap_index* idx, int lv, uint64_t nb) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, nb * 32);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        UMGAP_FAIL(UMGAP_ERR_NOMEM, "cannot allocate %.2f GB for table level %d: %s",
+                   nb * 32 / 1e9, lv, cudaGetErrorString(e));
+    }
+    idx->level_dev[lv] = (uint64_t*)p;
+    idx->level_nb[lv] = nb;
+    idx->nlevels = lv + 1;
+    idx->bytes += nb * 32;
+    fill_empty_kernel<<<148 * 8, 256>>>((ulonglong2*)p, nb * 2);
+    UMGAP_CUDA(cudaGetLastError());
+}
+
+static uint64_t buckets_for(uint64_t keys, double load) {
+    const uint64_t nb = (uint64_t)((double)keys / (4.0 * load)) + 1;
+    return std::max(nb, kMinBuckets);
+}
+
+void TableBuilder::begin(umgap_index* i, uint64_t expected_keys, double load_factor) {
+    idx = i;
+    expected = expected_keys;
+    if (load_factor <= 0) load_factor = 0.70;
+    if (load_factor > 1.0) UMGAP_FAIL(UMGAP_ERR_INVALID, "load factor must be in (0,1]");
+    use_device(idx->device);
+    alloc_level(idx, 0, buckets_for(expected_keys, load_factor));
+    ovf_cap = std::max<uint64_t>(1u << 20, expected_keys / 8);
+    UMGAP_CUDA(cudaMalloc((void**)&ovf_keys, ovf_cap * sizeof(uint64_t)));
+    UMGAP_CUDA(cudaMalloc((void**)&ovf_vals, ovf_cap * sizeof(uint32_t)));
+    UMGAP_CUDA(cudaMalloc((void**)&counters, C_N * sizeof(unsigned long long)));
+    UMGAP_CUDA(cudaMemset(counters, 0, C_N * sizeof(unsigned long long)));
+}
+
+static void launch_insert(umgap_index* idx, int lv, const uint64_t* keys, const uint32_t* vals,
+                          uint64_t n, uint64_t* ok, uint32_t* ov, uint64_t cap,
+                          unsigned long long* counters, const TaxView* tv, cudaStream_t st) {
+    if (!n) return;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(n, threads), 148ull * 64);
+    if (tv)
+        insert_kernel<true><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nb[lv], keys,
+                                                        vals, n, lv, ok, ov, cap, counters, *tv);
+    else
+        insert_kernel<false><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nb[lv], keys,
+                                                         vals, n, lv, ok, ov, cap, counters, TaxView{});
+    UMGAP_CUDA(cudaGetLastError());
+}
+
+void TableBuilder::insert_dev(const uint64_t* keys_dev, const uint32_t* vals_dev, uint64_t n,
+                              cudaStream_t stream) {
+    launch_insert(idx, 0, keys_dev, vals_dev, n, ovf_keys, ovf_vals, ovf_cap, counters, lca_view,
+                  stream);
+}
+
+void TableBuilder::finish() {
+    unsigned long long h[C_N];
+    UMGAP_CUDA(cudaDeviceSynchronize());
+    UMGAP_CUDA(cudaMemcpy(h, counters, sizeof h, cudaMemcpyDeviceToHost));
+    int lv = 0;
+    while (h[C_OVF] > 0) {
+        if (h[C_OVF] > ovf_cap)
+            UMGAP_FAIL(UMGAP_ERR_CAPACITY,
+                       "%llu keys overflowed table level %d (buffer holds %llu): lower the load factor",
+                       h[C_OVF], lv, (unsigned long long)ovf_cap);
+        if (lv + 1 >= kMaxLevels)
+            UMGAP_FAIL(UMGAP_ERR_CAPACITY, "table needs more than %d overflow levels", kMaxLevels);
+        // move the overflow list aside, reset the counter, build the next level from it
+        const uint64_t m = h[C_OVF];
+        DevBuf<uint64_t> k2(m);
+        DevBuf<uint32_t> v2(m);
+        UMGAP_CUDA(cudaMemcpy(k2.p, ovf_keys, m * sizeof(uint64_t), cudaMemcpyDeviceToDevice));
+        UMGAP_CUDA(cudaMemcpy(v2.p, ovf_vals, m * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+        UMGAP_CUDA(cudaMemset(counters + C_OVF, 0, sizeof(unsigned long long)));
+        ++lv;
+        alloc_level(idx, lv, buckets_for(m, 0.25));
+        launch_insert(idx, lv, k2.p, v2.p, m, ovf_keys, ovf_vals, ovf_cap, counters, lca_view, nullptr);
+        UMGAP_CUDA(cudaDeviceSynchronize());
+        UMGAP_CUDA(cudaMemcpy(h, counters, sizeof h, cudaMemcpyDeviceToHost));
+    }
+    if (h[C_BADVAL])
+        UMGAP_FAIL(UMGAP_ERR_CAPACITY, "%llu values do not fit the table (must be < 2^32-1)", h[C_BADVAL]);
+    if (h[C_DUP] && !lca_view)
+        UMGAP_FAIL(UMGAP_ERR_INVALID, "%llu duplicate keys in index input", h[C_DUP]);
+    idx->n_keys = h[C_INSERTED];
+    idx->n_displaced = h[C_DISPLACED];
+    idx->max_probe = h[C_MAXPROBE];
+    // flagged buckets of level 0 (what a lookup's second probe depends on)
+    UMGAP_CUDA(cudaMemset(counters, 0, sizeof(unsigned long long)));
+    count_flagged_kernel<<<148 * 8, 256>>>(idx->level_dev[0], idx->level_nb[0], counters);
+    UMGAP_CUDA(cudaGetLastError());
+    UMGAP_CUDA(cudaMemcpy(h, counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    idx->n_flagged = h[0];
+    abort();
+}
+
+void TableBuilder::abort() {
+    if (ovf_keys) cudaFree(ovf_keys);
+    if (ovf_vals) cudaFree(ovf_vals);
+    if (counters) cudaFree(counters);
+    ovf_keys = nullptr;
+    ovf_vals = nullptr;
+    counters = nullptr;
+}
+
+int TableBuilder::code_for(uint8_t byte) {
+    uint8_t& c = idx->code_of_byte[byte];
+    if (c == 0xFF) {
+        if (idx->alphabet_size >= 32) return -1;
+        c = (uint8_t)idx->alphabet_size++;
+    }
+    return c;
+}
+
+// ---- random-sector gather: the measured denominator of the random-sector roofline ------------
+__global__ void randsector_kernel(const ulonglong4* __restrict__ table, uint64_t nb, uint64_t n,
+                                  uint64_t seed, unsigned long long* sink) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc = 0;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {  // 4 independent sectors in flight per thread
+        ulonglong4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t h = mix45((i + u * stride + seed) & kKeyMask);
+            v[u] = load_bucket(table + home_bucket(h, nb));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    for (; i < n; i += stride) {
+        const uint64_t h = mix45((i + seed) & kKeyMask);
+        const ulonglong4 v = load_bucket(table + home_bucket(h, nb));
+        acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);  // keeps the loads alive
+}
+
+}  // namespace umgap
+
+using namespace umgap;
+
+extern "C" {
+
+int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
+                           uint64_t n, int k, int device, double load_factor, umgap_index** out) {
+    umgap_index* idx = nullptr;
+    int rc = guarded([&] {
+        if (!out || (n && (!keys || !values))) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (k <= 0 || k > 9)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "k-mer table supports 1 <= k <= 9 (got %d)", k);
+        idx = new umgap_index();
+        idx->device = device;
+        idx->k = k;
+        memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
+        TableBuilder b;
+        try {
+            b.begin(idx, n, load_factor);
+            const uint64_t batch = 1ull << 24;
+            std::vector<uint64_t> hk;
+            std::vector<uint32_t> hv;
+            DevBuf<uint64_t> dk(std::min(n, batch));
+            DevBuf<uint32_t> dv(std::min(n, batch));
+            for (uint64_t base = 0; base < n; base += batch) {
+                const uint64_t m = std::min(batch, n - base);
+                hk.assign(m, kInvalidKey);
+                hv.assign(m, 0);
+                for (uint64_t i = 0; i < m; ++i) {
+                    const uint64_t g = base + i;
+                    const uint64_t o = key_off ? key_off[g] : g * (uint64_t)k;
+                    const uint64_t len = key_off ? key_off[g + 1] - o : (uint64_t)k;
+                    if (len != (uint64_t)k) {
+                        ++idx->n_skipped;
+                        continue;
+                    }
+                    uint64_t code = 0;
+                    for (int r = 0; r < k; ++r) {
+                        const int c = b.code_for(keys[o + r]);
+                        if (c < 0)
+                            UMGAP_FAIL(UMGAP_ERR_CAPACITY,
+                                       "index keys use more than 32 distinct byte values");
+                        code = (code << 5) | (uint64_t)c;
+                    }
+                    if (values[g] >= 0xFFFFFFFFull)
+                        UMGAP_FAIL(UMGAP_ERR_CAPACITY, "value %llu of key %llu does not fit 32 bits",
+                                   (unsigned long long)values[g], (unsigned long long)g);
+                    hk[i] = code;
+                    hv[i] = (uint32_t)values[g];
+                }
+                UMGAP_CUDA(cudaMemcpy(dk.p, hk.data(), m * sizeof(uint64_t), cudaMemcpyHostToDevice));
+                UMGAP_CUDA(cudaMemcpy(dv.p, hv.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+                b.insert_dev(dk.p, dv.p, m);
+                UMGAP_CUDA(cudaDeviceSynchronize());
+            }
+            b.finish();
+        } catch (...) {
+            b.abort();
+            throw;
+        }
+        *out = idx;
+    });
+    if (rc != UMGAP_OK && idx) umgap_index_free(idx);
+    return rc;
+}
+
+void umgap_index_free(umgap_index* idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    for (int i = 0; i < idx->nlevels; ++i)
+        if (idx->level_dev[i]) cudaFree(idx->level_dev[i]);
+    if (idx->var_table) cudaFree(idx->var_table);
+    idx->ws.release();
+    delete idx;
+}
+
+int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info) {
+    return guarded([&] {
+        if (!idx || !info) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        info->n_keys = idx->n_keys;
+        info->n_buckets = 0;
+        for (int i = 0; i < idx->nlevels; ++i) info->n_buckets += idx->level_nb[i];
+        info->bytes = idx->bytes;
+        info->n_skipped = idx->n_skipped;
+        info->n_flagged = idx->n_flagged;
+        info->n_displaced = idx->n_displaced;
+        info->max_probe = idx->max_probe;
+        info->k = idx->k;
+        info->device = idx->device;
+        info->alphabet_size = idx->alphabet_size;
+    });
+}
+
+int umgap_randsector_bench(const umgap_index* idx, uint64_t n_gathers, int iters, double* rate) {
+    return guarded([&] {
+        if (!idx || !rate || idx->nlevels == 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(idx->device);
+        DevBuf<unsigned long long> sink(1);
+        UMGAP_CUDA(cudaMemset(sink.p, 0, sizeof(unsigned long long)));
+        cudaEvent_t e0, e1;
+        UMGAP_CUDA(cudaEventCreate(&e0));
+        UMGAP_CUDA(cudaEventCreate(&e1));
+        const ulonglong4* t = (const ulonglong4*)idx->level_dev[0];
+        const int threads = 256, blocks = 148 * 8;
+        for (int w = 0; w < 2; ++w)
+            randsector_kernel<<<blocks, threads>>>(t, idx->level_nb[0], n_gathers, 17 + w, sink.p);
+        double best = 0;
+        for (int it = 0; it < iters; ++it) {
+            UMGAP_CUDA(cudaEventRecord(e0));
+            randsector_kernel<<<blocks, threads>>>(t, idx->level_nb[0], n_gathers,
+                                                   1000003ull * (it + 3), sink.p);
+            UMGAP_CUDA(cudaEventRecord(e1));
+            UMGAP_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            UMGAP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::max(best, (double)n_gathers / (ms * 1e-3));
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *rate = best;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,313 @@
+// Warp-cooperative per-record machinery: the seedextend state machine (one lane per record) and
+// the taxa2agg aggregators LCA*, hybrid and MRTL (one warp per record) on the preorder-numbered
+// taxonomy.  Restates seedextend.rs:94-149,167-176, agg/mod.rs:27-44, tree/mod.rs:29-101,
+// tree/lca.rs:34-40, tree/mix.rs:43-64, rmq/rtl.rs:39-57 and taxa2agg.rs:159-181 in closed form:
+//
+//   S      = distinct taxa of the record with count >= lower bound, sorted by preorder index
+//   leaf   = member of S with no strict descendant in S  <=>  next member lies outside its subtree
+//   LCA*   = LCA(first leaf, last member)            (root of the collapsed induced tree)
+//   hybrid = from LCA*, descend into the child subtree holding the largest count while
+//            count/parent_count >= factor (IEEE f32 division), re-collapsing at every step
+//   MRTL   = member maximising the summed counts of its ancestors-or-self in S
+#pragma once
+#include "taxdev.cuh"
+
+namespace umgap {
+
+constexpr uint32_t kSkip = 0xFFFFFFFEu;  // internal: element removed from a stream
+
+// ---- seedextend -----------------------------------------------------------------------------
+// Streams the logical list ids[0], ids[stride], ... (count raw entries).  A raw UMGAP_MISS is a
+// 0 when one_on_one, otherwise it is not part of the list at all (prot2kmer2lca.rs:115,176).
+// Calls emit(v) for every element of every selected range, in order.
+template <class Emit>
+__device__ __forceinline__ void seedextend_stream(const uint32_t* ids, uint32_t stride,
+                                                  uint32_t count, bool one_on_one,
+                                                  uint32_t min_seed, uint32_t max_gap, Emit emit) {
+    auto fetch = [&](uint32_t raw) -> uint32_t {
+        const uint32_t v = ids[(uint64_t)raw * stride];
+        return v == kNoValue ? (one_on_one ? 0u : kSkip) : v;
+    };
+    auto flush = [&](uint32_t raw_from, uint32_t n) {  // emit n list elements starting at raw_from
+        for (uint32_t r = raw_from; n; ++r) {
+            const uint32_t v = fetch(r);
+            if (v == kSkip) continue;
+            emit(v);
+            --n;
+        }
+    };
+    // first element t[0] (the sentinel 0 when the list is empty)
+    uint32_t raw = 0;
+    uint32_t last = 0;
+    bool have_first = false;
+    for (; raw < count; ++raw) {
+        const uint32_t v = fetch(raw);
+        if (v != kSkip) {
+            last = v;
+            have_first = true;
+            break;
+        }
+    }
+    if (!have_first) return;  // t = [0]: every candidate range is empty
+    uint32_t start = 0, end = 1, same = 1, smax = 1;
+    uint32_t start_raw = raw;  // raw index at or before list element `start`
+    ++raw;
+    for (;;) {
+        // next list element t[end]; the sentinel once the raw entries are exhausted
+        uint32_t cur = 0;
+        bool sentinel = true;
+        for (; raw < count; ++raw) {
+            const uint32_t v = fetch(raw);
+            if (v != kSkip) {
+                cur = v;
+                sentinel = false;
+                break;
+            }
+        }
+        const uint32_t cur_raw = raw;  // raw position of t[end] (== count for the sentinel)
+        if (last == cur) {                                   // :109-113
+            ++same;
+        } else if (last == 0 && same > max_gap) {            // :116-127 gap too long
+            if (smax >= min_seed) flush(start_raw, end - same - start);
+            start = end;
+            start_raw = cur_raw;
+            last = cur;
+            same = 1;
+            smax = 1;
+        } else if (last == 0 && end - start == same) {       // :130-134 do not start with a gap
+            start = end + 1;
+            start_raw = cur_raw + 1;
+        } else {
+            if (last != 0) smax = smax > same ? smax : same; // :137-139
+            last = cur;                                      // :140-142
+            same = 1;
+        }
+        ++end;
+        if (sentinel) break;
+        ++raw;
+    }
+    // :144-149 -- `last` is 0 here (the sentinel was consumed), so the trailing zeros drop out
+    if (smax >= min_seed) {
+        if (last == 0) end -= same;
+        if (end > start) flush(start_raw, end - start);
+    }
+}
+
+// ---- warp utilities ----------------------------------------------------------------------------
+__device__ __forceinline__ void cmpex(uint32_t* a, uint32_t i, uint32_t l) {
+    const uint32_t x = a[i], y = a[l];
+    if (x > y) {
+        a[i] = y;
+        a[l] = x;
+    }
+}
+
+// Ascending bitonic sort of a[0..n) for any n (indices >= n behave as +infinity).
+__device__ __forceinline__ void warp_sort(uint32_t* a, uint32_t n, int lane) {
+    if (n < 2) return;
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const uint32_t pairs = np2 >> 1;
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t t = lane; t < pairs; t += 32) {
+            const uint32_t blk = t / hk, r = t - blk * hk;
+            const uint32_t i = blk * k + r, l = blk * k + (k - 1 - r);
+            if (l < n) cmpex(a, i, l);
+        }
+        __syncwarp();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < pairs; t += 32) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                if (l < n) cmpex(a, i, l);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// First index in [lo, hi) with A[idx] > bound (A ascending); hi when none.  All lanes call and
+// all receive the result.
+__device__ __forceinline__ uint32_t warp_upper_bound(const uint32_t* A, uint32_t lo, uint32_t hi,
+                                                     uint32_t bound, int lane) {
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t i = base + lane;
+        const bool gt = i < hi && A[i] > bound;
+        const unsigned m = __ballot_sync(0xffffffffu, gt);
+        if (m) return base + (uint32_t)__ffs(m) - 1;
+    }
+    return hi;
+}
+
+// LCA* of the members [lo, hi) of the sorted distinct list (A = dense index, L = last[A]).
+__device__ __forceinline__ uint32_t lca_star_range(const TaxView& tv, const uint32_t* A,
+                                                   const uint32_t* L, uint32_t lo, uint32_t hi,
+                                                   int lane) {
+    uint32_t first_leaf = hi - 1;
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t j = base + lane;
+        const bool leaf = j < hi && (j + 1 == hi || A[j + 1] > L[j]);
+        const unsigned m = __ballot_sync(0xffffffffu, leaf);
+        if (m) {
+            first_leaf = base + (uint32_t)__ffs(m) - 1;
+            break;
+        }
+    }
+    return warp_lca(tv, A[first_leaf], A[hi - 1], lane);
+}
+
+struct AggParams {
+    int strategy;
+    float factor;
+    float lower_bound;
+    int ranked_only;
+};
+
+constexpr uint32_t kAggUnknown = 0xFFFFFFFDu;  // internal: record holds an id unknown to the tree
+
+// Aggregates one record.  A[0..n) holds its non-zero taxon ids (any order); P needs n+1 and L
+// needs n entries of scratch.  Returns the snapped taxon id, the literal 1 for an empty record
+// (taxa2agg.rs:174-175), or kAggUnknown with *bad_id set.  All 32 lanes must call.
+__device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* A, uint32_t* P,
+                                                   uint32_t* L, uint32_t n, const AggParams& ap,
+                                                   int lane, uint32_t* bad_id) {
+    if (n == 0) return 1u;
+    // 1. taxon id -> preorder index
+    bool bad = false;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t id = A[i];
+        const uint32_t d = id <= tv.max_id ? tv.dense_of[id] : kNoTaxon;
+        if (d == kNoTaxon) {
+            bad = true;
+            *bad_id = id;
+        }
+        A[i] = d;
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, bad)) return kAggUnknown;
+    // 2. sort, 3. distinct + run starts
+    warp_sort(A, n, lane);
+    uint32_t m = 0;
+    uint32_t carry = kNoTaxon;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < n ? A[i] : kNoTaxon;
+        uint32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) prev = carry;
+        const bool head = i < n && (i == 0 || v != prev);
+        const unsigned mask = __ballot_sync(0xffffffffu, head);
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1));
+        carry = __shfl_sync(0xffffffffu, v, 31);
+        __syncwarp();
+        if (head) {
+            A[m + rank] = v;
+            P[m + rank] = i;
+        }
+        m += __popc(mask);
+        __syncwarp();
+    }
+    if (lane == 0) P[m] = n;
+    __syncwarp();
+    // 4. counts, lower-bound filter (agg/mod.rs:39-44: keep count >= lower_bound, f32 compare),
+    //    exclusive prefix sums of the kept counts into P
+    uint32_t kept = 0, running = 0;
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t j = base + lane;
+        uint32_t c = 0, v = 0;
+        if (j < m) {
+            c = P[j + 1] - P[j];
+            v = A[j];
+        }
+        const bool keep = j < m && (float)c >= ap.lower_bound;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1));
+        const uint32_t incl = warp_incl_scan(keep ? c : 0u, lane);
+        __syncwarp();
+        if (keep) {
+            A[kept + rank] = v;
+            P[kept + rank] = running + incl - c;
+        }
+        kept += __popc(mask);
+        running += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+    }
+    m = kept;
+    if (m == 0) return 1u;  // everything filtered: the literal "1"
+    if (lane == 0) P[m] = running;
+    for (uint32_t j = lane; j < m; j += 32) L[j] = tv.last[A[j]];
+    __syncwarp();
+
+    uint32_t result;
+    if (ap.strategy == UMGAP_AGG_LCA_STAR) {
+        result = lca_star_range(tv, A, L, 0, m, lane);
+    } else if (ap.strategy == UMGAP_AGG_HYBRID) {
+        uint32_t lo = 0, hi = m;
+        uint32_t base_node = lca_star_range(tv, A, L, lo, hi, lane);
+        uint32_t bval = running;
+        lo = warp_upper_bound(A, lo, hi, base_node - 1u, lane);  // first member >= base (base>=0)
+        if (base_node == 0) lo = 0;
+        for (;;) {
+            uint32_t g = lo;
+            if (g < hi && A[g] == base_node) ++g;  // the base itself is not one of its children
+            if (g >= hi) break;                    // no children: stop (tree/mix.rs:51)
+            const uint32_t child_depth = (uint32_t)tv.depth[base_node] + 1;
+            uint32_t best = 0, best_lo = 0, best_hi = 0;
+            while (g < hi) {
+                const uint32_t c = tv.anc[(uint64_t)A[g] * tv.stride + child_depth];
+                const uint32_t e = warp_upper_bound(A, g, hi, tv.last[c], lane);
+                const uint32_t sub = P[e] - P[g];
+                if (sub > best) {  // first maximal child in preorder wins ties
+                    best = sub;
+                    best_lo = g;
+                    best_hi = e;
+                }
+                g = e;
+            }
+            if (__fdiv_rn((float)best, (float)bval) < ap.factor) break;  // tree/mix.rs:57
+            base_node = lca_star_range(tv, A, L, best_lo, best_hi, lane);
+            bval = best;
+            hi = best_hi;
+            lo = base_node == 0 ? best_lo : warp_upper_bound(A, best_lo, best_hi, base_node - 1u, lane);
+        }
+        result = base_node;
+    } else {  // MRTL
+        uint32_t best_w = 0, best_j = 0;
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t j = base + lane;
+            uint32_t w = 0;
+            if (j < m) {
+                const uint32_t me = A[j];
+                for (uint32_t i = 0; i <= j; ++i)
+                    if (L[i] >= me) w += P[i + 1] - P[i];
+            }
+            // arg-max within the chunk, first index wins ties
+            uint32_t bw = w, bj = j;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const uint32_t ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (ow > bw || (ow == bw && oj < bj)) {
+                    bw = ow;
+                    bj = oj;
+                }
+            }
+            if (bw > best_w) {
+                best_w = bw;
+                best_j = bj;
+            }
+        }
+        result = A[best_j];
+    }
+    return ap.ranked_only ? tv.snap_ranked[result] : tv.snap_valid[result];
+}
+
+}  // namespace umgap
