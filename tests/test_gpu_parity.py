@@ -308,7 +308,7 @@ def test_classify_reads_matches_oracle_pipeline(capi, world, strategy, factor, l
             continue
         assert int(got[gi]) in want[h], (h, int(got[gi]), want[h])
         non_root += int(got[gi]) != 1
-    assert non_root > 40
+    assert non_root > (40 if strategy else 3)  # LCA* lands on the root whenever a read carries noise
     assert "e0" not in want and "s0" not in want and "s1" in want and "L0" in want and "M0" in want
 
 

@@ -44,8 +44,8 @@ struct umgap_index {
     int device = 0;
     int k = 9;  // 0: variable-length (tryptic) table
     int nlevels = 0;
-    uint64_t* level_dev[umgap::kMaxLevels] = {};
-    uint64_t level_nb[umgap::kMaxLevels] = {};
+    uint32_t* level_dev[umgap::kMaxLevels] = {};  // sector arrays (8 words per sector)
+    uint32_t level_nlines[umgap::kMaxLevels] = {};
     uint8_t code_of_byte[256];  // 0xFF = byte not in the index alphabet
     int alphabet_size = 0;
     uint64_t n_keys = 0, n_skipped = 0, n_flagged = 0, n_displaced = 0, max_probe = 0;
@@ -58,7 +58,7 @@ struct umgap_index {
         umgap::TableView v{};
         for (int i = 0; i < nlevels; ++i) {
             v.level[i] = reinterpret_cast<const ulonglong4*>(level_dev[i]);
-            v.nb[i] = level_nb[i];
+            v.nlines[i] = level_nlines[i];
         }
         v.nlevels = nlevels;
         v.k = k;

@@ -94,11 +94,14 @@ __device__ __forceinline__ uint32_t nt_code(uint8_t c) {
 
 constexpr int kTile = 128;          // k-mer start positions per warp pass (4 per lane)
 constexpr int kLookupWarps = 8;     // warps (= reads in flight) per CTA
+constexpr int kQueue = 2 * kTile;   // pending second probes of one tile (both strands)
 
 // One warp per read.  Per tile of 128 start positions the warp stages the nucleotide codes in
 // shared memory, translates every codon start once for both strands (F = forward codon at x,
 // R = codon of the reverse strand whose lowest forward coordinate is x), then each lane packs
-// 4 forward + 4 reverse k-mers and issues their 8 bucket loads back to back before resolving.
+// 4 forward + 4 reverse k-mers and issues their 8 sector loads back to back.  First probes are
+// resolved branch-free; the few lookups that ended on a flagged sector are compacted into a
+// per-warp shared-memory queue and re-probed 32 at a time, so the warp stays converged.
 // ids layout: forward k-mer starting at p -> ids[2*off + p]; reverse-strand k-mer starting at
 // reverse coordinate q -> ids[2*off + n + q]  (frame f record = entries f-1, f+2, f+5, ...).
 template <int K>
@@ -111,17 +114,21 @@ translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ n
     __shared__ uint8_t s_nt[kLookupWarps][W + 2 + 2];
     __shared__ uint8_t s_f[kLookupWarps][W + 4];
     __shared__ uint8_t s_r[kLookupWarps][W + 4];
+    __shared__ uint64_t q_h[kLookupWarps][kQueue];    // hash | next distance << 45 | level << 48
+    __shared__ uint32_t q_pos[kLookupWarps][kQueue];  // index into the read's ids slice
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
     if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
     __syncthreads();
+    const ulonglong4* __restrict__ level0 = t.level[0];
+    const uint32_t nlines0 = t.nlines[0];
     const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
     for (uint64_t r = (uint64_t)blockIdx.x * kLookupWarps + warp; r < nreads; r += nwarps) {
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         if (n < 3u * K) continue;  // no frame reaches K residues
         const uint32_t npos = n - 3u * K + 1;
-        uint32_t* out_f = ids + 2 * off;
-        uint32_t* out_r = out_f + n;
+        uint32_t* out = ids + 2 * off;  // forward ids at [p], reverse ids at [n + q]
         for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
             for (int i = lane; i < W + 2; i += 32) {
                 const uint32_t x = w0 + i;
@@ -135,9 +142,9 @@ translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ n
                 s_r[warp][i] = s_lut[has_n ? 64 : 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2)];
             }
             __syncwarp();
-            uint64_t hf[4], hr[4];
-            ulonglong4 bf[4], br[4];
-            bool vf[4], vr[4];
+            uint64_t h[8];       // 0..3 forward, 4..7 reverse
+            ulonglong4 sec[8];
+            bool valid[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int pl = lane + 32 * u;
@@ -153,30 +160,69 @@ translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ n
                     kr = (kr << 5) | (cr & 31u);
                 }
                 const bool live = w0 + pl < npos;
-                vf[u] = live && !(bad_f & 0x80u);
-                vr[u] = live && !(bad_r & 0x80u);
-                hf[u] = mix45(kf);
-                hr[u] = mix45(kr);
+                valid[u] = live && !(bad_f & 0x80u);
+                valid[u + 4] = live && !(bad_r & 0x80u);
+                h[u] = mix45(kf);
+                h[u + 4] = mix45(kr);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (vf[u]) bf[u] = load_bucket(t.level[0] + home_bucket(hf[u], t.nb[0]));
-                if (vr[u]) br[u] = load_bucket(t.level[0] + home_bucket(hr[u], t.nb[0]));
-            }
+            for (int u = 0; u < 8; ++u)
+                if (valid[u]) sec[u] = load_sector(level0 + probe_sector(h[u], nlines0, 0));
+            uint32_t qn = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t p = w0 + lane + 32 * u;
-                if (p < npos) {
-                    uint32_t val_f = kNoValue, val_r = kNoValue;
-                    if (vf[u] && !probe_bucket(bf[u], (uint32_t)hf[u] & kTagMask, val_f))
-                        val_f = probe_slow(t, hf[u]);
-                    if (vr[u] && !probe_bucket(br[u], (uint32_t)hr[u] & kTagMask, val_r))
-                        val_r = probe_slow(t, hr[u]);
-                    out_f[p] = val_f;
-                    out_r[npos - 1 - p] = val_r;
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t p = w0 + lane + 32 * (u & 3);
+                const uint32_t pos = u < 4 ? p : n + (npos - 1 - p);
+                bool more = false;
+                uint32_t v = kNoValue;
+                if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                if (p < npos && !more) out[pos] = v;
+                const unsigned m = __ballot_sync(0xffffffffu, more);
+                if (more) {
+                    const uint32_t at = qn + __popc(m & lt_mask);
+                    q_h[warp][at] = h[u] | (1ull << 45);
+                    q_pos[warp][at] = pos;
                 }
+                qn += __popc(m);
             }
             __syncwarp();
+            // re-probe the flagged ones, densely packed: distance d, then d+1, ... then next level
+            while (qn) {
+                uint32_t qnext = 0;
+                for (uint32_t c = 0; c < qn; c += 32) {
+                    const uint32_t i = c + lane;
+                    const bool active = i < qn;
+                    uint64_t hq = 0;
+                    uint32_t pos = 0;
+                    if (active) {
+                        hq = q_h[warp][i];
+                        pos = q_pos[warp][i];
+                    }
+                    uint32_t d = (uint32_t)(hq >> 45) & 7u;
+                    uint32_t lv = (uint32_t)(hq >> 48);
+                    const uint64_t hh = hq & kKeyMask;
+                    bool more = false;
+                    if (active) {
+                        const ulonglong4 s2 = load_sector(t.level[lv] + probe_sector(hh, t.nlines[lv], d));
+                        const uint32_t v = probe_sector_data(s2, (d << 28) | ((uint32_t)hh & kTagMask), more);
+                        if (more && ++d == (uint32_t)kMaxDisp) {
+                            d = 0;
+                            if (++lv == (uint32_t)t.nlevels) more = false;  // v is kNoValue here
+                        }
+                        if (!more) out[pos] = v;
+                    }
+                    __syncwarp();
+                    const unsigned m = __ballot_sync(0xffffffffu, more);
+                    if (more) {
+                        const uint32_t at = qnext + __popc(m & lt_mask);
+                        q_h[warp][at] = hh | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
+                        q_pos[warp][at] = pos;
+                    }
+                    qnext += __popc(m);
+                }
+                __syncwarp();
+                qn = qnext;
+            }
         }
     }
 }

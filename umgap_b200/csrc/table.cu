@@ -9,16 +9,42 @@ namespace umgap {
 
 enum { C_OVF = 0, C_DUP = 1, C_DISPLACED = 2, C_MAXPROBE = 3, C_INSERTED = 4, C_BADVAL = 5, C_N = 8 };
 
-__global__ void fill_empty_kernel(ulonglong2* p, uint64_t n16) {
+// Empty table: every meta = kEmptyMeta, every value = kNoValue.
+__global__ void fill_empty_kernel(uint4* p, uint64_t n16) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
-        p[i] = make_ulonglong2(kEmptySlot, kEmptySlot);
+        p[i] = (i & 1) ? make_uint4(kNoValue, kNoValue, kNoValue, kNoValue)
+                       : make_uint4(kEmptyMeta, kEmptyMeta, kEmptyMeta, kEmptyMeta);
 }
 
-// One thread per key.  Slots are claimed with 64-bit CAS in slot order, so two threads carrying
+// Folds `val` into a slot's value word.  The word starts as kNoValue; whoever comes first stores
+// its value, every later writer of the same key merges (LCA) or is counted as a duplicate.
+template <bool LCA>
+__device__ __forceinline__ void merge_value(unsigned int* addr, uint32_t val, const TaxView& tv,
+                                            unsigned long long* counters) {
+    unsigned int old = *reinterpret_cast<volatile unsigned int*>(addr);
+    for (;;) {
+        if (old == kNoValue) {
+            const unsigned int prev = atomicCAS(addr, kNoValue, val);
+            if (prev == kNoValue) return;
+            old = prev;
+        }
+        if (!LCA) {
+            atomicAdd(&counters[C_DUP], 1ull);
+            return;
+        }
+        const uint32_t merged = lca_ids(tv, old, val);
+        if (merged == old) return;
+        const unsigned int prev = atomicCAS(addr, old, merged);
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+// One thread per key.  Metas are claimed with 32-bit CAS in slot order, so two threads carrying
 // the same key always meet in the same slot (duplicates are detected, never stored twice).
 template <bool LCA>
-__global__ void insert_kernel(uint64_t* __restrict__ buckets, uint64_t nb,
+__global__ void insert_kernel(uint32_t* __restrict__ sectors, uint32_t nlines,
                               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                               uint64_t n, int level, uint64_t* __restrict__ ovf_keys,
                               uint32_t* __restrict__ ovf_vals, uint64_t ovf_cap,
@@ -34,58 +60,31 @@ __global__ void insert_kernel(uint64_t* __restrict__ buckets, uint64_t nb,
         }
         const uint64_t h = mix45(key);
         const uint32_t tag = (uint32_t)h & kTagMask;
-        uint64_t b = home_bucket(h, nb);
         bool done = false;
-        for (int d = 0; d < kMaxDisp && !done; ++d) {
-            unsigned long long* s = reinterpret_cast<unsigned long long*>(buckets + 4 * b);
-            const uint32_t want = ((uint32_t)d << 28) | tag;
-            const uint64_t entry = ((uint64_t)val << 32) | want;
+        for (uint32_t d = 0; d < (uint32_t)kMaxDisp && !done; ++d) {
+            unsigned int* meta = sectors + probe_sector(h, nlines, d) * 8;
+            const uint32_t want = (d << 28) | tag;
             for (int j = 0; j < 4 && !done; ++j) {
-                unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s + j);
-                for (;;) {
-                    if (cur == kEmptySlot) {
-                        const unsigned long long prev = atomicCAS(s + j, kEmptySlot, entry);
-                        if (prev == kEmptySlot) {
-                            atomicAdd(&counters[C_INSERTED], 1ull);
-                            if (d) atomicAdd(&counters[C_DISPLACED], 1ull);
-                            atomicMax(&counters[C_MAXPROBE],
-                                      (unsigned long long)(level * kMaxDisp + d + 1));
-                            done = true;
-                            break;
-                        }
-                        cur = prev;
-                        continue;
+                unsigned int cur = *reinterpret_cast<volatile unsigned int*>(meta + j);
+                if (cur == kEmptyMeta) {
+                    const unsigned int prev = atomicCAS(meta + j, kEmptyMeta, want);
+                    if (prev == kEmptyMeta) {
+                        atomicAdd(&counters[C_INSERTED], 1ull);
+                        if (d) atomicAdd(&counters[C_DISPLACED], 1ull);
+                        atomicMax(&counters[C_MAXPROBE], (unsigned long long)(level * kMaxDisp + d + 1));
+                        merge_value<LCA>(meta + 4 + j, val, tv, counters);
+                        done = true;
+                        break;
                     }
-                    if (((uint32_t)cur & ~kFlagBit) == want) {  // the same key is resident
-                        if (!LCA) {
-                            atomicAdd(&counters[C_DUP], 1ull);
-                            done = true;
-                            break;
-                        }
-                        const uint32_t old = (uint32_t)(cur >> 32);
-                        const uint32_t merged = lca_ids(tv, old, val);
-                        if (merged == old) {
-                            done = true;
-                            break;
-                        }
-                        const unsigned long long desired =
-                            (cur & 0xFFFFFFFFull) | ((unsigned long long)merged << 32);
-                        const unsigned long long prev = atomicCAS(s + j, cur, desired);
-                        if (prev == cur) {
-                            done = true;
-                            break;
-                        }
-                        cur = prev;
-                        continue;
-                    }
-                    break;  // occupied by another key
+                    cur = prev;
+                }
+                if ((cur & ~kFlagBit) == want) {  // the same key is resident
+                    merge_value<LCA>(meta + 4 + j, val, tv, counters);
+                    done = true;
                 }
             }
-            if (!done) {
-                if (!((uint32_t)(*reinterpret_cast<volatile unsigned long long*>(s)) & kFlagBit))
-                    atomicOr(s, (unsigned long long)kFlagBit);
-                b = (b + 1 == nb) ? 0 : b + 1;
-            }
+            if (!done && !(*reinterpret_cast<volatile unsigned int*>(meta) & kFlagBit))
+                atomicOr(meta, kFlagBit);
         }
         if (!done) {
             const unsigned long long o = atomicAdd(&counters[C_OVF], 1ull);
@@ -97,37 +96,37 @@ __global__ void insert_kernel(uint64_t* __restrict__ buckets, uint64_t nb,
     }
 }
 
-__global__ void count_flagged_kernel(const uint64_t* __restrict__ buckets, uint64_t nb,
+__global__ void count_flagged_kernel(const uint32_t* __restrict__ sectors, uint64_t nsectors,
                                      unsigned long long* out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long local = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) {
-        const uint64_t s0 = buckets[4 * i];
-        local += (s0 != kEmptySlot) && ((uint32_t)s0 & kFlagBit);
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsectors; i += stride)
+        local += sectors[8 * i] >> 31;
     for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
-static void alloc_level(umgap_index* idx, int lv, uint64_t nb) {
+static void alloc_level(umgap_index* idx, int lv, uint64_t nlines) {
+    if (nlines >= (1ull << 32)) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "table level of %llu lines exceeds 2^32", (unsigned long long)nlines);
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, nb * 32);
+    cudaError_t e = cudaMalloc(&p, nlines * 128);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         UMGAP_FAIL(UMGAP_ERR_NOMEM, "cannot allocate %.2f GB for table level %d: %s",
-                   nb * 32 / 1e9, lv, cudaGetErrorString(e));
+                   nlines * 128 / 1e9, lv, cudaGetErrorString(e));
     }
-    idx->level_dev[lv] = (uint64_t*)p;
-    idx->level_nb[lv] = nb;
+    idx->level_dev[lv] = (uint32_t*)p;
+    idx->level_nlines[lv] = (uint32_t)nlines;
     idx->nlevels = lv + 1;
-    idx->bytes += nb * 32;
-    fill_empty_kernel<<<148 * 8, 256>>>((ulonglong2*)p, nb * 2);
+    idx->bytes += nlines * 128;
+    fill_empty_kernel<<<148 * 8, 256>>>((uint4*)p, nlines * 8);
     UMGAP_CUDA(cudaGetLastError());
+    UMGAP_CUDA(cudaDeviceSynchronize());
 }
 
-static uint64_t buckets_for(uint64_t keys, double load) {
-    const uint64_t nb = (uint64_t)((double)keys / (4.0 * load)) + 1;
-    return std::max(nb, kMinBuckets);
+static uint64_t lines_for(uint64_t keys, double load) {
+    const uint64_t nl = (uint64_t)((double)keys / (16.0 * load)) + 1;
+    return std::max<uint64_t>(nl, kMinLines);
 }
 
 void TableBuilder::begin(umgap_index* i, uint64_t expected_keys, double load_factor) {
@@ -136,7 +135,7 @@ void TableBuilder::begin(umgap_index* i, uint64_t expected_keys, double load_fac
     if (load_factor <= 0) load_factor = 0.70;
     if (load_factor > 1.0) UMGAP_FAIL(UMGAP_ERR_INVALID, "load factor must be in (0,1]");
     use_device(idx->device);
-    alloc_level(idx, 0, buckets_for(expected_keys, load_factor));
+    alloc_level(idx, 0, lines_for(expected_keys, load_factor));
     ovf_cap = std::max<uint64_t>(1u << 20, expected_keys / 8);
     UMGAP_CUDA(cudaMalloc((void**)&ovf_keys, ovf_cap * sizeof(uint64_t)));
     UMGAP_CUDA(cudaMalloc((void**)&ovf_vals, ovf_cap * sizeof(uint32_t)));
@@ -151,10 +150,10 @@ static void launch_insert(umgap_index* idx, int lv, const uint64_t* keys, const 
     const int threads = 256;
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(n, threads), 148ull * 64);
     if (tv)
-        insert_kernel<true><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nb[lv], keys,
+        insert_kernel<true><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], keys,
                                                         vals, n, lv, ok, ov, cap, counters, *tv);
     else
-        insert_kernel<false><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nb[lv], keys,
+        insert_kernel<false><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], keys,
                                                          vals, n, lv, ok, ov, cap, counters, TaxView{});
     UMGAP_CUDA(cudaGetLastError());
 }
@@ -185,7 +184,7 @@ void TableBuilder::finish() {
         UMGAP_CUDA(cudaMemcpy(v2.p, ovf_vals, m * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
         UMGAP_CUDA(cudaMemset(counters + C_OVF, 0, sizeof(unsigned long long)));
         ++lv;
-        alloc_level(idx, lv, buckets_for(m, 0.25));
+        alloc_level(idx, lv, lines_for(m, 0.25));
         launch_insert(idx, lv, k2.p, v2.p, m, ovf_keys, ovf_vals, ovf_cap, counters, lca_view, nullptr);
         UMGAP_CUDA(cudaDeviceSynchronize());
         UMGAP_CUDA(cudaMemcpy(h, counters, sizeof h, cudaMemcpyDeviceToHost));
@@ -199,7 +198,7 @@ void TableBuilder::finish() {
     idx->max_probe = h[C_MAXPROBE];
     // flagged buckets of level 0 (what a lookup's second probe depends on)
     UMGAP_CUDA(cudaMemset(counters, 0, sizeof(unsigned long long)));
-    count_flagged_kernel<<<148 * 8, 256>>>(idx->level_dev[0], idx->level_nb[0], counters);
+    count_flagged_kernel<<<148 * 8, 256>>>(idx->level_dev[0], (uint64_t)idx->level_nlines[0] * 4, counters);
     UMGAP_CUDA(cudaGetLastError());
     UMGAP_CUDA(cudaMemcpy(h, counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     idx->n_flagged = h[0];
@@ -225,7 +224,7 @@ int TableBuilder::code_for(uint8_t byte) {
 }
 
 // ---- random-sector gather: the measured denominator of the random-sector roofline ------------
-__global__ void randsector_kernel(const ulonglong4* __restrict__ table, uint64_t nb, uint64_t n,
+__global__ void randsector_kernel(const ulonglong4* __restrict__ table, uint32_t nlines, uint64_t n,
                                   uint64_t seed, unsigned long long* sink) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t acc = 0;
@@ -235,14 +234,14 @@ __global__ void randsector_kernel(const ulonglong4* __restrict__ table, uint64_t
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint64_t h = mix45((i + u * stride + seed) & kKeyMask);
-            v[u] = load_bucket(table + home_bucket(h, nb));
+            v[u] = load_sector(table + probe_sector(h, nlines, 0));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc += v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
     }
     for (; i < n; i += stride) {
         const uint64_t h = mix45((i + seed) & kKeyMask);
-        const ulonglong4 v = load_bucket(table + home_bucket(h, nb));
+        const ulonglong4 v = load_sector(table + probe_sector(h, nlines, 0));
         acc += v.x ^ v.y ^ v.z ^ v.w;
     }
     if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);  // keeps the loads alive
@@ -330,7 +329,7 @@ int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info) {
         if (!idx || !info) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         info->n_keys = idx->n_keys;
         info->n_buckets = 0;
-        for (int i = 0; i < idx->nlevels; ++i) info->n_buckets += idx->level_nb[i];
+        for (int i = 0; i < idx->nlevels; ++i) info->n_buckets += (uint64_t)idx->level_nlines[i] * 4;
         info->bytes = idx->bytes;
         info->n_skipped = idx->n_skipped;
         info->n_flagged = idx->n_flagged;
@@ -354,11 +353,11 @@ int umgap_randsector_bench(const umgap_index* idx, uint64_t n_gathers, int iters
         const ulonglong4* t = (const ulonglong4*)idx->level_dev[0];
         const int threads = 256, blocks = 148 * 8;
         for (int w = 0; w < 2; ++w)
-            randsector_kernel<<<blocks, threads>>>(t, idx->level_nb[0], n_gathers, 17 + w, sink.p);
+            randsector_kernel<<<blocks, threads>>>(t, idx->level_nlines[0], n_gathers, 17 + w, sink.p);
         double best = 0;
         for (int it = 0; it < iters; ++it) {
             UMGAP_CUDA(cudaEventRecord(e0));
-            randsector_kernel<<<blocks, threads>>>(t, idx->level_nb[0], n_gathers,
+            randsector_kernel<<<blocks, threads>>>(t, idx->level_nlines[0], n_gathers,
                                                    1000003ull * (it + 3), sink.p);
             UMGAP_CUDA(cudaEventRecord(e1));
             UMGAP_CUDA(cudaEventSynchronize(e1));
