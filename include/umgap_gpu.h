@@ -189,6 +189,13 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
                                uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
                                void* stream);
 
+/* ---- measurement aid: when enabled, every launch of the two hot-path kernels is bracketed by CUDA
+ * events on the stream it is launched on.  umgap_kernel_times() waits for the recorded launches,
+ * returns the summed durations (ms) and launch counts since the last call, and clears them.      */
+int umgap_kernel_timing(int enable);
+int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
+                       uint64_t* classify_launches);
+
 /* ---- benchmark / test aids (synthetic data of SURVEY 8(d); not part of the reference) ---- */
 typedef struct umgap_synth_spec {
     uint64_t seed;

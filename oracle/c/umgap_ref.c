@@ -1,0 +1,732 @@
+/*
+ * umgap_ref.c -- CPU restatement ("port") of UMGAP's per-read classification path in plain C.
+ *
+ * TEST INFRASTRUCTURE ONLY: built into oracle/c/libumgap_ref.so and loaded by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Nothing in the
+ * product (umgap_b200/) links or calls it.
+ *
+ * It follows the reference's algorithm, not the GPU design: an in-memory `fst` image walked one
+ * node per key byte (fst::Map::get, call site prot2kmer2lca.rs:176), codon-table translation
+ * (dna/translation.rs:125-144, translate.rs:114-133), the seedextend state machine
+ * (seedextend.rs:94-149), the uniq join (uniq.rs:56-84) and induced-tree aggregation
+ * (tree/mod.rs:29-101, tree/lca.rs:34-40, tree/mix.rs:43-64, rmq/rtl.rs:39-57,
+ * taxa2agg.rs:159-181), chunk-parallel over 240-record chunks like the reference's rayon
+ * par_bridge (prot2kmer2lca.rs:163-166) -- here applied to the whole per-read chain, which is at
+ * least as parallel as the reference's process pipeline.
+ *
+ * The `fst` crate (0.3.5, Cargo.toml:23) is not vendored in the reference; its format v2 node
+ * encoding is restated from the published format.  Parity of the byte
+ * format with files written by the real crate is UNPINNED (see oracle/__init__.py).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ fst */
+
+static const char COMMON_INV[] =
+    "te/oasripcnw.hlm-du012g=:bf3y5&_4v9678k%?xCDASFIBEjPTzRNM+LOqHGWUV,YKJZXQ;)(~[]$!'*@";
+
+static int common_idx(uint8_t b) { /* 0 = not encodable, else index+1 (<= 63) */
+    for (int i = 0; i < 63; ++i)
+        if ((uint8_t)COMMON_INV[i] == b) return i + 1;
+    return 0;
+}
+
+static inline uint64_t unpack(const uint8_t* p, unsigned n) {
+    uint64_t v = 0;
+    for (unsigned i = 0; i < n; ++i) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+static unsigned pack_size(uint64_t v) {
+    unsigned s = 1;
+    while (s < 8 && v >= (1ull << (8 * s))) ++s;
+    return s;
+}
+
+/* fst::Map::get: one node hop per key byte, outputs summed.  Returns 1 when found. */
+int ref_fst_get(const uint8_t* d, uint64_t size, const uint8_t* key, uint32_t len, uint64_t* value) {
+    if (size < 32) return 0;
+    uint64_t addr = unpack(d + size - 8, 8);
+    uint64_t out = 0;
+    for (uint32_t kpos = 0; kpos <= len; ++kpos) {
+        /* decode the node at addr far enough to find key[kpos] (or its final state at the end) */
+        if (addr == 0) { /* EMPTY_ADDRESS: final, no transitions */
+            if (kpos == len) { *value = out; return 1; }
+            return 0;
+        }
+        const uint8_t s = d[addr];
+        const unsigned kind = s >> 6;
+        if (kind >= 2) { /* OneTransNext (11) / OneTrans (10): never final */
+            if (kpos == len) return 0;
+            const unsigned c = s & 0x3F, il = c == 0;
+            const uint8_t inp = il ? d[addr - 1] : (uint8_t)COMMON_INV[c - 1];
+            if (inp != key[kpos]) return 0;
+            if (kind == 3) { addr = addr - il - 1; continue; }
+            const uint8_t z = d[addr - il - 1];
+            const unsigned tsz = z >> 4, osz = z & 15;
+            const uint64_t dpos = addr - il - 1 - tsz;
+            const uint64_t delta = unpack(d + dpos, tsz);
+            const uint64_t start = dpos - osz;
+            if (osz) out += unpack(d + start, osz);
+            addr = delta ? start - delta : 0;
+            continue;
+        }
+        const int final = (s & 0x40) != 0;
+        unsigned n = s & 0x3F, nl = 0;
+        if (n == 0) { nl = 1; n = d[addr - 1]; if (n == 1) n = 256; }
+        const uint64_t base = addr - nl - 1;
+        const uint8_t z = d[base];
+        const unsigned tsz = z >> 4, osz = z & 15, isz = n > 32 ? 256 : 0;
+        const uint64_t start = base - isz - n - (uint64_t)n * tsz - (uint64_t)n * osz - (final ? osz : 0);
+        if (kpos == len) {
+            if (!final) return 0;
+            *value = out + (osz ? unpack(d + start, osz) : 0);
+            return 1;
+        }
+        unsigned i;
+        if (isz) {
+            i = d[base - 256 + key[kpos]];
+            if (i >= n) return 0;
+        } else {
+            for (i = 0; i < n; ++i)
+                if (d[base - 1 - i] == key[kpos]) break;
+            if (i == n) return 0;
+        }
+        const uint64_t delta = unpack(d + base - isz - n - (uint64_t)(i + 1) * tsz, tsz);
+        if (osz) out += unpack(d + base - isz - n - (uint64_t)n * tsz - (uint64_t)(i + 1) * osz, osz);
+        addr = delta ? start - delta : 0;
+    }
+    return 0;
+}
+
+/* Builder: the crate's incremental construction for sorted keys (shared prefixes, outputs pushed
+ * down so that a path sums to the value), without the suffix-sharing registry -- minimisation only
+ * changes the file size, never a lookup result. */
+typedef struct { uint8_t inp; uint64_t out, addr; } BTrans;
+typedef struct {
+    int is_final;
+    uint64_t final_out;
+    BTrans* tr; int ntr, cap;
+    int has_last; uint8_t last_inp; uint64_t last_out;
+} BNode;
+typedef struct {
+    uint8_t* buf; uint64_t len, cap;
+    BNode* stack; int depth, stack_cap; /* stack[0] = root; stack[i] reached by key[0..i) */
+    uint8_t* prev; uint32_t prev_len, prev_cap;
+    uint64_t last_addr, nkeys;
+    int error;
+} Builder;
+
+static void b_put(Builder* b, const void* p, uint64_t n) {
+    if (b->len + n > b->cap) {
+        while (b->len + n > b->cap) b->cap = b->cap * 2 + 4096;
+        b->buf = (uint8_t*)realloc(b->buf, b->cap);
+    }
+    memcpy(b->buf + b->len, p, n);
+    b->len += n;
+}
+static void b_put_int(Builder* b, uint64_t v, unsigned n) {
+    uint8_t t[8];
+    for (unsigned i = 0; i < n; ++i) t[i] = (uint8_t)(v >> (8 * i));
+    b_put(b, t, n);
+}
+static void node_reset(BNode* n) { n->is_final = 0; n->final_out = 0; n->ntr = 0; n->has_last = 0; }
+static void node_push(BNode* n, uint8_t inp, uint64_t out, uint64_t addr) {
+    if (n->ntr == n->cap) { n->cap = n->cap ? n->cap * 2 : 4; n->tr = (BTrans*)realloc(n->tr, n->cap * sizeof(BTrans)); }
+    n->tr[n->ntr].inp = inp; n->tr[n->ntr].out = out; n->tr[n->ntr].addr = addr; n->ntr++;
+}
+
+/* Writes one node, returns its address (index of its state byte). */
+static uint64_t emit_node(Builder* b, const BNode* n) {
+    if (n->is_final && n->ntr == 0 && n->final_out == 0) return 0; /* EMPTY_ADDRESS */
+    const uint64_t start = b->len;
+    if (!n->is_final && n->ntr == 1) {
+        const BTrans* t = &n->tr[0];
+        const int ci = common_idx(t->inp);
+        if (t->out == 0 && t->addr == b->last_addr && t->addr != 0 && start == t->addr + 1) { /* OneTransNext */
+            if (!ci) b_put(b, &t->inp, 1);
+            const uint8_t st = 0xC0 | (uint8_t)ci;
+            b_put(b, &st, 1);
+            return b->len - 1;
+        }
+        const uint64_t delta = t->addr ? start - t->addr : 0;
+        const unsigned osz = t->out ? pack_size(t->out) : 0, tsz = pack_size(delta);
+        if (osz) b_put_int(b, t->out, osz);
+        b_put_int(b, delta, tsz);
+        const uint8_t sizes = (uint8_t)((tsz << 4) | osz);
+        b_put(b, &sizes, 1);
+        if (!ci) b_put(b, &t->inp, 1);
+        const uint8_t st = 0x80 | (uint8_t)ci;
+        b_put(b, &st, 1);
+        return b->len - 1;
+    }
+    /* AnyTrans */
+    unsigned osz = 0, tsz = 1;
+    int any_out = n->is_final && n->final_out;
+    for (int i = 0; i < n->ntr; ++i) {
+        if (n->tr[i].out) any_out = 1;
+        const uint64_t delta = n->tr[i].addr ? start - n->tr[i].addr : 0;
+        const unsigned s = pack_size(delta);
+        if (s > tsz) tsz = s;
+    }
+    if (any_out) {
+        osz = n->is_final ? pack_size(n->final_out) : 1;
+        for (int i = 0; i < n->ntr; ++i) { const unsigned s = pack_size(n->tr[i].out); if (s > osz) osz = s; }
+    }
+    if (n->is_final && osz) b_put_int(b, n->final_out, osz);
+    if (osz) for (int i = n->ntr - 1; i >= 0; --i) b_put_int(b, n->tr[i].out, osz);
+    for (int i = n->ntr - 1; i >= 0; --i) b_put_int(b, n->tr[i].addr ? start - n->tr[i].addr : 0, tsz);
+    for (int i = n->ntr - 1; i >= 0; --i) b_put(b, &n->tr[i].inp, 1);
+    if (n->ntr > 32) {
+        uint8_t index[256];
+        memset(index, 255, 256);
+        for (int i = 0; i < n->ntr; ++i) index[n->tr[i].inp] = (uint8_t)i;
+        b_put(b, index, 256);
+    }
+    const uint8_t sizes = (uint8_t)((tsz << 4) | osz);
+    b_put(b, &sizes, 1);
+    uint8_t st = n->is_final ? 0x40 : 0;
+    if (n->ntr >= 1 && n->ntr <= 63) st |= (uint8_t)n->ntr;
+    else { const uint8_t cnt = n->ntr == 256 ? 1 : (uint8_t)n->ntr; b_put(b, &cnt, 1); }
+    b_put(b, &st, 1);
+    return b->len - 1;
+}
+
+/* Freezes stack[from+1 ..] bottom-up, linking each into its parent's pending transition. */
+static void compile_from(Builder* b, int from) {
+    while (b->depth > from) {
+        BNode* n = &b->stack[b->depth];
+        if (n->has_last) { b->error = 1; return; }
+        const uint64_t addr = emit_node(b, n);
+        if (addr) b->last_addr = addr;
+        node_reset(n);
+        b->depth--;
+        BNode* par = &b->stack[b->depth];
+        node_push(par, par->last_inp, par->last_out, addr);
+        par->has_last = 0;
+    }
+}
+
+static void builder_insert(Builder* b, const uint8_t* key, uint32_t len, uint64_t val) {
+    if (b->nkeys) { /* keys must be strictly increasing (MapBuilder::insert, buildindex.rs:41-43) */
+        const uint32_t mn = len < b->prev_len ? len : b->prev_len;
+        const int c = memcmp(b->prev, key, mn);
+        if (c > 0 || (c == 0 && b->prev_len >= len)) { b->error = 2; return; }
+    }
+    /* common prefix with the unfinished path, pushing output prefixes down (min under addition) */
+    uint32_t p = 0;
+    uint64_t out = val;
+    while (p < len && (int)p < b->depth && b->stack[p].has_last && b->stack[p].last_inp == key[p]) {
+        BNode* n = &b->stack[p];
+        const uint64_t common = n->last_out < out ? n->last_out : out;
+        const uint64_t push = n->last_out - common;
+        if (push) {
+            n->last_out = common;
+            BNode* c = &b->stack[p + 1];
+            if (c->is_final) c->final_out += push;
+            for (int i = 0; i < c->ntr; ++i) c->tr[i].out += push;
+            if (c->has_last) c->last_out += push;
+        }
+        out -= common;
+        ++p;
+    }
+    compile_from(b, (int)p);
+    if (b->error) return;
+    if ((int)(len + 1) > b->stack_cap) {
+        const int nc = (int)len + 16;
+        b->stack = (BNode*)realloc(b->stack, nc * sizeof(BNode));
+        memset(b->stack + b->stack_cap, 0, (nc - b->stack_cap) * sizeof(BNode));
+        b->stack_cap = nc;
+    }
+    if (p == len) { b->error = 2; return; } /* duplicate key */
+    for (uint32_t i = p; i < len; ++i) {
+        BNode* n = &b->stack[i];
+        n->has_last = 1; n->last_inp = key[i]; n->last_out = (i == p) ? out : 0;
+        node_reset(&b->stack[i + 1]);
+    }
+    b->depth = (int)len;
+    b->stack[len].is_final = 1;
+    if (len > b->prev_cap) { b->prev_cap = len + 16; b->prev = (uint8_t*)realloc(b->prev, b->prev_cap); }
+    memcpy(b->prev, key, len);
+    b->prev_len = len;
+    b->nkeys++;
+}
+
+/* Builds an fst Map image from sorted keys.  Returns a malloc'ed buffer (free with ref_free). */
+uint8_t* ref_fst_build(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values, uint64_t n,
+                       uint64_t* out_size) {
+    Builder b;
+    memset(&b, 0, sizeof b);
+    b.stack_cap = 64;
+    b.stack = (BNode*)calloc(b.stack_cap, sizeof(BNode));
+    b_put_int(&b, 2, 8); /* version */
+    b_put_int(&b, 0, 8); /* type: Map */
+    if (n && key_off[1] == key_off[0]) { /* the empty key */
+        b.stack[0].is_final = 1;
+        b.stack[0].final_out = values[0];
+        b.nkeys = 1;
+        for (uint64_t i = 1; i < n && !b.error; ++i)
+            builder_insert(&b, keys + key_off[i], (uint32_t)(key_off[i + 1] - key_off[i]), values[i]);
+    } else {
+        for (uint64_t i = 0; i < n && !b.error; ++i)
+            builder_insert(&b, keys + key_off[i], (uint32_t)(key_off[i + 1] - key_off[i]), values[i]);
+    }
+    uint8_t* result = NULL;
+    if (!b.error) {
+        compile_from(&b, 0);
+        uint64_t root = emit_node(&b, &b.stack[0]);
+        if (root == 0 && b.nkeys > 0) { /* a lone empty key with value 0: still needs a root byte */ }
+        b_put_int(&b, b.nkeys, 8);
+        b_put_int(&b, root, 8);
+        result = b.buf;
+        *out_size = b.len;
+    } else {
+        free(b.buf);
+        *out_size = 0;
+    }
+    for (int i = 0; i < b.stack_cap; ++i) free(b.stack[i].tr);
+    free(b.stack);
+    free(b.prev);
+    return result;
+}
+void ref_free(void* p) { free(p); }
+
+/* ------------------------------------------------------------------------------------ taxonomy */
+
+typedef struct {
+    uint64_t max_id, root, n;
+    int64_t* parent;   /* by id; -1 = no such taxon (TaxonList::ancestry, taxon.rs:158-163) */
+    uint32_t* snap_valid;  /* by id; 0xFFFFFFFF = None (TaxonTree::snapping, taxon.rs:251-301) */
+    uint32_t* snap_ranked;
+} RefTax;
+
+void* ref_tax_new(const uint64_t* ids, const uint64_t* parents, const uint8_t* rank, const uint8_t* valid, uint64_t n) {
+    RefTax* t = (RefTax*)calloc(1, sizeof(RefTax));
+    t->n = n;
+    for (uint64_t i = 0; i < n; ++i) if (ids[i] > t->max_id) t->max_id = ids[i];
+    const uint64_t m = t->max_id + 1;
+    t->parent = (int64_t*)malloc(m * sizeof(int64_t));
+    uint8_t* ok_v = (uint8_t*)calloc(m, 1), *ok_r = (uint8_t*)calloc(m, 1), *is_child = (uint8_t*)calloc(m, 1);
+    for (uint64_t i = 0; i < m; ++i) t->parent[i] = -1;
+    for (uint64_t i = 0; i < n; ++i) {
+        t->parent[ids[i]] = (int64_t)parents[i];
+        ok_v[ids[i]] = valid[i] != 0;
+        ok_r[ids[i]] = valid[i] != 0 && rank[i] != 0;
+        if (ids[i] != parents[i]) is_child[ids[i]] = 1;
+    }
+    int nroots = 0;
+    for (uint64_t i = 0; i < m; ++i) if (t->parent[i] >= 0 && !is_child[i]) { if (!nroots++) t->root = i; }
+    /* children lists (CSR) for the snapping DFS */
+    uint64_t* cnt = (uint64_t*)calloc(m + 1, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; ++i) if (ids[i] != parents[i] && parents[i] < m) cnt[parents[i] + 1]++;
+    for (uint64_t i = 0; i < m; ++i) cnt[i + 1] += cnt[i];
+    uint64_t* fill = (uint64_t*)malloc(m * sizeof(uint64_t));
+    memcpy(fill, cnt, m * sizeof(uint64_t));
+    uint64_t* child = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; ++i) if (ids[i] != parents[i] && parents[i] < m) child[fill[parents[i]]++] = ids[i];
+    t->snap_valid = (uint32_t*)malloc(m * sizeof(uint32_t));
+    t->snap_ranked = (uint32_t*)malloc(m * sizeof(uint32_t));
+    memset(t->snap_valid, 0xFF, m * sizeof(uint32_t));
+    memset(t->snap_ranked, 0xFF, m * sizeof(uint32_t));
+    if (nroots == 1) {
+        uint64_t* st = (uint64_t*)malloc((n + 2) * sizeof(uint64_t));
+        uint64_t sp = 0;
+        st[sp++] = t->root;
+        t->snap_valid[t->root] = ok_v[t->root] ? (uint32_t)t->root : (uint32_t)t->root;
+        t->snap_ranked[t->root] = (uint32_t)t->root;
+        uint8_t* seen = (uint8_t*)calloc(m, 1);
+        seen[t->root] = 1;
+        while (sp) {
+            const uint64_t cur = st[--sp];
+            for (uint64_t c = cnt[cur]; c < cnt[cur + 1]; ++c) {
+                const uint64_t ch = child[c];
+                if (seen[ch]) continue;
+                seen[ch] = 1;
+                t->snap_valid[ch] = ok_v[ch] ? (uint32_t)ch : t->snap_valid[cur];
+                t->snap_ranked[ch] = ok_r[ch] ? (uint32_t)ch : t->snap_ranked[cur];
+                st[sp++] = ch;
+            }
+        }
+        free(st);
+        free(seen);
+    } else {
+        t->n = 0; /* "More than one root!" / "There's no root!" */
+    }
+    free(ok_v); free(ok_r); free(is_child); free(cnt); free(fill); free(child);
+    return t;
+}
+void ref_tax_free(void* p) {
+    RefTax* t = (RefTax*)p;
+    if (!t) return;
+    free(t->parent); free(t->snap_valid); free(t->snap_ranked); free(t);
+}
+
+/* ----------------------------------------------------------------------------------- translate */
+
+static const char* table_aas(int table, const char** starts) {
+    static const struct { int id; const char* a; const char* s; } T[] = {
+        {1, "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "---M---------------M---------------M----------------------------"},
+        {2, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSS**VVVVAAAADDEEGGGG", "--------------------------------MMMM---------------M------------"},
+        {3, "FFLLSSSSYY**CCWWTTTTPPPPHHQQRRRRIIMMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "----------------------------------MM----------------------------"},
+        {4, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "--MM---------------M------------MMMM---------------M------------"},
+        {5, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSSSVVVVAAAADDEEGGGG", "---M----------------------------MMMM---------------M------------"},
+        {6, "FFLLSSSSYYQQCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {9, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG", "-----------------------------------M---------------M------------"},
+        {10, "FFLLSSSSYY**CCCWLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {11, "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "---M---------------M------------MMMM---------------M------------"},
+        {12, "FFLLSSSSYY**CC*WLLLSPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-------------------M---------------M----------------------------"},
+        {13, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNKKSSGGVVVVAAAADDEEGGGG", "---M------------------------------MM---------------M------------"},
+        {14, "FFLLSSSSYYY*CCWWLLLLPPPPHHQQRRRRIIIMTTTTNNNKSSSSVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {15, "FFLLSSSSYY*QCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {16, "FFLLSSSSYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {21, "FFLLSSSSYY**CCWWLLLLPPPPHHQQRRRRIIMMTTTTNNNKSSSSVVVVAAAADDEEGGGG", "-----------------------------------M---------------M------------"},
+        {22, "FFLLSS*SYY*LCC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "-----------------------------------M----------------------------"},
+        {23, "FF*LSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG", "--------------------------------M--M---------------M------------"},
+    };
+    for (unsigned i = 0; i < sizeof T / sizeof T[0]; ++i)
+        if (T[i].id == table) { *starts = T[i].s; return T[i].a; }
+    return NULL;
+}
+
+static inline int nt_ord(uint8_t c) { return c == 'T' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'G' ? 3 : 4; }
+
+/* translate_frame (translation.rs:136-144) of strand `fwd`/`rev` from offset f; returns length */
+static uint32_t translate_frame(const uint8_t* lut65, const uint8_t* nt, uint32_t n, int rev, uint32_t f, uint8_t* out) {
+    if (n <= f) return 0;
+    const uint32_t plen = (n - f) / 3;
+    for (uint32_t j = 0; j < plen; ++j) {
+        int a, b, c;
+        if (!rev) { a = nt_ord(nt[f + 3 * j]); b = nt_ord(nt[f + 3 * j + 1]); c = nt_ord(nt[f + 3 * j + 2]); }
+        else {
+            const uint32_t p = n - 1 - f - 3 * j; /* reverse strand = complement of the reversed read */
+            a = nt_ord(nt[p]); b = nt_ord(nt[p - 1]); c = nt_ord(nt[p - 2]);
+            if (a < 4) a ^= 2;
+            if (b < 4) b ^= 2;
+            if (c < 4) c ^= 2;
+        }
+        out[j] = (a | b | c) & 4 ? lut65[64] : lut65[16 * a + 4 * b + c];
+    }
+    return plen;
+}
+
+/* ---------------------------------------------------------------------------------- seedextend */
+
+/* seedextend.rs:94-149 statement by statement; t has len+1 entries (sentinel 0 appended by caller).
+ * Appends the selected ids to out; returns the new count. */
+static uint32_t seedextend(const uint32_t* t, uint32_t tlen, uint32_t S, uint32_t G, uint32_t* out, uint32_t m) {
+    uint32_t start = 0, end = 1, last = t[0], same = 1, smax = 1;
+    while (end < tlen) {
+        if (last == t[end]) { same++; end++; continue; }
+        if (last == 0 && same > G) {
+            if (smax >= S && end - same > start) for (uint32_t i = start; i < end - same; ++i) out[m++] = t[i];
+            start = end; last = t[end]; same = 1; smax = 1; end++;
+            continue;
+        }
+        if (last == 0 && end - start == same) { end++; start = end; continue; }
+        if (last != 0 && same > smax) smax = same;
+        last = t[end]; same = 1; end++;
+    }
+    if (smax >= S) {
+        if (last == 0) end -= same;
+        for (uint32_t i = start; i < end; ++i) out[m++] = t[i];
+    }
+    return m;
+}
+
+/* ----------------------------------------------------------------------------------- aggregate */
+
+typedef struct { uint32_t id; float value; int first_child, next_sibling, nchildren, linked; } TNode;
+typedef struct {
+    uint32_t* keys; int* vals; uint32_t cap; /* open-addressing id -> node index */
+    TNode* nodes; int nnodes, nodes_cap;
+    uint32_t* queue; int qcap;
+} AggScratch;
+
+static int map_get(AggScratch* s, uint32_t id) {
+    uint32_t h = (id * 2654435761u) & (s->cap - 1);
+    while (s->keys[h] != 0xFFFFFFFFu) { if (s->keys[h] == id) return s->vals[h]; h = (h + 1) & (s->cap - 1); }
+    return -1;
+}
+static void map_put(AggScratch* s, uint32_t id, int v) {
+    uint32_t h = (id * 2654435761u) & (s->cap - 1);
+    while (s->keys[h] != 0xFFFFFFFFu) h = (h + 1) & (s->cap - 1);
+    s->keys[h] = id; s->vals[h] = v;
+}
+static int node_new(AggScratch* s, uint32_t id, float value) {
+    if (s->nnodes == s->nodes_cap) { s->nodes_cap *= 2; s->nodes = (TNode*)realloc(s->nodes, s->nodes_cap * sizeof(TNode)); }
+    TNode* n = &s->nodes[s->nnodes];
+    n->id = id; n->value = value; n->first_child = -1; n->next_sibling = -1; n->nchildren = 0; n->linked = 0;
+    map_put(s, id, s->nnodes);
+    return s->nnodes++;
+}
+
+/* subtree sums after collapsing, computed on the fly: value(collapsed child) = sum of its subtree */
+static float subtree_sum(const AggScratch* s, int n) {
+    float v = s->nodes[n].value;
+    for (int c = s->nodes[n].first_child; c >= 0; c = s->nodes[c].next_sibling) v += subtree_sum(s, c);
+    return v;
+}
+
+/* taxa2agg for one record (taxa2agg.rs:159-181).  ids: the record's taxon ids (zeros allowed).
+ * Returns the snapped taxon id, 1 for an empty record, 0xFFFFFFFE on UnknownTaxon (bad in *bad). */
+static uint32_t aggregate_record(const RefTax* tax, AggScratch* s, const uint32_t* ids, uint32_t n, int strategy,
+                                 float factor, float lower_bound, int ranked, uint32_t* bad) {
+    /* count + filter (agg/mod.rs:27-44) into the node table: input taxa first */
+    uint32_t need = 64;
+    while (need < 8 * (n + 8)) need <<= 1;
+    if (need > s->cap) {
+        s->cap = need;
+        s->keys = (uint32_t*)realloc(s->keys, s->cap * sizeof(uint32_t));
+        s->vals = (int*)realloc(s->vals, s->cap * sizeof(int));
+    }
+    memset(s->keys, 0xFF, s->cap * sizeof(uint32_t));
+    s->nnodes = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (ids[i] == 0) continue;
+        const int k = map_get(s, ids[i]);
+        if (k >= 0) s->nodes[k].value += 1.0f; else node_new(s, ids[i], 1.0f);
+    }
+    /* lower bound: drop by zeroing and compacting */
+    int kept = 0;
+    for (int i = 0; i < s->nnodes; ++i) if (s->nodes[i].value >= lower_bound) kept++;
+    if (kept == 0) return 1u; /* literal "1" (taxa2agg.rs:174-175) */
+    if (kept != s->nnodes) {
+        memset(s->keys, 0xFF, s->cap * sizeof(uint32_t));
+        int w = 0;
+        for (int i = 0; i < s->nnodes; ++i)
+            if (s->nodes[i].value >= lower_bound) { s->nodes[w] = s->nodes[i]; map_put(s, s->nodes[w].id, w); ++w; }
+        s->nnodes = w;
+    }
+    const int ninput = s->nnodes;
+    uint32_t result;
+    if (strategy == 2) { /* MRTL, rmq/rtl.rs:39-57: last maximum in iteration order wins */
+        float best = -1.0f;
+        result = 0;
+        for (int i = 0; i < ninput; ++i) {
+            float c = s->nodes[i].value;
+            uint64_t next = s->nodes[i].id;
+            for (;;) {
+                if (next == tax->root) break;
+                if (next > tax->max_id || tax->parent[next] < 0) break;
+                const uint64_t anc = (uint64_t)tax->parent[next];
+                const int k = anc <= 0xFFFFFFFEull ? map_get(s, (uint32_t)anc) : -1;
+                if (k >= 0 && k < ninput) c += s->nodes[k].value;
+                if (anc == next) break;
+                next = anc;
+            }
+            if (next != tax->root) { *bad = (uint32_t)next; return 0xFFFFFFFEu; }
+            if (c >= best) { best = c; result = s->nodes[i].id; }
+        }
+    } else {
+        /* Tree::new (tree/mod.rs:29-48): link every taxon to its parent, queueing new ancestors */
+        if (s->qcap < 64) { s->qcap = 64; s->queue = (uint32_t*)realloc(s->queue, s->qcap * sizeof(uint32_t)); }
+        int qh = 0, qt = 0;
+        for (int i = 0; i < ninput; ++i) {
+            if (qt == s->qcap) { s->qcap *= 2; s->queue = (uint32_t*)realloc(s->queue, s->qcap * sizeof(uint32_t)); }
+            s->queue[qt++] = s->nodes[i].id;
+        }
+        while (qh < qt) {
+            const uint32_t id = s->queue[qh++];
+            if (id > tax->max_id || tax->parent[id] < 0) { *bad = id; return 0xFFFFFFFEu; }
+            const uint64_t par = (uint64_t)tax->parent[id];
+            if (par == id) continue;
+            if (s->nnodes * 4 >= (int)s->cap) { /* grow the map */
+                s->cap *= 2;
+                s->keys = (uint32_t*)realloc(s->keys, s->cap * sizeof(uint32_t));
+                s->vals = (int*)realloc(s->vals, s->cap * sizeof(int));
+                memset(s->keys, 0xFF, s->cap * sizeof(uint32_t));
+                for (int i = 0; i < s->nnodes; ++i) map_put(s, s->nodes[i].id, i);
+            }
+            int pk = map_get(s, (uint32_t)par);
+            if (pk < 0) pk = node_new(s, (uint32_t)par, 0.0f);
+            if (s->nodes[pk].nchildren == 0) { /* !tree.contains_key(parent): visit the parent too */
+                if (qt == s->qcap) { s->qcap *= 2; s->queue = (uint32_t*)realloc(s->queue, s->qcap * sizeof(uint32_t)); }
+                s->queue[qt++] = (uint32_t)par;
+            }
+            const int me = map_get(s, id);
+            if (!s->nodes[me].linked) { /* siblings is a HashSet: inserting twice is a no-op */
+                s->nodes[me].linked = 1;
+                s->nodes[me].next_sibling = s->nodes[pk].first_child;
+                s->nodes[pk].first_child = me;
+                s->nodes[pk].nchildren++;
+            }
+        }
+        int root = map_get(s, (uint32_t)tax->root);
+        if (root < 0) root = node_new(s, (uint32_t)tax->root, 0.0f); /* cannot happen for a valid tree */
+        /* collapse from the root (tree/mod.rs:71-86) */
+        int base = root;
+        while (s->nodes[base].nchildren == 1) base = s->nodes[base].first_child;
+        if (strategy == 1) { /* hybrid, tree/mix.rs:43-64 */
+            float bval = subtree_sum(s, root);
+            for (;;) {
+                int best = -1;
+                float bm = 0.0f;
+                for (int c = s->nodes[base].first_child; c >= 0; c = s->nodes[c].next_sibling) {
+                    const float v = subtree_sum(s, c);
+                    if (best < 0 || v >= bm) { best = c; bm = v; }
+                }
+                if (best < 0) break;
+                if (bm / bval < factor) break;
+                base = best;
+                while (s->nodes[base].nchildren == 1) base = s->nodes[base].first_child;
+                bval = bm;
+            }
+        }
+        result = s->nodes[base].id;
+    }
+    const uint32_t sn = ranked ? tax->snap_ranked[result] : tax->snap_valid[result];
+    if (sn == 0xFFFFFFFFu) { *bad = result; return 0xFFFFFFFEu; }
+    return sn;
+}
+
+/* ------------------------------------------------------------------------------------ pipeline */
+
+typedef struct {
+    int table, methionine, one_on_one, seedextend, min_seed_size, max_gap_size, strategy;
+    float factor, lower_bound;
+    int ranked_only, k;
+} RefOpts;
+
+typedef struct {
+    const uint8_t* img; uint64_t img_size;
+    const RefTax* tax;
+    RefOpts o;
+    const uint8_t* nt; const uint64_t* read_off; const uint64_t* group_off; uint64_t ngroups;
+    uint32_t* out;
+    uint64_t next; pthread_mutex_t* mu;
+    uint64_t lookups, hits;
+    uint8_t lut[65];
+    int error; uint32_t bad;
+    int lookups_only;
+} Job;
+
+static void* worker(void* arg) {
+    Job* job = (Job*)arg;
+    const RefOpts* o = &job->o;
+    AggScratch s;
+    memset(&s, 0, sizeof s);
+    s.nodes_cap = 256;
+    s.nodes = (TNode*)malloc(s.nodes_cap * sizeof(TNode));
+    uint32_t cap = 4096;
+    uint8_t* pep = (uint8_t*)malloc(cap);
+    uint32_t* ids = (uint32_t*)malloc((cap + 1) * sizeof(uint32_t));
+    uint32_t kept_cap = 8192, *kept = (uint32_t*)malloc(kept_cap * sizeof(uint32_t));
+    uint64_t lookups = 0, hits = 0;
+    const uint64_t chunk = 20; /* 240 records = 20 pairs x 12 frame records (prot2kmer2lca.rs:97-104) */
+    for (;;) {
+        pthread_mutex_lock(job->mu);
+        const uint64_t g0 = job->next;
+        job->next += chunk;
+        pthread_mutex_unlock(job->mu);
+        if (g0 >= job->ngroups) break;
+        const uint64_t g1 = g0 + chunk < job->ngroups ? g0 + chunk : job->ngroups;
+        for (uint64_t g = g0; g < g1; ++g) {
+            uint32_t m = 0;
+            int present = 0;
+            for (uint64_t r = job->group_off[g]; r < job->group_off[g + 1]; ++r) {
+                const uint8_t* nt = job->nt + job->read_off[r];
+                const uint32_t n = (uint32_t)(job->read_off[r + 1] - job->read_off[r]);
+                if (n / 3 + 2 > cap) {
+                    cap = n / 3 + 64;
+                    pep = (uint8_t*)realloc(pep, cap);
+                    ids = (uint32_t*)realloc(ids, (cap + 1) * sizeof(uint32_t));
+                }
+                for (int fr = 0; fr < 6; ++fr) {
+                    const uint32_t plen = translate_frame(job->lut, nt, n, fr >= 3, (uint32_t)(fr % 3), pep);
+                    if (plen < (uint32_t)o->k) continue; /* record dropped, header and all (:172) */
+                    present = 1;
+                    uint32_t cnt = 0;
+                    for (uint32_t i = 0; i + o->k <= plen; ++i) {
+                        uint64_t v;
+                        ++lookups;
+                        if (ref_fst_get(job->img, job->img_size, pep + i, (uint32_t)o->k, &v)) { ids[cnt++] = (uint32_t)v; ++hits; }
+                        else if (o->one_on_one) ids[cnt++] = 0;
+                    }
+                    if (job->lookups_only) continue;
+                    if (m + cnt + 1 > kept_cap) { kept_cap = 2 * (m + cnt + 1); kept = (uint32_t*)realloc(kept, kept_cap * sizeof(uint32_t)); }
+                    if (o->seedextend) {
+                        ids[cnt] = 0; /* sentinel (seedextend.rs:99) */
+                        m = seedextend(ids, cnt + 1, (uint32_t)o->min_seed_size, (uint32_t)o->max_gap_size, kept, m);
+                    } else {
+                        memcpy(kept + m, ids, cnt * sizeof(uint32_t));
+                        m += cnt;
+                    }
+                }
+            }
+            if (job->lookups_only) continue;
+            uint32_t res = 0xFFFFFFFFu; /* no record at all */
+            if (present) {
+                uint32_t bad = 0;
+                res = aggregate_record(job->tax, &s, kept, m, o->strategy, o->factor, o->lower_bound, o->ranked_only, &bad);
+                if (res == 0xFFFFFFFEu) { job->error = 1; job->bad = bad; res = 0xFFFFFFFFu; }
+            }
+            job->out[g] = res;
+        }
+    }
+    pthread_mutex_lock(job->mu);
+    job->lookups += lookups;
+    job->hits += hits;
+    pthread_mutex_unlock(job->mu);
+    free(s.keys); free(s.vals); free(s.nodes); free(s.queue); free(pep); free(ids); free(kept);
+    return NULL;
+}
+
+/* translate -a | prot2kmer2lca [-o] | [seedextend] | uniq -d | taxa2agg over `threads` threads.
+ * Returns 0, -1 on an unknown table, -4 on UnknownTaxon (*bad_taxon set). */
+int ref_classify(const uint8_t* img, uint64_t img_size, const void* tax, const RefOpts* opts, const uint8_t* nt,
+                 const uint64_t* read_off, const uint64_t* group_off, uint64_t ngroups, uint32_t* out, int threads,
+                 int lookups_only, uint64_t* n_lookups, uint64_t* n_hits, uint32_t* bad_taxon) {
+    const char* starts;
+    const char* aas = table_aas(opts->table, &starts);
+    if (!aas) return -1;
+    Job job;
+    memset(&job, 0, sizeof job);
+    for (int i = 0; i < 64; ++i) job.lut[i] = (opts->methionine && starts[i] == 'M') ? 'M' : (uint8_t)aas[i];
+    job.lut[64] = '-';
+    pthread_mutex_t mu;
+    pthread_mutex_init(&mu, NULL);
+    job.img = img; job.img_size = img_size; job.tax = (const RefTax*)tax; job.o = *opts;
+    job.nt = nt; job.read_off = read_off; job.group_off = group_off; job.ngroups = ngroups; job.out = out;
+    job.mu = &mu; job.lookups_only = lookups_only;
+    if (threads < 1) threads = 1;
+    pthread_t* th = (pthread_t*)malloc(threads * sizeof(pthread_t));
+    for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, worker, &job);
+    for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+    free(th);
+    pthread_mutex_destroy(&mu);
+    if (n_lookups) *n_lookups = job.lookups;
+    if (n_hits) *n_hits = job.hits;
+    if (job.error) { if (bad_taxon) *bad_taxon = job.bad; return -4; }
+    return 0;
+}
+
+/* Single-record entry points for the parity tests of the port against the Python oracle. */
+uint32_t ref_seedextend(const uint32_t* ids, uint32_t n, uint32_t S, uint32_t G, uint32_t* out) {
+    uint32_t* t = (uint32_t*)malloc((n + 1) * sizeof(uint32_t));
+    memcpy(t, ids, n * sizeof(uint32_t));
+    t[n] = 0;
+    const uint32_t m = seedextend(t, n + 1, S, G, out, 0);
+    free(t);
+    return m;
+}
+uint32_t ref_aggregate(const void* tax, const uint32_t* ids, uint32_t n, int strategy, float factor, float lower_bound,
+                       int ranked, uint32_t* bad) {
+    AggScratch s;
+    memset(&s, 0, sizeof s);
+    s.nodes_cap = 256;
+    s.nodes = (TNode*)malloc(s.nodes_cap * sizeof(TNode));
+    const uint32_t r = aggregate_record((const RefTax*)tax, &s, ids, n, strategy, factor, lower_bound, ranked, bad);
+    free(s.keys); free(s.vals); free(s.nodes); free(s.queue);
+    return r;
+}
+uint32_t ref_translate(int table, int methionine, const uint8_t* nt, uint32_t n, int frame /*0..5*/, uint8_t* out) {
+    const char* starts;
+    const char* aas = table_aas(table, &starts);
+    if (!aas) return 0xFFFFFFFFu;
+    uint8_t lut[65];
+    for (int i = 0; i < 64; ++i) lut[i] = (methionine && starts[i] == 'M') ? 'M' : (uint8_t)aas[i];
+    lut[64] = '-';
+    return translate_frame(lut, nt, n, frame >= 3, (uint32_t)(frame % 3), out);
+}

@@ -328,3 +328,33 @@ def test_classify_dev_entry_matches_host_entry(capi, world):
                             torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32), host)
+
+
+def test_synthetic_generators_match_numpy_mirror(capi):
+    """The device-side workload generator (bench aid) against oracle/synth.py, bit for bit."""
+    torch = pytest.importorskip("torch")
+    from oracle import synth
+    taxa = datagen.make_taxonomy(300, seed=51)
+    pre = synth.Preorder(taxa)
+    gtax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(taxa))
+    spec = capi.SynthSpec(seed=77, n_proteins=300, protein_len=120, home_pct=70, ancestor_pct=20)
+    gidx = capi.Index.build_synthetic(spec, gtax)
+    keys, vals = synth.build_index(77, 300, 120, 70, 20, pre)
+    assert gidx.info().n_keys == len(keys)
+    taxa_out, toff, _ = capi.kmer_lookup(gidx, keys.reshape(-1), np.arange(0, 9 * len(keys) + 1, 9, dtype=np.uint64), True)
+    assert np.array_equal(taxa_out.astype(np.uint64), vals)
+    for read_len, hit_pct in ((150, 70), (100, 100), (151, 0)):
+        npairs = 257
+        want = synth.reads(77, 300, 120, 5, 11, npairs, read_len, hit_pct)
+        d = torch.zeros(npairs * 2 * read_len, dtype=torch.uint8, device="cuda")
+        capi.synth_reads_dev(spec, 5, 11, npairs, read_len, hit_pct, d.data_ptr())
+        torch.cuda.synchronize()
+        got = d.cpu().numpy().reshape(npairs * 2, read_len)
+        assert np.array_equal(got, want), (read_len, hit_pct)
+    # the reads really come from the proteome: the pipeline classifies most hit pairs below the root
+    reads = synth.reads(77, 300, 120, 5, 0, 200, 150, 100)
+    nt = reads.reshape(-1)
+    off = np.arange(0, len(nt) + 1, 150, dtype=np.uint64)
+    goff = np.arange(0, 401, 2, dtype=np.uint64)
+    got, _ = capi.classify_reads(gidx, gtax, capi.default_opts(min_seed_size=3, strategy=capi.AGG_MRTL), nt, off, goff)
+    assert (got != 1).mean() > 0.8

@@ -31,6 +31,7 @@ SYMBOLS = [
     "umgap_seedextend", "umgap_aggregate",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
+    "umgap_kernel_timing", "umgap_kernel_times",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
 
@@ -349,3 +350,15 @@ def synth_reads_dev(spec: SynthSpec, read_seed: int, first_pair: int, npairs: in
     _check(load_library().umgap_synth_reads_dev(
         C.byref(spec), C.c_uint64(read_seed), C.c_uint64(first_pair), C.c_uint64(npairs),
         C.c_uint32(read_len), C.c_uint32(hit_pct), C.c_void_p(nt_ptr), C.c_void_p(stream)))
+
+
+def kernel_timing(enable: bool) -> None:
+    _check(load_library().umgap_kernel_timing(C.c_int(int(enable))))
+
+
+def kernel_times():
+    """(lookup_ms, lookup_launches, classify_ms, classify_launches) since the last call."""
+    a, b = C.c_double(), C.c_double()
+    na, nb = C.c_uint64(), C.c_uint64()
+    _check(load_library().umgap_kernel_times(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+    return a.value, na.value, b.value, nb.value

@@ -356,6 +356,44 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
         UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", o->strategy);
 }
 
+// ---- optional per-launch timing (umgap_kernel_timing) --------------------------------------------
+namespace {
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int kind;  // 0 lookup, 1 classify
+};
+bool g_timing = false;
+std::vector<TimedLaunch> g_launches;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    UMGAP_CUDA(cudaEventCreate(&e));
+    return e;
+}
+struct LaunchTimer {
+    cudaStream_t st;
+    TimedLaunch t{};
+    bool on;
+    LaunchTimer(int kind, cudaStream_t s) : st(s), on(g_timing) {
+        if (!on) return;
+        t.kind = kind;
+        t.a = take_event();
+        t.b = take_event();
+        UMGAP_CUDA(cudaEventRecord(t.a, st));
+    }
+    void stop() {
+        if (!on) return;
+        UMGAP_CUDA(cudaEventRecord(t.b, st));
+        g_launches.push_back(t);
+    }
+};
+}  // namespace
+
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
                                     const uint8_t* nt_dev, const uint64_t* read_off_dev,
                                     uint64_t nreads, uint32_t* ids_dev, cudaStream_t st) {
@@ -364,6 +402,7 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     make_code_lut(idx, o->table, o->methionine, lut);
     const TableView tv = idx->view();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kLookupWarps), 148ull * 32);
+    LaunchTimer timer(0, st);
     switch (idx->k) {
 #define UMGAP_CASE(KK)                                                                           \
     case KK:                                                                                     \
@@ -378,6 +417,7 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
             UMGAP_FAIL(UMGAP_ERR_INVALID, "unsupported k %d", idx->k);
     }
     UMGAP_CUDA(cudaGetLastError());
+    timer.stop();
 }
 
 static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
@@ -387,10 +427,12 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
                             cudaStream_t st) {
     if (!ngroups) return;
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ngroups, kAggWarps), 148ull * 64);
+    LaunchTimer timer(1, st);
     classify_kernel<<<blocks, kAggWarps * 32, 0, st>>>(tax->view, make_params(idx, o), ids_dev,
                                                        read_off_dev, group_off_dev, ngroups,
                                                        scratch_dev, out_dev, err);
     UMGAP_CUDA(cudaGetLastError());
+    timer.stop();
 }
 
 static void raise_dev_error(const DevError& e) {
@@ -398,6 +440,33 @@ static void raise_dev_error(const DevError& e) {
 }
 
 extern "C" {
+
+int umgap_kernel_timing(int enable) {
+    g_timing = enable != 0;
+    return UMGAP_OK;
+}
+
+int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
+                       uint64_t* classify_launches) {
+    return guarded([&] {
+        double ms[2] = {0, 0};
+        uint64_t cnt[2] = {0, 0};
+        for (TimedLaunch& t : g_launches) {
+            UMGAP_CUDA(cudaEventSynchronize(t.b));
+            float e = 0;
+            UMGAP_CUDA(cudaEventElapsedTime(&e, t.a, t.b));
+            ms[t.kind] += e;
+            cnt[t.kind]++;
+            g_event_pool.push_back(t.a);
+            g_event_pool.push_back(t.b);
+        }
+        g_launches.clear();
+        if (lookup_ms) *lookup_ms = ms[0];
+        if (lookup_launches) *lookup_launches = cnt[0];
+        if (classify_ms) *classify_ms = ms[1];
+        if (classify_launches) *classify_launches = cnt[1];
+    });
+}
 
 void umgap_pipeline_opts_default(umgap_pipeline_opts* o) {
     if (!o) return;
