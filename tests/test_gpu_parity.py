@@ -358,3 +358,46 @@ def test_synthetic_generators_match_numpy_mirror(capi):
     goff = np.arange(0, 401, 2, dtype=np.uint64)
     got, _ = capi.classify_reads(gidx, gtax, capi.default_opts(min_seed_size=3, strategy=capi.AGG_MRTL), nt, off, goff)
     assert (got != 1).mean() > 0.8
+
+
+def test_tryptic_lookup_matches_oracle(capi, world, tmp_path):
+    """prot2tryp2lca: digest + length/keep/drop filters + variable-length lookup (prot2tryp2lca.rs:105-134)."""
+    rng = random.Random(61)
+    proteins = world["proteins"]
+    # tryptic index: digest the proteome, keep 5..50, value = a taxon id
+    ids = [t[0] for t in world["otax"].by_id if t is not None]
+    tryp = {}
+    for p in proteins:
+        for pep in olookup.tryptic_filter(olookup.tryptic_digest(p), 5, 50):
+            tryp.setdefault(pep.encode(), rng.choice(ids))
+    keys = sorted(tryp)
+    gidx = capi.Index.from_pairs(keys, [tryp[k] for k in keys], k=0)
+    assert gidx.info().n_keys == len(keys) and gidx.info().k == 0
+    # same table through the fst loader
+    path = tmp_path / "tryp.fst"
+    path.write_bytes(fstv2.build([(k, tryp[k]) for k in keys]))
+    fidx = capi.Index.load_fst(str(path), k=0)
+    assert fidx.info().n_keys == len(keys)
+    lines = []
+    for p in proteins[:50]:
+        s = list(p)
+        for _ in range(4):
+            s[rng.randrange(len(s))] = rng.choice("*KRPX")
+        lines.append("".join(s))
+    lines += ["", "*", "K", "KP", "KKKK", "AAAAAKPAAAAAR*", "*" * 7, "MKR" * 30, "A" * 120, proteins[51][:200] + "*" + proteins[52][:150],
+              "MVRFKHVQLVKLNSLMFSKEIFTRRVLGYERPLEEIKEAYSKLVHQYHPDRNPNEGRA"]  # shape of prot2tryp.rs:22-36
+    aa, off = capi.pack_strings([l.encode() for l in lines])
+    oidx = olookup.DictIndex(tryp)
+    for idx in (gidx, fidx):
+        for one, mn, mx, keep, drop in [(False, 5, 50, "", ""), (True, 5, 50, "", ""), (True, 9, 45, "", ""), (False, 1, 7, "", ""),
+                                        (True, 5, 50, "L", ""), (True, 5, 50, "", "CW"), (False, 6, 30, "AE", "P")]:
+            taxa, toff = capi.tryp_lookup(idx, aa, off, mn, mx, keep, drop, one)
+            for i, line in enumerate(lines):
+                want = olookup.prot2tryp2lca([("h", [line])], oidx, one, mn, mx, keep, drop)[0][1]
+                got = [int(x) for x in taxa[int(toff[i]):int(toff[i + 1])]]
+                assert got == want, (one, mn, mx, keep, drop, line)
+    # the digest closed form equals the reference's double regex pass on every test line
+    for line in lines:
+        assert olookup.tryptic_digest(line) == olookup.tryptic_digest_regex(line)
+    with pytest.raises(capi.UmgapError):
+        capi.tryp_lookup(world["gidx"], aa, off)   # a k-mer table is not a peptide table

@@ -1,0 +1,151 @@
+"""CPU-side checks that need no GPU: the C ABI library loads and exports every declared symbol, the
+header and the ctypes mirror agree, compute entry points fail loudly without a device, the host-only
+CLI commands match the oracle's stream model, and the read partitioner works across 2 gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UMGAP = os.path.join(ROOT, "umgap_b200", "bin", "umgap")
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not (os.path.exists(os.path.join(ROOT, "umgap_b200", "lib", "libumgap_gpu.so")) and os.path.exists(UMGAP)):
+        subprocess.run(["make", "-j8", "all"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
+    from umgap_b200 import capi
+    return capi
+
+
+def test_library_exports_every_header_symbol(built):
+    header = open(os.path.join(ROOT, "include", "umgap_gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(umgap_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    assert sorted(built.SYMBOLS) == declared
+    lib = built.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.umgap_abi_version() == 1
+
+
+def test_structs_match_header_layout(built):
+    import ctypes as C
+    assert C.sizeof(built.PipelineOpts) == 40
+    assert C.sizeof(built.SynthSpec) == 32
+    o = built.default_opts()
+    assert (o.table, o.one_on_one, o.seedextend, o.min_seed_size, o.max_gap_size, o.strategy) == (1, 1, 1, 2, 0, 1)
+    assert abs(o.factor - 0.25) < 1e-9 and o.lower_bound == 0.0
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the compute entry points must fail, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert built.device_count() < 0
+    nt, off = built.pack_strings([b"ACGTACGTAC"])
+    with pytest.raises(built.UmgapError) as e:
+        built.translate(nt, off)
+    assert e.value.code == -3
+    with pytest.raises(built.UmgapError):
+        built.Index.from_pairs([b"ACDEFGHIK"], [5])
+    with pytest.raises(built.UmgapError):
+        built.Taxonomy.from_arrays([1], [1], [0], [1])
+
+
+def _run(args, stdin=b""):
+    p = subprocess.run([UMGAP] + args, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return p.returncode, p.stdout.decode(), p.stderr.decode()
+
+
+def test_cli_host_commands_match_oracle_streams(built, tmp_path):
+    from oracle import fasta as ofasta, pipeline as opipe
+    rc, out, _ = _run(["-V"])
+    assert rc == 0 and out == "umgap 1.1.1\n"       # scripts/umgap-analyse.sh:106-109 probes this
+    text = ">header1/1\n1\n2\n>header1/2\n3\n>x\n>y/1\n\n9\n>y/2\n>header1/1\n4\n"
+    for flags, kw in [([], {}), (["-d", "/"], {"delimiter": "/"}), (["-d", "/", "-s", " "], {"delimiter": "/", "separator": " "}),
+                      (["-d", "er", "-w"], {"delimiter": "er", "wrap": True})]:
+        rc, out, err = _run(["uniq"] + flags, text.encode())
+        assert rc == 0 and out == opipe.uniq_text(text, **kw), (flags, err)
+    # uniq.rs:22-40 doc example
+    rc, out, _ = _run(["uniq", "-d", "/"], b">header1/1\nsequence1\n>header1/2\nsequence2\n")
+    assert out == ">header1\nsequence1\nsequence2\n"
+    long_text = ">w\n" + "A" * 150 + "\n" + "C" * 10 + "\n"
+    rc, out, _ = _run(["uniq", "-s", "", "-w"], long_text.encode())
+    assert out == opipe.uniq_text(long_text, separator="", wrap=True)
+    rc, out, err = _run(["uniq"], b"no header\n")
+    assert rc == 1 and err == "Error: Expected > at beginning of fasta header.\n" and out == ""
+    f1, f2 = tmp_path / "a.fq", tmp_path / "b.fq"
+    q1 = "@r1/1\nACGT\nAC\n+\nIIII\nII\n@r2/1\nGGGG\n+\nIIII\n@r3/1\nTT\n+\nII\n"
+    q2 = "@r1/2\nTTTT\n+r1/2\nIIII\n@r2/2\nCCCC\n+\nIIII\n"
+    f1.write_text(q1)
+    f2.write_text(q2)
+    rc, out, _ = _run(["fastq2fasta", str(f1), str(f2)])
+    assert rc == 0 and out == ofasta.fastq2fasta([q1, q2])
+    rc, _, err = _run(["taxa2agg", "-m", "tree", "-a", "mrtl", "taxons.tsv"])
+    assert rc == 1 and "cannot be combined" in err   # taxa2agg.rs:134-138
+    rc, _, err = _run(["translate", "-a", "-f", "1"])
+    assert rc == 1 and "cannot be used with" in err   # translate.rs:52
+    rc, _, err = _run(["nonsense"])
+    assert rc == 1 and err.startswith("Error:")
+
+
+def test_split_groups_properties():
+    from umgap_b200.partition import slice_batch, split_groups
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        nreads = int(rng.integers(0, 200))
+        lens = rng.integers(0, 300, size=nreads)
+        read_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        cuts = np.sort(rng.choice(np.arange(1, max(nreads, 1)), size=min(max(nreads - 1, 0), int(rng.integers(0, 40))), replace=False)) if nreads > 1 else []
+        group_off = np.array([0] + list(cuts) + [nreads], dtype=np.uint64) if nreads else np.array([0], dtype=np.uint64)
+        nt = rng.integers(65, 70, size=int(read_off[-1]), dtype=np.uint8)
+        for world in (1, 2, 3, 8):
+            parts = split_groups(group_off, read_off, world)
+            assert parts[0][0] == 0 and parts[-1][1] == len(group_off) - 1
+            assert all(a <= b for a, b in parts) and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            cat = b"".join(bytes(slice_batch(nt, read_off, group_off, a, b)[0]) for a, b in parts)
+            assert cat == bytes(nt)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from umgap_b200.partition import classify_partitioned
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+rng = np.random.default_rng(7)
+lens = rng.integers(27, 200, size=501)
+read_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+group_off = np.array(list(range(0, 501, 2)) + [501], dtype=np.uint64)
+nt = rng.integers(65, 70, size=int(read_off[-1]), dtype=np.uint8)
+def fake_classify(nt_s, roff, goff):   # stands in for umgap_classify_reads on this rank's GPU
+    return np.array([int(nt_s[int(roff[int(goff[g])]):int(roff[int(goff[g + 1])])].astype(np.uint64).sum() % 100003)
+                     for g in range(len(goff) - 1)], dtype=np.uint32)
+got = classify_partitioned(fake_classify, nt, read_off, group_off, rank, 2, dist)
+want = fake_classify(nt, read_off, group_off)
+assert np.array_equal(got, want), "rank %d: partitioned result differs" % rank
+t = __import__("torch").tensor([float(rank + 1)])
+dist.all_reduce(t, op=dist.ReduceOp.MAX)      # the bench's max-over-ranks timing reduction
+assert t.item() == 2.0
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_partitioned_classification_two_gloo_ranks(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for r in range(2)]
+    for r, p in enumerate(procs):
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0, err.decode()[-2000:]
+        assert out.decode().strip() == f"ok {r}"

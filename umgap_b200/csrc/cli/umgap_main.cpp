@@ -1,0 +1,750 @@
+// `umgap` command line on top of libumgap_gpu.so: the reference's argv surface and FASTA stream
+// formats for the hot-path subcommands (src/main.rs:8-63; flags per SURVEY Appendix C).
+//
+//   translate      src/commands/translate.rs:46-133      -> umgap_translate
+//   prot2kmer2lca  src/commands/prot2kmer2lca.rs:70-193  -> umgap_index_load_fst + umgap_kmer_lookup
+//   prot2tryp2lca  src/commands/prot2tryp2lca.rs:41-140  -> umgap_index_load_fst(k=0) + umgap_tryp_lookup
+//   seedextend     src/commands/seedextend.rs:63-179     -> umgap_seedextend
+//   taxa2agg       src/commands/taxa2agg.rs:61-183       -> umgap_taxonomy_load + umgap_aggregate
+//   uniq           src/commands/uniq.rs:41-84            (host only)
+//   fastq2fasta    src/commands/fastq2fasta.rs:55-84     (host only)
+//   classify       the fused preset pipeline (extension) -> umgap_classify_reads
+//
+// Stream rules follow src/io/fasta.rs:30-67,164-180.  Errors go to stderr as `Error: ...`, exit 1
+// (quick_main!, src/main.rs:8).  The host does parsing and formatting only; every stage's
+// arithmetic runs on the GPU through the C ABI.
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "umgap_gpu.h"
+
+namespace {
+
+struct Fail : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+[[noreturn]] void fail(const std::string& m) { throw Fail(m); }
+void check(int rc) {
+    if (rc != UMGAP_OK) fail(umgap_last_error());
+}
+
+// ---- FASTA stream (src/io/fasta.rs) -------------------------------------------------------------
+struct Record {
+    std::string header;
+    std::vector<std::string> seq;
+};
+
+class LineSource {
+  public:
+    explicit LineSource(FILE* f) : f_(f), buf_(1 << 20) {}
+    bool next(std::string& line) {  // BufRead::lines(): strips "\n" or "\r\n"
+        line.clear();
+        bool any = false;
+        for (;;) {
+            if (pos_ == len_) {
+                len_ = fread(buf_.data(), 1, buf_.size(), f_);
+                pos_ = 0;
+                if (len_ == 0) break;
+            }
+            const char* p = (const char*)memchr(buf_.data() + pos_, '\n', len_ - pos_);
+            if (p) {
+                line.append(buf_.data() + pos_, p - (buf_.data() + pos_));
+                pos_ = (p - buf_.data()) + 1;
+                if (!line.empty() && line.back() == '\r') line.pop_back();
+                return true;
+            }
+            line.append(buf_.data() + pos_, len_ - pos_);
+            pos_ = len_;
+            any = true;
+        }
+        return any || !line.empty();
+    }
+
+  private:
+    FILE* f_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+};
+
+class FastaReader {
+  public:
+    FastaReader(FILE* f, bool unwrap) : src_(f), unwrap_(unwrap) { have_ = src_.next(pending_); }
+    bool next(Record& r) {  // fasta.rs:38-67
+        if (!have_) return false;
+        if (pending_.empty() || pending_[0] != '>') fail("Expected > at beginning of fasta header.");
+        r.header.assign(pending_, 1, std::string::npos);
+        r.seq.clear();
+        while ((have_ = src_.next(pending_)) && !(pending_.size() && pending_[0] == '>')) r.seq.push_back(pending_);
+        if (unwrap_) {
+            std::string all;
+            for (auto& s : r.seq) all += s;
+            r.seq.assign(1, all);
+        }
+        return true;
+    }
+
+  private:
+    LineSource src_;
+    bool unwrap_, have_;
+    std::string pending_;
+};
+
+void write_record(std::string& out, const std::string& header, const std::vector<std::string>& items,
+                  const std::string& sep, bool wrap) {  // fasta.rs:164-180
+    out += '>';
+    out += header;
+    std::string s;
+    for (size_t i = 0; i < items.size(); ++i) {
+        if (i) s += sep;
+        s += items[i];
+    }
+    if (!wrap) {
+        out += '\n';
+        out += s;
+    } else {
+        for (size_t k = 0; k < s.size(); k += 70) {
+            out += '\n';
+            out.append(s, k, 70);
+        }
+    }
+    if (!s.empty()) out += '\n';
+}
+
+void put(FILE* f, const std::string& s) {
+    if (!s.empty() && fwrite(s.data(), 1, s.size(), f) != s.size()) fail("failed writing output");
+}
+
+// ---- argv ---------------------------------------------------------------------------------------
+struct Spec {
+    char shortf;
+    const char* longf;
+    bool takes_value;
+};
+struct Args {
+    std::map<std::string, std::vector<std::string>> opt;  // keyed by long name
+    std::vector<std::string> pos;
+    bool has(const char* k) const { return opt.count(k) != 0; }
+    std::string get(const char* k, const std::string& dflt) const {
+        auto it = opt.find(k);
+        return it == opt.end() ? dflt : it->second.back();
+    }
+};
+
+Args parse(int argc, char** argv, int from, const std::vector<Spec>& specs) {
+    Args a;
+    for (int i = from; i < argc; ++i) {
+        std::string t = argv[i];
+        if (t == "--") {
+            for (++i; i < argc; ++i) a.pos.push_back(argv[i]);
+            break;
+        }
+        const Spec* sp = nullptr;
+        std::string inline_val;
+        bool has_inline = false;
+        if (t.size() > 2 && t[0] == '-' && t[1] == '-') {
+            std::string name = t.substr(2);
+            const size_t eq = name.find('=');
+            if (eq != std::string::npos) {
+                inline_val = name.substr(eq + 1);
+                name = name.substr(0, eq);
+                has_inline = true;
+            }
+            for (auto& s : specs)
+                if (name == s.longf) sp = &s;
+            if (!sp) fail("Found argument '" + t + "' which wasn't expected, or isn't valid in this context");
+        } else if (t.size() >= 2 && t[0] == '-' && !(t[1] >= '0' && t[1] <= '9')) {
+            for (auto& s : specs)
+                if (t[1] == s.shortf) sp = &s;
+            if (!sp) fail("Found argument '" + t + "' which wasn't expected, or isn't valid in this context");
+            if (t.size() > 2) {
+                if (sp->takes_value) {
+                    inline_val = t.substr(t[2] == '=' ? 3 : 2);
+                    has_inline = true;
+                } else {  // bundled flags, e.g. -mo
+                    a.opt[sp->longf].push_back("");
+                    for (size_t k = 2; k < t.size(); ++k) {
+                        const Spec* q = nullptr;
+                        for (auto& s : specs)
+                            if (t[k] == s.shortf) q = &s;
+                        if (!q || q->takes_value) fail("Found argument '" + t + "' which wasn't expected, or isn't valid in this context");
+                        a.opt[q->longf].push_back("");
+                    }
+                    continue;
+                }
+            }
+        } else {
+            a.pos.push_back(t);
+            continue;
+        }
+        if (sp->takes_value) {
+            if (!has_inline) {
+                if (i + 1 >= argc) fail(std::string("The argument '--") + sp->longf + " <" + sp->longf + ">' requires a value but none was supplied");
+                inline_val = argv[++i];
+            }
+            a.opt[sp->longf].push_back(inline_val);
+        } else {
+            a.opt[sp->longf].push_back("");
+        }
+    }
+    return a;
+}
+
+uint64_t parse_usize(const std::string& s) {  // Rust usize::from_str
+    size_t i = 0;
+    if (!s.empty() && s[0] == '+') i = 1;
+    if (i >= s.size()) fail(s.empty() ? "cannot parse integer from empty string" : "invalid digit found in string");
+    unsigned __int128 v = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') fail("invalid digit found in string");
+        v = v * 10 + (unsigned)(s[i] - '0');
+        if (v > (unsigned __int128)UINT64_MAX) fail("number too large to fit in target type");
+    }
+    return (uint64_t)v;
+}
+float parse_f32(const std::string& s) {
+    char* end = nullptr;
+    errno = 0;
+    const float v = strtof(s.c_str(), &end);
+    if (s.empty() || *end) fail("invalid float literal");
+    return v;
+}
+uint32_t taxon_u32(const std::string& s) {
+    const uint64_t v = parse_usize(s);
+    if (v >= 0xFFFFFFFFull) fail("taxon id " + s + " does not fit 32 bits");
+    return (uint32_t)v;
+}
+
+struct IndexHandle {
+    umgap_index* p = nullptr;
+    ~IndexHandle() { umgap_index_free(p); }
+};
+struct TaxHandle {
+    umgap_taxonomy* p = nullptr;
+    ~TaxHandle() { umgap_taxonomy_free(p); }
+};
+
+const size_t kBatchRecords = 1 << 16;
+
+// ---- translate ----------------------------------------------------------------------------------
+int cmd_translate(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'m', "methionine", false}, {'a', "all-frames", false}, {'f', "frame", true},
+                                   {'n', "append-name", false}, {'t', "table", true}, {'s', "show-table", false}});
+    if (a.has("all-frames") && a.has("frame")) fail("The argument '--all-frames' cannot be used with '--frame <frames>...'");
+    static const char* names[6] = {"1", "2", "3", "1R", "2R", "3R"};
+    const int table = (int)parse_usize(a.get("table", "1"));
+    const int meth = a.has("methionine");
+    // frames in the order given (translate.rs:82-93); the C ABI emits in reference order, so map
+    std::vector<int> order;
+    if (a.has("all-frames")) {
+        for (int i = 0; i < 6; ++i) order.push_back(i);
+    } else if (a.has("frame")) {
+        for (auto& f : a.opt["frame"]) {
+            int k = -1;
+            for (int i = 0; i < 6; ++i)
+                if (f == names[i]) k = i;
+            if (k < 0) fail("Invalid frame: " + f);
+            order.push_back(k);
+        }
+    }
+    if (a.has("show-table")) {  // TranslationTable::print (dna/translation.rs:146-173)
+        static const std::map<int, const char*> table_names = {
+            {1, "universal"}, {2, "vertebrate_mitochondrial"}, {3, "yeast_mitochondrial"}, {4, "mold_mitochondrial"},
+            {5, "invertebrate_mitochondrial"}, {6, "ciliate_nuclear"}, {9, "echinoderm_mitochondrial"}, {10, "euplotid_nuclear"},
+            {11, "bacterial"}, {12, "alternative_yeast_nuclear"}, {13, "ascidian_mitochondrial"}, {14, "flatworm_mitochondrial"},
+            {15, "blepharisma_macronuclear"}, {16, "chlorophycean_mitochondrial"}, {21, "trematode_mitochondrial"},
+            {22, "scenedesmus_mitochondrial"}, {23, "thraustochytrium_mitochondrial"}};
+        std::string nt, b1, b2, b3;
+        const char* tcag = "TCAG";
+        for (int i = 0; i < 64; ++i) {
+            b1 += tcag[i / 16];
+            b2 += tcag[(i / 4) % 4];
+            b3 += tcag[i % 4];
+            nt += b1.back();
+            nt += b2.back();
+            nt += b3.back();
+        }
+        std::vector<uint64_t> off = {0, 192};
+        std::vector<uint8_t> aa(umgap_translate_bound(192, 1, 1)), am(aa.size());
+        std::vector<uint64_t> aoff(2);
+        check(umgap_translate(0, (const uint8_t*)nt.data(), off.data(), 1, table, 0, 1, aa.data(), aoff.data()));
+        check(umgap_translate(0, (const uint8_t*)nt.data(), off.data(), 1, table, 1, 1, am.data(), aoff.data()));
+        std::string starts;  // a start codon is one that -m turns into M
+        for (int i = 0; i < 64; ++i) starts += (am[i] == 'M' && (aa[i] != 'M' || i == 35)) ? 'M' : '-';
+        auto it = table_names.find(table);
+        std::string out = std::string(it == table_names.end() ? "table" : it->second) + "=" + std::to_string(table) + "\n";
+        out += "AAs    = " + std::string((const char*)aa.data(), 64) + "\n";
+        out += "Starts = " + starts + "\n";
+        out += "Base1  = " + b1 + "\nBase2  = " + b2 + "\nBase3  = " + b3 + "\n";
+        put(stdout, out);
+        return 0;
+    }
+    uint8_t mask = 0;
+    for (int k : order) mask |= (uint8_t)(1u << k);
+    const int nsel = __builtin_popcount(mask);
+    int slot_of[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0, s = 0; i < 6; ++i)
+        if (mask >> i & 1) slot_of[i] = s++;
+    FastaReader rd(stdin, true);
+    std::vector<Record> recs;
+    Record r;
+    bool more = true;
+    // an unknown table is an error even on empty input (translate.rs:79)
+    {
+        const uint64_t z[1] = {0};
+        uint64_t ao[1];
+        uint8_t dummy[1];
+        check(umgap_translate(0, dummy, z, 0, table, meth, 1, dummy, ao));
+    }
+    while (more) {
+        recs.clear();
+        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
+        if (recs.empty()) break;
+        std::string out;
+        if (nsel) {
+            std::string nt;
+            std::vector<uint64_t> off(recs.size() + 1, 0);
+            for (size_t i = 0; i < recs.size(); ++i) {
+                nt += recs[i].seq[0];
+                off[i + 1] = nt.size();
+            }
+            std::vector<uint8_t> aa(umgap_translate_bound(nt.size(), recs.size(), mask));
+            std::vector<uint64_t> aoff(recs.size() * nsel + 1);
+            check(umgap_translate(0, (const uint8_t*)nt.data(), off.data(), recs.size(), table, meth, mask, aa.data(), aoff.data()));
+            for (size_t i = 0; i < recs.size(); ++i)
+                for (int k : order) {
+                    const size_t j = i * nsel + slot_of[k];
+                    std::string h = recs[i].header;
+                    if (a.has("append-name")) h += std::string("|") + names[k];
+                    write_record(out, h, {std::string((const char*)aa.data() + aoff[j], aoff[j + 1] - aoff[j])}, "", false);
+                }
+        }
+        put(stdout, out);
+    }
+    return 0;
+}
+
+// ---- prot2kmer2lca ------------------------------------------------------------------------------
+void stream_prot2kmer2lca(FILE* in, FILE* out_f, const umgap_index* idx, bool one_on_one) {
+    FastaReader rd(in, true);
+    std::vector<Record> recs;
+    Record r;
+    bool more = true;
+    while (more) {
+        recs.clear();
+        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
+        if (recs.empty()) break;
+        std::string aa;
+        std::vector<uint64_t> off(recs.size() + 1, 0);
+        for (size_t i = 0; i < recs.size(); ++i) {
+            aa += recs[i].seq[0];
+            off[i + 1] = aa.size();
+        }
+        std::vector<uint32_t> taxa(umgap_kmer_lookup_bound(aa.size(), recs.size()));
+        std::vector<uint64_t> toff(recs.size() + 1);
+        std::vector<uint8_t> kept(recs.size() + 1);
+        check(umgap_kmer_lookup(idx, (const uint8_t*)aa.data(), off.data(), recs.size(), one_on_one, taxa.data(), toff.data(), kept.data()));
+        std::string out;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            if (!kept[i]) continue;  // prot2kmer2lca.rs:172
+            out += '>';
+            out += recs[i].header;
+            out += '\n';
+            for (uint64_t j = toff[i]; j < toff[i + 1]; ++j) {
+                out += std::to_string(taxa[j]);
+                out += '\n';
+            }
+        }
+        put(out_f, out);
+        fflush(out_f);
+    }
+}
+
+int cmd_prot2kmer2lca(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'k', "length", true}, {'o', "one-on-one", false}, {'s', "socket", true},
+                                   {'m', "in-memory", false}, {'c', "chunksize", true}});
+    if (a.pos.size() != 1) fail("The following required arguments were not provided:\n    <fst-file>");
+    const int k = (int)parse_usize(a.get("length", "9"));
+    (void)parse_usize(a.get("chunksize", "240"));  // accepted; batches are sized for the GPU
+    IndexHandle idx;
+    check(umgap_index_load_fst(a.pos[0].c_str(), k, 0, 0.0, &idx.p));
+    if (!a.has("socket")) {
+        stream_prot2kmer2lca(stdin, stdout, idx.p, a.has("one-on-one"));
+        return 0;
+    }
+    // socket server mode (prot2kmer2lca.rs:116-137): one connection at a time, until killed
+    const std::string path = a.get("socket", "");
+    const int srv = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (srv < 0) fail(std::string("socket: ") + strerror(errno));
+    sockaddr_un addr{};
+    addr.sun_family = AF_UNIX;
+    if (path.size() >= sizeof addr.sun_path) fail("socket path too long");
+    strcpy(addr.sun_path, path.c_str());
+    if (bind(srv, (sockaddr*)&addr, sizeof addr) != 0) fail(std::string("bind: ") + strerror(errno));
+    if (listen(srv, 16) != 0) fail(std::string("listen: ") + strerror(errno));
+    printf("Socket created, listening for connections.\n");
+    fflush(stdout);
+    for (;;) {
+        const int c = accept(srv, nullptr, nullptr);
+        if (c < 0) {
+            if (errno == EINTR) continue;
+            fail(std::string("accept: ") + strerror(errno));
+        }
+        printf("Connection accepted.\n");
+        fflush(stdout);
+        FILE* in = fdopen(c, "r");
+        FILE* out = fdopen(dup(c), "w");
+        try {
+            stream_prot2kmer2lca(in, out, idx.p, a.has("one-on-one"));
+            printf("Connection finished succesfully.\n");
+        } catch (const Fail& e) {
+            printf("Connection died with an error: %s\n", e.what());
+        }
+        fflush(stdout);
+        fclose(out);
+        fclose(in);
+    }
+}
+
+// ---- prot2tryp2lca ------------------------------------------------------------------------------
+int cmd_prot2tryp2lca(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'o', "one-on-one", false}, {'m', "in-memory", false}, {'c', "chunksize", true},
+                                   {'p', "pattern", true}, {'l', "minlen", true}, {'L', "maxlen", true},
+                                   {'k', "keep", true}, {'d', "drop", true}});
+    if (a.pos.size() != 1) fail("The following required arguments were not provided:\n    <fst-file>");
+    if (a.get("pattern", "([KR])([^P])") != "([KR])([^P])")
+        fail("only the default cleavage pattern ([KR])([^P]) is implemented on the GPU path");
+    const int minlen = (int)parse_usize(a.get("minlen", "5")), maxlen = (int)parse_usize(a.get("maxlen", "50"));
+    const std::string keep = a.get("keep", ""), drop = a.get("drop", "");
+    IndexHandle idx;
+    check(umgap_index_load_fst(a.pos[0].c_str(), 0, 0, 0.0, &idx.p));
+    FastaReader rd(stdin, false);
+    std::vector<Record> recs;
+    Record r;
+    bool more = true;
+    while (more) {
+        recs.clear();
+        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
+        if (recs.empty()) break;
+        std::string aa;
+        std::vector<uint64_t> off(1, 0);
+        for (auto& rec : recs)
+            for (auto& line : rec.seq) {
+                aa += line;
+                off.push_back(aa.size());
+            }
+        const uint64_t nlines = off.size() - 1;
+        std::vector<uint32_t> taxa(umgap_tryp_lookup_bound(aa.size(), nlines));
+        std::vector<uint64_t> toff(nlines + 1);
+        check(umgap_tryp_lookup(idx.p, (const uint8_t*)aa.data(), off.data(), nlines, minlen, maxlen, keep.c_str(), drop.c_str(),
+                                a.has("one-on-one"), taxa.data(), toff.data()));
+        std::string out;
+        uint64_t l = 0;
+        for (auto& rec : recs) {
+            out += '>';
+            out += rec.header;
+            out += '\n';  // the header is always written (prot2tryp2lca.rs:108)
+            for (size_t s = 0; s < rec.seq.size(); ++s, ++l)
+                for (uint64_t j = toff[l]; j < toff[l + 1]; ++j) {
+                    out += std::to_string(taxa[j]);
+                    out += '\n';
+                }
+        }
+        put(stdout, out);
+    }
+    return 0;
+}
+
+// ---- seedextend / taxa2agg ---------------------------------------------------------------------
+void flatten_ids(const std::vector<Record>& recs, std::vector<uint32_t>& ids, std::vector<uint64_t>& off) {
+    ids.clear();
+    off.assign(1, 0);
+    for (auto& rec : recs) {
+        for (auto& s : rec.seq) ids.push_back(taxon_u32(s));
+        off.push_back(ids.size());
+    }
+}
+
+int cmd_seedextend(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'s', "min-seed-size", true}, {'g', "max-gap-size", true}, {'r', "ranked", true}, {'p', "penalty", true}});
+    if (a.has("ranked")) fail("seedextend --ranked is not implemented on the GPU path");
+    const int s = (int)parse_usize(a.get("min-seed-size", "2")), g = (int)parse_usize(a.get("max-gap-size", "0"));
+    FastaReader rd(stdin, false);
+    std::vector<Record> recs;
+    Record r;
+    bool more = true;
+    std::vector<uint32_t> ids, out_ids;
+    std::vector<uint64_t> off, ooff;
+    while (more) {
+        recs.clear();
+        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
+        if (recs.empty()) break;
+        flatten_ids(recs, ids, off);
+        out_ids.assign(ids.size() + 1, 0);
+        ooff.assign(recs.size() + 1, 0);
+        check(umgap_seedextend(0, ids.data(), off.data(), recs.size(), s, g, out_ids.data(), ooff.data()));
+        std::string out;
+        for (size_t i = 0; i < recs.size(); ++i) {
+            std::vector<std::string> items;
+            for (uint64_t j = ooff[i]; j < ooff[i + 1]; ++j) items.push_back(std::to_string(out_ids[j]));
+            write_record(out, recs[i].header, items, "\n", false);
+        }
+        put(stdout, out);
+    }
+    return 0;
+}
+
+int parse_strategy(const std::string& method, const std::string& strategy) {
+    const bool tree = method == "tree", rmq = method == "rmq";
+    if (!tree && !rmq) fail("Invalid method: " + method);
+    int st;
+    if (strategy == "lca*") st = UMGAP_AGG_LCA_STAR;
+    else if (strategy == "hybrid") st = UMGAP_AGG_HYBRID;
+    else if (strategy == "mrtl") st = UMGAP_AGG_MRTL;
+    else fail("Invalid strategy: " + strategy);
+    if (tree && st == UMGAP_AGG_MRTL)  // taxa2agg.rs:134-138
+        fail("Invalid invocation: Tree and MaximumRootToLeafPath cannot be combined");
+    if (rmq && st != UMGAP_AGG_MRTL)
+        fail("-m rmq -a " + strategy + " (the RMQ variants of lca*/hybrid) is not implemented on the GPU path; use -m tree");
+    return st;
+}
+
+int cmd_taxa2agg(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'s', "scored", false}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
+                                   {'f', "factor", true}, {'l', "lower-bound", true}});
+    if (a.pos.size() != 1) fail("The following required arguments were not provided:\n    <taxon-file>");
+    if (a.has("scored")) fail("taxa2agg --scored is not implemented on the GPU path");
+    const int st = parse_strategy(a.get("method", "tree"), a.get("aggregate", "hybrid"));
+    const float factor = parse_f32(a.get("factor", "0.25")), lb = parse_f32(a.get("lower-bound", "0"));
+    TaxHandle tax;
+    check(umgap_taxonomy_load(a.pos[0].c_str(), 0, &tax.p));
+    FastaReader rd(stdin, false);
+    std::vector<Record> recs;
+    Record r;
+    bool more = true;
+    std::vector<uint32_t> ids, res;
+    std::vector<uint64_t> off;
+    while (more) {
+        recs.clear();
+        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
+        if (recs.empty()) break;
+        flatten_ids(recs, ids, off);
+        res.assign(recs.size(), 0);
+        ids.push_back(0);
+        check(umgap_aggregate(tax.p, ids.data(), off.data(), recs.size(), st, factor, lb, a.has("ranked"), res.data()));
+        std::string out;
+        for (size_t i = 0; i < recs.size(); ++i) write_record(out, recs[i].header, {std::to_string(res[i])}, "\n", false);
+        put(stdout, out);
+    }
+    return 0;
+}
+
+// ---- uniq / fastq2fasta (host only) ---------------------------------------------------------------
+int cmd_uniq(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'s', "separator", true}, {'w', "wrap", false}, {'d', "delimiter", true}});
+    const std::string sep = a.get("separator", "\n");
+    const bool wrap = a.has("wrap"), has_delim = a.has("delimiter");
+    const std::string delim = a.get("delimiter", "");
+    FastaReader rd(stdin, false);
+    Record r, last;
+    bool have_last = false;
+    std::string out;
+    while (rd.next(r)) {  // uniq.rs:59-82
+        if (has_delim) {
+            const size_t p = r.header.find(delim);
+            if (p != std::string::npos) r.header.resize(p);
+        }
+        if (have_last && last.header == r.header) {
+            last.seq.insert(last.seq.end(), r.seq.begin(), r.seq.end());
+        } else {
+            if (have_last) write_record(out, last.header, last.seq, sep, wrap);
+            last = r;
+            have_last = true;
+        }
+        if (out.size() > (1 << 20)) {
+            put(stdout, out);
+            out.clear();
+        }
+    }
+    if (have_last) write_record(out, last.header, last.seq, sep, wrap);
+    put(stdout, out);
+    return 0;
+}
+
+struct FastqReader {  // src/io/fastq.rs:26-87
+    LineSource src;
+    explicit FastqReader(FILE* f) : src(f) {}
+    bool next(std::string& header, std::string& seq) {
+        std::string line;
+        if (!src.next(line)) return false;
+        if (line.empty() || line[0] != '@') fail("Expected @ at beginning of fastq header.");
+        header.assign(line, 1, std::string::npos);
+        seq.clear();
+        size_t n = 0;
+        bool got;
+        while ((got = src.next(line)) && !(line.size() && line[0] == '+')) {
+            seq += line;
+            ++n;
+        }
+        for (size_t i = 0; i < n; ++i)
+            if (!src.next(line)) fail("Expected as many quality lines as sequence lines.");
+        return true;
+    }
+};
+
+int cmd_fastq2fasta(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {});
+    if (a.pos.empty()) fail("The following required arguments were not provided:\n    <input>...");
+    std::vector<FILE*> files;
+    std::vector<std::unique_ptr<FastqReader>> rd;
+    for (auto& p : a.pos) {
+        FILE* f = fopen(p.c_str(), "r");
+        if (!f) fail(p + ": " + strerror(errno));
+        files.push_back(f);
+        rd.emplace_back(new FastqReader(f));
+    }
+    std::string out;
+    for (;;) {  // one record from every file, stop when any is exhausted (fastq2fasta.rs:62-84)
+        std::vector<std::pair<std::string, std::string>> row(rd.size());
+        bool ok = true;
+        for (size_t i = 0; i < rd.size() && ok; ++i) ok = rd[i]->next(row[i].first, row[i].second);
+        if (!ok) break;
+        for (auto& r : row) write_record(out, r.first, {r.second}, "", false);
+        if (out.size() > (1 << 20)) {
+            put(stdout, out);
+            out.clear();
+        }
+    }
+    put(stdout, out);
+    for (FILE* f : files) fclose(f);
+    return 0;
+}
+
+// ---- classify: the whole preset in one process (extension) ---------------------------------------
+int cmd_classify(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'t', "table", true}, {'M', "methionine", false}, {'k', "length", true}, {'O', "omit-misses", false},
+                                   {'S', "no-seedextend", false}, {'s', "min-seed-size", true}, {'g', "max-gap-size", true},
+                                   {'d', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
+                                   {'f', "factor", true}, {'l', "lower-bound", true}});
+    if (a.pos.size() != 2) fail("usage: umgap classify [flags] <fst-file> <taxon-file> < reads.fa");
+    umgap_pipeline_opts o;
+    umgap_pipeline_opts_default(&o);
+    o.table = (int)parse_usize(a.get("table", "1"));
+    o.methionine = a.has("methionine");
+    o.one_on_one = !a.has("omit-misses");
+    o.seedextend = !a.has("no-seedextend");
+    o.min_seed_size = (int)parse_usize(a.get("min-seed-size", "2"));
+    o.max_gap_size = (int)parse_usize(a.get("max-gap-size", "0"));
+    o.strategy = parse_strategy(a.get("method", a.get("aggregate", "hybrid") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "hybrid"));
+    o.factor = parse_f32(a.get("factor", "0.25"));
+    o.lower_bound = parse_f32(a.get("lower-bound", "0"));
+    o.ranked_only = a.has("ranked");
+    const bool has_delim = a.has("delimiter");
+    const std::string delim = a.get("delimiter", "/");
+    const int k = (int)parse_usize(a.get("length", "9"));
+    IndexHandle idx;
+    TaxHandle tax;
+    check(umgap_index_load_fst(a.pos[0].c_str(), k, 0, 0.0, &idx.p));
+    check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
+    FastaReader rd(stdin, true);
+    Record r;
+    std::string carry_header;  // group that may continue in the next batch
+    std::vector<std::string> heads;
+    std::string nt;
+    std::vector<uint64_t> roff, goff;
+    auto flush = [&]() {
+        if (heads.empty()) return;
+        std::vector<uint32_t> res(heads.size());
+        goff.push_back(roff.size() - 1);
+        check(umgap_classify_reads(idx.p, tax.p, &o, (const uint8_t*)nt.data(), roff.data(), roff.size() - 1, goff.data(), heads.size(), res.data(), nullptr));
+        std::string out;
+        for (size_t i = 0; i < heads.size(); ++i)
+            if (res[i] != UMGAP_ABSENT) write_record(out, heads[i], {std::to_string(res[i])}, "\n", false);
+        put(stdout, out);
+        heads.clear();
+        nt.clear();
+        roff.assign(1, 0);
+        goff.clear();
+    };
+    roff.assign(1, 0);
+    const size_t span = 3 * (size_t)k;
+    while (rd.next(r)) {
+        std::string h = r.header;
+        {
+            const size_t p = h.find(delim);
+            if (p != std::string::npos) h.resize(p);
+        }
+        // reads too short for any frame emit no record at all and so do not take part in uniq's
+        // grouping (prot2kmer2lca.rs:172 drops them before uniq sees them)
+        if (r.seq[0].size() < span) continue;
+        if (heads.empty() || heads.back() != h) {
+            if (heads.size() >= kBatchRecords) flush();
+            heads.push_back(h);
+            goff.push_back(roff.size() - 1);
+        }
+        nt += r.seq[0];
+        roff.push_back(nt.size());
+    }
+    flush();
+    return 0;
+}
+
+void usage(FILE* f) {
+    fputs("umgap 1.1.1 (umgap-b200: GPU implementation of the per-read classification path)\n\n"
+          "USAGE:\n    umgap <SUBCOMMAND>\n\nFLAGS:\n    -h, --help       Prints help information\n    -V, --version    Prints version information\n\n"
+          "SUBCOMMANDS:\n    translate        Translates DNA on stdin into amino acid sequences (six frames)\n"
+          "    prot2kmer2lca    Maps all k-mers of peptides to taxon ids through an fst index\n"
+          "    prot2tryp2lca    Digests peptides tryptically and maps them to taxon ids\n"
+          "    seedextend       Selects promising regions in sequences of taxon ids\n"
+          "    uniq             Joins consecutive FASTA records with the same header\n"
+          "    taxa2agg         Aggregates taxon ids per record (lca*, hybrid, mrtl)\n"
+          "    fastq2fasta      Interleaves FASTQ files into FASTA\n"
+          "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process\n", f);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        if (argc < 2) {
+            usage(stderr);
+            return 1;
+        }
+        const std::string sub = argv[1];
+        if (sub == "-V" || sub == "--version") {
+            puts("umgap 1.1.1");
+            return 0;
+        }
+        if (sub == "-h" || sub == "--help" || sub == "help") {
+            usage(stdout);
+            return 0;
+        }
+        if (sub == "translate") return cmd_translate(argc, argv);
+        if (sub == "prot2kmer2lca") return cmd_prot2kmer2lca(argc, argv);
+        if (sub == "prot2tryp2lca") return cmd_prot2tryp2lca(argc, argv);
+        if (sub == "seedextend") return cmd_seedextend(argc, argv);
+        if (sub == "taxa2agg") return cmd_taxa2agg(argc, argv);
+        if (sub == "uniq") return cmd_uniq(argc, argv);
+        if (sub == "fastq2fasta") return cmd_fastq2fasta(argc, argv);
+        if (sub == "classify") return cmd_classify(argc, argv);
+        fail("Found argument '" + sub + "' which wasn't expected, or isn't valid in this context");
+    } catch (const Fail& e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}

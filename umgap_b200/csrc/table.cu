@@ -7,6 +7,10 @@
 
 namespace umgap {
 
+int build_var_table_from_pairs(umgap_index* idx, const uint8_t* keys, const uint64_t* key_off,
+                               const uint64_t* values, uint64_t n, double load_factor);  // tryptic.cu
+void free_var_table(void* p);
+
 enum { C_OVF = 0, C_DUP = 1, C_DISPLACED = 2, C_MAXPROBE = 3, C_INSERTED = 4, C_BADVAL = 5, C_N = 8 };
 
 // Empty table: every meta = kEmptyMeta, every value = kNoValue.
@@ -258,12 +262,19 @@ int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const u
     umgap_index* idx = nullptr;
     int rc = guarded([&] {
         if (!out || (n && (!keys || !values))) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
-        if (k <= 0 || k > 9)
+        if (k < 0 || k > 9)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "k-mer table supports 1 <= k <= 9 (got %d)", k);
         idx = new umgap_index();
         idx->device = device;
         idx->k = k;
         memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
+        if (k == 0) {  // variable-length peptide table (prot2tryp2lca)
+            if (n && !key_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "key_off is required for a variable-length table");
+            const int r = build_var_table_from_pairs(idx, keys, key_off, values, n, load_factor);
+            if (r != UMGAP_OK) throw StatusError{r};
+            *out = idx;
+            return;
+        }
         TableBuilder b;
         try {
             b.begin(idx, n, load_factor);
@@ -319,7 +330,7 @@ void umgap_index_free(umgap_index* idx) {
     cudaSetDevice(idx->device);
     for (int i = 0; i < idx->nlevels; ++i)
         if (idx->level_dev[i]) cudaFree(idx->level_dev[i]);
-    if (idx->var_table) cudaFree(idx->var_table);
+    if (idx->var_table) free_var_table(idx->var_table);
     idx->ws.release();
     delete idx;
 }

@@ -1,19 +1,305 @@
-// Variable-length peptide table + tryptic digest/lookup kernel (prot2tryp2lca.rs:88-140).
+// prot2tryp2lca on the device (prot2tryp2lca.rs:88-140): variable-length peptide table + tryptic
+// digest / filter / lookup kernel.
+//
+// Table.  Tryptic peptides are 5..50 bytes of arbitrary content, so the key bytes themselves are
+// kept (one byte pool in HBM) and every tag match is verified against them: exact, no false
+// positives.  Slots are 16 bytes {tag:32, value:32, pool offset:56 | length:8}, two per 32-byte
+// sector, open addressing with linear probing at load factor <= 0.5; the home slot is
+// floor(hash * nslots / 2^64) and the tag the low 32 bits of the 64-bit hash.
+//
+// Digest.  The reference applies the regex ([KR])([^P]) -> "$1\n$2" twice, turns '*' into a line
+// break and drops empty pieces (:112-117).  In closed form (oracle.lookup.tryptic_digest, checked
+// against the regex form): a peptide starts at i iff c[i] != '*' and (i == 0 or c[i-1] == '*' or
+// (c[i-1] in KR and c[i] != 'P')); it ends before the next start or '*'.  One thread per start
+// position walks its peptide once, hashing as it goes.
+#include <algorithm>
+
 #include "index.h"
 
 namespace umgap {
-int build_var_table_from_fst(const char* path, umgap_index* idx, double load_factor) {
-    (void)path; (void)idx; (void)load_factor;
-    set_error("variable-length (tryptic) table not built yet");
-    return UMGAP_ERR_INVALID;
+
+struct VarSlot {
+    uint32_t tag;
+    uint32_t value;
+    uint64_t off_len;  // pool offset << 8 | length; ~0 = empty
+};
+constexpr uint64_t kVarEmpty = ~0ull;
+
+struct VarTable {
+    VarSlot* slots = nullptr;
+    uint8_t* pool = nullptr;
+    uint64_t nslots = 0, pool_bytes = 0;
+};
+
+__host__ __device__ __forceinline__ uint64_t pep_hash_step(uint64_t h, uint8_t c) {
+    h = (h ^ c) * 0x100000001B3ull;  // FNV-1a step
+    return h;
 }
+__host__ __device__ __forceinline__ uint64_t pep_hash_finish(uint64_t h, uint32_t len) {
+    h ^= len;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return h;
+}
+constexpr uint64_t kFnvBasis = 0xCBF29CE484222325ull;
+
+__global__ void var_fill_kernel(VarSlot* s, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        s[i].tag = 0;
+        s[i].value = kNoValue;
+        s[i].off_len = kVarEmpty;
+    }
+}
+
+__global__ void var_insert_kernel(VarSlot* slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                                  const uint64_t* __restrict__ key_off, const uint32_t* __restrict__ vals,
+                                  uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t off = key_off[i];
+        const uint32_t len = (uint32_t)(key_off[i + 1] - off);
+        uint64_t h = kFnvBasis;
+        for (uint32_t j = 0; j < len; ++j) h = pep_hash_step(h, pool[off + j]);
+        h = pep_hash_finish(h, len);
+        uint64_t s = __umul64hi(h, nslots);
+        const unsigned long long mine = (off << 8) | len;
+        for (;;) {
+            unsigned long long* p = reinterpret_cast<unsigned long long*>(&slots[s].off_len);
+            if (*reinterpret_cast<volatile unsigned long long*>(p) == kVarEmpty &&
+                atomicCAS(p, kVarEmpty, mine) == kVarEmpty) {
+                slots[s].tag = (uint32_t)h;
+                slots[s].value = vals[i];
+                break;
+            }
+            s = (s + 1 == nslots) ? 0 : s + 1;
+        }
+    }
+}
+
+struct TrypParams {
+    uint32_t minlen, maxlen;
+    uint32_t keep_all;       // bitmask with one bit per keep residue
+    int filter_sets;         // keep or drop set non-empty (prot2tryp2lca.rs:122)
+};
+
+constexpr uint32_t kTrypNone = 0xFFFFFFFEu;  // position that starts no (kept) peptide
+
+// out[i] for every input byte i: kTrypNone, kNoValue (kept peptide, miss) or the value.
+__global__ void __launch_bounds__(256)
+tryp_lookup_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                   const uint8_t* __restrict__ aa, const uint64_t* __restrict__ line_off, uint64_t nlines,
+                   const uint32_t* __restrict__ line_of_byte, uint64_t total, TrypParams tp,
+                   const uint8_t* __restrict__ set_lut /* [256]: bit7 = drop, low 6 bits = keep index+1 */,
+                   uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t line = line_of_byte[i];
+        const uint64_t b = line_off[line], e = line_off[line + 1];
+        const uint8_t c = aa[i];
+        bool start = c != '*';
+        if (start && i > b) {
+            const uint8_t p = aa[i - 1];
+            start = p == '*' || ((p == 'K' || p == 'R') && c != 'P');
+        }
+        uint32_t res = kTrypNone;
+        if (start) {
+            uint64_t h = kFnvBasis;
+            uint32_t len = 0, keep_seen = 0;
+            bool dropped = false, too_long = false;
+            for (uint64_t j = i; j < e; ++j) {
+                const uint8_t x = aa[j];
+                if (x == '*') break;
+                if (len == tp.maxlen) {  // one more residue would exceed -L: filtered out
+                    too_long = true;
+                    break;
+                }
+                h = pep_hash_step(h, x);
+                ++len;
+                const uint8_t s = set_lut[x];
+                dropped |= (s & 0x80) != 0;
+                if (s & 0x3F) keep_seen |= 1u << ((s & 0x3F) - 1);
+                if ((x == 'K' || x == 'R') && j + 1 < e && aa[j + 1] != 'P') break;
+            }
+            bool keep = !too_long && len >= tp.minlen;
+            if (keep && tp.filter_sets) keep = !dropped && keep_seen == tp.keep_all;
+            if (keep) {
+                h = pep_hash_finish(h, len);
+                res = kNoValue;
+                uint64_t s = __umul64hi(h, nslots);
+                for (;;) {
+                    const VarSlot sl = slots[s];
+                    if (sl.off_len == kVarEmpty) break;
+                    if (sl.tag == (uint32_t)h && (uint32_t)(sl.off_len & 0xFF) == len) {
+                        const uint8_t* k = pool + (sl.off_len >> 8);
+                        bool same = true;
+                        for (uint32_t q = 0; q < len; ++q) same &= k[q] == aa[i + q];
+                        if (same) {
+                            res = sl.value;
+                            break;
+                        }
+                    }
+                    s = (s + 1 == nslots) ? 0 : s + 1;
+                }
+            }
+        }
+        out[i] = res;
+    }
+}
+
+__global__ void line_of_byte_kernel(const uint64_t* __restrict__ line_off, uint64_t nlines, uint32_t* __restrict__ lob) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t l = warp; l < nlines; l += nwarps)
+        for (uint64_t i = line_off[l] + lane; i < line_off[l + 1]; i += 32) lob[i] = (uint32_t)l;
+}
+
+namespace {
+struct VarSink : FstSink {
+    std::vector<uint8_t> pool;
+    std::vector<uint64_t> off{0};
+    std::vector<uint32_t> vals;
+    uint64_t skipped = 0;
+    void on_key(const uint8_t* key, size_t len, uint64_t value) override {
+        if (len == 0 || len > 255) {
+            ++skipped;
+            return;
+        }
+        if (value >= 0xFFFFFFFFull)
+            UMGAP_FAIL(UMGAP_ERR_CAPACITY, "index value %llu does not fit 32 bits", (unsigned long long)value);
+        pool.insert(pool.end(), key, key + len);
+        off.push_back(pool.size());
+        vals.push_back((uint32_t)value);
+    }
+};
+}  // namespace
+
+static void build_var_table(umgap_index* idx, const std::vector<uint8_t>& pool, const std::vector<uint64_t>& off,
+                            const std::vector<uint32_t>& vals, double load_factor) {
+    use_device(idx->device);
+    if (load_factor <= 0 || load_factor > 0.9) load_factor = 0.5;
+    const uint64_t n = vals.size();
+    VarTable* t = new VarTable();
+    idx->var_table = t;
+    t->nslots = std::max<uint64_t>(1024, (uint64_t)((double)n / load_factor) + 1);
+    t->pool_bytes = pool.size();
+    UMGAP_CUDA(cudaMalloc((void**)&t->slots, t->nslots * sizeof(VarSlot)));
+    UMGAP_CUDA(cudaMalloc((void**)&t->pool, std::max<size_t>(pool.size(), 16)));
+    var_fill_kernel<<<148 * 8, 256>>>(t->slots, t->nslots);
+    UMGAP_CUDA(cudaGetLastError());
+    if (n) {
+        UMGAP_CUDA(cudaMemcpy(t->pool, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+        DevBuf<uint64_t> d_off(n + 1);
+        DevBuf<uint32_t> d_vals(n);
+        UMGAP_CUDA(cudaMemcpy(d_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_vals.p, vals.data(), n * 4, cudaMemcpyHostToDevice));
+        var_insert_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(n, 256), 148 * 32), 256>>>(t->slots, t->nslots, t->pool,
+                                                                                           d_off.p, d_vals.p, n);
+        UMGAP_CUDA(cudaGetLastError());
+        UMGAP_CUDA(cudaDeviceSynchronize());
+    }
+    idx->n_keys = n;
+    idx->bytes = t->nslots * sizeof(VarSlot) + pool.size();
+}
+
+int build_var_table_from_fst(const char* path, umgap_index* idx, double load_factor) {
+    return guarded([&] {
+        VarSink sink;
+        fst_stream_file(path, sink, nullptr);
+        idx->n_skipped = sink.skipped;
+        build_var_table(idx, sink.pool, sink.off, sink.vals, load_factor);
+    });
+}
+
+int build_var_table_from_pairs(umgap_index* idx, const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
+                               uint64_t n, double load_factor) {
+    return guarded([&] {
+        VarSink sink;
+        for (uint64_t i = 0; i < n; ++i) sink.on_key(keys + key_off[i], (size_t)(key_off[i + 1] - key_off[i]), values[i]);
+        idx->n_skipped = sink.skipped;
+        build_var_table(idx, sink.pool, sink.off, sink.vals, load_factor);
+    });
+}
+
+void free_var_table(void* p) {
+    VarTable* t = (VarTable*)p;
+    if (!t) return;
+    if (t->slots) cudaFree(t->slots);
+    if (t->pool) cudaFree(t->pool);
+    delete t;
+}
+
 }  // namespace umgap
 
+using namespace umgap;
+
 extern "C" {
-uint64_t umgap_tryp_lookup_bound(uint64_t total_aa, uint64_t nlines) { return total_aa + nlines + 1; }
-int umgap_tryp_lookup(const umgap_index*, const uint8_t*, const uint64_t*, uint64_t, int, int, const char*,
-                      const char*, int, uint32_t*, uint64_t*) {
-    umgap::set_error("umgap_tryp_lookup not implemented yet");
-    return UMGAP_ERR_INVALID;
+
+uint64_t umgap_tryp_lookup_bound(uint64_t total_aa, uint64_t nlines) {
+    (void)nlines;
+    return total_aa + 1;
 }
+
+int umgap_tryp_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t* line_off, uint64_t nlines,
+                      int minlen, int maxlen, const char* keep, const char* drop, int one_on_one,
+                      uint32_t* taxa_out, uint64_t* taxa_off) {
+    return guarded([&] {
+        if (!idx || !line_off || !taxa_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->k != 0 || !idx->var_table) UMGAP_FAIL(UMGAP_ERR_INVALID, "index is not a variable-length peptide table");
+        if (minlen < 0 || maxlen < 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "negative length bound");
+        for (uint64_t i = 0; i <= nlines; ++i) taxa_off[i] = 0;
+        const uint64_t total = nlines ? line_off[nlines] : 0;
+        if (!total) return;
+        if (!aa || !taxa_out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (total >= (1ull << 32) || nlines >= (1ull << 32)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large (>= 2^32 bytes)");
+        uint8_t lut[256] = {};
+        TrypParams tp{};
+        tp.minlen = (uint32_t)minlen;
+        tp.maxlen = (uint32_t)maxlen;
+        int nkeep = 0;
+        for (const char* p = keep ? keep : ""; *p; ++p) {
+            uint8_t& e = lut[(uint8_t)*p];
+            if (e & 0x3F) continue;
+            if (nkeep == 32) UMGAP_FAIL(UMGAP_ERR_INVALID, "more than 32 distinct residues in --keep");
+            e |= (uint8_t)(++nkeep);
+        }
+        for (const char* p = drop ? drop : ""; *p; ++p) lut[(uint8_t)*p] |= 0x80;
+        tp.keep_all = nkeep == 32 ? 0xFFFFFFFFu : ((1u << nkeep) - 1);
+        tp.filter_sets = (keep && *keep) || (drop && *drop);
+        use_device(idx->device);
+        const VarTable* t = (const VarTable*)idx->var_table;
+        DevBuf<uint8_t> d_aa(total), d_lut(256);
+        DevBuf<uint64_t> d_off(nlines + 1);
+        DevBuf<uint32_t> d_lob(total), d_out(total);
+        UMGAP_CUDA(cudaMemcpy(d_aa.p, aa, total, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_lut.p, lut, 256, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_off.p, line_off, (nlines + 1) * 8, cudaMemcpyHostToDevice));
+        line_of_byte_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, 8), 148 * 16), 256>>>(d_off.p, nlines, d_lob.p);
+        UMGAP_CUDA(cudaGetLastError());
+        tryp_lookup_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(total, 256), 148 * 16), 256>>>(
+            t->slots, t->nslots, t->pool, d_aa.p, d_off.p, nlines, d_lob.p, total, tp, d_lut.p, d_out.p);
+        UMGAP_CUDA(cudaGetLastError());
+        std::vector<uint32_t> raw(total);
+        UMGAP_CUDA(cudaMemcpy(raw.data(), d_out.p, total * 4, cudaMemcpyDeviceToHost));
+        uint64_t w = 0;
+        for (uint64_t l = 0; l < nlines; ++l) {
+            taxa_off[l] = w;
+            for (uint64_t i = line_off[l]; i < line_off[l + 1]; ++i) {
+                const uint32_t v = raw[i];
+                if (v == kTrypNone) continue;
+                if (v == kNoValue) {
+                    if (one_on_one) taxa_out[w++] = 0;  // prot2tryp2lca.rs:95,130
+                } else {
+                    taxa_out[w++] = v;
+                }
+            }
+        }
+        taxa_off[nlines] = w;
+    });
 }
+
+}  // extern "C"
