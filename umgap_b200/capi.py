@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libumgap_gpu.so")
+LIB_PATH = os.environ.get("UMGAP_GPU_LIB") or os.path.join(_HERE, "lib", "libumgap_gpu.so")
 
 MISS = 0xFFFFFFFF
 ABSENT = 0xFFFFFFFF

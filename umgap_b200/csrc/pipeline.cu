@@ -92,138 +92,159 @@ __device__ __forceinline__ uint32_t nt_code(uint8_t c) {
     return c == 'T' ? 0u : c == 'C' ? 1u : c == 'A' ? 2u : c == 'G' ? 3u : 4u;
 }
 
+#ifndef UMGAP_K1_BLOCKS
+#define UMGAP_K1_BLOCKS 3
+#endif
 constexpr int kTile = 128;          // k-mer start positions per warp pass (4 per lane)
-constexpr int kLookupWarps = 8;     // warps (= reads in flight) per CTA
-constexpr int kQueue = 2 * kTile;   // pending second probes of one tile (both strands)
+constexpr int kLookupWarps = 8;     // warps per CTA
+constexpr int kQueue = 2 * kTile;   // pending re-probes of one tile (both strands)
+constexpr int kQueueWide = 2;       // queue entries re-probed per lane and pass
 
-// One warp per read.  Per tile of 128 start positions the warp stages the nucleotide codes in
-// shared memory, translates every codon start once for both strands (F = forward codon at x,
-// R = codon of the reverse strand whose lowest forward coordinate is x), then each lane packs
-// 4 forward + 4 reverse k-mers and issues their 8 sector loads back to back.  First probes are
-// resolved branch-free; the few lookups that ended on a flagged sector are compacted into a
-// per-warp shared-memory queue and re-probed 32 at a time, so the warp stays converged.
-// ids layout: forward k-mer starting at p -> ids[2*off + p]; reverse-strand k-mer starting at
-// reverse coordinate q -> ids[2*off + n + q]  (frame f record = entries f-1, f+2, f+5, ...).
+// Per-warp shared-memory scratch of the lookup: nucleotide codes, the two codon-start residue
+// arrays (F = forward codon at x, R = codon of the reverse strand whose lowest forward
+// coordinate is x) and the queue of lookups that must probe another sector.
 template <int K>
-__global__ void __launch_bounds__(kLookupWarps * 32)
-translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ nt,
-                        const uint64_t* __restrict__ read_off, uint64_t nreads,
-                        uint32_t* __restrict__ ids) {
-    constexpr int W = kTile + 3 * (K - 1);  // codon starts needed per tile
-    __shared__ uint8_t s_lut[72];
-    __shared__ uint8_t s_nt[kLookupWarps][W + 2 + 2];
-    __shared__ uint8_t s_f[kLookupWarps][W + 4];
-    __shared__ uint8_t s_r[kLookupWarps][W + 4];
-    __shared__ uint64_t q_h[kLookupWarps][kQueue];    // hash | next distance << 45 | level << 48
-    __shared__ uint32_t q_pos[kLookupWarps][kQueue];  // index into the read's ids slice
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+struct LookupSmem {
+    static constexpr int W = kTile + 3 * (K - 1);  // codon starts needed per tile
+    uint8_t nt[W + 4];
+    uint8_t f[W + 4];
+    uint8_t r[W + 4];
+    uint64_t q[kQueue];  // hash | next distance << 45 | level << 48 | strand << 50 | tile position << 51
+};
+
+// All k-mer lookups of one read by one warp.  Per tile of 128 start positions: nucleotide codes
+// to shared memory, every codon start translated once per strand through the 65-entry LUT
+// (codon -> 5-bit index-alphabet code), then per strand each lane packs 4 keys, issues their 4
+// sector loads back to back and resolves them branch-free; lookups that ended on a flagged
+// sector are compacted into the queue and re-probed 64 at a time (2 loads in flight per
+// lane), so the warp stays converged.  out: forward k-mer starting at p -> out[p]; reverse-strand
+// k-mer starting at reverse coordinate q -> out[n + q]  (frame f record = entries f-1, f+2, ...).
+template <int K>
+__device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s_lut, LookupSmem<K>& sm,
+                                            const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane) {
+    constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
-    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
-    __syncthreads();
     const ulonglong4* __restrict__ level0 = t.level[0];
     const uint32_t nlines0 = t.nlines[0];
-    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
-    for (uint64_t r = (uint64_t)blockIdx.x * kLookupWarps + warp; r < nreads; r += nwarps) {
-        const uint64_t off = read_off[r];
-        const uint32_t n = (uint32_t)(read_off[r + 1] - off);
-        if (n < 3u * K) continue;  // no frame reaches K residues
-        const uint32_t npos = n - 3u * K + 1;
-        uint32_t* out = ids + 2 * off;  // forward ids at [p], reverse ids at [n + q]
-        for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
-            for (int i = lane; i < W + 2; i += 32) {
-                const uint32_t x = w0 + i;
-                s_nt[warp][i] = x < n ? (uint8_t)nt_code(nt[off + x]) : (uint8_t)4;
-            }
-            __syncwarp();
-            for (int i = lane; i < W; i += 32) {
-                const uint32_t a = s_nt[warp][i], b = s_nt[warp][i + 1], c = s_nt[warp][i + 2];
-                const bool has_n = ((a | b | c) & 4u) != 0;
-                s_f[warp][i] = s_lut[has_n ? 64 : 16 * a + 4 * b + c];
-                s_r[warp][i] = s_lut[has_n ? 64 : 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2)];
-            }
-            __syncwarp();
-            uint64_t h[8];       // 0..3 forward, 4..7 reverse
-            ulonglong4 sec[8];
-            bool valid[8];
+    const uint32_t npos = n - 3u * K + 1;
+    for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
+        for (int i = lane; i < W + 2; i += 32) {
+            const uint32_t x = w0 + i;
+            sm.nt[i] = x < n ? (uint8_t)nt_code(nt[x]) : (uint8_t)4;
+        }
+        __syncwarp();
+        for (int i = lane; i < W; i += 32) {
+            const uint32_t a = sm.nt[i], b = sm.nt[i + 1], c = sm.nt[i + 2];
+            const bool has_n = ((a | b | c) & 4u) != 0;
+            sm.f[i] = s_lut[has_n ? 64 : 16 * a + 4 * b + c];
+            sm.r[i] = s_lut[has_n ? 64 : 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2)];
+        }
+        __syncwarp();
+        uint32_t qn = 0;
+#pragma unroll 1
+        for (int strand = 0; strand < 2; ++strand) {
+            const uint8_t* codes = strand ? sm.r : sm.f;
+            uint64_t h[4];
+            ulonglong4 sec[4];
+            bool valid[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int pl = lane + 32 * u;
-                uint64_t kf = 0, kr = 0;
-                uint32_t bad_f = 0, bad_r = 0;
+                uint64_t key = 0;
+                uint32_t bad = 0;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    const uint32_t cf = s_f[warp][pl + 3 * i];
-                    const uint32_t cr = s_r[warp][pl + 3 * (K - 1 - i)];
-                    bad_f |= cf;
-                    bad_r |= cr;
-                    kf = (kf << 5) | (cf & 31u);
-                    kr = (kr << 5) | (cr & 31u);
+                    // forward: residues at pl, pl+3, ...; reverse: the same codon starts read downwards
+                    const uint32_t c = codes[pl + 3 * (strand ? K - 1 - i : i)];
+                    bad |= c;
+                    key = (key << 5) | (c & 31u);
                 }
-                const bool live = w0 + pl < npos;
-                valid[u] = live && !(bad_f & 0x80u);
-                valid[u + 4] = live && !(bad_r & 0x80u);
-                h[u] = mix45(kf);
-                h[u + 4] = mix45(kr);
+                valid[u] = (w0 + pl < npos) && !(bad & 0x80u);
+                h[u] = mix45(key);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 4; ++u)
                 if (valid[u]) sec[u] = load_sector(level0 + probe_sector(h[u], nlines0, 0));
-            uint32_t qn = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t p = w0 + lane + 32 * (u & 3);
-                const uint32_t pos = u < 4 ? p : n + (npos - 1 - p);
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = w0 + lane + 32 * u;
+                const uint32_t pos = strand ? n + (npos - 1 - p) : p;
                 bool more = false;
                 uint32_t v = kNoValue;
                 if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
                 if (p < npos && !more) out[pos] = v;
                 const unsigned m = __ballot_sync(0xffffffffu, more);
-                if (more) {
-                    const uint32_t at = qn + __popc(m & lt_mask);
-                    q_h[warp][at] = h[u] | (1ull << 45);
-                    q_pos[warp][at] = pos;
-                }
+                if (more)
+                    sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)strand << 50) | ((uint64_t)(lane + 32 * u) << 51);
                 qn += __popc(m);
             }
-            __syncwarp();
-            // re-probe the flagged ones, densely packed: distance d, then d+1, ... then next level
-            while (qn) {
-                uint32_t qnext = 0;
-                for (uint32_t c = 0; c < qn; c += 32) {
-                    const uint32_t i = c + lane;
-                    const bool active = i < qn;
-                    uint64_t hq = 0;
-                    uint32_t pos = 0;
-                    if (active) {
-                        hq = q_h[warp][i];
-                        pos = q_pos[warp][i];
+        }
+        __syncwarp();
+        // re-probe the flagged ones, densely packed: distance d, then d+1, ... then the next level
+        while (qn) {
+            uint32_t qnext = 0;
+            for (uint32_t c = 0; c < qn; c += 32 * kQueueWide) {
+                uint64_t hq[kQueueWide];
+                ulonglong4 s2[kQueueWide];
+#pragma unroll
+                for (int j = 0; j < kQueueWide; ++j) {
+                    const uint32_t i = c + 32 * j + lane;
+                    hq[j] = i < qn ? sm.q[i] : ~0ull;
+                }
+#pragma unroll
+                for (int j = 0; j < kQueueWide; ++j)
+                    if (hq[j] != ~0ull) {
+                        const uint32_t lv = (uint32_t)(hq[j] >> 48) & 3u;
+                        s2[j] = load_sector(t.level[lv] + probe_sector(hq[j] & kKeyMask, t.nlines[lv], (uint32_t)(hq[j] >> 45) & 7u));
                     }
-                    uint32_t d = (uint32_t)(hq >> 45) & 7u;
-                    uint32_t lv = (uint32_t)(hq >> 48);
-                    const uint64_t hh = hq & kKeyMask;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < kQueueWide; ++j) {
                     bool more = false;
-                    if (active) {
-                        const ulonglong4 s2 = load_sector(t.level[lv] + probe_sector(hh, t.nlines[lv], d));
-                        const uint32_t v = probe_sector_data(s2, (d << 28) | ((uint32_t)hh & kTagMask), more);
+                    uint64_t next = 0;
+                    if (hq[j] != ~0ull) {
+                        uint32_t d = (uint32_t)(hq[j] >> 45) & 7u;
+                        uint32_t lv = (uint32_t)(hq[j] >> 48) & 3u;
+                        const uint64_t hh = hq[j] & kKeyMask;
+                        const uint32_t v = probe_sector_data(s2[j], (d << 28) | ((uint32_t)hh & kTagMask), more);
                         if (more && ++d == (uint32_t)kMaxDisp) {
                             d = 0;
                             if (++lv == (uint32_t)t.nlevels) more = false;  // v is kNoValue here
                         }
-                        if (!more) out[pos] = v;
+                        if (!more) {
+                            const uint32_t p = w0 + ((uint32_t)(hq[j] >> 51) & 127u);
+                            out[(hq[j] >> 50) & 1 ? n + (npos - 1 - p) : p] = v;
+                        }
+                        next = (hq[j] & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
                     }
-                    __syncwarp();
                     const unsigned m = __ballot_sync(0xffffffffu, more);
-                    if (more) {
-                        const uint32_t at = qnext + __popc(m & lt_mask);
-                        q_h[warp][at] = hh | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
-                        q_pos[warp][at] = pos;
-                    }
+                    if (more) sm.q[qnext + __popc(m & lt_mask)] = next;
                     qnext += __popc(m);
                 }
                 __syncwarp();
-                qn = qnext;
             }
+            qn = qnext;
         }
+    }
+}
+
+// Lookup kernel: one warp per read, ids to global memory.
+template <int K>
+__global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
+translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ nt,
+                        const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
+                        uint32_t* __restrict__ ids) {
+    __shared__ uint8_t s_lut[72];
+    __shared__ LookupSmem<K> s_sm[kLookupWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
+    for (uint64_t r = r_begin + (uint64_t)blockIdx.x * kLookupWarps + warp; r < r_end; r += nwarps) {
+        const uint64_t off = read_off[r];
+        const uint32_t n = (uint32_t)(read_off[r + 1] - off);
+        if (n < 3u * K) continue;  // no frame reaches K residues
+        lookup_read<K>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
     }
 }
 
@@ -237,92 +258,222 @@ struct ClassifyParams {
 };
 
 constexpr int kAggWarps = 4;
-constexpr uint32_t kAggCap = 512;  // ids of a 2 x 150 nt pair: <= 496
+constexpr int kAggSlots = 2;        // groups whose frame records share one warp pass
+constexpr uint32_t kAggCap = 256;   // run-length entries per group held in shared memory
 
 struct DevError {  // first error raised by a kernel
     unsigned int flag;
     unsigned int taxon;
 };
 
+// seedextend of one frame record (rec = read-in-group * 6 + frame) of group [r0, r1); the kept
+// ids leave as run-length pairs (id, occurrences) -- zeros are dropped (taxa2agg.rs:169) and the
+// aggregators only need the multiset.  Returns false when the record does not exist (:172).
+__device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const uint32_t* read_ids, uint32_t n,
+                                                 uint32_t fr /* 0,1,2 forward; 3,4,5 reverse */, uint32_t* A,
+                                                 uint32_t* C, uint32_t cap, uint32_t* counter, uint32_t* read_priv) {
+    const uint32_t f = fr % 3;
+    const uint32_t plen = n >= f ? (n - f) / 3 : 0;  // peptide length of the frame
+    if (plen < (uint32_t)cp.k) return false;
+    const uint32_t cnt = plen - cp.k + 1;
+    const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + f;
+    // private slice of this record: pair i at words 6i, 6i+1 past 2*(strand*n + f), inside the read's 4n words
+    uint32_t* priv = read_priv ? read_priv + 2 * ((fr >= 3 ? n : 0) + f) : nullptr;
+    uint32_t run_id = 0, run_len = 0;
+    auto flush_run = [&]() {
+        if (run_len) {
+            const uint32_t at = atomicAdd(counter, 1u);
+            if (at < cap) {
+                A[at] = run_id;
+                C[at] = run_len;
+            }
+        }
+    };
+    auto push = [&](uint32_t v) {
+        if (v == 0) return;
+        if (v == run_id) {
+            ++run_len;
+        } else {
+            flush_run();
+            run_id = v;
+            run_len = 1;
+        }
+    };
+    if (cp.seedextend && cp.one_on_one && priv) {
+        // Single pass of the seedextend machine (seedextend.rs:101-149) that builds the run-length
+        // list of the CURRENT range tentatively in the record's private slice and commits it when the
+        // range is selected / rolls it back when the range is abandoned -- no second walk over the
+        // selected ranges.  Zeros never break a run (they are dropped before counting).
+        uint32_t k = 0, committed = 0, rid = 0, rlen = 0;
+        auto close_run = [&]() {
+            if (rlen) {
+                priv[6 * k] = rid;
+                priv[6 * k + 1] = rlen;
+                ++k;
+            }
+            rid = 0;
+            rlen = 0;
+        };
+        auto feed = [&](uint32_t v) {
+            if (v == 0) return;
+            if (v == rid) {
+                ++rlen;
+            } else {
+                close_run();
+                rid = v;
+                rlen = 1;
+            }
+        };
+        auto at = [&](uint32_t i) -> uint32_t {
+            const uint32_t v = base[3 * i];
+            return v == kNoValue ? 0u : v;
+        };
+        // The four cases of the reference loop body are evaluated as predicates so that the lanes of
+        // a warp (one record each, different data) do not serialise on divergent branches; only the
+        // rare stores of closed runs branch.  The next element is fetched one iteration ahead.
+        uint32_t last = at(0), start = 0, same = 1, smax = 1;
+        feed(last);
+        uint32_t nxt = cnt > 1 ? at(1) : 0u;
+        for (uint32_t end = 1; end <= cnt; ++end) {
+            const uint32_t cur = nxt;                        // the sentinel 0 (:99) when end == cnt
+            nxt = end + 1 < cnt ? at(end + 1) : 0u;
+            const bool differs = cur != last;
+            const bool gap_close = differs && last == 0 && same > cp.max_gap;                // :116-127
+            const bool lead_gap = differs && !gap_close && last == 0 && end - start == same;  // :130-134
+            const bool other = differs && !gap_close && !lead_gap;                            // :137-142
+            if (gap_close) {  // the range ends before the gap: keep its runs if it holds a seed
+                close_run();
+                if (smax >= cp.min_seed) committed = k; else k = committed;
+            }
+            smax = gap_close ? 1u : (other && last != 0 && same > smax) ? same : smax;
+            start = gap_close ? end : lead_gap ? end + 1 : start;
+            same = !differs ? same + 1 : lead_gap ? same : 1u;   // a leading gap leaves last / same stale
+            last = lead_gap ? last : cur;
+            if (!lead_gap && end < cnt) feed(cur);               // a leading gap also skips t[end]
+        }
+        close_run();
+        if (smax >= cp.min_seed) committed = k;              // :144-149 (trailing zeros carry no ids)
+        if (committed) {
+            const uint32_t to = atomicAdd(counter, committed);
+            if (to + committed <= cap && to + committed >= to)
+                for (uint32_t i = 0; i < committed; ++i) {
+                    A[to + i] = priv[6 * i];
+                    C[to + i] = priv[6 * i + 1];
+                }
+        }
+        return true;
+    }
+    if (cp.seedextend) {
+        seedextend_stream(base, 3, cnt, cp.one_on_one != 0, cp.min_seed, cp.max_gap, push);
+    } else {
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t v = base[3 * i];
+            if (v != kNoValue) push(v);
+        }
+    }
+    flush_run();
+    return true;
+}
+
+// The same for record rec (= read-in-group * 6 + frame) of the group starting at read r0, ids in
+// global memory.
+__device__ __forceinline__ bool seedextend_record(const ClassifyParams& cp, const uint32_t* __restrict__ ids,
+                                                  const uint64_t* __restrict__ read_off, uint64_t r0, uint32_t rec,
+                                                  uint32_t* A, uint32_t* C, uint32_t cap, uint32_t* counter,
+                                                  uint32_t* scratch) {
+    // scratch holds 12 words per nucleotide: a group's slice is [12*off(r0), ...): first 4 words per
+    // nucleotide of private record slices, then the four overflow lists of 2 words per nucleotide
+    const uint64_t r = r0 + rec / 6;
+    const uint64_t off = read_off[r], off0 = read_off[r0];
+    return seedextend_frame(cp, ids + 2 * off, (uint32_t)(read_off[r + 1] - off), rec % 6, A, C, cap, counter,
+                            scratch + 12 * off0 + 4 * (off - off0));
+}
+
+// One warp per pair of groups: the frame records of both groups (2 x 12 for read pairs) run their
+// seedextend machines side by side, one lane each; each group is then aggregated by the whole warp.
 __global__ void __launch_bounds__(kAggWarps * 32)
 classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                 const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ group_off,
-                uint64_t ngroups, uint32_t* __restrict__ scratch, uint32_t* __restrict__ taxon_out,
-                DevError* err) {
-    __shared__ uint32_t s_a[kAggWarps][kAggCap];
+                uint64_t g_begin, uint64_t ngroups /* end of the group range */, uint32_t* __restrict__ scratch,
+                uint32_t* __restrict__ taxon_out, DevError* err) {
+    __shared__ uint32_t s_a[kAggWarps][kAggSlots][kAggCap];
+    __shared__ uint32_t s_c[kAggWarps][kAggSlots][kAggCap];
     __shared__ uint32_t s_p[kAggWarps][kAggCap + 1];
     __shared__ uint32_t s_l[kAggWarps][kAggCap];
-    __shared__ uint32_t s_cnt[kAggWarps];
+    __shared__ uint32_t s_cnt[kAggWarps][kAggSlots];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * kAggWarps;
-    for (uint64_t g = (uint64_t)blockIdx.x * kAggWarps + warp; g < ngroups; g += nwarps) {
-        const uint64_t r0 = group_off[g], r1 = group_off[g + 1];
-        const uint64_t nrec = (r1 - r0) * 6;
-        uint32_t* A = s_a[warp];
-        uint32_t* P = s_p[warp];
-        uint32_t* L = s_l[warp];
-        uint32_t cap = kAggCap;
-        bool present = false;
-        uint32_t total = 0;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (lane == 0) s_cnt[warp] = 0;
-            __syncwarp();
+    const uint64_t nunits = (ngroups - g_begin + kAggSlots - 1) / kAggSlots;
+    for (uint64_t unit = (uint64_t)blockIdx.x * kAggWarps + warp; unit < nunits; unit += nwarps) {
+        const uint64_t g_base = g_begin + unit * kAggSlots;
+        const int ng = (int)((ngroups - g_base) < (uint64_t)kAggSlots ? (ngroups - g_base) : kAggSlots);
+        uint64_t r0[kAggSlots], nrec[kAggSlots];
+        for (int sl = 0; sl < kAggSlots; ++sl) {
+            r0[sl] = sl < ng ? group_off[g_base + sl] : 0;
+            nrec[sl] = sl < ng ? (group_off[g_base + sl + 1] - r0[sl]) * 6 : 0;
+        }
+        if (lane < kAggSlots) s_cnt[warp][lane] = 0;
+        __syncwarp();
+        unsigned present = 0;  // bit sl: group sl produced at least one record
+        if (nrec[0] + nrec[1] <= 32) {  // the common case: all records of both groups in one pass
+            const int sl = (uint64_t)lane < nrec[0] ? 0 : 1;
+            const uint64_t rec = sl ? lane - nrec[0] : lane;
             bool any = false;
-            for (uint64_t rec = lane; rec < nrec; rec += 32) {
-                const uint64_t r = r0 + rec / 6;
-                const uint32_t fr = (uint32_t)(rec % 6);  // 0,1,2 forward; 3,4,5 reverse
-                const uint64_t off = read_off[r];
-                const uint32_t n = (uint32_t)(read_off[r + 1] - off);
-                const uint32_t f = fr % 3;
-                const uint32_t plen = n >= f ? (n - f) / 3 : 0;  // peptide length of the frame
-                if (plen < (uint32_t)cp.k) continue;             // record dropped (:172)
-                any = true;
-                const uint32_t cnt = plen - cp.k + 1;
-                const uint32_t* base = ids + 2 * off + (fr >= 3 ? n : 0) + f;
-                auto push = [&](uint32_t v) {
-                    if (v == 0) return;  // taxa2agg.rs:169
-                    const uint32_t at = atomicAdd(&s_cnt[warp], 1u);
-                    if (at < cap) A[at] = v;
-                };
-                if (cp.seedextend) {
-                    seedextend_stream(base, 3, cnt, cp.one_on_one != 0, cp.min_seed, cp.max_gap, push);
-                } else {
-                    for (uint32_t i = 0; i < cnt; ++i) {
-                        const uint32_t v = base[3 * i];
-                        if (v != kNoValue) push(v);
-                    }
+            if (rec < nrec[sl])
+                any = seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, s_a[warp][sl], s_c[warp][sl], kAggCap, &s_cnt[warp][sl], scratch);
+            const unsigned m = __ballot_sync(0xffffffffu, any);
+            const unsigned lanes0 = nrec[0] >= 32 ? 0xffffffffu : ((1u << nrec[0]) - 1);
+            present = ((m & lanes0) ? 1u : 0u) | ((m & ~lanes0) ? 2u : 0u);
+        } else {
+            for (int sl = 0; sl < ng; ++sl) {
+                bool any = false;
+                for (uint64_t rec = lane; rec < nrec[sl]; rec += 32)
+                    any |= seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, s_a[warp][sl], s_c[warp][sl], kAggCap, &s_cnt[warp][sl], scratch);
+                if (__any_sync(0xffffffffu, any)) present |= 1u << sl;
+            }
+        }
+        __syncwarp();
+        for (int sl = 0; sl < ng; ++sl) {
+            uint32_t* A = s_a[warp][sl];
+            uint32_t* C = s_c[warp][sl];
+            uint32_t* P = s_p[warp];
+            uint32_t* L = s_l[warp];
+            uint32_t total = s_cnt[warp][sl];
+            if (total > kAggCap) {
+                // rare: more runs than the shared-memory list holds -> redo into the group's own slice
+                // of the global scratch (after the private record slices: four lists of gsize words; the number
+                // of runs is below gsize because a read yields fewer k-mers than 2x its length)
+                const uint64_t r1 = r0[sl] + nrec[sl] / 6;
+                const uint64_t gsize = 2 * (read_off[r1] - read_off[r0[sl]]);
+                const uint64_t gbase = 12 * read_off[r0[sl]] + 2 * gsize;  // past the private record slices
+                A = scratch + gbase;
+                C = A + gsize;
+                P = C + gsize;
+                L = P + gsize;
+                __syncwarp();
+                if (lane == 0) s_cnt[warp][sl] = 0;
+                __syncwarp();
+                for (uint64_t rec = lane; rec < nrec[sl]; rec += 32)
+                    seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, A, C, 0xFFFFFFFFu, &s_cnt[warp][sl], scratch);
+                __threadfence_block();
+                __syncwarp();
+                total = s_cnt[warp][sl];
+            }
+            uint32_t res;
+            if (!(present >> sl & 1)) {
+                res = UMGAP_ABSENT;
+            } else {
+                uint32_t bad = 0;
+                res = warp_aggregate<true>(tv, A, C, P, L, total, cp.agg, lane, &bad);
+                const uint32_t bad_any = __reduce_max_sync(0xffffffffu, bad);
+                if (res == kAggUnknown) {
+                    if (lane == 0 && atomicCAS(&err->flag, 0u, 1u) == 0u) err->taxon = bad_any;
+                    res = UMGAP_ABSENT;
                 }
             }
-            present = __any_sync(0xffffffffu, any);
-            __syncwarp();
-            total = s_cnt[warp];
-            if (total <= cap) break;
-            // rare: more kept ids than the shared-memory list holds -> redo into global scratch
-            // (the group's own slice of a buffer as large as `ids`, split in three)
-            // (scratch holds 6 words per nucleotide: the group's slice is split in three lists of
-            // gsize words; total < gsize because a read yields fewer k-mers than 2x its length)
-            const uint64_t gbase = 6 * read_off[r0];
-            const uint64_t gsize = 2 * (read_off[r1] - read_off[r0]);
-            A = scratch + gbase;
-            P = scratch + gbase + gsize;
-            L = scratch + gbase + 2 * gsize;
-            cap = 0xFFFFFFFFu;
+            if (lane == 0) taxon_out[g_base + sl] = res;
             __syncwarp();
         }
-        uint32_t res;
-        if (!present) {
-            res = UMGAP_ABSENT;
-        } else {
-            uint32_t bad = 0;
-            res = warp_aggregate(tv, A, P, L, total, cp.agg, lane, &bad);
-            const uint32_t bad_any = __reduce_max_sync(0xffffffffu, bad);
-            if (res == kAggUnknown) {
-                if (lane == 0 && atomicCAS(&err->flag, 0u, 1u) == 0u) err->taxon = bad_any;
-                res = UMGAP_ABSENT;
-            }
-        }
-        if (lane == 0) taxon_out[g] = res;
-        __syncwarp();
     }
 }
 
@@ -394,21 +545,21 @@ struct LaunchTimer {
 };
 }  // namespace
 
+// Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
-                                    const uint8_t* nt_dev, const uint64_t* read_off_dev,
-                                    uint64_t nreads, uint32_t* ids_dev, cudaStream_t st) {
-    if (!nreads) return;
+                                    const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
+                                    uint64_t r_end, uint32_t* ids_dev, cudaStream_t st) {
+    if (r_end <= r_begin) return;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
     const TableView tv = idx->view();
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kLookupWarps), 148ull * 32);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(r_end - r_begin, kLookupWarps), 148ull * 32);
     LaunchTimer timer(0, st);
     switch (idx->k) {
-#define UMGAP_CASE(KK)                                                                           \
-    case KK:                                                                                     \
-        translate_lookup_kernel<KK><<<blocks, kLookupWarps * 32, 0, st>>>(tv, lut, nt_dev,        \
-                                                                          read_off_dev, nreads,  \
-                                                                          ids_dev);              \
+#define UMGAP_CASE(KK)                                                                                      \
+    case KK:                                                                                                \
+        translate_lookup_kernel<KK><<<blocks, kLookupWarps * 32, 0, st>>>(tv, lut, nt_dev, read_off_dev,     \
+                                                                          r_begin, r_end, ids_dev);         \
         break;
         UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
         UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
@@ -422,17 +573,30 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
 
 static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
                             const umgap_pipeline_opts* o, const uint32_t* ids_dev,
-                            const uint64_t* read_off_dev, const uint64_t* group_off_dev,
-                            uint64_t ngroups, uint32_t* scratch_dev, uint32_t* out_dev, DevError* err,
+                            const uint64_t* read_off_dev, const uint64_t* group_off_dev, uint64_t g_begin,
+                            uint64_t g_end, uint32_t* scratch_dev, uint32_t* out_dev, DevError* err,
                             cudaStream_t st) {
-    if (!ngroups) return;
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ngroups, kAggWarps), 148ull * 64);
+    if (g_end <= g_begin) return;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(g_end - g_begin, kAggSlots), kAggWarps), 148ull * 64);
     LaunchTimer timer(1, st);
     classify_kernel<<<blocks, kAggWarps * 32, 0, st>>>(tax->view, make_params(idx, o), ids_dev,
-                                                       read_off_dev, group_off_dev, ngroups,
+                                                       read_off_dev, group_off_dev, g_begin, g_end,
                                                        scratch_dev, out_dev, err);
     UMGAP_CUDA(cudaGetLastError());
     timer.stop();
+}
+
+// The whole device-side classification of one batch: lookup kernel, then classify kernel.
+// (Running the classify kernel of one slice concurrently with the lookup kernel of the next, on two
+// streams with priorities, was measured and gives nothing: both kernels want the same registers
+// and issue slots -- profiles/README.md.)
+static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
+                            const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
+                            const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
+                            uint32_t* out_dev, DevError* err, cudaStream_t st) {
+    if (!ngroups) return;
+    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, st);
+    launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, scratch_dev, out_dev, err, st);
 }
 
 static void raise_dev_error(const DevError& e) {
@@ -489,7 +653,7 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
     return guarded([&] {
         check_opts(idx, nullptr, opts);
         use_device(idx->device);
-        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, nreads, ids_dev, (cudaStream_t)stream);
+        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, 0, nreads, ids_dev, (cudaStream_t)stream);
     });
 }
 
@@ -504,11 +668,10 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
         use_device(idx->device);
         cudaStream_t st = (cudaStream_t)stream;
         uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS, (2 * total_nt + 64) * sizeof(uint32_t));
-        uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (6 * total_nt + 64) * sizeof(uint32_t));
+        uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
-        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, nreads, ids, st);
-        launch_classify(idx, tax, opts, ids, read_off_dev, group_off_dev, ngroups, scratch,
+        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, group_off_dev, ngroups, ids, scratch,
                         taxon_out_dev, err, st);
     });
 }
@@ -569,14 +732,13 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                 // ids/scratch are shared by both chunks' kernels: kernels of consecutive chunks
                 // are ordered through `done` below, copies overlap freely.
                 uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS, (2 * std::max(cnt_nt, kChunkNt) + 64) * 4);
-                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (6 * std::max(cnt_nt, kChunkNt) + 64) * 4);
+                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * std::max(cnt_nt, kChunkNt) + 64) * 4);
                 cudaStream_t s = st[buf];
                 UMGAP_CUDA(cudaMemcpyAsync(d_nt, nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
                 UMGAP_CUDA(cudaMemcpyAsync(d_roff, h_roff[buf].data(), (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
                 UMGAP_CUDA(cudaMemcpyAsync(d_goff, h_goff[buf].data(), (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
                 if (used[buf ^ 1]) UMGAP_CUDA(cudaStreamWaitEvent(s, done[buf ^ 1], 0));
-                launch_translate_lookup(idx, opts, d_nt, d_roff, cnt_r, ids, s);
-                launch_classify(idx, tax, opts, ids, d_roff, d_goff, cnt_g, scratch, d_out, err, s);
+                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, d_goff, cnt_g, ids, scratch, d_out, err, s);
                 UMGAP_CUDA(cudaEventRecord(done[buf], s));
                 UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
                 used[buf] = true;

@@ -152,7 +152,7 @@ aggregate_kernel(TaxView tv, AggParams ap, const uint32_t* __restrict__ taxa,
         }
         __syncwarp();
         uint32_t bad = 0;
-        uint32_t res = warp_aggregate(tv, A, P, L, n, ap, lane, &bad);
+        uint32_t res = warp_aggregate<false>(tv, A, nullptr, P, L, n, ap, lane, &bad);
         bad = __reduce_max_sync(0xffffffffu, bad);
         if (res == kAggUnknown) {
             if (lane == 0 && atomicCAS(&err[0], 0u, 1u) == 0u) err[1] = bad;

@@ -29,15 +29,15 @@ __device__ __forceinline__ uint32_t lca_ids(const TaxView& t, uint32_t ia, uint3
 // the ancestor matrix; the deepest ancestor whose interval covers b wins.  All lanes must call.
 __device__ __forceinline__ uint32_t warp_lca(const TaxView& t, uint32_t a, uint32_t b, int lane) {
     if (a == b) return a;
-    const int da = t.depth[a];
+    const int da = __ldg(t.depth + a);
     uint32_t best = 0;  // the root (dense 0) covers everything
     for (int base = 0; base <= da; base += 32) {
         const int d = base + lane;
         uint32_t x = 0;
         bool covers = false;
         if (d <= da) {
-            x = t.anc[(uint64_t)a * t.stride + d];
-            covers = t.last[x] >= b;
+            x = __ldg(t.anc + (uint64_t)a * t.stride + d);
+            covers = __ldg(t.last + x) >= b;
         }
         const unsigned m = __ballot_sync(0xffffffffu, covers);
         if (m) {

@@ -53,7 +53,7 @@ static void build(umgap_taxonomy* tax, const std::vector<uint64_t>& ids,
     if (n == 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "empty taxonomy");
     uint64_t max_id = 0;
     for (uint64_t id : ids) max_id = std::max(max_id, id);
-    if (max_id >= 0xFFFFFFFEull) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "taxon ids must fit 32 bits");
+    if (max_id >= 0xFFFFFFF0ull) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "taxon ids must be below 2^32 - 16");
     // TaxonList::new: dense by id, a later line with the same id replaces an earlier one
     std::vector<int64_t> row_of(max_id + 1, -1);
     for (size_t i = 0; i < n; ++i) row_of[ids[i]] = (int64_t)i;

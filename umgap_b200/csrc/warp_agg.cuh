@@ -94,16 +94,24 @@ __device__ __forceinline__ void seedextend_stream(const uint32_t* ids, uint32_t 
 }
 
 // ---- warp utilities ----------------------------------------------------------------------------
-__device__ __forceinline__ void cmpex(uint32_t* a, uint32_t i, uint32_t l) {
+template <bool KV>
+__device__ __forceinline__ void cmpex(uint32_t* a, uint32_t* c, uint32_t i, uint32_t l) {
     const uint32_t x = a[i], y = a[l];
     if (x > y) {
         a[i] = y;
         a[l] = x;
+        if (KV) {
+            const uint32_t t = c[i];
+            c[i] = c[l];
+            c[l] = t;
+        }
     }
 }
 
-// Ascending bitonic sort of a[0..n) for any n (indices >= n behave as +infinity).
-__device__ __forceinline__ void warp_sort(uint32_t* a, uint32_t n, int lane) {
+// Ascending bitonic sort of a[0..n) for any n (indices >= n behave as +infinity); with KV the
+// payload c[] moves with its key.
+template <bool KV>
+__device__ __forceinline__ void warp_sort(uint32_t* a, uint32_t* c, uint32_t n, int lane) {
     if (n < 2) return;
     uint32_t np2 = 1;
     while (np2 < n) np2 <<= 1;
@@ -113,13 +121,13 @@ __device__ __forceinline__ void warp_sort(uint32_t* a, uint32_t n, int lane) {
         for (uint32_t t = lane; t < pairs; t += 32) {
             const uint32_t blk = t / hk, r = t - blk * hk;
             const uint32_t i = blk * k + r, l = blk * k + (k - 1 - r);
-            if (l < n) cmpex(a, i, l);
+            if (l < n) cmpex<KV>(a, c, i, l);
         }
         __syncwarp();
         for (uint32_t j = k >> 2; j > 0; j >>= 1) {
             for (uint32_t t = lane; t < pairs; t += 32) {
                 const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                if (l < n) cmpex(a, i, l);
+                if (l < n) cmpex<KV>(a, c, i, l);
             }
             __syncwarp();
         }
@@ -174,10 +182,12 @@ struct AggParams {
 
 constexpr uint32_t kAggUnknown = 0xFFFFFFFDu;  // internal: record holds an id unknown to the tree
 
-// Aggregates one record.  A[0..n) holds its non-zero taxon ids (any order); P needs n+1 and L
-// needs n entries of scratch.  Returns the snapped taxon id, the literal 1 for an empty record
+// Aggregates one record.  A[0..n) holds its non-zero taxon ids (any order) and, with KV, C[0..n)
+// how many times each entry occurred (run-length compressed input); P needs n+1 and L needs n
+// entries of scratch.  Returns the snapped taxon id, the literal 1 for an empty record
 // (taxa2agg.rs:174-175), or kAggUnknown with *bad_id set.  All 32 lanes must call.
-__device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* A, uint32_t* P,
+template <bool KV>
+__device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* A, uint32_t* C, uint32_t* P,
                                                    uint32_t* L, uint32_t n, const AggParams& ap,
                                                    int lane, uint32_t* bad_id) {
     if (n == 0) return 1u;
@@ -185,7 +195,7 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     bool bad = false;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t id = A[i];
-        const uint32_t d = id <= tv.max_id ? tv.dense_of[id] : kNoTaxon;
+        const uint32_t d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
         if (d == kNoTaxon) {
             bad = true;
             *bad_id = id;
@@ -195,7 +205,20 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     __syncwarp();
     if (__any_sync(0xffffffffu, bad)) return kAggUnknown;
     // 2. sort, 3. distinct + run starts
-    warp_sort(A, n, lane);
+    warp_sort<KV>(A, C, n, lane);
+    uint32_t occurrences = n;
+    if (KV) {  // C <- exclusive prefix sums of the occurrence counts (run start "positions")
+        uint32_t run = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t c = i < n ? C[i] : 0u;
+            const uint32_t incl = warp_incl_scan(c, lane);
+            if (i < n) C[i] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        occurrences = run;
+        __syncwarp();
+    }
     uint32_t m = 0;
     uint32_t carry = kNoTaxon;
     for (uint32_t base = 0; base < n; base += 32) {
@@ -208,14 +231,16 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
         const uint32_t rank = __popc(mask & ((1u << lane) - 1));
         carry = __shfl_sync(0xffffffffu, v, 31);
         __syncwarp();
+        const uint32_t startpos = KV ? (i < n ? C[i] : 0u) : i;
+        __syncwarp();
         if (head) {
             A[m + rank] = v;
-            P[m + rank] = i;
+            P[m + rank] = startpos;
         }
         m += __popc(mask);
         __syncwarp();
     }
-    if (lane == 0) P[m] = n;
+    if (lane == 0) P[m] = occurrences;
     __syncwarp();
     // 4. counts, lower-bound filter (agg/mod.rs:39-44: keep count >= lower_bound, f32 compare),
     //    exclusive prefix sums of the kept counts into P
@@ -243,7 +268,7 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     m = kept;
     if (m == 0) return 1u;  // everything filtered: the literal "1"
     if (lane == 0) P[m] = running;
-    for (uint32_t j = lane; j < m; j += 32) L[j] = tv.last[A[j]];
+    for (uint32_t j = lane; j < m; j += 32) L[j] = __ldg(tv.last + A[j]);
     __syncwarp();
 
     uint32_t result;
@@ -259,11 +284,11 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
             uint32_t g = lo;
             if (g < hi && A[g] == base_node) ++g;  // the base itself is not one of its children
             if (g >= hi) break;                    // no children: stop (tree/mix.rs:51)
-            const uint32_t child_depth = (uint32_t)tv.depth[base_node] + 1;
+            const uint32_t child_depth = (uint32_t)__ldg(tv.depth + base_node) + 1;
             uint32_t best = 0, best_lo = 0, best_hi = 0;
             while (g < hi) {
-                const uint32_t c = tv.anc[(uint64_t)A[g] * tv.stride + child_depth];
-                const uint32_t e = warp_upper_bound(A, g, hi, tv.last[c], lane);
+                const uint32_t c = __ldg(tv.anc + (uint64_t)A[g] * tv.stride + child_depth);
+                const uint32_t e = warp_upper_bound(A, g, hi, __ldg(tv.last + c), lane);
                 const uint32_t sub = P[e] - P[g];
                 if (sub > best) {  // first maximal child in preorder wins ties
                     best = sub;
@@ -307,7 +332,7 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
         }
         result = A[best_j];
     }
-    return ap.ranked_only ? tv.snap_ranked[result] : tv.snap_valid[result];
+    return ap.ranked_only ? __ldg(tv.snap_ranked + result) : __ldg(tv.snap_valid + result);
 }
 
 }  // namespace umgap
