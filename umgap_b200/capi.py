@@ -313,19 +313,22 @@ def aggregate(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, strategy: in
 
 
 def classify_reads(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarray,
-                   read_off: np.ndarray, group_off: np.ndarray):
-    """umgap_classify_reads (host buffers): returns (taxon per group, number of lookups)."""
+                   read_off: np.ndarray, group_off: np.ndarray, count_lookups: bool = True,
+                   out: Optional[np.ndarray] = None):
+    """umgap_classify_reads (host buffers): returns (taxon per group, number of lookups or None).
+    `out` may be a caller-provided (e.g. pinned) uint32 array of at least ngroups entries."""
     lib = load_library()
     nt = _arr(nt, np.uint8)
     read_off = _arr(read_off, np.uint64)
     group_off = _arr(group_off, np.uint64)
     ngroups = len(group_off) - 1
-    out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
     nl = C.c_uint64()
     _check(lib.umgap_classify_reads(index._h, tax._h, C.byref(opts), _p(nt), _p(read_off),
                                     C.c_uint64(len(read_off) - 1), _p(group_off),
-                                    C.c_uint64(ngroups), _p(out), C.byref(nl)))
-    return out[:ngroups], nl.value
+                                    C.c_uint64(ngroups), _p(out), C.byref(nl) if count_lookups else None))
+    return out[:ngroups], (nl.value if count_lookups else None)
 
 
 def classify_reads_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, nt_ptr: int,

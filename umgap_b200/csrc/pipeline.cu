@@ -477,12 +477,19 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
     }
 }
 
+// Subtracts the chunk's first nucleotide / first read from uploaded offset slices.
+__global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_t* b, uint64_t nb, uint64_t base_b) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) a[i] -= base_a;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] -= base_b;
+}
+
 }  // namespace umgap
 
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 5, WS_GOFF = 7, WS_OUT = 9 };
+enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12 };  // x3 buffers
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -698,57 +705,61 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         if (!ngroups) return;
         if (group_off[ngroups] != nreads || group_off[0] != 0)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off must cover reads 0..nreads");
-        // Chunked, double-buffered: while chunk c computes on its stream, chunk c+1 uploads.
-        const uint64_t kChunkNt = 96ull << 20;  // nucleotides per chunk
-        cudaStream_t st[2];
-        cudaEvent_t done[2];
-        for (int i = 0; i < 2; ++i) {
+        // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
+        // nucleotides and offsets of the next chunks upload and the results of the previous one
+        // download.  Offsets are uploaded as given and rebased on the device.
+        const uint64_t kChunkNt = 24ull << 20;  // nucleotides per chunk
+        constexpr int kBufs = 3;
+        cudaStream_t st[kBufs];
+        cudaEvent_t done[kBufs];
+        for (int i = 0; i < kBufs; ++i) {
             UMGAP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
             UMGAP_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         }
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
-        std::vector<uint64_t> h_roff[2], h_goff[2];
+        // nucleotides before group g (monotone in g): chunk ends are found by bisection
+        auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
         uint64_t g0 = 0;
-        int buf = 0;
-        bool used[2] = {false, false};
+        int buf = 0, prev = -1;
         try {
             while (g0 < ngroups) {
-                // extend the chunk group by group up to kChunkNt nucleotides (at least one group)
-                uint64_t g1 = g0;
-                const uint64_t nt0 = read_off[group_off[g0]];
-                while (g1 < ngroups && (g1 == g0 || read_off[group_off[g1 + 1]] - nt0 <= kChunkNt)) ++g1;
+                const uint64_t nt0 = nt_before(g0);
+                uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= kChunkNt, at least g0 + 1
+                while (lo < hi) {
+                    const uint64_t mid = lo + (hi - lo + 1) / 2;
+                    if (nt_before(mid) - nt0 <= kChunkNt) lo = mid; else hi = mid - 1;
+                }
+                const uint64_t g1 = lo;
                 const uint64_t r0 = group_off[g0], r1 = group_off[g1];
                 const uint64_t cnt_nt = read_off[r1] - nt0, cnt_r = r1 - r0, cnt_g = g1 - g0;
-                if (used[buf]) UMGAP_CUDA(cudaEventSynchronize(done[buf]));  // host vectors reusable
-                h_roff[buf].resize(cnt_r + 1);
-                for (uint64_t i = 0; i <= cnt_r; ++i) h_roff[buf][i] = read_off[r0 + i] - nt0;
-                h_goff[buf].resize(cnt_g + 1);
-                for (uint64_t i = 0; i <= cnt_g; ++i) h_goff[buf][i] = group_off[g0 + i] - r0;
-                uint8_t* d_nt = (uint8_t*)idx->ws.get(WS_NT + buf, cnt_nt + 64);
-                uint64_t* d_roff = (uint64_t*)idx->ws.get(WS_ROFF + buf, (cnt_r + 1) * 8);
-                uint64_t* d_goff = (uint64_t*)idx->ws.get(WS_GOFF + buf, (cnt_g + 1) * 8);
-                uint32_t* d_out = (uint32_t*)idx->ws.get(WS_OUT + buf, cnt_g * 4 + 16);
-                // ids/scratch are shared by both chunks' kernels: kernels of consecutive chunks
-                // are ordered through `done` below, copies overlap freely.
-                uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS, (2 * std::max(cnt_nt, kChunkNt) + 64) * 4);
-                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * std::max(cnt_nt, kChunkNt) + 64) * 4);
+                const uint64_t cap_nt = std::max(cnt_nt, kChunkNt);
+                uint8_t* d_nt = (uint8_t*)idx->ws.get(WS_NT + buf, cap_nt + 64);
+                uint64_t* d_roff = (uint64_t*)idx->ws.get(WS_ROFF + buf, (std::max<uint64_t>(cnt_r, kChunkNt / 32) + 1) * 8);
+                uint64_t* d_goff = (uint64_t*)idx->ws.get(WS_GOFF + buf, (std::max<uint64_t>(cnt_g, kChunkNt / 32) + 1) * 8);
+                uint32_t* d_out = (uint32_t*)idx->ws.get(WS_OUT + buf, std::max<uint64_t>(cnt_g, kChunkNt / 32) * 4 + 16);
+                // ids / scratch are shared by all chunks: the kernels of consecutive chunks are ordered
+                // through `done`, the copies around them overlap freely
+                uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS, (2 * cap_nt + 64) * 4);
+                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * cap_nt + 64) * 4);
                 cudaStream_t s = st[buf];
                 UMGAP_CUDA(cudaMemcpyAsync(d_nt, nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
-                UMGAP_CUDA(cudaMemcpyAsync(d_roff, h_roff[buf].data(), (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
-                UMGAP_CUDA(cudaMemcpyAsync(d_goff, h_goff[buf].data(), (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
-                if (used[buf ^ 1]) UMGAP_CUDA(cudaStreamWaitEvent(s, done[buf ^ 1], 0));
+                UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
+                UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
+                rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, d_goff, cnt_g + 1, r0);
+                UMGAP_CUDA(cudaGetLastError());
+                if (prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
                 launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, d_goff, cnt_g, ids, scratch, d_out, err, s);
                 UMGAP_CUDA(cudaEventRecord(done[buf], s));
                 UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
-                used[buf] = true;
-                buf ^= 1;
+                prev = buf;
+                buf = (buf + 1) % kBufs;
                 g0 = g1;
             }
-            for (int i = 0; i < 2; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
+            for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
             DevError he;
             UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < kBufs; ++i) {
                 cudaStreamDestroy(st[i]);
                 cudaEventDestroy(done[i]);
             }
