@@ -401,3 +401,111 @@ def test_tryptic_lookup_matches_oracle(capi, world, tmp_path):
         assert olookup.tryptic_digest(line) == olookup.tryptic_digest_regex(line)
     with pytest.raises(capi.UmgapError):
         capi.tryp_lookup(world["gidx"], aa, off)   # a k-mer table is not a peptide table
+
+
+def test_large_batch_matches_c_port(capi, tmp_path):
+    """50 000 synthetic pairs against a 2e6-key index: the CUDA path (through the fst loader) and the C
+    restatement of the reference algorithm agree on every pair for LCA* (deterministic), and on every
+    pair whose hybrid / MRTL answer is unique; the others lie in the Python oracle's admissible set."""
+    from oracle import cport, synth
+    taxa = datagen.make_taxonomy(2000, seed=81)
+    otax = OTaxonomy(taxa)
+    pre = synth.Preorder(taxa)
+    n_prot, plen = 5000, 408
+    keys, vals = synth.build_index(9, n_prot, plen, 70, 20, pre)
+    img_bytes = cport.fst_build_blob(keys.reshape(-1), np.arange(0, 9 * len(keys) + 1, 9, dtype=np.uint64), vals)
+    path = tmp_path / "synth.fst"
+    path.write_bytes(img_bytes)
+    gidx = capi.Index.load_fst(str(path), k=9)
+    assert gidx.info().n_keys == len(keys)
+    gtax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(taxa))
+    ctax = cport.RefTaxonomy(taxa)
+    img = cport.FstImage(img_bytes)
+    npairs = 50000
+    reads = synth.reads(9, n_prot, plen, 4, 0, npairs, 150, 70)
+    nt = reads.reshape(-1)
+    off = np.arange(0, len(nt) + 1, 150, dtype=np.uint64)
+    goff = np.arange(0, 2 * npairs + 1, 2, dtype=np.uint64)
+    index_dict = None
+    for strategy, s, g, lb in [(0, 3, 0, 0.0), (1, 3, 0, 0.0), (2, 2, 1, 1.0), (1, 2, 1, 2.0)]:
+        gopts = capi.default_opts(min_seed_size=s, max_gap_size=g, strategy=strategy, factor=0.25, lower_bound=lb)
+        got, nlook = capi.classify_reads(gidx, gtax, gopts, nt, off, goff)
+        copts = cport.RefOpts(table=1, methionine=0, one_on_one=1, seedextend=1, min_seed_size=s, max_gap_size=g,
+                              strategy=strategy, factor=0.25, lower_bound=lb, ranked_only=0, k=9)
+        want, nl, nh = cport.classify(img, ctax, copts, nt, off, goff, threads=os.cpu_count() or 1)
+        assert nlook == nl == npairs * 2 * 248
+        diff = np.nonzero(got != want)[0]
+        assert (got != 1).mean() > (0.5 if strategy else 0.05)   # LCA* falls to the root on any unrelated hit
+        if strategy == 0:
+            assert len(diff) == 0
+            continue
+        assert len(diff) < npairs * 0.02, len(diff)   # only tie-breaks may differ
+        if index_dict is None:
+            index_dict = {bytes(k): int(v) for k, v in zip(keys, vals)}
+        oidx = olookup.DictIndex(index_dict)
+        for gi in diff[:200]:
+            pair = [(f"r{gi}/1", bytes(reads[2 * gi]).decode()), (f"r{gi}/2", bytes(reads[2 * gi + 1]).decode())]
+            admissible = opipe.classify_reads(pair, oidx, otax, min_seed_size=s, max_gap_size=g, strategy=strategy,
+                                              factor=0.25, lower_bound=lb)[0][1]
+            assert len(admissible) > 1 and int(got[gi]) in admissible and int(want[gi]) in admissible, (gi, admissible)
+
+
+def test_full_size_index_properties(capi):
+    """BASELINE-size table (1e9 windows, built on the device): membership and values of sampled keys
+    re-derived on the host, misses for perturbed keys, and a stable checksum over two builds."""
+    torch = pytest.importorskip("torch")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free HBM")
+    from oracle import synth
+    taxa = datagen.make_taxonomy(5000, seed=1)
+    pre = synth.Preorder(taxa)
+    gtax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(taxa))
+    n_prot, plen = 2_500_000, 408
+    spec = capi.SynthSpec(seed=2, n_proteins=n_prot, protein_len=plen, home_pct=70, ancestor_pct=20)
+    gidx = capi.Index.build_synthetic(spec, gtax)
+    info = gidx.info()
+    nwin = n_prot * (plen - 8)
+    assert 0.99 * nwin < info.n_keys <= nwin             # a few 9-mers occur twice and merge
+    assert info.bytes < 12.5e9 and info.n_flagged / info.n_buckets < 0.3
+    # 2000 proteins sampled across the proteome: every window is a key; its value is the window's own
+    # value or (merged duplicates) an ancestor of it
+    rng = np.random.default_rng(3)
+    sample = np.sort(rng.choice(n_prot, size=500, replace=False))
+    exact = total = 0
+    for j in sample:
+        k, v = synth.windows(2, n_prot, plen, 70, 20, pre, int(j), int(j) + 1)
+        taxa_out, toff, _ = capi.kmer_lookup(gidx, k.reshape(-1), np.arange(0, 9 * len(k) + 1, 9, dtype=np.uint64), False)
+        assert len(taxa_out) == len(k)                   # no window is missing (misses would be omitted)
+        same = taxa_out.astype(np.uint64) == v
+        exact += int(same.sum())
+        total += len(k)
+        for got, own in zip(taxa_out[~same], v[~same]):
+            a, b = pre.dense_of[int(got)], pre.dense_of[int(own)]
+            assert pre.lca(a, b) == a                    # the stored value is an ancestor of this occurrence's
+    assert exact > 0.985 * total                         # ~1 % of the windows share their 9-mer with another one
+    # perturbing one residue of a key gives a miss (the key space is 5e11, the table holds 1e9)
+    k, _ = synth.windows(2, n_prot, plen, 70, 20, pre, 7, 8)
+    k = k.copy()
+    k[:, 4] = np.where(k[:, 4] == ord("W"), ord("C"), ord("W"))
+    taxa_out, _, _ = capi.kmer_lookup(gidx, k.reshape(-1), np.arange(0, 9 * len(k) + 1, 9, dtype=np.uint64), True)
+    assert (taxa_out == 0).mean() > 0.99
+    # the classification of device-generated reads is reproducible and mostly below the root
+    B = 200_000
+    nt = torch.empty(B * 300, dtype=torch.uint8, device="cuda")
+    capi.synth_reads_dev(spec, 3, 0, B, 150, 70, nt.data_ptr())
+    roff = torch.arange(0, 2 * B + 1, dtype=torch.int64, device="cuda") * 150
+    goff = torch.arange(0, 2 * B + 1, 2, dtype=torch.int64, device="cuda")
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(B, dtype=torch.int32, device="cuda")
+        capi.classify_reads_dev(gidx, gtax, capi.default_opts(min_seed_size=3), nt.data_ptr(), roff.data_ptr(), 2 * B,
+                                B * 300, goff.data_ptr(), B, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    host, _ = capi.classify_reads(gidx, gtax, capi.default_opts(min_seed_size=3), nt.cpu().numpy(),
+                                  roff.cpu().numpy().astype(np.uint64), goff.cpu().numpy().astype(np.uint64))
+    assert np.array_equal(host, outs[0].view(np.uint32))
+    assert 0.6 < (host != 1).mean() < 0.8                # 70 % of the pairs come from the proteome
+    gidx.close()
