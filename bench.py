@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--pairs-per-step", type=int, default=1_000_000)
     ap.add_argument("--index-keys", type=float, default=1e9, help="synthetic index size (9-mer windows)")
     ap.add_argument("--cpu-index-keys", type=float, default=2e7, help="index size of the host-resident CPU legs")
+    ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default policy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -177,7 +178,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -245,7 +246,7 @@ def run_ours(args):
     n_prot = max(1, int(args.index_keys // (PROTEIN_LEN - 8)))
     spec = capi.SynthSpec(seed=2, n_proteins=n_prot, protein_len=PROTEIN_LEN, home_pct=70, ancestor_pct=20)
     t0 = time.perf_counter()
-    gidx = capi.Index.build_synthetic(spec, gtax, device=local)
+    gidx = capi.Index.build_synthetic(spec, gtax, device=local, load_factor=args.load_factor)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     info = gidx.info()
@@ -271,13 +272,14 @@ def run_ours(args):
         capi.classify_reads_dev(gidx, gtax, opts, batches[i % nbatches].data_ptr(), roff.data_ptr(), nreads, total_nt,
                                 goff.data_ptr(), B, out.data_ptr(), stream)
 
-    # ---- device-resident throughput
-    for w in range(args.warmup):
-        step(w)
-    barrier()
+    # ---- device-resident throughput (clocks are sampled from the warm-up to the end of the timed region)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # let nvidia-smi start polling
+    for w in range(args.warmup):
+        step(w)
+    barrier()
     capi.kernel_timing(True)
     capi.kernel_times()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,7 +368,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
         "lookups_per_second": reads_total * LOOKUPS_PER_READ / (ms * 1e-3),
         "config": pipeline_config(args, {"index_keys_resident": int(info.n_keys), "index_bytes": int(info.bytes),
-                                         "index_build_s": build_s, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
+                                         "index_build_s": build_s, "index_load_factor": info.load_factor, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
                                          "classified_below_root_frac": classified}),
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(lookup_n + classify_n),

@@ -63,7 +63,8 @@ int umgap_device_count(void); /* number of CUDA devices, or negative status */
 /* Streams an `fst` 0.3.x (format v2) Map file once and builds the device table.
  * k > 0: fixed-length k-mer table (keys of any other length in the file can never be
  * queried by prot2kmer2lca -k and are skipped; k <= 9).  k == 0: variable-length peptide
- * table for prot2tryp2lca.  load_factor in (0,1]; <= 0 selects the default (0.70).           */
+ * table for prot2tryp2lca.  load_factor in (0,1]; <= 0 selects the default: the sparsest of
+ * 0.5 / 0.6 / 0.7 / 0.8 whose table fits in half of the free HBM (fewer second probes), else 0.85. */
 int umgap_index_load_fst(const char* path, int k, int device, double load_factor,
                          umgap_index** out);
 
@@ -85,6 +86,7 @@ typedef struct umgap_index_info {
     int k;                  /* 0 = variable-length table                                   */
     int device;
     int alphabet_size;      /* distinct residue bytes seen in keys                         */
+    double load_factor;     /* slots used / slots of the main level, as chosen at build     */
 } umgap_index_info;
 int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info);
 

@@ -47,7 +47,7 @@ class IndexInfo(C.Structure):
     _fields_ = [("n_keys", C.c_uint64), ("n_buckets", C.c_uint64), ("bytes", C.c_uint64),
                 ("n_skipped", C.c_uint64), ("n_flagged", C.c_uint64), ("n_displaced", C.c_uint64),
                 ("max_probe", C.c_uint64), ("k", C.c_int), ("device", C.c_int),
-                ("alphabet_size", C.c_int)]
+                ("alphabet_size", C.c_int), ("load_factor", C.c_double)]
 
 
 class TaxonomyInfo(C.Structure):

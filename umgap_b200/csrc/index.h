@@ -50,6 +50,7 @@ struct umgap_index {
     int alphabet_size = 0;
     uint64_t n_keys = 0, n_skipped = 0, n_flagged = 0, n_displaced = 0, max_probe = 0;
     uint64_t bytes = 0;
+    double load_factor = 0;  // of level 0, as chosen at build time
     // variable-length table (k == 0), see tryptic.cu
     void* var_table = nullptr;
     mutable umgap::Workspace ws;

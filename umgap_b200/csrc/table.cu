@@ -136,9 +136,23 @@ static uint64_t lines_for(uint64_t keys, double load) {
 void TableBuilder::begin(umgap_index* i, uint64_t expected_keys, double load_factor) {
     idx = i;
     expected = expected_keys;
-    if (load_factor <= 0) load_factor = 0.70;
     if (load_factor > 1.0) UMGAP_FAIL(UMGAP_ERR_INVALID, "load factor must be in (0,1]");
     use_device(idx->device);
+    if (load_factor <= 0) {
+        // Default policy: spend spare HBM on a sparser table.  Measured on the 1e9-key bench index
+        // (profiles/README.md): 23 % of the sectors are flagged at load 0.7 and 8 % at 0.5, and the
+        // lookup kernel runs 11.5 ms vs 8.6 ms per 1 M read pairs.  Take the sparsest of 0.5 / 0.6 /
+        // 0.7 / 0.8 whose table stays below half of the free device memory, else 0.85.
+        size_t free_b = 0, total_b = 0;
+        UMGAP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        load_factor = 0.85;
+        for (double lf : {0.5, 0.6, 0.7, 0.8})
+            if ((double)lines_for(expected_keys, lf) * 128.0 <= 0.5 * (double)free_b) {
+                load_factor = lf;
+                break;
+            }
+    }
+    idx->load_factor = load_factor;
     alloc_level(idx, 0, lines_for(expected_keys, load_factor));
     ovf_cap = std::max<uint64_t>(1u << 20, expected_keys / 8);
     UMGAP_CUDA(cudaMalloc((void**)&ovf_keys, ovf_cap * sizeof(uint64_t)));
@@ -349,6 +363,7 @@ int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info) {
         info->k = idx->k;
         info->device = idx->device;
         info->alphabet_size = idx->alphabet_size;
+        info->load_factor = idx->load_factor;
     });
 }
 
