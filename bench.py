@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--index-keys", type=float, default=1e9, help="synthetic index size (9-mer windows)")
     ap.add_argument("--cpu-index-keys", type=float, default=2e7, help="index size of the host-resident CPU legs")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default policy)")
+    ap.add_argument("--sharded", action="store_true", help="key-range-shard the index over the GPUs (peer-memory lookups) instead of replicating it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -66,7 +67,8 @@ def pipeline_config(args, extra=None):
         "pairs_per_step": args.pairs_per_step,
         "read_len": READ_LEN,
         "k": K,
-        "index": "replicated per GPU" if args.gpus > 1 else "single GPU",
+        "index": ("key-range sharded over the GPUs, remote sectors read over NVLink peer mappings" if getattr(args, "sharded", False)
+                  else "replicated per GPU") if args.gpus > 1 else "single GPU",
         "partitioning": f"reads partitioned over {args.gpus} GPU(s), no data-path collective",
         "cache": "inputs larger than L2: every step reads a different 300 MB batch and probes a table of GBs",
     }
@@ -246,7 +248,12 @@ def run_ours(args):
     n_prot = max(1, int(args.index_keys // (PROTEIN_LEN - 8)))
     spec = capi.SynthSpec(seed=2, n_proteins=n_prot, protein_len=PROTEIN_LEN, home_pct=70, ancestor_pct=20)
     t0 = time.perf_counter()
-    gidx = capi.Index.build_synthetic(spec, gtax, device=local, load_factor=args.load_factor)
+    shard_mode = args.sharded and world > 1
+    gidx = capi.Index.build_synthetic(spec, gtax, device=local, load_factor=args.load_factor,
+                                      shard=rank if shard_mode else 0, nshards=world if shard_mode else 1)
+    if shard_mode:
+        from umgap_b200 import sharded
+        sharded.attach_all(gidx, dist)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     info = gidx.info()

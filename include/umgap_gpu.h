@@ -75,6 +75,26 @@ int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const u
 
 void umgap_index_free(umgap_index* idx);
 
+/* ---- key-range-sharded index (multi-GPU, one process per GPU; SURVEY 8(e) mode 2) -----------
+ * Rank r builds shard r of nshards with one of the *_shard constructors (it keeps the keys whose
+ * hash falls in its range), exports a descriptor holding CUDA IPC handles of its table levels,
+ * the ranks exchange descriptors (e.g. torch.distributed all_gather) and every rank attaches all
+ * of them: afterwards the lookup kernel reads remote shards directly from the owning GPU's HBM
+ * over NVLink peer mappings -- there is no routing kernel and no collective on the data path.   */
+typedef struct umgap_shard_desc {
+    unsigned char ipc[4][64];        /* cudaIpcMemHandle_t of each level                        */
+    uint32_t nlines[4];
+    int nlevels, shard, nshards, device, alphabet_size;
+    unsigned char code_of_byte[256]; /* residue alphabet (must agree across shards)             */
+} umgap_shard_desc;
+int umgap_index_load_fst_shard(const char* path, int k, int device, double load_factor, int shard,
+                               int nshards, umgap_index** out);
+int umgap_index_from_pairs_shard(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
+                                 uint64_t n, int k, int device, double load_factor, int shard,
+                                 int nshards, umgap_index** out);
+int umgap_index_shard_desc(const umgap_index* idx, umgap_shard_desc* desc);
+int umgap_index_attach_shards(umgap_index* idx, const umgap_shard_desc* descs, int nshards);
+
 typedef struct umgap_index_info {
     uint64_t n_keys;        /* distinct keys resident                                      */
     uint64_t n_buckets;     /* 32-byte buckets                                             */
@@ -209,6 +229,9 @@ typedef struct umgap_synth_spec {
 /* Builds the table on the device from the counter-based proteome (no host copy). */
 int umgap_index_build_synthetic(const umgap_synth_spec* spec, const umgap_taxonomy* tax,
                                 int device, double load_factor, umgap_index** out);
+int umgap_index_build_synthetic_shard(const umgap_synth_spec* spec, const umgap_taxonomy* tax,
+                                      int device, double load_factor, int shard, int nshards,
+                                      umgap_index** out);
 /* Fills nt_dev with npairs*2 reads of read_len nucleotides drawn from the same proteome
  * (hit_pct % of pairs) or uniformly at random.                                              */
 int umgap_synth_reads_dev(const umgap_synth_spec* spec, uint64_t read_seed, uint64_t first_pair,

@@ -1,0 +1,27 @@
+"""Multi-GPU checks (need >= 2 visible GPUs: `gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import umgap_b200.capi as c
+    return c.device_count()
+
+
+def test_key_range_sharded_index_over_peer_memory():
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
+                        os.path.join(ROOT, "tests", "dist_sharded_check.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=600)
+    out = p.stdout.decode()
+    assert p.returncode == 0, p.stderr.decode()[-3000:]
+    assert "sharded ok rank 0/2" in out and "sharded ok rank 1/2" in out

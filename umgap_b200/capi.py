@@ -23,6 +23,8 @@ AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
 SYMBOLS = [
     "umgap_last_error", "umgap_abi_version", "umgap_device_count",
     "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
+    "umgap_index_load_fst_shard", "umgap_index_from_pairs_shard", "umgap_index_shard_desc",
+    "umgap_index_attach_shards", "umgap_index_build_synthetic_shard",
     "umgap_taxonomy_load", "umgap_taxonomy_from_arrays", "umgap_taxonomy_free",
     "umgap_taxonomy_get_info",
     "umgap_translate_bound", "umgap_translate",
@@ -60,6 +62,12 @@ class PipelineOpts(C.Structure):
                 ("seedextend", C.c_int), ("min_seed_size", C.c_int), ("max_gap_size", C.c_int),
                 ("strategy", C.c_int), ("factor", C.c_float), ("lower_bound", C.c_float),
                 ("ranked_only", C.c_int)]
+
+
+class ShardDesc(C.Structure):
+    _fields_ = [("ipc", (C.c_ubyte * 64) * 4), ("nlines", C.c_uint32 * 4), ("nlevels", C.c_int), ("shard", C.c_int),
+                ("nshards", C.c_int), ("device", C.c_int), ("alphabet_size", C.c_int),
+                ("code_of_byte", C.c_ubyte * 256)]
 
 
 class SynthSpec(C.Structure):
@@ -156,40 +164,54 @@ class Index:
 
     @classmethod
     def from_pairs(cls, keys: Sequence[bytes], values, k: int = 9, device: int = 0,
-                   load_factor: float = 0.0) -> "Index":
+                   load_factor: float = 0.0, shard: int = 0, nshards: int = 1) -> "Index":
         lens = np.fromiter((len(x) for x in keys), dtype=np.uint64, count=len(keys))
         off = np.zeros(len(keys) + 1, dtype=np.uint64)
         np.cumsum(lens, out=off[1:])
         blob = np.frombuffer(b"".join(keys) or b"\0", dtype=np.uint8)
-        return cls.from_blob(blob, off, values, k, device, load_factor)
+        return cls.from_blob(blob, off, values, k, device, load_factor, shard, nshards)
 
     @classmethod
     def from_blob(cls, blob: np.ndarray, off: Optional[np.ndarray], values, k: int = 9,
-                  device: int = 0, load_factor: float = 0.0) -> "Index":
+                  device: int = 0, load_factor: float = 0.0, shard: int = 0, nshards: int = 1) -> "Index":
         blob = _arr(blob, np.uint8)
         values = _arr(values, np.uint64)
         off = None if off is None else _arr(off, np.uint64)
         h = C.c_void_p()
-        _check(load_library().umgap_index_from_pairs(_p(blob), _p(off), _p(values),
-                                                     C.c_uint64(len(values)), C.c_int(k),
-                                                     C.c_int(device), C.c_double(load_factor),
-                                                     C.byref(h)))
+        _check(load_library().umgap_index_from_pairs_shard(_p(blob), _p(off), _p(values),
+                                                           C.c_uint64(len(values)), C.c_int(k),
+                                                           C.c_int(device), C.c_double(load_factor),
+                                                           C.c_int(shard), C.c_int(nshards), C.byref(h)))
         return cls(h)
 
     @classmethod
-    def load_fst(cls, path: str, k: int = 9, device: int = 0, load_factor: float = 0.0) -> "Index":
+    def load_fst(cls, path: str, k: int = 9, device: int = 0, load_factor: float = 0.0, shard: int = 0,
+                 nshards: int = 1) -> "Index":
         h = C.c_void_p()
-        _check(load_library().umgap_index_load_fst(path.encode(), C.c_int(k), C.c_int(device),
-                                                   C.c_double(load_factor), C.byref(h)))
+        _check(load_library().umgap_index_load_fst_shard(path.encode(), C.c_int(k), C.c_int(device),
+                                                         C.c_double(load_factor), C.c_int(shard),
+                                                         C.c_int(nshards), C.byref(h)))
         return cls(h)
 
     @classmethod
     def build_synthetic(cls, spec: SynthSpec, tax: Taxonomy, device: int = 0,
-                        load_factor: float = 0.0) -> "Index":
+                        load_factor: float = 0.0, shard: int = 0, nshards: int = 1) -> "Index":
         h = C.c_void_p()
-        _check(load_library().umgap_index_build_synthetic(C.byref(spec), tax._h, C.c_int(device),
-                                                          C.c_double(load_factor), C.byref(h)))
+        _check(load_library().umgap_index_build_synthetic_shard(C.byref(spec), tax._h, C.c_int(device),
+                                                                C.c_double(load_factor), C.c_int(shard),
+                                                                C.c_int(nshards), C.byref(h)))
         return cls(h)
+
+    def shard_desc(self) -> ShardDesc:
+        """Descriptor of this rank's shard (CUDA IPC handles of its levels) for the peers."""
+        d = ShardDesc()
+        _check(load_library().umgap_index_shard_desc(self._h, C.byref(d)))
+        return d
+
+    def attach_shards(self, descs: Sequence[ShardDesc]) -> None:
+        """Maps every shard (rank order) so that lookups read remote shards over NVLink."""
+        arr = (ShardDesc * len(descs))(*descs)
+        _check(load_library().umgap_index_attach_shards(self._h, arr, C.c_int(len(descs))))
 
     def info(self) -> IndexInfo:
         i = IndexInfo()

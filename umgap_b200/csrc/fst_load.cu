@@ -60,13 +60,23 @@ using namespace umgap;
 
 extern "C" int umgap_index_load_fst(const char* path, int k, int device, double load_factor,
                                     umgap_index** out) {
+    return umgap_index_load_fst_shard(path, k, device, load_factor, 0, 1, out);
+}
+
+// Every rank streams the whole file (the alphabet codes are assigned in file order, hence identical
+// on all ranks) and keeps the keys of its own hash range.
+extern "C" int umgap_index_load_fst_shard(const char* path, int k, int device, double load_factor, int shard,
+                                          int nshards, umgap_index** out) {
     umgap_index* idx = nullptr;
     int rc = guarded([&] {
         if (!path || !out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         if (k < 0 || k > 9) UMGAP_FAIL(UMGAP_ERR_INVALID, "k-mer table supports 1 <= k <= 9 (got %d)", k);
+        check_shard(shard, nshards, k);
         idx = new umgap_index();
         idx->device = device;
         idx->k = k;
+        idx->shard = shard;
+        idx->nshards = nshards;
         memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
         if (k == 0) {
             const int r = build_var_table_from_fst(path, idx, load_factor);

@@ -51,6 +51,12 @@ struct umgap_index {
     uint64_t n_keys = 0, n_skipped = 0, n_flagged = 0, n_displaced = 0, max_probe = 0;
     uint64_t bytes = 0;
     double load_factor = 0;  // of level 0, as chosen at build time
+    // key-range sharding (multi-GPU, table larger than one GPU): this handle holds shard `shard` of
+    // `nshards`; after umgap_index_attach_shards() `sharded` maps every shard (peers through CUDA IPC)
+    int shard = 0, nshards = 1;
+    bool attached = false;
+    umgap::ShardedView sharded{};
+    std::vector<void*> ipc_opened;
     // variable-length table (k == 0), see tryptic.cu
     void* var_table = nullptr;
     mutable umgap::Workspace ws;
@@ -89,6 +95,8 @@ struct TableBuilder {
     // byte -> code for the index alphabet, assigning a new code on first sight
     int code_for(uint8_t byte);
 };
+
+void check_shard(int shard, int nshards, int k);  // table.cu
 
 // FST v2 stream reader (fst_stream.cpp): calls `sink(key, len, value)` for every key in order.
 struct FstSink {

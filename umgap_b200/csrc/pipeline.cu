@@ -119,13 +119,11 @@ struct LookupSmem {
 // sector are compacted into the queue and re-probed 64 at a time (2 loads in flight per
 // lane), so the warp stays converged.  out: forward k-mer starting at p -> out[p]; reverse-strand
 // k-mer starting at reverse coordinate q -> out[n + q]  (frame f record = entries f-1, f+2, ...).
-template <int K>
-__device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s_lut, LookupSmem<K>& sm,
+template <int K, class TV>
+__device__ __forceinline__ void lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
                                             const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane) {
     constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
-    const ulonglong4* __restrict__ level0 = t.level[0];
-    const uint32_t nlines0 = t.nlines[0];
     const uint32_t npos = n - 3u * K + 1;
     for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
         for (int i = lane; i < W + 2; i += 32) {
@@ -164,7 +162,7 @@ __device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (valid[u]) sec[u] = load_sector(level0 + probe_sector(h[u], nlines0, 0));
+                if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t p = w0 + lane + 32 * u;
@@ -193,10 +191,8 @@ __device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s
                 }
 #pragma unroll
                 for (int j = 0; j < kQueueWide; ++j)
-                    if (hq[j] != ~0ull) {
-                        const uint32_t lv = (uint32_t)(hq[j] >> 48) & 3u;
-                        s2[j] = load_sector(t.level[lv] + probe_sector(hq[j] & kKeyMask, t.nlines[lv], (uint32_t)(hq[j] >> 45) & 7u));
-                    }
+                    if (hq[j] != ~0ull)
+                        s2[j] = load_sector(sector_addr(t, hq[j] & kKeyMask, (uint32_t)(hq[j] >> 48) & 3u, (uint32_t)(hq[j] >> 45) & 7u));
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < kQueueWide; ++j) {
@@ -209,7 +205,7 @@ __device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s
                         const uint32_t v = probe_sector_data(s2[j], (d << 28) | ((uint32_t)hh & kTagMask), more);
                         if (more && ++d == (uint32_t)kMaxDisp) {
                             d = 0;
-                            if (++lv == (uint32_t)t.nlevels) more = false;  // v is kNoValue here
+                            if (++lv == num_levels(t, hh)) more = false;  // v is kNoValue here
                         }
                         if (!more) {
                             const uint32_t p = w0 + ((uint32_t)(hq[j] >> 51) & 127u);
@@ -229,9 +225,9 @@ __device__ __forceinline__ void lookup_read(const TableView& t, const uint8_t* s
 }
 
 // Lookup kernel: one warp per read, ids to global memory.
-template <int K>
+template <int K, class TV>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
-translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ nt,
+translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
                         uint32_t* __restrict__ ids) {
     __shared__ uint8_t s_lut[72];
@@ -244,7 +240,7 @@ translate_lookup_kernel(TableView t, CodonLut lut, const uint8_t* __restrict__ n
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         if (n < 3u * K) continue;  // no frame reaches K residues
-        lookup_read<K>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
+        lookup_read<K, TV>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
     }
 }
 
@@ -559,14 +555,19 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     if (r_end <= r_begin) return;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
-    const TableView tv = idx->view();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(r_end - r_begin, kLookupWarps), 148ull * 32);
+    if (idx->nshards > 1 && !idx->attached)
+        UMGAP_FAIL(UMGAP_ERR_INVALID, "sharded index: call umgap_index_attach_shards() before looking up");
     LaunchTimer timer(0, st);
     switch (idx->k) {
 #define UMGAP_CASE(KK)                                                                                      \
     case KK:                                                                                                \
-        translate_lookup_kernel<KK><<<blocks, kLookupWarps * 32, 0, st>>>(tv, lut, nt_dev, read_off_dev,     \
-                                                                          r_begin, r_end, ids_dev);         \
+        if (idx->nshards > 1)                                                                               \
+            translate_lookup_kernel<KK, ShardedView><<<blocks, kLookupWarps * 32, 0, st>>>(                  \
+                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev);                          \
+        else                                                                                                \
+            translate_lookup_kernel<KK, TableView><<<blocks, kLookupWarps * 32, 0, st>>>(                    \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev);                           \
         break;
         UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
         UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)

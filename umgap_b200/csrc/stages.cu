@@ -67,8 +67,9 @@ translate_kernel(AsciiLut lut, const uint8_t* __restrict__ nt, const uint64_t* _
 
 // One warp per peptide; lanes stride the k-mer start positions.  out has one entry per
 // position (UMGAP_MISS for a miss); the host applies -o / compaction.
+template <class TV>
 __global__ void __launch_bounds__(256)
-kmer_lookup_kernel(TableView t, const uint8_t* __restrict__ code_of_byte,
+kmer_lookup_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ code_of_byte,
                    const uint8_t* __restrict__ aa, const uint64_t* __restrict__ pep_off,
                    uint64_t npeps, const uint64_t* __restrict__ out_off, uint32_t* __restrict__ out) {
     __shared__ uint8_t s_code[256];
@@ -246,8 +247,14 @@ int umgap_kmer_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t*
         UMGAP_CUDA(cudaMemcpy(d_code.p, idx->code_of_byte, 256, cudaMemcpyHostToDevice));
         UMGAP_CUDA(cudaMemcpy(d_poff.p, pep_off, (npeps + 1) * 8, cudaMemcpyHostToDevice));
         UMGAP_CUDA(cudaMemcpy(d_ooff.p, taxa_off, (npeps + 1) * 8, cudaMemcpyHostToDevice));
-        kmer_lookup_kernel<<<grid_for(npeps, 8), 256>>>(idx->view(), d_code.p, d_aa.p, d_poff.p, npeps,
-                                                        d_ooff.p, d_out.p);
+        if (idx->nshards > 1 && !idx->attached)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "sharded index: call umgap_index_attach_shards() before looking up");
+        if (idx->nshards > 1)
+            kmer_lookup_kernel<ShardedView><<<grid_for(npeps, 8), 256>>>(idx->sharded, d_code.p, d_aa.p, d_poff.p, npeps,
+                                                                         d_ooff.p, d_out.p);
+        else
+            kmer_lookup_kernel<TableView><<<grid_for(npeps, 8), 256>>>(idx->view(), d_code.p, d_aa.p, d_poff.p, npeps,
+                                                                       d_ooff.p, d_out.p);
         UMGAP_CUDA(cudaGetLastError());
         UMGAP_CUDA(cudaMemcpy(taxa_out, d_out.p, o * 4, cudaMemcpyDeviceToHost));
         if (one_on_one) {  // miss -> 0 (prot2kmer2lca.rs:115)

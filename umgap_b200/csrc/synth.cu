@@ -160,9 +160,15 @@ extern "C" {
 
 int umgap_index_build_synthetic(const umgap_synth_spec* spec, const umgap_taxonomy* tax, int device,
                                 double load_factor, umgap_index** out) {
+    return umgap_index_build_synthetic_shard(spec, tax, device, load_factor, 0, 1, out);
+}
+
+int umgap_index_build_synthetic_shard(const umgap_synth_spec* spec, const umgap_taxonomy* tax, int device,
+                                      double load_factor, int shard, int nshards, umgap_index** out) {
     umgap_index* idx = nullptr;
     int rc = guarded([&] {
         if (!spec || !tax || !out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        check_shard(shard, nshards, 9);
         if (spec->protein_len < 9 || spec->n_proteins == 0)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "synthetic proteome needs protein_len >= 9 and n_proteins >= 1");
         if (spec->home_pct + spec->ancestor_pct > 100) UMGAP_FAIL(UMGAP_ERR_INVALID, "percentages exceed 100");
@@ -170,6 +176,8 @@ int umgap_index_build_synthetic(const umgap_synth_spec* spec, const umgap_taxono
         idx = new umgap_index();
         idx->device = device;
         idx->k = 9;
+        idx->shard = shard;
+        idx->nshards = nshards;
         memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
         TableBuilder b;
         try {

@@ -11,6 +11,12 @@ int build_var_table_from_pairs(umgap_index* idx, const uint8_t* keys, const uint
                                const uint64_t* values, uint64_t n, double load_factor);  // tryptic.cu
 void free_var_table(void* p);
 
+void check_shard(int shard, int nshards, int k) {
+    if (nshards < 1 || nshards > kMaxShards || shard < 0 || shard >= nshards)
+        UMGAP_FAIL(UMGAP_ERR_INVALID, "shard %d of %d is out of range (at most %d shards)", shard, nshards, kMaxShards);
+    if (nshards > 1 && k <= 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "only k-mer tables can be sharded");
+}
+
 enum { C_OVF = 0, C_DUP = 1, C_DISPLACED = 2, C_MAXPROBE = 3, C_INSERTED = 4, C_BADVAL = 5, C_N = 8 };
 
 // Empty table: every meta = kEmptyMeta, every value = kNoValue.
@@ -48,7 +54,7 @@ __device__ __forceinline__ void merge_value(unsigned int* addr, uint32_t val, co
 // One thread per key.  Metas are claimed with 32-bit CAS in slot order, so two threads carrying
 // the same key always meet in the same slot (duplicates are detected, never stored twice).
 template <bool LCA>
-__global__ void insert_kernel(uint32_t* __restrict__ sectors, uint32_t nlines,
+__global__ void insert_kernel(uint32_t* __restrict__ sectors, uint32_t nlines, uint32_t shard, uint32_t nshards,
                               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                               uint64_t n, int level, uint64_t* __restrict__ ovf_keys,
                               uint32_t* __restrict__ ovf_vals, uint64_t ovf_cap,
@@ -63,10 +69,12 @@ __global__ void insert_kernel(uint32_t* __restrict__ sectors, uint32_t nlines,
             continue;
         }
         const uint64_t h = mix45(key);
+        uint32_t local32;
+        if (shard_split(h, nshards, local32) != shard) continue;  // another shard owns this key
         const uint32_t tag = (uint32_t)h & kTagMask;
         bool done = false;
         for (uint32_t d = 0; d < (uint32_t)kMaxDisp && !done; ++d) {
-            unsigned int* meta = sectors + probe_sector(h, nlines, d) * 8;
+            unsigned int* meta = sectors + probe_sector_local(local32, h, nlines, d) * 8;
             const uint32_t want = (d << 28) | tag;
             for (int j = 0; j < 4 && !done; ++j) {
                 unsigned int cur = *reinterpret_cast<volatile unsigned int*>(meta + j);
@@ -135,6 +143,8 @@ static uint64_t lines_for(uint64_t keys, double load) {
 
 void TableBuilder::begin(umgap_index* i, uint64_t expected_keys, double load_factor) {
     idx = i;
+    if (idx->nshards > 1)  // a shard holds its hash range's share of the keys (+3 % for imbalance)
+        expected_keys = expected_keys / idx->nshards + expected_keys / (32 * idx->nshards) + 1024;
     expected = expected_keys;
     if (load_factor > 1.0) UMGAP_FAIL(UMGAP_ERR_INVALID, "load factor must be in (0,1]");
     use_device(idx->device);
@@ -168,11 +178,12 @@ static void launch_insert(umgap_index* idx, int lv, const uint64_t* keys, const 
     const int threads = 256;
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(n, threads), 148ull * 64);
     if (tv)
-        insert_kernel<true><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], keys,
-                                                        vals, n, lv, ok, ov, cap, counters, *tv);
+        insert_kernel<true><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], (uint32_t)idx->shard,
+                                                        (uint32_t)idx->nshards, keys, vals, n, lv, ok, ov, cap, counters, *tv);
     else
-        insert_kernel<false><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], keys,
-                                                         vals, n, lv, ok, ov, cap, counters, TaxView{});
+        insert_kernel<false><<<blocks, threads, 0, st>>>(idx->level_dev[lv], idx->level_nlines[lv], (uint32_t)idx->shard,
+                                                         (uint32_t)idx->nshards, keys, vals, n, lv, ok, ov, cap, counters,
+                                                         TaxView{});
     UMGAP_CUDA(cudaGetLastError());
 }
 
@@ -273,14 +284,23 @@ extern "C" {
 
 int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
                            uint64_t n, int k, int device, double load_factor, umgap_index** out) {
+    return umgap_index_from_pairs_shard(keys, key_off, values, n, k, device, load_factor, 0, 1, out);
+}
+
+int umgap_index_from_pairs_shard(const uint8_t* keys, const uint64_t* key_off, const uint64_t* values,
+                                 uint64_t n, int k, int device, double load_factor, int shard, int nshards,
+                                 umgap_index** out) {
     umgap_index* idx = nullptr;
     int rc = guarded([&] {
         if (!out || (n && (!keys || !values))) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        check_shard(shard, nshards, k);
         if (k < 0 || k > 9)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "k-mer table supports 1 <= k <= 9 (got %d)", k);
         idx = new umgap_index();
         idx->device = device;
         idx->k = k;
+        idx->shard = shard;
+        idx->nshards = nshards;
         memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
         if (k == 0) {  // variable-length peptide table (prot2tryp2lca)
             if (n && !key_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "key_off is required for a variable-length table");
@@ -339,9 +359,67 @@ int umgap_index_from_pairs(const uint8_t* keys, const uint64_t* key_off, const u
     return rc;
 }
 
+int umgap_index_shard_desc(const umgap_index* idx, umgap_shard_desc* desc) {
+    return guarded([&] {
+        if (!idx || !desc) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->k <= 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "only k-mer tables can be sharded");
+        use_device(idx->device);
+        memset(desc, 0, sizeof *desc);
+        desc->shard = idx->shard;
+        desc->nshards = idx->nshards;
+        desc->device = idx->device;
+        desc->nlevels = idx->nlevels;
+        desc->alphabet_size = idx->alphabet_size;
+        memcpy(desc->code_of_byte, idx->code_of_byte, 256);
+        for (int lv = 0; lv < idx->nlevels; ++lv) {
+            desc->nlines[lv] = idx->level_nlines[lv];
+            cudaIpcMemHandle_t h;
+            UMGAP_CUDA(cudaIpcGetMemHandle(&h, idx->level_dev[lv]));
+            static_assert(sizeof h == 64, "IPC handle size");
+            memcpy(desc->ipc[lv], &h, 64);
+        }
+    });
+}
+
+int umgap_index_attach_shards(umgap_index* idx, const umgap_shard_desc* descs, int nshards) {
+    return guarded([&] {
+        if (!idx || !descs) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (nshards != idx->nshards || nshards < 1 || nshards > kMaxShards)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "expected %d shard descriptors", idx->nshards);
+        if (idx->attached) UMGAP_FAIL(UMGAP_ERR_INVALID, "shards are already attached");
+        use_device(idx->device);
+        ShardedView& v = idx->sharded;
+        memset(&v, 0, sizeof v);
+        v.nshards = nshards;
+        v.k = idx->k;
+        for (int o = 0; o < nshards; ++o) {
+            const umgap_shard_desc& d = descs[o];
+            if (d.shard != o || d.nshards != nshards) UMGAP_FAIL(UMGAP_ERR_INVALID, "descriptor %d is not shard %d of %d", o, o, nshards);
+            if (memcmp(d.code_of_byte, idx->code_of_byte, 256) != 0)
+                UMGAP_FAIL(UMGAP_ERR_INVALID, "shard %d was built with a different residue alphabet order", o);
+            v.nlevels[o] = d.nlevels;
+            for (int lv = 0; lv < d.nlevels; ++lv) {
+                v.nlines[o][lv] = d.nlines[lv];
+                if (o == idx->shard) {
+                    v.level[o][lv] = reinterpret_cast<const ulonglong4*>(idx->level_dev[lv]);
+                } else {  // the peer's HBM, mapped into this process over NVLink
+                    cudaIpcMemHandle_t h;
+                    memcpy(&h, d.ipc[lv], 64);
+                    void* p = nullptr;
+                    UMGAP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                    idx->ipc_opened.push_back(p);
+                    v.level[o][lv] = reinterpret_cast<const ulonglong4*>(p);
+                }
+            }
+        }
+        idx->attached = true;
+    });
+}
+
 void umgap_index_free(umgap_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    for (void* p : idx->ipc_opened) cudaIpcCloseMemHandle(p);
     for (int i = 0; i < idx->nlevels; ++i)
         if (idx->level_dev[i]) cudaFree(idx->level_dev[i]);
     if (idx->var_table) free_var_table(idx->var_table);

@@ -45,6 +45,19 @@ struct TableView {
     int k;
 };
 
+// Key-range-sharded table: shard o = floor((h >> 13) * nshards / 2^32) owns the key; the low 32
+// bits of that product spread the shard's keys over its own lines.  level[o] of a remote shard is
+// a peer mapping of that GPU's HBM (CUDA IPC over NVLink): the lookup kernel loads remote sectors
+// directly, no routing kernels and no collective on the data path.
+constexpr int kMaxShards = 8;
+struct ShardedView {
+    const ulonglong4* level[kMaxShards][kMaxLevels];
+    uint32_t nlines[kMaxShards][kMaxLevels];
+    int nlevels[kMaxShards];
+    int nshards;
+    int k;
+};
+
 __host__ __device__ __forceinline__ uint64_t mix45(uint64_t x) {
     x ^= x >> 22;
     x = (x * 0x2545F4914F6CDD1Dull) & kKeyMask;
@@ -52,11 +65,37 @@ __host__ __device__ __forceinline__ uint64_t mix45(uint64_t x) {
     return x;
 }
 
-// Sector index (line * 4 + sector) of probe d for hash h.
-__device__ __forceinline__ uint64_t probe_sector(uint64_t h, uint32_t nlines, uint32_t d) {
-    uint32_t line = __umulhi((uint32_t)(h >> 13), nlines) + (d >> 2);
+// Owner shard of hash h and the 32-bit value that places the key inside the shard (with one shard:
+// owner 0 and the top 32 bits of h).
+__host__ __device__ __forceinline__ uint32_t shard_split(uint64_t h, uint32_t nshards, uint32_t& local32) {
+    const uint64_t prod = (uint64_t)(uint32_t)(h >> 13) * nshards;
+    local32 = (uint32_t)prod;
+    return (uint32_t)(prod >> 32);
+}
+
+// Sector index (line * 4 + sector) of probe d for a key placed by local32 in a level of nlines lines.
+__device__ __forceinline__ uint64_t probe_sector_local(uint32_t local32, uint64_t h, uint32_t nlines, uint32_t d) {
+    uint32_t line = __umulhi(local32, nlines) + (d >> 2);
     if (line >= nlines) line -= nlines;
     return (uint64_t)line * 4 + (((uint32_t)h + d) & 3u);
+}
+__device__ __forceinline__ uint64_t probe_sector(uint64_t h, uint32_t nlines, uint32_t d) {
+    return probe_sector_local((uint32_t)(h >> 13), h, nlines, d);
+}
+
+// Address of the sector probe d of hash h reads in level lv, and the number of levels to try.
+__device__ __forceinline__ const ulonglong4* sector_addr(const TableView& t, uint64_t h, uint32_t lv, uint32_t d) {
+    return t.level[lv] + probe_sector(h, t.nlines[lv], d);
+}
+__device__ __forceinline__ uint32_t num_levels(const TableView& t, uint64_t) { return (uint32_t)t.nlevels; }
+__device__ __forceinline__ const ulonglong4* sector_addr(const ShardedView& t, uint64_t h, uint32_t lv, uint32_t d) {
+    uint32_t local32;
+    const uint32_t o = shard_split(h, (uint32_t)t.nshards, local32);
+    return t.level[o][lv] + probe_sector_local(local32, h, t.nlines[o][lv], d);
+}
+__device__ __forceinline__ uint32_t num_levels(const ShardedView& t, uint64_t h) {
+    uint32_t local32;
+    return (uint32_t)t.nlevels[shard_split(h, (uint32_t)t.nshards, local32)];
 }
 
 // 256-bit read-only load of one sector: a single LDG.E.256.
@@ -83,11 +122,13 @@ __device__ __forceinline__ uint32_t probe_sector_data(const ulonglong4& s, uint3
 
 // Remaining probes of a lookup whose probe d-1 ended on a flagged sector: continues at distance
 // d of level lv, then through the overflow levels.
-__device__ __forceinline__ uint32_t probe_continue(const TableView& t, uint64_t h, int lv, uint32_t d) {
+template <class TV>
+__device__ __forceinline__ uint32_t probe_continue(const TV& t, uint64_t h, uint32_t lv, uint32_t d) {
     const uint32_t tag = (uint32_t)h & kTagMask;
-    for (; lv < t.nlevels; ++lv, d = 0) {
+    const uint32_t nlv = num_levels(t, h);
+    for (; lv < nlv; ++lv, d = 0) {
         for (; d < (uint32_t)kMaxDisp; ++d) {
-            const ulonglong4 s = load_sector(t.level[lv] + probe_sector(h, t.nlines[lv], d));
+            const ulonglong4 s = load_sector(sector_addr(t, h, lv, d));
             bool more;
             const uint32_t v = probe_sector_data(s, (d << 28) | tag, more);
             if (!more) return v;
@@ -98,7 +139,8 @@ __device__ __forceinline__ uint32_t probe_continue(const TableView& t, uint64_t 
 }
 
 // Full lookup of one packed key (used where lookups are not software-pipelined).
-__device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t key) {
+template <class TV>
+__device__ __forceinline__ uint32_t table_lookup(const TV& t, uint64_t key) {
     if (key == kInvalidKey) return kNoValue;
     return probe_continue(t, mix45(key), 0, 0);
 }
