@@ -94,6 +94,9 @@ int umgap_index_from_pairs_shard(const uint8_t* keys, const uint64_t* key_off, c
                                  int nshards, umgap_index** out);
 int umgap_index_shard_desc(const umgap_index* idx, umgap_shard_desc* desc);
 int umgap_index_attach_shards(umgap_index* idx, const umgap_shard_desc* descs, int nshards);
+/* Same for one process that drives several GPUs (or several shards on one GPU): the shards' own
+ * handles, in shard order; peer access is enabled as needed.                                    */
+int umgap_index_attach_shards_local(umgap_index* idx, umgap_index* const* shards, int nshards);
 
 typedef struct umgap_index_info {
     uint64_t n_keys;        /* distinct keys resident                                      */

@@ -24,7 +24,7 @@ SYMBOLS = [
     "umgap_last_error", "umgap_abi_version", "umgap_device_count",
     "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
     "umgap_index_load_fst_shard", "umgap_index_from_pairs_shard", "umgap_index_shard_desc",
-    "umgap_index_attach_shards", "umgap_index_build_synthetic_shard",
+    "umgap_index_attach_shards", "umgap_index_attach_shards_local", "umgap_index_build_synthetic_shard",
     "umgap_taxonomy_load", "umgap_taxonomy_from_arrays", "umgap_taxonomy_free",
     "umgap_taxonomy_get_info",
     "umgap_translate_bound", "umgap_translate",
@@ -212,6 +212,11 @@ class Index:
         """Maps every shard (rank order) so that lookups read remote shards over NVLink."""
         arr = (ShardDesc * len(descs))(*descs)
         _check(load_library().umgap_index_attach_shards(self._h, arr, C.c_int(len(descs))))
+
+    def attach_shards_local(self, shards: Sequence["Index"]) -> None:
+        """Same-process variant: the shard handles themselves, in shard order."""
+        arr = (C.c_void_p * len(shards))(*[s._h for s in shards])
+        _check(load_library().umgap_index_attach_shards_local(self._h, arr, C.c_int(len(shards))))
 
     def info(self) -> IndexInfo:
         i = IndexInfo()

@@ -416,6 +416,38 @@ int umgap_index_attach_shards(umgap_index* idx, const umgap_shard_desc* descs, i
     });
 }
 
+int umgap_index_attach_shards_local(umgap_index* idx, umgap_index* const* shards, int nshards) {
+    return guarded([&] {
+        if (!idx || !shards) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (nshards != idx->nshards || nshards < 1 || nshards > kMaxShards)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "expected %d shards", idx->nshards);
+        if (idx->attached) UMGAP_FAIL(UMGAP_ERR_INVALID, "shards are already attached");
+        use_device(idx->device);
+        ShardedView& v = idx->sharded;
+        memset(&v, 0, sizeof v);
+        v.nshards = nshards;
+        v.k = idx->k;
+        for (int o = 0; o < nshards; ++o) {
+            const umgap_index* s = shards[o];
+            if (!s || s->shard != o || s->nshards != nshards || s->k != idx->k)
+                UMGAP_FAIL(UMGAP_ERR_INVALID, "handle %d is not shard %d of %d", o, o, nshards);
+            if (memcmp(s->code_of_byte, idx->code_of_byte, 256) != 0)
+                UMGAP_FAIL(UMGAP_ERR_INVALID, "shard %d was built with a different residue alphabet order", o);
+            if (s->device != idx->device) {  // same process, another GPU: plain peer access over NVLink
+                const cudaError_t e = cudaDeviceEnablePeerAccess(s->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) UMGAP_CUDA(e);
+                (void)cudaGetLastError();
+            }
+            v.nlevels[o] = s->nlevels;
+            for (int lv = 0; lv < s->nlevels; ++lv) {
+                v.nlines[o][lv] = s->level_nlines[lv];
+                v.level[o][lv] = reinterpret_cast<const ulonglong4*>(s->level_dev[lv]);
+            }
+        }
+        idx->attached = true;
+    });
+}
+
 void umgap_index_free(umgap_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
