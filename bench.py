@@ -43,6 +43,15 @@ N_TAXA = 5000
 PROTEIN_LEN = 408  # 400 nine-mer windows per protein
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The JSON line is the only thing that reaches the real stdout: fd 1 is pointed at stderr for the
+    whole run so that library chatter (NCCL prints its version banner on stdout) cannot precede it."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -54,6 +63,7 @@ def parse_args():
     ap.add_argument("--cpu-index-keys", type=float, default=2e7, help="index size of the host-resident CPU legs")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default policy)")
     ap.add_argument("--sharded", action="store_true", help="key-range-shard the index over the GPUs (peer-memory lookups) instead of replicating it")
+    ap.add_argument("--peer-loads", action="store_true", help="with --sharded: read remote shards through IPC peer mappings instead of the all-to-all exchange")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -67,7 +77,8 @@ def pipeline_config(args, extra=None):
         "pairs_per_step": args.pairs_per_step,
         "read_len": READ_LEN,
         "k": K,
-        "index": ("key-range sharded over the GPUs, remote sectors read over NVLink peer mappings" if getattr(args, "sharded", False)
+        "index": ("key-range sharded over the GPUs, " + ("remote sectors read over NVLink peer mappings" if getattr(args, "peer_loads", False)
+                                                           else "packed k-mer hashes and answers exchanged by NCCL all-to-all") if getattr(args, "sharded", False)
                   else "replicated per GPU") if args.gpus > 1 else "single GPU",
         "partitioning": f"reads partitioned over {args.gpus} GPU(s), no data-path collective",
         "cache": "inputs larger than L2: every step reads a different 300 MB batch and probes a table of GBs",
@@ -161,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # -------------------------------------------------------------------------------------------- clocks
@@ -275,7 +286,14 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
 
+    routed = None
+    if shard_mode and not args.peer_loads:
+        routed = sharded.RoutedClassifier(gidx, gtax, dist, total_nt)
+
     def step(i):
+        if routed is not None:  # hashes and answers cross NVLink in two all-to-alls, lookups stay local
+            routed.classify(opts, batches[i % nbatches], roff, goff, out, total_nt)
+            return
         capi.classify_reads_dev(gidx, gtax, opts, batches[i % nbatches].data_ptr(), roff.data_ptr(), nreads, total_nt,
                                 goff.data_ptr(), B, out.data_ptr(), stream)
 
@@ -308,7 +326,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C ABI call (pinned host input, H2D + D2H timed)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and routed is None:
         h_nt = torch.empty(total_nt, dtype=torch.uint8).pin_memory()
         h_nt.copy_(batches[0])
         def pinned(a):  # page-locked copy, so that every transfer of the timed region is truly asynchronous
@@ -381,13 +399,17 @@ def run_ours(args):
         "gpu_launches": int(lookup_n + classify_n),
         "kernel_ms": {"translate_lookup": lookup_ms, "classify": classify_ms},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -214,6 +214,30 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
                                uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
                                void* stream);
 
+/* ---- routed variant of the sharded mode: the exchange step of SURVEY 8(e).  Per batch and rank:
+ *   umgap_route_pack_dev     reads -> 45-bit k-mer hashes bucketed by owning shard: send_h_dev and
+ *                            send_pos_dev hold nshards buckets of `cap` entries, cursors_dev
+ *                            (2*nshards u64) the bucket fills and, after them, overflow flags;
+ *                            k-mers that cannot be keys are answered UMGAP_MISS in ids_dev directly
+ *   (host)                   all-to-all of the bucket fills and of the buckets (NCCL)
+ *   umgap_lookup_hashes_dev  looks the received hashes up in this rank's shard
+ *   (host)                   all-to-all of the answers
+ *   umgap_route_scatter_dev  answers -> ids_dev (the layout umgap_translate_lookup_dev produces)
+ *   umgap_classify_ids_dev   seedextend | uniq | taxa2agg over ids_dev
+ * umgap_b200/sharded.py drives this with torch.distributed.                                        */
+int umgap_route_pack_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                         const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
+                         uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev,
+                         uint32_t* ids_dev, void* stream);
+int umgap_lookup_hashes_dev(const umgap_index* idx, const uint64_t* h_dev, const uint64_t* counts_dev,
+                            int nsrc, uint64_t cap, uint32_t* out_dev, void* stream);
+int umgap_route_scatter_dev(const umgap_index* idx, const uint32_t* ans_dev, const uint32_t* send_pos_dev,
+                            const uint64_t* cursors_dev, uint64_t cap, uint32_t* ids_dev, void* stream);
+int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                           const uint32_t* ids_dev, const uint64_t* read_off_dev, uint64_t total_nt,
+                           const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev,
+                           void* stream);
+
 /* ---- measurement aid: when enabled, every launch of the two hot-path kernels is bracketed by CUDA
  * events on the stream it is launched on.  umgap_kernel_times() waits for the recorded launches,
  * returns the summed durations (ms) and launch counts since the last call, and clears them.      */

@@ -63,6 +63,19 @@ def main():
         want = opipe.classify_reads(reads, olookup.DictIndex(index), otax, min_seed_size=3, strategy=strategy)
         for (h, adm), g in zip(want, y):
             assert int(g) in adm, (h, int(g), adm)
+    # routed variant: NCCL all-to-all of packed hashes and answers, lookups in the local shard only
+    rc = sharded.RoutedClassifier(shard, gtax, dist, max_total_nt=int(roff[-1]) + 1000)
+    d_nt = torch.from_numpy(nt).cuda()
+    d_roff = torch.from_numpy(roff.astype(np.int64)).cuda()
+    d_goff = torch.from_numpy(goff.astype(np.int64)).cuda()
+    for strategy in (0, 1, 2):
+        opts = capi.default_opts(min_seed_size=3, strategy=strategy)
+        x, _ = capi.classify_reads(full, gtax, opts, nt, roff, goff)
+        d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
+        rc.classify(opts, d_nt, d_roff, d_goff, d_out, int(roff[-1]))
+        torch.cuda.synchronize()
+        assert not rc.overflowed()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), x), strategy
     dist.barrier()
     torch.cuda.synchronize()
     shard.close()

@@ -33,6 +33,7 @@ SYMBOLS = [
     "umgap_seedextend", "umgap_aggregate",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
+    "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
     "umgap_kernel_timing", "umgap_kernel_times",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
@@ -392,3 +393,30 @@ def kernel_times():
     na, nb = C.c_uint64(), C.c_uint64()
     _check(load_library().umgap_kernel_times(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
     return a.value, na.value, b.value, nb.value
+
+
+def route_pack_dev(index: Index, opts: PipelineOpts, nt_ptr: int, read_off_ptr: int, nreads: int, total_nt: int,
+                   cap: int, send_h_ptr: int, send_pos_ptr: int, cursors_ptr: int, ids_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_route_pack_dev(
+        index._h, C.byref(opts), C.c_void_p(nt_ptr), C.c_void_p(read_off_ptr), C.c_uint64(nreads), C.c_uint64(total_nt),
+        C.c_uint64(cap), C.c_void_p(send_h_ptr), C.c_void_p(send_pos_ptr), C.c_void_p(cursors_ptr), C.c_void_p(ids_ptr),
+        C.c_void_p(stream)))
+
+
+def lookup_hashes_dev(index: Index, h_ptr: int, counts_ptr: int, nsrc: int, cap: int, out_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_lookup_hashes_dev(index._h, C.c_void_p(h_ptr), C.c_void_p(counts_ptr), C.c_int(nsrc),
+                                                  C.c_uint64(cap), C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+
+def route_scatter_dev(index: Index, ans_ptr: int, send_pos_ptr: int, cursors_ptr: int, cap: int, ids_ptr: int,
+                      stream: int = 0) -> None:
+    _check(load_library().umgap_route_scatter_dev(index._h, C.c_void_p(ans_ptr), C.c_void_p(send_pos_ptr),
+                                                  C.c_void_p(cursors_ptr), C.c_uint64(cap), C.c_void_p(ids_ptr),
+                                                  C.c_void_p(stream)))
+
+
+def classify_ids_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, ids_ptr: int, read_off_ptr: int, total_nt: int,
+                     group_off_ptr: int, ngroups: int, out_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_classify_ids_dev(index._h, tax._h, C.byref(opts), C.c_void_p(ids_ptr),
+                                                 C.c_void_p(read_off_ptr), C.c_uint64(total_nt), C.c_void_p(group_off_ptr),
+                                                 C.c_uint64(ngroups), C.c_void_p(out_ptr), C.c_void_p(stream)))

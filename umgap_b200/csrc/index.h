@@ -69,6 +69,7 @@ struct umgap_index {
         }
         v.nlevels = nlevels;
         v.k = k;
+        v.nshards = (uint32_t)nshards;
         return v;
     }
 };

@@ -80,10 +80,18 @@ void make_ascii_lut_public(int table, int methionine, uint8_t* out65) {
     memcpy(out65, a.v, 65);
 }
 
+void make_code_lut_public(const umgap_index* idx, int table, int methionine, uint8_t* out65);
+
 static void make_code_lut(const umgap_index* idx, int table, int methionine, CodonLut& lut) {
     CodonLut a;
     make_ascii_lut(table, methionine, a);
     for (int i = 0; i < 65; ++i) lut.v[i] = idx->code_of_byte[a.v[i]];
+}
+
+void make_code_lut_public(const umgap_index* idx, int table, int methionine, uint8_t* out65) {
+    CodonLut l{};
+    make_code_lut(idx, table, methionine, l);
+    memcpy(out65, l.v, 65);
 }
 
 // nucleotide byte -> 0..3 in codon order T,C,A,G (translation.rs:20); anything else, lowercase
@@ -662,6 +670,21 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
         check_opts(idx, nullptr, opts);
         use_device(idx->device);
         launch_translate_lookup(idx, opts, nt_dev, read_off_dev, 0, nreads, ids_dev, (cudaStream_t)stream);
+    });
+}
+
+int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                           const uint32_t* ids_dev, const uint64_t* read_off_dev, uint64_t total_nt,
+                           const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, void* stream) {
+    return guarded([&] {
+        check_opts(idx, tax, opts);
+        if (!tax || !ids_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(idx->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
+        DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
+        UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
+        launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, scratch, taxon_out_dev, err, st);
     });
 }
 

@@ -43,6 +43,7 @@ struct TableView {
     uint32_t nlines[kMaxLevels];
     int nlevels;
     int k;
+    uint32_t nshards;  // > 1: this is one shard; its lines are addressed by the shard-local 32 bits
 };
 
 // Key-range-sharded table: shard o = floor((h >> 13) * nshards / 2^32) owns the key; the low 32
@@ -85,7 +86,9 @@ __device__ __forceinline__ uint64_t probe_sector(uint64_t h, uint32_t nlines, ui
 
 // Address of the sector probe d of hash h reads in level lv, and the number of levels to try.
 __device__ __forceinline__ const ulonglong4* sector_addr(const TableView& t, uint64_t h, uint32_t lv, uint32_t d) {
-    return t.level[lv] + probe_sector(h, t.nlines[lv], d);
+    uint32_t local32;
+    shard_split(h, t.nshards, local32);  // nshards == 1: the top 32 bits of h
+    return t.level[lv] + probe_sector_local(local32, h, t.nlines[lv], d);
 }
 __device__ __forceinline__ uint32_t num_levels(const TableView& t, uint64_t) { return (uint32_t)t.nlevels; }
 __device__ __forceinline__ const ulonglong4* sector_addr(const ShardedView& t, uint64_t h, uint32_t lv, uint32_t d) {
