@@ -372,7 +372,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     lookups_per_launch = nreads * LOOKUPS_PER_READ
-    avg_ms = lookup_ms / max(1, lookup_n)
+    avg_ms = max(lookup_ms / max(1, lookup_n), 1e-9)
     achieved = lookups_per_launch * BYTES_PER_LOOKUP / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -380,7 +380,7 @@ def run_ours(args):
         tj = json.load(open(tpath))
         if tj.get("pairs_per_launch") == B:
             traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "translate_lookup_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if routed is not None else "translate_lookup_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": lookups_per_launch * BYTES_PER_LOOKUP, "avg_launch_ms": avg_ms,
                 "kernel_share_of_step": lookup_ms / ms if ms else None,

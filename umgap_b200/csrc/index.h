@@ -99,6 +99,19 @@ struct TableBuilder {
 
 void check_shard(int shard, int nshards, int k);  // table.cu
 
+// Per-launch timing of the hot kernels (pipeline.cu): kind 0 = lookup, 1 = classify.
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int kind;
+};
+struct LaunchTimer {
+    cudaStream_t st;
+    TimedLaunch t{};
+    bool on;
+    LaunchTimer(int kind, cudaStream_t s);
+    void stop();
+};
+
 // FST v2 stream reader (fst_stream.cpp): calls `sink(key, len, value)` for every key in order.
 struct FstSink {
     virtual void on_key(const uint8_t* key, size_t len, uint64_t value) = 0;

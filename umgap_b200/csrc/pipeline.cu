@@ -518,16 +518,12 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
         UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", o->strategy);
 }
 
-// ---- optional per-launch timing (umgap_kernel_timing) --------------------------------------------
-namespace {
-struct TimedLaunch {
-    cudaEvent_t a, b;
-    int kind;  // 0 lookup, 1 classify
-};
+// ---- optional per-launch timing (umgap_kernel_timing), shared with route.cu -----------------------
+namespace umgap {
 bool g_timing = false;
 std::vector<TimedLaunch> g_launches;
-std::vector<cudaEvent_t> g_event_pool;
-cudaEvent_t take_event() {
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
     if (!g_event_pool.empty()) {
         cudaEvent_t e = g_event_pool.back();
         g_event_pool.pop_back();
@@ -537,24 +533,19 @@ cudaEvent_t take_event() {
     UMGAP_CUDA(cudaEventCreate(&e));
     return e;
 }
-struct LaunchTimer {
-    cudaStream_t st;
-    TimedLaunch t{};
-    bool on;
-    LaunchTimer(int kind, cudaStream_t s) : st(s), on(g_timing) {
-        if (!on) return;
-        t.kind = kind;
-        t.a = take_event();
-        t.b = take_event();
-        UMGAP_CUDA(cudaEventRecord(t.a, st));
-    }
-    void stop() {
-        if (!on) return;
-        UMGAP_CUDA(cudaEventRecord(t.b, st));
-        g_launches.push_back(t);
-    }
-};
-}  // namespace
+LaunchTimer::LaunchTimer(int kind, cudaStream_t s) : st(s), on(g_timing) {
+    if (!on) return;
+    t.kind = kind;
+    t.a = take_event();
+    t.b = take_event();
+    UMGAP_CUDA(cudaEventRecord(t.a, st));
+}
+void LaunchTimer::stop() {
+    if (!on) return;
+    UMGAP_CUDA(cudaEventRecord(t.b, st));
+    g_launches.push_back(t);
+}
+}  // namespace umgap
 
 // Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,

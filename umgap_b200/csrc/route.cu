@@ -188,8 +188,10 @@ int umgap_lookup_hashes_dev(const umgap_index* idx, const uint64_t* h_dev, const
         use_device(idx->device);
         // the shard's own view: the hashes were routed here because this shard owns them, and its
         // lines are addressed through the shard-local 32 bits exactly as at build time
+        LaunchTimer timer(0, (cudaStream_t)stream);
         lookup_hashes_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(idx->view(), h_dev, counts_dev, (uint32_t)nsrc, cap, out_dev);
         UMGAP_CUDA(cudaGetLastError());
+        timer.stop();
     });
 }
 
