@@ -127,12 +127,15 @@ struct LookupSmem {
 // sector are compacted into the queue and re-probed 64 at a time (2 loads in flight per
 // lane), so the warp stays converged.  out: forward k-mer starting at p -> out[p]; reverse-strand
 // k-mer starting at reverse coordinate q -> out[n + q]  (frame f record = entries f-1, f+2, ...).
+// Returns (warp-uniform) the read's frame mask: bit strand*3 + frame is set when that frame record
+// holds at least one non-zero taxon id -- the classify kernel runs seedextend on those only.
 template <int K, class TV>
-__device__ __forceinline__ void lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
-                                            const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane) {
+__device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
+                                                const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane) {
     constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
     const uint32_t npos = n - 3u * K + 1;
+    uint32_t hitbits = 0;
     for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
         for (int i = lane; i < W + 2; i += 32) {
             const uint32_t x = w0 + i;
@@ -179,6 +182,8 @@ __device__ __forceinline__ void lookup_read(const TV& t, const uint8_t* s_lut, L
                 uint32_t v = kNoValue;
                 if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
                 if (p < npos && !more) out[pos] = v;
+                // frame of a k-mer: forward start p -> p % 3, reverse coordinate q = npos-1-p -> q % 3
+                if (!more && v != kNoValue && v != 0) hitbits |= 1u << (strand * 3 + (strand ? npos - 1 - p : p) % 3);
                 const unsigned m = __ballot_sync(0xffffffffu, more);
                 if (more)
                     sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)strand << 50) | ((uint64_t)(lane + 32 * u) << 51);
@@ -217,7 +222,9 @@ __device__ __forceinline__ void lookup_read(const TV& t, const uint8_t* s_lut, L
                         }
                         if (!more) {
                             const uint32_t p = w0 + ((uint32_t)(hq[j] >> 51) & 127u);
-                            out[(hq[j] >> 50) & 1 ? n + (npos - 1 - p) : p] = v;
+                            const uint32_t rev = (uint32_t)(hq[j] >> 50) & 1u;
+                            out[rev ? n + (npos - 1 - p) : p] = v;
+                            if (v != kNoValue && v != 0) hitbits |= 1u << (rev * 3 + (rev ? npos - 1 - p : p) % 3);
                         }
                         next = (hq[j] & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
                     }
@@ -230,14 +237,15 @@ __device__ __forceinline__ void lookup_read(const TV& t, const uint8_t* s_lut, L
             qn = qnext;
         }
     }
+    return __reduce_or_sync(0xffffffffu, hitbits);
 }
 
-// Lookup kernel: one warp per read, ids to global memory.
+// Lookup kernel: one warp per read, ids to global memory, frame hit masks to frame_hits.
 template <int K, class TV>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
 translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
-                        uint32_t* __restrict__ ids) {
+                        uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits) {
     __shared__ uint8_t s_lut[72];
     __shared__ LookupSmem<K> s_sm[kLookupWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -247,8 +255,9 @@ translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_
     for (uint64_t r = r_begin + (uint64_t)blockIdx.x * kLookupWarps + warp; r < r_end; r += nwarps) {
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
-        if (n < 3u * K) continue;  // no frame reaches K residues
-        lookup_read<K, TV>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
+        uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
+        if (n >= 3u * K) mask = lookup_read<K, TV>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
+        if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)mask;
     }
 }
 
@@ -262,8 +271,8 @@ struct ClassifyParams {
 };
 
 constexpr int kAggWarps = 4;
-constexpr int kAggSlots = 2;        // groups whose frame records share one warp pass
-constexpr uint32_t kAggCap = 256;   // run-length entries per group held in shared memory
+constexpr int kAggSlots = 8;        // groups whose live frame records are pooled by one warp
+constexpr uint32_t kAggCap = 96;    // run-length entries per group held in shared memory
 
 struct DevError {  // first error raised by a kernel
     unsigned int flag;
@@ -393,63 +402,105 @@ __device__ __forceinline__ bool seedextend_record(const ClassifyParams& cp, cons
                             scratch + 12 * off0 + 4 * (off - off0));
 }
 
-// One warp per pair of groups: the frame records of both groups (2 x 12 for read pairs) run their
-// seedextend machines side by side, one lane each; each group is then aggregated by the whole warp.
+// One warp per kAggSlots groups.  Of a pair's twelve frame records only the one or two that
+// carry hits need the seedextend machine (the lookup kernel left a 6-bit mask per read), so the
+// warp first pools the live records of all its groups and runs their machines side by side, one
+// lane each, 32 at a time; every group's run-length list is then aggregated by the whole warp.
 __global__ void __launch_bounds__(kAggWarps * 32)
 classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                 const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ group_off,
-                uint64_t g_begin, uint64_t ngroups /* end of the group range */, uint32_t* __restrict__ scratch,
-                uint32_t* __restrict__ taxon_out, DevError* err) {
+                uint64_t g_begin, uint64_t ngroups /* end of the group range */,
+                const uint8_t* __restrict__ frame_hits /* may be null: every record is live */,
+                uint32_t* __restrict__ scratch, uint32_t* __restrict__ taxon_out, DevError* err) {
     __shared__ uint32_t s_a[kAggWarps][kAggSlots][kAggCap];
     __shared__ uint32_t s_c[kAggWarps][kAggSlots][kAggCap];
     __shared__ uint32_t s_p[kAggWarps][kAggCap + 1];
     __shared__ uint32_t s_l[kAggWarps][kAggCap];
     __shared__ uint32_t s_cnt[kAggWarps][kAggSlots];
+    __shared__ uint64_t s_r0[kAggWarps][kAggSlots];
+    __shared__ uint32_t s_nrec[kAggWarps][kAggSlots + 1];  // exclusive prefix of the groups' record counts
+    __shared__ uint32_t s_live[kAggWarps][64];             // pooled live records: slot << 24 | record
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
     const uint64_t nwarps = (uint64_t)gridDim.x * kAggWarps;
     const uint64_t nunits = (ngroups - g_begin + kAggSlots - 1) / kAggSlots;
     for (uint64_t unit = (uint64_t)blockIdx.x * kAggWarps + warp; unit < nunits; unit += nwarps) {
         const uint64_t g_base = g_begin + unit * kAggSlots;
         const int ng = (int)((ngroups - g_base) < (uint64_t)kAggSlots ? (ngroups - g_base) : kAggSlots);
-        uint64_t r0[kAggSlots], nrec[kAggSlots];
-        for (int sl = 0; sl < kAggSlots; ++sl) {
-            r0[sl] = sl < ng ? group_off[g_base + sl] : 0;
-            nrec[sl] = sl < ng ? (group_off[g_base + sl + 1] - r0[sl]) * 6 : 0;
+        // group geometry: lane sl < ng loads group sl; groups of more than 2^24/6 reads are clamped
+        // here and handled by the overflow path below (their records are enumerated there again)
+        uint64_t my_r0 = 0, my_n = 0;
+        if (lane < ng) {
+            my_r0 = group_off[g_base + lane];
+            my_n = (group_off[g_base + lane + 1] - my_r0) * 6;
         }
-        if (lane < kAggSlots) s_cnt[warp][lane] = 0;
+        const uint32_t my_n32 = my_n > 0xFFFFFFu ? 0xFFFFFFu : (uint32_t)my_n;
+        const uint32_t incl = warp_incl_scan(lane < ng ? my_n32 : 0u, lane);
+        if (lane < kAggSlots) {
+            s_r0[warp][lane] = my_r0;
+            s_nrec[warp][lane] = incl - (lane < ng ? my_n32 : 0u);
+            s_cnt[warp][lane] = 0;
+        }
+        const uint32_t total_recs = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) s_nrec[warp][kAggSlots] = total_recs;
         __syncwarp();
-        unsigned present = 0;  // bit sl: group sl produced at least one record
-        if (nrec[0] + nrec[1] <= 32) {  // the common case: all records of both groups in one pass
-            const int sl = (uint64_t)lane < nrec[0] ? 0 : 1;
-            const uint64_t rec = sl ? lane - nrec[0] : lane;
-            bool any = false;
-            if (rec < nrec[sl])
-                any = seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, s_a[warp][sl], s_c[warp][sl], kAggCap, &s_cnt[warp][sl], scratch);
-            const unsigned m = __ballot_sync(0xffffffffu, any);
-            const unsigned lanes0 = nrec[0] >= 32 ? 0xffffffffu : ((1u << nrec[0]) - 1);
-            present = ((m & lanes0) ? 1u : 0u) | ((m & ~lanes0) ? 2u : 0u);
-        } else {
-            for (int sl = 0; sl < ng; ++sl) {
-                bool any = false;
-                for (uint64_t rec = lane; rec < nrec[sl]; rec += 32)
-                    any |= seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, s_a[warp][sl], s_c[warp][sl], kAggCap, &s_cnt[warp][sl], scratch);
-                if (__any_sync(0xffffffffu, any)) present |= 1u << sl;
+        unsigned present = 0;  // bit sl: group sl produced at least one record (prot2kmer2lca.rs:172)
+        uint32_t nlive = 0;
+        auto run_pass = [&](uint32_t count) {  // seedextend machines of the first `count` pooled records
+            if ((uint32_t)lane < count) {
+                const uint32_t e = s_live[warp][lane];
+                const uint32_t sl = e >> 24, rec = e & 0xFFFFFFu;
+                seedextend_record(cp, ids, read_off, s_r0[warp][sl], rec, s_a[warp][sl], s_c[warp][sl], kAggCap,
+                                  &s_cnt[warp][sl], scratch);
+            }
+            __syncwarp();
+        };
+        for (uint32_t base = 0; base < total_recs; base += 32) {
+            const uint32_t e = base + lane;
+            bool exists = false, live = false;
+            uint32_t sl = 0, rec = 0;
+            if (e < total_recs) {
+                while (sl + 1 < (uint32_t)ng && e >= s_nrec[warp][sl + 1]) ++sl;
+                rec = e - s_nrec[warp][sl];
+                const uint64_t r = s_r0[warp][sl] + rec / 6;
+                const uint32_t fr = rec % 6, f = fr % 3;
+                const uint32_t n = (uint32_t)(read_off[r + 1] - read_off[r]);
+                exists = n >= f && (n - f) / 3 >= (uint32_t)cp.k;
+                live = exists && (!frame_hits || (frame_hits[r] >> fr & 1));
+            }
+            for (int q = 0; q < ng; ++q)
+                if (__ballot_sync(0xffffffffu, exists && sl == (uint32_t)q)) present |= 1u << q;
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (live) s_live[warp][nlive + __popc(m & lt_mask)] = (sl << 24) | rec;
+            nlive += __popc(m);
+            __syncwarp();
+            if (nlive >= 32) {
+                run_pass(32);
+                const uint32_t rest = nlive - 32;  // < 32: slide the remainder to the front
+                const uint32_t moved = (uint32_t)lane < rest ? s_live[warp][32 + lane] : 0u;
+                __syncwarp();
+                if ((uint32_t)lane < rest) s_live[warp][lane] = moved;
+                nlive = rest;
+                __syncwarp();
             }
         }
-        __syncwarp();
+        if (nlive) run_pass(nlive);
         for (int sl = 0; sl < ng; ++sl) {
             uint32_t* A = s_a[warp][sl];
             uint32_t* C = s_c[warp][sl];
             uint32_t* P = s_p[warp];
             uint32_t* L = s_l[warp];
             uint32_t total = s_cnt[warp][sl];
-            if (total > kAggCap) {
-                // rare: more runs than the shared-memory list holds -> redo into the group's own slice
-                // of the global scratch (after the private record slices: four lists of gsize words; the number
-                // of runs is below gsize because a read yields fewer k-mers than 2x its length)
-                const uint64_t r1 = r0[sl] + nrec[sl] / 6;
-                const uint64_t gsize = 2 * (read_off[r1] - read_off[r0[sl]]);
-                const uint64_t gbase = 12 * read_off[r0[sl]] + 2 * gsize;  // past the private record slices
+            const uint64_t r0 = s_r0[warp][sl];
+            const uint64_t nrec = (group_off[g_base + sl + 1] - r0) * 6;
+            if (total > kAggCap || nrec > 0xFFFFFFu) {
+                // rare: more runs than the shared-memory list holds (or a huge group) -> redo into the
+                // group's own slice of the global scratch (after the private record slices: four lists
+                // of gsize words; the number of runs is below gsize because a read yields fewer k-mers
+                // than 2x its length)
+                const uint64_t r1 = r0 + nrec / 6;
+                const uint64_t gsize = 2 * (read_off[r1] - read_off[r0]);
+                const uint64_t gbase = 12 * read_off[r0] + 2 * gsize;
                 A = scratch + gbase;
                 C = A + gsize;
                 P = C + gsize;
@@ -457,8 +508,10 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                 __syncwarp();
                 if (lane == 0) s_cnt[warp][sl] = 0;
                 __syncwarp();
-                for (uint64_t rec = lane; rec < nrec[sl]; rec += 32)
-                    seedextend_record(cp, ids, read_off, r0[sl], (uint32_t)rec, A, C, 0xFFFFFFFFu, &s_cnt[warp][sl], scratch);
+                bool any = false;
+                for (uint64_t rec = lane; rec < nrec; rec += 32)
+                    any |= seedextend_record(cp, ids, read_off, r0, (uint32_t)rec, A, C, 0xFFFFFFFFu, &s_cnt[warp][sl], scratch);
+                if (__any_sync(0xffffffffu, any)) present |= 1u << sl;
                 __threadfence_block();
                 __syncwarp();
                 total = s_cnt[warp][sl];
@@ -493,7 +546,7 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12 };  // x3 buffers
+enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15 };  // x3 buffers
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -550,7 +603,7 @@ void LaunchTimer::stop() {
 // Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
                                     const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
-                                    uint64_t r_end, uint32_t* ids_dev, cudaStream_t st) {
+                                    uint64_t r_end, uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st) {
     if (r_end <= r_begin) return;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
@@ -563,10 +616,10 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     case KK:                                                                                                \
         if (idx->nshards > 1)                                                                               \
             translate_lookup_kernel<KK, ShardedView><<<blocks, kLookupWarps * 32, 0, st>>>(                  \
-                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev);                          \
+                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev);          \
         else                                                                                                \
             translate_lookup_kernel<KK, TableView><<<blocks, kLookupWarps * 32, 0, st>>>(                    \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev);                           \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev);           \
         break;
         UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
         UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
@@ -581,14 +634,14 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
 static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
                             const umgap_pipeline_opts* o, const uint32_t* ids_dev,
                             const uint64_t* read_off_dev, const uint64_t* group_off_dev, uint64_t g_begin,
-                            uint64_t g_end, uint32_t* scratch_dev, uint32_t* out_dev, DevError* err,
-                            cudaStream_t st) {
+                            uint64_t g_end, const uint8_t* frame_hits_dev, uint32_t* scratch_dev, uint32_t* out_dev,
+                            DevError* err, cudaStream_t st) {
     if (g_end <= g_begin) return;
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(g_end - g_begin, kAggSlots), kAggWarps), 148ull * 64);
     LaunchTimer timer(1, st);
     classify_kernel<<<blocks, kAggWarps * 32, 0, st>>>(tax->view, make_params(idx, o), ids_dev,
                                                        read_off_dev, group_off_dev, g_begin, g_end,
-                                                       scratch_dev, out_dev, err);
+                                                       frame_hits_dev, scratch_dev, out_dev, err);
     UMGAP_CUDA(cudaGetLastError());
     timer.stop();
 }
@@ -600,10 +653,10 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
                             const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
-                            uint32_t* out_dev, DevError* err, cudaStream_t st) {
+                            uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st) {
     if (!ngroups) return;
-    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, st);
-    launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, scratch_dev, out_dev, err, st);
+    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
+    launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
 }
 
 static void raise_dev_error(const DevError& e) {
@@ -660,7 +713,7 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
     return guarded([&] {
         check_opts(idx, nullptr, opts);
         use_device(idx->device);
-        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, 0, nreads, ids_dev, (cudaStream_t)stream);
+        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, 0, nreads, ids_dev, nullptr, (cudaStream_t)stream);
     });
 }
 
@@ -675,7 +728,7 @@ int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, co
         uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
-        launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, scratch, taxon_out_dev, err, st);
+        launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, nullptr, scratch, taxon_out_dev, err, st);
     });
 }
 
@@ -693,7 +746,8 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
         uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
-        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, group_off_dev, ngroups, ids, scratch,
+        uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, nreads + 64);
+        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, group_off_dev, ngroups, ids, scratch, hits,
                         taxon_out_dev, err, st);
     });
 }
@@ -764,7 +818,8 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                 rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, d_goff, cnt_g + 1, r0);
                 UMGAP_CUDA(cudaGetLastError());
                 if (prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
-                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, d_goff, cnt_g, ids, scratch, d_out, err, s);
+                uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
+                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, d_goff, cnt_g, ids, scratch, hits, d_out, err, s);
                 UMGAP_CUDA(cudaEventRecord(done[buf], s));
                 UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
                 prev = buf;
