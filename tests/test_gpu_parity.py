@@ -509,3 +509,23 @@ def test_full_size_index_properties(capi):
     assert np.array_equal(host, outs[0].view(np.uint32))
     assert 0.6 < (host != 1).mean() < 0.8                # 70 % of the pairs come from the proteome
     gidx.close()
+
+
+def test_region_partitioned_probing_gives_identical_results(capi, world):
+    """Tables beyond the probe-region size are looked up one hash-prefix region per kernel pass; forcing
+    4 MiB regions on the 16 MiB test table (4 passes) must not change a single answer."""
+    reads = datagen.make_reads(world["proteins"], 400, seed=101)
+    reads += [("s/1", "ACGT" * 5), ("s/2", "N" * 90)]
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
+    keys = sorted(world["index"])
+    gidx = capi.Index.from_pairs(keys, [world["index"][k] for k in keys], k=9)
+    for strategy in (0, 1, 2):
+        opts = capi.default_opts(min_seed_size=2, max_gap_size=1, strategy=strategy)
+        gidx.set_probe_region(0)
+        a, _ = capi.classify_reads(gidx, world["gtax"], opts, nt, off, goff)
+        gidx.set_probe_region(4 << 20)
+        b, _ = capi.classify_reads(gidx, world["gtax"], opts, nt, off, goff)
+        assert np.array_equal(a, b)
+        assert (a != 1).sum() > 100
+    gidx.close()

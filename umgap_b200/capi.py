@@ -23,6 +23,7 @@ AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
 SYMBOLS = [
     "umgap_last_error", "umgap_abi_version", "umgap_device_count",
     "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
+    "umgap_index_set_probe_region",
     "umgap_index_load_fst_shard", "umgap_index_from_pairs_shard", "umgap_index_shard_desc",
     "umgap_index_attach_shards", "umgap_index_attach_shards_local", "umgap_index_build_synthetic_shard",
     "umgap_taxonomy_load", "umgap_taxonomy_from_arrays", "umgap_taxonomy_free",
@@ -223,6 +224,9 @@ class Index:
         i = IndexInfo()
         _check(load_library().umgap_index_get_info(self._h, C.byref(i)))
         return i
+
+    def set_probe_region(self, nbytes: int) -> None:
+        _check(load_library().umgap_index_set_probe_region(self._h, C.c_uint64(nbytes)))
 
     def randsector_rate(self, n_gathers: int, iters: int = 5) -> float:
         r = C.c_double()

@@ -129,9 +129,13 @@ struct LookupSmem {
 // k-mer starting at reverse coordinate q -> out[n + q]  (frame f record = entries f-1, f+2, ...).
 // Returns (warp-uniform) the read's frame mask: bit strand*3 + frame is set when that frame record
 // holds at least one non-zero taxon id -- the classify kernel runs seedextend on those only.
-template <int K, class TV>
+// region_lo / region_hi: only k-mers whose hash prefix (h >> 13) lies in [region_lo, region_hi) are
+// looked up and written in this pass (tables beyond the GPU's address-translation reach are probed
+// one region at a time, see launch_translate_lookup); 0 / 2^32 selects everything.
+template <int K, class TV, bool REGION>
 __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
-                                                const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane) {
+                                                const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane,
+                                                uint64_t region_lo, uint64_t region_hi) {
     constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
     const uint32_t npos = n - 3u * K + 1;
@@ -156,6 +160,7 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
             uint64_t h[4];
             ulonglong4 sec[4];
             bool valid[4];
+            bool elsewhere[REGION ? 4 : 1];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int pl = lane + 32 * u;
@@ -168,8 +173,16 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
                     bad |= c;
                     key = (key << 5) | (c & 31u);
                 }
-                valid[u] = (w0 + pl < npos) && !(bad & 0x80u);
                 h[u] = mix45(key);
+                valid[u] = (w0 + pl < npos) && !(bad & 0x80u);
+                if (REGION) {
+                    // another pass answers this position: valid k-mers of other regions, and -- except in
+                    // the first pass -- the k-mers that cannot be keys (a miss in every pass)
+                    const uint64_t prefix = h[u] >> 13;
+                    const bool mine = valid[u] ? (prefix >= region_lo && prefix < region_hi) : region_lo == 0;
+                    elsewhere[u] = !mine;
+                    valid[u] = valid[u] && mine;
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -181,7 +194,7 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
                 bool more = false;
                 uint32_t v = kNoValue;
                 if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-                if (p < npos && !more) out[pos] = v;
+                if (p < npos && !more && !(REGION && elsewhere[REGION ? u : 0])) out[pos] = v;
                 // frame of a k-mer: forward start p -> p % 3, reverse coordinate q = npos-1-p -> q % 3
                 if (!more && v != kNoValue && v != 0) hitbits |= 1u << (strand * 3 + (strand ? npos - 1 - p : p) % 3);
                 const unsigned m = __ballot_sync(0xffffffffu, more);
@@ -241,11 +254,12 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
 }
 
 // Lookup kernel: one warp per read, ids to global memory, frame hit masks to frame_hits.
-template <int K, class TV>
+template <int K, class TV, bool REGION>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
 translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
-                        uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits) {
+                        uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits, uint64_t region_lo,
+                        uint64_t region_hi) {
     __shared__ uint8_t s_lut[72];
     __shared__ LookupSmem<K> s_sm[kLookupWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -256,8 +270,8 @@ translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
-        if (n >= 3u * K) mask = lookup_read<K, TV>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane);
-        if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)mask;
+        if (n >= 3u * K) mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi);
+        if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)(!REGION || region_lo == 0 ? mask : (mask | frame_hits[r]));
     }
 }
 
@@ -610,25 +624,38 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(r_end - r_begin, kLookupWarps), 148ull * 32);
     if (idx->nshards > 1 && !idx->attached)
         UMGAP_FAIL(UMGAP_ERR_INVALID, "sharded index: call umgap_index_attach_shards() before looking up");
-    LaunchTimer timer(0, st);
-    switch (idx->k) {
-#define UMGAP_CASE(KK)                                                                                      \
-    case KK:                                                                                                \
-        if (idx->nshards > 1)                                                                               \
-            translate_lookup_kernel<KK, ShardedView><<<blocks, kLookupWarps * 32, 0, st>>>(                  \
-                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev);          \
-        else                                                                                                \
-            translate_lookup_kernel<KK, TableView><<<blocks, kLookupWarps * 32, 0, st>>>(                    \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev);           \
+    // Random probes over more than ~64 GiB collapse to a quarter of the line rate on B200 (address-
+    // translation reach, profiles/r01_randsector_sweep.log) while any 64 GiB window runs at full rate:
+    // a larger level 0 is probed one hash-prefix region at a time (the line index is monotone in the
+    // prefix).  Every pass translates and packs all k-mers again, which costs less than the cliff.
+    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
+    const uint64_t table_bytes = (uint64_t)idx->level_nlines[0] * 128;
+    const int nregions = idx->nshards > 1 ? 1 : (int)std::max<uint64_t>(1, ceil_div(table_bytes, region_bytes));
+    for (int reg = 0; reg < nregions; ++reg) {
+        const uint64_t lo = (1ull << 32) * reg / nregions, hi = (1ull << 32) * (reg + 1) / nregions;
+        LaunchTimer timer(0, st);
+        switch (idx->k) {
+#define UMGAP_CASE(KK)                                                                                       \
+    case KK:                                                                                                 \
+        if (idx->nshards > 1)                                                                                \
+            translate_lookup_kernel<KK, ShardedView, false><<<blocks, kLookupWarps * 32, 0, st>>>(            \
+                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);   \
+        else if (nregions > 1)                                                                               \
+            translate_lookup_kernel<KK, TableView, true><<<blocks, kLookupWarps * 32, 0, st>>>(               \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);    \
+        else                                                                                                 \
+            translate_lookup_kernel<KK, TableView, false><<<blocks, kLookupWarps * 32, 0, st>>>(              \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);    \
         break;
-        UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
-        UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
+            UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
+            UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
 #undef UMGAP_CASE
-        default:
-            UMGAP_FAIL(UMGAP_ERR_INVALID, "unsupported k %d", idx->k);
+            default:
+                UMGAP_FAIL(UMGAP_ERR_INVALID, "unsupported k %d", idx->k);
+        }
+        UMGAP_CUDA(cudaGetLastError());
+        timer.stop();
     }
-    UMGAP_CUDA(cudaGetLastError());
-    timer.stop();
 }
 
 static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
@@ -664,6 +691,13 @@ static void raise_dev_error(const DevError& e) {
 }
 
 extern "C" {
+
+int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes) {
+    return guarded([&] {
+        if (!idx) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        idx->region_bytes = bytes;
+    });
+}
 
 int umgap_kernel_timing(int enable) {
     g_timing = enable != 0;
