@@ -150,7 +150,7 @@ def run_reference(args):
     inst = cpu_instance(args.cpu_index_keys)
     dt, _, _ = cpu_run(inst, 0, 2000, threads)
     # bounded sample per step: the whole run (warmup + steps) stays around a minute
-    per_step = int(min(args.pairs_per_step, 250_000, max(1000, 2000 * (60.0 / max(1, args.steps + args.warmup)) / max(dt, 1e-4))))
+    per_step = int(min(args.pairs_per_step, 100_000, max(1000, 2000 * (60.0 / max(1, args.steps + args.warmup)) / max(dt, 1e-4))))
     for w in range(args.warmup):
         cpu_run(inst, 1_000_000 + w * per_step, per_step, threads)
     total_t, total_l = 0.0, 0

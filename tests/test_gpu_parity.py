@@ -527,5 +527,5 @@ def test_region_partitioned_probing_gives_identical_results(capi, world):
         gidx.set_probe_region(4 << 20)
         b, _ = capi.classify_reads(gidx, world["gtax"], opts, nt, off, goff)
         assert np.array_equal(a, b)
-        assert (a != 1).sum() > 100
+        assert (a != 1).sum() > (100 if strategy else 10)
     gidx.close()
