@@ -75,7 +75,7 @@ def taxa2agg_sets(text: str, tax: Taxonomy, strategy: int, factor: float = 0.25,
 
 
 def classify_reads(reads: Sequence[Tuple[str, str]], index, tax: Taxonomy, *, table: int = 1,
-                   methionine: bool = False, k: int = 9, use_seedextend: bool = True,
+                   methionine: bool = False, k: int = 9, one_on_one: bool = True, use_seedextend: bool = True,
                    min_seed_size: int = 2, max_gap_size: int = 0, delimiter: Optional[str] = "/",
                    strategy: int = agg.HYBRID, factor: float = 0.25, lower_bound: float = 0.0,
                    ranked_only: bool = False) -> List[Tuple[str, Set[int]]]:
@@ -83,7 +83,7 @@ def classify_reads(reads: Sequence[Tuple[str, str]], index, tax: Taxonomy, *, ta
     reads, composed through the text stages above so that every stream-format quirk applies."""
     text = "".join(fasta.write_record(h, [s], "", False) for h, s in reads)
     text = translate_text(text, table, methionine)
-    text = prot2kmer2lca_text(text, index, k, one_on_one=True)
+    text = prot2kmer2lca_text(text, index, k, one_on_one=one_on_one)
     if use_seedextend:
         text = seedextend_text(text, min_seed_size, max_gap_size)
     text = uniq_text(text, delimiter)

@@ -529,3 +529,31 @@ def test_region_partitioned_probing_gives_identical_results(capi, world):
         assert np.array_equal(a, b)
         assert (a != 1).sum() > (100 if strategy else 10)
     gidx.close()
+
+
+@pytest.mark.parametrize("table,meth,one,use_se,s,g,strategy,ranked", [
+    (1, False, False, True, 2, 0, 1, False),    # misses omitted before seedextend (no -o)
+    (1, False, False, True, 3, 1, 2, False),
+    (1, False, False, False, 2, 0, 0, False),   # no seedextend, no -o (tryptic-style aggregation of all hits)
+    (11, True, True, True, 2, 1, 1, True),      # bacterial code, -m, ranked snapping
+    (4, True, True, False, 2, 0, 2, False),
+])
+def test_classify_reads_option_matrix(capi, world, table, meth, one, use_se, s, g, strategy, ranked):
+    """Every switch of the fused entry point against the oracle's text pipeline."""
+    reads = datagen.make_reads(world["proteins"], 150, seed=111 + table)
+    reads += [("x/1", "ATG" * 20 + "TTG" * 15), ("x/2", "CTG" * 30 + "NNN" + "GTG" * 9)]   # start codons that -m rewrites
+    oidx = olookup.DictIndex(world["index"])
+    want = dict(opipe.classify_reads(reads, oidx, world["otax"], table=table, methionine=meth, one_on_one=one,
+                                     use_seedextend=use_se, min_seed_size=s, max_gap_size=g, strategy=strategy,
+                                     factor=0.25, lower_bound=0.0, ranked_only=ranked))
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
+    opts = capi.default_opts(table=table, methionine=int(meth), one_on_one=int(one), seedextend=int(use_se), min_seed_size=s,
+                             max_gap_size=g, strategy=strategy, ranked_only=int(ranked))
+    got, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, goff)
+    below = 0
+    for gi in range(len(goff) - 1):
+        h = reads[2 * gi][0].split("/")[0]
+        assert int(got[gi]) in want[h], (h, int(got[gi]), want[h])
+        below += int(got[gi]) != 1
+    assert below > 5
