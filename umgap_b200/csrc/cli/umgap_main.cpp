@@ -651,8 +651,7 @@ int cmd_classify(int argc, char** argv) {
     o.factor = parse_f32(a.get("factor", "0.25"));
     o.lower_bound = parse_f32(a.get("lower-bound", "0"));
     o.ranked_only = a.has("ranked");
-    const bool has_delim = a.has("delimiter");
-    const std::string delim = a.get("delimiter", "/");
+    const std::string delim = a.get("delimiter", "/");  // the presets join the mates with `uniq -d /`
     const int k = (int)parse_usize(a.get("length", "9"));
     IndexHandle idx;
     TaxHandle tax;
