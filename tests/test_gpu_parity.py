@@ -557,3 +557,32 @@ def test_classify_reads_option_matrix(capi, world, table, meth, one, use_se, s, 
         assert int(got[gi]) in want[h], (h, int(got[gi]), want[h])
         below += int(got[gi]) != 1
     assert below > 5
+
+
+def test_committed_golden_fixture(capi):
+    """The CUDA path against tests/golden/pipeline_small.json (frozen oracle outputs; the script that
+    made them is tests/golden/make_golden.py)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_small.json")))
+    ids = np.array([t[0] for t in g["taxa"]], dtype=np.uint64)
+    gtax = capi.Taxonomy.from_arrays(ids, np.array([t[2] for t in g["taxa"]], dtype=np.uint64),
+                                     np.array([t[1] for t in g["taxa"]], dtype=np.uint8),
+                                     np.array([t[3] for t in g["taxa"]], dtype=np.uint8))
+    gidx = capi.Index.from_pairs([k.encode() for k, _ in g["index"]], [v for _, v in g["index"]], k=9)
+    reads = g["reads"]
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    heads = [h.split("/")[0] for h, _ in reads]
+    goff = [0] + [i for i in range(1, len(reads) + 1) if i == len(reads) or heads[i] != heads[i - 1]]
+    for case in g["cases"]:
+        o = case["options"]
+        opts = capi.default_opts(one_on_one=int(o.get("one_on_one", True)), seedextend=int(o.get("use_seedextend", True)),
+                                 min_seed_size=o.get("min_seed_size", 2), max_gap_size=o.get("max_gap_size", 0),
+                                 strategy=o["strategy"], factor=o.get("factor", 0.25), lower_bound=o.get("lower_bound", 0.0))
+        got, _ = capi.classify_reads(gidx, gtax, opts, nt, off, np.array(goff, dtype=np.uint64))
+        want = dict((h, s) for h, s in case["expected"])
+        for gi in range(len(goff) - 1):
+            h = heads[goff[gi]]
+            if h in want:
+                assert int(got[gi]) in want[h], (case["name"], h, int(got[gi]), want[h])
+            else:
+                assert int(got[gi]) == capi.ABSENT, (case["name"], h)

@@ -258,3 +258,17 @@ def test_taxa2agg_record_loop(tax):
     # lower bound drops singletons (agg/mod.rs:39-44)
     out = pipeline.taxa2agg_sets(">a\n185751\n185751\n185752\n", tax, agg.LCA_STAR, lower_bound=2)
     assert out == [("a", {185751})]
+
+
+def test_oracle_reproduces_committed_golden_fixture():
+    """tests/golden/pipeline_small.json (frozen oracle outputs) still matches the oracle."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    frozen = json.load(open(os.path.join(here, "golden", "pipeline_small.json")))
+    fresh = json.loads(json.dumps(mod.build()))
+    assert fresh == frozen
