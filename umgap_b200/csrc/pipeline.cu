@@ -811,7 +811,7 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
         // nucleotides and offsets of the next chunks upload and the results of the previous one
         // download.  Offsets are uploaded as given and rebased on the device.
-        const uint64_t kChunkNt = 24ull << 20;  // nucleotides per chunk
+        const uint64_t kChunkNt = 48ull << 20;  // nucleotides per chunk (measured best of 8..96 MiB)
         constexpr int kBufs = 3;
         cudaStream_t st[kBufs];
         cudaEvent_t done[kBufs];
