@@ -275,6 +275,269 @@ translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_
     }
 }
 
+// ---- sampled lookups: seedextend makes most lookups provably irrelevant ----------------------------
+// With `prot2kmer2lca -o | seedextend -s S` (S >= 2) a frame record contributes ids only if it holds
+// a run of S equal non-zero ids at S CONSECUTIVE k-mer positions (seedextend.rs:137-149: same_max
+// counts consecutive list elements, and with -o the list has one element per position).  Any S
+// consecutive positions contain one whose index in the frame is a multiple of s = min(S, 4).  So a
+// first kernel probes only those positions (1/s of the lookups, lookup_sampled_kernel); a frame none
+// of whose sampled k-mers returned a non-zero taxon cannot hold a seed, its record comes out empty
+// whatever the other positions hold, and they are never looked up.  The frames with a sampled hit --
+// the one or two true reading frames of a read from the index, plus the odd stray hit -- are queued as
+// work items and a second kernel probes their remaining positions, four frames per warp round
+// (lookup_rest_kernel).  Bit-identical output, about half of the HBM line fills and a third of the
+// instructions.  Reads too long for one tile take the plain lookup_read path inside the first kernel.
+
+// Re-probes the queued lookups until all are answered.  Queue entry: hash | distance << 45 |
+// level << 48 | strand << 50 | tile position << 51 | unit << 58; unit u writes through outs[u] with
+// geometry ns[u] / nposs[u].
+template <int K, class TV, int UNITS>
+__device__ __forceinline__ void drain_queue(const TV& t, LookupSmem<K>& sm, uint32_t qn, uint32_t* const (&outs)[UNITS],
+                                            const uint32_t (&ns)[UNITS], const uint32_t (&nposs)[UNITS], uint32_t& hitbits,
+                                            int lane) {
+    const unsigned lt_mask = (1u << lane) - 1;
+    __syncwarp();
+    while (qn) {
+        uint32_t qnext = 0;
+        for (uint32_t c = 0; c < qn; c += 32) {
+            const uint32_t i = c + lane;
+            const uint64_t hq = i < qn ? sm.q[i] : ~0ull;
+            bool more = false;
+            uint64_t next = 0;
+            if (hq != ~0ull) {
+                uint32_t d = (uint32_t)(hq >> 45) & 7u, lv = (uint32_t)(hq >> 48) & 3u;
+                const uint64_t hh = hq & kKeyMask;
+                const ulonglong4 s2 = load_sector(sector_addr(t, hh, lv, d));
+                const uint32_t v = probe_sector_data(s2, (d << 28) | ((uint32_t)hh & kTagMask), more);
+                if (more && ++d == (uint32_t)kMaxDisp) {
+                    d = 0;
+                    if (++lv == num_levels(t, hh)) more = false;  // v is kNoValue here
+                }
+                if (!more) {
+                    const uint32_t u = UNITS > 1 ? (uint32_t)(hq >> 58) & 3u : 0u;
+                    uint32_t* out = outs[0];
+                    uint32_t n = ns[0], npos = nposs[0];
+#pragma unroll
+                    for (int k = 1; k < UNITS; ++k)
+                        if (u == (uint32_t)k) {
+                            out = outs[k];
+                            n = ns[k];
+                            npos = nposs[k];
+                        }
+                    const uint32_t p = (uint32_t)(hq >> 51) & 127u, rev = (uint32_t)(hq >> 50) & 1u;
+                    const uint32_t y = rev ? npos - 1 - p : p;
+                    out[rev ? n + y : y] = v;
+                    if (v != kNoValue && v != 0) hitbits |= 1u << (rev * 3 + y % 3);
+                }
+                next = (hq & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
+            }
+            __syncwarp();
+            const unsigned m = __ballot_sync(0xffffffffu, more);
+            if (more) sm.q[qnext + __popc(m & lt_mask)] = next;
+            qnext += __popc(m);
+            __syncwarp();
+        }
+        qn = qnext;
+    }
+}
+
+// Phase 1: one warp per read, the sampled positions of all six frames.  Writes the frame mask and
+// queues one work item (read << 3 | frame) per frame with a hit.
+template <int K, class TV, int STRIDE>
+__global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
+lookup_sampled_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
+                      const uint64_t* __restrict__ read_off, uint64_t nreads, uint32_t* __restrict__ ids,
+                      uint8_t* __restrict__ frame_hits, uint32_t* __restrict__ items,
+                      unsigned long long* __restrict__ nitems) {
+    constexpr uint32_t kBlock = 3 * STRIDE;                    // sampled coordinates: y % kBlock < 3
+    constexpr uint32_t kOneTile = (kTile / kBlock) * kBlock;   // reads with npos <= this fit one tile
+    constexpr int W = LookupSmem<K>::W;
+    __shared__ uint8_t s_lut[72];
+    __shared__ LookupSmem<K> s_sm[kLookupWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
+    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    LookupSmem<K>& sm = s_sm[warp];
+    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
+    for (uint64_t r = (uint64_t)blockIdx.x * kLookupWarps + warp; r < nreads; r += nwarps) {
+        const uint64_t off = read_off[r];
+        const uint32_t n = (uint32_t)(read_off[r + 1] - off);
+        uint32_t mask = 0;
+        if (n >= 3u * K) {
+            const uint32_t npos = n - 3u * K + 1;
+            if (npos > kOneTile) {  // long read: every position, no work items
+                mask = lookup_read<K, TV, false>(t, s_lut, sm, nt + off, n, ids + 2 * off, lane, 0, 0);
+            } else {
+                uint32_t* out = ids + 2 * off;
+                for (int i = lane; i < W + 2; i += 32) sm.nt[i] = (uint32_t)i < n ? (uint8_t)nt_code(nt[off + i]) : (uint8_t)4;
+                __syncwarp();
+                for (int i = lane; i < W; i += 32) {
+                    const uint32_t a = sm.nt[i], b = sm.nt[i + 1], c = sm.nt[i + 2];
+                    const bool has_n = ((a | b | c) & 4u) != 0;
+                    sm.f[i] = s_lut[has_n ? 64 : 16 * a + 4 * b + c];
+                    sm.r[i] = s_lut[has_n ? 64 : 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2)];
+                }
+                __syncwarp();
+                // candidates of one strand: e = 0..cnt-1 -> y = kBlock * (e / 3) + e % 3 (< npos); both strands
+                // are enumerated back to back, three per lane and round
+                const uint32_t cnt = 3 * ((npos - 1) / kBlock + 1);
+                uint32_t qn = 0, hitbits = 0;
+                for (uint32_t e0 = 0; e0 < 2 * cnt; e0 += 96) {
+                    uint64_t h[3];
+                    ulonglong4 sec[3];
+                    uint32_t ys[3];
+                    bool valid[3], act[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t e = e0 + lane + 32 * u;
+                        const uint32_t sd = e >= cnt ? 1u : 0u, ee = e - sd * cnt;
+                        const uint32_t y = kBlock * (ee / 3) + ee % 3;
+                        act[u] = e < 2 * cnt && y < npos;
+                        ys[u] = y | (sd << 31);
+                        const uint32_t pl = act[u] ? (sd ? npos - 1 - y : y) : 0u;
+                        const uint8_t* codes = sd ? sm.r : sm.f;
+                        uint64_t key = 0;
+                        uint32_t bad = 0;
+#pragma unroll
+                        for (int i = 0; i < K; ++i) {
+                            const uint32_t c = codes[pl + 3 * (sd ? K - 1 - i : i)];
+                            bad |= c;
+                            key = (key << 5) | (c & 31u);
+                        }
+                        h[u] = mix45(key);
+                        valid[u] = act[u] && !(bad & 0x80u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const uint32_t sd = ys[u] >> 31, y = ys[u] & 0x7FFFFFFFu;
+                        bool more = false;
+                        uint32_t v = kNoValue;
+                        if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                        if (act[u] && !more) {
+                            out[sd ? n + y : y] = v;
+                            if (v != kNoValue && v != 0) hitbits |= 1u << (sd * 3 + y % 3);
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, more);
+                        if (more)
+                            sm.q[qn + __popc(m & lt_mask)] =
+                                h[u] | (1ull << 45) | ((uint64_t)sd << 50) | ((uint64_t)(sd ? npos - 1 - y : y) << 51);
+                        qn += __popc(m);
+                    }
+                }
+                uint32_t* const outs[1] = {out};
+                const uint32_t ns[1] = {n}, nposs[1] = {npos};
+                drain_queue<K, TV, 1>(t, sm, qn, outs, ns, nposs, hitbits, lane);
+                mask = __reduce_or_sync(0xffffffffu, hitbits);
+                if (mask && lane == 0) {  // one work item per live frame
+                    const unsigned long long at = atomicAdd(nitems, (unsigned long long)__popc(mask));
+                    uint32_t k = 0;
+                    for (uint32_t fr = 0; fr < 6; ++fr)
+                        if (mask >> fr & 1) items[at + k++] = (uint32_t)(r << 3) | fr;
+                }
+            }
+        }
+        if (lane == 0) frame_hits[r] = (uint8_t)mask;
+        __syncwarp();
+    }
+}
+
+// Phase 2: the non-sampled positions of the live frames, four frames (of any four reads) per warp round,
+// one position per lane and frame.
+template <int K, class TV, int STRIDE>
+__global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
+lookup_rest_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
+                   const uint64_t* __restrict__ read_off, uint32_t* __restrict__ ids, const uint32_t* __restrict__ items,
+                   const unsigned long long* __restrict__ nitems_dev) {
+    constexpr int W = LookupSmem<K>::W;
+    __shared__ uint8_t s_lut[72];
+    __shared__ LookupSmem<K> s_sm[kLookupWarps];           // only the queue is used
+    __shared__ uint8_t s_codes[kLookupWarps][4][W + 8];     // codon-start residues of each unit's strand
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
+    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    LookupSmem<K>& sm = s_sm[warp];
+    const uint64_t nitems = *nitems_dev;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
+    for (uint64_t base = ((uint64_t)blockIdx.x * kLookupWarps + warp) * 4; base < nitems; base += nwarps * 4) {
+        uint32_t* outs[4];
+        uint32_t ns[4], nposs[4], frs[4];
+        bool have[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            have[u] = base + u < nitems;
+            const uint32_t item = have[u] ? items[base + u] : 0u;
+            const uint64_t r = item >> 3;
+            frs[u] = item & 7u;
+            const uint64_t off = read_off[r];
+            ns[u] = have[u] ? (uint32_t)(read_off[r + 1] - off) : 3u * K;
+            nposs[u] = ns[u] - 3u * K + 1;
+            outs[u] = ids + 2 * off;
+            // stage the strand of this frame: residue of every codon start of the read
+            const bool rev = frs[u] >= 3;
+            const uint8_t* src = nt + off;
+            for (int i = lane; i < W; i += 32) {
+                uint32_t a = 4, b = 4, c = 4;
+                if (have[u] && (uint32_t)i + 2 < ns[u]) {
+                    a = nt_code(src[i]);
+                    b = nt_code(src[i + 1]);
+                    c = nt_code(src[i + 2]);
+                }
+                const bool has_n = ((a | b | c) & 4u) != 0;
+                s_codes[warp][u][i] = s_lut[has_n ? 64 : rev ? 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2) : 16 * a + 4 * b + c];
+            }
+        }
+        __syncwarp();
+        uint64_t h[4];
+        ulonglong4 sec[4];
+        uint32_t ys[4];
+        bool valid[4], act[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // lane -> the lane-th non-sampled position of the frame: j = STRIDE * (lane / (STRIDE-1)) + 1 + lane % (STRIDE-1)
+            const uint32_t rev = frs[u] >= 3 ? 1u : 0u, f = frs[u] % 3;
+            const uint32_t j = STRIDE * ((uint32_t)lane / (STRIDE - 1)) + 1 + (uint32_t)lane % (STRIDE - 1);
+            const uint32_t y = 3 * j + f;
+            act[u] = have[u] && y < nposs[u];
+            ys[u] = y;
+            const uint32_t pl = act[u] ? (rev ? nposs[u] - 1 - y : y) : 0u;
+            uint64_t key = 0;
+            uint32_t bad = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t c = s_codes[warp][u][pl + 3 * (rev ? K - 1 - i : i)];
+                bad |= c;
+                key = (key << 5) | (c & 31u);
+            }
+            h[u] = mix45(key);
+            valid[u] = act[u] && !(bad & 0x80u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+        uint32_t qn = 0, hitbits = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t rev = frs[u] >= 3 ? 1u : 0u, y = ys[u];
+            bool more = false;
+            uint32_t v = kNoValue;
+            if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+            if (act[u] && !more) outs[u][rev ? ns[u] + y : y] = v;
+            const unsigned m = __ballot_sync(0xffffffffu, more);
+            if (more)
+                sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)rev << 50) |
+                                                 ((uint64_t)(rev ? nposs[u] - 1 - y : y) << 51) | ((uint64_t)u << 58);
+            qn += __popc(m);
+        }
+        drain_queue<K, TV, 4>(t, sm, qn, outs, ns, nposs, hitbits, lane);
+        __syncwarp();
+    }
+}
+
 // ---- classify: seedextend + uniq join + aggregate, one warp per group ----------------------------
 struct ClassifyParams {
     int k;
@@ -560,7 +823,7 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15 };  // x3 buffers
+enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_ITEMS = 16, WS_NITEMS = 17 };  // x3 buffers
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -677,12 +940,54 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
 // (Running the classify kernel of one slice concurrently with the lookup kernel of the next, on two
 // streams with priorities, was measured and gives nothing: both kernels want the same registers
 // and issue slots -- profiles/README.md.)
+// Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
+// the frames flagged in frame_hits_dev have complete ids afterwards, which is all the classify kernel reads.
+template <int STRIDE>
+static void launch_sampled(const umgap_index* idx, const CodonLut& lut, const uint8_t* nt_dev, const uint64_t* read_off_dev,
+                           uint64_t nreads, uint32_t* ids_dev, uint8_t* frame_hits_dev, uint32_t* items,
+                           unsigned long long* nitems, cudaStream_t st) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kLookupWarps), 148ull * 32);
+    LaunchTimer timer(0, st);
+    lookup_sampled_kernel<9, TableView, STRIDE><<<blocks, kLookupWarps * 32, 0, st>>>(idx->view(), lut, nt_dev, read_off_dev, nreads,
+                                                                                     ids_dev, frame_hits_dev, items, nitems);
+    UMGAP_CUDA(cudaGetLastError());
+    // the number of work items is only known on the device: size the grid for the typical 1-2 live frames per read
+    const unsigned blocks2 = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads * 3 / 2, 4), kLookupWarps) + 1, 148ull * 32);
+    lookup_rest_kernel<9, TableView, STRIDE><<<blocks2, kLookupWarps * 32, 0, st>>>(idx->view(), lut, nt_dev, read_off_dev, ids_dev,
+                                                                                   items, nitems);
+    UMGAP_CUDA(cudaGetLastError());
+    timer.stop();
+}
+
+static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
+                                            const uint64_t* read_off_dev, uint64_t nreads, uint32_t* ids_dev,
+                                            uint8_t* frame_hits_dev, cudaStream_t st) {
+    static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
+    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
+    if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
+        (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 29))
+        return false;
+    if (!nreads) return true;
+    CodonLut lut{};
+    make_code_lut(idx, o->table, o->methionine, lut);
+    uint32_t* items = (uint32_t*)idx->ws.get(WS_ITEMS, (6 * nreads + 64) * sizeof(uint32_t));
+    unsigned long long* nitems = (unsigned long long*)idx->ws.get(WS_NITEMS, 64);
+    UMGAP_CUDA(cudaMemsetAsync(nitems, 0, sizeof(unsigned long long), st));
+    switch (std::min(o->min_seed_size, 4)) {
+        case 2: launch_sampled<2>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
+        case 3: launch_sampled<3>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
+        default: launch_sampled<4>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
+    }
+    return true;
+}
+
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
                             const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
                             uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st) {
     if (!ngroups) return;
-    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
+    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, st))
+        launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
     launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
 }
 
