@@ -39,6 +39,12 @@ ms1 = timeit(lambda: capi.translate_lookup_dev(gidx, opts, nt.data_ptr(), roff.d
 print(f"translate_lookup: {ms1:.3f} ms  {nlook/ms1/1e6:.2f} G lookups/s  {nlook*32/ms1/1e6:.1f} GB/s algorithmic", flush=True)
 ms2 = timeit(lambda: capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st))
 print(f"classify (both kernels): {ms2:.3f} ms  {npairs*2/ms2/1e3:.2f} M reads/s", flush=True)
+capi.kernel_timing(True); capi.kernel_times()
+for _ in range(5):
+    capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st)
+torch.cuda.synchronize()
+lm, ln, cm, cn = capi.kernel_times(); capi.kernel_timing(False)
+print(f"kernels: lookup {lm/max(ln,1):.3f} ms  classify {cm/max(cn,1):.3f} ms", flush=True)
 o = out.cpu().numpy().view(np.uint32)
 print("classified below root:", float((o != 1).mean()), "absent:", int((o == 0xFFFFFFFF).sum()))
 hits = (ids[: 2 * npairs * 2 * L].view(torch.int32) != -1)

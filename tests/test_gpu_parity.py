@@ -586,3 +586,53 @@ def test_committed_golden_fixture(capi):
                 assert int(got[gi]) in want[h], (case["name"], h, int(got[gi]), want[h])
             else:
                 assert int(got[gi]) == capi.ABSENT, (case["name"], h)
+
+
+@pytest.mark.parametrize("s,g,strategy", [(2, 0, 0), (3, 0, 1), (3, 2, 2), (4, 1, 1), (7, 0, 1)])
+def test_sampled_lookup_ragged_batches(capi, world, s, g, strategy):
+    """`-o | seedextend -s S` lets the lookup kernel probe every min(S,4)-th position first and the rest only for
+    frames with a hit (pipeline.cu: lookup_sampled_kernel).  Its warp batches mix reads of every length here:
+    empty, shorter than one k-mer, 27..33 nt, 100..320 nt with hits on either strand, reads longer than a
+    batch (plain path) -- all against the oracle's text pipeline."""
+    rng = random.Random(1000 + 7 * s + g)
+    prots = world["proteins"]
+    reads = []
+    gi = 0
+    def add(seqs):
+        nonlocal gi
+        for m, sq in enumerate(seqs, 1):
+            reads.append((f"q{gi}/{m}", sq))
+        gi += 1
+    for L in (100, 126, 150, 151, 152, 153, 250, 301, 320):
+        for pair in datagen.make_reads(prots, 12, seed=500 + L + s, read_len=L, hit_frac=0.8)[::1]:
+            reads.append(pair)
+    # regroup the make_reads pairs under fresh headers, interleaved with the odd sizes
+    paired = [(reads[i][1], reads[i + 1][1]) for i in range(0, len(reads), 2)]
+    reads.clear()
+    rng.shuffle(paired)
+    long_nt = "".join(rng.choice(datagen.CODONS.get(a, ["GCT"])) for p in prots[:6] for a in p)   # > 960 nt
+    assert len(long_nt) > 1200
+    odd = ["", "A", "ACGTACGTACGTACGTACGTACGTAC", "ACG" * 9, "N" * 33, long_nt, datagen.revcomp(long_nt)[:1100],
+           long_nt[:961], long_nt[:960], long_nt[5:965], "acgt" * 40]
+    for a, b in paired:
+        add([a, b])
+        if rng.random() < 0.5:
+            k = rng.randrange(1, 4)
+            add([rng.choice(odd) for _ in range(k)])
+    oidx = olookup.DictIndex(world["index"])
+    want = dict(opipe.classify_reads(reads, oidx, world["otax"], use_seedextend=True, min_seed_size=s, max_gap_size=g,
+                                     strategy=strategy, factor=0.25, lower_bound=0.0))
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    heads = [h.split("/")[0] for h, _ in reads]
+    goff = [0] + [i for i in range(1, len(reads) + 1) if i == len(reads) or heads[i] != heads[i - 1]]
+    opts = capi.default_opts(seedextend=1, min_seed_size=s, max_gap_size=g, strategy=strategy)
+    got, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, np.array(goff, dtype=np.uint64))
+    below = 0
+    for k in range(len(goff) - 1):
+        h = heads[goff[k]]
+        if h not in want:
+            assert int(got[k]) == capi.ABSENT, h
+            continue
+        assert int(got[k]) in want[h], (h, int(got[k]), want[h])
+        below += int(got[k]) != 1
+    assert below > (20 if strategy else 2)

@@ -109,7 +109,7 @@ struct LaunchTimer {
     cudaStream_t st;
     TimedLaunch t{};
     bool on;
-    LaunchTimer(int kind, cudaStream_t s);
+    LaunchTimer(int kind, cudaStream_t s, bool enabled = true);
     void stop();
 };
 

@@ -256,10 +256,10 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
 // Lookup kernel: one warp per read, ids to global memory, frame hit masks to frame_hits.
 template <int K, class TV, bool REGION>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
-translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
+translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
                         uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits, uint64_t region_lo,
-                        uint64_t region_hi) {
+                        uint64_t region_hi, uint32_t longer_than /* 0: every read; else only reads longer than this */) {
     __shared__ uint8_t s_lut[72];
     __shared__ LookupSmem<K> s_sm[kLookupWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,6 +269,7 @@ translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_
     for (uint64_t r = r_begin + (uint64_t)blockIdx.x * kLookupWarps + warp; r < r_end; r += nwarps) {
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
+        if (longer_than && n <= longer_than) continue;  // the sampled kernel has done this read
         uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
         if (n >= 3u * K) mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi);
         if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)(!REGION || region_lo == 0 ? mask : (mask | frame_hits[r]));
@@ -279,29 +280,98 @@ translate_lookup_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_
 // With `prot2kmer2lca -o | seedextend -s S` (S >= 2) a frame record contributes ids only if it holds
 // a run of S equal non-zero ids at S CONSECUTIVE k-mer positions (seedextend.rs:137-149: same_max
 // counts consecutive list elements, and with -o the list has one element per position).  Any S
-// consecutive positions contain one whose index in the frame is a multiple of s = min(S, 4).  So a
-// first kernel probes only those positions (1/s of the lookups, lookup_sampled_kernel); a frame none
-// of whose sampled k-mers returned a non-zero taxon cannot hold a seed, its record comes out empty
-// whatever the other positions hold, and they are never looked up.  The frames with a sampled hit --
-// the one or two true reading frames of a read from the index, plus the odd stray hit -- are queued as
-// work items and a second kernel probes their remaining positions, four frames per warp round
-// (lookup_rest_kernel).  Bit-identical output, about half of the HBM line fills and a third of the
-// instructions.  Reads too long for one tile take the plain lookup_read path inside the first kernel.
+// consecutive positions contain one whose index in the frame is a multiple of s = min(S, 4).  So the
+// kernel first probes only those positions (1/s of the lookups); a frame none of whose sampled k-mers
+// returned a non-zero taxon cannot hold a seed, its record comes out empty whatever the other
+// positions hold, and they are never looked up.  The frames with a sampled hit -- the one or two true
+// reading frames of a read from the index, plus the odd stray hit -- are probed at every position in a
+// second phase of the same warp (the sampled lines are still in L2), and only these frames' ids are
+// written.  Bit-identical output, about half of the HBM line fills.
+//
+// Work layout: translate_codes_kernel first turns the nucleotides into the two residue-code arrays
+// (forward codon starting at x, reverse-strand codon whose lowest forward coordinate is x), streaming.
+// In the lookup kernel one warp takes a batch of up to kSReads consecutive reads (<= kSSpan nucleotides),
+// copies their code spans to shared memory with 16-byte loads, and every LANE walks one frame record:
+// the 9-residue key rolls from one position to the next (one shared-memory byte per residue), two
+// lookups in flight per lane.  A read longer than kSSpan takes the plain lookup_read path.
+#ifndef UMGAP_S_READS
+#define UMGAP_S_READS 16
+#endif
+#ifndef UMGAP_S_BLOCKS
+#define UMGAP_S_BLOCKS 7
+#endif
+constexpr int kSReads = UMGAP_S_READS;
+constexpr int kSSpan = 160 * kSReads;
+constexpr int kSQueue = 192;
+constexpr int kSWarps = 4;
+constexpr int kSBlocks = UMGAP_S_BLOCKS;  // CTAs per SM the launch bounds ask for
+constexpr int kSItems = 32 + 6 * kSReads;
 
-// Re-probes the queued lookups until all are answered.  Queue entry: hash | distance << 45 |
-// level << 48 | strand << 50 | tile position << 51 | unit << 58; unit u writes through outs[u] with
-// geometry ns[u] / nposs[u].
-template <int K, class TV, int UNITS>
-__device__ __forceinline__ void drain_queue(const TV& t, LookupSmem<K>& sm, uint32_t qn, uint32_t* const (&outs)[UNITS],
-                                            const uint32_t (&ns)[UNITS], const uint32_t (&nposs)[UNITS], uint32_t& hitbits,
-                                            int lane) {
+// nt -> residue codes of both strands, 16 positions per thread.  codes[x] = forward, codes[rev_off + x] =
+// reverse.  A codon that runs past total_nt holds N; codons that straddle two reads are never used.
+__global__ void __launch_bounds__(256)
+translate_codes_kernel(const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt, uint64_t total_nt,
+                       uint8_t* __restrict__ codes, uint64_t rev_off) {
+    __shared__ uint8_t s_lut[72];
+    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const uint64_t nchunks = (total_nt + 15) / 16;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t ch = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+        const uint64_t x0 = ch * 16;
+        uint32_t w[5];
+        if (x0 + 20 <= total_nt) {
+            const uint4 v = *reinterpret_cast<const uint4*>(nt + x0);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            w[4] = *reinterpret_cast<const uint32_t*>(nt + x0 + 16);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                w[i] = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint64_t x = x0 + 4 * i + b;
+                    w[i] |= (uint32_t)(x < total_nt ? nt[x] : (uint8_t)'N') << (8 * b);
+                }
+            }
+        }
+        uint32_t c[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) c[i] = nt_code((uint8_t)(w[i >> 2] >> (8 * (i & 3))));
+        uint32_t fo[4] = {0, 0, 0, 0}, ro[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t a = c[i], b = c[i + 1], d = c[i + 2];
+            const bool has_n = ((a | b | d) & 4u) != 0;
+            fo[i >> 2] |= (uint32_t)s_lut[has_n ? 64 : 16 * a + 4 * b + d] << (8 * (i & 3));
+            ro[i >> 2] |= (uint32_t)s_lut[has_n ? 64 : 16 * (d ^ 2) + 4 * (b ^ 2) + (a ^ 2)] << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4*>(codes + x0) = make_uint4(fo[0], fo[1], fo[2], fo[3]);
+        *reinterpret_cast<uint4*>(codes + rev_off + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+    }
+}
+
+struct SampledSmem {
+    uint4 f[(kSSpan + 32) / 16];  // code spans as copied in 16-byte chunks; the batch starts at byte `mis`
+    uint4 r[(kSSpan + 32) / 16];
+    uint64_t q[kSQueue];          // hash | distance << 45 | level << 48 | tag << 50
+    uint32_t roff[kSReads + 1];   // read starts relative to the batch
+    uint32_t mask[kSReads];       // frame hit masks
+    uint16_t item[kSItems];       // second phase: frame record | segment << 7
+};
+constexpr uint32_t kSRevOff = sizeof(uint4) * ((kSSpan + 32) / 16);  // byte distance from f[] to r[]
+
+// Re-probes the queued lookups until all are answered; done(tag, value) receives each answer.
+template <class TV, class Done>
+__device__ __forceinline__ void drain_queue(const TV& t, uint64_t* q, uint32_t qn, int lane, Done done) {
     const unsigned lt_mask = (1u << lane) - 1;
     __syncwarp();
     while (qn) {
         uint32_t qnext = 0;
+#pragma unroll 1
         for (uint32_t c = 0; c < qn; c += 32) {
             const uint32_t i = c + lane;
-            const uint64_t hq = i < qn ? sm.q[i] : ~0ull;
+            const uint64_t hq = i < qn ? q[i] : ~0ull;
             bool more = false;
             uint64_t next = 0;
             if (hq != ~0ull) {
@@ -313,27 +383,12 @@ __device__ __forceinline__ void drain_queue(const TV& t, LookupSmem<K>& sm, uint
                     d = 0;
                     if (++lv == num_levels(t, hh)) more = false;  // v is kNoValue here
                 }
-                if (!more) {
-                    const uint32_t u = UNITS > 1 ? (uint32_t)(hq >> 58) & 3u : 0u;
-                    uint32_t* out = outs[0];
-                    uint32_t n = ns[0], npos = nposs[0];
-#pragma unroll
-                    for (int k = 1; k < UNITS; ++k)
-                        if (u == (uint32_t)k) {
-                            out = outs[k];
-                            n = ns[k];
-                            npos = nposs[k];
-                        }
-                    const uint32_t p = (uint32_t)(hq >> 51) & 127u, rev = (uint32_t)(hq >> 50) & 1u;
-                    const uint32_t y = rev ? npos - 1 - p : p;
-                    out[rev ? n + y : y] = v;
-                    if (v != kNoValue && v != 0) hitbits |= 1u << (rev * 3 + y % 3);
-                }
+                if (!more) done((uint32_t)(hq >> 50), v);
                 next = (hq & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
             }
             __syncwarp();
             const unsigned m = __ballot_sync(0xffffffffu, more);
-            if (more) sm.q[qnext + __popc(m & lt_mask)] = next;
+            if (more) q[qnext + __popc(m & lt_mask)] = next;
             qnext += __popc(m);
             __syncwarp();
         }
@@ -341,200 +396,223 @@ __device__ __forceinline__ void drain_queue(const TV& t, LookupSmem<K>& sm, uint
     }
 }
 
-// Phase 1: one warp per read, the sampled positions of all six frames.  Writes the frame mask and
-// queues one work item (read << 3 | frame) per frame with a hit.
+// Geometry of frame record rec (= read-in-batch * 6 + frame) from the batch's read offsets: number of
+// k-mer positions cntf, shared-memory byte address a0 of the first residue of position 0 (relative to
+// the batch's first forward code), address step per position dir (+3 forward, -3 reverse; residue kk
+// of position j is at a0 + dir * (j + kk)), and the index of position 0 in the batch's ids.
+template <int K>
+__device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint32_t rec, uint32_t& a0, int& dir, uint32_t& o0) {
+    const uint32_t i = rec / 6, fr = rec % 6, sd = fr >= 3 ? 1u : 0u, f = fr - 3 * sd;
+    const uint32_t ro = sm.roff[i], n = sm.roff[i + 1] - ro;
+    if (n < 3u * K) return 0;
+    const uint32_t npos = n - 3u * K + 1;
+    dir = sd ? -3 : 3;
+    a0 = sd ? kSRevOff + ro + (npos - 1 - f) + 3u * (K - 1) : ro + f;
+    o0 = 2 * ro + sd * n + f;
+    return (npos - f + 2) / 3;  // positions y = f + 3j < npos
+}
+
 template <int K, class TV, int STRIDE>
-__global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
-lookup_sampled_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
-                      const uint64_t* __restrict__ read_off, uint64_t nreads, uint32_t* __restrict__ ids,
-                      uint8_t* __restrict__ frame_hits, uint32_t* __restrict__ items,
-                      unsigned long long* __restrict__ nitems) {
-    constexpr uint32_t kBlock = 3 * STRIDE;                    // sampled coordinates: y % kBlock < 3
-    constexpr uint32_t kOneTile = (kTile / kBlock) * kBlock;   // reads with npos <= this fit one tile
-    constexpr int W = LookupSmem<K>::W;
-    __shared__ uint8_t s_lut[72];
-    __shared__ LookupSmem<K> s_sm[kLookupWarps];
+__global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
+lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
+                      uint32_t nreads, uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits) {
+    __shared__ SampledSmem s_sm[kSWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
-    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
-    __syncthreads();
-    LookupSmem<K>& sm = s_sm[warp];
-    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
-    for (uint64_t r = (uint64_t)blockIdx.x * kLookupWarps + warp; r < nreads; r += nwarps) {
-        const uint64_t off = read_off[r];
-        const uint32_t n = (uint32_t)(read_off[r + 1] - off);
-        uint32_t mask = 0;
-        if (n >= 3u * K) {
-            const uint32_t npos = n - 3u * K + 1;
-            if (npos > kOneTile) {  // long read: every position, no work items
-                mask = lookup_read<K, TV, false>(t, s_lut, sm, nt + off, n, ids + 2 * off, lane, 0, 0);
-            } else {
-                uint32_t* out = ids + 2 * off;
-                for (int i = lane; i < W + 2; i += 32) sm.nt[i] = (uint32_t)i < n ? (uint8_t)nt_code(nt[off + i]) : (uint8_t)4;
-                __syncwarp();
-                for (int i = lane; i < W; i += 32) {
-                    const uint32_t a = sm.nt[i], b = sm.nt[i + 1], c = sm.nt[i + 2];
-                    const bool has_n = ((a | b | c) & 4u) != 0;
-                    sm.f[i] = s_lut[has_n ? 64 : 16 * a + 4 * b + c];
-                    sm.r[i] = s_lut[has_n ? 64 : 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2)];
+    SampledSmem& sm = s_sm[warp];
+    const uint32_t nunits = (nreads + kSReads - 1) / kSReads;
+    const uint32_t nwarps = gridDim.x * kSWarps;
+#pragma unroll 1
+    for (uint32_t unit = blockIdx.x * kSWarps + warp; unit < nunits; unit += nwarps) {
+        uint32_t cur = unit * kSReads;
+        const uint32_t end = min(cur + (uint32_t)kSReads, nreads);
+#pragma unroll 1
+        while (cur < end) {
+            // ---- batch geometry: as many of the unit's remaining reads as fit kSSpan nucleotides
+            const uint32_t left = end - cur;
+            const uint64_t my_off = read_off[cur + min((uint32_t)lane, left)];
+            const uint64_t off0 = __shfl_sync(0xffffffffu, my_off, 0);
+            const unsigned fits = __ballot_sync(0xffffffffu, lane >= 1 && (uint32_t)lane <= left && my_off - off0 <= (uint64_t)kSSpan);
+            const uint32_t nb = (uint32_t)__popc(fits);
+            if (nb == 0) {  // a single read longer than the batch span: left to the plain kernel (launched next)
+                cur += 1;
+                continue;
+            }
+            const uint32_t rel = (uint32_t)(my_off - off0);
+            const uint32_t span = __shfl_sync(0xffffffffu, rel, nb);
+            if ((uint32_t)lane <= nb) sm.roff[lane] = rel;
+            if ((uint32_t)lane < nb) sm.mask[lane] = 0;
+            // ---- stage both code spans, 16 bytes per lane and load
+            const uint32_t mis = (uint32_t)((uintptr_t)(codes + off0) & 15u);
+            {
+                const uint4* gf = reinterpret_cast<const uint4*>(codes + off0 - mis);
+                const uint4* gr = reinterpret_cast<const uint4*>(codes + rev_off + off0 - mis);
+                const uint32_t nch = (mis + span + 15) / 16;
+                for (uint32_t c = lane; c < nch; c += 32) {
+                    sm.f[c] = __ldg(gf + c);
+                    sm.r[c] = __ldg(gr + c);
                 }
-                __syncwarp();
-                // candidates of one strand: e = 0..cnt-1 -> y = kBlock * (e / 3) + e % 3 (< npos); both strands
-                // are enumerated back to back, three per lane and round
-                const uint32_t cnt = 3 * ((npos - 1) / kBlock + 1);
-                uint32_t qn = 0, hitbits = 0;
-                for (uint32_t e0 = 0; e0 < 2 * cnt; e0 += 96) {
-                    uint64_t h[3];
-                    ulonglong4 sec[3];
-                    uint32_t ys[3];
-                    bool valid[3], act[3];
+            }
+            __syncwarp();
+            const uint8_t* cb = reinterpret_cast<const uint8_t*>(sm.f) + mis;
+            uint32_t* const out0 = ids + 2 * off0;
+            uint32_t qn = 0;
+            // ---- phase 1: every lane walks the sampled positions (j = 0, STRIDE, ...) of one frame record
+            auto done1 = [&](uint32_t tag, uint32_t v) {
+                if (v != kNoValue && v != 0) atomicOr(&sm.mask[tag >> 3], 1u << (tag & 7u));
+            };
+#pragma unroll 1
+            for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
+                const uint32_t rec = rec0 + lane;
+                uint32_t a = 0, o0 = 0, cs = 0;
+                int dir = 3;
+                if (rec < 6 * nb) cs = (record_geometry<K>(sm, rec, a, dir, o0) + STRIDE - 1) / STRIDE;
+                const uint32_t tag = ((rec / 6) << 3) | (rec % 6);
+                uint64_t key = 0;
+                uint32_t bad = 0;
+                if (cs) {
 #pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t e = e0 + lane + 32 * u;
-                        const uint32_t sd = e >= cnt ? 1u : 0u, ee = e - sd * cnt;
-                        const uint32_t y = kBlock * (ee / 3) + ee % 3;
-                        act[u] = e < 2 * cnt && y < npos;
-                        ys[u] = y | (sd << 31);
-                        const uint32_t pl = act[u] ? (sd ? npos - 1 - y : y) : 0u;
-                        const uint8_t* codes = sd ? sm.r : sm.f;
-                        uint64_t key = 0;
-                        uint32_t bad = 0;
+                    for (int kk = 0; kk < K; ++kk) {
+                        const uint32_t c = cb[a + dir * kk];
+                        key = (key << 5) | (c & 31u);
+                        bad = (bad << 1) | (c >> 7);
+                    }
+                }
+                const uint32_t max_cs = __reduce_max_sync(0xffffffffu, cs);
+#pragma unroll 1
+                for (uint32_t s0 = 0; s0 < max_cs; s0 += 2) {
+                    if (qn + 64 > (uint32_t)kSQueue) {
+                        drain_queue(t, sm.q, qn, lane, done1);
+                        qn = 0;
+                    }
+                    uint64_t h[2];
+                    ulonglong4 sec[2];
+                    bool valid[2];
 #pragma unroll
-                        for (int i = 0; i < K; ++i) {
-                            const uint32_t c = codes[pl + 3 * (sd ? K - 1 - i : i)];
-                            bad |= c;
-                            key = (key << 5) | (c & 31u);
-                        }
+                    for (int u = 0; u < 2; ++u) {
                         h[u] = mix45(key);
-                        valid[u] = act[u] && !(bad & 0x80u);
+                        valid[u] = s0 + u < cs && bad == 0;
+                        if (s0 + u + 1 < cs) {  // roll on to the next sampled position
+#pragma unroll
+                            for (int m = 0; m < STRIDE; ++m) {
+                                const uint32_t c = cb[a + dir * (K + m)];
+                                key = ((key << 5) | (c & 31u)) & kKeyMask;
+                                bad = ((bad << 1) | (c >> 7)) & ((1u << K) - 1);
+                            }
+                            a += dir * STRIDE;
+                        }
                     }
 #pragma unroll
-                    for (int u = 0; u < 3; ++u)
+                    for (int u = 0; u < 2; ++u)
                         if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
 #pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const uint32_t sd = ys[u] >> 31, y = ys[u] & 0x7FFFFFFFu;
+                    for (int u = 0; u < 2; ++u) {
                         bool more = false;
-                        uint32_t v = kNoValue;
-                        if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-                        if (act[u] && !more) {
-                            out[sd ? n + y : y] = v;
-                            if (v != kNoValue && v != 0) hitbits |= 1u << (sd * 3 + y % 3);
+                        if (valid[u]) {
+                            const uint32_t v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                            if (!more) done1(tag, v);
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, more);
-                        if (more)
-                            sm.q[qn + __popc(m & lt_mask)] =
-                                h[u] | (1ull << 45) | ((uint64_t)sd << 50) | ((uint64_t)(sd ? npos - 1 - y : y) << 51);
+                        if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)tag << 50);
                         qn += __popc(m);
                     }
                 }
-                uint32_t* const outs[1] = {out};
-                const uint32_t ns[1] = {n}, nposs[1] = {npos};
-                drain_queue<K, TV, 1>(t, sm, qn, outs, ns, nposs, hitbits, lane);
-                mask = __reduce_or_sync(0xffffffffu, hitbits);
-                if (mask && lane == 0) {  // one work item per live frame
-                    const unsigned long long at = atomicAdd(nitems, (unsigned long long)__popc(mask));
-                    uint32_t k = 0;
-                    for (uint32_t fr = 0; fr < 6; ++fr)
-                        if (mask >> fr & 1) items[at + k++] = (uint32_t)(r << 3) | fr;
+            }
+            drain_queue(t, sm.q, qn, lane, done1);
+            qn = 0;
+            __syncwarp();
+            if ((uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
+            // ---- phase 2: every position of the frames with a sampled hit, in segments of `seg` positions per lane
+            uint32_t total = 0;
+#pragma unroll 1
+            for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
+                const uint32_t rec = rec0 + lane;
+                uint32_t a, o0, cntf = 0;
+                int dir;
+                if (rec < 6 * nb && (sm.mask[rec / 6] >> (rec % 6) & 1u)) cntf = record_geometry<K>(sm, rec, a, dir, o0);
+                total += __reduce_add_sync(0xffffffffu, cntf);
+            }
+            if (total) {
+                const uint32_t seg = max(4u, (total + 27) / 28);
+                uint32_t nitems = 0;
+#pragma unroll 1
+                for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
+                    const uint32_t rec = rec0 + lane;
+                    uint32_t a, o0, cntf = 0;
+                    int dir;
+                    if (rec < 6 * nb && (sm.mask[rec / 6] >> (rec % 6) & 1u)) cntf = record_geometry<K>(sm, rec, a, dir, o0);
+                    const uint32_t nseg = (cntf + seg - 1) / seg;
+                    const uint32_t incl = warp_incl_scan(nseg, lane);
+                    for (uint32_t g = 0; g < nseg; ++g) sm.item[nitems + incl - nseg + g] = (uint16_t)(rec | (g << 7));
+                    nitems += __shfl_sync(0xffffffffu, incl, 31);
                 }
-            }
-        }
-        if (lane == 0) frame_hits[r] = (uint8_t)mask;
-        __syncwarp();
-    }
-}
-
-// Phase 2: the non-sampled positions of the live frames, four frames (of any four reads) per warp round,
-// one position per lane and frame.
-template <int K, class TV, int STRIDE>
-__global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
-lookup_rest_kernel(const __grid_constant__ TV t, CodonLut lut, const uint8_t* __restrict__ nt,
-                   const uint64_t* __restrict__ read_off, uint32_t* __restrict__ ids, const uint32_t* __restrict__ items,
-                   const unsigned long long* __restrict__ nitems_dev) {
-    constexpr int W = LookupSmem<K>::W;
-    __shared__ uint8_t s_lut[72];
-    __shared__ LookupSmem<K> s_sm[kLookupWarps];           // only the queue is used
-    __shared__ uint8_t s_codes[kLookupWarps][4][W + 8];     // codon-start residues of each unit's strand
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1;
-    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
-    __syncthreads();
-    LookupSmem<K>& sm = s_sm[warp];
-    const uint64_t nitems = *nitems_dev;
-    const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
-    for (uint64_t base = ((uint64_t)blockIdx.x * kLookupWarps + warp) * 4; base < nitems; base += nwarps * 4) {
-        uint32_t* outs[4];
-        uint32_t ns[4], nposs[4], frs[4];
-        bool have[4];
+                __syncwarp();
+                auto done2 = [&](uint32_t o, uint32_t v) { out0[o] = v; };
+#pragma unroll 1
+                for (uint32_t it0 = 0; it0 < nitems; it0 += 32) {
+                    uint32_t a = 0, o = 0, cnt = 0;
+                    int dir = 3;
+                    if (it0 + lane < nitems) {
+                        const uint32_t item = sm.item[it0 + lane];
+                        uint32_t a0, o0;
+                        const uint32_t cntf = record_geometry<K>(sm, item & 127u, a0, dir, o0);
+                        const uint32_t j0 = (item >> 7) * seg;
+                        cnt = min(seg, cntf - j0);
+                        a = a0 + dir * j0;
+                        o = o0 + 3 * j0;
+                    }
+                    uint64_t key = 0;
+                    uint32_t bad = 0;
+                    if (cnt) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            have[u] = base + u < nitems;
-            const uint32_t item = have[u] ? items[base + u] : 0u;
-            const uint64_t r = item >> 3;
-            frs[u] = item & 7u;
-            const uint64_t off = read_off[r];
-            ns[u] = have[u] ? (uint32_t)(read_off[r + 1] - off) : 3u * K;
-            nposs[u] = ns[u] - 3u * K + 1;
-            outs[u] = ids + 2 * off;
-            // stage the strand of this frame: residue of every codon start of the read
-            const bool rev = frs[u] >= 3;
-            const uint8_t* src = nt + off;
-            for (int i = lane; i < W; i += 32) {
-                uint32_t a = 4, b = 4, c = 4;
-                if (have[u] && (uint32_t)i + 2 < ns[u]) {
-                    a = nt_code(src[i]);
-                    b = nt_code(src[i + 1]);
-                    c = nt_code(src[i + 2]);
+                        for (int kk = 0; kk < K; ++kk) {
+                            const uint32_t c = cb[a + dir * kk];
+                            key = (key << 5) | (c & 31u);
+                            bad = (bad << 1) | (c >> 7);
+                        }
+                    }
+                    const uint32_t max_cnt = __reduce_max_sync(0xffffffffu, cnt);
+#pragma unroll 1
+                    for (uint32_t s0 = 0; s0 < max_cnt; s0 += 2) {
+                        if (qn + 64 > (uint32_t)kSQueue) {
+                            drain_queue(t, sm.q, qn, lane, done2);
+                            qn = 0;
+                        }
+                        uint64_t h[2];
+                        ulonglong4 sec[2];
+                        bool valid[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            h[u] = mix45(key);
+                            valid[u] = s0 + u < cnt && bad == 0;
+                            if (s0 + u + 1 < cnt) {
+                                const uint32_t c = cb[a + dir * K];
+                                key = ((key << 5) | (c & 31u)) & kKeyMask;
+                                bad = ((bad << 1) | (c >> 7)) & ((1u << K) - 1);
+                                a += dir;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            bool more = false;
+                            uint32_t v = kNoValue;
+                            if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                            const uint32_t oi = o + 3 * (s0 + u);
+                            if (s0 + u < cnt && !more) out0[oi] = v;
+                            const unsigned m = __ballot_sync(0xffffffffu, more);
+                            if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)oi << 50);
+                            qn += __popc(m);
+                        }
+                    }
                 }
-                const bool has_n = ((a | b | c) & 4u) != 0;
-                s_codes[warp][u][i] = s_lut[has_n ? 64 : rev ? 16 * (c ^ 2) + 4 * (b ^ 2) + (a ^ 2) : 16 * a + 4 * b + c];
+                drain_queue(t, sm.q, qn, lane, done2);
             }
+            __syncwarp();
+            cur += nb;
         }
-        __syncwarp();
-        uint64_t h[4];
-        ulonglong4 sec[4];
-        uint32_t ys[4];
-        bool valid[4], act[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            // lane -> the lane-th non-sampled position of the frame: j = STRIDE * (lane / (STRIDE-1)) + 1 + lane % (STRIDE-1)
-            const uint32_t rev = frs[u] >= 3 ? 1u : 0u, f = frs[u] % 3;
-            const uint32_t j = STRIDE * ((uint32_t)lane / (STRIDE - 1)) + 1 + (uint32_t)lane % (STRIDE - 1);
-            const uint32_t y = 3 * j + f;
-            act[u] = have[u] && y < nposs[u];
-            ys[u] = y;
-            const uint32_t pl = act[u] ? (rev ? nposs[u] - 1 - y : y) : 0u;
-            uint64_t key = 0;
-            uint32_t bad = 0;
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                const uint32_t c = s_codes[warp][u][pl + 3 * (rev ? K - 1 - i : i)];
-                bad |= c;
-                key = (key << 5) | (c & 31u);
-            }
-            h[u] = mix45(key);
-            valid[u] = act[u] && !(bad & 0x80u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
-        uint32_t qn = 0, hitbits = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t rev = frs[u] >= 3 ? 1u : 0u, y = ys[u];
-            bool more = false;
-            uint32_t v = kNoValue;
-            if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-            if (act[u] && !more) outs[u][rev ? ns[u] + y : y] = v;
-            const unsigned m = __ballot_sync(0xffffffffu, more);
-            if (more)
-                sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)rev << 50) |
-                                                 ((uint64_t)(rev ? nposs[u] - 1 - y : y) << 51) | ((uint64_t)u << 58);
-            qn += __popc(m);
-        }
-        drain_queue<K, TV, 4>(t, sm, qn, outs, ns, nposs, hitbits, lane);
-        __syncwarp();
     }
 }
 
@@ -786,8 +864,18 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                 if (lane == 0) s_cnt[warp][sl] = 0;
                 __syncwarp();
                 bool any = false;
-                for (uint64_t rec = lane; rec < nrec; rec += 32)
+                for (uint64_t rec = lane; rec < nrec; rec += 32) {
+                    if (frame_hits) {  // a frame without hits contributes nothing (and, after sampled lookups, has no ids)
+                        const uint64_t r = r0 + rec / 6;
+                        const uint32_t fr = (uint32_t)(rec % 6), f = fr % 3;
+                        if (!(frame_hits[r] >> fr & 1)) {
+                            const uint32_t n = (uint32_t)(read_off[r + 1] - read_off[r]);
+                            any |= n >= f && (n - f) / 3 >= (uint32_t)cp.k;
+                            continue;
+                        }
+                    }
                     any |= seedextend_record(cp, ids, read_off, r0, (uint32_t)rec, A, C, 0xFFFFFFFFu, &s_cnt[warp][sl], scratch);
+                }
                 if (__any_sync(0xffffffffu, any)) present |= 1u << sl;
                 __threadfence_block();
                 __syncwarp();
@@ -823,7 +911,7 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_ITEMS = 16, WS_NITEMS = 17 };  // x3 buffers
+enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 16 };  // x3 buffers
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -863,7 +951,7 @@ static cudaEvent_t take_event() {
     UMGAP_CUDA(cudaEventCreate(&e));
     return e;
 }
-LaunchTimer::LaunchTimer(int kind, cudaStream_t s) : st(s), on(g_timing) {
+LaunchTimer::LaunchTimer(int kind, cudaStream_t s, bool enabled) : st(s), on(g_timing && enabled) {
     if (!on) return;
     t.kind = kind;
     t.a = take_event();
@@ -880,7 +968,8 @@ void LaunchTimer::stop() {
 // Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
                                     const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
-                                    uint64_t r_end, uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st) {
+                                    uint64_t r_end, uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st,
+                                    uint32_t longer_than = 0, bool timed = true) {
     if (r_end <= r_begin) return;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
@@ -896,19 +985,19 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     const int nregions = idx->nshards > 1 ? 1 : (int)std::max<uint64_t>(1, ceil_div(table_bytes, region_bytes));
     for (int reg = 0; reg < nregions; ++reg) {
         const uint64_t lo = (1ull << 32) * reg / nregions, hi = (1ull << 32) * (reg + 1) / nregions;
-        LaunchTimer timer(0, st);
+        LaunchTimer timer(0, st, timed);
         switch (idx->k) {
 #define UMGAP_CASE(KK)                                                                                       \
     case KK:                                                                                                 \
         if (idx->nshards > 1)                                                                                \
             translate_lookup_kernel<KK, ShardedView, false><<<blocks, kLookupWarps * 32, 0, st>>>(            \
-                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);   \
+                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);   \
         else if (nregions > 1)                                                                               \
             translate_lookup_kernel<KK, TableView, true><<<blocks, kLookupWarps * 32, 0, st>>>(               \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);    \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);    \
         else                                                                                                 \
             translate_lookup_kernel<KK, TableView, false><<<blocks, kLookupWarps * 32, 0, st>>>(              \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi);    \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);    \
         break;
             UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
             UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
@@ -940,53 +1029,52 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
 // (Running the classify kernel of one slice concurrently with the lookup kernel of the next, on two
 // streams with priorities, was measured and gives nothing: both kernels want the same registers
 // and issue slots -- profiles/README.md.)
-// Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
-// the frames flagged in frame_hits_dev have complete ids afterwards, which is all the classify kernel reads.
 template <int STRIDE>
-static void launch_sampled(const umgap_index* idx, const CodonLut& lut, const uint8_t* nt_dev, const uint64_t* read_off_dev,
-                           uint64_t nreads, uint32_t* ids_dev, uint8_t* frame_hits_dev, uint32_t* items,
-                           unsigned long long* nitems, cudaStream_t st) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kLookupWarps), 148ull * 32);
-    LaunchTimer timer(0, st);
-    lookup_sampled_kernel<9, TableView, STRIDE><<<blocks, kLookupWarps * 32, 0, st>>>(idx->view(), lut, nt_dev, read_off_dev, nreads,
-                                                                                     ids_dev, frame_hits_dev, items, nitems);
-    UMGAP_CUDA(cudaGetLastError());
-    // the number of work items is only known on the device: size the grid for the typical 1-2 live frames per read
-    const unsigned blocks2 = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads * 3 / 2, 4), kLookupWarps) + 1, 148ull * 32);
-    lookup_rest_kernel<9, TableView, STRIDE><<<blocks2, kLookupWarps * 32, 0, st>>>(idx->view(), lut, nt_dev, read_off_dev, ids_dev,
-                                                                                   items, nitems);
-    UMGAP_CUDA(cudaGetLastError());
-    timer.stop();
+static void launch_sampled(const umgap_index* idx, const uint8_t* codes, uint64_t rev_off, const uint64_t* read_off_dev, uint64_t nreads, uint32_t* ids_dev,
+                           uint8_t* frame_hits_dev, cudaStream_t st) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads, kSReads), kSWarps), 148ull * kSBlocks * 4);
+    lookup_sampled_kernel<9, TableView, STRIDE><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), codes, rev_off, read_off_dev,
+                                                                                (uint32_t)nreads, ids_dev, frame_hits_dev);
 }
 
+// Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
+// the frames flagged in frame_hits_dev have ids afterwards, which is all the classify kernel reads.
 static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
-                                            const uint64_t* read_off_dev, uint64_t nreads, uint32_t* ids_dev,
-                                            uint8_t* frame_hits_dev, cudaStream_t st) {
+                                            const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
+                                            uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st) {
     static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
-        (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 29))
+        (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 31) ||
+        ((uintptr_t)nt_dev & 15u) != 0)
         return false;
     if (!nreads) return true;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
-    uint32_t* items = (uint32_t*)idx->ws.get(WS_ITEMS, (6 * nreads + 64) * sizeof(uint32_t));
-    unsigned long long* nitems = (unsigned long long*)idx->ws.get(WS_NITEMS, 64);
-    UMGAP_CUDA(cudaMemsetAsync(nitems, 0, sizeof(unsigned long long), st));
+    const uint64_t rev_off = (total_nt + 15) / 16 * 16 + 16;
+    uint8_t* codes = (uint8_t*)idx->ws.get(WS_CODES, 2 * rev_off);
+    LaunchTimer timer(0, st);
+    const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(total_nt, 16), 256) + 1, 148ull * 16);
+    translate_codes_kernel<<<tblocks, 256, 0, st>>>(lut, nt_dev, total_nt, codes, rev_off);
+    UMGAP_CUDA(cudaGetLastError());
     switch (std::min(o->min_seed_size, 4)) {
-        case 2: launch_sampled<2>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
-        case 3: launch_sampled<3>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
-        default: launch_sampled<4>(idx, lut, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, items, nitems, st); break;
+        case 2: launch_sampled<2>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
+        case 3: launch_sampled<3>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
+        default: launch_sampled<4>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
     }
+    UMGAP_CUDA(cudaGetLastError());
+    // reads longer than a warp batch (rare): the plain kernel, which skips everything else
+    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, (uint32_t)kSSpan, false);
+    timer.stop();
     return true;
 }
 
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
-                            const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
+                            const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
                             uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st) {
     if (!ngroups) return;
-    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, ids_dev, frame_hits_dev, st))
+    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st))
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
     launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
 }
@@ -1086,7 +1174,7 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
         uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, nreads + 64);
-        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, group_off_dev, ngroups, ids, scratch, hits,
+        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, total_nt, group_off_dev, ngroups, ids, scratch, hits,
                         taxon_out_dev, err, st);
     });
 }
@@ -1158,7 +1246,7 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                 UMGAP_CUDA(cudaGetLastError());
                 if (prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
                 uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
-                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, d_goff, cnt_g, ids, scratch, hits, d_out, err, s);
+                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, cnt_nt, d_goff, cnt_g, ids, scratch, hits, d_out, err, s);
                 UMGAP_CUDA(cudaEventRecord(done[buf], s));
                 UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
                 prev = buf;
