@@ -284,28 +284,29 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
 // kernel first probes only those positions (1/s of the lookups); a frame none of whose sampled k-mers
 // returned a non-zero taxon cannot hold a seed, its record comes out empty whatever the other
 // positions hold, and they are never looked up.  The frames with a sampled hit -- the one or two true
-// reading frames of a read from the index, plus the odd stray hit -- are probed at every position in a
-// second phase of the same warp (the sampled lines are still in L2), and only these frames' ids are
-// written.  Bit-identical output, about half of the HBM line fills.
+// reading frames of a read from the index, plus the odd stray hit -- get their remaining positions
+// probed in a second phase of the same warp, and only these frames' ids are written.  Bit-identical
+// output, about 0.4 of the HBM line fills.
 //
 // Work layout: translate_codes_kernel first turns the nucleotides into the two residue-code arrays
 // (forward codon starting at x, reverse-strand codon whose lowest forward coordinate is x), streaming.
-// In the lookup kernel one warp takes a batch of up to kSReads consecutive reads (<= kSSpan nucleotides),
-// copies their code spans to shared memory with 16-byte loads, and every LANE walks one frame record:
-// the 9-residue key rolls from one position to the next (one shared-memory byte per residue), two
-// lookups in flight per lane.  A read longer than kSSpan takes the plain lookup_read path.
-#ifndef UMGAP_S_READS
-#define UMGAP_S_READS 16
-#endif
+// In the lookup kernel one warp takes a batch of up to kSReads = 5 consecutive reads (<= kSSpan
+// nucleotides; 30 frame records), copies their code spans to shared memory with 16-byte loads, and every
+// LANE walks one frame record: the 9-residue key rolls from one position to the next (one shared-memory
+// byte per residue), two lookups in flight per lane.  The answers of a record's first kSValRows sampled
+// positions stay in shared memory for the second phase.  A read longer than kSSpan is left to the plain
+// kernel.
 #ifndef UMGAP_S_BLOCKS
 #define UMGAP_S_BLOCKS 7
 #endif
-constexpr int kSReads = UMGAP_S_READS;
+constexpr int kSReads = 5;
 constexpr int kSSpan = 160 * kSReads;
-constexpr int kSQueue = 192;
+constexpr int kSQueue = 128;
 constexpr int kSWarps = 4;
 constexpr int kSBlocks = UMGAP_S_BLOCKS;  // CTAs per SM the launch bounds ask for
 constexpr int kSItems = 32 + 6 * kSReads;
+constexpr int kSValRows = 16;
+static_assert(6 * kSReads <= 32, "one lane per frame record of a batch");
 
 // nt -> residue codes of both strands, 16 positions per thread.  codes[x] = forward, codes[rev_off + x] =
 // reverse.  A codon that runs past total_nt holds N; codons that straddle two reads are never used.
@@ -357,7 +358,8 @@ struct SampledSmem {
     uint64_t q[kSQueue];          // hash | distance << 45 | level << 48 | tag << 50
     uint32_t roff[kSReads + 1];   // read starts relative to the batch
     uint32_t mask[kSReads];       // frame hit masks
-    uint16_t item[kSItems];       // second phase: frame record | segment << 7
+    uint32_t val[kSValRows][32];  // answer of sampled position s < kSValRows of the record walked by lane l: val[s][l]
+    uint16_t item[kSItems];       // second phase: frame record | segment << 5
 };
 constexpr uint32_t kSRevOff = sizeof(uint4) * ((kSSpan + 32) / 16);  // byte distance from f[] to r[]
 
@@ -457,17 +459,17 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
             const uint8_t* cb = reinterpret_cast<const uint8_t*>(sm.f) + mis;
             uint32_t* const out0 = ids + 2 * off0;
             uint32_t qn = 0;
-            // ---- phase 1: every lane walks the sampled positions (j = 0, STRIDE, ...) of one frame record
-            auto done1 = [&](uint32_t tag, uint32_t v) {
-                if (v != kNoValue && v != 0) atomicOr(&sm.mask[tag >> 3], 1u << (tag & 7u));
+            // ---- phase 1: lane `rec` walks the sampled positions (j = 0, STRIDE, ...) of frame record `rec`
+            const uint32_t rec = lane;
+            auto done1 = [&](uint32_t tag, uint32_t v) {  // tag = record | sampled index << 5
+                const uint32_t rc = tag & 31u, sx = tag >> 5;
+                if (sx < (uint32_t)kSValRows) sm.val[sx][rc] = v;
+                if (v != kNoValue && v != 0) atomicOr(&sm.mask[rc / 6], 1u << (rc % 6));
             };
-#pragma unroll 1
-            for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
-                const uint32_t rec = rec0 + lane;
+            {
                 uint32_t a = 0, o0 = 0, cs = 0;
                 int dir = 3;
                 if (rec < 6 * nb) cs = (record_geometry<K>(sm, rec, a, dir, o0) + STRIDE - 1) / STRIDE;
-                const uint32_t tag = ((rec / 6) << 3) | (rec % 6);
                 uint64_t key = 0;
                 uint32_t bad = 0;
                 if (cs) {
@@ -492,6 +494,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
                     for (int u = 0; u < 2; ++u) {
                         h[u] = mix45(key);
                         valid[u] = s0 + u < cs && bad == 0;
+                        if (s0 + u < cs && bad != 0 && s0 + u < (uint32_t)kSValRows) sm.val[s0 + u][lane] = kNoValue;
                         if (s0 + u + 1 < cs) {  // roll on to the next sampled position
 #pragma unroll
                             for (int m = 0; m < STRIDE; ++m) {
@@ -507,6 +510,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
                         if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
+                        const uint32_t tag = rec | ((s0 + u) << 5);
                         bool more = false;
                         if (valid[u]) {
                             const uint32_t v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
@@ -522,44 +526,36 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
             qn = 0;
             __syncwarp();
             if ((uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
-            // ---- phase 2: every position of the frames with a sampled hit, in segments of `seg` positions per lane
-            uint32_t total = 0;
-#pragma unroll 1
-            for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
-                const uint32_t rec = rec0 + lane;
-                uint32_t a, o0, cntf = 0;
+            // ---- phase 2: every position of the frames with a sampled hit, in segments of `seg` positions per lane;
+            //      sampled positions whose answer is still in val[] are copied, the others probed
+            uint32_t cntf = 0;
+            {
+                uint32_t a, o0;
                 int dir;
                 if (rec < 6 * nb && (sm.mask[rec / 6] >> (rec % 6) & 1u)) cntf = record_geometry<K>(sm, rec, a, dir, o0);
-                total += __reduce_add_sync(0xffffffffu, cntf);
             }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, cntf);
             if (total) {
                 const uint32_t seg = max(4u, (total + 27) / 28);
-                uint32_t nitems = 0;
-#pragma unroll 1
-                for (uint32_t rec0 = 0; rec0 < 6 * nb; rec0 += 32) {
-                    const uint32_t rec = rec0 + lane;
-                    uint32_t a, o0, cntf = 0;
-                    int dir;
-                    if (rec < 6 * nb && (sm.mask[rec / 6] >> (rec % 6) & 1u)) cntf = record_geometry<K>(sm, rec, a, dir, o0);
-                    const uint32_t nseg = (cntf + seg - 1) / seg;
-                    const uint32_t incl = warp_incl_scan(nseg, lane);
-                    for (uint32_t g = 0; g < nseg; ++g) sm.item[nitems + incl - nseg + g] = (uint16_t)(rec | (g << 7));
-                    nitems += __shfl_sync(0xffffffffu, incl, 31);
-                }
+                const uint32_t nseg = (cntf + seg - 1) / seg;
+                const uint32_t incl = warp_incl_scan(nseg, lane);
+                for (uint32_t g = 0; g < nseg; ++g) sm.item[incl - nseg + g] = (uint16_t)(rec | (g << 5));
+                const uint32_t nitems = __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 auto done2 = [&](uint32_t o, uint32_t v) { out0[o] = v; };
 #pragma unroll 1
                 for (uint32_t it0 = 0; it0 < nitems; it0 += 32) {
-                    uint32_t a = 0, o = 0, cnt = 0;
+                    uint32_t a = 0, o = 0, cnt = 0, j = 0, rc = 0;
                     int dir = 3;
                     if (it0 + lane < nitems) {
                         const uint32_t item = sm.item[it0 + lane];
                         uint32_t a0, o0;
-                        const uint32_t cntf = record_geometry<K>(sm, item & 127u, a0, dir, o0);
-                        const uint32_t j0 = (item >> 7) * seg;
-                        cnt = min(seg, cntf - j0);
-                        a = a0 + dir * j0;
-                        o = o0 + 3 * j0;
+                        rc = item & 31u;
+                        const uint32_t n_pos = record_geometry<K>(sm, rc, a0, dir, o0);
+                        j = (item >> 5) * seg;
+                        cnt = min(seg, n_pos - j);
+                        a = a0 + dir * j;
+                        o = o0 + 3 * j;
                     }
                     uint64_t key = 0;
                     uint32_t bad = 0;
@@ -580,11 +576,16 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
                         }
                         uint64_t h[2];
                         ulonglong4 sec[2];
+                        uint32_t v[2];
                         bool valid[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
+                            const bool act = s0 + u < cnt;
+                            const uint32_t jj = j + s0 + u, sx = jj / STRIDE;
+                            const bool cached = act && jj % STRIDE == 0 && sx < (uint32_t)kSValRows;
+                            v[u] = cached ? sm.val[sx][rc] : kNoValue;
                             h[u] = mix45(key);
-                            valid[u] = s0 + u < cnt && bad == 0;
+                            valid[u] = act && !cached && bad == 0;
                             if (s0 + u + 1 < cnt) {
                                 const uint32_t c = cb[a + dir * K];
                                 key = ((key << 5) | (c & 31u)) & kKeyMask;
@@ -598,10 +599,9 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             bool more = false;
-                            uint32_t v = kNoValue;
-                            if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                            if (valid[u]) v[u] = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
                             const uint32_t oi = o + 3 * (s0 + u);
-                            if (s0 + u < cnt && !more) out0[oi] = v;
+                            if (s0 + u < cnt && !more) out0[oi] = v[u];
                             const unsigned m = __ballot_sync(0xffffffffu, more);
                             if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)oi << 50);
                             qn += __popc(m);
