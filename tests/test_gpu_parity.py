@@ -285,6 +285,13 @@ def test_classify_reads_matches_oracle_pipeline(capi, world, strategy, factor, l
     reads += [("L0/1", long_nt), ("L0/2", datagen.revcomp(long_nt))]
     # six long reads joined into one group: more kept ids than the shared-memory list holds
     reads += [(f"M0/{i}", long_nt if i % 2 else datagen.revcomp(long_nt)) for i in range(1, 7)]
+    # groups with 39 / 68 / 184 distinct kept taxa: more than one per lane, more than the per-group
+    # shared-memory table takes (list path through global scratch)
+    def nt_of(p):
+        return "".join(datagen.CODONS.get(a, ["GCT"])[0] for a in p)
+    for name, cnt in (("D2", 2), ("D4", 4), ("D12", 12)):
+        reads += [(f"{name}/{i}", nt_of(world["proteins"][10 + i]) if i % 2 else datagen.revcomp(nt_of(world["proteins"][10 + i])))
+                  for i in range(cnt)]
     oidx = olookup.DictIndex(world["index"])
     want = opipe.classify_reads(reads, oidx, world["otax"], use_seedextend=bool(use_se), min_seed_size=s,
                                 max_gap_size=g, strategy=strategy, factor=factor, lower_bound=lb)
@@ -309,7 +316,7 @@ def test_classify_reads_matches_oracle_pipeline(capi, world, strategy, factor, l
         assert int(got[gi]) in want[h], (h, int(got[gi]), want[h])
         non_root += int(got[gi]) != 1
     assert non_root > (40 if strategy else 3)  # LCA* lands on the root whenever a read carries noise
-    assert "e0" not in want and "s0" not in want and "s1" in want and "L0" in want and "M0" in want
+    assert "e0" not in want and "s0" not in want and "s1" in want and "L0" in want and "M0" in want and "D12" in want
 
 
 def test_classify_dev_entry_matches_host_entry(capi, world):

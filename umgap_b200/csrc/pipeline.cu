@@ -627,47 +627,63 @@ struct ClassifyParams {
 
 constexpr int kAggWarps = 4;
 constexpr int kAggSlots = 8;        // groups whose live frame records are pooled by one warp
-constexpr uint32_t kAggCap = 96;    // run-length entries per group held in shared memory
+constexpr uint32_t kAggTable = 64;  // slots of a group's (taxon -> occurrences) table in shared memory
+constexpr uint32_t kAggFull = 48;   // distinct taxa beyond which a group is redone through global scratch
 
 struct DevError {  // first error raised by a kernel
     unsigned int flag;
     unsigned int taxon;
 };
 
-// seedextend of one frame record (rec = read-in-group * 6 + frame) of group [r0, r1); the kept
-// ids leave as run-length pairs (id, occurrences) -- zeros are dropped (taxa2agg.rs:169) and the
-// aggregators only need the multiset.  Returns false when the record does not exist (:172).
+// Where seedextend's kept ids go.  The aggregators only need the multiset of non-zero ids
+// (taxa2agg.rs:169 drops zeros, agg/mod.rs:27-36 counts), so a group's kept ids are counted on the fly:
+// TableSink -- open-addressing table of kAggTable (taxon, occurrences) slots in shared memory, filled with
+//              atomics by the lanes that run the group's frame records; `distinct` counts the slots taken.
+// ListSink  -- append-only (taxon, occurrences) list of unbounded size in global scratch (huge groups).
+struct TableSink {
+    uint32_t* keys;      // 0 = free
+    uint32_t* cnts;
+    uint32_t* distinct;
+    __device__ __forceinline__ void add(uint32_t id, uint32_t len) const {
+        uint32_t slot = (id * 0x9E3779B1u) >> 26;
+        for (uint32_t probe = 0; probe < kAggTable; ++probe) {
+            const uint32_t prev = atomicCAS(&keys[slot], 0u, id);
+            if (prev == 0u) atomicAdd(distinct, 1u);
+            if (prev == 0u || prev == id) {
+                atomicAdd(&cnts[slot], len);
+                return;
+            }
+            slot = (slot + 1) & (kAggTable - 1);
+        }
+        atomicAdd(distinct, kAggTable);  // table full: the group takes the list path
+    }
+};
+struct ListSink {
+    uint32_t* A;
+    uint32_t* C;
+    uint32_t* counter;
+    __device__ __forceinline__ void add(uint32_t id, uint32_t len) const {
+        const uint32_t at = atomicAdd(counter, 1u);
+        A[at] = id;
+        C[at] = len;
+    }
+};
+
+// seedextend of one frame record (fr = 0,1,2 forward; 3,4,5 reverse) of a read with n nucleotides whose
+// ids start at read_ids; the kept ids leave as run-length pairs through sink.add(id, occurrences).
+// Returns false when the record does not exist (prot2kmer2lca.rs:172).  read_priv: the read's 4n words
+// of private scratch.
+template <class Sink>
 __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const uint32_t* read_ids, uint32_t n,
-                                                 uint32_t fr /* 0,1,2 forward; 3,4,5 reverse */, uint32_t* A,
-                                                 uint32_t* C, uint32_t cap, uint32_t* counter, uint32_t* read_priv) {
+                                                 uint32_t fr, const Sink& sink, uint32_t* read_priv) {
     const uint32_t f = fr % 3;
     const uint32_t plen = n >= f ? (n - f) / 3 : 0;  // peptide length of the frame
     if (plen < (uint32_t)cp.k) return false;
     const uint32_t cnt = plen - cp.k + 1;
     const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + f;
     // private slice of this record: pair i at words 6i, 6i+1 past 2*(strand*n + f), inside the read's 4n words
-    uint32_t* priv = read_priv ? read_priv + 2 * ((fr >= 3 ? n : 0) + f) : nullptr;
-    uint32_t run_id = 0, run_len = 0;
-    auto flush_run = [&]() {
-        if (run_len) {
-            const uint32_t at = atomicAdd(counter, 1u);
-            if (at < cap) {
-                A[at] = run_id;
-                C[at] = run_len;
-            }
-        }
-    };
-    auto push = [&](uint32_t v) {
-        if (v == 0) return;
-        if (v == run_id) {
-            ++run_len;
-        } else {
-            flush_run();
-            run_id = v;
-            run_len = 1;
-        }
-    };
-    if (cp.seedextend && cp.one_on_one && priv) {
+    uint32_t* priv = read_priv + 2 * ((fr >= 3 ? n : 0) + f);
+    if (cp.seedextend && cp.one_on_one) {
         // Single pass of the seedextend machine (seedextend.rs:101-149) that builds the run-length
         // list of the CURRENT range tentatively in the record's private slice and commits it when the
         // range is selected / rolls it back when the range is abandoned -- no second walk over the
@@ -721,16 +737,20 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
         }
         close_run();
         if (smax >= cp.min_seed) committed = k;              // :144-149 (trailing zeros carry no ids)
-        if (committed) {
-            const uint32_t to = atomicAdd(counter, committed);
-            if (to + committed <= cap && to + committed >= to)
-                for (uint32_t i = 0; i < committed; ++i) {
-                    A[to + i] = priv[6 * i];
-                    C[to + i] = priv[6 * i + 1];
-                }
-        }
+        for (uint32_t i = 0; i < committed; ++i) sink.add(priv[6 * i], priv[6 * i + 1]);
         return true;
     }
+    uint32_t run_id = 0, run_len = 0;
+    auto push = [&](uint32_t v) {
+        if (v == 0) return;
+        if (v == run_id) {
+            ++run_len;
+        } else {
+            if (run_len) sink.add(run_id, run_len);
+            run_id = v;
+            run_len = 1;
+        }
+    };
     if (cp.seedextend) {
         seedextend_stream(base, 3, cnt, cp.one_on_one != 0, cp.min_seed, cp.max_gap, push);
     } else {
@@ -739,39 +759,42 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
             if (v != kNoValue) push(v);
         }
     }
-    flush_run();
+    if (run_len) sink.add(run_id, run_len);
     return true;
 }
 
 // The same for record rec (= read-in-group * 6 + frame) of the group starting at read r0, ids in
 // global memory.
+template <class Sink>
 __device__ __forceinline__ bool seedextend_record(const ClassifyParams& cp, const uint32_t* __restrict__ ids,
                                                   const uint64_t* __restrict__ read_off, uint64_t r0, uint32_t rec,
-                                                  uint32_t* A, uint32_t* C, uint32_t cap, uint32_t* counter,
-                                                  uint32_t* scratch) {
+                                                  const Sink& sink, uint32_t* scratch) {
     // scratch holds 12 words per nucleotide: a group's slice is [12*off(r0), ...): first 4 words per
     // nucleotide of private record slices, then the four overflow lists of 2 words per nucleotide
     const uint64_t r = r0 + rec / 6;
     const uint64_t off = read_off[r], off0 = read_off[r0];
-    return seedextend_frame(cp, ids + 2 * off, (uint32_t)(read_off[r + 1] - off), rec % 6, A, C, cap, counter,
+    return seedextend_frame(cp, ids + 2 * off, (uint32_t)(read_off[r + 1] - off), rec % 6, sink,
                             scratch + 12 * off0 + 4 * (off - off0));
 }
 
 // One warp per kAggSlots groups.  Of a pair's twelve frame records only the one or two that
 // carry hits need the seedextend machine (the lookup kernel left a 6-bit mask per read), so the
 // warp first pools the live records of all its groups and runs their machines side by side, one
-// lane each, 32 at a time; every group's run-length list is then aggregated by the whole warp.
+// lane each, 32 at a time, counting the kept ids in the groups' shared-memory tables; every group's
+// distinct taxa (a dozen, typically) are then sorted in registers and aggregated by the whole warp.
 __global__ void __launch_bounds__(kAggWarps * 32)
 classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                 const uint64_t* __restrict__ read_off, const uint64_t* __restrict__ group_off,
                 uint64_t g_begin, uint64_t ngroups /* end of the group range */,
                 const uint8_t* __restrict__ frame_hits /* may be null: every record is live */,
                 uint32_t* __restrict__ scratch, uint32_t* __restrict__ taxon_out, DevError* err) {
-    __shared__ uint32_t s_a[kAggWarps][kAggSlots][kAggCap];
-    __shared__ uint32_t s_c[kAggWarps][kAggSlots][kAggCap];
-    __shared__ uint32_t s_p[kAggWarps][kAggCap + 1];
-    __shared__ uint32_t s_l[kAggWarps][kAggCap];
-    __shared__ uint32_t s_cnt[kAggWarps][kAggSlots];
+    __shared__ uint32_t s_key[kAggWarps][kAggSlots][kAggTable];
+    __shared__ uint32_t s_occ[kAggWarps][kAggSlots][kAggTable];
+    __shared__ uint32_t s_a[kAggWarps][kAggTable + 1];   // per-warp scratch of the aggregation
+    __shared__ uint32_t s_c[kAggWarps][kAggTable + 1];
+    __shared__ uint32_t s_p[kAggWarps][kAggTable + 1];
+    __shared__ uint32_t s_l[kAggWarps][kAggTable + 1];
+    __shared__ uint32_t s_cnt[kAggWarps][kAggSlots];       // distinct taxa per group (list length on the list path)
     __shared__ uint64_t s_r0[kAggWarps][kAggSlots];
     __shared__ uint32_t s_nrec[kAggWarps][kAggSlots + 1];  // exclusive prefix of the groups' record counts
     __shared__ uint32_t s_live[kAggWarps][64];             // pooled live records: slot << 24 | record
@@ -783,7 +806,7 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
         const uint64_t g_base = g_begin + unit * kAggSlots;
         const int ng = (int)((ngroups - g_base) < (uint64_t)kAggSlots ? (ngroups - g_base) : kAggSlots);
         // group geometry: lane sl < ng loads group sl; groups of more than 2^24/6 reads are clamped
-        // here and handled by the overflow path below (their records are enumerated there again)
+        // here and handled by the list path below (their records are enumerated there again)
         uint64_t my_r0 = 0, my_n = 0;
         if (lane < ng) {
             my_r0 = group_off[g_base + lane];
@@ -796,6 +819,10 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
             s_nrec[warp][lane] = incl - (lane < ng ? my_n32 : 0u);
             s_cnt[warp][lane] = 0;
         }
+        for (uint32_t i = lane; i < kAggSlots * kAggTable; i += 32) {
+            (&s_key[warp][0][0])[i] = 0;
+            (&s_occ[warp][0][0])[i] = 0;
+        }
         const uint32_t total_recs = __shfl_sync(0xffffffffu, incl, 31);
         if (lane == 0) s_nrec[warp][kAggSlots] = total_recs;
         __syncwarp();
@@ -805,8 +832,10 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
             if ((uint32_t)lane < count) {
                 const uint32_t e = s_live[warp][lane];
                 const uint32_t sl = e >> 24, rec = e & 0xFFFFFFu;
-                seedextend_record(cp, ids, read_off, s_r0[warp][sl], rec, s_a[warp][sl], s_c[warp][sl], kAggCap,
-                                  &s_cnt[warp][sl], scratch);
+                // a group that already overflowed its table is redone below: skip its remaining records
+                if (s_cnt[warp][sl] <= kAggFull)
+                    seedextend_record(cp, ids, read_off, s_r0[warp][sl], rec,
+                                      TableSink{s_key[warp][sl], s_occ[warp][sl], &s_cnt[warp][sl]}, scratch);
             }
             __syncwarp();
         };
@@ -841,25 +870,19 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
         }
         if (nlive) run_pass(nlive);
         for (int sl = 0; sl < ng; ++sl) {
-            uint32_t* A = s_a[warp][sl];
-            uint32_t* C = s_c[warp][sl];
-            uint32_t* P = s_p[warp];
-            uint32_t* L = s_l[warp];
-            uint32_t total = s_cnt[warp][sl];
             const uint64_t r0 = s_r0[warp][sl];
             const uint64_t nrec = (group_off[g_base + sl + 1] - r0) * 6;
-            if (total > kAggCap || nrec > 0xFFFFFFu) {
-                // rare: more runs than the shared-memory list holds (or a huge group) -> redo into the
-                // group's own slice of the global scratch (after the private record slices: four lists
-                // of gsize words; the number of runs is below gsize because a read yields fewer k-mers
-                // than 2x its length)
+            const uint32_t distinct = s_cnt[warp][sl];
+            uint32_t res, bad = 0;
+            if (distinct > kAggFull || nrec > 0xFFFFFFu) {
+                // rare: more distinct taxa than the table takes (or a huge group) -> redo into the group's own
+                // slice of the global scratch (after the private record slices: four lists of gsize words;
+                // the number of runs is below gsize because a read yields fewer k-mers than 2x its length)
                 const uint64_t r1 = r0 + nrec / 6;
                 const uint64_t gsize = 2 * (read_off[r1] - read_off[r0]);
                 const uint64_t gbase = 12 * read_off[r0] + 2 * gsize;
-                A = scratch + gbase;
-                C = A + gsize;
-                P = C + gsize;
-                L = P + gsize;
+                uint32_t* A = scratch + gbase;
+                uint32_t* C = A + gsize;
                 __syncwarp();
                 if (lane == 0) s_cnt[warp][sl] = 0;
                 __syncwarp();
@@ -874,24 +897,56 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
                             continue;
                         }
                     }
-                    any |= seedextend_record(cp, ids, read_off, r0, (uint32_t)rec, A, C, 0xFFFFFFFFu, &s_cnt[warp][sl], scratch);
+                    any |= seedextend_record(cp, ids, read_off, r0, (uint32_t)rec, ListSink{A, C, &s_cnt[warp][sl]}, scratch);
                 }
                 if (__any_sync(0xffffffffu, any)) present |= 1u << sl;
                 __threadfence_block();
                 __syncwarp();
-                total = s_cnt[warp][sl];
-            }
-            uint32_t res;
-            if (!(present >> sl & 1)) {
+                res = !(present >> sl & 1) ? UMGAP_ABSENT
+                                           : warp_aggregate<true>(tv, A, C, C + gsize, C + 2 * gsize, s_cnt[warp][sl], cp.agg, lane, &bad);
+            } else if (!(present >> sl & 1)) {
                 res = UMGAP_ABSENT;
             } else {
-                uint32_t bad = 0;
-                res = warp_aggregate<true>(tv, A, C, P, L, total, cp.agg, lane, &bad);
-                const uint32_t bad_any = __reduce_max_sync(0xffffffffu, bad);
-                if (res == kAggUnknown) {
-                    if (lane == 0 && atomicCAS(&err->flag, 0u, 1u) == 0u) err->taxon = bad_any;
-                    res = UMGAP_ABSENT;
+                // compact the table: slots lane and lane + 32
+                const uint32_t k0 = s_key[warp][sl][lane], k1 = s_key[warp][sl][lane + 32];
+                const unsigned m0 = __ballot_sync(0xffffffffu, k0 != 0), m1 = __ballot_sync(0xffffffffu, k1 != 0);
+                const uint32_t n0 = (uint32_t)__popc(m0), n = n0 + (uint32_t)__popc(m1);
+                if (n <= 32) {
+                    __syncwarp();
+                    if (k0) {
+                        const uint32_t at = (uint32_t)__popc(m0 & lt_mask);
+                        s_a[warp][at] = k0;
+                        s_c[warp][at] = s_occ[warp][sl][lane];
+                    }
+                    if (k1) {
+                        const uint32_t at = n0 + (uint32_t)__popc(m1 & lt_mask);
+                        s_a[warp][at] = k1;
+                        s_c[warp][at] = s_occ[warp][sl][lane + 32];
+                    }
+                    __syncwarp();
+                    const uint32_t id = (uint32_t)lane < n ? s_a[warp][lane] : 0u, c = (uint32_t)lane < n ? s_c[warp][lane] : 0u;
+                    __syncwarp();
+                    res = warp_aggregate_distinct(tv, id, c, n, s_a[warp], s_p[warp], s_l[warp], cp.agg, lane, &bad);
+                } else {
+                    __syncwarp();
+                    if (k0) {
+                        const uint32_t at = (uint32_t)__popc(m0 & lt_mask);
+                        s_a[warp][at] = k0;
+                        s_c[warp][at] = s_occ[warp][sl][lane];
+                    }
+                    if (k1) {
+                        const uint32_t at = n0 + (uint32_t)__popc(m1 & lt_mask);
+                        s_a[warp][at] = k1;
+                        s_c[warp][at] = s_occ[warp][sl][lane + 32];
+                    }
+                    __syncwarp();
+                    res = warp_aggregate<true>(tv, s_a[warp], s_c[warp], s_p[warp], s_l[warp], n, cp.agg, lane, &bad);
                 }
+            }
+            if (res == kAggUnknown) {
+                const uint32_t bad_any = __reduce_max_sync(0xffffffffu, bad);
+                if (lane == 0 && atomicCAS(&err->flag, 0u, 1u) == 0u) err->taxon = bad_any;
+                res = UMGAP_ABSENT;
             }
             if (lane == 0) taxon_out[g_base + sl] = res;
             __syncwarp();

@@ -182,6 +182,74 @@ struct AggParams {
 
 constexpr uint32_t kAggUnknown = 0xFFFFFFFDu;  // internal: record holds an id unknown to the tree
 
+// The strategies proper, on the sorted distinct kept members: A[0..m) dense indices ascending, P[0..m]
+// exclusive prefix sums of their counts (P[m] = running = total), L[j] = last[A[j]].  All lanes call.
+__device__ __forceinline__ uint32_t agg_finish(const TaxView& tv, const uint32_t* A, const uint32_t* P, const uint32_t* L,
+                                               uint32_t m, uint32_t running, const AggParams& ap, int lane) {
+    uint32_t result;
+    if (ap.strategy == UMGAP_AGG_LCA_STAR) {
+        result = lca_star_range(tv, A, L, 0, m, lane);
+    } else if (ap.strategy == UMGAP_AGG_HYBRID) {
+        uint32_t lo = 0, hi = m;
+        uint32_t base_node = lca_star_range(tv, A, L, lo, hi, lane);
+        uint32_t bval = running;
+        lo = warp_upper_bound(A, lo, hi, base_node - 1u, lane);  // first member >= base (base>=0)
+        if (base_node == 0) lo = 0;
+        for (;;) {
+            uint32_t g = lo;
+            if (g < hi && A[g] == base_node) ++g;  // the base itself is not one of its children
+            if (g >= hi) break;                    // no children: stop (tree/mix.rs:51)
+            const uint32_t child_depth = (uint32_t)__ldg(tv.depth + base_node) + 1;
+            uint32_t best = 0, best_lo = 0, best_hi = 0;
+            while (g < hi) {
+                const uint32_t c = __ldg(tv.anc + (uint64_t)A[g] * tv.stride + child_depth);
+                const uint32_t e = warp_upper_bound(A, g, hi, __ldg(tv.last + c), lane);
+                const uint32_t sub = P[e] - P[g];
+                if (sub > best) {  // first maximal child in preorder wins ties
+                    best = sub;
+                    best_lo = g;
+                    best_hi = e;
+                }
+                g = e;
+            }
+            if (__fdiv_rn((float)best, (float)bval) < ap.factor) break;  // tree/mix.rs:57
+            base_node = lca_star_range(tv, A, L, best_lo, best_hi, lane);
+            bval = best;
+            hi = best_hi;
+            lo = base_node == 0 ? best_lo : warp_upper_bound(A, best_lo, best_hi, base_node - 1u, lane);
+        }
+        result = base_node;
+    } else {  // MRTL
+        uint32_t best_w = 0, best_j = 0;
+        for (uint32_t base = 0; base < m; base += 32) {
+            const uint32_t j = base + lane;
+            uint32_t w = 0;
+            if (j < m) {
+                const uint32_t me = A[j];
+                for (uint32_t i = 0; i <= j; ++i)
+                    if (L[i] >= me) w += P[i + 1] - P[i];
+            }
+            // arg-max within the chunk, first index wins ties
+            uint32_t bw = w, bj = j;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const uint32_t ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (ow > bw || (ow == bw && oj < bj)) {
+                    bw = ow;
+                    bj = oj;
+                }
+            }
+            if (bw > best_w) {
+                best_w = bw;
+                best_j = bj;
+            }
+        }
+        result = A[best_j];
+    }
+    return ap.ranked_only ? __ldg(tv.snap_ranked + result) : __ldg(tv.snap_valid + result);
+}
+
 // Aggregates one record.  A[0..n) holds its non-zero taxon ids (any order) and, with KV, C[0..n)
 // how many times each entry occurred (run-length compressed input); P needs n+1 and L needs n
 // entries of scratch.  Returns the snapped taxon id, the literal 1 for an empty record
@@ -270,69 +338,59 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     if (lane == 0) P[m] = running;
     for (uint32_t j = lane; j < m; j += 32) L[j] = __ldg(tv.last + A[j]);
     __syncwarp();
+    return agg_finish(tv, A, P, L, m, running, ap, lane);
+}
 
-    uint32_t result;
-    if (ap.strategy == UMGAP_AGG_LCA_STAR) {
-        result = lca_star_range(tv, A, L, 0, m, lane);
-    } else if (ap.strategy == UMGAP_AGG_HYBRID) {
-        uint32_t lo = 0, hi = m;
-        uint32_t base_node = lca_star_range(tv, A, L, lo, hi, lane);
-        uint32_t bval = running;
-        lo = warp_upper_bound(A, lo, hi, base_node - 1u, lane);  // first member >= base (base>=0)
-        if (base_node == 0) lo = 0;
-        for (;;) {
-            uint32_t g = lo;
-            if (g < hi && A[g] == base_node) ++g;  // the base itself is not one of its children
-            if (g >= hi) break;                    // no children: stop (tree/mix.rs:51)
-            const uint32_t child_depth = (uint32_t)__ldg(tv.depth + base_node) + 1;
-            uint32_t best = 0, best_lo = 0, best_hi = 0;
-            while (g < hi) {
-                const uint32_t c = __ldg(tv.anc + (uint64_t)A[g] * tv.stride + child_depth);
-                const uint32_t e = warp_upper_bound(A, g, hi, __ldg(tv.last + c), lane);
-                const uint32_t sub = P[e] - P[g];
-                if (sub > best) {  // first maximal child in preorder wins ties
-                    best = sub;
-                    best_lo = g;
-                    best_hi = e;
-                }
-                g = e;
-            }
-            if (__fdiv_rn((float)best, (float)bval) < ap.factor) break;  // tree/mix.rs:57
-            base_node = lca_star_range(tv, A, L, best_lo, best_hi, lane);
-            bval = best;
-            hi = best_hi;
-            lo = base_node == 0 ? best_lo : warp_upper_bound(A, best_lo, best_hi, base_node - 1u, lane);
-        }
-        result = base_node;
-    } else {  // MRTL
-        uint32_t best_w = 0, best_j = 0;
-        for (uint32_t base = 0; base < m; base += 32) {
-            const uint32_t j = base + lane;
-            uint32_t w = 0;
-            if (j < m) {
-                const uint32_t me = A[j];
-                for (uint32_t i = 0; i <= j; ++i)
-                    if (L[i] >= me) w += P[i + 1] - P[i];
-            }
-            // arg-max within the chunk, first index wins ties
-            uint32_t bw = w, bj = j;
+// Register-resident ascending bitonic sort of one (key, payload) pair per lane.
+__device__ __forceinline__ void warp_sort32(uint32_t& d, uint32_t& c, int lane) {
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const uint32_t ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (ow > bw || (ow == bw && oj < bj)) {
-                    bw = ow;
-                    bj = oj;
-                }
-            }
-            if (bw > best_w) {
-                best_w = bw;
-                best_j = bj;
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t od = __shfl_xor_sync(0xffffffffu, d, j);
+            const uint32_t oc = __shfl_xor_sync(0xffffffffu, c, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            const bool take = (lower == up) ? (od < d) : (od > d);
+            if (take) {
+                d = od;
+                c = oc;
             }
         }
-        result = A[best_j];
     }
-    return ap.ranked_only ? __ldg(tv.snap_ranked + result) : __ldg(tv.snap_valid + result);
+}
+
+// Aggregates a record given as n <= 32 DISTINCT non-zero taxon ids with their occurrence counts, one per
+// lane (lane i < n holds id / cnt): everything up to the strategies stays in registers.  P needs n+1 and
+// A, L need n entries of scratch.  Same results as warp_aggregate.  All 32 lanes must call.
+__device__ __forceinline__ uint32_t warp_aggregate_distinct(const TaxView& tv, uint32_t id, uint32_t cnt, uint32_t n,
+                                                            uint32_t* A, uint32_t* P, uint32_t* L, const AggParams& ap,
+                                                            int lane, uint32_t* bad_id) {
+    if (n == 0) return 1u;
+    const bool have = (uint32_t)lane < n;
+    uint32_t d = kNoTaxon;
+    if (have) {
+        d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
+        if (d == kNoTaxon) *bad_id = id;
+    }
+    if (__any_sync(0xffffffffu, have && d == kNoTaxon)) return kAggUnknown;
+    uint32_t c = have ? cnt : 0u;
+    warp_sort32(d, c, lane);  // the n members first (kNoTaxon = 0xFFFFFFFF pads the rest)
+    const bool keep = d != kNoTaxon && (float)c >= ap.lower_bound;  // agg/mod.rs:39-44
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const uint32_t m = (uint32_t)__popc(mask);
+    if (m == 0) return 1u;  // everything filtered: the literal "1"
+    const uint32_t incl = warp_incl_scan(keep ? c : 0u, lane);
+    const uint32_t running = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    if (keep) {
+        const uint32_t rank = (uint32_t)__popc(mask & ((1u << lane) - 1));
+        A[rank] = d;
+        P[rank] = incl - c;
+        L[rank] = __ldg(tv.last + d);
+    }
+    if (lane == 0) P[m] = running;
+    __syncwarp();
+    return agg_finish(tv, A, P, L, m, running, ap, lane);
 }
 
 }  // namespace umgap
