@@ -307,6 +307,7 @@ def run_ours(args):
     barrier()
     capi.kernel_timing(True)
     capi.kernel_times()
+    launches0 = capi.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -316,6 +317,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     lookup_ms, lookup_n, classify_ms, classify_n = capi.kernel_times()
+    launches = capi.kernel_launch_count() - launches0
     capi.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -380,8 +382,17 @@ def run_ours(args):
         tj = json.load(open(tpath))
         if tj.get("pairs_per_launch") == B:
             traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if routed is not None else "translate_lookup_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    lines = None
+    if os.path.exists(tpath) and traffic:
+        lines = tj.get("lookup_kernel_dram_bytes_per_launch", traffic) / 128.0 / nreads
+    roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if routed is not None
+                else "lookup stage = translate_codes_kernel + lookup_sampled_kernel<9,TableView,3> (+ long-read pass), timed as one bracket",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "algorithmic bytes = 248 k-mers x 32 B per read (SURVEY 8(d)); in front of seedextend -s3 the kernel probes every "
+                        "third position first and the rest only for frames with a hit (bit-identical output), so the HBM actually moves "
+                        "`traffic` bytes: 128-byte line fills at the random-line ceiling (profiles/README.md)",
+                "dram_lines_per_read": lines,
                 "algorithmic_bytes_per_launch": lookups_per_launch * BYTES_PER_LOOKUP, "avg_launch_ms": avg_ms,
                 "kernel_share_of_step": lookup_ms / ms if ms else None,
                 "lookups_per_second_kernel": lookups_per_launch / (avg_ms * 1e-3)}
@@ -396,7 +407,7 @@ def run_ours(args):
                                          "index_build_s": build_s, "index_load_factor": info.load_factor, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
                                          "classified_below_root_frac": classified}),
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": int(lookup_n + classify_n),
+        "gpu_launches": int(launches),
         "kernel_ms": {"translate_lookup": lookup_ms, "classify": classify_ms},
     }
     emit(json.dumps(line))

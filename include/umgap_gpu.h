@@ -248,6 +248,10 @@ int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, co
 int umgap_kernel_timing(int enable);
 int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
                        uint64_t* classify_launches);
+/* Number of kernels the fused path (umgap_classify_reads[_dev], umgap_translate_lookup_dev,
+ * umgap_classify_ids_dev) has launched in this process; the lookup stage is up to three launches
+ * (residue-code pre-pass, sampled lookup kernel, long-read pass).                                  */
+int umgap_kernel_launch_count(uint64_t* launches);
 
 /* ---- benchmark / test aids (synthetic data of SURVEY 8(d); not part of the reference) ---- */
 typedef struct umgap_synth_spec {

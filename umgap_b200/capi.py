@@ -35,7 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
-    "umgap_kernel_timing", "umgap_kernel_times",
+    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
 
@@ -397,6 +397,13 @@ def kernel_times():
     na, nb = C.c_uint64(), C.c_uint64()
     _check(load_library().umgap_kernel_times(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
     return a.value, na.value, b.value, nb.value
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by the fused path in this process so far."""
+    n = C.c_uint64()
+    _check(load_library().umgap_kernel_launch_count(C.byref(n)))
+    return n.value
 
 
 def route_pack_dev(index: Index, opts: PipelineOpts, nt_ptr: int, read_off_ptr: int, nreads: int, total_nt: int,

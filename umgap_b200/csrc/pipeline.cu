@@ -683,6 +683,52 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
     const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + f;
     // private slice of this record: pair i at words 6i, 6i+1 past 2*(strand*n + f), inside the read's 4n words
     uint32_t* priv = read_priv + 2 * ((fr >= 3 ? n : 0) + f);
+    if (cp.seedextend && cp.one_on_one && cp.max_gap == 0 && cp.min_seed >= 2 && cnt <= 63) {
+        // -g 0: every zero ends a range (seedextend.rs:116-127 fires for any gap, same >= 1 > 0), so the
+        // ranges are the maximal zero-free stretches, and a stretch is selected iff it holds min_seed equal
+        // consecutive ids (:137-149).  On bit masks, one record per lane, no per-element state machine:
+        // nz = id != 0, eq = id equals its predecessor; a seed ends where min_seed - 1 consecutive eq bits meet
+        // nz; the kept ids leave as (id, run length) for each run of the stretches that hold a seed.
+        uint32_t nz_lo = 0, eq_lo = 0, nz_hi = 0, eq_hi = 0, prev = kNoValue;
+        const uint32_t c_lo = cnt < 32 ? cnt : 32;
+#pragma unroll 4
+        for (uint32_t i = 0; i < c_lo; ++i) {
+            uint32_t v = base[3 * i];
+            v = v == kNoValue ? 0u : v;
+            nz_lo |= (uint32_t)(v != 0) << i;
+            eq_lo |= (uint32_t)(v == prev) << i;
+            prev = v;
+        }
+#pragma unroll 4
+        for (uint32_t i = 32; i < cnt; ++i) {
+            uint32_t v = base[3 * i];
+            v = v == kNoValue ? 0u : v;
+            nz_hi |= (uint32_t)(v != 0) << (i - 32);
+            eq_hi |= (uint32_t)(v == prev) << (i - 32);
+            prev = v;
+        }
+        const uint64_t nz = (uint64_t)nz_hi << 32 | nz_lo, eq = (uint64_t)eq_hi << 32 | eq_lo;
+        uint64_t seed = nz & eq;
+        for (uint32_t k = 1; k + 1 < cp.min_seed && seed; ++k) seed &= eq << k;
+        uint64_t kept = 0;
+        while (seed) {  // the stretch around the lowest remaining seed
+            const uint32_t sp = (uint32_t)__ffsll((long long)seed) - 1;
+            const uint64_t up = ((nz + (1ull << sp)) ^ nz) & nz;            // from the seed to the stretch's last id
+            const uint64_t zeros_below = ~nz & ((1ull << sp) - 1);
+            const uint32_t first = zeros_below ? 64u - (uint32_t)__clzll((long long)zeros_below) : 0u;
+            const uint64_t stretch = up | (((1ull << sp) - 1) & ~((1ull << first) - 1));
+            kept |= stretch;
+            seed &= ~stretch;
+        }
+        const uint64_t ends = (kept & ~eq) | ~kept;  // run heads, and everything outside the kept stretches (bit 63 included)
+        uint64_t heads = kept & ~eq;
+        while (heads) {
+            const uint32_t hp = (uint32_t)__ffsll((long long)heads) - 1;
+            heads &= heads - 1;
+            sink.add(base[3 * hp], (uint32_t)__ffsll((long long)(ends >> (hp + 1))));
+        }
+        return true;
+    }
     if (cp.seedextend && cp.one_on_one) {
         // Single pass of the seedextend machine (seedextend.rs:101-149) that builds the run-length
         // list of the CURRENT range tentatively in the record's private slice and commits it when the
@@ -966,7 +1012,7 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_IDS = 0, WS_SCRATCH = 1, WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 16 };  // x3 buffers
+enum { WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 18, WS_IDS = 21, WS_SCRATCH = 24 };  // x3 buffers each
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -993,6 +1039,7 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
 
 // ---- optional per-launch timing (umgap_kernel_timing), shared with route.cu -----------------------
 namespace umgap {
+static uint64_t g_launch_count = 0;  // kernels launched by the fused path
 bool g_timing = false;
 std::vector<TimedLaunch> g_launches;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -1061,6 +1108,7 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
                 UMGAP_FAIL(UMGAP_ERR_INVALID, "unsupported k %d", idx->k);
         }
         UMGAP_CUDA(cudaGetLastError());
+        ++g_launch_count;
         timer.stop();
     }
 }
@@ -1077,6 +1125,7 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
                                                        read_off_dev, group_off_dev, g_begin, g_end,
                                                        frame_hits_dev, scratch_dev, out_dev, err);
     UMGAP_CUDA(cudaGetLastError());
+    ++g_launch_count;
     timer.stop();
 }
 
@@ -1096,7 +1145,7 @@ static void launch_sampled(const umgap_index* idx, const uint8_t* codes, uint64_
 // the frames flagged in frame_hits_dev have ids afterwards, which is all the classify kernel reads.
 static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
                                             const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
-                                            uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st) {
+                                            uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
     static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
@@ -1107,11 +1156,12 @@ static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
     const uint64_t rev_off = (total_nt + 15) / 16 * 16 + 16;
-    uint8_t* codes = (uint8_t*)idx->ws.get(WS_CODES, 2 * rev_off);
+    uint8_t* codes = (uint8_t*)idx->ws.get(WS_CODES + buf, 2 * rev_off);
     LaunchTimer timer(0, st);
     const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(total_nt, 16), 256) + 1, 148ull * 16);
     translate_codes_kernel<<<tblocks, 256, 0, st>>>(lut, nt_dev, total_nt, codes, rev_off);
     UMGAP_CUDA(cudaGetLastError());
+    g_launch_count += 2;  // the pre-pass and the sampled lookup kernel below
     switch (std::min(o->min_seed_size, 4)) {
         case 2: launch_sampled<2>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
         case 3: launch_sampled<3>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
@@ -1127,9 +1177,9 @@ static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
                             const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
-                            uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st) {
+                            uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st, int buf = 0) {
     if (!ngroups) return;
-    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st))
+    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf))
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
     launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
 }
@@ -1145,6 +1195,11 @@ int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes) {
         if (!idx) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         idx->region_bytes = bytes;
     });
+}
+
+int umgap_kernel_launch_count(uint64_t* launches) {
+    if (launches) *launches = g_launch_count;
+    return UMGAP_OK;
 }
 
 int umgap_kernel_timing(int enable) {
@@ -1259,10 +1314,15 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
         // nucleotides and offsets of the next chunks upload and the results of the previous one
         // download.  Offsets are uploaded as given and rebased on the device.
-        const uint64_t kChunkNt = 48ull << 20;  // nucleotides per chunk (measured best of 8..96 MiB)
+        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 8..96 MiB; UMGAP_CHUNK_MB overrides)
+            const char* e = getenv("UMGAP_CHUNK_MB");
+            const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
+            return (mb ? mb : 48ull) << 20;
+        }();
         constexpr int kBufs = 3;
         cudaStream_t st[kBufs];
         cudaEvent_t done[kBufs];
+        static const bool ordered = getenv("UMGAP_CHUNK_ORDERED") != nullptr;
         for (int i = 0; i < kBufs; ++i) {
             UMGAP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
             UMGAP_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
@@ -1274,12 +1334,16 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         uint64_t g0 = 0;
         int buf = 0, prev = -1;
         try {
+            int chunk_no = 0;
             while (g0 < ngroups) {
                 const uint64_t nt0 = nt_before(g0);
-                uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= kChunkNt, at least g0 + 1
+                // the first chunks are short so that the kernels start early: 1/8, 1/4, 1/2 of a chunk, then full ones
+                const uint64_t limit = chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
+                ++chunk_no;
+                uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
                 while (lo < hi) {
                     const uint64_t mid = lo + (hi - lo + 1) / 2;
-                    if (nt_before(mid) - nt0 <= kChunkNt) lo = mid; else hi = mid - 1;
+                    if (nt_before(mid) - nt0 <= limit) lo = mid; else hi = mid - 1;
                 }
                 const uint64_t g1 = lo;
                 const uint64_t r0 = group_off[g0], r1 = group_off[g1];
@@ -1289,19 +1353,21 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                 uint64_t* d_roff = (uint64_t*)idx->ws.get(WS_ROFF + buf, (std::max<uint64_t>(cnt_r, kChunkNt / 32) + 1) * 8);
                 uint64_t* d_goff = (uint64_t*)idx->ws.get(WS_GOFF + buf, (std::max<uint64_t>(cnt_g, kChunkNt / 32) + 1) * 8);
                 uint32_t* d_out = (uint32_t*)idx->ws.get(WS_OUT + buf, std::max<uint64_t>(cnt_g, kChunkNt / 32) * 4 + 16);
-                // ids / scratch are shared by all chunks: the kernels of consecutive chunks are ordered
-                // through `done`, the copies around them overlap freely
-                uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS, (2 * cap_nt + 64) * 4);
-                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * cap_nt + 64) * 4);
+                // every stream has its own ids / scratch / hits / codes: the kernels of consecutive chunks are not
+                // ordered against each other, so one chunk's classify kernel and the next chunk's lookup kernel fill
+                // each other's tails (UMGAP_CHUNK_ORDERED=1 restores the strict order, for measurements)
+                uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS + buf, (2 * cap_nt + 64) * 4);
+                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH + buf, (12 * cap_nt + 64) * 4);
                 cudaStream_t s = st[buf];
                 UMGAP_CUDA(cudaMemcpyAsync(d_nt, nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
                 UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
                 UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
                 rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, d_goff, cnt_g + 1, r0);
                 UMGAP_CUDA(cudaGetLastError());
-                if (prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
-                uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
-                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, cnt_nt, d_goff, cnt_g, ids, scratch, hits, d_out, err, s);
+                ++g_launch_count;
+                if (ordered && prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
+                uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS + buf, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
+                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, cnt_nt, d_goff, cnt_g, ids, scratch, hits, d_out, err, s, buf);
                 UMGAP_CUDA(cudaEventRecord(done[buf], s));
                 UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
                 prev = buf;
