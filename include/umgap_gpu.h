@@ -252,6 +252,11 @@ int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* cla
  * umgap_classify_ids_dev) has launched in this process; the lookup stage is up to three launches
  * (residue-code pre-pass, sampled lookup kernel, long-read pass).                                  */
 int umgap_kernel_launch_count(uint64_t* launches);
+/* umgap_classify_reads_dev cuts a batch into `slices` group ranges whose lookup and classify kernels
+ * alternate on two internal streams (they fill each other's tails); 1 = one lookup and one classify
+ * launch on the caller's stream.  Returns the previous setting; slices <= 0 only queries.  Default 8
+ * (environment UMGAP_SLICES).                                                                      */
+int umgap_pipeline_slices(int slices);
 
 /* ---- benchmark / test aids (synthetic data of SURVEY 8(d); not part of the reference) ---- */
 typedef struct umgap_synth_spec {

@@ -39,6 +39,11 @@ ms1 = timeit(lambda: capi.translate_lookup_dev(gidx, opts, nt.data_ptr(), roff.d
 print(f"translate_lookup: {ms1:.3f} ms  {nlook/ms1/1e6:.2f} G lookups/s  {nlook*32/ms1/1e6:.1f} GB/s algorithmic", flush=True)
 ms2 = timeit(lambda: capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st))
 print(f"classify (both kernels): {ms2:.3f} ms  {npairs*2/ms2/1e3:.2f} M reads/s", flush=True)
+for sl in [int(x) for x in os.environ.get("PROBE_SLICES", "").split(",") if x]:
+    capi.pipeline_slices(sl)
+    ms3 = timeit(lambda: capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st), 8)
+    print(f"slices {sl}: {ms3:.3f} ms  {npairs*2/ms3/1e3:.2f} M reads/s", flush=True)
+capi.pipeline_slices(1)
 capi.kernel_timing(True); capi.kernel_times()
 for _ in range(5):
     capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st)

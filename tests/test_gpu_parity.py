@@ -337,6 +337,36 @@ def test_classify_dev_entry_matches_host_entry(capi, world):
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32), host)
 
 
+def test_sliced_device_path_matches_unsliced(capi, world):
+    """umgap_classify_reads_dev cuts a large batch into slices on two internal streams (lookup kernel of one slice
+    beside the classify kernel of the previous one); same answers as one slice and as the host-buffer entry."""
+    torch = pytest.importorskip("torch")
+    base = datagen.make_reads(world["proteins"], 400, seed=77, hit_frac=0.8)
+    base += [("t/1", "ACGT" * 10), ("t/2", ""), ("u/1", "ACG" * 400), ("u/2", "TTGACC" * 30)]   # ragged, one read beyond a warp batch
+    reads = base * 80                                                                                # 32 320 groups
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
+    opts = capi.default_opts(min_seed_size=3, strategy=capi.AGG_HYBRID)
+    host, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, goff)
+    assert np.array_equal(host[:len(base) // 2], host[len(base) // 2:len(base)])
+    d_nt = torch.from_numpy(nt).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_goff = torch.from_numpy(goff.astype(np.int64)).cuda()
+    before = capi.pipeline_slices(0)
+    try:
+        for slices in (1, 2, 6, 7):
+            capi.pipeline_slices(slices)
+            d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
+            for _ in range(2):   # twice: the second call reuses every buffer while the first may still be in flight
+                capi.classify_reads_dev(world["gidx"], world["gtax"], opts, d_nt.data_ptr(), d_off.data_ptr(), len(reads),
+                                        int(off[-1]), d_goff.data_ptr(), len(goff) - 1, d_out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy().view(np.uint32), host), slices
+    finally:
+        capi.pipeline_slices(before)
+
+
 def test_synthetic_generators_match_numpy_mirror(capi):
     """The device-side workload generator (bench aid) against oracle/synth.py, bit for bit."""
     torch = pytest.importorskip("torch")

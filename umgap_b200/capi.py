@@ -35,7 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
-    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count",
+    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_pipeline_slices",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
 
@@ -397,6 +397,11 @@ def kernel_times():
     na, nb = C.c_uint64(), C.c_uint64()
     _check(load_library().umgap_kernel_times(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
     return a.value, na.value, b.value, nb.value
+
+
+def pipeline_slices(slices: int = 0) -> int:
+    """Sets (slices > 0) the number of slices of classify_reads_dev; returns the previous value."""
+    return int(load_library().umgap_pipeline_slices(C.c_int(slices)))
 
 
 def kernel_launch_count() -> int:

@@ -61,6 +61,9 @@ struct umgap_index {
     // variable-length table (k == 0), see tryptic.cu
     void* var_table = nullptr;
     mutable umgap::Workspace ws;
+    // two internal streams + events of the sliced device path (pipeline.cu), created on first use
+    mutable cudaStream_t aux_stream[2] = {};
+    mutable cudaEvent_t aux_fork = nullptr, aux_join[2] = {};
 
     umgap::TableView view() const {
         umgap::TableView v{};
@@ -111,6 +114,7 @@ struct LaunchTimer {
     bool on;
     LaunchTimer(int kind, cudaStream_t s, bool enabled = true);
     void stop();
+    void cancel();  // drop the bracket (events go back to the pool)
 };
 
 // FST v2 stream reader (fst_stream.cpp): calls `sink(key, len, value)` for every key in order.

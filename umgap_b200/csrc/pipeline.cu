@@ -417,17 +417,21 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
 template <int K, class TV, int STRIDE>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
 lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
-                      uint32_t nreads, uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits) {
+                      uint32_t nreads, uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits,
+                      const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi) {
     __shared__ SampledSmem s_sm[kSWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     SampledSmem& sm = s_sm[warp];
-    const uint32_t nunits = (nreads + kSReads - 1) / kSReads;
+    // the reads of groups [g_lo, g_hi) when a group table is given (slices of the device path), else all reads
+    const uint32_t r_begin = group_off ? (uint32_t)group_off[g_lo] : 0u;
+    const uint32_t r_end = group_off ? (uint32_t)group_off[g_hi] : nreads;
+    const uint32_t nunits = (r_end - r_begin + kSReads - 1) / kSReads;
     const uint32_t nwarps = gridDim.x * kSWarps;
 #pragma unroll 1
     for (uint32_t unit = blockIdx.x * kSWarps + warp; unit < nunits; unit += nwarps) {
-        uint32_t cur = unit * kSReads;
-        const uint32_t end = min(cur + (uint32_t)kSReads, nreads);
+        uint32_t cur = r_begin + unit * kSReads;
+        const uint32_t end = min(cur + (uint32_t)kSReads, r_end);
 #pragma unroll 1
         while (cur < end) {
             // ---- batch geometry: as many of the unit's remaining reads as fit kSSpan nucleotides
@@ -1040,6 +1044,11 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
 // ---- optional per-launch timing (umgap_kernel_timing), shared with route.cu -----------------------
 namespace umgap {
 static uint64_t g_launch_count = 0;  // kernels launched by the fused path
+static int g_slices = [] {           // slices of the device-buffer entry point (umgap_pipeline_slices)
+    const char* e = getenv("UMGAP_SLICES");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? std::min(v, 64) : 8;
+}();
 bool g_timing = false;
 std::vector<TimedLaunch> g_launches;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -1059,6 +1068,12 @@ LaunchTimer::LaunchTimer(int kind, cudaStream_t s, bool enabled) : st(s), on(g_t
     t.a = take_event();
     t.b = take_event();
     UMGAP_CUDA(cudaEventRecord(t.a, st));
+}
+void LaunchTimer::cancel() {
+    if (!on) return;
+    g_event_pool.push_back(t.a);
+    g_event_pool.push_back(t.b);
+    on = false;
 }
 void LaunchTimer::stop() {
     if (!on) return;
@@ -1133,55 +1148,110 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
 // (Running the classify kernel of one slice concurrently with the lookup kernel of the next, on two
 // streams with priorities, was measured and gives nothing: both kernels want the same registers
 // and issue slots -- profiles/README.md.)
-template <int STRIDE>
-static void launch_sampled(const umgap_index* idx, const uint8_t* codes, uint64_t rev_off, const uint64_t* read_off_dev, uint64_t nreads, uint32_t* ids_dev,
-                           uint8_t* frame_hits_dev, cudaStream_t st) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads, kSReads), kSWarps), 148ull * kSBlocks * 4);
-    lookup_sampled_kernel<9, TableView, STRIDE><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), codes, rev_off, read_off_dev,
-                                                                                (uint32_t)nreads, ids_dev, frame_hits_dev);
+struct SampledPlan {  // the sampled lookup stage of one batch
+    int stride = 0;       // 0: not applicable, use the plain kernel
+    uint8_t* codes = nullptr;
+    uint64_t rev_off = 0;
+};
+
+// reads_hint: number of reads the launch will find in its group range (sizes the grid only).
+static void launch_sampled(const umgap_index* idx, const SampledPlan& sp, const uint64_t* read_off_dev, uint64_t nreads,
+                           uint64_t reads_hint, uint32_t* ids_dev, uint8_t* frame_hits_dev, const uint64_t* group_off_dev,
+                           uint64_t g_lo, uint64_t g_hi, cudaStream_t st) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, 148ull * kSBlocks * 4);
+#define UMGAP_SAMPLED(S)                                                                                                     \
+    lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.codes, sp.rev_off, read_off_dev,  \
+                                                                           (uint32_t)nreads, ids_dev, frame_hits_dev,        \
+                                                                           group_off_dev, g_lo, g_hi)
+    switch (sp.stride) {
+        case 2: UMGAP_SAMPLED(2); break;
+        case 3: UMGAP_SAMPLED(3); break;
+        default: UMGAP_SAMPLED(4); break;
+    }
+#undef UMGAP_SAMPLED
+    UMGAP_CUDA(cudaGetLastError());
+    ++g_launch_count;
 }
 
 // Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
 // the frames flagged in frame_hits_dev have ids afterwards, which is all the classify kernel reads.
-static bool launch_translate_lookup_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
-                                            const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
-                                            uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
+// Decides whether the stage applies and, if so, launches what has to run once per batch: the residue-code
+// pre-pass and the plain kernel over the reads longer than a warp batch (rare; it skips everything else).
+static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
+                                   const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
+                                   uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
     static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
+    SampledPlan sp;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
         (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 31) ||
         ((uintptr_t)nt_dev & 15u) != 0)
-        return false;
-    if (!nreads) return true;
+        return sp;
+    sp.stride = std::min(o->min_seed_size, 4);
+    if (!nreads) return sp;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
-    const uint64_t rev_off = (total_nt + 15) / 16 * 16 + 16;
-    uint8_t* codes = (uint8_t*)idx->ws.get(WS_CODES + buf, 2 * rev_off);
-    LaunchTimer timer(0, st);
+    sp.rev_off = (total_nt + 15) / 16 * 16 + 16;
+    sp.codes = (uint8_t*)idx->ws.get(WS_CODES + buf, 2 * sp.rev_off);
     const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(total_nt, 16), 256) + 1, 148ull * 16);
-    translate_codes_kernel<<<tblocks, 256, 0, st>>>(lut, nt_dev, total_nt, codes, rev_off);
+    translate_codes_kernel<<<tblocks, 256, 0, st>>>(lut, nt_dev, total_nt, sp.codes, sp.rev_off);
     UMGAP_CUDA(cudaGetLastError());
-    g_launch_count += 2;  // the pre-pass and the sampled lookup kernel below
-    switch (std::min(o->min_seed_size, 4)) {
-        case 2: launch_sampled<2>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
-        case 3: launch_sampled<3>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
-        default: launch_sampled<4>(idx, codes, rev_off, read_off_dev, nreads, ids_dev, frame_hits_dev, st); break;
-    }
-    UMGAP_CUDA(cudaGetLastError());
-    // reads longer than a warp batch (rare): the plain kernel, which skips everything else
+    ++g_launch_count;
     launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, (uint32_t)kSSpan, false);
-    timer.stop();
-    return true;
+    return sp;
 }
 
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
                             const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
-                            uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st, int buf = 0) {
+                            uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st, int buf = 0,
+                            bool sliced = false) {
     if (!ngroups) return;
-    if (!launch_translate_lookup_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf))
+    LaunchTimer timer(0, st);
+    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
+    if (!sp.stride) {
+        timer.cancel();  // the plain launch brackets itself
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
-    launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
+        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
+        return;
+    }
+    const int kSlices = g_slices;
+    if (!sliced || kSlices < 2 || ngroups < 4096u * (uint64_t)kSlices || !nreads) {
+        if (nreads) launch_sampled(idx, sp, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, st);
+        timer.stop();
+        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
+        return;
+    }
+    // Sliced: the groups are cut into kSlices ranges; the lookup and classify kernels of a slice follow each other on
+    // one of two internal streams (even / odd slices), so the classify kernel of slice i runs beside the lookup kernel
+    // of slice i + 1 and never more than two slices are in flight.  (One stream of back-to-back lookup kernels plus a
+    // higher-priority stream of classify kernels was measured and is slower: 7.1 vs 6.6 ms, the lookup kernels run
+    // ahead and the classify kernels pile up at the end.)  The lookup kernel takes its read range from the group table on the
+    // device; every buffer is addressed by absolute read / nucleotide position, so the slices share them.
+    timer.stop();  // the bracket of this mode covers the once-per-batch part only; the slices are bracketed one by one
+    if (!idx->aux_fork) {
+        for (int i = 0; i < 2; ++i) {
+            UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->aux_stream[i], cudaStreamNonBlocking));
+            UMGAP_CUDA(cudaEventCreateWithFlags(&idx->aux_join[i], cudaEventDisableTiming));
+        }
+        UMGAP_CUDA(cudaEventCreateWithFlags(&idx->aux_fork, cudaEventDisableTiming));
+    }
+    UMGAP_CUDA(cudaEventRecord(idx->aux_fork, st));
+    for (int i = 0; i < 2; ++i) UMGAP_CUDA(cudaStreamWaitEvent(idx->aux_stream[i], idx->aux_fork, 0));
+    for (int sl = 0; sl < kSlices; ++sl) {
+        const uint64_t g_lo = ngroups * sl / kSlices, g_hi = ngroups * (sl + 1) / kSlices;
+        cudaStream_t s = idx->aux_stream[sl & 1];
+        {
+            LaunchTimer t2(0, s);
+            launch_sampled(idx, sp, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev, g_lo, g_hi, s);
+            t2.stop();
+        }
+        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, g_lo, g_hi, frame_hits_dev, scratch_dev, out_dev, err, s);
+    }
+    for (int i = 0; i < 2; ++i) {
+        UMGAP_CUDA(cudaEventRecord(idx->aux_join[i], idx->aux_stream[i]));
+        UMGAP_CUDA(cudaStreamWaitEvent(st, idx->aux_join[i], 0));
+    }
 }
 
 static void raise_dev_error(const DevError& e) {
@@ -1195,6 +1265,12 @@ int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes) {
         if (!idx) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         idx->region_bytes = bytes;
     });
+}
+
+int umgap_pipeline_slices(int slices) {
+    const int before = g_slices;
+    if (slices > 0) g_slices = std::min(slices, 64);
+    return before;
 }
 
 int umgap_kernel_launch_count(uint64_t* launches) {
@@ -1285,7 +1361,7 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
         uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, nreads + 64);
         launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, total_nt, group_off_dev, ngroups, ids, scratch, hits,
-                        taxon_out_dev, err, st);
+                        taxon_out_dev, err, st, 0, true);
     });
 }
 

@@ -456,6 +456,11 @@ void umgap_index_free(umgap_index* idx) {
         if (idx->level_dev[i]) cudaFree(idx->level_dev[i]);
     if (idx->var_table) free_var_table(idx->var_table);
     idx->ws.release();
+    for (int i = 0; i < 2; ++i) {
+        if (idx->aux_stream[i]) cudaStreamDestroy(idx->aux_stream[i]);
+        if (idx->aux_join[i]) cudaEventDestroy(idx->aux_join[i]);
+    }
+    if (idx->aux_fork) cudaEventDestroy(idx->aux_fork);
     delete idx;
 }
 
