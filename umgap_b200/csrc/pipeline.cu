@@ -1390,10 +1390,10 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
         // nucleotides and offsets of the next chunks upload and the results of the previous one
         // download.  Offsets are uploaded as given and rebased on the device.
-        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 8..96 MiB; UMGAP_CHUNK_MB overrides)
+        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 6..96 MiB: gpurun_out/e2e_probe*.log; UMGAP_CHUNK_MB overrides)
             const char* e = getenv("UMGAP_CHUNK_MB");
             const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
-            return (mb ? mb : 48ull) << 20;
+            return (mb ? mb : 24ull) << 20;
         }();
         constexpr int kBufs = 3;
         cudaStream_t st[kBufs];
