@@ -253,23 +253,38 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
     return __reduce_or_sync(0xffffffffu, hitbits);
 }
 
+// Work list of the plain kernel behind the sampled one: the reads (absolute indices) at list[base .. base + *count),
+// base = first read of group g_lo when a group table is given, else 0.
+struct ReadList {
+    const uint32_t* list = nullptr;
+    const uint32_t* count = nullptr;
+    const uint64_t* group_off = nullptr;
+    uint64_t g_lo = 0;
+};
+
 // Lookup kernel: one warp per read, ids to global memory, frame hit masks to frame_hits.
 template <int K, class TV, bool REGION>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
 translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
                         uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits, uint64_t region_lo,
-                        uint64_t region_hi, uint32_t longer_than /* 0: every read; else only reads longer than this */) {
+                        uint64_t region_hi, ReadList rl /* rl.list set: only the reads of that list */) {
     __shared__ uint8_t s_lut[72];
     __shared__ LookupSmem<K> s_sm[kLookupWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
     __syncthreads();
     const uint64_t nwarps = (uint64_t)gridDim.x * kLookupWarps;
-    for (uint64_t r = r_begin + (uint64_t)blockIdx.x * kLookupWarps + warp; r < r_end; r += nwarps) {
+    const uint32_t* list = nullptr;
+    if (rl.list) {  // the reads the sampled kernel left over (longer than one of its batches)
+        list = rl.list + (rl.group_off ? rl.group_off[rl.g_lo] : 0);
+        r_begin = 0;
+        r_end = *rl.count;
+    }
+    for (uint64_t i = r_begin + (uint64_t)blockIdx.x * kLookupWarps + warp; i < r_end; i += nwarps) {
+        const uint64_t r = list ? list[i] : i;
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
-        if (longer_than && n <= longer_than) continue;  // the sampled kernel has done this read
         uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
         if (n >= 3u * K) mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi);
         if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)(!REGION || region_lo == 0 ? mask : (mask | frame_hits[r]));
@@ -312,13 +327,17 @@ static_assert(6 * kSReads <= 32, "one lane per frame record of a batch");
 // reverse.  A codon that runs past total_nt holds N; codons that straddle two reads are never used.
 __global__ void __launch_bounds__(256)
 translate_codes_kernel(const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt, uint64_t total_nt,
-                       uint8_t* __restrict__ codes, uint64_t rev_off) {
+                       uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
+                       const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi) {
     __shared__ uint8_t s_lut[72];
     if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
     __syncthreads();
-    const uint64_t nchunks = (total_nt + 15) / 16;
+    // all nucleotides, or (slices of the device path) those of groups [g_lo, g_hi); a 16-byte chunk that straddles two
+    // slices is written by both with the same bytes
+    const uint64_t ch_lo = group_off ? read_off[group_off[g_lo]] / 16 : 0;
+    const uint64_t nchunks = ((group_off ? read_off[group_off[g_hi]] : total_nt) + 15) / 16;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t ch = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+    for (uint64_t ch = ch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
         const uint64_t x0 = ch * 16;
         uint32_t w[5];
         if (x0 + 20 <= total_nt) {
@@ -418,7 +437,8 @@ template <int K, class TV, int STRIDE>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
 lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
                       uint32_t nreads, uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits,
-                      const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi) {
+                      const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
+                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
     __shared__ SampledSmem s_sm[kSWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -440,7 +460,8 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
             const uint64_t off0 = __shfl_sync(0xffffffffu, my_off, 0);
             const unsigned fits = __ballot_sync(0xffffffffu, lane >= 1 && (uint32_t)lane <= left && my_off - off0 <= (uint64_t)kSSpan);
             const uint32_t nb = (uint32_t)__popc(fits);
-            if (nb == 0) {  // a single read longer than the batch span: left to the plain kernel (launched next)
+            if (nb == 0) {  // a single read longer than the batch span: queued for the plain kernel (launched next)
+                if (lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
                 cur += 1;
                 continue;
             }
@@ -1016,7 +1037,7 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 18, WS_IDS = 21, WS_SCRATCH = 24 };  // x3 buffers each
+enum { WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 18, WS_IDS = 21, WS_SCRATCH = 24, WS_LONG = 27 };  // x3 buffers each
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -1086,11 +1107,11 @@ void LaunchTimer::stop() {
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
                                     const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
                                     uint64_t r_end, uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st,
-                                    uint32_t longer_than = 0, bool timed = true) {
+                                    ReadList rl = ReadList(), bool timed = true) {
     if (r_end <= r_begin) return;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(r_end - r_begin, kLookupWarps), 148ull * 32);
+    const unsigned blocks = rl.list ? 148u : (unsigned)std::min<uint64_t>(ceil_div(r_end - r_begin, kLookupWarps), 148ull * 32);
     if (idx->nshards > 1 && !idx->attached)
         UMGAP_FAIL(UMGAP_ERR_INVALID, "sharded index: call umgap_index_attach_shards() before looking up");
     // Random probes over more than ~64 GiB collapse to a quarter of the line rate on B200 (address-
@@ -1108,13 +1129,13 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     case KK:                                                                                                 \
         if (idx->nshards > 1)                                                                                \
             translate_lookup_kernel<KK, ShardedView, false><<<blocks, kLookupWarps * 32, 0, st>>>(            \
-                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);   \
+                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);   \
         else if (nregions > 1)                                                                               \
             translate_lookup_kernel<KK, TableView, true><<<blocks, kLookupWarps * 32, 0, st>>>(               \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);    \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);    \
         else                                                                                                 \
             translate_lookup_kernel<KK, TableView, false><<<blocks, kLookupWarps * 32, 0, st>>>(              \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, longer_than);    \
+                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);    \
         break;
             UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
             UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
@@ -1152,17 +1173,33 @@ struct SampledPlan {  // the sampled lookup stage of one batch
     int stride = 0;       // 0: not applicable, use the plain kernel
     uint8_t* codes = nullptr;
     uint64_t rev_off = 0;
+    CodonLut lut{};
+    uint32_t* long_count = nullptr;  // 64 counters (one per slice), then the list of reads left to the plain kernel
+    uint32_t* long_list = nullptr;
 };
 
+// Residue-code pre-pass over all nucleotides, or over those of groups [g_lo, g_hi) (nt_hint sizes the grid).
+static void launch_codes(const SampledPlan& sp, const uint8_t* nt_dev, uint64_t total_nt, uint64_t nt_hint,
+                         const uint64_t* read_off_dev, const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi,
+                         cudaStream_t st) {
+    const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nt_hint, 16), 256) + 1, 148ull * 16);
+    translate_codes_kernel<<<tblocks, 256, 0, st>>>(sp.lut, nt_dev, total_nt, sp.codes, sp.rev_off, read_off_dev, group_off_dev,
+                                                    g_lo, g_hi);
+    UMGAP_CUDA(cudaGetLastError());
+    ++g_launch_count;
+}
+
 // reads_hint: number of reads the launch will find in its group range (sizes the grid only).
-static void launch_sampled(const umgap_index* idx, const SampledPlan& sp, const uint64_t* read_off_dev, uint64_t nreads,
-                           uint64_t reads_hint, uint32_t* ids_dev, uint8_t* frame_hits_dev, const uint64_t* group_off_dev,
-                           uint64_t g_lo, uint64_t g_hi, cudaStream_t st) {
+static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const SampledPlan& sp, const uint8_t* nt_dev,
+                           const uint64_t* read_off_dev, uint64_t nreads, uint64_t reads_hint, uint32_t* ids_dev,
+                           uint8_t* frame_hits_dev, const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi, int slice,
+                           cudaStream_t st) {
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, 148ull * kSBlocks * 4);
 #define UMGAP_SAMPLED(S)                                                                                                     \
     lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.codes, sp.rev_off, read_off_dev,  \
                                                                            (uint32_t)nreads, ids_dev, frame_hits_dev,        \
-                                                                           group_off_dev, g_lo, g_hi)
+                                                                           group_off_dev, g_lo, g_hi, sp.long_list,          \
+                                                                           sp.long_count + slice)
     switch (sp.stride) {
         case 2: UMGAP_SAMPLED(2); break;
         case 3: UMGAP_SAMPLED(3); break;
@@ -1171,6 +1208,13 @@ static void launch_sampled(const umgap_index* idx, const SampledPlan& sp, const 
 #undef UMGAP_SAMPLED
     UMGAP_CUDA(cudaGetLastError());
     ++g_launch_count;
+    // the reads the kernel queued (longer than a warp batch; rare): every position, plain kernel over the list
+    ReadList rl;
+    rl.list = sp.long_list;
+    rl.count = sp.long_count + slice;
+    rl.group_off = group_off_dev;
+    rl.g_lo = g_lo;
+    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, rl, false);
 }
 
 // Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
@@ -1179,7 +1223,7 @@ static void launch_sampled(const umgap_index* idx, const SampledPlan& sp, const 
 // pre-pass and the plain kernel over the reads longer than a warp batch (rare; it skips everything else).
 static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
                                    const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
-                                   uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
+                                   uint8_t* frame_hits_dev, cudaStream_t st, int buf, bool defer_prepass) {
     static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
     SampledPlan sp;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
@@ -1193,11 +1237,11 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
     make_code_lut(idx, o->table, o->methionine, lut);
     sp.rev_off = (total_nt + 15) / 16 * 16 + 16;
     sp.codes = (uint8_t*)idx->ws.get(WS_CODES + buf, 2 * sp.rev_off);
-    const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(total_nt, 16), 256) + 1, 148ull * 16);
-    translate_codes_kernel<<<tblocks, 256, 0, st>>>(lut, nt_dev, total_nt, sp.codes, sp.rev_off);
-    UMGAP_CUDA(cudaGetLastError());
-    ++g_launch_count;
-    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, (uint32_t)kSSpan, false);
+    sp.lut = lut;
+    sp.long_count = (uint32_t*)idx->ws.get(WS_LONG + buf, (64 + nreads) * sizeof(uint32_t));
+    sp.long_list = sp.long_count + 64;
+    UMGAP_CUDA(cudaMemsetAsync(sp.long_count, 0, 64 * sizeof(uint32_t), st));
+    if (!defer_prepass) launch_codes(sp, nt_dev, total_nt, total_nt, nullptr, nullptr, 0, 0, st);
     return sp;
 }
 
@@ -1207,17 +1251,18 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
                             uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st, int buf = 0,
                             bool sliced = false) {
     if (!ngroups) return;
+    const int kSlices = g_slices;
+    const bool slice_it = sliced && kSlices >= 2 && ngroups >= 4096u * (uint64_t)kSlices && nreads;
     LaunchTimer timer(0, st);
-    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
+    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf, slice_it);
     if (!sp.stride) {
         timer.cancel();  // the plain launch brackets itself
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
         launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
         return;
     }
-    const int kSlices = g_slices;
-    if (!sliced || kSlices < 2 || ngroups < 4096u * (uint64_t)kSlices || !nreads) {
-        if (nreads) launch_sampled(idx, sp, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, st);
+    if (!slice_it) {
+        if (nreads) launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, 0, st);
         timer.stop();
         launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
         return;
@@ -1243,7 +1288,9 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
         cudaStream_t s = idx->aux_stream[sl & 1];
         {
             LaunchTimer t2(0, s);
-            launch_sampled(idx, sp, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev, g_lo, g_hi, s);
+            launch_codes(sp, nt_dev, total_nt, ceil_div(total_nt, kSlices), read_off_dev, group_off_dev, g_lo, g_hi, s);
+            launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev,
+                           g_lo, g_hi, sl, s);
             t2.stop();
         }
         launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, g_lo, g_hi, frame_hits_dev, scratch_dev, out_dev, err, s);
