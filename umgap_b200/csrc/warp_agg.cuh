@@ -341,6 +341,78 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     return agg_finish(tv, A, P, L, m, running, ap, lane);
 }
 
+// LCA of dense x <= y: the deepest depth at which the two rows of the ancestor matrix agree (rows are padded
+// with kNoTaxon past the node's own depth); one round of two independent loads per 32 depths.  Also returns
+// that depth (undefined when x == y).  All lanes must call.
+__device__ __forceinline__ uint32_t warp_lca_rows(const TaxView& t, uint32_t x, uint32_t y, int lane, uint32_t& depth) {
+    depth = 0;
+    if (x == y) return x;
+    uint32_t best = 0;  // the root (dense 0, depth 0) is on every path
+    for (uint32_t base = 0; base < t.stride; base += 32) {
+        const uint32_t d = base + lane;
+        uint32_t ax = kNoTaxon, ay = kNoTaxon;
+        if (d < t.stride) {
+            ax = __ldg(t.anc + (uint64_t)x * t.stride + d);
+            ay = __ldg(t.anc + (uint64_t)y * t.stride + d);
+        }
+        const unsigned same = __ballot_sync(0xffffffffu, ax == ay && ax != kNoTaxon);
+        if (same) {
+            const int top = 31 - __clz(same);
+            best = __shfl_sync(0xffffffffu, ax, top);
+            depth = base + (uint32_t)top;
+        }
+        if (same != 0xffffffffu) break;  // the paths agree on a prefix of depths only
+    }
+    return best;
+}
+
+// The strategies LCA* and hybrid on m <= 32 sorted distinct kept members held one per lane (lane j < m: dense
+// index a, subtree end l = last[a], p0 = exclusive prefix of the counts; lanes >= m: a = kNoTaxon, p0 = running).
+// Same results as agg_finish; a level of the hybrid descent is one parallel step: every member loads its ancestor
+// one below the base, equal neighbours form the child ranges, their sums come from the prefix, a warp arg-max picks
+// the first heaviest child.  All lanes must call.
+__device__ __forceinline__ uint32_t agg_finish32(const TaxView& tv, uint32_t a, uint32_t l, uint32_t p0, uint32_t m,
+                                                 uint32_t running, const AggParams& ap, int lane) {
+    const unsigned all = m >= 32 ? 0xffffffffu : (1u << m) - 1;
+    const uint32_t a_next = __shfl_down_sync(0xffffffffu, a, 1);
+    // member j is a leaf of the induced tree iff the next member lies outside its subtree; the last member of any
+    // child range is one (what follows it belongs to another child)
+    const unsigned leaves = __ballot_sync(0xffffffffu, (uint32_t)lane < m && ((uint32_t)lane + 1 == m || a_next > l));
+    uint32_t base_depth = 0;
+    auto lca_star = [&](unsigned range) -> uint32_t {  // LCA(first leaf, last member) of a contiguous member range
+        const int first_leaf = __ffs((int)(leaves & range)) - 1, last = 31 - __clz(range);
+        return warp_lca_rows(tv, __shfl_sync(0xffffffffu, a, first_leaf), __shfl_sync(0xffffffffu, a, last), lane, base_depth);
+    };
+    uint32_t base_node = lca_star(all);
+    if (ap.strategy == UMGAP_AGG_HYBRID) {
+        unsigned range = all;   // members inside the subtree of the current base's range
+        uint32_t hi = m, bval = running;
+        for (;;) {
+            // the members below the base: inside the range, not an ancestor of the base, not the base itself
+            const bool below = (range >> lane & 1u) && a > base_node;
+            const unsigned cmask = __ballot_sync(0xffffffffu, below);
+            if (!cmask) break;  // no children: stop (tree/mix.rs:51)
+            const uint32_t ch = below ? __ldg(tv.anc + (uint64_t)a * tv.stride + base_depth + 1) : kNoTaxon;
+            const uint32_t ch_prev = __shfl_up_sync(0xffffffffu, ch, 1);
+            const bool head = below && (lane == __ffs((int)cmask) - 1 || ch != ch_prev);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1);
+            const uint32_t end = above ? (uint32_t)__ffs((int)above) - 1 : hi;  // one past the child's last member
+            const uint32_t p_end = __shfl_sync(0xffffffffu, p0, end & 31);
+            const uint32_t sub = head ? (end < 32 ? p_end : running) - p0 : 0u;
+            const uint32_t best = __reduce_max_sync(0xffffffffu, sub);
+            if (__fdiv_rn((float)best, (float)bval) < ap.factor) break;  // tree/mix.rs:57
+            const int bl = __ffs((int)__ballot_sync(0xffffffffu, head && sub == best)) - 1;  // first maximal child in preorder
+            const uint32_t best_hi = __shfl_sync(0xffffffffu, end, bl);
+            range = (best_hi >= 32 ? 0xffffffffu : (1u << best_hi) - 1) & ~((1u << bl) - 1);
+            base_node = lca_star(range);
+            bval = best;
+            hi = best_hi;
+        }
+    }
+    return ap.ranked_only ? __ldg(tv.snap_ranked + base_node) : __ldg(tv.snap_valid + base_node);
+}
+
 // Register-resident ascending bitonic sort of one (key, payload) pair per lane.
 __device__ __forceinline__ void warp_sort32(uint32_t& d, uint32_t& c, int lane) {
 #pragma unroll
@@ -390,7 +462,11 @@ __device__ __forceinline__ uint32_t warp_aggregate_distinct(const TaxView& tv, u
     }
     if (lane == 0) P[m] = running;
     __syncwarp();
-    return agg_finish(tv, A, P, L, m, running, ap, lane);
+    if (ap.strategy == UMGAP_AGG_MRTL) return agg_finish(tv, A, P, L, m, running, ap, lane);
+    // member j to lane j: dense index, subtree end, exclusive prefix of the counts (P[m] = running beyond the members)
+    const bool mem = (uint32_t)lane < m;
+    const uint32_t a = mem ? A[lane] : kNoTaxon, l = mem ? L[lane] : 0u, p0 = mem ? P[lane] : running;
+    return agg_finish32(tv, a, l, p0, m, running, ap, lane);
 }
 
 }  // namespace umgap
