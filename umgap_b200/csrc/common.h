@@ -59,7 +59,7 @@ void use_device(int device);  // cudaSetDevice with a clear error when no GPU is
 
 // Grow-only device scratch, one buffer per slot; freed with the owning handle.
 struct Workspace {
-    static const int kSlots = 30;
+    static const int kSlots = 56;
     void* ptr[kSlots] = {};
     size_t cap[kSlots] = {};
     void* get(int slot, size_t bytes);

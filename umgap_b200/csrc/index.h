@@ -64,6 +64,9 @@ struct umgap_index {
     // two internal streams + events of the sliced device path (pipeline.cu), created on first use
     mutable cudaStream_t aux_stream[2] = {};
     mutable cudaEvent_t aux_fork = nullptr, aux_join[2] = {};
+    // streams + events of the chunked host-buffer path
+    mutable cudaStream_t chunk_stream[6] = {};
+    mutable cudaEvent_t chunk_done[6] = {};
 
     umgap::TableView view() const {
         umgap::TableView v{};

@@ -1037,7 +1037,11 @@ __global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_
 using namespace umgap;
 
 // ---- workspace slots of an index handle --------------------------------------------------------
-enum { WS_ERR = 2, WS_NT = 3, WS_ROFF = 6, WS_GOFF = 9, WS_OUT = 12, WS_HITS = 15, WS_CODES = 18, WS_IDS = 21, WS_SCRATCH = 24, WS_LONG = 27 };  // x3 buffers each
+constexpr int kMaxBufs = 6;  // chunk streams of the host-buffer path, each with its own set of buffers
+enum { WS_ERR = 0, WS_NT = 1, WS_ROFF = WS_NT + kMaxBufs, WS_GOFF = WS_ROFF + kMaxBufs, WS_OUT = WS_GOFF + kMaxBufs, WS_HITS = WS_OUT + kMaxBufs,
+       WS_CODES = WS_HITS + kMaxBufs, WS_IDS = WS_CODES + kMaxBufs, WS_SCRATCH = WS_IDS + kMaxBufs, WS_LONG = WS_SCRATCH + kMaxBufs,
+       WS_END = WS_LONG + kMaxBufs };
+static_assert(WS_END <= Workspace::kSlots, "workspace slots");
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
     ClassifyParams cp{};
@@ -1437,19 +1441,24 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
         // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
         // nucleotides and offsets of the next chunks upload and the results of the previous one
         // download.  Offsets are uploaded as given and rebased on the device.
-        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 6..96 MiB: gpurun_out/e2e_probe*.log; UMGAP_CHUNK_MB overrides)
+        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 6..96 MiB x 3..6 streams: profiles/r01_e2e_chunk_sweep.log; UMGAP_CHUNK_MB overrides)
             const char* e = getenv("UMGAP_CHUNK_MB");
             const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
-            return (mb ? mb : 24ull) << 20;
+            return (mb ? mb : 16ull) << 20;
         }();
-        constexpr int kBufs = 3;
-        cudaStream_t st[kBufs];
-        cudaEvent_t done[kBufs];
+        static const int kBufs = [] {  // chunks in flight (streams); UMGAP_CHUNK_STREAMS overrides
+            const char* e = getenv("UMGAP_CHUNK_STREAMS");
+            const int v = e ? atoi(e) : 0;
+            return v > 0 ? std::min(v, kMaxBufs) : 4;
+        }();
         static const bool ordered = getenv("UMGAP_CHUNK_ORDERED") != nullptr;
-        for (int i = 0; i < kBufs; ++i) {
-            UMGAP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-            UMGAP_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        }
+        if (!idx->chunk_stream[0])
+            for (int i = 0; i < kMaxBufs; ++i) {
+                UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->chunk_stream[i], cudaStreamNonBlocking));
+                UMGAP_CUDA(cudaEventCreateWithFlags(&idx->chunk_done[i], cudaEventDisableTiming));
+            }
+        cudaStream_t* st = idx->chunk_stream;
+        cudaEvent_t* done = idx->chunk_done;
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
         // nucleotides before group g (monotone in g): chunk ends are found by bisection
@@ -1500,10 +1509,6 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
             for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
             DevError he;
             UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < kBufs; ++i) {
-                cudaStreamDestroy(st[i]);
-                cudaEventDestroy(done[i]);
-            }
             raise_dev_error(he);
         } catch (...) {
             cudaDeviceSynchronize();

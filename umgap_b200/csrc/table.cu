@@ -461,6 +461,10 @@ void umgap_index_free(umgap_index* idx) {
         if (idx->aux_join[i]) cudaEventDestroy(idx->aux_join[i]);
     }
     if (idx->aux_fork) cudaEventDestroy(idx->aux_fork);
+    for (int i = 0; i < 6; ++i) {
+        if (idx->chunk_stream[i]) cudaStreamDestroy(idx->chunk_stream[i]);
+        if (idx->chunk_done[i]) cudaEventDestroy(idx->chunk_done[i]);
+    }
     delete idx;
 }
 
