@@ -32,4 +32,4 @@ for _ in range(n):
     capi.classify_reads(gidx, gtax, opts, nt_np, h_roff, h_goff, count_lookups=False, out=h_out)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
-print(f"e2e {os.environ.get('UMGAP_CHUNK_MB','48')} MB chunks ordered={os.environ.get('UMGAP_CHUNK_ORDERED','0')}: {dt*1e3:.3f} ms per call  {2*npairs/dt/1e6:.1f} M reads/s  checksum {int(h_out.astype(np.uint64).sum())}", flush=True)
+print(f"e2e {os.environ.get('UMGAP_CHUNK_MB','default')} MB chunks ordered={os.environ.get('UMGAP_CHUNK_ORDERED','0')}: {dt*1e3:.3f} ms per call  {2*npairs/dt/1e6:.1f} M reads/s  checksum {int(h_out.astype(np.uint64).sum())}", flush=True)

@@ -329,8 +329,19 @@ __global__ void __launch_bounds__(256)
 translate_codes_kernel(const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt, uint64_t total_nt,
                        uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
                        const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi) {
-    __shared__ uint8_t s_lut[72];
-    if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
+    // s_pair[i] = forward residue | reverse residue << 8 of the codon with index i = 16 a + 4 b + c in A,C,G,T order
+    // (complement = 3 - code); [64] = a codon holding an N.  lut.v is in T,C,A,G order (translation.rs:20).
+    __shared__ uint16_t s_pair[65];
+    if (threadIdx.x < 65) {
+        const uint32_t i = threadIdx.x;
+        if (i == 64) {
+            s_pair[64] = (uint16_t)(lut.v[64] | (uint32_t)lut.v[64] << 8);
+        } else {
+            const uint32_t tcag = 0x0312u;  // nibble k = T,C,A,G index of A,C,G,T code k: A->2, C->1, G->3, T->0
+            const uint32_t a = (tcag >> (4 * (i >> 4))) & 3u, bb = (tcag >> (4 * ((i >> 2) & 3u))) & 3u, c = (tcag >> (4 * (i & 3u))) & 3u;
+            s_pair[i] = (uint16_t)(lut.v[16 * a + 4 * bb + c] | (uint32_t)lut.v[16 * (c ^ 2) + 4 * (bb ^ 2) + (a ^ 2)] << 8);
+        }
+    }
     __syncthreads();
     // all nucleotides, or (slices of the device path) those of groups [g_lo, g_hi); a 16-byte chunk that straddles two
     // slices is written by both with the same bytes
@@ -355,16 +366,29 @@ translate_codes_kernel(const __grid_constant__ CodonLut lut, const uint8_t* __re
                 }
             }
         }
-        uint32_t c[18];
+        // four bytes at a time: code = ((x >> 1) ^ (x >> 2)) & 3 maps A,C,G,T to 0,1,2,3; a byte is one of those four
+        // letters iff the letter of its code equals it (anything else, lowercase included, is N: dna/mod.rs:34-44);
+        // N sets bit 2 of the byte's code
 #pragma unroll
-        for (int i = 0; i < 18; ++i) c[i] = nt_code((uint8_t)(w[i >> 2] >> (8 * (i & 3))));
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t x = w[i];
+            const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+            const uint32_t sel = (t & 0xFu) | ((t >> 4) & 0xF0u) | ((t >> 8) & 0xF00u) | ((t >> 12) & 0xF000u);
+            const uint32_t diff = __byte_perm(0x54474341u, 0u, sel) ^ x;  // "ACGT"[code] against the byte
+            const uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;  // 0x80 in every differing byte
+            w[i] = t | (nz >> 5);
+        }
         uint32_t fo[4] = {0, 0, 0, 0}, ro[4] = {0, 0, 0, 0};
+        uint32_t idx = ((w[0] & 3u) << 2) | ((w[0] >> 8) & 3u);            // codon index so far: codes 0 and 1
+        uint32_t nm = ((w[0] >> 2) & 1u) << 1 | ((w[0] >> 10) & 1u);        // their N flags
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const uint32_t a = c[i], b = c[i + 1], d = c[i + 2];
-            const bool has_n = ((a | b | d) & 4u) != 0;
-            fo[i >> 2] |= (uint32_t)s_lut[has_n ? 64 : 16 * a + 4 * b + d] << (8 * (i & 3));
-            ro[i >> 2] |= (uint32_t)s_lut[has_n ? 64 : 16 * (d ^ 2) + 4 * (b ^ 2) + (a ^ 2)] << (8 * (i & 3));
+            const uint32_t c = (w[(i + 2) >> 2] >> (8 * ((i + 2) & 3))) & 7u;
+            idx = ((idx << 2) | (c & 3u)) & 63u;
+            nm = ((nm << 1) | (c >> 2)) & 7u;
+            const uint32_t pr = s_pair[nm ? 64u : idx];
+            fo[i >> 2] |= (pr & 0xFFu) << (8 * (i & 3));
+            ro[i >> 2] |= (pr >> 8) << (8 * (i & 3));
         }
         *reinterpret_cast<uint4*>(codes + x0) = make_uint4(fo[0], fo[1], fo[2], fo[3]);
         *reinterpret_cast<uint4*>(codes + rev_off + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
