@@ -24,7 +24,7 @@ roff = (torch.arange(0, npairs * 2 + 1, dtype=torch.int64, device="cuda") * L)
 goff = torch.arange(0, npairs * 2 + 1, 2, dtype=torch.int64, device="cuda")
 out = torch.zeros(npairs, dtype=torch.int32, device="cuda")
 ids = torch.empty(2 * npairs * 2 * L + 64, dtype=torch.int32, device="cuda")
-opts = capi.default_opts(min_seed_size=3, strategy=1)
+opts = capi.default_opts(min_seed_size=int(os.environ.get("PROBE_SEED", "3")), max_gap_size=int(os.environ.get("PROBE_GAP", "0")), strategy=int(os.environ.get("PROBE_STRATEGY", "1")))
 st = torch.cuda.current_stream().cuda_stream
 def timeit(f, n=5):
     for _ in range(2): f()

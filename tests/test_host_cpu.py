@@ -149,3 +149,83 @@ def test_partitioned_classification_two_gloo_ranks(tmp_path):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err.decode()[-2000:]
         assert out.decode().strip() == f"ok {r}"
+
+
+def test_seedextend_closed_form():
+    """The classify kernel runs seedextend in closed form on bit masks (pipeline.cu: seedextend_frame): ranges =
+    stretches between gaps longer than -g, selected iff they hold -s equal consecutive non-zero ids, plus the machine's
+    one irregularity (a record that begins with 1..g zeros loses its first non-zero id).  This is the same closed form in
+    Python against the line-by-line restatement of seedextend.rs:94-149 on random lists."""
+    import random
+    from collections import Counter
+    from oracle.seedextend import seedextend
+    M64 = (1 << 64) - 1
+
+    def ffs(x):
+        return (x & -x).bit_length()
+
+    def closed_form(ids, S, G):
+        cnt = len(ids)
+        nz = eq = 0
+        prev = None
+        for i, v in enumerate(ids):
+            if v != 0:
+                nz |= 1 << i
+            if prev is not None and v == prev:
+                eq |= 1 << i
+            prev = v
+        if not nz:
+            return Counter()
+        valid = (1 << cnt) - 1
+        inr = nz
+        if G:
+            g_eff = min(G, 63)
+            z = ffs(nz) - 1
+            if 1 <= z <= g_eff:
+                above = ~((2 << z) - 1) & M64
+                nz &= above
+                valid &= above
+                eq &= above & ~(1 << (z + 1))
+            zero = ~nz & valid
+            lng = zero
+            g = 1
+            while g <= g_eff and lng:
+                lng &= zero >> g
+                g += 1
+            cover = lng
+            for g in range(1, g_eff + 1):
+                cover |= (lng << g) & M64
+            inr = valid & ~cover
+        seed = nz & eq
+        k = 1
+        while k + 1 < S and seed:
+            seed &= (eq << k) & M64
+            k += 1
+        kept = 0
+        while seed:
+            sp = ffs(seed) - 1
+            up = (((inr + (1 << sp)) & M64) ^ inr) & inr
+            below = ~inr & ((1 << sp) - 1)
+            first = below.bit_length() if below else 0
+            rng_ = up | (((1 << sp) - 1) & ~((1 << first) - 1))
+            kept |= rng_
+            seed &= ~rng_
+        out = Counter()
+        ends = ~(kept & nz & eq) & M64
+        heads = kept & nz & ~eq
+        while heads:
+            hp = ffs(heads) - 1
+            heads &= heads - 1
+            out[ids[hp]] += ffs(ends >> (hp + 1))
+        return out
+
+    rnd = random.Random(5)
+    for _ in range(30000):
+        cnt = rnd.choice([1, 2, 3, 5, 8, 13, 21, 33, 41, 42, 63])
+        alpha = rnd.choice([2, 3, 4])
+        pz = rnd.choice([0.1, 0.3, 0.5, 0.8])
+        ids = [0 if rnd.random() < pz else rnd.randrange(1, alpha + 1) for _ in range(cnt)]
+        S = rnd.choice([2, 2, 3, 3, 4, 5, 7])
+        G = rnd.choice([0, 1, 1, 2, 3, 5, 70])
+        want = Counter(x for x in seedextend(ids, S, G) if x != 0)
+        assert closed_form(ids, S, G) == want, (ids, S, G)

@@ -732,12 +732,15 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
     const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + f;
     // private slice of this record: pair i at words 6i, 6i+1 past 2*(strand*n + f), inside the read's 4n words
     uint32_t* priv = read_priv + 2 * ((fr >= 3 ? n : 0) + f);
-    if (cp.seedextend && cp.one_on_one && cp.max_gap == 0 && cp.min_seed >= 2 && cnt <= 63) {
-        // -g 0: every zero ends a range (seedextend.rs:116-127 fires for any gap, same >= 1 > 0), so the
-        // ranges are the maximal zero-free stretches, and a stretch is selected iff it holds min_seed equal
-        // consecutive ids (:137-149).  On bit masks, one record per lane, no per-element state machine:
-        // nz = id != 0, eq = id equals its predecessor; a seed ends where min_seed - 1 consecutive eq bits meet
-        // nz; the kept ids leave as (id, run length) for each run of the stretches that hold a seed.
+    if (cp.seedextend && cp.one_on_one && cp.min_seed >= 2 && cnt <= 63) {
+        // The seedextend machine (seedextend.rs:101-149) in closed form on bit masks, one record per lane, no
+        // per-element state: a gap of more than max_gap zeros ends a range (:116-127), shorter gaps stay inside it,
+        // so the ranges are the stretches between long gaps; a range is selected iff it holds min_seed equal
+        // consecutive non-zero ids (:137-149; any zero breaks a run).  The one irregularity of the machine: a record
+        // that BEGINS with 1..max_gap zeros loses its first non-zero id (:130-134 moves the range start past t[end]
+        // without making it `last`), after which everything restarts behind that id.  (Checked against the
+        // line-by-line restatement on random lists: tests/test_host_cpu.py::test_seedextend_closed_form.)
+        // nz = id != 0, eq = id equals its predecessor; the kept ids leave as (id, run length).
         uint32_t nz_lo = 0, eq_lo = 0, nz_hi = 0, eq_hi = 0, prev = kNoValue;
         const uint32_t c_lo = cnt < 32 ? cnt : 32;
 #pragma unroll 4
@@ -756,21 +759,40 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
             eq_hi |= (uint32_t)(v == prev) << (i - 32);
             prev = v;
         }
-        const uint64_t nz = (uint64_t)nz_hi << 32 | nz_lo, eq = (uint64_t)eq_hi << 32 | eq_lo;
+        uint64_t nz = (uint64_t)nz_hi << 32 | nz_lo, eq = (uint64_t)eq_hi << 32 | eq_lo;
+        if (!nz) return true;
+        uint64_t inr = nz;  // positions inside a range
+        if (cp.max_gap) {
+            const uint32_t G = cp.max_gap < 63 ? cp.max_gap : 63;
+            uint64_t valid = (1ull << cnt) - 1;
+            const uint32_t z = (uint32_t)__ffsll((long long)nz) - 1;  // leading zeros
+            if (z >= 1 && z <= G) {  // the record starts with a short gap: positions 0..z vanish, a fresh run starts at z + 1
+                const uint64_t above = ~((2ull << z) - 1);
+                nz &= above;
+                valid &= above;
+                eq &= above & ~(1ull << (z + 1));
+            }
+            const uint64_t zero = ~nz & valid;
+            uint64_t lng = zero;  // first positions of G + 1 consecutive zeros ...
+            for (uint32_t g = 1; g <= G && lng; ++g) lng &= zero >> g;
+            uint64_t cover = lng;  // ... and every position of such a gap
+            for (uint32_t g = 1; g <= G; ++g) cover |= lng << g;
+            inr = valid & ~cover;
+        }
         uint64_t seed = nz & eq;
         for (uint32_t k = 1; k + 1 < cp.min_seed && seed; ++k) seed &= eq << k;
         uint64_t kept = 0;
-        while (seed) {  // the stretch around the lowest remaining seed
+        while (seed) {  // the range around the lowest remaining seed
             const uint32_t sp = (uint32_t)__ffsll((long long)seed) - 1;
-            const uint64_t up = ((nz + (1ull << sp)) ^ nz) & nz;            // from the seed to the stretch's last id
-            const uint64_t zeros_below = ~nz & ((1ull << sp) - 1);
-            const uint32_t first = zeros_below ? 64u - (uint32_t)__clzll((long long)zeros_below) : 0u;
-            const uint64_t stretch = up | (((1ull << sp) - 1) & ~((1ull << first) - 1));
-            kept |= stretch;
-            seed &= ~stretch;
+            const uint64_t up = ((inr + (1ull << sp)) ^ inr) & inr;          // from the seed to the range's last position
+            const uint64_t out_below = ~inr & ((1ull << sp) - 1);
+            const uint32_t first = out_below ? 64u - (uint32_t)__clzll((long long)out_below) : 0u;
+            const uint64_t range = up | (((1ull << sp) - 1) & ~((1ull << first) - 1));
+            kept |= range;
+            seed &= ~range;
         }
-        const uint64_t ends = (kept & ~eq) | ~kept;  // run heads, and everything outside the kept stretches (bit 63 included)
-        uint64_t heads = kept & ~eq;
+        const uint64_t ends = ~(kept & nz & eq);  // where a run of equal kept ids stops (bit 63 included)
+        uint64_t heads = kept & nz & ~eq;
         while (heads) {
             const uint32_t hp = (uint32_t)__ffsll((long long)heads) - 1;
             heads &= heads - 1;
