@@ -252,6 +252,9 @@ int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* cla
  * umgap_classify_ids_dev) has launched in this process; the lookup stage is up to three launches
  * (residue-code pre-pass, sampled lookup kernel, long-read pass).                                  */
 int umgap_kernel_launch_count(uint64_t* launches);
+/* Bytes umgap_classify_reads has copied host -> device and device -> host in this process (offset arrays
+ * that are arithmetic progressions are regenerated on the device instead of being uploaded).        */
+int umgap_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 /* umgap_classify_reads_dev cuts a batch into `slices` group ranges whose lookup and classify kernels
  * alternate on two internal streams (they fill each other's tails); 1 = one lookup and one classify
  * launch on the caller's stream.  Returns the previous setting; slices <= 0 only queries.  Default 8

@@ -35,7 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
-    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_pipeline_slices",
+    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
 
@@ -402,6 +402,13 @@ def kernel_times():
 def pipeline_slices(slices: int = 0) -> int:
     """Sets (slices > 0) the number of slices of classify_reads_dev; returns the previous value."""
     return int(load_library().umgap_pipeline_slices(C.c_int(slices)))
+
+
+def transfer_bytes():
+    """(h2d, d2h) bytes classify_reads has moved over PCIe in this process so far."""
+    a, b = C.c_uint64(), C.c_uint64()
+    _check(load_library().umgap_transfer_bytes(C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def kernel_launch_count() -> int:

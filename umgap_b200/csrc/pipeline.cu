@@ -1071,11 +1071,14 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
     }
 }
 
-// Subtracts the chunk's first nucleotide / first read from uploaded offset slices.
-__global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_t* b, uint64_t nb, uint64_t base_b) {
+// Chunk-relative offset slices: an uploaded slice has the chunk's first nucleotide / first read subtracted; a slice the
+// host found to be an arithmetic progression (all reads of one length, all groups of one size) was not uploaded at all
+// and is written here (step != 0).
+__global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_t step_a, uint64_t* b, uint64_t nb,
+                              uint64_t base_b, uint64_t step_b) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) a[i] -= base_a;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] -= base_b;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) a[i] = step_a ? i * step_a : a[i] - base_a;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = step_b ? i * step_b : b[i] - base_b;
 }
 
 }  // namespace umgap
@@ -1115,6 +1118,7 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
 // ---- optional per-launch timing (umgap_kernel_timing), shared with route.cu -----------------------
 namespace umgap {
 static uint64_t g_launch_count = 0;  // kernels launched by the fused path
+static uint64_t g_h2d_bytes = 0, g_d2h_bytes = 0;  // bytes umgap_classify_reads moved over PCIe
 static int g_slices = [] {           // slices of the device-buffer entry point (umgap_pipeline_slices)
     const char* e = getenv("UMGAP_SLICES");
     const int v = e ? atoi(e) : 0;
@@ -1351,6 +1355,21 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
     }
 }
 
+// Common difference of off[0..n] when it is an arithmetic progression with a non-zero step, else 0.
+static uint64_t uniform_step(const uint64_t* off, uint64_t n) {
+    static const bool disabled = getenv("UMGAP_UPLOAD_OFFSETS") != nullptr;
+    if (n == 0 || disabled) return 0;
+    const uint64_t step = off[1] - off[0];
+    if (!step || off[n] - off[0] != n * step) return 0;
+    for (uint64_t i0 = 1; i0 < n; i0 += 4096) {  // blockwise so that the inner loop vectorises
+        const uint64_t i1 = std::min(n, i0 + 4096);
+        uint64_t bad = 0;
+        for (uint64_t i = i0; i < i1; ++i) bad |= (off[i + 1] - off[i]) ^ step;
+        if (bad) return 0;
+    }
+    return step;
+}
+
 static void raise_dev_error(const DevError& e) {
     if (e.flag) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", e.taxon);
 }
@@ -1368,6 +1387,12 @@ int umgap_pipeline_slices(int slices) {
     const int before = g_slices;
     if (slices > 0) g_slices = std::min(slices, 64);
     return before;
+}
+
+int umgap_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = g_h2d_bytes;
+    if (d2h) *d2h = g_d2h_bytes;
+    return UMGAP_OK;
 }
 
 int umgap_kernel_launch_count(uint64_t* launches) {
@@ -1538,9 +1563,13 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                 uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH + buf, (12 * cap_nt + 64) * 4);
                 cudaStream_t s = st[buf];
                 UMGAP_CUDA(cudaMemcpyAsync(d_nt, nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
-                UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
-                UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
-                rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, d_goff, cnt_g + 1, r0);
+                // offsets that form an arithmetic progression (the usual case: reads of one length, pairs) stay on the host
+                const uint64_t step_r = uniform_step(read_off + r0, cnt_r), step_g = uniform_step(group_off + g0, cnt_g);
+                if (!step_r) UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
+                if (!step_g) UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
+                g_h2d_bytes += cnt_nt + (step_r ? 0 : (cnt_r + 1) * 8) + (step_g ? 0 : (cnt_g + 1) * 8);
+                g_d2h_bytes += cnt_g * 4;
+                rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, step_r, d_goff, cnt_g + 1, r0, step_g);
                 UMGAP_CUDA(cudaGetLastError());
                 ++g_launch_count;
                 if (ordered && prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
