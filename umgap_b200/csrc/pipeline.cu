@@ -132,10 +132,20 @@ struct LookupSmem {
 // region_lo / region_hi: only k-mers whose hash prefix (h >> 13) lies in [region_lo, region_hi) are
 // looked up and written in this pass (tables beyond the GPU's address-translation reach are probed
 // one region at a time, see launch_translate_lookup); 0 / 2^32 selects everything.
+// Two layouts of a read's ids (2n words; a strand's k-mers in words [strand * n, strand * n + npos)):
+//   position-major  k-mer at coordinate y -> strand * n + y; frame f's record is the stride-3 subsequence from f;
+//   frame-major     the three frame records of a strand one after the other, each contiguous (behind the sampled
+//                   lookup kernel, which writes whole frame records: fewer partially written sectors).
+// Index of position j of frame f of a strand in the frame-major layout, relative to the strand's first word.
+__device__ __forceinline__ uint32_t frame_major_index(uint32_t n, uint32_t k, uint32_t f, uint32_t j) {
+    const uint32_t c0 = n / 3 - k + 1, c1 = (n - 1) / 3 - k + 1;  // positions of frames 0 and 1 (n >= 3k)
+    return (f > 0 ? c0 : 0u) + (f > 1 ? c1 : 0u) + j;
+}
+
 template <int K, class TV, bool REGION>
 __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
                                                 const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane,
-                                                uint64_t region_lo, uint64_t region_hi) {
+                                                uint64_t region_lo, uint64_t region_hi, bool frame_major = false) {
     constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
     const uint32_t npos = n - 3u * K + 1;
@@ -190,7 +200,8 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t p = w0 + lane + 32 * u;
-                const uint32_t pos = strand ? n + (npos - 1 - p) : p;
+                const uint32_t y = strand ? npos - 1 - p : p;
+                const uint32_t pos = (strand ? n : 0u) + (frame_major ? frame_major_index(n, K, y % 3, y / 3) : y);
                 bool more = false;
                 uint32_t v = kNoValue;
                 if (valid[u]) v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
@@ -236,7 +247,8 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
                         if (!more) {
                             const uint32_t p = w0 + ((uint32_t)(hq[j] >> 51) & 127u);
                             const uint32_t rev = (uint32_t)(hq[j] >> 50) & 1u;
-                            out[rev ? n + (npos - 1 - p) : p] = v;
+                            const uint32_t y = rev ? npos - 1 - p : p;
+                            out[(rev ? n : 0u) + (frame_major ? frame_major_index(n, K, y % 3, y / 3) : y)] = v;
                             if (v != kNoValue && v != 0) hitbits |= 1u << (rev * 3 + (rev ? npos - 1 - p : p) % 3);
                         }
                         next = (hq[j] & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
@@ -286,7 +298,8 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
-        if (n >= 3u * K) mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi);
+        if (n >= 3u * K)
+            mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi, list != nullptr);
         if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)(!REGION || region_lo == 0 ? mask : (mask | frame_hits[r]));
     }
 }
@@ -453,7 +466,7 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
     const uint32_t npos = n - 3u * K + 1;
     dir = sd ? -3 : 3;
     a0 = sd ? kSRevOff + ro + (npos - 1 - f) + 3u * (K - 1) : ro + f;
-    o0 = 2 * ro + sd * n + f;
+    o0 = 2 * ro + sd * n + frame_major_index(n, K, f, 0);
     return (npos - f + 2) / 3;  // positions y = f + 3j < npos
 }
 
@@ -604,7 +617,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
                         j = (item >> 5) * seg;
                         cnt = min(seg, n_pos - j);
                         a = a0 + dir * j;
-                        o = o0 + 3 * j;
+                        o = o0 + j;
                     }
                     uint64_t key = 0;
                     uint32_t bad = 0;
@@ -649,7 +662,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
                         for (int u = 0; u < 2; ++u) {
                             bool more = false;
                             if (valid[u]) v[u] = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-                            const uint32_t oi = o + 3 * (s0 + u);
+                            const uint32_t oi = o + s0 + u;
                             if (s0 + u < cnt && !more) out0[oi] = v[u];
                             const unsigned m = __ballot_sync(0xffffffffu, more);
                             if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)oi << 50);
@@ -667,6 +680,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
 
 // ---- classify: seedextend + uniq join + aggregate, one warp per group ----------------------------
 struct ClassifyParams {
+    int frame_major;  // layout of the ids (see frame_major_index): 1 behind the sampled lookup kernel
     int k;
     int one_on_one;
     int seedextend;
@@ -729,7 +743,8 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
     const uint32_t plen = n >= f ? (n - f) / 3 : 0;  // peptide length of the frame
     if (plen < (uint32_t)cp.k) return false;
     const uint32_t cnt = plen - cp.k + 1;
-    const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + f;
+    const uint32_t st = cp.frame_major ? 1u : 3u;  // distance of consecutive positions of the record
+    const uint32_t* base = read_ids + (fr >= 3 ? n : 0) + (cp.frame_major ? frame_major_index(n, (uint32_t)cp.k, f, 0) : f);
     // private slice of this record: pair i at words 6i, 6i+1 past 2*(strand*n + f), inside the read's 4n words
     uint32_t* priv = read_priv + 2 * ((fr >= 3 ? n : 0) + f);
     if (cp.seedextend && cp.one_on_one && cp.min_seed >= 2 && cnt <= 63) {
@@ -745,7 +760,7 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
         const uint32_t c_lo = cnt < 32 ? cnt : 32;
 #pragma unroll 4
         for (uint32_t i = 0; i < c_lo; ++i) {
-            uint32_t v = base[3 * i];
+            uint32_t v = base[st * i];
             v = v == kNoValue ? 0u : v;
             nz_lo |= (uint32_t)(v != 0) << i;
             eq_lo |= (uint32_t)(v == prev) << i;
@@ -753,7 +768,7 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
         }
 #pragma unroll 4
         for (uint32_t i = 32; i < cnt; ++i) {
-            uint32_t v = base[3 * i];
+            uint32_t v = base[st * i];
             v = v == kNoValue ? 0u : v;
             nz_hi |= (uint32_t)(v != 0) << (i - 32);
             eq_hi |= (uint32_t)(v == prev) << (i - 32);
@@ -796,7 +811,7 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
         while (heads) {
             const uint32_t hp = (uint32_t)__ffsll((long long)heads) - 1;
             heads &= heads - 1;
-            sink.add(base[3 * hp], (uint32_t)__ffsll((long long)(ends >> (hp + 1))));
+            sink.add(base[st * hp], (uint32_t)__ffsll((long long)(ends >> (hp + 1))));
         }
         return true;
     }
@@ -826,7 +841,7 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
             }
         };
         auto at = [&](uint32_t i) -> uint32_t {
-            const uint32_t v = base[3 * i];
+            const uint32_t v = base[st * i];
             return v == kNoValue ? 0u : v;
         };
         // The four cases of the reference loop body are evaluated as predicates so that the lanes of
@@ -869,10 +884,10 @@ __device__ __forceinline__ bool seedextend_frame(const ClassifyParams& cp, const
         }
     };
     if (cp.seedextend) {
-        seedextend_stream(base, 3, cnt, cp.one_on_one != 0, cp.min_seed, cp.max_gap, push);
+        seedextend_stream(base, st, cnt, cp.one_on_one != 0, cp.min_seed, cp.max_gap, push);
     } else {
         for (uint32_t i = 0; i < cnt; ++i) {
-            const uint32_t v = base[3 * i];
+            const uint32_t v = base[st * i];
             if (v != kNoValue) push(v);
         }
     }
@@ -1207,11 +1222,13 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
                             const umgap_pipeline_opts* o, const uint32_t* ids_dev,
                             const uint64_t* read_off_dev, const uint64_t* group_off_dev, uint64_t g_begin,
                             uint64_t g_end, const uint8_t* frame_hits_dev, uint32_t* scratch_dev, uint32_t* out_dev,
-                            DevError* err, cudaStream_t st) {
+                            DevError* err, cudaStream_t st, bool frame_major = false) {
     if (g_end <= g_begin) return;
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(g_end - g_begin, kAggSlots), kAggWarps), 148ull * 64);
     LaunchTimer timer(1, st);
-    classify_kernel<<<blocks, kAggWarps * 32, 0, st>>>(tax->view, make_params(idx, o), ids_dev,
+    ClassifyParams cp = make_params(idx, o);
+    cp.frame_major = frame_major ? 1 : 0;
+    classify_kernel<<<blocks, kAggWarps * 32, 0, st>>>(tax->view, cp, ids_dev,
                                                        read_off_dev, group_off_dev, g_begin, g_end,
                                                        frame_hits_dev, scratch_dev, out_dev, err);
     UMGAP_CUDA(cudaGetLastError());
@@ -1248,7 +1265,12 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
                            const uint64_t* read_off_dev, uint64_t nreads, uint64_t reads_hint, uint32_t* ids_dev,
                            uint8_t* frame_hits_dev, const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi, int slice,
                            cudaStream_t st) {
-    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, 148ull * kSBlocks * 4);
+    static const unsigned grid_cap = [] {  // CTAs of one launch (UMGAP_S_GRID = CTAs per SM, for measurements)
+        const char* e = getenv("UMGAP_S_GRID");
+        const int v = e ? atoi(e) : 0;
+        return 148u * (unsigned)(v > 0 ? v : kSBlocks * 4);
+    }();
+    const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, grid_cap);
 #define UMGAP_SAMPLED(S)                                                                                                     \
     lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.codes, sp.rev_off, read_off_dev,  \
                                                                            (uint32_t)nreads, ids_dev, frame_hits_dev,        \
@@ -1318,7 +1340,7 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
     if (!slice_it) {
         if (nreads) launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, 0, st);
         timer.stop();
-        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
+        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st, true);
         return;
     }
     // Sliced: the groups are cut into kSlices ranges; the lookup and classify kernels of a slice follow each other on
@@ -1347,7 +1369,7 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
                            g_lo, g_hi, sl, s);
             t2.stop();
         }
-        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, g_lo, g_hi, frame_hits_dev, scratch_dev, out_dev, err, s);
+        launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, g_lo, g_hi, frame_hits_dev, scratch_dev, out_dev, err, s, true);
     }
     for (int i = 0; i < 2; ++i) {
         UMGAP_CUDA(cudaEventRecord(idx->aux_join[i], idx->aux_stream[i]));
