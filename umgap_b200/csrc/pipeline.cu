@@ -316,14 +316,15 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
 // probed in a second phase of the same warp, and only these frames' ids are written.  Bit-identical
 // output, about 0.4 of the HBM line fills.
 //
-// Work layout: translate_codes_kernel first turns the nucleotides into the two residue-code arrays
-// (forward codon starting at x, reverse-strand codon whose lowest forward coordinate is x), streaming.
-// In the lookup kernel one warp takes a batch of up to kSReads = 5 consecutive reads (<= kSSpan
-// nucleotides; 30 frame records), copies their code spans to shared memory with 16-byte loads, and every
-// LANE walks one frame record: the 9-residue key rolls from one position to the next (one shared-memory
-// byte per residue), two lookups in flight per lane.  The answers of a record's first kSValRows sampled
-// positions stay in shared memory for the second phase.  A read longer than kSSpan is left to the plain
-// kernel.
+// Work layout: one warp takes a batch of up to kSReads = 5 consecutive reads (<= kSSpan nucleotides; 30
+// frame records).  It translates the batch itself, 16 nucleotides per lane and step, four bytes per
+// instruction, into two residue-code arrays in shared memory (forward codon starting at x, reverse-strand
+// codon whose lowest forward coordinate is x).  Then every LANE walks one frame record: the 9-residue key
+// rolls from one position to the next (one shared-memory byte per residue), two lookups in flight per
+// lane.  The answers of a record's first kSValRows sampled positions stay in shared memory for the second
+// phase.  A read longer than kSSpan is queued for the plain kernel.  (A streaming pre-pass kernel that
+// left the residue codes in HBM was measured: 5.86 vs 5.49 ms per step -- 1.4 GB of extra DRAM traffic
+// and a launch per slice.)
 #ifndef UMGAP_S_BLOCKS
 #define UMGAP_S_BLOCKS 7
 #endif
@@ -336,75 +337,49 @@ constexpr int kSItems = 32 + 6 * kSReads;
 constexpr int kSValRows = 16;
 static_assert(6 * kSReads <= 32, "one lane per frame record of a batch");
 
-// nt -> residue codes of both strands, 16 positions per thread.  codes[x] = forward, codes[rev_off + x] =
-// reverse.  A codon that runs past total_nt holds N; codons that straddle two reads are never used.
-__global__ void __launch_bounds__(256)
-translate_codes_kernel(const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt, uint64_t total_nt,
-                       uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
-                       const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi) {
-    // s_pair[i] = forward residue | reverse residue << 8 of the codon with index i = 16 a + 4 b + c in A,C,G,T order
-    // (complement = 3 - code); [64] = a codon holding an N.  lut.v is in T,C,A,G order (translation.rs:20).
-    __shared__ uint16_t s_pair[65];
+// Residue codes of the 16 codon starts of one chunk, both strands: w[0..4] = its 16 nucleotide bytes plus the 4 that
+// follow (two are needed).  Four bytes at a time: code = ((x >> 1) ^ (x >> 2)) & 3 maps A,C,G,T to 0,1,2,3; a byte is
+// one of those letters iff the letter of its code equals it (anything else, lowercase included, is N: dna/mod.rs:34-44),
+// N sets bit 2 of the byte's code.  The codon index rolls from one start to the next; pair[] holds the forward and the
+// reverse-strand residue of each codon (see fill_pair_lut).
+__device__ __forceinline__ void translate_chunk16(uint32_t (&w)[5], const uint16_t* pair, uint32_t (&fo)[4], uint32_t (&ro)[4]) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t x = w[i];
+        const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+        const uint32_t sel = (t & 0xFu) | ((t >> 4) & 0xF0u) | ((t >> 8) & 0xF00u) | ((t >> 12) & 0xF000u);
+        const uint32_t diff = __byte_perm(0x54474341u, 0u, sel) ^ x;  // "ACGT"[code] against the byte
+        const uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;  // 0x80 in every differing byte
+        w[i] = t | (nz >> 5);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fo[i] = ro[i] = 0;
+    uint32_t idx = ((w[0] & 3u) << 2) | ((w[0] >> 8) & 3u);            // codon index so far: codes 0 and 1
+    uint32_t nm = ((w[0] >> 2) & 1u) << 1 | ((w[0] >> 10) & 1u);        // their N flags
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t c = (w[(i + 2) >> 2] >> (8 * ((i + 2) & 3))) & 7u;
+        idx = ((idx << 2) | (c & 3u)) & 63u;
+        nm = ((nm << 1) | (c >> 2)) & 7u;
+        const uint32_t pr = pair[nm ? 64u : idx];
+        fo[i >> 2] |= (pr & 0xFFu) << (8 * (i & 3));
+        ro[i >> 2] |= (pr >> 8) << (8 * (i & 3));
+    }
+}
+
+// pair[i] = forward residue | reverse residue << 8 of the codon with index i = 16 a + 4 b + c in A,C,G,T order
+// (complement = 3 - code); [64] = a codon holding an N.  lut.v is in T,C,A,G order (translation.rs:20).  Threads
+// 0..64 of the CTA fill it; the caller synchronises.
+__device__ __forceinline__ void fill_pair_lut(const CodonLut& lut, uint16_t* pair) {
     if (threadIdx.x < 65) {
         const uint32_t i = threadIdx.x;
         if (i == 64) {
-            s_pair[64] = (uint16_t)(lut.v[64] | (uint32_t)lut.v[64] << 8);
+            pair[64] = (uint16_t)(lut.v[64] | (uint32_t)lut.v[64] << 8);
         } else {
             const uint32_t tcag = 0x0312u;  // nibble k = T,C,A,G index of A,C,G,T code k: A->2, C->1, G->3, T->0
             const uint32_t a = (tcag >> (4 * (i >> 4))) & 3u, bb = (tcag >> (4 * ((i >> 2) & 3u))) & 3u, c = (tcag >> (4 * (i & 3u))) & 3u;
-            s_pair[i] = (uint16_t)(lut.v[16 * a + 4 * bb + c] | (uint32_t)lut.v[16 * (c ^ 2) + 4 * (bb ^ 2) + (a ^ 2)] << 8);
+            pair[i] = (uint16_t)(lut.v[16 * a + 4 * bb + c] | (uint32_t)lut.v[16 * (c ^ 2) + 4 * (bb ^ 2) + (a ^ 2)] << 8);
         }
-    }
-    __syncthreads();
-    // all nucleotides, or (slices of the device path) those of groups [g_lo, g_hi); a 16-byte chunk that straddles two
-    // slices is written by both with the same bytes
-    const uint64_t ch_lo = group_off ? read_off[group_off[g_lo]] / 16 : 0;
-    const uint64_t nchunks = ((group_off ? read_off[group_off[g_hi]] : total_nt) + 15) / 16;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t ch = ch_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
-        const uint64_t x0 = ch * 16;
-        uint32_t w[5];
-        if (x0 + 20 <= total_nt) {
-            const uint4 v = *reinterpret_cast<const uint4*>(nt + x0);
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            w[4] = *reinterpret_cast<const uint32_t*>(nt + x0 + 16);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                w[i] = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint64_t x = x0 + 4 * i + b;
-                    w[i] |= (uint32_t)(x < total_nt ? nt[x] : (uint8_t)'N') << (8 * b);
-                }
-            }
-        }
-        // four bytes at a time: code = ((x >> 1) ^ (x >> 2)) & 3 maps A,C,G,T to 0,1,2,3; a byte is one of those four
-        // letters iff the letter of its code equals it (anything else, lowercase included, is N: dna/mod.rs:34-44);
-        // N sets bit 2 of the byte's code
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const uint32_t x = w[i];
-            const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
-            const uint32_t sel = (t & 0xFu) | ((t >> 4) & 0xF0u) | ((t >> 8) & 0xF00u) | ((t >> 12) & 0xF000u);
-            const uint32_t diff = __byte_perm(0x54474341u, 0u, sel) ^ x;  // "ACGT"[code] against the byte
-            const uint32_t nz = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;  // 0x80 in every differing byte
-            w[i] = t | (nz >> 5);
-        }
-        uint32_t fo[4] = {0, 0, 0, 0}, ro[4] = {0, 0, 0, 0};
-        uint32_t idx = ((w[0] & 3u) << 2) | ((w[0] >> 8) & 3u);            // codon index so far: codes 0 and 1
-        uint32_t nm = ((w[0] >> 2) & 1u) << 1 | ((w[0] >> 10) & 1u);        // their N flags
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t c = (w[(i + 2) >> 2] >> (8 * ((i + 2) & 3))) & 7u;
-            idx = ((idx << 2) | (c & 3u)) & 63u;
-            nm = ((nm << 1) | (c >> 2)) & 7u;
-            const uint32_t pr = s_pair[nm ? 64u : idx];
-            fo[i >> 2] |= (pr & 0xFFu) << (8 * (i & 3));
-            ro[i >> 2] |= (pr >> 8) << (8 * (i & 3));
-        }
-        *reinterpret_cast<uint4*>(codes + x0) = make_uint4(fo[0], fo[1], fo[2], fo[3]);
-        *reinterpret_cast<uint4*>(codes + rev_off + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
     }
 }
 
@@ -472,13 +447,16 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
 
 template <int K, class TV, int STRIDE>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
-lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ codes, uint64_t rev_off, const uint64_t* __restrict__ read_off,
-                      uint32_t nreads, uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits,
-                      const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
+lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
+                      uint64_t total_nt, const uint64_t* __restrict__ read_off, uint32_t nreads, uint32_t* __restrict__ ids,
+                      uint8_t* __restrict__ frame_hits, const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
                       uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
     __shared__ SampledSmem s_sm[kSWarps];
+    __shared__ uint16_t s_pair[65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
+    fill_pair_lut(lut, s_pair);
+    __syncthreads();
     SampledSmem& sm = s_sm[warp];
     // the reads of groups [g_lo, g_hi) when a group table is given (slices of the device path), else all reads
     const uint32_t r_begin = group_off ? (uint32_t)group_off[g_lo] : 0u;
@@ -507,14 +485,23 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const uint8_t* __restrict__ 
             if ((uint32_t)lane <= nb) sm.roff[lane] = rel;
             if ((uint32_t)lane < nb) sm.mask[lane] = 0;
             // ---- stage both code spans, 16 bytes per lane and load
-            const uint32_t mis = (uint32_t)((uintptr_t)(codes + off0) & 15u);
+            // ---- stage: 16 nucleotides per lane and step (plus the 4 bytes that follow them: two are needed), translated
+            //      in registers (translate.rs:114-133, dna/mod.rs:23-103, dna/translation.rs:125-144), both residue-code
+            //      chunks to shared memory; the batch starts at byte `mis` of the first chunk
+            const uint32_t mis = (uint32_t)((uintptr_t)(nt + off0) & 15u);
             {
-                const uint4* gf = reinterpret_cast<const uint4*>(codes + off0 - mis);
-                const uint4* gr = reinterpret_cast<const uint4*>(codes + rev_off + off0 - mis);
+                const uint64_t x_first = off0 - mis;  // nt is 16-byte aligned, so is this
                 const uint32_t nch = (mis + span + 15) / 16;
                 for (uint32_t c = lane; c < nch; c += 32) {
-                    sm.f[c] = __ldg(gf + c);
-                    sm.r[c] = __ldg(gr + c);
+                    const uint64_t x0 = x_first + 16ull * c;
+                    uint32_t w[5];
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(nt + x0));  // the chunk holds a nucleotide of the batch
+                    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                    w[4] = x0 + 20 <= total_nt ? __ldg(reinterpret_cast<const uint32_t*>(nt + x0 + 16)) : 0x4E4E4E4Eu;  // 'N's past the end
+                    uint32_t fo[4], ro[4];
+                    translate_chunk16(w, s_pair, fo, ro);
+                    sm.f[c] = make_uint4(fo[0], fo[1], fo[2], fo[3]);
+                    sm.r[c] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
                 }
             }
             __syncwarp();
@@ -1103,7 +1090,7 @@ using namespace umgap;
 // ---- workspace slots of an index handle --------------------------------------------------------
 constexpr int kMaxBufs = 6;  // chunk streams of the host-buffer path, each with its own set of buffers
 enum { WS_ERR = 0, WS_NT = 1, WS_ROFF = WS_NT + kMaxBufs, WS_GOFF = WS_ROFF + kMaxBufs, WS_OUT = WS_GOFF + kMaxBufs, WS_HITS = WS_OUT + kMaxBufs,
-       WS_CODES = WS_HITS + kMaxBufs, WS_IDS = WS_CODES + kMaxBufs, WS_SCRATCH = WS_IDS + kMaxBufs, WS_LONG = WS_SCRATCH + kMaxBufs,
+       WS_IDS = WS_HITS + kMaxBufs, WS_SCRATCH = WS_IDS + kMaxBufs, WS_LONG = WS_SCRATCH + kMaxBufs,
        WS_END = WS_LONG + kMaxBufs };
 static_assert(WS_END <= Workspace::kSlots, "workspace slots");
 
@@ -1242,23 +1229,11 @@ static void launch_classify(const umgap_index* idx, const umgap_taxonomy* tax,
 // and issue slots -- profiles/README.md.)
 struct SampledPlan {  // the sampled lookup stage of one batch
     int stride = 0;       // 0: not applicable, use the plain kernel
-    uint8_t* codes = nullptr;
-    uint64_t rev_off = 0;
     CodonLut lut{};
+    uint64_t total_nt = 0;
     uint32_t* long_count = nullptr;  // 64 counters (one per slice), then the list of reads left to the plain kernel
     uint32_t* long_list = nullptr;
 };
-
-// Residue-code pre-pass over all nucleotides, or over those of groups [g_lo, g_hi) (nt_hint sizes the grid).
-static void launch_codes(const SampledPlan& sp, const uint8_t* nt_dev, uint64_t total_nt, uint64_t nt_hint,
-                         const uint64_t* read_off_dev, const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi,
-                         cudaStream_t st) {
-    const unsigned tblocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nt_hint, 16), 256) + 1, 148ull * 16);
-    translate_codes_kernel<<<tblocks, 256, 0, st>>>(sp.lut, nt_dev, total_nt, sp.codes, sp.rev_off, read_off_dev, group_off_dev,
-                                                    g_lo, g_hi);
-    UMGAP_CUDA(cudaGetLastError());
-    ++g_launch_count;
-}
 
 // reads_hint: number of reads the launch will find in its group range (sizes the grid only).
 static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const SampledPlan& sp, const uint8_t* nt_dev,
@@ -1271,11 +1246,10 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
         return 148u * (unsigned)(v > 0 ? v : kSBlocks * 4);
     }();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, grid_cap);
-#define UMGAP_SAMPLED(S)                                                                                                     \
-    lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.codes, sp.rev_off, read_off_dev,  \
-                                                                           (uint32_t)nreads, ids_dev, frame_hits_dev,        \
-                                                                           group_off_dev, g_lo, g_hi, sp.long_list,          \
-                                                                           sp.long_count + slice)
+#define UMGAP_SAMPLED(S)                                                                                                      \
+    lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev,   \
+                                                                           (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, \
+                                                                           g_lo, g_hi, sp.long_list, sp.long_count + slice)
     switch (sp.stride) {
         case 2: UMGAP_SAMPLED(2); break;
         case 3: UMGAP_SAMPLED(3); break;
@@ -1295,11 +1269,11 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
 
 // Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
 // the frames flagged in frame_hits_dev have ids afterwards, which is all the classify kernel reads.
-// Decides whether the stage applies and, if so, launches what has to run once per batch: the residue-code
-// pre-pass and the plain kernel over the reads longer than a warp batch (rare; it skips everything else).
+// Decides whether the stage applies and, if so, prepares what a batch needs once: the codon table and the
+// work list through which reads longer than a warp batch reach the plain kernel.
 static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
                                    const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
-                                   uint8_t* frame_hits_dev, cudaStream_t st, int buf, bool defer_prepass) {
+                                   uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
     static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
     SampledPlan sp;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
@@ -1311,13 +1285,11 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
     if (!nreads) return sp;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
-    sp.rev_off = (total_nt + 15) / 16 * 16 + 16;
-    sp.codes = (uint8_t*)idx->ws.get(WS_CODES + buf, 2 * sp.rev_off);
+    sp.total_nt = total_nt;
     sp.lut = lut;
     sp.long_count = (uint32_t*)idx->ws.get(WS_LONG + buf, (64 + nreads) * sizeof(uint32_t));
     sp.long_list = sp.long_count + 64;
     UMGAP_CUDA(cudaMemsetAsync(sp.long_count, 0, 64 * sizeof(uint32_t), st));
-    if (!defer_prepass) launch_codes(sp, nt_dev, total_nt, total_nt, nullptr, nullptr, 0, 0, st);
     return sp;
 }
 
@@ -1330,7 +1302,7 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
     const int kSlices = g_slices;
     const bool slice_it = sliced && kSlices >= 2 && ngroups >= 4096u * (uint64_t)kSlices && nreads;
     LaunchTimer timer(0, st);
-    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf, slice_it);
+    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
     if (!sp.stride) {
         timer.cancel();  // the plain launch brackets itself
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
@@ -1364,7 +1336,6 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
         cudaStream_t s = idx->aux_stream[sl & 1];
         {
             LaunchTimer t2(0, s);
-            launch_codes(sp, nt_dev, total_nt, ceil_div(total_nt, kSlices), read_off_dev, group_off_dev, g_lo, g_hi, s);
             launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev,
                            g_lo, g_hi, sl, s);
             t2.stop();
