@@ -337,6 +337,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     classified = float((out != 1).float().mean().item())
+    # the random-sector ceiling of this table on this GPU (uniform random 32-byte gathers over level 0)
+    rand_sectors_per_s = gidx.randsector_rate(1 << 28, 3) if rank == 0 and not shard_mode else None
 
     # ---- end to end through the host-buffer C ABI call (pinned host input, H2D + D2H timed)
     e2e = None
@@ -429,6 +431,13 @@ def run_ours(args):
                                     "classify_bracket_sum_ms_per_step": classify_ms / args.steps,
                                     "step_ms": ms / args.steps,
                                     "what": "brackets of concurrent streams overlap: their sum exceeds the step"},
+                "random_sector_roofline": None if not rand_sectors_per_s or not lines else {
+                    "gathers_per_second": rand_sectors_per_s,
+                    "what": "bench/randsector microbenchmark (umgap_randsector_bench): uniform random 32-byte gathers over this table; "
+                            "every gather fills a 128-byte line",
+                    "kernel_line_fills_per_second": lines * nreads / (use_ms * 1e-3),
+                    "frac_line_fills": lines * nreads / (use_ms * 1e-3) / rand_sectors_per_s,
+                    "frac_effective_lookups": lookups_per_launch / (use_ms * 1e-3) / rand_sectors_per_s},
                 "kernel_share_of_step": min(1.0, use_ms / (ms / args.steps)) if ms else None,
                 "lookups_per_second_kernel": lookups_per_launch / (use_ms * 1e-3)}
     cb = None if args.no_cpu_baseline else cpu_baseline(args)

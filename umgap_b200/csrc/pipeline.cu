@@ -330,7 +330,11 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
 #endif
 constexpr int kSReads = 5;
 constexpr int kSSpan = 160 * kSReads;
-constexpr int kSQueue = 128;
+#ifndef UMGAP_S_UNROLL
+#define UMGAP_S_UNROLL 2
+#endif
+constexpr int kSU = UMGAP_S_UNROLL;     // lookups in flight per lane
+constexpr int kSQueue = 64 * kSU;
 constexpr int kSWarps = 4;
 constexpr int kSBlocks = UMGAP_S_BLOCKS;  // CTAs per SM the launch bounds ask for
 constexpr int kSItems = 32 + 6 * kSReads;
@@ -531,16 +535,16 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                 }
                 const uint32_t max_cs = __reduce_max_sync(0xffffffffu, cs);
 #pragma unroll 1
-                for (uint32_t s0 = 0; s0 < max_cs; s0 += 2) {
-                    if (qn + 64 > (uint32_t)kSQueue) {
+                for (uint32_t s0 = 0; s0 < max_cs; s0 += kSU) {
+                    if (qn + 32 * kSU > (uint32_t)kSQueue) {
                         drain_queue(t, sm.q, qn, lane, done1);
                         qn = 0;
                     }
-                    uint64_t h[2];
-                    ulonglong4 sec[2];
-                    bool valid[2];
+                    uint64_t h[kSU];
+                    ulonglong4 sec[kSU];
+                    bool valid[kSU];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < kSU; ++u) {
                         h[u] = mix45(key);
                         valid[u] = s0 + u < cs && bad == 0;
                         if (s0 + u < cs && bad != 0 && s0 + u < (uint32_t)kSValRows) sm.val[s0 + u][lane] = kNoValue;
@@ -555,10 +559,10 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+                    for (int u = 0; u < kSU; ++u)
                         if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < kSU; ++u) {
                         const uint32_t tag = rec | ((s0 + u) << 5);
                         bool more = false;
                         if (valid[u]) {
@@ -618,17 +622,17 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     }
                     const uint32_t max_cnt = __reduce_max_sync(0xffffffffu, cnt);
 #pragma unroll 1
-                    for (uint32_t s0 = 0; s0 < max_cnt; s0 += 2) {
-                        if (qn + 64 > (uint32_t)kSQueue) {
+                    for (uint32_t s0 = 0; s0 < max_cnt; s0 += kSU) {
+                        if (qn + 32 * kSU > (uint32_t)kSQueue) {
                             drain_queue(t, sm.q, qn, lane, done2);
                             qn = 0;
                         }
-                        uint64_t h[2];
-                        ulonglong4 sec[2];
-                        uint32_t v[2];
-                        bool valid[2];
+                        uint64_t h[kSU];
+                        ulonglong4 sec[kSU];
+                        uint32_t v[kSU];
+                        bool valid[kSU];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < kSU; ++u) {
                             const bool act = s0 + u < cnt;
                             const uint32_t jj = j + s0 + u, sx = jj / STRIDE;
                             const bool cached = act && jj % STRIDE == 0 && sx < (uint32_t)kSValRows;
@@ -643,10 +647,10 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u)
+                        for (int u = 0; u < kSU; ++u)
                             if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < kSU; ++u) {
                             bool more = false;
                             if (valid[u]) v[u] = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
                             const uint32_t oi = o + s0 + u;
