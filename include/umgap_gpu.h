@@ -260,6 +260,11 @@ int umgap_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
  * launch on the caller's stream.  Returns the previous setting; slices <= 0 only queries.  Default 8
  * (environment UMGAP_SLICES).                                                                      */
 int umgap_pipeline_slices(int slices);
+/* In front of `seedextend -s S` (S >= 2, with -o) the fused path probes every min(S,4)-th k-mer position first
+ * and the others only for frames with a hit -- the same results with half the memory traffic.  0 switches
+ * this off (every position is probed, as without seedextend), 1 on (default; environment UMGAP_NO_SAMPLING
+ * starts with it off), a negative value only queries.  Returns the previous setting.                     */
+int umgap_pipeline_sampling(int enable);
 
 /* ---- benchmark / test aids (synthetic data of SURVEY 8(d); not part of the reference) ---- */
 typedef struct umgap_synth_spec {

@@ -545,6 +545,24 @@ def test_full_size_index_properties(capi):
                                   roff.cpu().numpy().astype(np.uint64), goff.cpu().numpy().astype(np.uint64))
     assert np.array_equal(host, outs[0].view(np.uint32))
     assert 0.6 < (host != 1).mean() < 0.8                # 70 % of the pairs come from the proteome
+    # sampled lookups (every min(S,4)-th position first, sliced over two streams) against the every-position kernel,
+    # full-size table, the presets of umgap-analyse.sh and the bench configuration: identical taxa for every pair
+    for s_, g_, strat, lb in ((3, 0, capi.AGG_HYBRID, 0.0), (2, 1, capi.AGG_MRTL, 1.0), (3, 1, capi.AGG_HYBRID, 1.0),
+                              (4, 1, capi.AGG_LCA_STAR, 5.0)):
+        o = capi.default_opts(min_seed_size=s_, max_gap_size=g_, strategy=strat, lower_bound=lb)
+        got = {}
+        for sampling in (1, 0):
+            before = capi.pipeline_sampling(sampling)
+            try:
+                out = torch.zeros(B, dtype=torch.int32, device="cuda")
+                capi.classify_reads_dev(gidx, gtax, o, nt.data_ptr(), roff.data_ptr(), 2 * B, B * 300, goff.data_ptr(), B,
+                                        out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                got[sampling] = out.cpu().numpy()
+            finally:
+                capi.pipeline_sampling(before)
+        assert np.array_equal(got[0], got[1]), (s_, g_, strat)
+        assert (got[1] != 1).mean() > 0.3
     gidx.close()
 
 

@@ -35,7 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
-    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices",
+    "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices", "umgap_pipeline_sampling",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
 
@@ -409,6 +409,11 @@ def transfer_bytes():
     a, b = C.c_uint64(), C.c_uint64()
     _check(load_library().umgap_transfer_bytes(C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def pipeline_sampling(enable: int = -1) -> int:
+    """Switches the sampled lookups of the fused path on (1) / off (0); returns the previous setting."""
+    return int(load_library().umgap_pipeline_sampling(C.c_int(enable)))
 
 
 def kernel_launch_count() -> int:

@@ -1125,6 +1125,7 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
 namespace umgap {
 static uint64_t g_launch_count = 0;  // kernels launched by the fused path
 static uint64_t g_h2d_bytes = 0, g_d2h_bytes = 0;  // bytes umgap_classify_reads moved over PCIe
+static bool g_sampling = getenv("UMGAP_NO_SAMPLING") == nullptr;  // sampled lookups in front of seedextend (umgap_pipeline_sampling)
 static int g_slices = [] {           // slices of the device-buffer entry point (umgap_pipeline_slices)
     const char* e = getenv("UMGAP_SLICES");
     const int v = e ? atoi(e) : 0;
@@ -1278,8 +1279,8 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
 static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
                                    const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
                                    uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
-    static const bool disabled = getenv("UMGAP_NO_SAMPLING") != nullptr;
     SampledPlan sp;
+    const bool disabled = !g_sampling;
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
         (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 31) ||
@@ -1378,6 +1379,12 @@ int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes) {
         if (!idx) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         idx->region_bytes = bytes;
     });
+}
+
+int umgap_pipeline_sampling(int enable) {
+    const int before = g_sampling ? 1 : 0;
+    if (enable >= 0) g_sampling = enable != 0;
+    return before;
 }
 
 int umgap_pipeline_slices(int slices) {
