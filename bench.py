@@ -407,8 +407,9 @@ def run_ours(args):
     if os.path.exists(tpath) and traffic:
         lines = tj.get("lookup_kernel_dram_bytes_per_launch", traffic) / 128.0 / nreads
     alg_bytes = lookups_per_launch * BYTES_PER_LOOKUP
-    if routed is not None:
-        use_ms, mode = avg_ms, "brackets of the timed region"
+    if routed is not None or slices == 1:
+        use_ms = avg_ms if routed is not None else max(lookup_ms / max(1, lookup_n), 1e-9)
+        mode = "CUDA-event brackets around every launch of the lookup stage in the timed region, on its stream"
     else:
         # In the timed region a step is cut into slices whose lookup kernels run beside the previous slice's classify
         # kernel on two streams: their event brackets overlap each other and include the time a kernel waits for SMs the
@@ -430,7 +431,8 @@ def run_ours(args):
                 "in_timed_region": {"slices_per_step": slices, "lookup_bracket_sum_ms_per_step": avg_ms,
                                     "classify_bracket_sum_ms_per_step": classify_ms / args.steps,
                                     "step_ms": ms / args.steps,
-                                    "what": "brackets of concurrent streams overlap: their sum exceeds the step"},
+                                    "what": "one lookup stage and one classify launch per step, one after the other" if slices == 1
+                                            else "brackets of concurrent streams overlap: their sum exceeds the step"},
                 "random_sector_roofline": None if not rand_sectors_per_s or not lines else {
                     "gathers_per_second": rand_sectors_per_s,
                     "what": "bench/randsector microbenchmark (umgap_randsector_bench): uniform random 32-byte gathers over this table; "

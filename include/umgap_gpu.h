@@ -255,10 +255,12 @@ int umgap_kernel_launch_count(uint64_t* launches);
 /* Bytes umgap_classify_reads has copied host -> device and device -> host in this process (offset arrays
  * that are arithmetic progressions are regenerated on the device instead of being uploaded).        */
 int umgap_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
-/* umgap_classify_reads_dev cuts a batch into `slices` group ranges whose lookup and classify kernels
- * alternate on two internal streams (they fill each other's tails); 1 = one lookup and one classify
- * launch on the caller's stream.  Returns the previous setting; slices <= 0 only queries.  Default 8
- * (environment UMGAP_SLICES).                                                                      */
+/* umgap_classify_reads_dev can cut a batch into `slices` group ranges whose lookup and classify kernels
+ * alternate on two internal streams (the classify kernel of a slice beside the lookup kernel of the next);
+ * 1 (default; environment UMGAP_SLICES) = one lookup and one classify launch on the caller's stream.  With
+ * the lookup kernel handing out its units dynamically the slices no longer pay (profiles/README.md 2c); the
+ * mechanism stays for workloads with a heavier classify stage.  Returns the previous setting; slices <= 0
+ * only queries.                                                                                          */
 int umgap_pipeline_slices(int slices);
 /* In front of `seedextend -s S` (S >= 2, with -o) the fused path probes every min(S,4)-th k-mer position first
  * and the others only for frames with a hit -- the same results with half the memory traffic.  0 switches

@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
 lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
                       uint64_t total_nt, const uint64_t* __restrict__ read_off, uint32_t nreads, uint32_t* __restrict__ ids,
                       uint8_t* __restrict__ frame_hits, const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
-                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
+                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ unit_count) {
     __shared__ SampledSmem s_sm[kSWarps];
     __shared__ uint16_t s_pair[65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -466,9 +466,14 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
     const uint32_t r_begin = group_off ? (uint32_t)group_off[g_lo] : 0u;
     const uint32_t r_end = group_off ? (uint32_t)group_off[g_hi] : nreads;
     const uint32_t nunits = (r_end - r_begin + kSReads - 1) / kSReads;
-    const uint32_t nwarps = gridDim.x * kSWarps;
+    // units are handed out through a counter: their cost varies (reads with and without live frames), and a launch
+    // holds only a few units per resident warp
 #pragma unroll 1
-    for (uint32_t unit = blockIdx.x * kSWarps + warp; unit < nunits; unit += nwarps) {
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(unit_count, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= nunits) break;
         uint32_t cur = r_begin + unit * kSReads;
         const uint32_t end = min(cur + (uint32_t)kSReads, r_end);
 #pragma unroll 1
@@ -1129,7 +1134,7 @@ static bool g_sampling = getenv("UMGAP_NO_SAMPLING") == nullptr;  // sampled loo
 static int g_slices = [] {           // slices of the device-buffer entry point (umgap_pipeline_slices)
     const char* e = getenv("UMGAP_SLICES");
     const int v = e ? atoi(e) : 0;
-    return v > 0 ? std::min(v, 64) : 8;
+    return v > 0 ? std::min(v, 64) : 1;
 }();
 bool g_timing = false;
 std::vector<TimedLaunch> g_launches;
@@ -1248,13 +1253,14 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
     static const unsigned grid_cap = [] {  // CTAs of one launch (UMGAP_S_GRID = CTAs per SM, for measurements)
         const char* e = getenv("UMGAP_S_GRID");
         const int v = e ? atoi(e) : 0;
-        return 148u * (unsigned)(v > 0 ? v : kSBlocks * 4);
+        return 148u * (unsigned)(v > 0 ? v : kSBlocks);  // one resident wave: the units are handed out dynamically
     }();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, grid_cap);
 #define UMGAP_SAMPLED(S)                                                                                                      \
     lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev,   \
                                                                            (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, \
-                                                                           g_lo, g_hi, sp.long_list, sp.long_count + slice)
+                                                                           g_lo, g_hi, sp.long_list, sp.long_count + slice,       \
+                                                                           sp.long_count + 64 + slice)
     switch (sp.stride) {
         case 2: UMGAP_SAMPLED(2); break;
         case 3: UMGAP_SAMPLED(3); break;
@@ -1292,9 +1298,10 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
     make_code_lut(idx, o->table, o->methionine, lut);
     sp.total_nt = total_nt;
     sp.lut = lut;
-    sp.long_count = (uint32_t*)idx->ws.get(WS_LONG + buf, (64 + nreads) * sizeof(uint32_t));
-    sp.long_list = sp.long_count + 64;
-    UMGAP_CUDA(cudaMemsetAsync(sp.long_count, 0, 64 * sizeof(uint32_t), st));
+    // 64 long-read counters and 64 unit counters (one of each per slice), then the long-read list
+    sp.long_count = (uint32_t*)idx->ws.get(WS_LONG + buf, (128 + nreads) * sizeof(uint32_t));
+    sp.long_list = sp.long_count + 128;
+    UMGAP_CUDA(cudaMemsetAsync(sp.long_count, 0, 128 * sizeof(uint32_t), st));
     return sp;
 }
 
