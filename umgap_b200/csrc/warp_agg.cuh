@@ -413,26 +413,8 @@ __device__ __forceinline__ uint32_t agg_finish32(const TaxView& tv, uint32_t a, 
     return ap.ranked_only ? __ldg(tv.snap_ranked + base_node) : __ldg(tv.snap_valid + base_node);
 }
 
-// Register-resident ascending bitonic sort of one (key, payload) pair per lane.
-__device__ __forceinline__ void warp_sort32(uint32_t& d, uint32_t& c, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t od = __shfl_xor_sync(0xffffffffu, d, j);
-            const uint32_t oc = __shfl_xor_sync(0xffffffffu, c, j);
-            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-            const bool take = (lower == up) ? (od < d) : (od > d);
-            if (take) {
-                d = od;
-                c = oc;
-            }
-        }
-    }
-}
-
 // Aggregates a record given as n <= 32 DISTINCT non-zero taxon ids with their occurrence counts, one per
-// lane (lane i < n holds id / cnt): everything up to the strategies stays in registers.  P needs n+1 and
+// lane (lane i < n holds id / cnt): filter, rank sort and prefix sums in registers.  P needs n+1 and
 // A, L need n entries of scratch.  Same results as warp_aggregate.  All 32 lanes must call.
 __device__ __forceinline__ uint32_t warp_aggregate_distinct(const TaxView& tv, uint32_t id, uint32_t cnt, uint32_t n,
                                                             uint32_t* A, uint32_t* P, uint32_t* L, const AggParams& ap,
@@ -445,27 +427,39 @@ __device__ __forceinline__ uint32_t warp_aggregate_distinct(const TaxView& tv, u
         if (d == kNoTaxon) *bad_id = id;
     }
     if (__any_sync(0xffffffffu, have && d == kNoTaxon)) return kAggUnknown;
-    uint32_t c = have ? cnt : 0u;
-    warp_sort32(d, c, lane);  // the n members first (kNoTaxon = 0xFFFFFFFF pads the rest)
-    const bool keep = d != kNoTaxon && (float)c >= ap.lower_bound;  // agg/mod.rs:39-44
+    // lower-bound filter first (agg/mod.rs:39-44, f32 compare), then a rank sort of the kept members: the dozen
+    // members of a typical record take a dozen shuffles, a sorting network over all 32 lanes takes 15 steps of two
+    const bool keep = have && (float)cnt >= ap.lower_bound;
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const uint32_t m = (uint32_t)__popc(mask);
     if (m == 0) return 1u;  // everything filtered: the literal "1"
-    const uint32_t incl = warp_incl_scan(keep ? c : 0u, lane);
-    const uint32_t running = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t rank = 0;  // members are distinct: the number of smaller kept members is the sorted position
+    for (unsigned rest = mask; rest; rest &= rest - 1) {
+        const uint32_t dj = __shfl_sync(0xffffffffu, d, __ffs((int)rest) - 1);
+        rank += dj < d ? 1u : 0u;
+    }
     __syncwarp();
     if (keep) {
-        const uint32_t rank = (uint32_t)__popc(mask & ((1u << lane) - 1));
         A[rank] = d;
-        P[rank] = incl - c;
-        L[rank] = __ldg(tv.last + d);
+        L[rank] = cnt;  // the counts travel through L
     }
-    if (lane == 0) P[m] = running;
     __syncwarp();
-    if (ap.strategy == UMGAP_AGG_MRTL) return agg_finish(tv, A, P, L, m, running, ap, lane);
-    // member j to lane j: dense index, subtree end, exclusive prefix of the counts (P[m] = running beyond the members)
+    // member j to lane j: dense index, subtree end, exclusive prefix of the counts (running beyond the members)
     const bool mem = (uint32_t)lane < m;
-    const uint32_t a = mem ? A[lane] : kNoTaxon, l = mem ? L[lane] : 0u, p0 = mem ? P[lane] : running;
+    const uint32_t a = mem ? A[lane] : kNoTaxon, c = mem ? L[lane] : 0u;
+    const uint32_t incl = warp_incl_scan(c, lane);
+    const uint32_t running = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t p0 = mem ? incl - c : running, l = mem ? __ldg(tv.last + a) : 0u;
+    if (ap.strategy == UMGAP_AGG_MRTL) {
+        __syncwarp();
+        if (mem) {
+            P[lane] = p0;
+            L[lane] = l;
+        }
+        if (lane == 0) P[m] = running;
+        __syncwarp();
+        return agg_finish(tv, A, P, L, m, running, ap, lane);
+    }
     return agg_finish32(tv, a, l, p0, m, running, ap, lane);
 }
 
