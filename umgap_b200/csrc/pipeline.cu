@@ -316,8 +316,8 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
 // probed in a second phase of the same warp, and only these frames' ids are written.  Bit-identical
 // output, about 0.4 of the HBM line fills.
 //
-// Work layout: one warp takes a batch of up to kSReads = 5 consecutive reads (<= kSSpan nucleotides; 30
-// frame records).  It translates the batch itself, 16 nucleotides per lane and step, four bytes per
+// Work layout: one warp takes a batch of up to kSReads = 5 consecutive reads (<= kSSpan = 1280 nucleotides;
+// 30 frame records).  It translates the batch itself, 16 nucleotides per lane and step, four bytes per
 // instruction, into two residue-code arrays in shared memory (forward codon starting at x, reverse-strand
 // codon whose lowest forward coordinate is x).  Then every LANE walks one frame record: the 9-residue key
 // rolls from one position to the next (one shared-memory byte per residue), two lookups in flight per
@@ -329,7 +329,7 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
 #define UMGAP_S_BLOCKS 7
 #endif
 constexpr int kSReads = 5;
-constexpr int kSSpan = 160 * kSReads;
+constexpr int kSSpan = 256 * kSReads;  // five reads of up to 256 nt fill 30 lanes; longer reads leave lanes idle
 #ifndef UMGAP_S_UNROLL
 #define UMGAP_S_UNROLL 2
 #endif
