@@ -17,7 +17,7 @@ gidx = capi.Index.build_synthetic(spec, gtax, 0, lf)
 torch.cuda.synchronize()
 info = gidx.info()
 print("index build s", time.time() - t0, {f[0]: getattr(info, f[0]) for f in info._fields_}, flush=True)
-L = 150
+L = int(os.environ.get("PROBE_LEN", "150"))
 nt = torch.empty(npairs * 2 * L, dtype=torch.uint8, device="cuda")
 capi.synth_reads_dev(spec, 3, 0, npairs, L, 70, nt.data_ptr())
 roff = (torch.arange(0, npairs * 2 + 1, dtype=torch.int64, device="cuda") * L)
