@@ -4,6 +4,7 @@
 // region-partitioned probe order would produce).
 //   ./randsector <table_MiB> <gathers_M> [variant|all] [window_MiB]
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -98,7 +99,38 @@ int main(int argc, char** argv) {
     const char* var = argc > 3 ? argv[3] : "0";
     const uint64_t wmib = argc > 4 ? strtoull(argv[4], 0, 10) : mib;
     const uint64_t bytes = mib << 20, wbytes = (wmib > mib ? mib : wmib) << 20;
-    char* t; CK(cudaMalloc(&t, bytes)); CK(cudaMemset(t, 1, bytes));
+    char* t;
+    if (getenv("RS_VMM")) {
+        // virtual-memory-management allocation: one physical handle, address range aligned to RS_VMM MiB —
+        // does the driver map it with pages larger than 2 MiB (address-translation reach of a >64 GiB table)?
+        CK(cudaFree(0));
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = 0;
+        size_t gmin = 0, grec = 0;
+        cuMemGetAllocationGranularity(&gmin, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+        cuMemGetAllocationGranularity(&grec, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+        const size_t align = strtoull(getenv("RS_VMM"), 0, 10) << 20;
+        printf("vmm: granularity min %zu recommended %zu, alignment %zu\n", gmin, grec, align);
+        CUmemGenericAllocationHandle h;
+        CUresult r = cuMemCreate(&h, bytes, &prop, 0);
+        if (r != CUDA_SUCCESS) { printf("cuMemCreate %d\n", (int)r); return 1; }
+        CUdeviceptr va = 0;
+        r = cuMemAddressReserve(&va, bytes, align, 0, 0);
+        if (r != CUDA_SUCCESS) { printf("cuMemAddressReserve %d\n", (int)r); return 1; }
+        r = cuMemMap(va, bytes, 0, h, 0);
+        if (r != CUDA_SUCCESS) { printf("cuMemMap %d\n", (int)r); return 1; }
+        CUmemAccessDesc acc = {};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = cuMemSetAccess(va, bytes, &acc, 1);
+        if (r != CUDA_SUCCESS) { printf("cuMemSetAccess %d\n", (int)r); return 1; }
+        t = (char*)va;
+    } else {
+        CK(cudaMalloc(&t, bytes));
+    }
+    CK(cudaMemset(t, 1, bytes));
     unsigned long long* sink; CK(cudaMalloc(&sink, 8)); CK(cudaMemset(sink, 0, 8));
     const bool all = !strcmp(var, "all");
     const int v = atoi(var);

@@ -114,7 +114,7 @@ typedef struct umgap_index_info {
 int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info);
 /* A level-0 table larger than `bytes` is probed one hash-prefix region of at most that size per
  * lookup-kernel pass (B200's random-access rate collapses beyond ~64 GiB of footprint; default
- * 48 GiB, 0 restores it).  Results do not depend on it.                                          */
+ * 60 GiB, 0 restores it).  Results do not depend on it.                                          */
 int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes);
 
 /* ---- taxonomy: replaces taxon::read_taxa_file + TaxonTree::new + TaxonList::new +

@@ -44,6 +44,18 @@ for sl in [int(x) for x in os.environ.get("PROBE_SLICES", "").split(",") if x]:
     ms3 = timeit(lambda: capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st), 8)
     print(f"slices {sl}: {ms3:.3f} ms  {npairs*2/ms3/1e3:.2f} M reads/s", flush=True)
 capi.pipeline_slices(1)
+for gib in [float(x) for x in os.environ.get("PROBE_REGIONS", "").split(",") if x]:   # probe-region sizes in GiB
+    gidx.set_probe_region(int(gib * (1 << 30)))
+    for sampling in (1, 0):
+        capi.pipeline_sampling(sampling)
+        ms4 = timeit(lambda: capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st), 4)
+        capi.kernel_timing(True); capi.kernel_times()
+        capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st)
+        torch.cuda.synchronize()
+        lm, ln, cm, cn = capi.kernel_times(); capi.kernel_timing(False)
+        print(f"region {gib} GiB sampling {sampling}: step {ms4:.3f} ms  {npairs*2/ms4/1e3:.2f} M reads/s  lookup stage {lm:.3f} ms ({ln} brackets) classify {cm:.3f} ms  sum(out) {int(out.sum())}", flush=True)
+    capi.pipeline_sampling(1)
+gidx.set_probe_region(0)
 capi.kernel_timing(True); capi.kernel_times()
 for _ in range(5):
     capi.classify_reads_dev(gidx, gtax, opts, nt.data_ptr(), roff.data_ptr(), npairs * 2, npairs * 2 * L, goff.data_ptr(), npairs, out.data_ptr(), st)

@@ -691,3 +691,10 @@ def test_sampled_lookup_ragged_batches(capi, world, s, g, strategy):
         assert int(got[k]) in want[h], (h, int(got[k]), want[h])
         below += int(got[k]) != 1
     assert below > (20 if strategy else 2)
+    # the same batch with the table probed in hash-prefix regions: the two phases run as separate launches per region
+    try:
+        world["gidx"].set_probe_region(4 << 20)
+        again, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, np.array(goff, dtype=np.uint64))
+    finally:
+        world["gidx"].set_probe_region(0)
+    assert np.array_equal(np.asarray(got), np.asarray(again))

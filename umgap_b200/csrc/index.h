@@ -51,7 +51,7 @@ struct umgap_index {
     uint64_t n_keys = 0, n_skipped = 0, n_flagged = 0, n_displaced = 0, max_probe = 0;
     uint64_t bytes = 0;
     double load_factor = 0;  // of level 0, as chosen at build time
-    uint64_t region_bytes = 0;  // probe-region size of the lookup kernel (0 = default 48 GiB)
+    uint64_t region_bytes = 0;  // probe-region size of the lookup kernel (0 = default 60 GiB)
     // key-range sharding (multi-GPU, table larger than one GPU): this handle holds shard `shard` of
     // `nshards`; after umgap_index_attach_shards() `sharded` maps every shard (peers through CUDA IPC)
     int shard = 0, nshards = 1;

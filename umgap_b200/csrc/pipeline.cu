@@ -433,6 +433,53 @@ __device__ __forceinline__ void drain_queue(const TV& t, uint64_t* q, uint32_t q
     }
 }
 
+// One probe of every queued lookup, two sector loads in flight per lane; the lookups that need another probe are
+// compacted to the front of the queue, their number is returned.  The region passes (MODE 1 / 2 of the sampled
+// kernel) send ALL their lookups through the queue, first probes included (distance 0, level 0): a pass probes only
+// 1/R of the positions a lane walks, and probing from the walk would spend a DRAM latency per step on a few lanes.
+template <class TV, class Done>
+__device__ __forceinline__ uint32_t drain_round(const TV& t, uint64_t* q, uint32_t qn, int lane, Done done) {
+    const unsigned lt_mask = (1u << lane) - 1;
+    uint32_t qnext = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t c = 0; c < qn; c += 64) {
+        uint64_t hq[2];
+        ulonglong4 s2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t i = c + 32 * j + lane;
+            hq[j] = i < qn ? q[i] : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (hq[j] != ~0ull)
+                s2[j] = load_sector(sector_addr(t, hq[j] & kKeyMask, (uint32_t)(hq[j] >> 48) & 3u, (uint32_t)(hq[j] >> 45) & 7u));
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            bool more = false;
+            uint64_t next = 0;
+            if (hq[j] != ~0ull) {
+                uint32_t d = (uint32_t)(hq[j] >> 45) & 7u, lv = (uint32_t)(hq[j] >> 48) & 3u;
+                const uint64_t hh = hq[j] & kKeyMask;
+                const uint32_t v = probe_sector_data(s2[j], (d << 28) | ((uint32_t)hh & kTagMask), more);
+                if (more && ++d == (uint32_t)kMaxDisp) {
+                    d = 0;
+                    if (++lv == num_levels(t, hh)) more = false;  // v is kNoValue here
+                }
+                if (!more) done((uint32_t)(hq[j] >> 50), v);
+                next = (hq[j] & ~(0x1Full << 45)) | ((uint64_t)d << 45) | ((uint64_t)lv << 48);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, more);
+            if (more) q[qnext + __popc(m & lt_mask)] = next;
+            qnext += __popc(m);
+        }
+        __syncwarp();
+    }
+    return qnext;
+}
+
 // Geometry of frame record rec (= read-in-batch * 6 + frame) from the batch's read offsets: number of
 // k-mer positions cntf, shared-memory byte address a0 of the first residue of position 0 (relative to
 // the batch's first forward code), address step per position dir (+3 forward, -3 reverse; residue kk
@@ -449,12 +496,18 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
     return (npos - f + 2) / 3;  // positions y = f + 3j < npos
 }
 
-template <int K, class TV, int STRIDE>
+// MODE 0: both phases in one launch (tables within the address-translation reach).  Tables probed one hash-prefix
+// region [region_lo, region_hi) per pass (launch_translate_lookup) run the phases as separate launches: MODE 1 =
+// phase 1 of one region (only the frame masks leave the kernel, OR-ed over the passes), MODE 2 = phase 2 of one
+// region (every position of the live frames whose hash prefix lies in the region, sampled ones included; batches
+// without a live frame are not even translated).
+template <int K, class TV, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
 lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
                       uint64_t total_nt, const uint64_t* __restrict__ read_off, uint32_t nreads, uint32_t* __restrict__ ids,
                       uint8_t* __restrict__ frame_hits, const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
-                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ unit_count) {
+                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ unit_count,
+                      uint64_t region_lo, uint64_t region_hi) {
     __shared__ SampledSmem s_sm[kSWarps];
     __shared__ uint16_t s_pair[65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -485,14 +538,23 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
             const unsigned fits = __ballot_sync(0xffffffffu, lane >= 1 && (uint32_t)lane <= left && my_off - off0 <= (uint64_t)kSSpan);
             const uint32_t nb = (uint32_t)__popc(fits);
             if (nb == 0) {  // a single read longer than the batch span: queued for the plain kernel (launched next)
-                if (lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
+                if ((MODE == 0 || (MODE == 1 && region_lo == 0)) && lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
                 cur += 1;
                 continue;
             }
             const uint32_t rel = (uint32_t)(my_off - off0);
             const uint32_t span = __shfl_sync(0xffffffffu, rel, nb);
             if ((uint32_t)lane <= nb) sm.roff[lane] = rel;
-            if ((uint32_t)lane < nb) sm.mask[lane] = 0;
+            if ((uint32_t)lane < nb) sm.mask[lane] = MODE == 2 ? (uint32_t)frame_hits[cur + lane] : 0u;
+            if (MODE == 2) {  // nothing to do for a batch without a live frame
+                __syncwarp();
+                const uint32_t live = (uint32_t)lane < 6 * nb ? (sm.mask[lane / 6] >> (lane % 6)) & 1u : 0u;
+                if (!__any_sync(0xffffffffu, live)) {
+                    __syncwarp();
+                    cur += nb;
+                    continue;
+                }
+            }
             // ---- stage both code spans, 16 bytes per lane and load
             // ---- stage: 16 nucleotides per lane and step (plus the 4 bytes that follow them: two are needed), translated
             //      in registers (translate.rs:114-133, dna/mod.rs:23-103, dna/translation.rs:125-144), both residue-code
@@ -521,10 +583,10 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
             const uint32_t rec = lane;
             auto done1 = [&](uint32_t tag, uint32_t v) {  // tag = record | sampled index << 5
                 const uint32_t rc = tag & 31u, sx = tag >> 5;
-                if (sx < (uint32_t)kSValRows) sm.val[sx][rc] = v;
+                if (MODE == 0 && sx < (uint32_t)kSValRows) sm.val[sx][rc] = v;
                 if (v != kNoValue && v != 0) atomicOr(&sm.mask[rc / 6], 1u << (rc % 6));
             };
-            {
+            if (MODE != 2) {
                 uint32_t a = 0, o0 = 0, cs = 0;
                 int dir = 3;
                 if (rec < 6 * nb) cs = (record_geometry<K>(sm, rec, a, dir, o0) + STRIDE - 1) / STRIDE;
@@ -542,8 +604,13 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
 #pragma unroll 1
                 for (uint32_t s0 = 0; s0 < max_cs; s0 += kSU) {
                     if (qn + 32 * kSU > (uint32_t)kSQueue) {
-                        drain_queue(t, sm.q, qn, lane, done1);
-                        qn = 0;
+                        if (MODE == 0) {
+                            drain_queue(t, sm.q, qn, lane, done1);
+                            qn = 0;
+                        } else {
+                            do qn = drain_round(t, sm.q, qn, lane, done1);
+                            while (qn + 32 * kSU > (uint32_t)kSQueue);
+                        }
                     }
                     uint64_t h[kSU];
                     ulonglong4 sec[kSU];
@@ -552,7 +619,8 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     for (int u = 0; u < kSU; ++u) {
                         h[u] = mix45(key);
                         valid[u] = s0 + u < cs && bad == 0;
-                        if (s0 + u < cs && bad != 0 && s0 + u < (uint32_t)kSValRows) sm.val[s0 + u][lane] = kNoValue;
+                        if (MODE == 1) valid[u] = valid[u] && (h[u] >> 13) >= region_lo && (h[u] >> 13) < region_hi;
+                        if (MODE == 0 && s0 + u < cs && bad != 0 && s0 + u < (uint32_t)kSValRows) sm.val[s0 + u][lane] = kNoValue;
                         if (s0 + u + 1 < cs) {  // roll on to the next sampled position
 #pragma unroll
                             for (int m = 0; m < STRIDE; ++m) {
@@ -563,27 +631,44 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                             a += dir * STRIDE;
                         }
                     }
+                    if (MODE == 1) {  // region pass: the in-region lookups are probed from the queue, densely
 #pragma unroll
-                    for (int u = 0; u < kSU; ++u)
-                        if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
-#pragma unroll
-                    for (int u = 0; u < kSU; ++u) {
-                        const uint32_t tag = rec | ((s0 + u) << 5);
-                        bool more = false;
-                        if (valid[u]) {
-                            const uint32_t v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-                            if (!more) done1(tag, v);
+                        for (int u = 0; u < kSU; ++u) {
+                            const unsigned m = __ballot_sync(0xffffffffu, valid[u]);
+                            if (valid[u]) sm.q[qn + __popc(m & lt_mask)] = h[u] | ((uint64_t)rec << 50);
+                            qn += __popc(m);
                         }
-                        const unsigned m = __ballot_sync(0xffffffffu, more);
-                        if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)tag << 50);
-                        qn += __popc(m);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kSU; ++u)
+                            if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+#pragma unroll
+                        for (int u = 0; u < kSU; ++u) {
+                            const uint32_t tag = rec | ((s0 + u) << 5);
+                            bool more = false;
+                            if (valid[u]) {
+                                const uint32_t v = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                                if (!more) done1(tag, v);
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, more);
+                            if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)tag << 50);
+                            qn += __popc(m);
+                        }
                     }
                 }
             }
-            drain_queue(t, sm.q, qn, lane, done1);
+            if (MODE == 0) drain_queue(t, sm.q, qn, lane, done1);
+            else
+                while (qn) qn = drain_round(t, sm.q, qn, lane, done1);
             qn = 0;
             __syncwarp();
-            if ((uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
+            if (MODE == 0 && (uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
+            if (MODE == 1) {  // the masks accumulate over the region passes; phase 2 is another launch
+                if ((uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)(region_lo == 0 ? sm.mask[lane] : (sm.mask[lane] | frame_hits[cur + lane]));
+                __syncwarp();
+                cur += nb;
+                continue;
+            }
             // ---- phase 2: every position of the frames with a sampled hit, in segments of `seg` positions per lane;
             //      sampled positions whose answer is still in val[] are copied, the others probed
             uint32_t cntf = 0;
@@ -629,21 +714,32 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
 #pragma unroll 1
                     for (uint32_t s0 = 0; s0 < max_cnt; s0 += kSU) {
                         if (qn + 32 * kSU > (uint32_t)kSQueue) {
-                            drain_queue(t, sm.q, qn, lane, done2);
-                            qn = 0;
+                            if (MODE == 0) {
+                                drain_queue(t, sm.q, qn, lane, done2);
+                                qn = 0;
+                            } else {
+                                do qn = drain_round(t, sm.q, qn, lane, done2);
+                                while (qn + 32 * kSU > (uint32_t)kSQueue);
+                            }
                         }
                         uint64_t h[kSU];
                         ulonglong4 sec[kSU];
                         uint32_t v[kSU];
                         bool valid[kSU];
+                        bool mine[kSU];  // MODE 2: this pass answers the position
 #pragma unroll
                         for (int u = 0; u < kSU; ++u) {
                             const bool act = s0 + u < cnt;
                             const uint32_t jj = j + s0 + u, sx = jj / STRIDE;
-                            const bool cached = act && jj % STRIDE == 0 && sx < (uint32_t)kSValRows;
+                            const bool cached = MODE == 0 && act && jj % STRIDE == 0 && sx < (uint32_t)kSValRows;
                             v[u] = cached ? sm.val[sx][rc] : kNoValue;
                             h[u] = mix45(key);
                             valid[u] = act && !cached && bad == 0;
+                            mine[u] = act;
+                            if (MODE == 2) {  // a k-mer that cannot be a key is a miss in every pass: the first one writes it
+                                mine[u] = act && (bad == 0 ? ((h[u] >> 13) >= region_lo && (h[u] >> 13) < region_hi) : region_lo == 0);
+                                valid[u] = valid[u] && mine[u];
+                            }
                             if (s0 + u + 1 < cnt) {
                                 const uint32_t c = cb[a + dir * K];
                                 key = ((key << 5) | (c & 31u)) & kKeyMask;
@@ -651,22 +747,35 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                                 a += dir;
                             }
                         }
+                        if (MODE == 2) {  // region pass: in-region lookups through the queue; a k-mer that cannot be a key is a miss
 #pragma unroll
-                        for (int u = 0; u < kSU; ++u)
-                            if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+                            for (int u = 0; u < kSU; ++u) {
+                                const uint32_t oi = o + s0 + u;
+                                if (mine[u] && !valid[u]) out0[oi] = kNoValue;
+                                const unsigned m = __ballot_sync(0xffffffffu, valid[u]);
+                                if (valid[u]) sm.q[qn + __popc(m & lt_mask)] = h[u] | ((uint64_t)oi << 50);
+                                qn += __popc(m);
+                            }
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < kSU; ++u) {
-                            bool more = false;
-                            if (valid[u]) v[u] = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
-                            const uint32_t oi = o + s0 + u;
-                            if (s0 + u < cnt && !more) out0[oi] = v[u];
-                            const unsigned m = __ballot_sync(0xffffffffu, more);
-                            if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)oi << 50);
-                            qn += __popc(m);
+                            for (int u = 0; u < kSU; ++u)
+                                if (valid[u]) sec[u] = load_sector(sector_addr(t, h[u], 0, 0));
+#pragma unroll
+                            for (int u = 0; u < kSU; ++u) {
+                                bool more = false;
+                                if (valid[u]) v[u] = probe_sector_data(sec[u], (uint32_t)h[u] & kTagMask, more);
+                                const uint32_t oi = o + s0 + u;
+                                if (mine[u] && !more) out0[oi] = v[u];
+                                const unsigned m = __ballot_sync(0xffffffffu, more);
+                                if (more) sm.q[qn + __popc(m & lt_mask)] = h[u] | (1ull << 45) | ((uint64_t)oi << 50);
+                                qn += __popc(m);
+                            }
                         }
                     }
                 }
-                drain_queue(t, sm.q, qn, lane, done2);
+                if (MODE == 0) drain_queue(t, sm.q, qn, lane, done2);
+                else
+                    while (qn) qn = drain_round(t, sm.q, qn, lane, done2);
             }
             __syncwarp();
             cur += nb;
@@ -1169,6 +1278,12 @@ void LaunchTimer::stop() {
 }
 }  // namespace umgap
 
+// Level 0 of a table larger than this is probed one hash-prefix region per launch.  Random gathers keep the full
+// line rate up to a 64 GiB footprint and lose half of it at 80 GiB (profiles/r01_randsector_sweep.log,
+// r01_vmm_pages_probe.log); the batch buffers need their share of the reach, and every pass costs a translation
+// of the batch, so the regions are as large as that allows (128 GB table: 2 regions 8.3 ms, 3 regions 10.4 ms).
+constexpr uint64_t kDefaultRegionBytes = 60ull << 30;
+
 // Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
                                     const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
@@ -1184,7 +1299,7 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
     // translation reach, profiles/r01_randsector_sweep.log) while any 64 GiB window runs at full rate:
     // a larger level 0 is probed one hash-prefix region at a time (the line index is monotone in the
     // prefix).  Every pass translates and packs all k-mers again, which costs less than the cliff.
-    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
+    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : kDefaultRegionBytes;
     const uint64_t table_bytes = (uint64_t)idx->level_nlines[0] * 128;
     const int nregions = idx->nshards > 1 ? 1 : (int)std::max<uint64_t>(1, ceil_div(table_bytes, region_bytes));
     for (int reg = 0; reg < nregions; ++reg) {
@@ -1243,6 +1358,7 @@ struct SampledPlan {  // the sampled lookup stage of one batch
     uint64_t total_nt = 0;
     uint32_t* long_count = nullptr;  // 64 counters (one per slice), then the list of reads left to the plain kernel
     uint32_t* long_list = nullptr;
+    int nregions = 1;     // > 1: level 0 exceeds the probe region, phases as separate launches per hash-prefix region
 };
 
 // reads_hint: number of reads the launch will find in its group range (sizes the grid only).
@@ -1256,19 +1372,36 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
         return 148u * (unsigned)(v > 0 ? v : kSBlocks);  // one resident wave: the units are handed out dynamically
     }();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, grid_cap);
-#define UMGAP_SAMPLED(S)                                                                                                      \
-    lookup_sampled_kernel<9, TableView, S><<<blocks, kSWarps * 32, 0, st>>>(idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev,   \
-                                                                           (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, \
-                                                                           g_lo, g_hi, sp.long_list, sp.long_count + slice,       \
-                                                                           sp.long_count + 64 + slice)
-    switch (sp.stride) {
-        case 2: UMGAP_SAMPLED(2); break;
-        case 3: UMGAP_SAMPLED(3); break;
-        default: UMGAP_SAMPLED(4); break;
+#define UMGAP_SAMPLED(S, MODE, COUNTER, LO, HI)                                                                                \
+    lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
+        idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo,  \
+        g_hi, sp.long_list, sp.long_count + slice, sp.long_count + 64 + (COUNTER), LO, HI)
+#define UMGAP_SAMPLED_STRIDES(MODE, COUNTER, LO, HI)                 \
+    switch (sp.stride) {                                             \
+        case 2: UMGAP_SAMPLED(2, MODE, COUNTER, LO, HI); break;      \
+        case 3: UMGAP_SAMPLED(3, MODE, COUNTER, LO, HI); break;      \
+        default: UMGAP_SAMPLED(4, MODE, COUNTER, LO, HI); break;     \
+    }                                                                \
+    UMGAP_CUDA(cudaGetLastError());                                  \
+    ++g_launch_count
+    if (sp.nregions <= 1) {
+        UMGAP_SAMPLED_STRIDES(0, slice, 0ull, 1ull << 32);
+    } else {
+        // phase 1 of every region (frame masks complete after the last), then phase 2 of every region; a launch
+        // confines its probes to one region of level 0 (address-translation reach, launch_translate_lookup)
+        for (int ph = 1; ph <= 2; ++ph)
+            for (int reg = 0; reg < sp.nregions; ++reg) {
+                const uint64_t lo = (1ull << 32) * reg / sp.nregions, hi = (1ull << 32) * (reg + 1) / sp.nregions;
+                const int counter = (ph - 1) * sp.nregions + reg;
+                if (ph == 1) {
+                    UMGAP_SAMPLED_STRIDES(1, counter, lo, hi);
+                } else {
+                    UMGAP_SAMPLED_STRIDES(2, counter, lo, hi);
+                }
+            }
     }
+#undef UMGAP_SAMPLED_STRIDES
 #undef UMGAP_SAMPLED
-    UMGAP_CUDA(cudaGetLastError());
-    ++g_launch_count;
     // the reads the kernel queued (longer than a warp batch; rare): every position, plain kernel over the list
     ReadList rl;
     rl.list = sp.long_list;
@@ -1287,12 +1420,13 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
                                    uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
     SampledPlan sp;
     const bool disabled = !g_sampling;
-    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : 48ull << 30;
+    const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : kDefaultRegionBytes;
+    const uint64_t nregions = std::max<uint64_t>(1, ceil_div((uint64_t)idx->level_nlines[0] * 128, region_bytes));
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
-        (uint64_t)idx->level_nlines[0] * 128 > region_bytes || !frame_hits_dev || nreads >= (1ull << 31) ||
-        ((uintptr_t)nt_dev & 15u) != 0)
+        nregions > 32 || !frame_hits_dev || nreads >= (1ull << 31) || ((uintptr_t)nt_dev & 15u) != 0)
         return sp;
     sp.stride = std::min(o->min_seed_size, 4);
+    sp.nregions = (int)nregions;
     if (!nreads) return sp;
     CodonLut lut{};
     make_code_lut(idx, o->table, o->methionine, lut);
@@ -1312,9 +1446,9 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
                             bool sliced = false) {
     if (!ngroups) return;
     const int kSlices = g_slices;
-    const bool slice_it = sliced && kSlices >= 2 && ngroups >= 4096u * (uint64_t)kSlices && nreads;
     LaunchTimer timer(0, st);
     const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
+    const bool slice_it = sliced && kSlices >= 2 && ngroups >= 4096u * (uint64_t)kSlices && nreads && sp.nregions == 1;
     if (!sp.stride) {
         timer.cancel();  // the plain launch brackets itself
         launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
