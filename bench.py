@@ -264,7 +264,8 @@ def run_ours(args):
                                       shard=rank if shard_mode else 0, nshards=world if shard_mode else 1)
     if shard_mode:
         from umgap_b200 import sharded
-        sharded.attach_all(gidx, dist)
+        if args.peer_loads:
+            sharded.attach_all(gidx, dist)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     info = gidx.info()
@@ -393,8 +394,8 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     lookups_per_launch = nreads * LOOKUPS_PER_READ
-    # a step's lookup stage = the once-per-batch bracket plus one bracket per slice (routed mode: one launch per step)
-    avg_ms = max(lookup_ms / max(1, args.steps if routed is None else lookup_n), 1e-9)
+    # a step's lookup stage = the once-per-batch bracket plus one bracket per slice (routed mode: one launch per exchange round)
+    avg_ms = max(lookup_ms / max(1, args.steps), 1e-9)   # routed mode: the local-shard lookups of both exchange rounds
     achieved = lookups_per_launch * BYTES_PER_LOOKUP / (avg_ms * 1e-3) / 1e9
     alone_ms = max(alone_lookup_ms / alone_steps, 1e-9)
     traffic = None

@@ -242,6 +242,30 @@ int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, co
                            const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev,
                            void* stream);
 
+/* Sampled form of the exchange step (behind `-o | seedextend -s S`, S >= 2, k = 9: umgap_route_sampled_applies
+ * returns 1): what umgap_classify_reads_dev does against a local table, with the lookups routed.
+ *   umgap_route_pack_sampled_dev(phase 1)  every min(S,4)-th position of every frame record -> buckets
+ *                                          (send_pos = read * 8 + frame); clears frame_hits_dev
+ *   (host) exchange, umgap_lookup_hashes_dev, exchange back
+ *   umgap_route_scatter_hits_dev           non-zero answers -> frame masks (one byte per read)
+ *   umgap_route_pack_sampled_dev(phase 2)  every position of the frames whose mask bit is up -> buckets
+ *                                          (send_pos = index into ids_dev, frame-major layout)
+ *   (host) exchange, umgap_lookup_hashes_dev, exchange back, umgap_route_scatter_dev
+ *   umgap_classify_ids_masked_dev          seedextend | uniq | taxa2agg over the flagged frames
+ * Both phases of a batch go through the same index handle, phase 1 first (it leaves the list of reads
+ * longer than a warp batch for phase 2).  frame_hits_dev: nreads bytes rounded up to 4, 4-byte aligned.  */
+int umgap_route_sampled_applies(const umgap_index* idx, const umgap_pipeline_opts* opts);
+int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase,
+                                 const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
+                                 uint64_t total_nt, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
+                                 uint64_t* cursors_dev, uint8_t* frame_hits_dev, uint32_t* ids_dev, void* stream);
+int umgap_route_scatter_hits_dev(const umgap_index* idx, const uint32_t* ans_dev, const uint32_t* send_pos_dev,
+                                 const uint64_t* cursors_dev, uint64_t cap, uint8_t* frame_hits_dev, void* stream);
+int umgap_classify_ids_masked_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                                  const uint32_t* ids_dev, const uint64_t* read_off_dev, uint64_t total_nt,
+                                  const uint64_t* group_off_dev, uint64_t ngroups, const uint8_t* frame_hits_dev,
+                                  int frame_major, uint32_t* taxon_out_dev, void* stream);
+
 /* ---- measurement aid: when enabled, every launch of the two hot-path kernels is bracketed by CUDA
  * events on the stream it is launched on.  umgap_kernel_times() waits for the recorded launches,
  * returns the summed durations (ms) and launch counts since the last call, and clears them.      */

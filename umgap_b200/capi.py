@@ -35,6 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
+    "umgap_route_sampled_applies", "umgap_route_pack_sampled_dev", "umgap_route_scatter_hits_dev", "umgap_classify_ids_masked_dev",
     "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices", "umgap_pipeline_sampling",
     "umgap_index_build_synthetic", "umgap_synth_reads_dev", "umgap_randsector_bench",
 ]
@@ -441,6 +442,36 @@ def route_scatter_dev(index: Index, ans_ptr: int, send_pos_ptr: int, cursors_ptr
     _check(load_library().umgap_route_scatter_dev(index._h, C.c_void_p(ans_ptr), C.c_void_p(send_pos_ptr),
                                                   C.c_void_p(cursors_ptr), C.c_uint64(cap), C.c_void_p(ids_ptr),
                                                   C.c_void_p(stream)))
+
+
+def route_sampled_applies(index: Index, opts: PipelineOpts) -> bool:
+    """True when the sampled form of the exchange step is exact for these options (k = 9, -o, seedextend -s >= 2)."""
+    return bool(load_library().umgap_route_sampled_applies(index._h, C.byref(opts)))
+
+
+def route_pack_sampled_dev(index: Index, opts: PipelineOpts, phase: int, nt_ptr: int, read_off_ptr: int, nreads: int,
+                           total_nt: int, cap: int, send_h_ptr: int, send_pos_ptr: int, cursors_ptr: int,
+                           frame_hits_ptr: int, ids_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_route_pack_sampled_dev(
+        index._h, C.byref(opts), C.c_int(phase), C.c_void_p(nt_ptr), C.c_void_p(read_off_ptr), C.c_uint64(nreads),
+        C.c_uint64(total_nt), C.c_uint64(cap), C.c_void_p(send_h_ptr), C.c_void_p(send_pos_ptr), C.c_void_p(cursors_ptr),
+        C.c_void_p(frame_hits_ptr), C.c_void_p(ids_ptr), C.c_void_p(stream)))
+
+
+def route_scatter_hits_dev(index: Index, ans_ptr: int, send_pos_ptr: int, cursors_ptr: int, cap: int,
+                           frame_hits_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_route_scatter_hits_dev(index._h, C.c_void_p(ans_ptr), C.c_void_p(send_pos_ptr),
+                                                       C.c_void_p(cursors_ptr), C.c_uint64(cap),
+                                                       C.c_void_p(frame_hits_ptr), C.c_void_p(stream)))
+
+
+def classify_ids_masked_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, ids_ptr: int, read_off_ptr: int,
+                            total_nt: int, group_off_ptr: int, ngroups: int, frame_hits_ptr: int, frame_major: bool,
+                            out_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_classify_ids_masked_dev(
+        index._h, tax._h, C.byref(opts), C.c_void_p(ids_ptr), C.c_void_p(read_off_ptr), C.c_uint64(total_nt),
+        C.c_void_p(group_off_ptr), C.c_uint64(ngroups), C.c_void_p(frame_hits_ptr), C.c_int(1 if frame_major else 0),
+        C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def classify_ids_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, ids_ptr: int, read_off_ptr: int, total_nt: int,

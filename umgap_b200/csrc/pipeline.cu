@@ -137,10 +137,7 @@ struct LookupSmem {
 //   frame-major     the three frame records of a strand one after the other, each contiguous (behind the sampled
 //                   lookup kernel, which writes whole frame records: fewer partially written sectors).
 // Index of position j of frame f of a strand in the frame-major layout, relative to the strand's first word.
-__device__ __forceinline__ uint32_t frame_major_index(uint32_t n, uint32_t k, uint32_t f, uint32_t j) {
-    const uint32_t c0 = n / 3 - k + 1, c1 = (n - 1) / 3 - k + 1;  // positions of frames 0 and 1 (n >= 3k)
-    return (f > 0 ? c0 : 0u) + (f > 1 ? c1 : 0u) + j;
-}
+// (frame_major_index: table.cuh)
 
 template <int K, class TV, bool REGION>
 __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
@@ -480,6 +477,69 @@ __device__ __forceinline__ uint32_t drain_round(const TV& t, uint64_t* q, uint32
     return qnext;
 }
 
+// Routed (key-range-sharded) mode: where the sampled kernel's lookups go instead of the local table -- the bucket of
+// the shard that owns the hash (route.cu; the ranks swap the buckets by NCCL and answer them from their own shard).
+struct RouteSink {
+    uint64_t* send_h = nullptr;             // [nshards][cap] hashes
+    uint32_t* send_pos = nullptr;           // [nshards][cap] where the answer belongs (phase 1: read * 8 + frame, phase 2: ids index)
+    unsigned long long* cursors = nullptr;  // [nshards] bucket fills, then [nshards] overflow flags
+    uint64_t cap = 0;
+    uint32_t nshards = 1;
+};
+
+// Appends the queued lookups (hash | tag << 50) to their owners' buckets; lanes bound for the same shard claim
+// consecutive slots with one atomic.  pos(tag) = the send_pos value.
+template <class Pos>
+__device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t* q, uint32_t qn, int lane, Pos pos) {
+    const unsigned lt_mask = (1u << lane) - 1;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t c = 0; c < qn; c += 32) {
+        const bool active = c + lane < qn;
+        const uint64_t e = active ? q[c + lane] : 0ull;
+        const uint64_t h = e & kKeyMask;
+        uint32_t local32;
+        const uint32_t owner = shard_split(h, rs.nshards, local32);
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(act, owner);
+            const int leader = __ffs(peers) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&rs.cursors[owner], (unsigned long long)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const unsigned long long at = base + __popc(peers & lt_mask);
+            if (at < rs.cap) {
+                rs.send_h[(uint64_t)owner * rs.cap + at] = h;
+                rs.send_pos[(uint64_t)owner * rs.cap + at] = pos((uint32_t)(e >> 50));
+            } else {
+                rs.cursors[rs.nshards + owner] = 1;  // bucket overflow: the host retries with a larger capacity
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Makes room in (all = false) or empties (all = true) the per-warp queue of the sampled kernel, by its mode.
+template <int MODE, class TV, class Done, class Pos>
+__device__ __forceinline__ uint32_t service_queue(const TV& t, const RouteSink& rs, uint64_t* q, uint32_t qn, int lane, bool all,
+                                                  uint32_t room, Done done, Pos pos) {
+    if (MODE == 0) {
+        drain_queue(t, q, qn, lane, done);
+        return 0;
+    }
+    if (MODE <= 2) {
+        if (all) {
+            while (qn) qn = drain_round(t, q, qn, lane, done);
+        } else {
+            do qn = drain_round(t, q, qn, lane, done);
+            while (qn + room > (uint32_t)kSQueue);
+        }
+        return qn;
+    }
+    route_flush(rs, q, qn, lane, pos);
+    return 0;
+}
+
 // Geometry of frame record rec (= read-in-batch * 6 + frame) from the batch's read offsets: number of
 // k-mer positions cntf, shared-memory byte address a0 of the first residue of position 0 (relative to
 // the batch's first forward code), address step per position dir (+3 forward, -3 reverse; residue kk
@@ -500,14 +560,17 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
 // region [region_lo, region_hi) per pass (launch_translate_lookup) run the phases as separate launches: MODE 1 =
 // phase 1 of one region (only the frame masks leave the kernel, OR-ed over the passes), MODE 2 = phase 2 of one
 // region (every position of the live frames whose hash prefix lies in the region, sampled ones included; batches
-// without a live frame are not even translated).
+// without a live frame are not even translated).  MODE 3 / 4: the two phases of the routed mode -- the walk is the same,
+// the lookups go to the owners' buckets (RouteSink) instead of the table; phase 1's answers come back as frame masks
+// (route_scatter_hits_kernel), phase 2 sends every position of the live frames.
 template <int K, class TV, int STRIDE, int MODE>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
 lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
                       uint64_t total_nt, const uint64_t* __restrict__ read_off, uint32_t nreads, uint32_t* __restrict__ ids,
                       uint8_t* __restrict__ frame_hits, const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
                       uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ unit_count,
-                      uint64_t region_lo, uint64_t region_hi) {
+                      uint64_t region_lo, uint64_t region_hi, const __grid_constant__ RouteSink rs) {
+    constexpr bool kPhase2Only = MODE == 2 || MODE == 4;
     __shared__ SampledSmem s_sm[kSWarps];
     __shared__ uint16_t s_pair[65];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -538,15 +601,16 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
             const unsigned fits = __ballot_sync(0xffffffffu, lane >= 1 && (uint32_t)lane <= left && my_off - off0 <= (uint64_t)kSSpan);
             const uint32_t nb = (uint32_t)__popc(fits);
             if (nb == 0) {  // a single read longer than the batch span: queued for the plain kernel (launched next)
-                if ((MODE == 0 || (MODE == 1 && region_lo == 0)) && lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
+                if ((MODE == 0 || MODE == 3 || (MODE == 1 && region_lo == 0)) && lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
+                if (MODE == 3 && lane == 0) frame_hits[cur] = 0x3F;  // routed: the plain pack kernel sends every position of it
                 cur += 1;
                 continue;
             }
             const uint32_t rel = (uint32_t)(my_off - off0);
             const uint32_t span = __shfl_sync(0xffffffffu, rel, nb);
             if ((uint32_t)lane <= nb) sm.roff[lane] = rel;
-            if ((uint32_t)lane < nb) sm.mask[lane] = MODE == 2 ? (uint32_t)frame_hits[cur + lane] : 0u;
-            if (MODE == 2) {  // nothing to do for a batch without a live frame
+            if ((uint32_t)lane < nb) sm.mask[lane] = kPhase2Only ? (uint32_t)frame_hits[cur + lane] : 0u;
+            if (kPhase2Only) {  // nothing to do for a batch without a live frame
                 __syncwarp();
                 const uint32_t live = (uint32_t)lane < 6 * nb ? (sm.mask[lane / 6] >> (lane % 6)) & 1u : 0u;
                 if (!__any_sync(0xffffffffu, live)) {
@@ -586,7 +650,10 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                 if (MODE == 0 && sx < (uint32_t)kSValRows) sm.val[sx][rc] = v;
                 if (v != kNoValue && v != 0) atomicOr(&sm.mask[rc / 6], 1u << (rc % 6));
             };
-            if (MODE != 2) {
+            const uint32_t cur0 = cur;
+            auto pos1 = [&](uint32_t tag) { return (cur0 + tag / 6u) * 8u + tag % 6u; };       // routed phase 1: read * 8 + frame
+            auto pos2 = [&](uint32_t tag) { return (uint32_t)(2 * off0) + tag; };               // routed phase 2: index into ids
+            if (!kPhase2Only) {
                 uint32_t a = 0, o0 = 0, cs = 0;
                 int dir = 3;
                 if (rec < 6 * nb) cs = (record_geometry<K>(sm, rec, a, dir, o0) + STRIDE - 1) / STRIDE;
@@ -603,15 +670,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                 const uint32_t max_cs = __reduce_max_sync(0xffffffffu, cs);
 #pragma unroll 1
                 for (uint32_t s0 = 0; s0 < max_cs; s0 += kSU) {
-                    if (qn + 32 * kSU > (uint32_t)kSQueue) {
-                        if (MODE == 0) {
-                            drain_queue(t, sm.q, qn, lane, done1);
-                            qn = 0;
-                        } else {
-                            do qn = drain_round(t, sm.q, qn, lane, done1);
-                            while (qn + 32 * kSU > (uint32_t)kSQueue);
-                        }
-                    }
+                    if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done1, pos1);
                     uint64_t h[kSU];
                     ulonglong4 sec[kSU];
                     bool valid[kSU];
@@ -631,7 +690,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                             a += dir * STRIDE;
                         }
                     }
-                    if (MODE == 1) {  // region pass: the in-region lookups are probed from the queue, densely
+                    if (MODE == 1 || MODE == 3) {  // region pass: the in-region lookups are probed from the queue, densely; routed: all go to the buckets
 #pragma unroll
                         for (int u = 0; u < kSU; ++u) {
                             const unsigned m = __ballot_sync(0xffffffffu, valid[u]);
@@ -657,14 +716,16 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     }
                 }
             }
-            if (MODE == 0) drain_queue(t, sm.q, qn, lane, done1);
-            else
-                while (qn) qn = drain_round(t, sm.q, qn, lane, done1);
-            qn = 0;
+            qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done1, pos1);
             __syncwarp();
             if (MODE == 0 && (uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
             if (MODE == 1) {  // the masks accumulate over the region passes; phase 2 is another launch
                 if ((uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)(region_lo == 0 ? sm.mask[lane] : (sm.mask[lane] | frame_hits[cur + lane]));
+                __syncwarp();
+                cur += nb;
+                continue;
+            }
+            if (MODE == 3) {  // the masks come back from the owners of the hashes
                 __syncwarp();
                 cur += nb;
                 continue;
@@ -713,15 +774,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     const uint32_t max_cnt = __reduce_max_sync(0xffffffffu, cnt);
 #pragma unroll 1
                     for (uint32_t s0 = 0; s0 < max_cnt; s0 += kSU) {
-                        if (qn + 32 * kSU > (uint32_t)kSQueue) {
-                            if (MODE == 0) {
-                                drain_queue(t, sm.q, qn, lane, done2);
-                                qn = 0;
-                            } else {
-                                do qn = drain_round(t, sm.q, qn, lane, done2);
-                                while (qn + 32 * kSU > (uint32_t)kSQueue);
-                            }
-                        }
+                        if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done2, pos2);
                         uint64_t h[kSU];
                         ulonglong4 sec[kSU];
                         uint32_t v[kSU];
@@ -747,7 +800,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                                 a += dir;
                             }
                         }
-                        if (MODE == 2) {  // region pass: in-region lookups through the queue; a k-mer that cannot be a key is a miss
+                        if (kPhase2Only) {  // region pass: in-region lookups through the queue (routed: all, to the buckets); a k-mer that cannot be a key is a miss
 #pragma unroll
                             for (int u = 0; u < kSU; ++u) {
                                 const uint32_t oi = o + s0 + u;
@@ -773,9 +826,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                         }
                     }
                 }
-                if (MODE == 0) drain_queue(t, sm.q, qn, lane, done2);
-                else
-                    while (qn) qn = drain_round(t, sm.q, qn, lane, done2);
+                qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done2, pos2);
             }
             __syncwarp();
             cur += nb;
@@ -1375,7 +1426,7 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
 #define UMGAP_SAMPLED(S, MODE, COUNTER, LO, HI)                                                                                \
     lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
         idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo,  \
-        g_hi, sp.long_list, sp.long_count + slice, sp.long_count + 64 + (COUNTER), LO, HI)
+        g_hi, sp.long_list, sp.long_count + slice, sp.long_count + 64 + (COUNTER), LO, HI, RouteSink())
 #define UMGAP_SAMPLED_STRIDES(MODE, COUNTER, LO, HI)                 \
     switch (sp.stride) {                                             \
         case 2: UMGAP_SAMPLED(2, MODE, COUNTER, LO, HI); break;      \
@@ -1609,6 +1660,98 @@ int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, co
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
         launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, nullptr, scratch, taxon_out_dev, err, st);
+    });
+}
+
+int umgap_classify_ids_masked_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                                  const uint32_t* ids_dev, const uint64_t* read_off_dev, uint64_t total_nt,
+                                  const uint64_t* group_off_dev, uint64_t ngroups, const uint8_t* frame_hits_dev,
+                                  int frame_major, uint32_t* taxon_out_dev, void* stream) {
+    return guarded([&] {
+        check_opts(idx, tax, opts);
+        if (!tax || !ids_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(idx->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
+        DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
+        UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
+        launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch, taxon_out_dev, err, st,
+                        frame_major != 0);
+    });
+}
+
+extern "C++" {
+namespace umgap {
+void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                            const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
+                            uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
+                            cudaStream_t st);  // route.cu
+}
+}
+
+int umgap_route_sampled_applies(const umgap_index* idx, const umgap_pipeline_opts* o) {
+    return idx && o && g_sampling && o->seedextend && o->one_on_one && o->min_seed_size >= 2 && idx->k == 9 ? 1 : 0;
+}
+
+int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
+                                 const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
+                                 uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev,
+                                 uint8_t* frame_hits_dev, uint32_t* ids_dev, void* stream) {
+    return guarded([&] {
+        if (!idx || !opts || !send_h_dev || !send_pos_dev || !cursors_dev || !ids_dev || !frame_hits_dev)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (!umgap_route_sampled_applies(idx, opts))
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "sampled routing needs k = 9, -o and seedextend -s >= 2 (umgap_route_sampled_applies)");
+        if (phase != 1 && phase != 2) UMGAP_FAIL(UMGAP_ERR_INVALID, "phase must be 1 or 2");
+        if (2 * total_nt >= (1ull << 32) || nreads >= (1ull << 28)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large for 32-bit positions");
+        if (((uintptr_t)nt_dev & 15u) || ((uintptr_t)frame_hits_dev & 3u)) UMGAP_FAIL(UMGAP_ERR_INVALID, "nt_dev must be 16-byte, frame_hits_dev 4-byte aligned");
+        use_device(idx->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        UMGAP_CUDA(cudaMemsetAsync(cursors_dev, 0, 2 * (size_t)idx->nshards * sizeof(uint64_t), st));
+        // 64 long-read counters, 64 unit counters, then the list of the reads longer than a warp batch (filled by phase 1)
+        uint32_t* counters = (uint32_t*)idx->ws.get(WS_LONG, (128 + nreads) * sizeof(uint32_t));
+        if (phase == 1) {
+            UMGAP_CUDA(cudaMemsetAsync(counters, 0, 128 * sizeof(uint32_t), st));
+            UMGAP_CUDA(cudaMemsetAsync(frame_hits_dev, 0, (nreads + 3) / 4 * 4, st));
+        } else {
+            UMGAP_CUDA(cudaMemsetAsync(counters + 64, 0, 64 * sizeof(uint32_t), st));
+        }
+        if (!nreads) return;
+        CodonLut lut{};
+        make_code_lut(idx, opts->table, opts->methionine, lut);
+        RouteSink rs;
+        rs.send_h = send_h_dev;
+        rs.send_pos = send_pos_dev;
+        rs.cursors = reinterpret_cast<unsigned long long*>(cursors_dev);
+        rs.cap = cap;
+        rs.nshards = (uint32_t)idx->nshards;
+        const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads, kSReads), kSWarps) + 1, 148ull * kSBlocks);
+        const int stride = std::min(opts->min_seed_size, 4);
+#define UMGAP_ROUTE_SAMPLED(S, MODE)                                                                                          \
+    lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
+        idx->view(), lut, nt_dev, total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, counters + 128, \
+        counters, counters + 64, 0ull, 1ull << 32, rs)
+        if (phase == 1) {
+            switch (stride) {
+                case 2: UMGAP_ROUTE_SAMPLED(2, 3); break;
+                case 3: UMGAP_ROUTE_SAMPLED(3, 3); break;
+                default: UMGAP_ROUTE_SAMPLED(4, 3); break;
+            }
+        } else {
+            switch (stride) {
+                case 2: UMGAP_ROUTE_SAMPLED(2, 4); break;
+                case 3: UMGAP_ROUTE_SAMPLED(3, 4); break;
+                default: UMGAP_ROUTE_SAMPLED(4, 4); break;
+            }
+        }
+#undef UMGAP_ROUTE_SAMPLED
+        UMGAP_CUDA(cudaGetLastError());
+        ++g_launch_count;
+        if (phase == 2) {  // every position of the reads longer than a warp batch
+            launch_route_pack_list(idx, opts, nt_dev, read_off_dev, cap, send_h_dev, send_pos_dev, cursors_dev, ids_dev, counters + 128,
+                                   counters, st);
+            ++g_launch_count;
+        }
     });
 }
 

@@ -33,7 +33,9 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
                   const uint64_t* __restrict__ read_off, uint64_t nreads, uint64_t cap,
                   uint64_t* __restrict__ send_h, uint32_t* __restrict__ send_pos,
                   unsigned long long* __restrict__ cursors /* [nshards] + [nshards]: overflow flag */,
-                  uint32_t* __restrict__ ids) {
+                  uint32_t* __restrict__ ids, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
+    // list set: only the reads list[0 .. *list_count) (those the sampled pack kernel left over: longer than one of its
+    // batches), their ids in the frame-major layout the classify kernel reads behind the sampled path
     constexpr int W = kRouteTile + 3 * (K - 1);
     __shared__ uint8_t s_lut[72];
     __shared__ uint8_t s_nt[kRouteWarps][W + 4];
@@ -44,7 +46,9 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
     if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
     __syncthreads();
     const uint64_t nwarps = (uint64_t)gridDim.x * kRouteWarps;
-    for (uint64_t r = (uint64_t)blockIdx.x * kRouteWarps + warp; r < nreads; r += nwarps) {
+    if (list) nreads = *list_count;
+    for (uint64_t ri = (uint64_t)blockIdx.x * kRouteWarps + warp; ri < nreads; ri += nwarps) {
+        const uint64_t r = list ? list[ri] : ri;
         const uint64_t off = read_off[r];
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         if (n < 3u * K) continue;
@@ -80,7 +84,8 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
                     const uint32_t p = w0 + pl;
                     const bool live = p < npos;
                     const bool valid = live && !(bad & 0x80u);
-                    const uint32_t pos = strand ? n + (npos - 1 - p) : p;
+                    const uint32_t y = strand ? npos - 1 - p : p;
+                    const uint32_t pos = (strand ? n : 0u) + (list ? frame_major_index(n, K, y % 3, y / 3) : y);
                     if (live && !valid) out[pos] = kNoValue;
                     const uint64_t h = mix45(key);
                     uint32_t local32;
@@ -152,6 +157,37 @@ __global__ void route_scatter_kernel(const uint32_t* __restrict__ ans, const uin
     }
 }
 
+// Answers of the sampled pack phase 1 (send_pos = read * 8 + frame): a non-zero taxon raises the frame's bit in the
+// read's frame mask (bytes of frame_hits, OR-ed word-wise).
+__global__ void route_scatter_hits_kernel(const uint32_t* __restrict__ ans, const uint32_t* __restrict__ send_pos,
+                                          const unsigned long long* __restrict__ cursors, uint32_t nshards, uint64_t cap,
+                                          uint32_t* __restrict__ frame_hits_words) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t o = 0; o < nshards; ++o) {
+        const uint64_t n = cursors[o] < cap ? cursors[o] : cap;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint32_t v = ans[(uint64_t)o * cap + i];
+            if (v != 0 && v != kNoValue) {
+                const uint32_t pos = send_pos[(uint64_t)o * cap + i], rd = pos >> 3, f = pos & 7u;
+                atomicOr(&frame_hits_words[rd >> 2], (1u << f) << (8 * (rd & 3u)));
+            }
+        }
+    }
+}
+
+// The plain pack kernel over a device work list (pipeline.cu: umgap_route_pack_sampled_dev, phase 2).
+void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                            const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
+                            uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
+                            cudaStream_t st) {
+    CodonLut72 lut{};
+    make_code_lut_public(idx, opts->table, opts->methionine, lut.v);
+    route_pack_kernel<9><<<148, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, 0, cap, send_h_dev,
+                                                          send_pos_dev, reinterpret_cast<unsigned long long*>(cursors_dev),
+                                                          ids_dev, list, list_count);
+    UMGAP_CUDA(cudaGetLastError());
+}
+
 }  // namespace umgap
 
 using namespace umgap;
@@ -175,7 +211,8 @@ int umgap_route_pack_dev(const umgap_index* idx, const umgap_pipeline_opts* opts
         const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kRouteWarps), 148ull * 32);
         route_pack_kernel<9><<<blocks, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, nreads, cap,
                                                                  send_h_dev, send_pos_dev,
-                                                                 reinterpret_cast<unsigned long long*>(cursors_dev), ids_dev);
+                                                                 reinterpret_cast<unsigned long long*>(cursors_dev), ids_dev,
+                                                                 nullptr, nullptr);
         UMGAP_CUDA(cudaGetLastError());
     });
 }
@@ -203,6 +240,20 @@ int umgap_route_scatter_dev(const umgap_index* idx, const uint32_t* ans_dev, con
         route_scatter_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(ans_dev, send_pos_dev,
                                                                        reinterpret_cast<const unsigned long long*>(cursors_dev),
                                                                        (uint32_t)idx->nshards, cap, ids_dev);
+        UMGAP_CUDA(cudaGetLastError());
+    });
+}
+
+int umgap_route_scatter_hits_dev(const umgap_index* idx, const uint32_t* ans_dev, const uint32_t* send_pos_dev,
+                                 const uint64_t* cursors_dev, uint64_t cap, uint8_t* frame_hits_dev, void* stream) {
+    return guarded([&] {
+        if (!idx || !ans_dev || !send_pos_dev || !cursors_dev || !frame_hits_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if ((uintptr_t)frame_hits_dev & 3u) UMGAP_FAIL(UMGAP_ERR_INVALID, "frame_hits_dev must be 4-byte aligned");
+        use_device(idx->device);
+        route_scatter_hits_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(ans_dev, send_pos_dev,
+                                                                            reinterpret_cast<const unsigned long long*>(cursors_dev),
+                                                                            (uint32_t)idx->nshards, cap,
+                                                                            reinterpret_cast<uint32_t*>(frame_hits_dev));
         UMGAP_CUDA(cudaGetLastError());
     });
 }

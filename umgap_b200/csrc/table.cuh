@@ -148,4 +148,12 @@ __device__ __forceinline__ uint32_t table_lookup(const TV& t, uint64_t key) {
     return probe_continue(t, mix45(key), 0, 0);
 }
 
+// Layouts of a read's ids (2n words; strand s in words [s * n, s * n + npos)): position-major, or frame-major = the
+// three frame records of a strand one after the other, each contiguous.  Index of position j of frame f of a strand
+// in the frame-major layout, relative to the strand's first word (n nucleotides, k residues per key, n >= 3k).
+__device__ __forceinline__ uint32_t frame_major_index(uint32_t n, uint32_t k, uint32_t f, uint32_t j) {
+    const uint32_t c0 = n / 3 - k + 1, c1 = (n - 1) / 3 - k + 1;  // positions of frames 0 and 1
+    return (f > 0 ? c0 : 0u) + (f > 1 ? c1 : 0u) + j;
+}
+
 }  // namespace umgap

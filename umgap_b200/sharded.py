@@ -1,9 +1,12 @@
 """Key-range-sharded index across the GPUs of one node (mode 2).
 
-Every rank (one process per GPU) builds the shard of the table that owns its hash range, the ranks
-exchange the shards' CUDA IPC descriptors with one ``all_gather`` at start-up and attach them; from
-then on the lookup kernel loads remote sectors straight from the owning GPU's HBM over NVLink peer
-mappings.  The exchange below is control-plane only -- there is no collective on the data path.
+Every rank (one process per GPU) builds the shard of the table that owns its hash range.  Two ways to reach a key
+another rank owns:
+
+* ``RoutedClassifier`` (the default of ``bench.py --sharded``): the exchange step -- packed k-mer hashes travel to
+  their owners and the answers back (NCCL over NVLink), every lookup runs against local HBM;
+* ``attach_all``: the ranks swap the shards' CUDA IPC descriptors once and the lookup kernel loads remote sectors
+  through peer mappings (no collective on the data path; request-rate bound, kept for comparison and tests).
 """
 from __future__ import annotations
 
@@ -27,11 +30,20 @@ def attach_all(index: capi.Index, dist, device=None) -> None:
 
 
 class RoutedClassifier:
-    """Per-batch driver of the routed sharded mode: pack + bucket -> all-to-all (hashes) -> local
-    lookups -> all-to-all (answers) -> scatter -> classify.  One instance per rank; `index` is this
-    rank's shard.  The two all-to-alls are the only collectives on the data path."""
+    """Per-batch driver of the routed sharded mode.  One instance per rank; `index` is this rank's shard.
 
-    def __init__(self, index: capi.Index, tax: capi.Taxonomy, dist, max_total_nt: int, slack: float = 1.08):
+    Behind `-o | seedextend -s S` (S >= 2; capi.route_sampled_applies) the batch takes the two phases of the sampled
+    lookups (pipeline.cu: lookup_sampled_kernel), each an exchange round:
+      phase 1  every min(S,4)-th position of every frame record -> owners' buckets -> exchange -> local lookups ->
+               exchange back -> frame masks;
+      phase 2  every position of the frames with a sampled hit -> buckets -> exchange -> lookups -> exchange back ->
+               ids;  then the classify kernel over the flagged frames.
+    Otherwise one round with every position.  An exchange round moves only the filled part of each bucket: the fills
+    are swapped first (one small all-to-all, read on the host), then grouped NCCL send/recv of the hashes (8 B per
+    lookup) and, after the lookups, of the answers (4 B back).  These are the only collectives on the data path."""
+
+    def __init__(self, index: capi.Index, tax: capi.Taxonomy, dist, max_total_nt: int, slack: float = 1.08,
+                 max_reads: int | None = None):
         import torch
         self.index, self.tax, self.dist, self.torch = index, tax, dist, torch
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
@@ -48,22 +60,74 @@ class RoutedClassifier:
         self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=dev)
         self.recv_counts = torch.zeros(G, dtype=torch.int64, device=dev)
         self.ids = torch.empty(2 * self.max_total_nt + 64, dtype=torch.int32, device=dev)
+        self.max_reads = int(max_reads) if max_reads is not None else self.max_total_nt // 27 + 1
+        self.frame_hits = torch.zeros(self.max_reads + 8, dtype=torch.uint8, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.bool, device=dev)
+        self.lookups_routed = 0   # hashes this rank sent in the last batch (both phases)
+
+    # -- one exchange round: buckets out, lookups in the local shard, answers back into self.ans_back
+    def _round(self, st) -> None:
+        torch, dist = self.torch, self.dist
+        G, cap, me = self.world, self.cap, self.rank
+        self.overflow |= self.cursors[G:].any()
+        fills = self.cursors[:G].clamp(max=cap)
+        dist.all_to_all_single(self.recv_counts, fills)                                # bucket fills
+        both = torch.stack([fills, self.recv_counts]).cpu()                            # the one host read of a round
+        sc, rc = both[0].tolist(), both[1].tolist()
+        self.lookups_routed += sum(sc)
+        self._swap(self.send_h, sc, self.recv_h, rc)                                   # hashes: 8 B per lookup
+        capi.lookup_hashes_dev(self.index, self.recv_h.data_ptr(), self.recv_counts.data_ptr(), G, cap,
+                               self.ans.data_ptr(), st)
+        self._swap(self.ans, rc, self.ans_back, sc)                                    # answers: 4 B per lookup
+
+    def _swap(self, send, send_counts, recv, recv_counts) -> None:
+        dist = self.dist
+        cap, me = self.cap, self.rank
+        ops = []
+        for peer in range(self.world):
+            if peer == me:
+                continue
+            if send_counts[peer]:
+                ops.append(dist.P2POp(dist.isend, send[peer * cap: peer * cap + send_counts[peer]], peer))
+            if recv_counts[peer]:
+                ops.append(dist.P2POp(dist.irecv, recv[peer * cap: peer * cap + recv_counts[peer]], peer))
+        n = send_counts[me]
+        if n:
+            recv[me * cap: me * cap + n].copy_(send[me * cap: me * cap + n])           # this rank's own bucket
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
 
     def classify(self, opts, nt, read_off, group_off, out, total_nt: int) -> None:
         """nt (uint8), read_off / group_off (int64), out (int32): CUDA tensors of this rank's batch."""
-        torch, dist = self.torch, self.dist
+        torch = self.torch
         if total_nt > self.max_total_nt:
             raise ValueError("batch larger than the buffers of this RoutedClassifier")
-        G, cap = self.world, self.cap
+        cap = self.cap
         st = torch.cuda.current_stream().cuda_stream
         nreads, ngroups = read_off.numel() - 1, group_off.numel() - 1
+        self.overflow.zero_()
+        self.lookups_routed = 0
+        if capi.route_sampled_applies(self.index, opts) and nt.data_ptr() % 16 == 0:
+            if nreads > self.max_reads:
+                raise ValueError("more reads than the frame-mask buffer of this RoutedClassifier holds")
+            for phase in (1, 2):
+                capi.route_pack_sampled_dev(self.index, opts, phase, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
+                                            self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(),
+                                            self.frame_hits.data_ptr(), self.ids.data_ptr(), st)
+                self._round(st)
+                if phase == 1:
+                    capi.route_scatter_hits_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
+                                                self.cursors.data_ptr(), cap, self.frame_hits.data_ptr(), st)
+                else:
+                    capi.route_scatter_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
+                                           self.cursors.data_ptr(), cap, self.ids.data_ptr(), st)
+            capi.classify_ids_masked_dev(self.index, self.tax, opts, self.ids.data_ptr(), read_off.data_ptr(), total_nt,
+                                         group_off.data_ptr(), ngroups, self.frame_hits.data_ptr(), True, out.data_ptr(), st)
+            return
         capi.route_pack_dev(self.index, opts, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
                             self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(), self.ids.data_ptr(), st)
-        dist.all_to_all_single(self.recv_counts, self.cursors[:G].contiguous())      # bucket fills
-        dist.all_to_all_single(self.recv_h, self.send_h)                              # hashes: G equal buckets of cap
-        capi.lookup_hashes_dev(self.index, self.recv_h.data_ptr(), self.recv_counts.data_ptr(), G, cap,
-                               self.ans.data_ptr(), st)
-        dist.all_to_all_single(self.ans_back, self.ans)                               # answers
+        self._round(st)
         capi.route_scatter_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(),
                                cap, self.ids.data_ptr(), st)
         capi.classify_ids_dev(self.index, self.tax, opts, self.ids.data_ptr(), read_off.data_ptr(), total_nt,
@@ -71,4 +135,4 @@ class RoutedClassifier:
 
     def overflowed(self) -> bool:
         """True when a bucket overflowed in the last batch (extreme key skew): rebuild with more slack."""
-        return bool(self.cursors[self.world:].any().item())
+        return bool(self.overflow.item())
