@@ -80,7 +80,9 @@ def pipeline_config(args, extra=None):
         "index": ("key-range sharded over the GPUs, " + ("remote sectors read over NVLink peer mappings" if getattr(args, "peer_loads", False)
                                                            else "packed k-mer hashes and answers exchanged by NCCL all-to-all") if getattr(args, "sharded", False)
                   else "replicated per GPU") if args.gpus > 1 else "single GPU",
-        "partitioning": f"reads partitioned over {args.gpus} GPU(s), no data-path collective",
+        "partitioning": f"reads partitioned over {args.gpus} GPU(s), " + (
+            "two exchange rounds per batch (sampled positions, then the live frames): grouped NCCL send/recv of the filled bucket parts"
+            if getattr(args, "sharded", False) and not getattr(args, "peer_loads", False) and args.gpus > 1 else "no data-path collective"),
         "cache": "inputs larger than L2: every step reads a different 300 MB batch and probes a table of GBs",
     }
     if extra:
@@ -332,6 +334,14 @@ def run_ours(args):
     alone_lookup_ms, _, alone_classify_ms, _ = capi.kernel_times()
     capi.pipeline_slices(slices)
     capi.kernel_timing(False)
+    routed_stages = None
+    if routed is not None:   # where a routed step spends its time: a few extra steps with event brackets around the stages
+        routed.profile = True
+        for s in range(alone_steps):
+            step(s)
+        routed.profile = False
+        routed_stages = {k: round(v / alone_steps, 3) for k, v in routed.stage_ms.items()}
+        routed_stages["lookups_routed_per_step"] = routed.lookups_routed
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -457,6 +467,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "kernel_ms": {"translate_lookup": lookup_ms, "classify": classify_ms},
     }
+    if routed_stages is not None:
+        line["routed_stages_ms_per_step"] = routed_stages
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

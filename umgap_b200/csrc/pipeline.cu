@@ -487,27 +487,43 @@ struct RouteSink {
     uint32_t nshards = 1;
 };
 
-// Appends the queued lookups (hash | tag << 50) to their owners' buckets; lanes bound for the same shard claim
-// consecutive slots with one atomic.  pos(tag) = the send_pos value.
+// Appends the queued lookups (hash | tag << 50) to their owners' buckets.  One atomic per owner and flush: lane o
+// counts the queue's entries bound for shard o, claims that many consecutive slots of bucket o, and hands them out
+// chunk by chunk (a claim per 32-entry chunk was measured: the two or eight cursors are same-address atomics, 10 M of
+// them per 1 M pairs, and the pack kernels ran at a third of their speed).  pos(tag) = the send_pos value.
 template <class Pos>
 __device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t* q, uint32_t qn, int lane, Pos pos) {
     const unsigned lt_mask = (1u << lane) - 1;
     __syncwarp();
+    uint32_t mine = 0;  // lane o: entries bound for shard o
+#pragma unroll 1
+    for (uint32_t c = 0; c < qn; c += 32) {
+        const bool active = c + lane < qn;
+        uint32_t local32;
+        const uint32_t owner = active ? shard_split(q[c + lane] & kKeyMask, rs.nshards, local32) : 0xFFFFFFFFu;
+        for (uint32_t o = 0; o < rs.nshards; ++o) {
+            const unsigned m = __ballot_sync(0xffffffffu, owner == o);
+            if ((uint32_t)lane == o) mine += __popc(m);
+        }
+    }
+    unsigned long long next = 0;  // lane o: next free slot of bucket o
+    if ((uint32_t)lane < rs.nshards && mine) next = atomicAdd(&rs.cursors[lane], (unsigned long long)mine);
 #pragma unroll 1
     for (uint32_t c = 0; c < qn; c += 32) {
         const bool active = c + lane < qn;
         const uint64_t e = active ? q[c + lane] : 0ull;
         const uint64_t h = e & kKeyMask;
         uint32_t local32;
-        const uint32_t owner = shard_split(h, rs.nshards, local32);
-        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const uint32_t owner = active ? shard_split(h, rs.nshards, local32) : 0xFFFFFFFFu;
+        const unsigned long long base = __shfl_sync(0xffffffffu, next, active ? (int)owner : 0);
+        uint32_t before = 0;  // entries of this chunk bound for the same shard in lower lanes
+        for (uint32_t o = 0; o < rs.nshards; ++o) {
+            const unsigned m = __ballot_sync(0xffffffffu, owner == o);
+            if (owner == o) before = __popc(m & lt_mask);
+            if ((uint32_t)lane == o) next += __popc(m);
+        }
         if (active) {
-            const unsigned peers = __match_any_sync(act, owner);
-            const int leader = __ffs(peers) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&rs.cursors[owner], (unsigned long long)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const unsigned long long at = base + __popc(peers & lt_mask);
+            const unsigned long long at = base + before;
             if (at < rs.cap) {
                 rs.send_h[(uint64_t)owner * rs.cap + at] = h;
                 rs.send_pos[(uint64_t)owner * rs.cap + at] = pos((uint32_t)(e >> 50));

@@ -64,23 +64,55 @@ class RoutedClassifier:
         self.frame_hits = torch.zeros(self.max_reads + 8, dtype=torch.uint8, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.bool, device=dev)
         self.lookups_routed = 0   # hashes this rank sent in the last batch (both phases)
+        self.profile = False      # True: CUDA-event brackets around the stages of a batch, summed in self.stage_ms
+        self.stage_ms: dict = {}
+        self._marks: list = []
 
-    # -- one exchange round: buckets out, lookups in the local shard, answers back into self.ans_back
+    def _mark(self, name: str) -> None:
+        if self.profile:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def _collect(self) -> None:
+        if not self.profile or not self._marks:
+            return
+        self.torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self._marks, self._marks[1:]):
+            self.stage_ms[name] = self.stage_ms.get(name, 0.0) + a.elapsed_time(b)
+        self._marks = []
+
+    # -- one exchange round: buckets out, lookups in the local shard, answers back into self.ans_back.  This rank's own
+    #    bucket is neither sent nor copied: it is looked up in place while the other buckets travel.
     def _round(self, st) -> None:
         torch, dist = self.torch, self.dist
         G, cap, me = self.world, self.cap, self.rank
         self.overflow |= self.cursors[G:].any()
-        fills = self.cursors[:G].clamp(max=cap)
-        dist.all_to_all_single(self.recv_counts, fills)                                # bucket fills
-        both = torch.stack([fills, self.recv_counts]).cpu()                            # the one host read of a round
+        self.fills = self.cursors[:G].clamp(max=cap)
+        dist.all_to_all_single(self.recv_counts, self.fills)                           # bucket fills
+        both = torch.stack([self.fills, self.recv_counts]).cpu()                       # the one host read of a round
         sc, rc = both[0].tolist(), both[1].tolist()
         self.lookups_routed += sum(sc)
-        self._swap(self.send_h, sc, self.recv_h, rc)                                   # hashes: 8 B per lookup
-        capi.lookup_hashes_dev(self.index, self.recv_h.data_ptr(), self.recv_counts.data_ptr(), G, cap,
-                               self.ans.data_ptr(), st)
-        self._swap(self.ans, rc, self.ans_back, sc)                                    # answers: 4 B per lookup
+        self._mark("counts")
+        works = self._swap(self.send_h, sc, self.recv_h, rc)                           # hashes: 8 B per lookup
+        if sc[me]:
+            capi.lookup_hashes_dev(self.index, self.send_h.data_ptr() + 8 * me * cap, self.fills.data_ptr() + 8 * me, 1, cap,
+                                   self.ans_back.data_ptr() + 4 * me * cap, st)
+        self._mark("lookup_own_bucket")
+        for w in works:
+            w.wait()
+        self._mark("swap_hashes_exposed")
+        self.recv_counts[me] = 0
+        if G > 1:
+            capi.lookup_hashes_dev(self.index, self.recv_h.data_ptr(), self.recv_counts.data_ptr(), G, cap,
+                                   self.ans.data_ptr(), st)
+        self._mark("lookup_received")
+        for w in self._swap(self.ans, rc, self.ans_back, sc):                          # answers: 4 B per lookup
+            w.wait()
+        self._mark("swap_answers")
 
-    def _swap(self, send, send_counts, recv, recv_counts) -> None:
+    def _swap(self, send, send_counts, recv, recv_counts):
+        """Grouped send/recv of the filled part of every other rank's bucket; returns the work handles."""
         dist = self.dist
         cap, me = self.cap, self.rank
         ops = []
@@ -91,12 +123,7 @@ class RoutedClassifier:
                 ops.append(dist.P2POp(dist.isend, send[peer * cap: peer * cap + send_counts[peer]], peer))
             if recv_counts[peer]:
                 ops.append(dist.P2POp(dist.irecv, recv[peer * cap: peer * cap + recv_counts[peer]], peer))
-        n = send_counts[me]
-        if n:
-            recv[me * cap: me * cap + n].copy_(send[me * cap: me * cap + n])           # this rank's own bucket
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def classify(self, opts, nt, read_off, group_off, out, total_nt: int) -> None:
         """nt (uint8), read_off / group_off (int64), out (int32): CUDA tensors of this rank's batch."""
@@ -111,10 +138,12 @@ class RoutedClassifier:
         if capi.route_sampled_applies(self.index, opts) and nt.data_ptr() % 16 == 0:
             if nreads > self.max_reads:
                 raise ValueError("more reads than the frame-mask buffer of this RoutedClassifier holds")
+            self._mark("start")
             for phase in (1, 2):
                 capi.route_pack_sampled_dev(self.index, opts, phase, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
                                             self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(),
                                             self.frame_hits.data_ptr(), self.ids.data_ptr(), st)
+                self._mark(f"pack{phase}")
                 self._round(st)
                 if phase == 1:
                     capi.route_scatter_hits_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
@@ -122,8 +151,11 @@ class RoutedClassifier:
                 else:
                     capi.route_scatter_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
                                            self.cursors.data_ptr(), cap, self.ids.data_ptr(), st)
+                self._mark(f"scatter{phase}")
             capi.classify_ids_masked_dev(self.index, self.tax, opts, self.ids.data_ptr(), read_off.data_ptr(), total_nt,
                                          group_off.data_ptr(), ngroups, self.frame_hits.data_ptr(), True, out.data_ptr(), st)
+            self._mark("classify")
+            self._collect()
             return
         capi.route_pack_dev(self.index, opts, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
                             self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(), self.ids.data_ptr(), st)
