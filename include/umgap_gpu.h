@@ -218,6 +218,32 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
                                uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
                                void* stream);
 
+/* ---- fused peptide path: prot2tryp2lca | uniq -d / | taxa2agg (the tryptic presets of
+ * scripts/umgap-analyse.sh:291-300, behind the gene predictor) without text between the stages.
+ * Lines l in [group_off[g], group_off[g+1]) are the records `uniq` joins.  Every peptide line is digested
+ * (prot2tryp2lca.rs:112-117), the peptides of minlen..maxlen bytes that pass the keep / drop sets are looked up
+ * in the variable-length table `idx` (k = 0), and the taxa of a group are aggregated (zeros dropped,
+ * taxa2agg.rs:169; a group without a hit yields 1, :174-175; a group without lines UMGAP_ABSENT).   */
+typedef struct umgap_tryp_opts {
+    int minlen;         /* prot2tryp2lca -l, default 5                                     */
+    int maxlen;         /* prot2tryp2lca -L, default 50                                    */
+    const char* keep;   /* prot2tryp2lca -k (NULL or "" = none)                            */
+    const char* drop;   /* prot2tryp2lca -d                                                */
+    int strategy;       /* UMGAP_AGG_*                                                     */
+    float factor;       /* taxa2agg -f                                                     */
+    float lower_bound;  /* taxa2agg -l                                                     */
+    int ranked_only;    /* taxa2agg -r                                                     */
+} umgap_tryp_opts;
+void umgap_tryp_opts_default(umgap_tryp_opts* o);
+int umgap_classify_peptides(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts,
+                            const uint8_t* aa, const uint64_t* line_off, uint64_t nlines,
+                            const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out);
+/* Device-resident variant, asynchronous on `stream`; total_aa = line_off[nlines].                 */
+int umgap_classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts,
+                                const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines,
+                                uint64_t total_aa, const uint64_t* group_off_dev, uint64_t ngroups,
+                                uint32_t* taxon_out_dev, void* stream);
+
 /* ---- routed variant of the sharded mode: the exchange step of SURVEY 8(e).  Per batch and rank:
  *   umgap_route_pack_dev     reads -> 45-bit k-mer hashes bucketed by owning shard: send_h_dev and
  *                            send_pos_dev hold nshards buckets of `cap` entries, cursors_dev

@@ -440,6 +440,73 @@ def test_tryptic_lookup_matches_oracle(capi, world, tmp_path):
         capi.tryp_lookup(world["gidx"], aa, off)   # a k-mer table is not a peptide table
 
 
+@pytest.mark.parametrize("strategy,lb,mn,mx,keep,drop,ranked", [
+    (2, 1.0, 9, 45, "", "", False),     # tryptic-sensitivity: prot2tryp2lca -l9 -L45 | uniq | taxa2agg -l1 -a mrtl
+    (2, 5.0, 9, 45, "", "", False),     # tryptic-precision: -l5
+    (1, 0.0, 5, 50, "", "", False),     # command defaults, hybrid
+    (0, 0.0, 5, 50, "", "CW", True),    # drop set, ranked snapping, LCA*
+    (1, 2.0, 6, 30, "L", "", False),    # keep set
+])
+def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, strategy, lb, mn, mx, keep, drop, ranked):
+    """umgap_classify_peptides (digest + lookup + uniq join + aggregation on the device) against the oracle's text
+    stages `prot2tryp2lca | uniq -d / | taxa2agg` (scripts/umgap-analyse.sh:291-300), and the device-buffer entry
+    point against the host-buffer one."""
+    rng = random.Random(77 + strategy)
+    proteins = world["proteins"]
+    otax = world["otax"]
+    ids = [t[0] for t in otax.by_id if t is not None]
+    tryp = {}
+    for i, p in enumerate(proteins):   # peptides of one protein share a neighbourhood of the tree now and then
+        home = rng.choice(ids)
+        for pep in olookup.tryptic_filter(olookup.tryptic_digest(p), 5, 50):
+            tryp.setdefault(pep.encode(), home if rng.random() < 0.6 else rng.choice(ids))
+    keys = sorted(tryp)
+    gidx = capi.Index.from_pairs(keys, [tryp[k] for k in keys], k=0)
+    # predicted-gene style input: fragments of proteins, two records per fragment pair (`/1`, `/2`), some noise
+    recs = []
+    for g in range(300):
+        p = rng.choice(proteins)
+        for mate in (1, 2):
+            a = rng.randrange(0, max(1, len(p) - 60))
+            frag = list(p[a:a + rng.randrange(20, 140)])
+            for _ in range(rng.randrange(0, 3)):
+                frag[rng.randrange(len(frag))] = rng.choice("*KRPX")
+            recs.append((f"g{g}/{mate}", "".join(frag)))
+    recs += [("e0/1", ""), ("e0/2", "*"), ("e1/1", "K"), ("e1/2", "MKR" * 30), ("solo", proteins[3][:200]), ("e2/1", "A" * 120), ("e2/2", "KP")]
+    text = "".join(f">{h}\n{sq}\n" if sq else f">{h}\n" for h, sq in recs)
+    oidx = olookup.DictIndex(tryp)
+    ids_text = opipe.prot2tryp2lca_text(text, oidx, False, mn, mx, keep, drop)
+    want = opipe.taxa2agg_sets(opipe.uniq_text(ids_text, "/"), otax, strategy, 0.25, lb, ranked)
+    aa, off = capi.pack_strings([sq.encode() for _, sq in recs])
+    heads = [h.split("/")[0] for h, _ in recs]
+    goff = np.array([0] + [i for i in range(1, len(recs) + 1) if i == len(recs) or heads[i] != heads[i - 1]], dtype=np.uint64)
+    opts = capi.tryp_opts(minlen=mn, maxlen=mx, keep=keep, drop=drop, strategy=strategy, factor=0.25, lower_bound=lb,
+                          ranked_only=int(ranked))
+    got = capi.classify_peptides(gidx, world["gtax"], opts, aa, off, goff)
+    assert len(want) == len(got) == len(goff) - 1
+    below = 0
+    for (h, adm), g_ in zip(want, got):
+        assert int(g_) in adm, (h, int(g_), adm)
+        below += int(g_) != 1
+    assert below > (100 if lb < 5 else 10)
+    # device-buffer entry point, asynchronous on the current stream
+    import torch
+    d_aa = torch.from_numpy(aa).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_goff = torch.from_numpy(goff.astype(np.int64)).cuda()
+    d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
+    capi.classify_peptides_dev(gidx, world["gtax"], opts, d_aa.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]),
+                               d_goff.data_ptr(), len(goff) - 1, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), got)
+    # a group without lines has no record; a k-mer table is not a peptide table
+    g2 = capi.classify_peptides(gidx, world["gtax"], opts, aa, off, np.array([0, 2, 2, 4], dtype=np.uint64))
+    assert int(g2[1]) == capi.ABSENT and int(g2[0]) == int(got[0])
+    with pytest.raises(capi.UmgapError):
+        capi.classify_peptides(world["gidx"], world["gtax"], opts, aa, off, goff)
+    gidx.close()
+
+
 def test_large_batch_matches_c_port(capi, tmp_path):
     """50 000 synthetic pairs against a 2e6-key index: the CUDA path (through the fst loader) and the C
     restatement of the reference algorithm agree on every pair for LCA* (deterministic), and on every

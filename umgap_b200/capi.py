@@ -33,6 +33,7 @@ SYMBOLS = [
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
     "umgap_seedextend", "umgap_aggregate",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
+    "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
     "umgap_translate_lookup_dev",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
     "umgap_route_sampled_applies", "umgap_route_pack_sampled_dev", "umgap_route_scatter_hits_dev", "umgap_classify_ids_masked_dev",
@@ -65,6 +66,11 @@ class PipelineOpts(C.Structure):
                 ("seedextend", C.c_int), ("min_seed_size", C.c_int), ("max_gap_size", C.c_int),
                 ("strategy", C.c_int), ("factor", C.c_float), ("lower_bound", C.c_float),
                 ("ranked_only", C.c_int)]
+
+
+class TrypOpts(C.Structure):
+    _fields_ = [("minlen", C.c_int), ("maxlen", C.c_int), ("keep", C.c_char_p), ("drop", C.c_char_p),
+                ("strategy", C.c_int), ("factor", C.c_float), ("lower_bound", C.c_float), ("ranked_only", C.c_int)]
 
 
 class ShardDesc(C.Structure):
@@ -343,6 +349,39 @@ def aggregate(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, strategy: in
                                C.c_float(factor), C.c_float(lower_bound),
                                C.c_int(int(ranked_only)), _p(out)))
     return out[:nrecs]
+
+
+def tryp_opts(**kw) -> TrypOpts:
+    """umgap_tryp_opts_default plus overrides (keep / drop as str or bytes)."""
+    o = TrypOpts()
+    load_library().umgap_tryp_opts_default(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        if k in ("keep", "drop") and isinstance(v, str):
+            v = v.encode()
+        setattr(o, k, v)
+    return o
+
+
+def classify_peptides(index: Index, tax: Taxonomy, opts: TrypOpts, aa: np.ndarray, line_off: np.ndarray,
+                      group_off: np.ndarray) -> np.ndarray:
+    """umgap_classify_peptides (host buffers): prot2tryp2lca | uniq | taxa2agg, one taxon per group of lines."""
+    aa = _arr(aa, np.uint8)
+    line_off = _arr(line_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    _check(load_library().umgap_classify_peptides(index._h, tax._h, C.byref(opts), _p(aa), _p(line_off),
+                                                  C.c_uint64(len(line_off) - 1), _p(group_off), C.c_uint64(ngroups), _p(out)))
+    return out[:ngroups]
+
+
+def classify_peptides_dev(index: Index, tax: Taxonomy, opts: TrypOpts, aa_ptr: int, line_off_ptr: int, nlines: int,
+                          total_aa: int, group_off_ptr: int, ngroups: int, out_ptr: int, stream: int = 0) -> None:
+    _check(load_library().umgap_classify_peptides_dev(
+        index._h, tax._h, C.byref(opts), C.c_void_p(aa_ptr), C.c_void_p(line_off_ptr), C.c_uint64(nlines), C.c_uint64(total_aa),
+        C.c_void_p(group_off_ptr), C.c_uint64(ngroups), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
 
 def classify_reads(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarray,

@@ -168,6 +168,18 @@ static unsigned grid_for(uint64_t items, unsigned per_block, unsigned max_blocks
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ceil_div(items, per_block), max_blocks));
 }
 
+// The aggregation kernel over device-resident records (the fused peptide path of tryptic.cu); scratch_dev holds
+// 3 * rec_off[nrecs] + nrecs + 8 words, err_dev two (flag, offending taxon id).
+void launch_aggregate(const umgap_taxonomy* tax, int strategy, float factor, float lower_bound, int ranked_only,
+                      const uint32_t* taxa_dev, const uint64_t* rec_off_dev, uint64_t nrecs, uint32_t* scratch_dev,
+                      uint32_t* out_dev, unsigned int* err_dev, cudaStream_t st) {
+    if (!nrecs) return;
+    AggParams ap{strategy, factor, lower_bound, ranked_only};
+    aggregate_kernel<<<grid_for(nrecs, kStageAggWarps), kStageAggWarps * 32, 0, st>>>(tax->view, ap, taxa_dev, rec_off_dev, nrecs,
+                                                                                   scratch_dev, out_dev, err_dev);
+    UMGAP_CUDA(cudaGetLastError());
+}
+
 }  // namespace umgap
 
 using namespace umgap;

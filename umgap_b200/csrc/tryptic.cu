@@ -88,6 +88,53 @@ struct TrypParams {
 
 constexpr uint32_t kTrypNone = 0xFFFFFFFEu;  // position that starts no (kept) peptide
 
+// What starts at byte i of the line [b, e): kTrypNone (no kept peptide starts here), kNoValue (a kept peptide
+// the table does not hold) or the peptide's value.
+__device__ __forceinline__ uint32_t tryp_at(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                                            const uint8_t* __restrict__ aa, uint64_t i, uint64_t b, uint64_t e,
+                                            const TrypParams& tp, const uint8_t* __restrict__ set_lut) {
+    const uint8_t c = aa[i];
+    bool start = c != '*';
+    if (start && i > b) {
+        const uint8_t p = aa[i - 1];
+        start = p == '*' || ((p == 'K' || p == 'R') && c != 'P');
+    }
+    if (!start) return kTrypNone;
+    uint64_t h = kFnvBasis;
+    uint32_t len = 0, keep_seen = 0;
+    bool dropped = false, too_long = false;
+    for (uint64_t j = i; j < e; ++j) {
+        const uint8_t x = aa[j];
+        if (x == '*') break;
+        if (len == tp.maxlen) {  // one more residue would exceed -L: filtered out
+            too_long = true;
+            break;
+        }
+        h = pep_hash_step(h, x);
+        ++len;
+        const uint8_t s = set_lut[x];
+        dropped |= (s & 0x80) != 0;
+        if (s & 0x3F) keep_seen |= 1u << ((s & 0x3F) - 1);
+        if ((x == 'K' || x == 'R') && j + 1 < e && aa[j + 1] != 'P') break;
+    }
+    bool keep = !too_long && len >= tp.minlen;
+    if (keep && tp.filter_sets) keep = !dropped && keep_seen == tp.keep_all;
+    if (!keep) return kTrypNone;
+    h = pep_hash_finish(h, len);
+    uint64_t s = __umul64hi(h, nslots);
+    for (;;) {
+        const VarSlot sl = slots[s];
+        if (sl.off_len == kVarEmpty) return kNoValue;
+        if (sl.tag == (uint32_t)h && (uint32_t)(sl.off_len & 0xFF) == len) {
+            const uint8_t* k = pool + (sl.off_len >> 8);
+            bool same = true;
+            for (uint32_t q = 0; q < len; ++q) same &= k[q] == aa[i + q];
+            if (same) return sl.value;
+        }
+        s = (s + 1 == nslots) ? 0 : s + 1;
+    }
+}
+
 // out[i] for every input byte i: kTrypNone, kNoValue (kept peptide, miss) or the value.
 __global__ void __launch_bounds__(256)
 tryp_lookup_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
@@ -98,56 +145,37 @@ tryp_lookup_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uin
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint64_t line = line_of_byte[i];
-        const uint64_t b = line_off[line], e = line_off[line + 1];
-        const uint8_t c = aa[i];
-        bool start = c != '*';
-        if (start && i > b) {
-            const uint8_t p = aa[i - 1];
-            start = p == '*' || ((p == 'K' || p == 'R') && c != 'P');
-        }
-        uint32_t res = kTrypNone;
-        if (start) {
-            uint64_t h = kFnvBasis;
-            uint32_t len = 0, keep_seen = 0;
-            bool dropped = false, too_long = false;
-            for (uint64_t j = i; j < e; ++j) {
-                const uint8_t x = aa[j];
-                if (x == '*') break;
-                if (len == tp.maxlen) {  // one more residue would exceed -L: filtered out
-                    too_long = true;
-                    break;
-                }
-                h = pep_hash_step(h, x);
-                ++len;
-                const uint8_t s = set_lut[x];
-                dropped |= (s & 0x80) != 0;
-                if (s & 0x3F) keep_seen |= 1u << ((s & 0x3F) - 1);
-                if ((x == 'K' || x == 'R') && j + 1 < e && aa[j + 1] != 'P') break;
-            }
-            bool keep = !too_long && len >= tp.minlen;
-            if (keep && tp.filter_sets) keep = !dropped && keep_seen == tp.keep_all;
-            if (keep) {
-                h = pep_hash_finish(h, len);
-                res = kNoValue;
-                uint64_t s = __umul64hi(h, nslots);
-                for (;;) {
-                    const VarSlot sl = slots[s];
-                    if (sl.off_len == kVarEmpty) break;
-                    if (sl.tag == (uint32_t)h && (uint32_t)(sl.off_len & 0xFF) == len) {
-                        const uint8_t* k = pool + (sl.off_len >> 8);
-                        bool same = true;
-                        for (uint32_t q = 0; q < len; ++q) same &= k[q] == aa[i + q];
-                        if (same) {
-                            res = sl.value;
-                            break;
-                        }
-                    }
-                    s = (s + 1 == nslots) ? 0 : s + 1;
-                }
-            }
-        }
-        out[i] = res;
+        out[i] = tryp_at(slots, nslots, pool, aa, i, line_off[line], line_off[line + 1], tp, set_lut);
     }
+}
+
+// Fused path (umgap_classify_peptides): one warp per line, the lanes stride over its bytes; out[i] = the taxon of the
+// kept peptide starting at byte i, 0 where none starts or the table does not hold it (taxa2agg drops zeros,
+// taxa2agg.rs:169) -- the array the aggregation kernel reads with the groups' byte ranges as records.
+__global__ void __launch_bounds__(256)
+tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                         const uint8_t* __restrict__ aa, const uint64_t* __restrict__ line_off, uint64_t nlines, TrypParams tp,
+                         const uint8_t* __restrict__ set_lut, uint32_t* __restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = set_lut[threadIdx.x];
+    __syncthreads();
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t l = warp; l < nlines; l += nwarps) {
+        const uint64_t b = line_off[l], e = line_off[l + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const uint32_t v = tryp_at(slots, nslots, pool, aa, i, b, e, tp, s_lut);
+            out[i] = (v == kTrypNone || v == kNoValue) ? 0u : v;
+        }
+    }
+}
+
+// rec_off[g] = line_off[group_off[g]]: the byte range of the lines `uniq` joins into group g
+__global__ void group_bytes_kernel(const uint64_t* __restrict__ line_off, const uint64_t* __restrict__ group_off, uint64_t ngroups,
+                                   uint64_t* __restrict__ rec_off) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= ngroups; g += stride) rec_off[g] = line_off[group_off[g]];
 }
 
 __global__ void line_of_byte_kernel(const uint64_t* __restrict__ line_off, uint64_t nlines, uint32_t* __restrict__ lob) {
@@ -237,7 +265,118 @@ void free_var_table(void* p) {
 
 using namespace umgap;
 
+static TrypParams make_tryp_params(int minlen, int maxlen, const char* keep, const char* drop, uint8_t (&lut)[256]) {
+    if (minlen < 0 || maxlen < 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "negative length bound");
+    TrypParams tp{};
+    tp.minlen = (uint32_t)minlen;
+    tp.maxlen = (uint32_t)maxlen;
+    int nkeep = 0;
+    for (const char* p = keep ? keep : ""; *p; ++p) {
+        uint8_t& e = lut[(uint8_t)*p];
+        if (e & 0x3F) continue;
+        if (nkeep == 32) UMGAP_FAIL(UMGAP_ERR_INVALID, "more than 32 distinct residues in --keep");
+        e |= (uint8_t)(++nkeep);
+    }
+    for (const char* p = drop ? drop : ""; *p; ++p) lut[(uint8_t)*p] |= 0x80;
+    tp.keep_all = nkeep == 32 ? 0xFFFFFFFFu : ((1u << nkeep) - 1);
+    tp.filter_sets = (keep && *keep) || (drop && *drop);
+    return tp;
+}
+
+namespace umgap {
+// stages.cu: the aggregation kernel over device-resident records (zeros dropped, empty record -> 1)
+void launch_aggregate(const umgap_taxonomy* tax, int strategy, float factor, float lower_bound, int ranked_only,
+                      const uint32_t* taxa_dev, const uint64_t* rec_off_dev, uint64_t nrecs, uint32_t* scratch_dev,
+                      uint32_t* out_dev, unsigned int* err_dev, cudaStream_t st);
+}
+
+// workspace slots of a peptide-table handle (a k = 0 index never runs the k-mer pipeline, whose slots these overlap)
+enum { TWS_LUT = 0, TWS_OUT = 1, TWS_REC = 2, TWS_SCRATCH = 3, TWS_ERR = 4, TWS_AA = 5, TWS_LOFF = 6, TWS_GOFF = 7, TWS_RES = 8 };
+
+static void classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* o,
+                                  const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines, uint64_t total_aa,
+                                  const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, unsigned int** err_out,
+                                  cudaStream_t st) {
+    if (!idx || !tax || !o) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+    if (idx->k != 0 || !idx->var_table) UMGAP_FAIL(UMGAP_ERR_INVALID, "index is not a variable-length peptide table");
+    if (tax->device != idx->device) UMGAP_FAIL(UMGAP_ERR_INVALID, "index and taxonomy live on different devices");
+    if (o->strategy < UMGAP_AGG_LCA_STAR || o->strategy > UMGAP_AGG_MRTL) UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", o->strategy);
+    uint8_t lut[256] = {};
+    const TrypParams tp = make_tryp_params(o->minlen, o->maxlen, o->keep, o->drop, lut);
+    use_device(idx->device);
+    const VarTable* t = (const VarTable*)idx->var_table;
+    uint8_t* d_lut = (uint8_t*)idx->ws.get(TWS_LUT, 256);
+    uint32_t* d_out = (uint32_t*)idx->ws.get(TWS_OUT, (total_aa + 1) * sizeof(uint32_t));
+    uint64_t* d_rec = (uint64_t*)idx->ws.get(TWS_REC, (ngroups + 1) * sizeof(uint64_t));
+    uint32_t* d_scratch = (uint32_t*)idx->ws.get(TWS_SCRATCH, (3 * total_aa + ngroups + 8) * sizeof(uint32_t));
+    unsigned int* d_err = (unsigned int*)idx->ws.get(TWS_ERR, 2 * sizeof(unsigned int));
+    if (err_out) *err_out = d_err;
+    UMGAP_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(unsigned int), st));
+    if (!ngroups) return;
+    UMGAP_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    if (nlines && total_aa) {
+        tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, 8), 148 * 16), 256, 0, st>>>(
+            t->slots, t->nslots, t->pool, aa_dev, line_off_dev, nlines, tp, d_lut, d_out);
+        UMGAP_CUDA(cudaGetLastError());
+    }
+    group_bytes_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(ngroups + 1, 256), 148 * 8), 256, 0, st>>>(line_off_dev, group_off_dev,
+                                                                                                        ngroups, d_rec);
+    UMGAP_CUDA(cudaGetLastError());
+    launch_aggregate(tax, o->strategy, o->factor, o->lower_bound, o->ranked_only, d_out, d_rec, ngroups, d_scratch, taxon_out_dev,
+                     d_err, st);
+}
+
 extern "C" {
+
+void umgap_tryp_opts_default(umgap_tryp_opts* o) {
+    if (!o) return;
+    o->minlen = 5;                 // prot2tryp2lca -l / -L defaults (prot2tryp2lca.rs:61-67)
+    o->maxlen = 50;
+    o->keep = nullptr;
+    o->drop = nullptr;
+    o->strategy = UMGAP_AGG_HYBRID;  // taxa2agg defaults (taxa2agg.rs:111-125)
+    o->factor = 0.25f;
+    o->lower_bound = 0.0f;
+    o->ranked_only = 0;
+}
+
+int umgap_classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts,
+                                const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines, uint64_t total_aa,
+                                const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, void* stream) {
+    return guarded([&] {
+        classify_peptides_dev(idx, tax, opts, aa_dev, line_off_dev, nlines, total_aa, group_off_dev, ngroups, taxon_out_dev, nullptr,
+                              (cudaStream_t)stream);
+    });
+}
+
+int umgap_classify_peptides(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts, const uint8_t* aa,
+                            const uint64_t* line_off, uint64_t nlines, const uint64_t* group_off, uint64_t ngroups,
+                            uint32_t* taxon_out) {
+    return guarded([&] {
+        if (!idx || !line_off || !group_off || (ngroups && !taxon_out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (!ngroups) return;
+        if (group_off[ngroups] > nlines) UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off exceeds the number of lines");
+        const uint64_t total = nlines ? line_off[nlines] : 0;
+        if (total && !aa) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(idx->device);
+        uint8_t* d_aa = (uint8_t*)idx->ws.get(TWS_AA, total + 16);
+        uint64_t* d_loff = (uint64_t*)idx->ws.get(TWS_LOFF, (nlines + 1) * sizeof(uint64_t));
+        uint64_t* d_goff = (uint64_t*)idx->ws.get(TWS_GOFF, (ngroups + 1) * sizeof(uint64_t));
+        uint32_t* d_res = (uint32_t*)idx->ws.get(TWS_RES, ngroups * sizeof(uint32_t));
+        if (total) UMGAP_CUDA(cudaMemcpyAsync(d_aa, aa, total, cudaMemcpyHostToDevice, 0));
+        UMGAP_CUDA(cudaMemcpyAsync(d_loff, line_off, (nlines + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, 0));
+        UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off, (ngroups + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, 0));
+        unsigned int* d_err = nullptr;
+        classify_peptides_dev(idx, tax, opts, d_aa, d_loff, nlines, total, d_goff, ngroups, d_res, &d_err, 0);
+        unsigned int he[2] = {0, 0};
+        UMGAP_CUDA(cudaMemcpyAsync(taxon_out, d_res, ngroups * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
+        UMGAP_CUDA(cudaMemcpyAsync(he, d_err, sizeof he, cudaMemcpyDeviceToHost, 0));
+        UMGAP_CUDA(cudaStreamSynchronize(0));
+        if (he[0]) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", he[1]);
+        for (uint64_t g = 0; g < ngroups; ++g)   // a group without lines has no record in the reference
+            if (group_off[g + 1] == group_off[g]) taxon_out[g] = UMGAP_ABSENT;
+    });
+}
 
 uint64_t umgap_tryp_lookup_bound(uint64_t total_aa, uint64_t nlines) {
     (void)nlines;
@@ -257,19 +396,7 @@ int umgap_tryp_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t*
         if (!aa || !taxa_out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         if (total >= (1ull << 32) || nlines >= (1ull << 32)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large (>= 2^32 bytes)");
         uint8_t lut[256] = {};
-        TrypParams tp{};
-        tp.minlen = (uint32_t)minlen;
-        tp.maxlen = (uint32_t)maxlen;
-        int nkeep = 0;
-        for (const char* p = keep ? keep : ""; *p; ++p) {
-            uint8_t& e = lut[(uint8_t)*p];
-            if (e & 0x3F) continue;
-            if (nkeep == 32) UMGAP_FAIL(UMGAP_ERR_INVALID, "more than 32 distinct residues in --keep");
-            e |= (uint8_t)(++nkeep);
-        }
-        for (const char* p = drop ? drop : ""; *p; ++p) lut[(uint8_t)*p] |= 0x80;
-        tp.keep_all = nkeep == 32 ? 0xFFFFFFFFu : ((1u << nkeep) - 1);
-        tp.filter_sets = (keep && *keep) || (drop && *drop);
+        const TrypParams tp = make_tryp_params(minlen, maxlen, keep, drop, lut);
         use_device(idx->device);
         const VarTable* t = (const VarTable*)idx->var_table;
         DevBuf<uint8_t> d_aa(total), d_lut(256);
