@@ -149,25 +149,108 @@ tryp_lookup_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uin
     }
 }
 
-// Fused path (umgap_classify_peptides): one warp per line, the lanes stride over its bytes; out[i] = the taxon of the
-// kept peptide starting at byte i, 0 where none starts or the table does not hold it (taxa2agg drops zeros,
-// taxa2agg.rs:169) -- the array the aggregation kernel reads with the groups' byte ranges as records.
-__global__ void __launch_bounds__(256)
-tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
-                         const uint8_t* __restrict__ aa, const uint64_t* __restrict__ line_off, uint64_t nlines, TrypParams tp,
-                         const uint8_t* __restrict__ set_lut, uint32_t* __restrict__ out) {
-    __shared__ uint8_t s_lut[256];
-    s_lut[threadIdx.x] = set_lut[threadIdx.x];
-    __syncthreads();
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (uint64_t l = warp; l < nlines; l += nwarps) {
-        const uint64_t b = line_off[l], e = line_off[l + 1];
-        for (uint64_t i = b + lane; i < e; i += 32) {
-            const uint32_t v = tryp_at(slots, nslots, pool, aa, i, b, e, tp, s_lut);
-            out[i] = (v == kTrypNone || v == kNoValue) ? 0u : v;
+// Fused path (umgap_classify_peptides): ONE THREAD PER LINE.  The lane walks its line once, eight bytes per load,
+// carrying the digest state (prot2tryp2lca.rs:112-117 in the closed form above: a peptide ends before a '*', before a
+// residue that follows K/R and is not P, and at the end of the line), the running hash, the length and the keep / drop
+// flags; a finished peptide that passes the filters is parked in a four-entry list in shared memory, and the lookups
+// run from the list afterwards (or when it is full), so that the lanes of a warp probe together instead of one
+// lane at a time in the middle of the walk.  out[i] = the taxon of the kept peptide starting at byte i; the caller
+// zeroed out[] (taxa2agg drops zeros, taxa2agg.rs:169), so `out` with the groups' byte ranges as records is what
+// the aggregation kernel reads.  (A warp per line with the lanes striding over its bytes was the first form: 2.95 ms
+// per 1 M pairs of 50-residue lines, instruction-bound -- five of 32 lanes walk a peptide at a time.)
+constexpr int kPepList = 4;
+constexpr int kPepThreads = 128;
+
+__device__ __forceinline__ void tryp_probe(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                                           const uint8_t* __restrict__ aa, uint64_t h, uint64_t start, uint32_t len,
+                                           uint32_t* __restrict__ out) {
+    uint64_t s = __umul64hi(h, nslots);
+    for (;;) {
+        const VarSlot sl = slots[s];
+        if (sl.off_len == kVarEmpty) return;
+        if (sl.tag == (uint32_t)h && (uint32_t)(sl.off_len & 0xFF) == len) {
+            const uint8_t* k = pool + (sl.off_len >> 8);
+            bool same = true;
+            for (uint32_t q = 0; q < len; ++q) same &= k[q] == aa[start + q];
+            if (same) {
+                out[start] = sl.value;
+                return;
+            }
         }
+        s = (s + 1 == nslots) ? 0 : s + 1;
+    }
+}
+
+__global__ void __launch_bounds__(kPepThreads)
+tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
+                         const uint8_t* __restrict__ aa, uint64_t total_aa, const uint64_t* __restrict__ line_off, uint64_t nlines,
+                         TrypParams tp, const uint8_t* __restrict__ set_lut, uint32_t* __restrict__ out) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint64_t s_hash[kPepList][kPepThreads];
+    __shared__ uint64_t s_where[kPepList][kPepThreads];  // start << 8 | length
+    for (int i = threadIdx.x; i < 256; i += kPepThreads) s_lut[i] = set_lut[i];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * kPepThreads;
+    const int t = threadIdx.x;
+    for (uint64_t l = (uint64_t)blockIdx.x * kPepThreads + t; l < nlines; l += stride) {
+        const uint64_t b = line_off[l], e = line_off[l + 1];
+        uint64_t h = kFnvBasis, pstart = b, word = 0;
+        uint32_t len = 0, keep_seen = 0, npend = 0;
+        bool dropped = false, too_long = false, prev_kr = false;
+        auto flush = [&]() {
+            for (uint32_t p = 0; p < npend; ++p)
+                tryp_probe(slots, nslots, pool, aa, s_hash[p][t], s_where[p][t] >> 8, (uint32_t)(s_where[p][t] & 0xFF), out);
+            npend = 0;
+        };
+        auto finish = [&]() {  // the peptide [pstart, pstart + len) is complete
+            bool keep = !too_long && len >= tp.minlen && len > 0;
+            if (keep && tp.filter_sets) keep = !dropped && keep_seen == tp.keep_all;
+            if (keep) {
+                if (npend == (uint32_t)kPepList) flush();
+                s_hash[npend][t] = pep_hash_finish(h, len);
+                s_where[npend][t] = (pstart << 8) | len;
+                ++npend;
+            }
+            h = kFnvBasis;
+            len = 0;
+            keep_seen = 0;
+            dropped = too_long = false;
+        };
+        for (uint64_t i = b; i < e; ++i) {
+            if (i == b || (i & 7u) == 0) {  // next aligned word (bytes past the end of the buffer are never loaded)
+                const uint64_t w0 = i & ~7ull;
+                if (w0 + 8 <= total_aa) {
+                    word = __ldg(reinterpret_cast<const unsigned long long*>(aa + w0));
+                } else {
+                    word = 0;
+                    for (uint64_t q = w0; q < total_aa; ++q) word |= (uint64_t)aa[q] << (8 * (q - w0));
+                }
+            }
+            const uint8_t x = (uint8_t)(word >> (8 * (i & 7u)));
+            if (x == '*') {
+                finish();
+                prev_kr = false;
+                pstart = i + 1;
+                continue;
+            }
+            if (prev_kr && x != 'P' && len > 0) {
+                finish();
+                pstart = i;
+            }
+            if (len == 0) pstart = i;
+            if (len == tp.maxlen) {
+                too_long = true;  // one more residue would exceed -L: the peptide is filtered out, its tail skipped
+            } else if (!too_long) {
+                h = pep_hash_step(h, x);
+                ++len;
+                const uint8_t sl = s_lut[x];
+                dropped |= (sl & 0x80) != 0;
+                if (sl & 0x3F) keep_seen |= 1u << ((sl & 0x3F) - 1);
+            }
+            prev_kr = x == 'K' || x == 'R';
+        }
+        finish();
+        flush();
     }
 }
 
@@ -314,9 +397,11 @@ static void classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* 
     UMGAP_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(unsigned int), st));
     if (!ngroups) return;
     UMGAP_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    UMGAP_CUDA(cudaMemsetAsync(d_out, 0, (total_aa + 1) * sizeof(uint32_t), st));
     if (nlines && total_aa) {
-        tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, 8), 148 * 16), 256, 0, st>>>(
-            t->slots, t->nslots, t->pool, aa_dev, line_off_dev, nlines, tp, d_lut, d_out);
+        if (((uintptr_t)aa_dev & 7u) != 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "aa_dev must be 8-byte aligned");
+        tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, kPepThreads), 148 * 16), kPepThreads, 0, st>>>(
+            t->slots, t->nslots, t->pool, aa_dev, total_aa, line_off_dev, nlines, tp, d_lut, d_out);
         UMGAP_CUDA(cudaGetLastError());
     }
     group_bytes_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(ngroups + 1, 256), 148 * 8), 256, 0, st>>>(line_off_dev, group_off_dev,
