@@ -112,6 +112,16 @@ typedef struct umgap_index_info {
     double load_factor;     /* slots used / slots of the main level, as chosen at build     */
 } umgap_index_info;
 int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info);
+/* splitkmers | sort | joinkmers | buildindex on the device (splitkmers.rs:44-66, joinkmers.rs:53-105,
+ * buildindex.rs:32-48): the k-mer table straight from a protein table.  Protein r = aa[prot_off[r] ..
+ * prot_off[r+1]) with taxon id prot_taxon[r] (the two columns of the TSV `splitkmers` reads).  Every k-mer
+ * maps to the hybrid (factor 0.95) aggregate of its proteins' taxa, each first replaced by its nearest
+ * valid ancestor, the result snapped to a ranked taxon; taxa the taxonomy does not hold are dropped.
+ * The table lives on the taxonomy's device.                                                        */
+int umgap_index_build_from_proteins(const umgap_taxonomy* tax, const uint8_t* aa, const uint64_t* prot_off,
+                                    const uint64_t* prot_taxon, uint64_t nprot, int k, double load_factor,
+                                    umgap_index** out);
+
 /* A level-0 table larger than `bytes` is probed one hash-prefix region of at most that size per
  * lookup-kernel pass (B200's random-access rate collapses beyond ~64 GiB of footprint; default
  * 60 GiB, 0 restores it).  Results do not depend on it.                                          */

@@ -507,6 +507,52 @@ def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, strategy, 
     gidx.close()
 
 
+@pytest.mark.parametrize("k", [9, 5])
+def test_index_built_from_proteins_matches_oracle_joinkmers(capi, world, k):
+    """umgap_index_build_from_proteins (windows, radix sort, hybrid-0.95 aggregation per k-mer, ranked snapping, table
+    insert on the device) against the oracle's `splitkmers | sort | joinkmers`: every k-mer the reference would
+    emit is in the table with an admissible value, nothing else is."""
+    from oracle import indexbuild
+    rng = random.Random(400 + k)
+    otax = world["otax"]
+    known = [t[0] for t in otax.by_id if t is not None]
+    absent = [i for i in range(1, len(otax.by_id)) if otax.by_id[i] is None][:5]
+    assert absent
+    base = world["proteins"][:60]
+    rows = []
+    for i, p in enumerate(base):
+        home = rng.choice(known)
+        rows.append((home, p))
+        for _ in range(rng.randrange(0, 4)):     # homologues: shared stretches under related and unrelated taxa
+            a = rng.randrange(0, len(p) - 30)
+            frag = p[a:a + rng.randrange(20, 120)]
+            tid = rng.choice([home, home, rng.choice(known), rng.choice(absent)])
+            rows.append((tid, frag + "".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(rng.randrange(0, 12)))))
+    rows += [(rng.choice(known), "ACDEFGH"[:k - 1]), (rng.choice(known), ""), (rng.choice(known), "MKX*UB" * 4), (absent[0], base[0])]
+    rows += [(rng.choice(known), base[1])] * 3   # the same protein under three more taxa
+    want = indexbuild.build(rows, otax, k)
+    assert len(want) > 3000
+    gidx = capi.Index.build_from_proteins(world["gtax"], [sq.encode() for _, sq in rows], [t for t, _ in rows], k=k)
+    info = gidx.info()
+    assert info.n_keys == len(want) and info.k == k
+    kmers = sorted(want)
+    misses = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(k)) for _ in range(3000)]
+    misses = [m for m in misses if m not in want]
+    aa, off = capi.pack_strings([x.encode() for x in kmers + misses])
+    got, goff, _ = capi.kmer_lookup(gidx, aa, off, True)
+    assert len(got) == len(kmers) + len(misses)
+    multi = 0
+    for kmer, v in zip(kmers, got[:len(kmers)]):
+        assert int(v) in want[kmer], (kmer, int(v), want[kmer])
+        multi += int(v) != 1
+    assert multi > 1000
+    assert not np.any(got[len(kmers):])          # -o: a miss is 0
+    # a taxon id beyond the taxonomy's id range is an error (an index panic in the reference)
+    with pytest.raises(capi.UmgapError):
+        capi.Index.build_from_proteins(world["gtax"], [base[0].encode()], [len(otax.by_id) + 1000], k=k)
+    gidx.close()
+
+
 def test_large_batch_matches_c_port(capi, tmp_path):
     """50 000 synthetic pairs against a 2e6-key index: the CUDA path (through the fst loader) and the C
     restatement of the reference algorithm agree on every pair for LCA* (deterministic), and on every

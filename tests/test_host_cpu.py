@@ -229,3 +229,24 @@ def test_seedextend_closed_form():
         G = rnd.choice([0, 1, 1, 2, 3, 5, 70])
         want = Counter(x for x in seedextend(ids, S, G) if x != 0)
         assert closed_form(ids, S, G) == want, (ids, S, G)
+
+
+def test_oracle_joinkmers_on_a_hand_made_tree():
+    """oracle.indexbuild (splitkmers.rs:44-66, joinkmers.rs:53-105) on a tree small enough to check by hand:
+    1 (root, no rank) - 2 (superkingdom) - 3 (genus) - {4 (species), 5 (species, invalid)}; 6 (species) under 2."""
+    from oracle import indexbuild
+    from oracle.taxonomy import Taxonomy
+    taxa = [(1, "root", "no rank", 1, True), (2, "sk", "superkingdom", 1, True), (3, "g", "genus", 2, True),
+            (4, "s1", "species", 3, True), (5, "s2", "species", 3, False), (6, "s3", "species", 2, True)]
+    tax = Taxonomy(taxa)
+    rows = [(4, "AAAAAC"), (5, "AAAAAD"), (6, "AAAAA"), (4, "AAAA"), (7, "CCCCC"), (5, "DDDDD")]
+    assert indexbuild.splitkmers(rows, 5) == [("AAAAA", 4), ("AAAAC", 4), ("AAAAA", 5), ("AAAAD", 5), ("AAAAA", 6),
+                                              ("CCCCC", 7), ("DDDDD", 5)]
+    assert indexbuild.splitkmers([(4, "ABCDEF")], 5, "B") == [("CDEF", 4)]
+    got = indexbuild.build(rows, tax, 5)
+    # AAAAA: taxa 4, 3 (5 is invalid -> its valid ancestor 3) and 6: no child of 2 holds 95 % -> 2
+    assert got["AAAAA"] == {2}
+    assert got["AAAAC"] == {4}
+    assert got["AAAAD"] == {3} and got["DDDDD"] == {3}
+    assert "CCCCC" not in got          # taxon 7 is unknown: dropped, nothing left, nothing printed
+    assert len(got) == 4

@@ -23,7 +23,7 @@ AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
 SYMBOLS = [
     "umgap_last_error", "umgap_abi_version", "umgap_device_count",
     "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
-    "umgap_index_set_probe_region",
+    "umgap_index_set_probe_region", "umgap_index_build_from_proteins",
     "umgap_index_load_fst_shard", "umgap_index_from_pairs_shard", "umgap_index_shard_desc",
     "umgap_index_attach_shards", "umgap_index_attach_shards_local", "umgap_index_build_synthetic_shard",
     "umgap_taxonomy_load", "umgap_taxonomy_from_arrays", "umgap_taxonomy_free",
@@ -191,6 +191,17 @@ class Index:
                                                            C.c_uint64(len(values)), C.c_int(k),
                                                            C.c_int(device), C.c_double(load_factor),
                                                            C.c_int(shard), C.c_int(nshards), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_from_proteins(cls, tax: "Taxonomy", proteins: Sequence[bytes], taxa, k: int = 9,
+                            load_factor: float = 0.0) -> "Index":
+        """umgap_index_build_from_proteins: splitkmers | sort | joinkmers | buildindex on the device."""
+        aa, off = pack_strings(list(proteins))
+        taxa = _arr(np.asarray(taxa, dtype=np.uint64), np.uint64)
+        h = C.c_void_p()
+        _check(load_library().umgap_index_build_from_proteins(tax._h, _p(aa), _p(off), _p(taxa), C.c_uint64(len(taxa)),
+                                                              C.c_int(k), C.c_double(load_factor), C.byref(h)))
         return cls(h)
 
     @classmethod
