@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default policy)")
     ap.add_argument("--sharded", action="store_true", help="key-range-shard the index over the GPUs (peer-memory lookups) instead of replicating it")
     ap.add_argument("--peer-loads", action="store_true", help="with --sharded: read remote shards through IPC peer mappings instead of the all-to-all exchange")
+    ap.add_argument("--routed-lanes", type=int, default=1, help="with --sharded: group ranges of a batch whose exchange rounds alternate on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -291,7 +292,7 @@ def run_ours(args):
 
     routed = None
     if shard_mode and not args.peer_loads:
-        routed = sharded.RoutedClassifier(gidx, gtax, dist, total_nt)
+        routed = sharded.RoutedClassifier(gidx, gtax, dist, total_nt, lanes=args.routed_lanes)
 
     def step(i):
         if routed is not None:  # hashes and answers cross NVLink in two all-to-alls, lookups stay local

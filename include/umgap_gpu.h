@@ -289,12 +289,16 @@ int umgap_classify_ids_dev(const umgap_index* idx, const umgap_taxonomy* tax, co
  *   (host) exchange, umgap_lookup_hashes_dev, exchange back, umgap_route_scatter_dev
  *   umgap_classify_ids_masked_dev          seedextend | uniq | taxa2agg over the flagged frames
  * Both phases of a batch go through the same index handle, phase 1 first (it leaves the list of reads
- * longer than a warp batch for phase 2).  frame_hits_dev: nreads bytes rounded up to 4, 4-byte aligned.  */
+ * longer than a warp batch for phase 2).  frame_hits_dev: nreads bytes rounded up to 4, 4-byte aligned.
+ * group_off_dev != NULL packs only the reads of groups [g_lo, g_hi) -- a batch can be cut into group ranges
+ * that run on different streams with their own buckets and `slot` (0..5: the work list of the range), all
+ * against the same frame_hits_dev / ids_dev, which the caller then clears once per batch.               */
 int umgap_route_sampled_applies(const umgap_index* idx, const umgap_pipeline_opts* opts);
 int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase,
                                  const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads,
                                  uint64_t total_nt, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
-                                 uint64_t* cursors_dev, uint8_t* frame_hits_dev, uint32_t* ids_dev, void* stream);
+                                 uint64_t* cursors_dev, uint8_t* frame_hits_dev, uint32_t* ids_dev,
+                                 const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi, int slot, void* stream);
 int umgap_route_scatter_hits_dev(const umgap_index* idx, const uint32_t* ans_dev, const uint32_t* send_pos_dev,
                                  const uint64_t* cursors_dev, uint64_t cap, uint8_t* frame_hits_dev, void* stream);
 int umgap_classify_ids_masked_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,

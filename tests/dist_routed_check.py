@@ -49,7 +49,7 @@ def main():
     nt, roff = capi.pack_strings([r[1].encode() for r in reads])
     goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
     total_nt = int(roff[-1])
-    rc = sharded.RoutedClassifier(shard, gtax, dist, max_total_nt=total_nt + 1000)
+    rc = sharded.RoutedClassifier(shard, gtax, dist, max_total_nt=total_nt + 1000, lanes=2)
     d_nt = torch.zeros(total_nt + 64, dtype=torch.uint8, device="cuda")
     d_nt[:total_nt] = torch.from_numpy(nt)
     d_roff = torch.from_numpy(roff.astype(np.int64)).cuda()
@@ -60,7 +60,9 @@ def main():
              dict(seedextend=1, min_seed_size=6, max_gap_size=2, strategy=0),    # sampled, stride 4
              dict(seedextend=0, min_seed_size=2, max_gap_size=0, strategy=1),    # every position
              dict(seedextend=1, min_seed_size=1, max_gap_size=0, strategy=1)]    # every position (S < 2)
-    for case in cases:
+    for case, cut in [(c, cut) for cut in (False, True) for c in cases]:
+        # cut: the batch is split into two group ranges on two streams whose exchange rounds alternate (sampled form only)
+        rc.min_groups_per_lane = 16 if cut else 1 << 30
         opts = capi.default_opts(**case)
         sampled = capi.route_sampled_applies(shard, opts)
         assert sampled == (case["seedextend"] == 1 and case["min_seed_size"] >= 2), case
@@ -84,10 +86,11 @@ def main():
         n_routed = torch.tensor([rc.lookups_routed], dtype=torch.int64, device="cuda")
         dist.all_reduce(n_routed)
         if rank == 0:
-            print(f"routed case {case}: sampled={sampled} lookups routed {int(n_routed.item())}", flush=True)
+            print(f"routed case {case} cut={cut}: sampled={sampled} lookups routed {int(n_routed.item())}", flush=True)
     # a bucket that overflows is reported, not silently dropped
     tiny = sharded.RoutedClassifier(shard, gtax, dist, max_total_nt=total_nt + 1000, slack=0.01)
-    tiny.cap = 64
+    for lane in tiny.lanes:
+        lane.cap = 64
     d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
     tiny.classify(capi.default_opts(seedextend=1, min_seed_size=3), d_nt[:total_nt], d_roff, d_goff, d_out, total_nt)
     assert tiny.overflowed()

@@ -501,11 +501,13 @@ def route_sampled_applies(index: Index, opts: PipelineOpts) -> bool:
 
 def route_pack_sampled_dev(index: Index, opts: PipelineOpts, phase: int, nt_ptr: int, read_off_ptr: int, nreads: int,
                            total_nt: int, cap: int, send_h_ptr: int, send_pos_ptr: int, cursors_ptr: int,
-                           frame_hits_ptr: int, ids_ptr: int, stream: int = 0) -> None:
+                           frame_hits_ptr: int, ids_ptr: int, stream: int = 0, group_off_ptr: int = 0, g_lo: int = 0,
+                           g_hi: int = 0, slot: int = 0) -> None:
     _check(load_library().umgap_route_pack_sampled_dev(
         index._h, C.byref(opts), C.c_int(phase), C.c_void_p(nt_ptr), C.c_void_p(read_off_ptr), C.c_uint64(nreads),
         C.c_uint64(total_nt), C.c_uint64(cap), C.c_void_p(send_h_ptr), C.c_void_p(send_pos_ptr), C.c_void_p(cursors_ptr),
-        C.c_void_p(frame_hits_ptr), C.c_void_p(ids_ptr), C.c_void_p(stream)))
+        C.c_void_p(frame_hits_ptr), C.c_void_p(ids_ptr), C.c_void_p(group_off_ptr), C.c_uint64(g_lo), C.c_uint64(g_hi),
+        C.c_int(slot), C.c_void_p(stream)))
 
 
 def route_scatter_hits_dev(index: Index, ans_ptr: int, send_pos_ptr: int, cursors_ptr: int, cap: int,

@@ -618,7 +618,9 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
             const uint32_t nb = (uint32_t)__popc(fits);
             if (nb == 0) {  // a single read longer than the batch span: queued for the plain kernel (launched next)
                 if ((MODE == 0 || MODE == 3 || (MODE == 1 && region_lo == 0)) && lane == 0) long_list[r_begin + atomicAdd(long_count, 1u)] = cur;
-                if (MODE == 3 && lane == 0) frame_hits[cur] = 0x3F;  // routed: the plain pack kernel sends every position of it
+                if (MODE == 3 && lane == 0)  // routed: the plain pack kernel sends every position of it (word-wise OR: another
+                                             // stream may be OR-ing a neighbouring read's mask into the same word)
+                    atomicOr(reinterpret_cast<uint32_t*>(frame_hits) + (cur >> 2), 0x3Fu << (8 * (cur & 3u)));
                 cur += 1;
                 continue;
             }
@@ -1701,7 +1703,7 @@ namespace umgap {
 void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
                             const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
                             uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
-                            cudaStream_t st);  // route.cu
+                            const uint64_t* group_off_dev, uint64_t g_lo, cudaStream_t st);  // route.cu
 }
 }
 
@@ -1712,23 +1714,26 @@ int umgap_route_sampled_applies(const umgap_index* idx, const umgap_pipeline_opt
 int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
                                  const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
                                  uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev,
-                                 uint8_t* frame_hits_dev, uint32_t* ids_dev, void* stream) {
+                                 uint8_t* frame_hits_dev, uint32_t* ids_dev, const uint64_t* group_off_dev, uint64_t g_lo,
+                                 uint64_t g_hi, int slot, void* stream) {
     return guarded([&] {
         if (!idx || !opts || !send_h_dev || !send_pos_dev || !cursors_dev || !ids_dev || !frame_hits_dev)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         if (!umgap_route_sampled_applies(idx, opts))
             UMGAP_FAIL(UMGAP_ERR_INVALID, "sampled routing needs k = 9, -o and seedextend -s >= 2 (umgap_route_sampled_applies)");
         if (phase != 1 && phase != 2) UMGAP_FAIL(UMGAP_ERR_INVALID, "phase must be 1 or 2");
+        if (slot < 0 || slot >= kMaxBufs) UMGAP_FAIL(UMGAP_ERR_INVALID, "slot must be in [0, %d)", kMaxBufs);
         if (2 * total_nt >= (1ull << 32) || nreads >= (1ull << 28)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large for 32-bit positions");
         if (((uintptr_t)nt_dev & 15u) || ((uintptr_t)frame_hits_dev & 3u)) UMGAP_FAIL(UMGAP_ERR_INVALID, "nt_dev must be 16-byte, frame_hits_dev 4-byte aligned");
         use_device(idx->device);
         cudaStream_t st = (cudaStream_t)stream;
         UMGAP_CUDA(cudaMemsetAsync(cursors_dev, 0, 2 * (size_t)idx->nshards * sizeof(uint64_t), st));
         // 64 long-read counters, 64 unit counters, then the list of the reads longer than a warp batch (filled by phase 1)
-        uint32_t* counters = (uint32_t*)idx->ws.get(WS_LONG, (128 + nreads) * sizeof(uint32_t));
+        uint32_t* counters = (uint32_t*)idx->ws.get(WS_LONG + slot, (128 + nreads) * sizeof(uint32_t));
         if (phase == 1) {
             UMGAP_CUDA(cudaMemsetAsync(counters, 0, 128 * sizeof(uint32_t), st));
-            UMGAP_CUDA(cudaMemsetAsync(frame_hits_dev, 0, (nreads + 3) / 4 * 4, st));
+            // a group range shares frame_hits_dev with the other ranges of the batch: the caller cleared it
+            if (!group_off_dev) UMGAP_CUDA(cudaMemsetAsync(frame_hits_dev, 0, (nreads + 3) / 4 * 4, st));
         } else {
             UMGAP_CUDA(cudaMemsetAsync(counters + 64, 0, 64 * sizeof(uint32_t), st));
         }
@@ -1745,7 +1750,7 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         const int stride = std::min(opts->min_seed_size, 4);
 #define UMGAP_ROUTE_SAMPLED(S, MODE)                                                                                          \
     lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
-        idx->view(), lut, nt_dev, total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, counters + 128, \
+        idx->view(), lut, nt_dev, total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo, g_hi, counters + 128, \
         counters, counters + 64, 0ull, 1ull << 32, rs)
         if (phase == 1) {
             switch (stride) {
@@ -1765,7 +1770,7 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         ++g_launch_count;
         if (phase == 2) {  // every position of the reads longer than a warp batch
             launch_route_pack_list(idx, opts, nt_dev, read_off_dev, cap, send_h_dev, send_pos_dev, cursors_dev, ids_dev, counters + 128,
-                                   counters, st);
+                                   counters, group_off_dev, g_lo, st);
             ++g_launch_count;
         }
     });

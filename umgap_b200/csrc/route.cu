@@ -33,7 +33,8 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
                   const uint64_t* __restrict__ read_off, uint64_t nreads, uint64_t cap,
                   uint64_t* __restrict__ send_h, uint32_t* __restrict__ send_pos,
                   unsigned long long* __restrict__ cursors /* [nshards] + [nshards]: overflow flag */,
-                  uint32_t* __restrict__ ids, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count) {
+                  uint32_t* __restrict__ ids, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
+                  const uint64_t* __restrict__ group_off, uint64_t g_lo) {
     // list set: only the reads list[0 .. *list_count) (those the sampled pack kernel left over: longer than one of its
     // batches), their ids in the frame-major layout the classify kernel reads behind the sampled path
     constexpr int W = kRouteTile + 3 * (K - 1);
@@ -46,7 +47,10 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
     if (threadIdx.x < 72) s_lut[threadIdx.x] = lut.v[threadIdx.x];
     __syncthreads();
     const uint64_t nwarps = (uint64_t)gridDim.x * kRouteWarps;
-    if (list) nreads = *list_count;
+    if (list) {
+        nreads = *list_count;
+        if (group_off) list += group_off[g_lo];  // the list of a group range starts at the range's first read
+    }
     for (uint64_t ri = (uint64_t)blockIdx.x * kRouteWarps + warp; ri < nreads; ri += nwarps) {
         const uint64_t r = list ? list[ri] : ri;
         const uint64_t off = read_off[r];
@@ -179,12 +183,12 @@ __global__ void route_scatter_hits_kernel(const uint32_t* __restrict__ ans, cons
 void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
                             const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
                             uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
-                            cudaStream_t st) {
+                            const uint64_t* group_off_dev, uint64_t g_lo, cudaStream_t st) {
     CodonLut72 lut{};
     make_code_lut_public(idx, opts->table, opts->methionine, lut.v);
     route_pack_kernel<9><<<148, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, 0, cap, send_h_dev,
                                                           send_pos_dev, reinterpret_cast<unsigned long long*>(cursors_dev),
-                                                          ids_dev, list, list_count);
+                                                          ids_dev, list, list_count, group_off_dev, g_lo);
     UMGAP_CUDA(cudaGetLastError());
 }
 
@@ -212,7 +216,7 @@ int umgap_route_pack_dev(const umgap_index* idx, const umgap_pipeline_opts* opts
         route_pack_kernel<9><<<blocks, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, nreads, cap,
                                                                  send_h_dev, send_pos_dev,
                                                                  reinterpret_cast<unsigned long long*>(cursors_dev), ids_dev,
-                                                                 nullptr, nullptr);
+                                                                 nullptr, nullptr, nullptr, 0);
         UMGAP_CUDA(cudaGetLastError());
     });
 }

@@ -29,6 +29,23 @@ def attach_all(index: capi.Index, dist, device=None) -> None:
     index.attach_shards(descs)
 
 
+class _Lane:
+    """Buckets, counters and stream of one group range of a batch (RoutedClassifier cuts a batch into `lanes` ranges)."""
+
+    def __init__(self, torch, G: int, cap: int, dev, slot: int):
+        self.cap, self.slot = cap, slot
+        self.send_h = torch.empty(G * cap, dtype=torch.int64, device=dev)
+        self.recv_h = torch.empty(G * cap, dtype=torch.int64, device=dev)
+        self.send_pos = torch.empty(G * cap, dtype=torch.int32, device=dev)
+        self.ans = torch.empty(G * cap, dtype=torch.int32, device=dev)
+        self.ans_back = torch.empty(G * cap, dtype=torch.int32, device=dev)
+        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=dev)
+        self.recv_counts = torch.zeros(G, dtype=torch.int64, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.bool, device=dev)
+        self.fills = None
+        self.stream = torch.cuda.Stream(device=dev)
+
+
 class RoutedClassifier:
     """Per-batch driver of the routed sharded mode.  One instance per rank; `index` is this rank's shard.
 
@@ -40,10 +57,13 @@ class RoutedClassifier:
                ids;  then the classify kernel over the flagged frames.
     Otherwise one round with every position.  An exchange round moves only the filled part of each bucket: the fills
     are swapped first (one small all-to-all, read on the host), then grouped NCCL send/recv of the hashes (8 B per
-    lookup) and, after the lookups, of the answers (4 B back).  These are the only collectives on the data path."""
+    lookup) and, after the lookups, of the answers (4 B back).  These are the only collectives on the data path.
+
+    A large batch is cut into `lanes` group ranges, each with its own buckets and stream; the host issues their stages
+    alternately, so the transfers of one range run beside the pack / lookup / scatter kernels of the other."""
 
     def __init__(self, index: capi.Index, tax: capi.Taxonomy, dist, max_total_nt: int, slack: float = 1.08,
-                 max_reads: int | None = None):
+                 max_reads: int | None = None, lanes: int = 1):
         import torch
         self.index, self.tax, self.dist, self.torch = index, tax, dist, torch
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
@@ -51,22 +71,20 @@ class RoutedClassifier:
         # bucket capacity: every one of the 2*nt lookups valid and evenly spread, plus slack for skew
         self.cap = int(2 * self.max_total_nt / self.world * slack) + 4096
         dev = torch.device("cuda", torch.cuda.current_device())
-        G, cap = self.world, self.cap
-        self.send_h = torch.empty(G * cap, dtype=torch.int64, device=dev)
-        self.recv_h = torch.empty(G * cap, dtype=torch.int64, device=dev)
-        self.send_pos = torch.empty(G * cap, dtype=torch.int32, device=dev)
-        self.ans = torch.empty(G * cap, dtype=torch.int32, device=dev)
-        self.ans_back = torch.empty(G * cap, dtype=torch.int32, device=dev)
-        self.cursors = torch.zeros(2 * G, dtype=torch.int64, device=dev)
-        self.recv_counts = torch.zeros(G, dtype=torch.int64, device=dev)
+        G = self.world
+        self.nlanes = max(1, min(int(lanes), 4))
+        # lane 0 holds full-size buckets (a batch that is not cut uses it alone), the others their share
+        self.lanes = [_Lane(torch, G, self.cap if i == 0 else int(self.cap / self.nlanes * 1.05) + 4096, dev, i)
+                      for i in range(self.nlanes)]
         self.ids = torch.empty(2 * self.max_total_nt + 64, dtype=torch.int32, device=dev)
         self.max_reads = int(max_reads) if max_reads is not None else self.max_total_nt // 27 + 1
         self.frame_hits = torch.zeros(self.max_reads + 8, dtype=torch.uint8, device=dev)
-        self.overflow = torch.zeros(1, dtype=torch.bool, device=dev)
         self.lookups_routed = 0   # hashes this rank sent in the last batch (both phases)
-        self.profile = False      # True: CUDA-event brackets around the stages of a batch, summed in self.stage_ms
+        self.min_groups_per_lane = 65536
+        self.profile = False      # True: CUDA-event brackets around the stages of a batch (uncut), summed in self.stage_ms
         self.stage_ms: dict = {}
         self._marks: list = []
+        self._used: list = []
 
     def _mark(self, name: str) -> None:
         if self.profile:
@@ -82,39 +100,46 @@ class RoutedClassifier:
             self.stage_ms[name] = self.stage_ms.get(name, 0.0) + a.elapsed_time(b)
         self._marks = []
 
-    # -- one exchange round: buckets out, lookups in the local shard, answers back into self.ans_back.  This rank's own
-    #    bucket is neither sent nor copied: it is looked up in place while the other buckets travel.
-    def _round(self, st) -> None:
+    # -- one exchange round of a lane, in three host steps (a generator: the caller alternates the lanes between them).
+    #    This rank's own bucket is neither sent nor copied: it is looked up in place while the other buckets travel.
+    def _round(self, lane: _Lane, stream):
         torch, dist = self.torch, self.dist
-        G, cap, me = self.world, self.cap, self.rank
-        self.overflow |= self.cursors[G:].any()
-        self.fills = self.cursors[:G].clamp(max=cap)
-        dist.all_to_all_single(self.recv_counts, self.fills)                           # bucket fills
-        both = torch.stack([self.fills, self.recv_counts]).cpu()                       # the one host read of a round
-        sc, rc = both[0].tolist(), both[1].tolist()
-        self.lookups_routed += sum(sc)
-        self._mark("counts")
-        works = self._swap(self.send_h, sc, self.recv_h, rc)                           # hashes: 8 B per lookup
-        if sc[me]:
-            capi.lookup_hashes_dev(self.index, self.send_h.data_ptr() + 8 * me * cap, self.fills.data_ptr() + 8 * me, 1, cap,
-                                   self.ans_back.data_ptr() + 4 * me * cap, st)
-        self._mark("lookup_own_bucket")
-        for w in works:
-            w.wait()
-        self._mark("swap_hashes_exposed")
-        self.recv_counts[me] = 0
-        if G > 1:
-            capi.lookup_hashes_dev(self.index, self.recv_h.data_ptr(), self.recv_counts.data_ptr(), G, cap,
-                                   self.ans.data_ptr(), st)
-        self._mark("lookup_received")
-        for w in self._swap(self.ans, rc, self.ans_back, sc):                          # answers: 4 B per lookup
-            w.wait()
-        self._mark("swap_answers")
+        G, cap, me = self.world, lane.cap, self.rank
+        st = stream.cuda_stream
+        with torch.cuda.stream(stream):
+            lane.overflow |= lane.cursors[G:].any()
+            lane.fills = lane.cursors[:G].clamp(max=cap)
+            dist.all_to_all_single(lane.recv_counts, lane.fills)                       # bucket fills
+            both = torch.stack([lane.fills, lane.recv_counts]).cpu()                   # the one host read of a round
+            sc, rc = both[0].tolist(), both[1].tolist()
+            self.lookups_routed += sum(sc)
+            self._mark("counts")
+            works = self._swap(lane, lane.send_h, sc, lane.recv_h, rc)                 # hashes: 8 B per lookup
+            if sc[me]:
+                capi.lookup_hashes_dev(self.index, lane.send_h.data_ptr() + 8 * me * cap, lane.fills.data_ptr() + 8 * me, 1, cap,
+                                       lane.ans_back.data_ptr() + 4 * me * cap, st)
+            self._mark("lookup_own_bucket")
+        yield
+        with torch.cuda.stream(stream):
+            for w in works:
+                w.wait()
+            self._mark("swap_hashes_exposed")
+            lane.recv_counts[me] = 0
+            if G > 1:
+                capi.lookup_hashes_dev(self.index, lane.recv_h.data_ptr(), lane.recv_counts.data_ptr(), G, cap,
+                                       lane.ans.data_ptr(), st)
+            self._mark("lookup_received")
+            works = self._swap(lane, lane.ans, rc, lane.ans_back, sc)                  # answers: 4 B per lookup
+        yield
+        with torch.cuda.stream(stream):
+            for w in works:
+                w.wait()
+            self._mark("swap_answers")
 
-    def _swap(self, send, send_counts, recv, recv_counts):
+    def _swap(self, lane: _Lane, send, send_counts, recv, recv_counts):
         """Grouped send/recv of the filled part of every other rank's bucket; returns the work handles."""
         dist = self.dist
-        cap, me = self.cap, self.rank
+        cap, me = lane.cap, self.rank
         ops = []
         for peer in range(self.world):
             if peer == me:
@@ -125,46 +150,82 @@ class RoutedClassifier:
                 ops.append(dist.P2POp(dist.irecv, recv[peer * cap: peer * cap + recv_counts[peer]], peer))
         return dist.batch_isend_irecv(ops) if ops else []
 
+    def _sampled_steps(self, lane: _Lane, stream, opts, nt, read_off, group_off, nreads, total_nt, g_lo, g_hi, ranged):
+        """The two exchange rounds of one group range (generator of host steps)."""
+        torch = self.torch
+        st = stream.cuda_stream
+        for phase in (1, 2):
+            with torch.cuda.stream(stream):
+                capi.route_pack_sampled_dev(self.index, opts, phase, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, lane.cap,
+                                            lane.send_h.data_ptr(), lane.send_pos.data_ptr(), lane.cursors.data_ptr(),
+                                            self.frame_hits.data_ptr(), self.ids.data_ptr(), st,
+                                            group_off.data_ptr() if ranged else 0, g_lo, g_hi, lane.slot)
+                self._mark(f"pack{phase}")
+            yield
+            yield from self._round(lane, stream)
+            with torch.cuda.stream(stream):
+                if phase == 1:
+                    capi.route_scatter_hits_dev(self.index, lane.ans_back.data_ptr(), lane.send_pos.data_ptr(),
+                                                lane.cursors.data_ptr(), lane.cap, self.frame_hits.data_ptr(), st)
+                else:
+                    capi.route_scatter_dev(self.index, lane.ans_back.data_ptr(), lane.send_pos.data_ptr(),
+                                           lane.cursors.data_ptr(), lane.cap, self.ids.data_ptr(), st)
+                self._mark(f"scatter{phase}")
+            yield
+
     def classify(self, opts, nt, read_off, group_off, out, total_nt: int) -> None:
         """nt (uint8), read_off / group_off (int64), out (int32): CUDA tensors of this rank's batch."""
         torch = self.torch
         if total_nt > self.max_total_nt:
             raise ValueError("batch larger than the buffers of this RoutedClassifier")
-        cap = self.cap
-        st = torch.cuda.current_stream().cuda_stream
+        main = torch.cuda.current_stream()
+        st = main.cuda_stream
         nreads, ngroups = read_off.numel() - 1, group_off.numel() - 1
-        self.overflow.zero_()
         self.lookups_routed = 0
+        for lane in self.lanes:
+            lane.overflow.zero_()
         if capi.route_sampled_applies(self.index, opts) and nt.data_ptr() % 16 == 0:
             if nreads > self.max_reads:
                 raise ValueError("more reads than the frame-mask buffer of this RoutedClassifier holds")
+            nl = self.nlanes if not self.profile and ngroups >= self.min_groups_per_lane * self.nlanes else 1
+            self._used = self.lanes[:nl]
             self._mark("start")
-            for phase in (1, 2):
-                capi.route_pack_sampled_dev(self.index, opts, phase, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
-                                            self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(),
-                                            self.frame_hits.data_ptr(), self.ids.data_ptr(), st)
-                self._mark(f"pack{phase}")
-                self._round(st)
-                if phase == 1:
-                    capi.route_scatter_hits_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
-                                                self.cursors.data_ptr(), cap, self.frame_hits.data_ptr(), st)
-                else:
-                    capi.route_scatter_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(),
-                                           self.cursors.data_ptr(), cap, self.ids.data_ptr(), st)
-                self._mark(f"scatter{phase}")
+            if nl == 1:
+                steps = [self._sampled_steps(self.lanes[0], main, opts, nt, read_off, group_off, nreads, total_nt, 0, 0, False)]
+            else:
+                self.frame_hits[:nreads + 8].zero_()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                steps = []
+                for i, lane in enumerate(self._used):
+                    lane.stream.wait_event(fork)
+                    steps.append(self._sampled_steps(lane, lane.stream, opts, nt, read_off, group_off, nreads, total_nt,
+                                                     ngroups * i // nl, ngroups * (i + 1) // nl, True))
+            while steps:   # the lanes' host steps alternate (same order on every rank: the collectives match up)
+                for g in list(steps):
+                    try:
+                        next(g)
+                    except StopIteration:
+                        steps.remove(g)
+            if nl > 1:
+                for lane in self._used:
+                    main.wait_stream(lane.stream)
             capi.classify_ids_masked_dev(self.index, self.tax, opts, self.ids.data_ptr(), read_off.data_ptr(), total_nt,
                                          group_off.data_ptr(), ngroups, self.frame_hits.data_ptr(), True, out.data_ptr(), st)
             self._mark("classify")
             self._collect()
             return
-        capi.route_pack_dev(self.index, opts, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, cap,
-                            self.send_h.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(), self.ids.data_ptr(), st)
-        self._round(st)
-        capi.route_scatter_dev(self.index, self.ans_back.data_ptr(), self.send_pos.data_ptr(), self.cursors.data_ptr(),
-                               cap, self.ids.data_ptr(), st)
+        lane = self.lanes[0]
+        self._used = [lane]
+        capi.route_pack_dev(self.index, opts, nt.data_ptr(), read_off.data_ptr(), nreads, total_nt, lane.cap,
+                            lane.send_h.data_ptr(), lane.send_pos.data_ptr(), lane.cursors.data_ptr(), self.ids.data_ptr(), st)
+        for _ in self._round(lane, main):
+            pass
+        capi.route_scatter_dev(self.index, lane.ans_back.data_ptr(), lane.send_pos.data_ptr(), lane.cursors.data_ptr(),
+                               lane.cap, self.ids.data_ptr(), st)
         capi.classify_ids_dev(self.index, self.tax, opts, self.ids.data_ptr(), read_off.data_ptr(), total_nt,
                               group_off.data_ptr(), ngroups, out.data_ptr(), st)
 
     def overflowed(self) -> bool:
         """True when a bucket overflowed in the last batch (extreme key skew): rebuild with more slack."""
-        return bool(self.overflow.item())
+        return any(bool(lane.overflow.item()) for lane in self._used)
