@@ -431,7 +431,7 @@ def run_ours(args):
         use_ms, mode = alone_ms, "lookup stage timed alone on the timed region's batches (umgap_pipeline_slices(1)), CUDA events on its stream"
     achieved = alg_bytes / (use_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if routed is not None
-                else "lookup stage = translate_codes_kernel + lookup_sampled_kernel<9,TableView,3> (+ long-read pass), one event bracket",
+                else "lookup stage = lookup_sampled_kernel<9,TableView,3,0> (translation inside the kernel; + the long-read pass of translate_lookup_kernel), one event bracket",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "timing": mode,
                 "note": "algorithmic bytes = 248 k-mers x 32 B per read (SURVEY 8(d)); in front of seedextend -s3 the kernel probes every "
