@@ -129,3 +129,102 @@ def test_socket_server_mode(files, tmp_path):
     finally:
         srv.kill()
         srv.wait()
+
+
+def test_fused_cli_block_parser_edge_cases(files):
+    """`umgap classify` parses the stream a block at a time: CRLF line ends, hard-wrapped and empty records, a last
+    record without a newline, groups cut by the batch seam (UMGAP_CLI_BATCH) -- always the bytes of the five-stage pipe."""
+    d = files["dir"]
+    reads = files["reads"]
+    text = files["fasta"].replace("\n", "\r\n", 40)                      # some CRLF line ends
+    text += ">empty/1\n>empty/2\n\n>tail/1\n" + reads[0][1][:75] + "\n" + reads[0][1][75:] + "\n>tail/2\n" + reads[1][1]   # no final newline
+    rc, t_out, err = run(["translate", "-a"], text)
+    assert rc == 0, err
+    rc, k_out, _ = run(["prot2kmer2lca", "-o", str(d / "nine.fst")], t_out)
+    rc, s_out, _ = run(["seedextend", "-s", "3"], k_out)
+    rc, u_out, _ = run(["uniq", "-d", "/"], s_out)
+    rc, want, _ = run(["taxa2agg", "-a", "lca*", str(d / "taxons.tsv")], u_out)
+    args = ["classify", "-s", "3", "-a", "lca*", str(d / "nine.fst"), str(d / "taxons.tsv")]
+    for batch in (None, "1", "7", "40"):
+        env = dict(os.environ)
+        if batch:
+            env["UMGAP_CLI_BATCH"] = batch
+        p = subprocess.run([UMGAP] + args, input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout.decode() == want, batch
+    assert want.count(">") >= 80
+    rc, out, err = run(args, "ACGT\n>r\nACGT\n")
+    assert rc == 1 and "Expected > at beginning of fasta header." in err
+    rc, out, err = run(args, "")
+    assert rc == 0 and out == ""
+
+
+def test_cli_wall_clock_through_pipes(tmp_path):
+    """SURVEY 8(d) timing method, last item: wall-clock runs of the CLI through pipes.  200 000 synthetic reads
+    (the bench generator) against a 2e6-key fst file: the five-stage pipe of `umgap-analyse.sh` with our binaries,
+    the fused `umgap classify`, and the C restatement of the reference on the host cores; the two CLI forms must
+    print the same bytes.  Timings go to stdout and gpurun_out/cli_wall_clock.log (a record, not an assertion)."""
+    import numpy as np
+    from oracle import cport, synth
+    taxa = datagen.make_taxonomy(5000, seed=1)
+    pre = synth.Preorder(taxa)
+    n_prot, plen, npairs, rlen = 5000, 408, 100_000, 150
+    keys, vals = synth.build_index(2, n_prot, plen, 70, 20, pre)
+    fst = cport.fst_build_blob(keys.reshape(-1), np.arange(0, 9 * len(keys) + 1, 9, dtype=np.uint64), vals)
+    (tmp_path / "nine.fst").write_bytes(fst)
+    (tmp_path / "taxons.tsv").write_bytes(("\n".join(format_taxon(t) for t in taxa) + "\n").encode("latin-1"))
+    nt = np.concatenate([synth.reads(2, n_prot, plen, 3, c, min(50_000, npairs - c), rlen, 70) for c in range(0, npairs, 50_000)])
+    with open(tmp_path / "reads.fa", "wb") as f:
+        for i in range(0, 2 * npairs, 2):
+            f.write(b">r%d/1\n%s\n>r%d/2\n%s\n" % (i // 2, nt[i].tobytes(), i // 2, nt[i + 1].tobytes()))
+    d = str(tmp_path)
+    pipe = (f"{UMGAP} translate -a < {d}/reads.fa | {UMGAP} prot2kmer2lca -o {d}/nine.fst | {UMGAP} seedextend -s 3 | "
+            f"{UMGAP} uniq -d / | {UMGAP} taxa2agg -a hybrid {d}/taxons.tsv > {d}/staged.out")
+    fused = f"{UMGAP} classify -s 3 -a hybrid {d}/nine.fst {d}/taxons.tsv < {d}/reads.fa > {d}/fused.out"
+    times = {}
+    for name, cmd in (("fused_cold", fused), ("staged", pipe), ("fused", fused)):
+        t0 = time.perf_counter()
+        p = subprocess.run(["bash", "-o", "pipefail", "-c", cmd], stderr=subprocess.PIPE, timeout=600)
+        times[name] = time.perf_counter() - t0
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+    # steady state of the fused command: the same reads fifty times over (10 M reads, 1.6 GB of FASTA)
+    reps = 50
+    big = f"for i in $(seq {reps}); do cat {d}/reads.fa; done | {UMGAP} classify -s 3 -a hybrid {d}/nine.fst {d}/taxons.tsv | wc -l > {d}/big.count"
+    t0 = time.perf_counter()
+    p = subprocess.run(["bash", "-o", "pipefail", "-c", big], stderr=subprocess.PIPE, timeout=600)
+    times["fused_big"] = time.perf_counter() - t0
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert int((tmp_path / "big.count").read_text()) == 2 * reps * npairs
+    staged, fused_out = (tmp_path / "staged.out").read_bytes(), (tmp_path / "fused.out").read_bytes()
+    assert staged == fused_out
+    assert staged.count(b">") == npairs
+    # the reference's algorithm on the host cores (C restatement, in-memory arrays: no text parsing at all)
+    img, ctax = cport.FstImage(fst), cport.RefTaxonomy(taxa)
+    opts = cport.RefOpts(table=1, methionine=0, one_on_one=1, seedextend=1, min_seed_size=3, max_gap_size=0, strategy=1,
+                         factor=0.25, lower_bound=0.0, ranked_only=0, k=9)
+    flat = np.ascontiguousarray(nt.reshape(-1))
+    off = np.arange(0, flat.size + 1, rlen, dtype=np.uint64)
+    goff = np.arange(0, 2 * npairs + 1, 2, dtype=np.uint64)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref, _, _ = cport.classify(img, ctax, opts, flat, off, goff, threads=threads)
+    times["c_port"] = time.perf_counter() - t0
+    got = np.array([int(x) for x in fused_out.split(b"\n")[1::2]], dtype=np.uint64)
+    agree = float((got == np.asarray(ref, dtype=np.uint64)).mean())
+    assert agree > 0.97     # hybrid ties may differ (the C port takes one admissible answer, the GPU another)
+    lines = [f"CLI wall clock, {2 * npairs} reads of {rlen} nt ({os.path.getsize(tmp_path / 'reads.fa') / 1e6:.0f} MB of FASTA), "
+             f"{len(keys)}-key fst file ({len(fst) / 1e6:.0f} MB), {threads} host threads",
+             f"  five-stage pipe (translate | prot2kmer2lca -o | seedextend | uniq | taxa2agg): {times['staged']:.2f} s = "
+             f"{2 * npairs / times['staged'] / 1e3:.0f} k reads/s",
+             f"  fused `umgap classify`: {times['fused']:.2f} s = {2 * npairs / times['fused'] / 1e3:.0f} k reads/s "
+             f"(first run, cold: {times['fused_cold']:.2f} s) -- index load, FASTA parsing and CUDA start-up included",
+             f"  fused `umgap classify`, the same reads {reps} times through a pipe ({2 * reps * npairs} reads): {times['fused_big']:.2f} s = "
+             f"{2 * reps * npairs / times['fused_big'] / 1e6:.2f} M reads/s; beyond the single run's time (start-up): "
+             f"{2 * (reps - 1) * npairs / max(times['fused_big'] - times['fused'], 1e-3) / 1e6:.2f} M reads/s",
+             f"  C restatement of the reference, arrays in memory, {threads} threads: {times['c_port']:.2f} s = "
+             f"{2 * npairs / times['c_port'] / 1e3:.0f} k reads/s; answers equal to the CLI's on {agree:.4f} of the pairs"]
+    print("\n".join(lines))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "cli_wall_clock.log"), "w") as f:
+            f.write("\n".join(lines) + "\n")

@@ -17,6 +17,7 @@
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -24,9 +25,12 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "umgap_gpu.h"
@@ -657,46 +661,189 @@ int cmd_classify(int argc, char** argv) {
     TaxHandle tax;
     check(umgap_index_load_fst(a.pos[0].c_str(), k, 0, 0.0, &idx.p));
     check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
-    FastaReader rd(stdin, true);
-    Record r;
-    std::string carry_header;  // group that may continue in the next batch
-    std::vector<std::string> heads;
-    std::string nt;
-    std::vector<uint64_t> roff, goff;
-    auto flush = [&]() {
-        if (heads.empty()) return;
-        std::vector<uint32_t> res(heads.size());
-        goff.push_back(roff.size() - 1);
-        check(umgap_classify_reads(idx.p, tax.p, &o, (const uint8_t*)nt.data(), roff.data(), roff.size() - 1, goff.data(), heads.size(), res.data(), nullptr));
-        std::string out;
-        for (size_t i = 0; i < heads.size(); ++i)
-            if (res[i] != UMGAP_ABSENT) write_record(out, heads[i], {std::to_string(res[i])}, "\n", false);
-        put(stdout, out);
-        heads.clear();
-        nt.clear();
-        roff.assign(1, 0);
-        goff.clear();
+    // Host side of the fused command: the stream is parsed a block at a time straight into the arrays the library
+    // takes (no per-record strings; fasta.rs:38-67 with unwrap: a record is its header line and the concatenation of
+    // the lines up to the next line that starts with '>'), and a second thread classifies and prints batch i while
+    // this one parses batch i + 1.
+    struct Batch {
+        std::string nt, harena;
+        std::vector<uint64_t> roff, goff, hoff;  // hoff[g] .. hoff[g+1]: header of group g in harena
+        void reset() {
+            nt.clear();
+            harena.clear();
+            roff.assign(1, 0);
+            goff.clear();
+            hoff.assign(1, 0);
+        }
+        size_t groups() const { return hoff.size() - 1; }
     };
-    roff.assign(1, 0);
-    const size_t span = 3 * (size_t)k;
-    while (rd.next(r)) {
-        std::string h = r.header;
+    // groups per library call (UMGAP_CLI_BATCH overrides it, for tests of the batch seam)
+    const size_t batch_groups = getenv("UMGAP_CLI_BATCH") ? std::max<size_t>(1, strtoull(getenv("UMGAP_CLI_BATCH"), nullptr, 10)) : (size_t)1 << 19;
+    Batch batches[2];
+    std::mutex mu;
+    std::condition_variable cv;
+    int ready[2] = {0, 0};  // 0: free for the parser, 1: full, waiting for the classifier
+    bool done = false;
+    std::string worker_error;
+    std::thread worker([&] {
+        std::string out;
+        std::vector<uint32_t> res;
+        try {
+            for (int b = 0;; b ^= 1) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready[b] == 1 || done; });
+                    if (ready[b] != 1) break;
+                }
+                Batch& B = batches[b];
+                const size_t ng = B.groups();
+                if (ng) {
+                    res.resize(ng);
+                    B.goff.push_back(B.roff.size() - 1);
+                    check(umgap_classify_reads(idx.p, tax.p, &o, (const uint8_t*)B.nt.data(), B.roff.data(), B.roff.size() - 1,
+                                               B.goff.data(), ng, res.data(), nullptr));
+                    out.clear();
+                    char num[16];
+                    for (size_t g = 0; g < ng; ++g) {
+                        if (res[g] == UMGAP_ABSENT) continue;
+                        out += '>';
+                        out.append(B.harena, B.hoff[g], B.hoff[g + 1] - B.hoff[g]);
+                        out += '\n';
+                        const int n = snprintf(num, sizeof num, "%u", res[g]);
+                        out.append(num, n);
+                        out += '\n';
+                    }
+                    put(stdout, out);
+                }
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    ready[b] = 0;
+                }
+                cv.notify_all();
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            worker_error = e.what();
+            ready[0] = ready[1] = 0;
+            cv.notify_all();
+        }
+    });
+    int cur = 0;
+    auto acquire = [&](int b) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready[b] == 0; });
+        batches[b].reset();
+    };
+    auto submit = [&](int b) {
         {
-            const size_t p = h.find(delim);
-            if (p != std::string::npos) h.resize(p);
+            std::lock_guard<std::mutex> lk(mu);
+            ready[b] = 1;
         }
-        // reads too short for any frame emit no record at all and so do not take part in uniq's
-        // grouping (prot2kmer2lca.rs:172 drops them before uniq sees them)
-        if (r.seq[0].size() < span) continue;
-        if (heads.empty() || heads.back() != h) {
-            if (heads.size() >= kBatchRecords) flush();
-            heads.push_back(h);
-            goff.push_back(roff.size() - 1);
+        cv.notify_all();
+    };
+    std::string parse_error;
+    try {
+        acquire(cur);
+        Batch* B = &batches[cur];
+        const size_t span = 3 * (size_t)k;
+        std::vector<char> buf(64u << 20);
+        size_t have = 0;
+        bool eof = false, first = true;
+        while (!eof || have) {
+            if (!eof) {
+                if (have == buf.size()) buf.resize(buf.size() * 2);  // one record larger than the block
+                const size_t n = fread(buf.data() + have, 1, buf.size() - have, stdin);
+                if (n == 0) eof = true;
+                have += n;
+            }
+            if (first && have) {
+                if (buf[0] != '>') fail("Expected > at beginning of fasta header.");
+                first = false;
+            }
+            // records that are complete: everything before the last line that starts with '>' (all of it at the end)
+            size_t limit = have;
+            if (!eof) {
+                limit = 0;
+                for (size_t q = have; q > 1;) {
+                    const void* m = memrchr(buf.data(), '>', q);
+                    if (!m) break;
+                    const size_t at = (const char*)m - buf.data();
+                    if (at > 0 && buf[at - 1] == '\n') {
+                        limit = at;
+                        break;
+                    }
+                    q = at;
+                }
+                if (limit == 0) {
+                    if (have == buf.size()) continue;   // grow the buffer and read on
+                    if (!eof) continue;
+                }
+            }
+            const char* p = buf.data();
+            const char* const end = buf.data() + limit;
+            while (p < end) {
+                // header line
+                const char* e = (const char*)memchr(p, '\n', end - p);
+                const char* hend = e ? e : end;
+                const char* hs = p + 1;
+                size_t hl = hend - hs;
+                if (hl && hs[hl - 1] == '\r') --hl;
+                p = e ? e + 1 : end;
+                const size_t nt0 = B->nt.size();
+                while (p < end && *p != '>') {  // sequence lines
+                    const char* le = (const char*)memchr(p, '\n', end - p);
+                    const char* lend = le ? le : end;
+                    size_t ll = lend - p;
+                    if (ll && p[ll - 1] == '\r') --ll;
+                    B->nt.append(p, ll);
+                    p = le ? le + 1 : end;
+                }
+                // reads too short for any frame emit no record at all and so do not take part in uniq's
+                // grouping (prot2kmer2lca.rs:172 drops them before uniq sees them)
+                if (B->nt.size() - nt0 < span) {
+                    B->nt.resize(nt0);
+                    continue;
+                }
+                if (!delim.empty()) {  // uniq -d: the header up to the first occurrence of the delimiter (uniq.rs:61-68)
+                    const void* m = memmem(hs, hl, delim.data(), delim.size());
+                    if (m) hl = (const char*)m - hs;
+                }
+                const size_t ng = B->groups();
+                const bool same = ng && B->hoff[ng] - B->hoff[ng - 1] == hl && memcmp(B->harena.data() + B->hoff[ng - 1], hs, hl) == 0;
+                if (!same) {
+                    if (ng >= batch_groups) {  // a new group starts: the batch can go
+                        std::string tail(B->nt, nt0);   // this read belongs to the next batch
+                        B->nt.resize(nt0);
+                        submit(cur);
+                        cur ^= 1;
+                        acquire(cur);
+                        if (!worker_error.empty()) fail(worker_error);
+                        B = &batches[cur];
+                        B->nt = tail;
+                    }
+                    B->goff.push_back(B->roff.size() - 1);
+                    B->harena.append(hs, hl);
+                    B->hoff.push_back(B->harena.size());
+                }
+                B->roff.push_back(B->nt.size());
+            }
+            memmove(buf.data(), buf.data() + limit, have - limit);
+            have -= limit;
+            if (eof && limit == 0 && have) fail("Expected > at beginning of fasta header.");
         }
-        nt += r.seq[0];
-        roff.push_back(nt.size());
+        submit(cur);
+    } catch (const std::exception& e) {
+        parse_error = e.what();
     }
-    flush();
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return (ready[0] == 0 && ready[1] == 0) || !worker_error.empty(); });
+        done = true;
+    }
+    cv.notify_all();
+    worker.join();
+    if (!parse_error.empty()) fail(parse_error);
+    if (!worker_error.empty()) fail(worker_error);
     return 0;
 }
 
