@@ -131,6 +131,122 @@ void put(FILE* f, const std::string& s) {
     if (!s.empty() && fwrite(s.data(), 1, s.size(), f) != s.size()) fail("failed writing output");
 }
 
+// ---- block-wise reading: the hot stages parse the stream in place, without a string per line ------
+// Hands out regions of the stream that hold whole records (a record starts at a line that begins with '>').
+class BlockReader {
+  public:
+    explicit BlockReader(FILE* f, size_t block = 32u << 20) : f_(f), buf_(block) {}
+    bool next(const char*& p, const char*& end) {
+        memmove(buf_.data(), buf_.data() + used_, have_ - used_);
+        have_ -= used_;
+        used_ = 0;
+        for (;;) {
+            if (!eof_) {
+                if (have_ == buf_.size()) buf_.resize(buf_.size() * 2);  // one record larger than the block
+                const size_t n = fread(buf_.data() + have_, 1, buf_.size() - have_, f_);
+                if (n == 0) eof_ = true;
+                have_ += n;
+            }
+            if (first_ && have_) {
+                if (buf_[0] != '>') fail("Expected > at beginning of fasta header.");  // fasta.rs:44-49
+                first_ = false;
+            }
+            size_t limit = have_;
+            if (!eof_) {  // everything before the last line that starts with '>'
+                limit = 0;
+                for (size_t q = have_; q > 1;) {
+                    const void* m = memrchr(buf_.data(), '>', q);
+                    if (!m) break;
+                    const size_t at = (const char*)m - buf_.data();
+                    if (at > 0 && buf_[at - 1] == '\n') {
+                        limit = at;
+                        break;
+                    }
+                    q = at;
+                }
+                if (limit == 0) continue;  // no complete record yet: read on
+            }
+            if (limit == 0) return false;
+            p = buf_.data();
+            end = buf_.data() + limit;
+            used_ = limit;
+            return true;
+        }
+    }
+
+  private:
+    FILE* f_;
+    std::vector<char> buf_;
+    size_t have_ = 0, used_ = 0;
+    bool eof_ = false, first_ = true;
+};
+
+// The next line of [p, end) without its "\n" / "\r\n" (BufRead::lines()); advances p.
+inline void take_line(const char*& p, const char* end, const char*& ls, size_t& ll) {
+    const char* e = (const char*)memchr(p, '\n', end - p);
+    const char* le = e ? e : end;
+    ls = p;
+    ll = le - p;
+    if (ll && ls[ll - 1] == '\r') --ll;
+    p = e ? e + 1 : end;
+}
+
+// Decimal taxon id of one line (Rust usize::from_str, then the 32-bit range of the tables).
+inline uint32_t taxon_of_line(const char* s, size_t n) {
+    size_t i = (n && s[0] == '+') ? 1 : 0;
+    if (i >= n) fail(n == 0 ? "cannot parse integer from empty string" : "invalid digit found in string");
+    uint64_t v = 0;
+    for (; i < n; ++i) {
+        const unsigned d = (unsigned)(s[i] - '0');
+        if (d > 9) fail("invalid digit found in string");
+        if (v > (UINT64_MAX - d) / 10) fail("number too large to fit in target type");
+        v = v * 10 + d;
+    }
+    if (v >= 0xFFFFFFFFull) fail("taxon id " + std::string(s, n) + " does not fit 32 bits");
+    return (uint32_t)v;
+}
+
+inline void append_u32(std::string& out, uint32_t v) {
+    char tmp[10];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) out += tmp[--n];
+}
+
+// A batch of records whose items are taxon ids, one per line (the streams between prot2kmer2lca, seedextend, uniq
+// and taxa2agg): headers in one arena, ids flattened, CSR offsets.
+struct IdBatch {
+    std::string harena;
+    std::vector<uint64_t> hoff{0}, off{0};
+    std::vector<uint32_t> ids;
+    size_t size() const { return off.size() - 1; }
+    void clear() {
+        harena.clear();
+        hoff.assign(1, 0);
+        off.assign(1, 0);
+        ids.clear();
+    }
+};
+// Parses the records of [p, end) into b (appending); stops after `max_records`.  Returns where it stopped.
+inline const char* parse_id_records(const char* p, const char* end, IdBatch& b, size_t max_records) {
+    while (p < end && b.size() < max_records) {
+        const char* ls;
+        size_t ll;
+        take_line(p, end, ls, ll);  // header line: '>' + header
+        b.harena.append(ls + 1, ll - 1);
+        b.hoff.push_back(b.harena.size());
+        while (p < end && *p != '>') {
+            take_line(p, end, ls, ll);
+            b.ids.push_back(taxon_of_line(ls, ll));
+        }
+        b.off.push_back(b.ids.size());
+    }
+    return p;
+}
+
 // ---- argv ---------------------------------------------------------------------------------------
 struct Spec {
     char shortf;
@@ -224,11 +340,6 @@ float parse_f32(const std::string& s) {
     const float v = strtof(s.c_str(), &end);
     if (s.empty() || *end) fail("invalid float literal");
     return v;
-}
-uint32_t taxon_u32(const std::string& s) {
-    const uint64_t v = parse_usize(s);
-    if (v >= 0xFFFFFFFFull) fail("taxon id " + s + " does not fit 32 bits");
-    return (uint32_t)v;
 }
 
 struct IndexHandle {
@@ -367,7 +478,7 @@ void stream_prot2kmer2lca(FILE* in, FILE* out_f, const umgap_index* idx, bool on
             out += recs[i].header;
             out += '\n';
             for (uint64_t j = toff[i]; j < toff[i + 1]; ++j) {
-                out += std::to_string(taxa[j]);
+                append_u32(out, taxa[j]);
                 out += '\n';
             }
         }
@@ -472,41 +583,41 @@ int cmd_prot2tryp2lca(int argc, char** argv) {
 }
 
 // ---- seedextend / taxa2agg ---------------------------------------------------------------------
-void flatten_ids(const std::vector<Record>& recs, std::vector<uint32_t>& ids, std::vector<uint64_t>& off) {
-    ids.clear();
-    off.assign(1, 0);
-    for (auto& rec : recs) {
-        for (auto& s : rec.seq) ids.push_back(taxon_u32(s));
-        off.push_back(ids.size());
-    }
-}
-
 int cmd_seedextend(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'s', "min-seed-size", true}, {'g', "max-gap-size", true}, {'r', "ranked", true}, {'p', "penalty", true}});
     if (a.has("ranked")) fail("seedextend --ranked is not implemented on the GPU path");
     const int s = (int)parse_usize(a.get("min-seed-size", "2")), g = (int)parse_usize(a.get("max-gap-size", "0"));
-    FastaReader rd(stdin, false);
-    std::vector<Record> recs;
-    Record r;
-    bool more = true;
-    std::vector<uint32_t> ids, out_ids;
-    std::vector<uint64_t> off, ooff;
-    while (more) {
-        recs.clear();
-        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
-        if (recs.empty()) break;
-        flatten_ids(recs, ids, off);
-        out_ids.assign(ids.size() + 1, 0);
-        ooff.assign(recs.size() + 1, 0);
-        check(umgap_seedextend(0, ids.data(), off.data(), recs.size(), s, g, out_ids.data(), ooff.data()));
-        std::string out;
-        for (size_t i = 0; i < recs.size(); ++i) {
-            std::vector<std::string> items;
-            for (uint64_t j = ooff[i]; j < ooff[i + 1]; ++j) items.push_back(std::to_string(out_ids[j]));
-            write_record(out, recs[i].header, items, "\n", false);
+    BlockReader br(stdin);
+    IdBatch b;
+    std::vector<uint32_t> out_ids;
+    std::vector<uint64_t> ooff;
+    std::string out;
+    auto flush = [&]() {
+        if (!b.size()) return;
+        out_ids.assign(b.ids.size() + 1, 0);
+        ooff.assign(b.size() + 1, 0);
+        b.ids.push_back(0);  // never read: keeps data() valid for an all-empty batch
+        check(umgap_seedextend(0, b.ids.data(), b.off.data(), b.size(), s, g, out_ids.data(), ooff.data()));
+        out.clear();
+        for (size_t i = 0; i < b.size(); ++i) {  // fasta.rs:164-180: header, then one id per line
+            out += '>';
+            out.append(b.harena, b.hoff[i], b.hoff[i + 1] - b.hoff[i]);
+            out += '\n';
+            for (uint64_t j = ooff[i]; j < ooff[i + 1]; ++j) {
+                append_u32(out, out_ids[j]);
+                out += '\n';
+            }
         }
         put(stdout, out);
-    }
+        b.clear();
+    };
+    const char *p, *end;
+    while (br.next(p, end))
+        while (p < end) {
+            p = parse_id_records(p, end, b, kBatchRecords);
+            if (b.size() >= kBatchRecords) flush();
+        }
+    flush();
     return 0;
 }
 
@@ -534,24 +645,33 @@ int cmd_taxa2agg(int argc, char** argv) {
     const float factor = parse_f32(a.get("factor", "0.25")), lb = parse_f32(a.get("lower-bound", "0"));
     TaxHandle tax;
     check(umgap_taxonomy_load(a.pos[0].c_str(), 0, &tax.p));
-    FastaReader rd(stdin, false);
-    std::vector<Record> recs;
-    Record r;
-    bool more = true;
-    std::vector<uint32_t> ids, res;
-    std::vector<uint64_t> off;
-    while (more) {
-        recs.clear();
-        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
-        if (recs.empty()) break;
-        flatten_ids(recs, ids, off);
-        res.assign(recs.size(), 0);
-        ids.push_back(0);
-        check(umgap_aggregate(tax.p, ids.data(), off.data(), recs.size(), st, factor, lb, a.has("ranked"), res.data()));
-        std::string out;
-        for (size_t i = 0; i < recs.size(); ++i) write_record(out, recs[i].header, {std::to_string(res[i])}, "\n", false);
+    BlockReader br(stdin);
+    IdBatch b;
+    std::vector<uint32_t> res;
+    std::string out;
+    auto flush = [&]() {
+        if (!b.size()) return;
+        res.assign(b.size(), 0);
+        b.ids.push_back(0);
+        check(umgap_aggregate(tax.p, b.ids.data(), b.off.data(), b.size(), st, factor, lb, a.has("ranked"), res.data()));
+        out.clear();
+        for (size_t i = 0; i < b.size(); ++i) {
+            out += '>';
+            out.append(b.harena, b.hoff[i], b.hoff[i + 1] - b.hoff[i]);
+            out += '\n';
+            append_u32(out, res[i]);
+            out += '\n';
+        }
         put(stdout, out);
-    }
+        b.clear();
+    };
+    const char *p, *end;
+    while (br.next(p, end))
+        while (p < end) {
+            p = parse_id_records(p, end, b, kBatchRecords);
+            if (b.size() >= kBatchRecords) flush();
+        }
+    flush();
     return 0;
 }
 
