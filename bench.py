@@ -349,6 +349,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     classified = float((out != 1).float().mean().item())
+    # the observed k-mer hit rate of the workload (every position of batch 0 looked up once, untimed)
+    kmer_hit_rate = None
+    if rank == 0 and not shard_mode:
+        ids_all = torch.full((2 * total_nt + 64,), -1, dtype=torch.int32, device=dev)
+        capi.translate_lookup_dev(gidx, opts, batches[0].data_ptr(), roff.data_ptr(), nreads, total_nt, ids_all.data_ptr(), stream)
+        torch.cuda.synchronize()
+        per_read = ids_all[: 2 * total_nt].view(nreads, 2 * READ_LEN)
+        npos = READ_LEN - 3 * K + 1
+        hits = int((per_read[:, :npos] != -1).sum().item()) + int((per_read[:, READ_LEN:READ_LEN + npos] != -1).sum().item())
+        kmer_hit_rate = hits / float(nreads * LOOKUPS_PER_READ)
+        del ids_all, per_read
     # the random-sector ceiling of this table on this GPU (uniform random 32-byte gathers over level 0)
     rand_sectors_per_s = gidx.randsector_rate(1 << 28, 3) if rank == 0 and not shard_mode else None
 
@@ -463,7 +474,7 @@ def run_ours(args):
         "lookups_per_second": reads_total * LOOKUPS_PER_READ / (ms * 1e-3),
         "config": pipeline_config(args, {"index_keys_resident": int(info.n_keys), "index_bytes": int(info.bytes),
                                          "index_build_s": build_s, "index_load_factor": info.load_factor, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
-                                         "classified_below_root_frac": classified}),
+                                         "classified_below_root_frac": classified, "kmer_hit_rate": kmer_hit_rate}),
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches),
         "kernel_ms": {"translate_lookup": lookup_ms, "classify": classify_ms},

@@ -131,6 +131,29 @@ def test_socket_server_mode(files, tmp_path):
         srv.wait()
 
 
+def test_fused_peptide_cli_matches_the_three_stage_pipe(files):
+    """`umgap classify-peptides` prints what `prot2tryp2lca | uniq -d / | taxa2agg` prints (tryptic presets)."""
+    d = files["dir"]
+    recs = []
+    for i, p in enumerate(files["proteins"][:40]):
+        recs.append((f"g{i}/1", [p[:120]]))
+        recs.append((f"g{i}/2", [p[100:200], p[200:260] + "*" + p[260:300]]))     # two physical lines in one record
+    recs += [("e/1", []), ("e/2", ["*"]), ("solo", ["MKR" * 20])]
+    text = "".join(f">{h}\n" + "".join(l + "\n" for l in ls) for h, ls in recs)
+    for tflags, aflags in ((["-l", "9", "-L", "45"], ["-m", "rmq", "-a", "mrtl", "-l", "1"]),
+                           (["-l", "5", "-L", "50", "-d", "CW"], ["-a", "lca*"])):
+        rc, t_out, err = run(["prot2tryp2lca"] + tflags + [str(d / "tryp.fst")], text)
+        assert rc == 0, err
+        rc, u_out, _ = run(["uniq", "-d", "/"], t_out)
+        rc, want, err = run(["taxa2agg"] + aflags + [str(d / "taxons.tsv")], u_out)
+        assert rc == 0, err
+        fused_flags = tflags + [("-b" if f == "-l" else f) for f in aflags]
+        rc, got, err = run(["classify-peptides"] + fused_flags + [str(d / "tryp.fst"), str(d / "taxons.tsv")], text)
+        assert rc == 0, err
+        assert got == want, (tflags, aflags)
+        assert got.count(">") == 42 and sum(l != "1" for l in got.split("\n")[1::2]) > 10
+
+
 def test_fused_cli_block_parser_edge_cases(files):
     """`umgap classify` parses the stream a block at a time: CRLF line ends, hard-wrapped and empty records, a last
     record without a newline, groups cut by the batch seam (UMGAP_CLI_BATCH) -- always the bytes of the five-stage pipe."""

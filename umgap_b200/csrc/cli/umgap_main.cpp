@@ -967,6 +967,86 @@ int cmd_classify(int argc, char** argv) {
     return 0;
 }
 
+// ---- classify-peptides: the tryptic presets in one process (extension) -----------------------------
+// prot2tryp2lca | uniq -d / | taxa2agg (scripts/umgap-analyse.sh:291-300) behind the gene predictor: peptide records
+// on stdin, `>header\n<taxon>\n` per group of records on stdout.
+int cmd_classify_peptides(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'l', "minlen", true}, {'L', "maxlen", true}, {'k', "keep", true}, {'d', "drop", true},
+                                   {'D', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
+                                   {'f', "factor", true}, {'b', "lower-bound", true}});
+    if (a.pos.size() != 2) fail("usage: umgap classify-peptides [flags] <tryptic-fst-file> <taxon-file> < peptides.fa");
+    umgap_tryp_opts o;
+    umgap_tryp_opts_default(&o);
+    o.minlen = (int)parse_usize(a.get("minlen", "5"));
+    o.maxlen = (int)parse_usize(a.get("maxlen", "50"));
+    const std::string keep = a.get("keep", ""), drop = a.get("drop", "");
+    o.keep = keep.c_str();
+    o.drop = drop.c_str();
+    o.strategy = parse_strategy(a.get("method", a.get("aggregate", "mrtl") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "mrtl"));
+    o.factor = parse_f32(a.get("factor", "0.25"));
+    o.lower_bound = parse_f32(a.get("lower-bound", "0"));
+    o.ranked_only = a.has("ranked");
+    const std::string delim = a.get("delimiter", "/");
+    IndexHandle idx;
+    TaxHandle tax;
+    check(umgap_index_load_fst(a.pos[0].c_str(), 0, 0, 0.0, &idx.p));
+    check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
+    BlockReader br(stdin);
+    std::string aa, harena, out;
+    std::vector<uint64_t> loff{0}, goff, hoff{0};
+    std::vector<uint32_t> res;
+    auto flush = [&]() {
+        const size_t ng = hoff.size() - 1;
+        if (!ng) return;
+        goff.push_back(loff.size() - 1);
+        res.assign(ng, 0);
+        aa.reserve(aa.size() + 16);
+        check(umgap_classify_peptides(idx.p, tax.p, &o, (const uint8_t*)aa.data(), loff.data(), loff.size() - 1, goff.data(), ng, res.data()));
+        out.clear();
+        for (size_t g = 0; g < ng; ++g) {
+            out += '>';
+            out.append(harena, hoff[g], hoff[g + 1] - hoff[g]);
+            out += '\n';
+            append_u32(out, res[g] == UMGAP_ABSENT ? 1u : res[g]);  // a record without lines aggregates to the literal 1
+            out += '\n';
+        }
+        put(stdout, out);
+        aa.clear();
+        harena.clear();
+        loff.assign(1, 0);
+        goff.clear();
+        hoff.assign(1, 0);
+    };
+    const char *p, *end;
+    while (br.next(p, end))
+        while (p < end) {
+            const char* ls;
+            size_t ll;
+            take_line(p, end, ls, ll);
+            const char* hs = ls + 1;
+            size_t hl = ll - 1;
+            if (!delim.empty()) {
+                const void* m = memmem(hs, hl, delim.data(), delim.size());
+                if (m) hl = (const char*)m - hs;
+            }
+            const size_t ng = hoff.size() - 1;
+            const bool same = ng && hoff[ng] - hoff[ng - 1] == hl && memcmp(harena.data() + hoff[ng - 1], hs, hl) == 0;
+            if (!same) {
+                if (ng >= kBatchRecords * 4) flush();
+                goff.push_back(loff.size() - 1);
+                harena.append(hs, hl);
+                hoff.push_back(harena.size());
+            }
+            while (p < end && *p != '>') {  // one item per physical line (prot2tryp2lca.rs:105-118)
+                take_line(p, end, ls, ll);
+                aa.append(ls, ll);
+                loff.push_back(aa.size());
+            }
+        }
+    flush();
+    return 0;
+}
+
 void usage(FILE* f) {
     fputs("umgap 1.1.1 (umgap-b200: GPU implementation of the per-read classification path)\n\n"
           "USAGE:\n    umgap <SUBCOMMAND>\n\nFLAGS:\n    -h, --help       Prints help information\n    -V, --version    Prints version information\n\n"
@@ -977,7 +1057,8 @@ void usage(FILE* f) {
           "    uniq             Joins consecutive FASTA records with the same header\n"
           "    taxa2agg         Aggregates taxon ids per record (lca*, hybrid, mrtl)\n"
           "    fastq2fasta      Interleaves FASTQ files into FASTA\n"
-          "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process\n", f);
+          "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process\n"
+          "    classify-peptides  prot2tryp2lca | uniq | taxa2agg in one process\n", f);
 }
 
 }  // namespace
@@ -1005,6 +1086,7 @@ int main(int argc, char** argv) {
         if (sub == "uniq") return cmd_uniq(argc, argv);
         if (sub == "fastq2fasta") return cmd_fastq2fasta(argc, argv);
         if (sub == "classify") return cmd_classify(argc, argv);
+        if (sub == "classify-peptides") return cmd_classify_peptides(argc, argv);
         fail("Found argument '" + sub + "' which wasn't expected, or isn't valid in this context");
     } catch (const Fail& e) {
         fprintf(stderr, "Error: %s\n", e.what());
