@@ -177,6 +177,11 @@ int umgap_tryp_lookup(const umgap_index* idx, const uint8_t* aa, const uint64_t*
  * rec_off[nrecs] entries; out_off has nrecs+1 entries.                                     */
 int umgap_seedextend(int device, const uint32_t* taxa, const uint64_t* rec_off, uint64_t nrecs,
                      int min_seed_size, int max_gap_size, uint32_t* out, uint64_t* out_off);
+/* seedextend -r <taxon file> [-p penalty] (seedextend.rs:151-164): of a record's extended seeds only the one with
+ * the highest summed rank score is kept (the last of equal maxima); an id scores TaxonList::score (taxon.rs:181-191,
+ * rank.rs:86-99), `penalty` (reference default 5) when that is None.                                          */
+int umgap_seedextend_ranked(const umgap_taxonomy* tax, const uint32_t* taxa, const uint64_t* rec_off, uint64_t nrecs,
+                            int min_seed_size, int max_gap_size, int penalty, uint32_t* out, uint64_t* out_off);
 
 /* ---- taxa2agg: replaces the record loop of taxa2agg.rs:159-181 with the aggregators
  * tree::lca (tree/lca.rs:34-40), tree::mix (tree/mix.rs:43-64) and rmq::rtl

@@ -56,6 +56,15 @@ def seedextend_text(text: str, min_seed_size: int = 2, max_gap_size: int = 0) ->
     return "".join(out)
 
 
+def seedextend_ranked_text(text: str, tax: Taxonomy, min_seed_size: int = 2, max_gap_size: int = 0, penalty: int = 5) -> str:
+    """seedextend -r <taxon file> -p <penalty>, src/commands/seedextend.rs:84-176."""
+    out = []
+    for header, seq in fasta.read_records(text, unwrap=False):
+        ids = se.seedextend_ranked(_parse_ids(seq), tax, min_seed_size, max_gap_size, penalty)
+        out.append(fasta.write_record(header, [str(i) for i in ids], "\n", False))
+    return "".join(out)
+
+
 def uniq_text(text: str, delimiter: Optional[str] = None, separator: str = "\n",
               wrap: bool = False) -> str:
     recs = fasta.uniq(fasta.read_records(text, unwrap=False), delimiter)

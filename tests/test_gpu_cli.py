@@ -61,6 +61,10 @@ def test_stagewise_pipeline_matches_oracle_text(files):
         rc, s_out, err = run(["seedextend", "-s", str(s), "-g", str(g)], k_out)
         assert rc == 0, err
         assert s_out == opipe.seedextend_text(k_out, s, g)
+    for s, g, pen in ((2, 0, 5), (3, 1, 7)):   # -r: the best-scoring extended seed only
+        rc, r_out, err = run(["seedextend", "-s", str(s), "-g", str(g), "-r", str(d / "taxons.tsv"), "-p", str(pen)], k_out)
+        assert rc == 0, err
+        assert r_out == opipe.seedextend_ranked_text(k_out, files["otax"], s, g, pen)
     rc, s_out, _ = run(["seedextend", "-s", "3"], k_out)
     rc, u_out, _ = run(["uniq", "-d", "/"], s_out)
     assert u_out == opipe.uniq_text(s_out, "/")

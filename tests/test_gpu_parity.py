@@ -218,6 +218,35 @@ def _check_agg(capi, world, recs, strategy, factor, lb, ranked):
     return singles
 
 
+def test_ranked_seedextend_matches_oracle(capi, world):
+    """umgap_seedextend_ranked (seedextend -r, seedextend.rs:151-164) against the oracle on random id lists over the
+    world's taxonomy (ranked, unranked and unknown ids, misses, runs and gaps)."""
+    rng = random.Random(202)
+    otax = world["otax"]
+    known = [t[0] for t in otax.by_id if t is not None]
+    unknown = [i for i in range(1, len(otax.by_id)) if otax.by_id[i] is None][:3] + [len(otax.by_id) + 50]
+    recs = [[], [0], [0, 0, 0], [known[0]] * 5]
+    for _ in range(600):
+        pool = [rng.choice(known) for _ in range(rng.randrange(1, 5))] + [0, 0, rng.choice(unknown)]
+        rec = []
+        for _ in range(rng.randrange(1, 14)):
+            rec += [rng.choice(pool)] * rng.randrange(1, 6)
+        recs.append(rec)
+    flat = np.array([x for r in recs for x in r] or [0], dtype=np.uint32)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in recs], out=off[1:])
+    picked = 0
+    for s, g, pen in [(2, 0, 5), (3, 1, 5), (2, 2, 12), (4, 0, 0), (1, 0, 5)]:
+        got, goff = capi.seedextend_ranked(world["gtax"], flat, off, s, g, pen)
+        plain, poff = capi.seedextend(flat, off, s, g)[:2]
+        for i, rec in enumerate(recs):
+            want = ose.seedextend_ranked(rec, otax, s, g, pen)
+            mine = [int(x) for x in got[int(goff[i]):int(goff[i + 1])]]
+            assert mine == want, (s, g, pen, rec, mine, want)
+            picked += len(mine) < int(poff[i + 1] - poff[i])
+    assert picked > 200      # the ranked mode really drops seeds the plain mode keeps
+
+
 def test_aggregate_matches_oracle(capi, world):
     rng = random.Random(14)
     otax = world["otax"]

@@ -250,3 +250,25 @@ def test_oracle_joinkmers_on_a_hand_made_tree():
     assert got["AAAAD"] == {3} and got["DDDDD"] == {3}
     assert "CCCCC" not in got          # taxon 7 is unknown: dropped, nothing left, nothing printed
     assert len(got) == 4
+
+
+def test_oracle_ranked_seedextend_and_rank_score_ladder():
+    """oracle.seedextend ranked mode (seedextend.rs:151-164, taxon.rs:181-191, rank.rs:86-99)."""
+    from oracle import seedextend as ose
+    from oracle.taxonomy import Taxonomy, RANKS
+    # the ladder as written: everything above species scores 12, species and below and "no rank" nothing
+    for i, r in enumerate(RANKS):
+        want = 12 if 0 < i < RANKS.index("species") else None
+        assert ose.rank_score(i) == want, r
+    R = {r: i for i, r in enumerate(RANKS)}
+    taxa = [(1, "root", 0, 1, True), (2, "sk", R["superkingdom"], 1, True), (3, "g", R["genus"], 2, True),
+            (4, "s", R["species"], 3, True), (5, "nr", 0, 3, True), (6, "nr2", 0, 1, True)]
+    tax = Taxonomy(taxa)
+    assert [ose.taxon_score(tax, t) for t in (0, 1, 2, 3, 4, 5, 6, 7)] == [None, None, 12, 12, None, 12, None, None]
+    # two extended seeds: 3 3 3 (36) and 4 4 4 4 (4 x penalty 5 = 20) -> the first; with penalty 9 they tie -> the last
+    ids = [3, 3, 3, 0, 0, 4, 4, 4, 4]
+    assert ose.seedextend(ids, 2, 0) == [3, 3, 3, 4, 4, 4, 4]
+    assert ose.seedextend_ranked(ids, tax, 2, 0, 5) == [3, 3, 3]
+    assert ose.seedextend_ranked(ids, tax, 2, 0, 9) == [4, 4, 4, 4]
+    assert ose.seedextend_ranked(ids, tax, 2, 0, 10) == [4, 4, 4, 4]
+    assert ose.seedextend_ranked([1, 2, 3], tax, 2, 0, 5) == []

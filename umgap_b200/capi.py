@@ -31,7 +31,7 @@ SYMBOLS = [
     "umgap_translate_bound", "umgap_translate",
     "umgap_kmer_lookup_bound", "umgap_kmer_lookup",
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
-    "umgap_seedextend", "umgap_aggregate",
+    "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
     "umgap_translate_lookup_dev",
@@ -347,6 +347,19 @@ def seedextend(taxa: np.ndarray, rec_off: np.ndarray, min_seed_size: int = 2,
                                 C.c_int(min_seed_size), C.c_int(max_gap_size), _p(out),
                                 _p(out_off)))
     return out[: int(out_off[-1])], out_off
+
+
+def seedextend_ranked(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, min_seed_size: int = 2, max_gap_size: int = 0,
+                      penalty: int = 5):
+    """umgap_seedextend_ranked: (kept ids, offsets)."""
+    taxa = _arr(taxa, np.uint32)
+    rec_off = _arr(rec_off, np.uint64)
+    nrecs = len(rec_off) - 1
+    out = np.zeros(max(int(rec_off[-1]), 1), dtype=np.uint32)
+    out_off = np.zeros(nrecs + 1, dtype=np.uint64)
+    _check(load_library().umgap_seedextend_ranked(tax._h, _p(taxa), _p(rec_off), C.c_uint64(nrecs), C.c_int(min_seed_size),
+                                                  C.c_int(max_gap_size), C.c_int(penalty), _p(out), _p(out_off)))
+    return out[:int(out_off[-1])], out_off
 
 
 def aggregate(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, strategy: int,

@@ -585,8 +585,10 @@ int cmd_prot2tryp2lca(int argc, char** argv) {
 // ---- seedextend / taxa2agg ---------------------------------------------------------------------
 int cmd_seedextend(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'s', "min-seed-size", true}, {'g', "max-gap-size", true}, {'r', "ranked", true}, {'p', "penalty", true}});
-    if (a.has("ranked")) fail("seedextend --ranked is not implemented on the GPU path");
     const int s = (int)parse_usize(a.get("min-seed-size", "2")), g = (int)parse_usize(a.get("max-gap-size", "0"));
+    const int penalty = (int)parse_usize(a.get("penalty", "5"));
+    TaxHandle tax;  // -r: only the extended seed with the highest rank score is kept (seedextend.rs:84-90,151-164)
+    if (a.has("ranked")) check(umgap_taxonomy_load(a.get("ranked", "").c_str(), 0, &tax.p));
     BlockReader br(stdin);
     IdBatch b;
     std::vector<uint32_t> out_ids;
@@ -597,7 +599,10 @@ int cmd_seedextend(int argc, char** argv) {
         out_ids.assign(b.ids.size() + 1, 0);
         ooff.assign(b.size() + 1, 0);
         b.ids.push_back(0);  // never read: keeps data() valid for an all-empty batch
-        check(umgap_seedextend(0, b.ids.data(), b.off.data(), b.size(), s, g, out_ids.data(), ooff.data()));
+        if (tax.p)
+            check(umgap_seedextend_ranked(tax.p, b.ids.data(), b.off.data(), b.size(), s, g, penalty, out_ids.data(), ooff.data()));
+        else
+            check(umgap_seedextend(0, b.ids.data(), b.off.data(), b.size(), s, g, out_ids.data(), ooff.data()));
         out.clear();
         for (size_t i = 0; i < b.size(); ++i) {  // fasta.rs:164-180: header, then one id per line
             out += '>';

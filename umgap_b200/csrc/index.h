@@ -20,6 +20,7 @@ struct TaxView {
     const uint32_t* anc;         // ancestor matrix                                  [n*stride]
     const uint32_t* snap_valid;  // dense -> taxon id after snapping (taxon.rs:294-301)
     const uint32_t* snap_ranked; // same with ranked_only
+    const uint8_t* seed_score;   // dense -> TaxonList::score (taxon.rs:181-191, rank.rs:86-99), 0 = None
     uint32_t n;
     uint32_t max_id;
     uint32_t stride;             // max_depth+1 rounded up to a multiple of 8

@@ -115,6 +115,80 @@ seedextend_kernel(const uint32_t* __restrict__ taxa, const uint64_t* __restrict_
     }
 }
 
+// seedextend -r (seedextend.rs:151-164): of the extended seeds of a record only the one with the highest summed rank
+// score survives (`max_by_key`: the last of equal maxima); an id scores TaxonList::score, `penalty` when that is None
+// (unranked lineage, species and below -- see taxonomy.cu -- the 0 of a miss, ids the taxonomy does not hold).
+// One lane per record, the reference's loop as written (:101-149), over the ids plus the sentinel 0.
+__global__ void __launch_bounds__(128)
+seedextend_ranked_kernel(TaxView tv, const uint32_t* __restrict__ taxa, const uint64_t* __restrict__ rec_off, uint64_t nrecs,
+                         uint32_t min_seed, uint32_t max_gap, uint32_t penalty, uint32_t* __restrict__ out,
+                         uint32_t* __restrict__ out_len) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrecs; r += stride) {
+        const uint64_t off = rec_off[r];
+        const uint32_t n = (uint32_t)(rec_off[r + 1] - off);
+        const uint32_t* ids = taxa + off;
+        auto at = [&](uint32_t i) { return i < n ? ids[i] : 0u; };
+        auto score = [&](uint32_t t) -> uint64_t {
+            if (t > tv.max_id) return penalty;  // (taxon 0 is the reference's "unknown" taxon unless the file defines it)
+            const uint32_t d = __ldg(tv.dense_of + t);
+            if (d == kNoTaxon) return penalty;
+            const uint32_t s = __ldg(tv.seed_score + d);
+            return s ? s : penalty;
+        };
+        bool have = false;
+        uint32_t bs = 0, be = 0;
+        uint64_t best = 0;
+        auto seed = [&](uint32_t s, uint32_t e) {
+            if (e < s) e = s;
+            uint64_t sum = 0;
+            for (uint32_t i = s; i < e; ++i) sum += score(at(i));
+            if (!have || sum >= best) {
+                have = true;
+                best = sum;
+                bs = s;
+                be = e;
+            }
+        };
+        const uint32_t len = n + 1;
+        uint32_t start = 0, end = 1, last_tid = at(0), same_tid = 1, same_max = 1;
+        while (end < len) {
+            const uint32_t cur = at(end);
+            if (last_tid == cur) {
+                ++same_tid;
+                ++end;
+                continue;
+            }
+            if (last_tid == 0 && same_tid > max_gap) {
+                if (same_max >= min_seed) seed(start, end - same_tid);
+                start = end;
+                last_tid = cur;
+                same_tid = 1;
+                same_max = 1;
+                ++end;
+                continue;
+            }
+            if (last_tid == 0 && (end - start) == same_tid) {
+                ++end;
+                start = end;
+                continue;
+            }
+            if (last_tid != 0) same_max = max(same_max, same_tid);
+            last_tid = cur;
+            same_tid = 1;
+            ++end;
+        }
+        if (same_max >= min_seed) {
+            if (last_tid == 0) end -= same_tid;
+            seed(start, end);
+        }
+        uint32_t m = 0;
+        if (have)
+            for (uint32_t i = bs; i < be; ++i) out[off + m++] = at(i);
+        out_len[r] = m;
+    }
+}
+
 constexpr int kStageAggWarps = 4;
 constexpr uint32_t kStageAggCap = 512;
 
@@ -301,6 +375,36 @@ int umgap_seedextend(int device, const uint32_t* taxa, const uint64_t* rec_off, 
         UMGAP_CUDA(cudaMemcpy(d_off.p, rec_off, (nrecs + 1) * 8, cudaMemcpyHostToDevice));
         seedextend_kernel<<<grid_for(nrecs, 128), 128>>>(d_in.p, d_off.p, nrecs, (uint32_t)min_seed_size,
                                                          (uint32_t)max_gap_size, d_out.p, d_len.p);
+        UMGAP_CUDA(cudaGetLastError());
+        std::vector<uint32_t> len(nrecs), tmp(total + 1);
+        UMGAP_CUDA(cudaMemcpy(len.data(), d_len.p, nrecs * 4, cudaMemcpyDeviceToHost));
+        if (total) UMGAP_CUDA(cudaMemcpy(tmp.data(), d_out.p, total * 4, cudaMemcpyDeviceToHost));
+        uint64_t w = 0;
+        for (uint64_t r = 0; r < nrecs; ++r) {
+            out_off[r] = w;
+            memcpy(out + w, tmp.data() + rec_off[r], (size_t)len[r] * 4);
+            w += len[r];
+        }
+        out_off[nrecs] = w;
+    });
+}
+
+int umgap_seedextend_ranked(const umgap_taxonomy* tax, const uint32_t* taxa, const uint64_t* rec_off, uint64_t nrecs,
+                            int min_seed_size, int max_gap_size, int penalty, uint32_t* out, uint64_t* out_off) {
+    return guarded([&] {
+        if (!tax || !rec_off || !out_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (min_seed_size < 0 || max_gap_size < 0 || penalty < 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "negative size");
+        const uint64_t total = rec_off[nrecs];
+        for (uint64_t i = 0; i <= nrecs; ++i) out_off[i] = 0;
+        if (!nrecs) return;
+        if (total && (!taxa || !out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(tax->device);
+        DevBuf<uint32_t> d_in(total + 1), d_out(total + 1), d_len(nrecs);
+        DevBuf<uint64_t> d_off(nrecs + 1);
+        if (total) UMGAP_CUDA(cudaMemcpy(d_in.p, taxa, total * 4, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemcpy(d_off.p, rec_off, (nrecs + 1) * 8, cudaMemcpyHostToDevice));
+        seedextend_ranked_kernel<<<grid_for(nrecs, 128), 128>>>(tax->view, d_in.p, d_off.p, nrecs, (uint32_t)min_seed_size,
+                                                                (uint32_t)max_gap_size, (uint32_t)penalty, d_out.p, d_len.p);
         UMGAP_CUDA(cudaGetLastError());
         std::vector<uint32_t> len(nrecs), tmp(total + 1);
         UMGAP_CUDA(cudaMemcpy(len.data(), d_len.p, nrecs * 4, cudaMemcpyDeviceToHost));

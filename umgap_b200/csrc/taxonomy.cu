@@ -137,6 +137,17 @@ static void build(umgap_taxonomy* tax, const std::vector<uint64_t>& ids,
         snap_ranked[x] = rk ? id_of[x] : (x == 0 ? id_of[0] : snap_ranked[parent[x]]);
     }
 
+    // seedextend -r: the rank score of a taxon is that of its nearest ancestor-or-self with a rank (the root ends the
+    // walk whatever its rank), taxon.rs:181-191.  Rank::score (rank.rs:86-99) is a ladder of `self < X` tests whose first
+    // rung, `self < Species`, already holds for every rank above species: those score 12, species and below fall
+    // through every rung to None, and so does "no rank" (its comparisons are all false).  Restated as written.
+    std::vector<uint8_t> seed_score(nd), eff_rank(nd);
+    for (uint32_t x = 0; x < nd; ++x) {
+        const uint8_t rk = rank[row_of[id_of[x]]];
+        eff_rank[x] = (x == 0 || rk != 0) ? rk : eff_rank[parent[x]];
+        seed_score[x] = (eff_rank[x] != 0 && eff_rank[x] < 27 /* Rank::Species */) ? 12 : 0;
+    }
+
     tax->ids = ids;
     tax->parents = parents;
     tax->root = root;
@@ -157,6 +168,7 @@ static void build(umgap_taxonomy* tax, const std::vector<uint64_t>& ids,
     v.anc = upload(tax, anc);
     v.snap_valid = upload(tax, snap_valid);
     v.snap_ranked = upload(tax, snap_ranked);
+    v.seed_score = upload(tax, seed_score);
     v.n = nd;
     v.max_id = (uint32_t)max_id;
     v.stride = stride;
