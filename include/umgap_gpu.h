@@ -253,7 +253,7 @@ void umgap_tryp_opts_default(umgap_tryp_opts* o);
 int umgap_classify_peptides(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts,
                             const uint8_t* aa, const uint64_t* line_off, uint64_t nlines,
                             const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out);
-/* Device-resident variant, asynchronous on `stream`; total_aa = line_off[nlines].                 */
+/* Device-resident variant, asynchronous on `stream`; total_aa = line_off[nlines]; aa_dev 8-byte aligned. */
 int umgap_classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* opts,
                                 const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines,
                                 uint64_t total_aa, const uint64_t* group_off_dev, uint64_t ngroups,
