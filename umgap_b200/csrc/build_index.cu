@@ -113,6 +113,9 @@ int umgap_index_build_from_proteins(const umgap_taxonomy* tax, const uint8_t* aa
                 *out = idx;
                 return;
             }
+            if (W >= (1ull << 31))  // the run-length encoding of the sorted windows is a library call with 32-bit counts
+                UMGAP_FAIL(UMGAP_ERR_CAPACITY, "%llu k-mer windows: more than 2^31 per call, build the index from shards of the protein table",
+                           (unsigned long long)W);
             size_t free_b = 0, total_b = 0;
             UMGAP_CUDA(cudaMemGetInfo(&free_b, &total_b));
             if ((double)W * 48.0 + (double)total > 0.9 * (double)free_b)
