@@ -565,6 +565,18 @@ def test_index_built_from_proteins_matches_oracle_joinkmers(capi, world, k):
     info = gidx.info()
     assert info.n_keys == len(want) and info.k == k
     kmers = sorted(want)
+    # the same table built in three passes over hash-prefix ranges of the k-mers (protein tables too large to sort at once)
+    os.environ["UMGAP_BUILD_PASSES"] = "3"
+    try:
+        pidx = capi.Index.build_from_proteins(world["gtax"], [sq.encode() for _, sq in rows], [t for t, _ in rows], k=k)
+    finally:
+        del os.environ["UMGAP_BUILD_PASSES"]
+    assert pidx.info().n_keys == len(want)
+    aa_k, off_k = capi.pack_strings([x.encode() for x in kmers])
+    one_pass, _, _ = capi.kmer_lookup(gidx, aa_k, off_k, True)
+    three_pass, _, _ = capi.kmer_lookup(pidx, aa_k, off_k, True)
+    assert np.array_equal(one_pass, three_pass)
+    pidx.close()
     misses = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(k)) for _ in range(3000)]
     misses = [m for m in misses if m not in want]
     aa, off = capi.pack_strings([x.encode() for x in kmers + misses])
