@@ -191,11 +191,12 @@ def test_seedextend_matches_oracle(capi):
     rng = random.Random(10)
     recs = _random_id_lists(rng, 600)
     recs += [[0, 5, 5, 5], [0, 5, 5], [0, 0, 5, 5, 5], [7, 7, 7, 0, 1, 1], [5, 5, 0, 6, 6],
-             [9606, 9606, 2759, 9606, 9606, 9606, 9606, 9606, 9606, 9606, 8287]]
+             [9606, 9606, 2759, 9606, 9606, 9606, 9606, 9606, 9606, 9606, 8287],
+             [0, 5, 0, 7], [0, 5, 0, 0, 7, 7], [0, 0, 5, 0, 0, 0, 7]]   # inverted range after a leading gap (-s1 -g1)
     flat = np.array([x for r in recs for x in r], dtype=np.uint32)
     off = np.zeros(len(recs) + 1, dtype=np.uint64)
     off[1:] = np.cumsum([len(r) for r in recs])
-    for s in (2, 3, 4):
+    for s in (0, 1, 2, 3, 4):
         for g in (0, 1, 2):
             out, ooff = capi.seedextend(flat, off, s, g)
             for i, r in enumerate(recs):

@@ -1,4 +1,4 @@
-// Streaming reader for `fst` 0.3.x Map files (on-disk format version 1/2), the index format
+// Streaming reader for `fst` 0.3.x Map files (on-disk format version 2), the index format
 // `umgap buildindex` writes (buildindex.rs:32-48) and the lookup commands open
 // (prot2kmer2lca.rs:109-114).  The crate is a third-party dependency that is not vendored in the
 // reference (Cargo.toml:23); this file implements its published node encoding:
@@ -132,7 +132,9 @@ struct Mapped {
 
 void check_header(const Mapped& m, uint64_t& len, uint64_t& root) {
     const uint64_t version = unpack(m.data, 8);
-    if (version == 0 || version > 2) UMGAP_FAIL(UMGAP_ERR_IO, "unsupported fst version %llu", (unsigned long long)version);
+    // Version 1 lacks the 256-byte transition index of nodes with more than 32 transitions, which the
+    // node decoder assumes; `fst` 0.3.5 (Cargo.toml:23) writes version 2 only.
+    if (version != 2) UMGAP_FAIL(UMGAP_ERR_IO, "unsupported fst version %llu (expected 2)", (unsigned long long)version);
     len = unpack(m.data + m.size - 16, 8);
     root = unpack(m.data + m.size - 8, 8);
     if (!((root == 0 && m.size == 32) || root + 17 == m.size))

@@ -68,7 +68,10 @@ __device__ __forceinline__ void seedextend_stream(const uint32_t* ids, uint32_t 
         if (last == cur) {                                   // :109-113
             ++same;
         } else if (last == 0 && same > max_gap) {            // :116-127 gap too long
-            if (smax >= min_seed) flush(start_raw, end - same - start);
+            // the reference slices start..end-same here; after a leading gap (:130-134) start can lie
+            // beyond it (min_seed <= 1, max_gap >= 1), where the reference panics: an empty selection
+            const uint32_t e = end - same;
+            if (smax >= min_seed && e > start) flush(start_raw, e - start);
             start = end;
             start_raw = cur_raw;
             last = cur;
