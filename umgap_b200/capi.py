@@ -35,6 +35,7 @@ SYMBOLS = [
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
     "umgap_translate_lookup_dev",
+    "umgap_packed_words", "umgap_pack_reads", "umgap_classify_reads_packed",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
     "umgap_route_sampled_applies", "umgap_route_pack_sampled_dev", "umgap_route_scatter_hits_dev", "umgap_classify_ids_masked_dev",
     "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices", "umgap_pipeline_sampling",
@@ -424,6 +425,36 @@ def classify_reads(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarr
     _check(lib.umgap_classify_reads(index._h, tax._h, C.byref(opts), _p(nt), _p(read_off),
                                     C.c_uint64(len(read_off) - 1), _p(group_off),
                                     C.c_uint64(ngroups), _p(out), C.byref(nl) if count_lookups else None))
+    return out[:ngroups], (nl.value if count_lookups else None)
+
+
+def pack_reads(nt: np.ndarray, threads: int = 0, pinned=None):
+    """umgap_pack_reads: nucleotide bytes -> (codes uint32[], nmask uint16[]), 16 nucleotides per word.  `pinned`:
+    optional (codes, nmask) arrays to fill (e.g. views of page-locked memory)."""
+    lib = load_library()
+    lib.umgap_packed_words.restype = C.c_uint64
+    nt = _arr(nt, np.uint8)
+    nw = int(lib.umgap_packed_words(C.c_uint64(len(nt))))
+    codes, nmask = pinned if pinned is not None else (np.zeros(max(nw, 1), dtype=np.uint32), np.zeros(max(nw, 1), dtype=np.uint16))
+    assert len(codes) >= nw and len(nmask) >= nw
+    _check(lib.umgap_pack_reads(_p(nt), C.c_uint64(len(nt)), _p(codes), _p(nmask), C.c_int(threads)))
+    return codes, nmask
+
+
+def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes: np.ndarray, nmask: Optional[np.ndarray],
+                          read_off: np.ndarray, group_off: np.ndarray, count_lookups: bool = True,
+                          out: Optional[np.ndarray] = None):
+    """umgap_classify_reads_packed (host buffers, 2-bit nucleotides + N flags)."""
+    lib = load_library()
+    read_off = _arr(read_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    nl = C.c_uint64()
+    _check(lib.umgap_classify_reads_packed(index._h, tax._h, C.byref(opts), _p(codes), _p(nmask), _p(read_off),
+                                           C.c_uint64(len(read_off) - 1), _p(group_off), C.c_uint64(ngroups), _p(out),
+                                           C.byref(nl) if count_lookups else None))
     return out[:ngroups], (nl.value if count_lookups else None)
 
 

@@ -100,6 +100,15 @@ __device__ __forceinline__ uint32_t nt_code(uint8_t c) {
     return c == 'T' ? 0u : c == 'C' ? 1u : c == 'A' ? 2u : c == 'G' ? 3u : 4u;
 }
 
+// Where a batch's nucleotides come from: the bytes as received, or the packed form of
+// umgap_classify_reads_packed -- codes[x / 16] holds nucleotide x at bits 2 (x % 16) (A, C, G, T = 0, 1, 2, 3),
+// nmask[x / 16] bit x % 16 is up when the byte was none of those letters (N, dna/mod.rs:34-44).
+struct NtSrc {
+    const uint8_t* bytes = nullptr;
+    const uint32_t* codes = nullptr;
+    const uint16_t* nmask = nullptr;
+};
+
 #ifndef UMGAP_K1_BLOCKS
 #define UMGAP_K1_BLOCKS 3
 #endif
@@ -139,9 +148,9 @@ struct LookupSmem {
 // Index of position j of frame f of a strand in the frame-major layout, relative to the strand's first word.
 // (frame_major_index: table.cuh)
 
-template <int K, class TV, bool REGION>
+template <int K, class TV, bool REGION, bool PACKED>
 __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lut, LookupSmem<K>& sm,
-                                                const uint8_t* __restrict__ nt, uint32_t n, uint32_t* out, int lane,
+                                                const NtSrc& nv, uint64_t off, uint32_t n, uint32_t* out, int lane,
                                                 uint64_t region_lo, uint64_t region_hi, bool frame_major = false) {
     constexpr int W = LookupSmem<K>::W;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -150,7 +159,14 @@ __device__ __forceinline__ uint32_t lookup_read(const TV& t, const uint8_t* s_lu
     for (uint32_t w0 = 0; w0 < npos; w0 += kTile) {
         for (int i = lane; i < W + 2; i += 32) {
             const uint32_t x = w0 + i;
-            sm.nt[i] = x < n ? (uint8_t)nt_code(nt[x]) : (uint8_t)4;
+            if (PACKED) {  // A,C,G,T = 0..3 -> codon order T,C,A,G (nibble k of 0x0312)
+                const uint64_t g = off + x;
+                const uint32_t c = x < n ? (__ldg(nv.codes + (g >> 4)) >> (2 * (g & 15))) & 3u : 0u;
+                const bool isn = x >= n || ((__ldg(nv.nmask + (g >> 4)) >> (g & 15)) & 1u);
+                sm.nt[i] = isn ? (uint8_t)4 : (uint8_t)((0x0312u >> (4 * c)) & 3u);
+            } else {
+                sm.nt[i] = x < n ? (uint8_t)nt_code(nv.bytes[off + x]) : (uint8_t)4;
+            }
         }
         __syncwarp();
         for (int i = lane; i < W; i += 32) {
@@ -272,9 +288,9 @@ struct ReadList {
 };
 
 // Lookup kernel: one warp per read, ids to global memory, frame hit masks to frame_hits.
-template <int K, class TV, bool REGION>
+template <int K, class TV, bool REGION, bool PACKED>
 __global__ void __launch_bounds__(kLookupWarps * 32, UMGAP_K1_BLOCKS)
-translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
+translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const NtSrc nv,
                         const uint64_t* __restrict__ read_off, uint64_t r_begin, uint64_t r_end,
                         uint32_t* __restrict__ ids, uint8_t* __restrict__ frame_hits, uint64_t region_lo,
                         uint64_t region_hi, ReadList rl /* rl.list set: only the reads of that list */) {
@@ -296,7 +312,7 @@ translate_lookup_kernel(const __grid_constant__ TV t, const __grid_constant__ Co
         const uint32_t n = (uint32_t)(read_off[r + 1] - off);
         uint32_t mask = 0;  // a read none of whose frames reaches K residues has no records at all
         if (n >= 3u * K)
-            mask = lookup_read<K, TV, REGION>(t, s_lut, s_sm[warp], nt + off, n, ids + 2 * off, lane, region_lo, region_hi, list != nullptr);
+            mask = lookup_read<K, TV, REGION, PACKED>(t, s_lut, s_sm[warp], nv, off, n, ids + 2 * off, lane, region_lo, region_hi, list != nullptr);
         if (frame_hits && lane == 0) frame_hits[r] = (uint8_t)(!REGION || region_lo == 0 ? mask : (mask | frame_hits[r]));
     }
 }
@@ -362,6 +378,25 @@ __device__ __forceinline__ void translate_chunk16(uint32_t (&w)[5], const uint16
         const uint32_t c = (w[(i + 2) >> 2] >> (8 * ((i + 2) & 3))) & 7u;
         idx = ((idx << 2) | (c & 3u)) & 63u;
         nm = ((nm << 1) | (c >> 2)) & 7u;
+        const uint32_t pr = pair[nm ? 64u : idx];
+        fo[i >> 2] |= (pr & 0xFFu) << (8 * (i & 3));
+        ro[i >> 2] |= (pr >> 8) << (8 * (i & 3));
+    }
+}
+
+// The same from the packed form: codes = 20 nucleotides at 2 bits each (the chunk's 16 and the 4 that follow),
+// nbits = their N flags.
+__device__ __forceinline__ void translate_chunk16_packed(uint64_t codes, uint32_t nbits, const uint16_t* pair, uint32_t (&fo)[4],
+                                                         uint32_t (&ro)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fo[i] = ro[i] = 0;
+    uint32_t idx = (((uint32_t)codes & 3u) << 2) | (((uint32_t)codes >> 2) & 3u);
+    uint32_t nm = ((nbits & 1u) << 1) | ((nbits >> 1) & 1u);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t c = (uint32_t)(codes >> (2 * (i + 2))) & 3u;
+        idx = ((idx << 2) | c) & 63u;
+        nm = ((nm << 1) | ((nbits >> (i + 2)) & 1u)) & 7u;
         const uint32_t pr = pair[nm ? 64u : idx];
         fo[i >> 2] |= (pr & 0xFFu) << (8 * (i & 3));
         ro[i >> 2] |= (pr >> 8) << (8 * (i & 3));
@@ -579,9 +614,9 @@ __device__ __forceinline__ uint32_t record_geometry(const SampledSmem& sm, uint3
 // without a live frame are not even translated).  MODE 3 / 4: the two phases of the routed mode -- the walk is the same,
 // the lookups go to the owners' buckets (RouteSink) instead of the table; phase 1's answers come back as frame masks
 // (route_scatter_hits_kernel), phase 2 sends every position of the live frames.
-template <int K, class TV, int STRIDE, int MODE>
+template <int K, class TV, int STRIDE, int MODE, bool PACKED>
 __global__ void __launch_bounds__(kSWarps * 32, kSBlocks)
-lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const uint8_t* __restrict__ nt,
+lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ CodonLut lut, const NtSrc nv,
                       uint64_t total_nt, const uint64_t* __restrict__ read_off, uint32_t nreads, uint32_t* __restrict__ ids,
                       uint8_t* __restrict__ frame_hits, const uint64_t* __restrict__ group_off, uint64_t g_lo, uint64_t g_hi,
                       uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t* __restrict__ unit_count,
@@ -641,17 +676,33 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
             // ---- stage: 16 nucleotides per lane and step (plus the 4 bytes that follow them: two are needed), translated
             //      in registers (translate.rs:114-133, dna/mod.rs:23-103, dna/translation.rs:125-144), both residue-code
             //      chunks to shared memory; the batch starts at byte `mis` of the first chunk
-            const uint32_t mis = (uint32_t)((uintptr_t)(nt + off0) & 15u);
+            const uint32_t mis = PACKED ? (uint32_t)(off0 & 15u) : (uint32_t)((uintptr_t)(nv.bytes + off0) & 15u);
             {
-                const uint64_t x_first = off0 - mis;  // nt is 16-byte aligned, so is this
+                const uint64_t x_first = off0 - mis;  // the byte array is 16-byte aligned, so is this
                 const uint32_t nch = (mis + span + 15) / 16;
                 for (uint32_t c = lane; c < nch; c += 32) {
                     const uint64_t x0 = x_first + 16ull * c;
+                    uint32_t fo[4], ro[4];
+                    if (PACKED) {  // one word of codes and one of N flags per chunk, plus the low bits of the next
+                        const uint64_t wi = x0 >> 4;
+                        uint64_t codes = __ldg(nv.codes + wi);
+                        uint32_t nbits = __ldg(nv.nmask + wi);
+                        if (x0 + 16 < total_nt) {
+                            codes |= (uint64_t)(__ldg(nv.codes + wi + 1) & 0xFFu) << 32;
+                            nbits |= ((uint32_t)__ldg(nv.nmask + wi + 1) & 0xFu) << 16;
+                        } else {
+                            nbits |= 0xFu << 16;  // N past the end
+                        }
+                        translate_chunk16_packed(codes, nbits, s_pair, fo, ro);
+                        sm.f[c] = make_uint4(fo[0], fo[1], fo[2], fo[3]);
+                        sm.r[c] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+                        continue;
+                    }
+                    const uint8_t* nt = nv.bytes;
                     uint32_t w[5];
                     const uint4 v = __ldg(reinterpret_cast<const uint4*>(nt + x0));  // the chunk holds a nucleotide of the batch
                     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
                     w[4] = x0 + 20 <= total_nt ? __ldg(reinterpret_cast<const uint32_t*>(nt + x0 + 16)) : 0x4E4E4E4Eu;  // 'N's past the end
-                    uint32_t fo[4], ro[4];
                     translate_chunk16(w, s_pair, fo, ro);
                     sm.f[c] = make_uint4(fo[0], fo[1], fo[2], fo[3]);
                     sm.r[c] = make_uint4(ro[0], ro[1], ro[2], ro[3]);
@@ -1262,11 +1313,12 @@ classify_kernel(TaxView tv, ClassifyParams cp, const uint32_t* __restrict__ ids,
 
 // Chunk-relative offset slices: an uploaded slice has the chunk's first nucleotide / first read subtracted; a slice the
 // host found to be an arithmetic progression (all reads of one length, all groups of one size) was not uploaded at all
-// and is written here (step != 0).
-__global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_t step_a, uint64_t* b, uint64_t nb,
+// and is written here (step != 0).  add_a: a packed chunk starts inside its first 16-nucleotide word.
+__global__ void rebase_kernel(uint64_t* a, uint64_t na, uint64_t base_a, uint64_t step_a, uint64_t add_a, uint64_t* b, uint64_t nb,
                               uint64_t base_b, uint64_t step_b) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) a[i] = step_a ? i * step_a : a[i] - base_a;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride)
+        a[i] = (step_a ? i * step_a : a[i] - base_a) + add_a;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = step_b ? i * step_b : b[i] - base_b;
 }
 
@@ -1355,7 +1407,7 @@ constexpr uint64_t kDefaultRegionBytes = 60ull << 30;
 
 // Lookup launch over reads [r_begin, r_end).
 static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline_opts* o,
-                                    const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t r_begin,
+                                    const NtSrc& nv, const uint64_t* read_off_dev, uint64_t r_begin,
                                     uint64_t r_end, uint32_t* ids_dev, uint8_t* frame_hits_dev, cudaStream_t st,
                                     ReadList rl = ReadList(), bool timed = true) {
     if (r_end <= r_begin) return;
@@ -1375,21 +1427,27 @@ static void launch_translate_lookup(const umgap_index* idx, const umgap_pipeline
         const uint64_t lo = (1ull << 32) * reg / nregions, hi = (1ull << 32) * (reg + 1) / nregions;
         LaunchTimer timer(0, st, timed);
         switch (idx->k) {
+#define UMGAP_TL(KK, VIEW, VIEWARG, REG)                                                                     \
+    if (nv.codes)                                                                                            \
+        translate_lookup_kernel<KK, VIEW, REG, true><<<blocks, kLookupWarps * 32, 0, st>>>(                   \
+            VIEWARG, lut, nv, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);            \
+    else                                                                                                     \
+        translate_lookup_kernel<KK, VIEW, REG, false><<<blocks, kLookupWarps * 32, 0, st>>>(                  \
+            VIEWARG, lut, nv, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl)
 #define UMGAP_CASE(KK)                                                                                       \
     case KK:                                                                                                 \
-        if (idx->nshards > 1)                                                                                \
-            translate_lookup_kernel<KK, ShardedView, false><<<blocks, kLookupWarps * 32, 0, st>>>(            \
-                idx->sharded, lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);   \
-        else if (nregions > 1)                                                                               \
-            translate_lookup_kernel<KK, TableView, true><<<blocks, kLookupWarps * 32, 0, st>>>(               \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);    \
-        else                                                                                                 \
-            translate_lookup_kernel<KK, TableView, false><<<blocks, kLookupWarps * 32, 0, st>>>(              \
-                idx->view(), lut, nt_dev, read_off_dev, r_begin, r_end, ids_dev, frame_hits_dev, lo, hi, rl);    \
+        if (idx->nshards > 1) {                                                                              \
+            UMGAP_TL(KK, ShardedView, idx->sharded, false);                                                  \
+        } else if (nregions > 1) {                                                                           \
+            UMGAP_TL(KK, TableView, idx->view(), true);                                                      \
+        } else {                                                                                             \
+            UMGAP_TL(KK, TableView, idx->view(), false);                                                     \
+        }                                                                                                    \
         break;
             UMGAP_CASE(1) UMGAP_CASE(2) UMGAP_CASE(3) UMGAP_CASE(4) UMGAP_CASE(5) UMGAP_CASE(6)
             UMGAP_CASE(7) UMGAP_CASE(8) UMGAP_CASE(9)
 #undef UMGAP_CASE
+#undef UMGAP_TL
             default:
                 UMGAP_FAIL(UMGAP_ERR_INVALID, "unsupported k %d", idx->k);
         }
@@ -1431,7 +1489,7 @@ struct SampledPlan {  // the sampled lookup stage of one batch
 };
 
 // reads_hint: number of reads the launch will find in its group range (sizes the grid only).
-static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const SampledPlan& sp, const uint8_t* nt_dev,
+static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const SampledPlan& sp, const NtSrc& nv,
                            const uint64_t* read_off_dev, uint64_t nreads, uint64_t reads_hint, uint32_t* ids_dev,
                            uint8_t* frame_hits_dev, const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi, int slice,
                            cudaStream_t st) {
@@ -1441,10 +1499,12 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
         return 148u * (unsigned)(v > 0 ? v : kSBlocks);  // one resident wave: the units are handed out dynamically
     }();
     const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(reads_hint, kSReads), kSWarps) + 1, grid_cap);
-#define UMGAP_SAMPLED(S, MODE, COUNTER, LO, HI)                                                                                \
-    lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
-        idx->view(), sp.lut, nt_dev, sp.total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo,  \
+#define UMGAP_SAMPLED_P(S, MODE, COUNTER, LO, HI, PK)                                                                          \
+    lookup_sampled_kernel<9, TableView, S, MODE, PK><<<blocks, kSWarps * 32, 0, st>>>(                                          \
+        idx->view(), sp.lut, nv, sp.total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo,      \
         g_hi, sp.long_list, sp.long_count + slice, sp.long_count + 64 + (COUNTER), LO, HI, RouteSink())
+#define UMGAP_SAMPLED(S, MODE, COUNTER, LO, HI)                                                                                \
+    if (nv.codes) UMGAP_SAMPLED_P(S, MODE, COUNTER, LO, HI, true); else UMGAP_SAMPLED_P(S, MODE, COUNTER, LO, HI, false)
 #define UMGAP_SAMPLED_STRIDES(MODE, COUNTER, LO, HI)                 \
     switch (sp.stride) {                                             \
         case 2: UMGAP_SAMPLED(2, MODE, COUNTER, LO, HI); break;      \
@@ -1471,20 +1531,21 @@ static void launch_sampled(const umgap_index* idx, const umgap_pipeline_opts* o,
     }
 #undef UMGAP_SAMPLED_STRIDES
 #undef UMGAP_SAMPLED
+#undef UMGAP_SAMPLED_P
     // the reads the kernel queued (longer than a warp batch; rare): every position, plain kernel over the list
     ReadList rl;
     rl.list = sp.long_list;
     rl.count = sp.long_count + slice;
     rl.group_off = group_off_dev;
     rl.g_lo = g_lo;
-    launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, rl, false);
+    launch_translate_lookup(idx, o, nv, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st, rl, false);
 }
 
 // Sampled lookups (see lookup_sampled_kernel): valid only in front of seedextend with -o and S >= 2; only
 // the frames flagged in frame_hits_dev have ids afterwards, which is all the classify kernel reads.
 // Decides whether the stage applies and, if so, prepares what a batch needs once: the codon table and the
 // work list through which reads longer than a warp batch reach the plain kernel.
-static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const uint8_t* nt_dev,
+static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_opts* o, const NtSrc& nv,
                                    const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint32_t* ids_dev,
                                    uint8_t* frame_hits_dev, cudaStream_t st, int buf) {
     SampledPlan sp;
@@ -1492,7 +1553,7 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
     const uint64_t region_bytes = idx->region_bytes ? idx->region_bytes : kDefaultRegionBytes;
     const uint64_t nregions = std::max<uint64_t>(1, ceil_div((uint64_t)idx->level_nlines[0] * 128, region_bytes));
     if (disabled || !o->seedextend || !o->one_on_one || o->min_seed_size < 2 || idx->k != 9 || idx->nshards > 1 ||
-        nregions > 32 || !frame_hits_dev || nreads >= (1ull << 31) || ((uintptr_t)nt_dev & 15u) != 0)
+        nregions > 32 || !frame_hits_dev || nreads >= (1ull << 31) || (!nv.codes && ((uintptr_t)nv.bytes & 15u) != 0))
         return sp;
     sp.stride = std::min(o->min_seed_size, 4);
     sp.nregions = (int)nregions;
@@ -1509,23 +1570,23 @@ static SampledPlan prepare_sampled(const umgap_index* idx, const umgap_pipeline_
 }
 
 static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* o,
-                            const uint8_t* nt_dev, const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
+                            const NtSrc& nv, const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
                             const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* ids_dev, uint32_t* scratch_dev,
                             uint8_t* frame_hits_dev, uint32_t* out_dev, DevError* err, cudaStream_t st, int buf = 0,
                             bool sliced = false) {
     if (!ngroups) return;
     const int kSlices = g_slices;
     LaunchTimer timer(0, st);
-    const SampledPlan sp = prepare_sampled(idx, o, nt_dev, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
+    const SampledPlan sp = prepare_sampled(idx, o, nv, read_off_dev, nreads, total_nt, ids_dev, frame_hits_dev, st, buf);
     const bool slice_it = sliced && kSlices >= 2 && ngroups >= 4096u * (uint64_t)kSlices && nreads && sp.nregions == 1;
     if (!sp.stride) {
         timer.cancel();  // the plain launch brackets itself
-        launch_translate_lookup(idx, o, nt_dev, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
+        launch_translate_lookup(idx, o, nv, read_off_dev, 0, nreads, ids_dev, frame_hits_dev, st);
         launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st);
         return;
     }
     if (!slice_it) {
-        if (nreads) launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, 0, st);
+        if (nreads) launch_sampled(idx, o, sp, nv, read_off_dev, nreads, nreads, ids_dev, frame_hits_dev, nullptr, 0, 0, 0, st);
         timer.stop();
         launch_classify(idx, tax, o, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch_dev, out_dev, err, st, true);
         return;
@@ -1551,7 +1612,7 @@ static void launch_pipeline(const umgap_index* idx, const umgap_taxonomy* tax, c
         cudaStream_t s = idx->aux_stream[sl & 1];
         {
             LaunchTimer t2(0, s);
-            launch_sampled(idx, o, sp, nt_dev, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev,
+            launch_sampled(idx, o, sp, nv, read_off_dev, nreads, ceil_div(nreads, kSlices), ids_dev, frame_hits_dev, group_off_dev,
                            g_lo, g_hi, sl, s);
             t2.stop();
         }
@@ -1662,7 +1723,9 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
     return guarded([&] {
         check_opts(idx, nullptr, opts);
         use_device(idx->device);
-        launch_translate_lookup(idx, opts, nt_dev, read_off_dev, 0, nreads, ids_dev, nullptr, (cudaStream_t)stream);
+        NtSrc nv;
+        nv.bytes = nt_dev;
+        launch_translate_lookup(idx, opts, nv, read_off_dev, 0, nreads, ids_dev, nullptr, (cudaStream_t)stream);
     });
 }
 
@@ -1748,9 +1811,11 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         rs.nshards = (uint32_t)idx->nshards;
         const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(nreads, kSReads), kSWarps) + 1, 148ull * kSBlocks);
         const int stride = std::min(opts->min_seed_size, 4);
+        NtSrc nv;
+        nv.bytes = nt_dev;
 #define UMGAP_ROUTE_SAMPLED(S, MODE)                                                                                          \
-    lookup_sampled_kernel<9, TableView, S, MODE><<<blocks, kSWarps * 32, 0, st>>>(                                              \
-        idx->view(), lut, nt_dev, total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo, g_hi, counters + 128, \
+    lookup_sampled_kernel<9, TableView, S, MODE, false><<<blocks, kSWarps * 32, 0, st>>>(                                       \
+        idx->view(), lut, nv, total_nt, read_off_dev, (uint32_t)nreads, ids_dev, frame_hits_dev, group_off_dev, g_lo, g_hi, counters + 128, \
         counters, counters + 64, 0ull, 1ull << 32, rs)
         if (phase == 1) {
             switch (stride) {
@@ -1791,113 +1856,202 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
         DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemsetAsync(err, 0, sizeof(DevError), st));
         uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS, nreads + 64);
-        launch_pipeline(idx, tax, opts, nt_dev, read_off_dev, nreads, total_nt, group_off_dev, ngroups, ids, scratch, hits,
+        NtSrc nv;
+        nv.bytes = nt_dev;
+        launch_pipeline(idx, tax, opts, nv, read_off_dev, nreads, total_nt, group_off_dev, ngroups, ids, scratch, hits,
                         taxon_out_dev, err, st, 0, true);
     });
 }
+
+extern "C++" {
+namespace {
+// N flags of a packed chunk that travel as (word index << 16 | flags) entries when few words hold an N.
+__global__ void nmask_scatter_kernel(uint16_t* nmask, const uint64_t* entries, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nmask[entries[i] >> 16] = (uint16_t)(entries[i] & 0xFFFFu);
+}
+
+struct HostReads {  // one of the two host forms of a batch's nucleotides
+    const uint8_t* nt = nullptr;       // bytes as received
+    const uint32_t* codes = nullptr;   // packed: 2 bits per nucleotide ...
+    const uint16_t* nmask = nullptr;   // ... and one N flag each (NULL: no N anywhere)
+};
+
+}  // namespace
+
+static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                          const HostReads& hr, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
+                          uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+    check_opts(idx, tax, opts);
+    if (!tax) UMGAP_FAIL(UMGAP_ERR_INVALID, "null taxonomy");
+    const bool packed = hr.codes != nullptr;
+    if ((nreads && ((!hr.nt && !packed) || !read_off)) || (ngroups && (!group_off || !taxon_out)))
+        UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+    use_device(idx->device);
+    if (n_lookups) {
+        uint64_t c = 0;
+        const uint64_t span = 3ull * idx->k;
+        for (uint64_t r = 0; r < nreads; ++r) {
+            const uint64_t n = read_off[r + 1] - read_off[r];
+            if (n >= span) c += 2 * (n - span + 1);
+        }
+        *n_lookups = c;
+    }
+    if (!ngroups) return;
+    if (group_off[ngroups] != nreads || group_off[0] != 0)
+        UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off must cover reads 0..nreads");
+    // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
+    // nucleotides and offsets of the next chunks upload and the results of the previous one
+    // download.  Offsets are uploaded as given and rebased on the device.
+    // nucleotides per chunk (measured best of 6..96 MiB x 3..6 streams: profiles/r01_e2e_chunk_sweep.log; UMGAP_CHUNK_MB, or
+    // UMGAP_CHUNK_NT in nucleotides, override it -- read per call, so that tests can move the chunk seams)
+    const uint64_t kChunkNt = []() -> uint64_t {
+        const char* n = getenv("UMGAP_CHUNK_NT");
+        if (n && strtoull(n, nullptr, 10)) return std::max<uint64_t>(512, strtoull(n, nullptr, 10));
+        const char* e = getenv("UMGAP_CHUNK_MB");
+        const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
+        return (uint64_t)((mb ? mb : 16ull) << 20);
+    }();
+    static const int kBufs = [] {  // chunks in flight (streams); UMGAP_CHUNK_STREAMS overrides
+        const char* e = getenv("UMGAP_CHUNK_STREAMS");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? std::min(v, kMaxBufs) : 4;
+    }();
+    static const bool ordered = getenv("UMGAP_CHUNK_ORDERED") != nullptr;
+    if (!idx->chunk_stream[0])
+        for (int i = 0; i < kMaxBufs; ++i) {
+            UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->chunk_stream[i], cudaStreamNonBlocking));
+            UMGAP_CUDA(cudaEventCreateWithFlags(&idx->chunk_done[i], cudaEventDisableTiming));
+        }
+    cudaStream_t* st = idx->chunk_stream;
+    cudaEvent_t* done = idx->chunk_done;
+    DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
+    UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
+    // nucleotides before group g (monotone in g): chunk ends are found by bisection
+    auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
+    uint64_t g0 = 0;
+    int buf = 0, prev = -1;
+    PinnedStage* stage = idx->host_stage;
+    try {
+        int chunk_no = 0;
+        while (g0 < ngroups) {
+            const uint64_t nt0 = nt_before(g0);
+            // the first chunks are short so that the kernels start early: 1/8, 1/4, 1/2 of a chunk, then full ones
+            const uint64_t limit = chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
+            ++chunk_no;
+            uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
+            while (lo < hi) {
+                const uint64_t mid = lo + (hi - lo + 1) / 2;
+                if (nt_before(mid) - nt0 <= limit) lo = mid; else hi = mid - 1;
+            }
+            const uint64_t g1 = lo;
+            const uint64_t r0 = group_off[g0], r1 = group_off[g1];
+            // packed chunks start at the 16-nucleotide word that holds their first nucleotide
+            const uint64_t shift = packed ? (nt0 & 15u) : 0;
+            const uint64_t cnt_nt = read_off[r1] - nt0 + shift, cnt_r = r1 - r0, cnt_g = g1 - g0;
+            const uint64_t cap_nt = std::max(cnt_nt, kChunkNt + 16);
+            uint64_t* d_roff = (uint64_t*)idx->ws.get(WS_ROFF + buf, (std::max<uint64_t>(cnt_r, kChunkNt / 32) + 1) * 8);
+            uint64_t* d_goff = (uint64_t*)idx->ws.get(WS_GOFF + buf, (std::max<uint64_t>(cnt_g, kChunkNt / 32) + 1) * 8);
+            uint32_t* d_out = (uint32_t*)idx->ws.get(WS_OUT + buf, std::max<uint64_t>(cnt_g, kChunkNt / 32) * 4 + 16);
+            // every stream has its own ids / scratch / hits / codes: the kernels of consecutive chunks are not
+            // ordered against each other, so one chunk's classify kernel and the next chunk's lookup kernel fill
+            // each other's tails (UMGAP_CHUNK_ORDERED=1 restores the strict order, for measurements)
+            uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS + buf, (2 * cap_nt + 64) * 4);
+            uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH + buf, (12 * cap_nt + 64) * 4);
+            cudaStream_t s = st[buf];
+            NtSrc nv;
+            uint64_t moved = 0;
+            if (!packed) {
+                uint8_t* d_nt = (uint8_t*)idx->ws.get(WS_NT + buf, cap_nt + 64);
+                UMGAP_CUDA(cudaMemcpyAsync(d_nt, hr.nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
+                moved = cnt_nt;
+                nv.bytes = d_nt;
+            } else {
+                // device layout of a packed chunk: the code words, then the N-flag words, then the sparse N entries
+                const uint64_t w0 = nt0 >> 4, nw = ceil_div(cnt_nt, 16), cap_w = cap_nt / 16 + 2;
+                uint8_t* base = (uint8_t*)idx->ws.get(WS_NT + buf, cap_w * 4 + cap_w * 2 + 64 + cap_w * 8);
+                uint32_t* d_codes = (uint32_t*)base;
+                uint16_t* d_nmask = (uint16_t*)(base + cap_w * 4);
+                uint64_t* d_entries = (uint64_t*)(base + ((cap_w * 6 + 63) & ~63ull));
+                UMGAP_CUDA(cudaMemcpyAsync(d_codes, hr.codes + w0, nw * 4, cudaMemcpyHostToDevice, s));
+                moved = nw * 4;
+                if (hr.nmask) {
+                    // words with an N are rare (0.1 % N: one word in 60): they travel as entries unless there are many
+                    uint64_t* e = stage[buf].get(nw / 4 + 1);
+                    uint64_t ne = 0;
+                    const uint16_t* m = hr.nmask + w0;
+                    for (uint64_t w = 0; w < nw && ne <= nw / 4; ++w)
+                        if (m[w]) e[ne++] = (w << 16) | m[w];
+                    if (ne <= nw / 4) {
+                        UMGAP_CUDA(cudaMemsetAsync(d_nmask, 0, nw * 2, s));
+                        if (ne) {
+                            UMGAP_CUDA(cudaMemcpyAsync(d_entries, e, ne * 8, cudaMemcpyHostToDevice, s));
+                            nmask_scatter_kernel<<<(unsigned)ceil_div(ne, 256), 256, 0, s>>>(d_nmask, d_entries, ne);
+                            UMGAP_CUDA(cudaGetLastError());
+                            ++g_launch_count;
+                        }
+                        if (!stage[buf].used) UMGAP_CUDA(cudaEventCreateWithFlags(&stage[buf].used, cudaEventDisableTiming));
+                        UMGAP_CUDA(cudaEventRecord(stage[buf].used, s));
+                        moved += ne * 8;
+                    } else {
+                        UMGAP_CUDA(cudaMemcpyAsync(d_nmask, m, nw * 2, cudaMemcpyHostToDevice, s));
+                        moved += nw * 2;
+                    }
+                } else {
+                    UMGAP_CUDA(cudaMemsetAsync(d_nmask, 0, nw * 2, s));
+                }
+                nv.codes = d_codes;
+                nv.nmask = d_nmask;
+            }
+            // offsets that form an arithmetic progression (the usual case: reads of one length, pairs) stay on the host
+            const uint64_t step_r = uniform_step(read_off + r0, cnt_r), step_g = uniform_step(group_off + g0, cnt_g);
+            if (!step_r) UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
+            if (!step_g) UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
+            g_h2d_bytes += moved + (step_r ? 0 : (cnt_r + 1) * 8) + (step_g ? 0 : (cnt_g + 1) * 8);
+            g_d2h_bytes += cnt_g * 4;
+            rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, step_r, shift, d_goff, cnt_g + 1, r0, step_g);
+            UMGAP_CUDA(cudaGetLastError());
+            ++g_launch_count;
+            if (ordered && prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
+            uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS + buf, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
+            launch_pipeline(idx, tax, opts, nv, d_roff, cnt_r, cnt_nt, d_goff, cnt_g, ids, scratch, hits, d_out, err, s, buf);
+            UMGAP_CUDA(cudaEventRecord(done[buf], s));
+            UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
+            prev = buf;
+            buf = (buf + 1) % kBufs;
+            g0 = g1;
+        }
+        for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
+        DevError he;
+        UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
+        raise_dev_error(he);
+    } catch (...) {
+        cudaDeviceSynchronize();
+        throw;
+    }
+}
+}  // extern "C++"
 
 int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
                          const umgap_pipeline_opts* opts, const uint8_t* nt, const uint64_t* read_off,
                          uint64_t nreads, const uint64_t* group_off, uint64_t ngroups,
                          uint32_t* taxon_out, uint64_t* n_lookups) {
     return guarded([&] {
-        check_opts(idx, tax, opts);
-        if (!tax) UMGAP_FAIL(UMGAP_ERR_INVALID, "null taxonomy");
-        if ((nreads && (!nt || !read_off)) || (ngroups && (!group_off || !taxon_out)))
-            UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
-        use_device(idx->device);
-        if (n_lookups) {
-            uint64_t c = 0;
-            const uint64_t span = 3ull * idx->k;
-            for (uint64_t r = 0; r < nreads; ++r) {
-                const uint64_t n = read_off[r + 1] - read_off[r];
-                if (n >= span) c += 2 * (n - span + 1);
-            }
-            *n_lookups = c;
-        }
-        if (!ngroups) return;
-        if (group_off[ngroups] != nreads || group_off[0] != 0)
-            UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off must cover reads 0..nreads");
-        // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
-        // nucleotides and offsets of the next chunks upload and the results of the previous one
-        // download.  Offsets are uploaded as given and rebased on the device.
-        static const uint64_t kChunkNt = [] {  // nucleotides per chunk (measured best of 6..96 MiB x 3..6 streams: profiles/r01_e2e_chunk_sweep.log; UMGAP_CHUNK_MB overrides)
-            const char* e = getenv("UMGAP_CHUNK_MB");
-            const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
-            return (mb ? mb : 16ull) << 20;
-        }();
-        static const int kBufs = [] {  // chunks in flight (streams); UMGAP_CHUNK_STREAMS overrides
-            const char* e = getenv("UMGAP_CHUNK_STREAMS");
-            const int v = e ? atoi(e) : 0;
-            return v > 0 ? std::min(v, kMaxBufs) : 4;
-        }();
-        static const bool ordered = getenv("UMGAP_CHUNK_ORDERED") != nullptr;
-        if (!idx->chunk_stream[0])
-            for (int i = 0; i < kMaxBufs; ++i) {
-                UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->chunk_stream[i], cudaStreamNonBlocking));
-                UMGAP_CUDA(cudaEventCreateWithFlags(&idx->chunk_done[i], cudaEventDisableTiming));
-            }
-        cudaStream_t* st = idx->chunk_stream;
-        cudaEvent_t* done = idx->chunk_done;
-        DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
-        UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
-        // nucleotides before group g (monotone in g): chunk ends are found by bisection
-        auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
-        uint64_t g0 = 0;
-        int buf = 0, prev = -1;
-        try {
-            int chunk_no = 0;
-            while (g0 < ngroups) {
-                const uint64_t nt0 = nt_before(g0);
-                // the first chunks are short so that the kernels start early: 1/8, 1/4, 1/2 of a chunk, then full ones
-                const uint64_t limit = chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
-                ++chunk_no;
-                uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
-                while (lo < hi) {
-                    const uint64_t mid = lo + (hi - lo + 1) / 2;
-                    if (nt_before(mid) - nt0 <= limit) lo = mid; else hi = mid - 1;
-                }
-                const uint64_t g1 = lo;
-                const uint64_t r0 = group_off[g0], r1 = group_off[g1];
-                const uint64_t cnt_nt = read_off[r1] - nt0, cnt_r = r1 - r0, cnt_g = g1 - g0;
-                const uint64_t cap_nt = std::max(cnt_nt, kChunkNt);
-                uint8_t* d_nt = (uint8_t*)idx->ws.get(WS_NT + buf, cap_nt + 64);
-                uint64_t* d_roff = (uint64_t*)idx->ws.get(WS_ROFF + buf, (std::max<uint64_t>(cnt_r, kChunkNt / 32) + 1) * 8);
-                uint64_t* d_goff = (uint64_t*)idx->ws.get(WS_GOFF + buf, (std::max<uint64_t>(cnt_g, kChunkNt / 32) + 1) * 8);
-                uint32_t* d_out = (uint32_t*)idx->ws.get(WS_OUT + buf, std::max<uint64_t>(cnt_g, kChunkNt / 32) * 4 + 16);
-                // every stream has its own ids / scratch / hits / codes: the kernels of consecutive chunks are not
-                // ordered against each other, so one chunk's classify kernel and the next chunk's lookup kernel fill
-                // each other's tails (UMGAP_CHUNK_ORDERED=1 restores the strict order, for measurements)
-                uint32_t* ids = (uint32_t*)idx->ws.get(WS_IDS + buf, (2 * cap_nt + 64) * 4);
-                uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH + buf, (12 * cap_nt + 64) * 4);
-                cudaStream_t s = st[buf];
-                UMGAP_CUDA(cudaMemcpyAsync(d_nt, nt + nt0, cnt_nt, cudaMemcpyHostToDevice, s));
-                // offsets that form an arithmetic progression (the usual case: reads of one length, pairs) stay on the host
-                const uint64_t step_r = uniform_step(read_off + r0, cnt_r), step_g = uniform_step(group_off + g0, cnt_g);
-                if (!step_r) UMGAP_CUDA(cudaMemcpyAsync(d_roff, read_off + r0, (cnt_r + 1) * 8, cudaMemcpyHostToDevice, s));
-                if (!step_g) UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off + g0, (cnt_g + 1) * 8, cudaMemcpyHostToDevice, s));
-                g_h2d_bytes += cnt_nt + (step_r ? 0 : (cnt_r + 1) * 8) + (step_g ? 0 : (cnt_g + 1) * 8);
-                g_d2h_bytes += cnt_g * 4;
-                rebase_kernel<<<148, 256, 0, s>>>(d_roff, cnt_r + 1, nt0, step_r, d_goff, cnt_g + 1, r0, step_g);
-                UMGAP_CUDA(cudaGetLastError());
-                ++g_launch_count;
-                if (ordered && prev >= 0) UMGAP_CUDA(cudaStreamWaitEvent(s, done[prev], 0));
-                uint8_t* hits = (uint8_t*)idx->ws.get(WS_HITS + buf, std::max<uint64_t>(cnt_r, kChunkNt / 16) + 64);
-                launch_pipeline(idx, tax, opts, d_nt, d_roff, cnt_r, cnt_nt, d_goff, cnt_g, ids, scratch, hits, d_out, err, s, buf);
-                UMGAP_CUDA(cudaEventRecord(done[buf], s));
-                UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_out, cnt_g * 4, cudaMemcpyDeviceToHost, s));
-                prev = buf;
-                buf = (buf + 1) % kBufs;
-                g0 = g1;
-            }
-            for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
-            DevError he;
-            UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
-            raise_dev_error(he);
-        } catch (...) {
-            cudaDeviceSynchronize();
-            throw;
-        }
+        HostReads hr;
+        hr.nt = nt;
+        classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
+    });
+}
+
+int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                                const uint32_t* codes, const uint16_t* nmask, const uint64_t* read_off, uint64_t nreads,
+                                const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+    return guarded([&] {
+        if (nreads && !codes) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        HostReads hr;
+        hr.codes = codes;
+        hr.nmask = nmask;
+        classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
     });
 }
 

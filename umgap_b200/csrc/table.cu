@@ -464,6 +464,8 @@ void umgap_index_free(umgap_index* idx) {
     for (int i = 0; i < 6; ++i) {
         if (idx->chunk_stream[i]) cudaStreamDestroy(idx->chunk_stream[i]);
         if (idx->chunk_done[i]) cudaEventDestroy(idx->chunk_done[i]);
+        if (idx->host_stage[i].used) cudaEventDestroy(idx->host_stage[i].used);
+        if (idx->host_stage[i].p) cudaFreeHost(idx->host_stage[i].p);
     }
     delete idx;
 }
