@@ -18,6 +18,7 @@
  * encoding is restated from the published format.  Parity of the byte
  * format with files written by the real crate is UNPINNED (see oracle/__init__.py).
  */
+#define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -729,4 +730,362 @@ uint32_t ref_translate(int table, int methionine, const uint8_t* nt, uint32_t n,
     for (int i = 0; i < 64; ++i) lut[i] = (methionine && starts[i] == 'M') ? 'M' : (uint8_t)aas[i];
     lut[64] = '-';
     return translate_frame(lut, nt, n, frame >= 3, (uint32_t)(frame % 3), out);
+}
+
+/* ------------------------------------------------------------------------------ peptide pipeline */
+/* prot2tryp2lca | uniq -d / | taxa2agg (the tryptic presets, scripts/umgap-analyse.sh:291-300).
+ * prot2tryp2lca.rs:105-134 per LINE: the default pattern ([KR])([^P]) applied twice and '*' -> newline is the
+ * closed form "a peptide ends after K/R unless the next residue is P (or the line ends), and at '*'"
+ * (oracle/lookup.py: tryptic_digest, checked against the two regex passes); empty pieces drop out (:119), the
+ * byte length must lie in minlen..maxlen (:120-123), optional keep / drop residue sets (:124-129), every survivor
+ * is one fst::Map::get over the whole peptide (:130); misses are omitted (no -o in the presets). */
+typedef struct {
+    int minlen, maxlen;
+    const char* keep;
+    const char* drop;
+    int strategy;
+    float factor, lower_bound;
+    int ranked_only;
+} RefTrypOpts;
+
+typedef struct {
+    const uint8_t* img; uint64_t img_size;
+    const RefTax* tax;
+    RefTrypOpts o;
+    const uint8_t* aa; const uint64_t* line_off; const uint64_t* group_off; uint64_t ngroups;
+    uint32_t* out;
+    uint64_t next; pthread_mutex_t* mu;
+    uint64_t lookups, hits;
+    int error; uint32_t bad;
+} PepJob;
+
+static int pep_passes_sets(const uint8_t* p, uint32_t n, const char* keep, const char* drop) {
+    if ((!keep || !*keep) && (!drop || !*drop)) return 1;
+    uint8_t seen[256];
+    memset(seen, 0, sizeof seen);
+    for (uint32_t i = 0; i < n; ++i) seen[p[i]] = 1;
+    if (keep) for (const char* c = keep; *c; ++c) if (!seen[(uint8_t)*c]) return 0;
+    if (drop) for (const char* c = drop; *c; ++c) if (seen[(uint8_t)*c]) return 0;
+    return 1;
+}
+
+static void* pep_worker(void* arg) {
+    PepJob* job = (PepJob*)arg;
+    const RefTrypOpts* o = &job->o;
+    AggScratch s;
+    memset(&s, 0, sizeof s);
+    s.nodes_cap = 256;
+    s.nodes = (TNode*)malloc(s.nodes_cap * sizeof(TNode));
+    uint32_t kept_cap = 1024, *kept = (uint32_t*)malloc(kept_cap * sizeof(uint32_t));
+    uint64_t lookups = 0, hits = 0;
+    const uint64_t chunk = 120; /* 240 records = 120 pairs x 2 peptide records */
+    for (;;) {
+        pthread_mutex_lock(job->mu);
+        const uint64_t g0 = job->next;
+        job->next += chunk;
+        pthread_mutex_unlock(job->mu);
+        if (g0 >= job->ngroups) break;
+        const uint64_t g1 = g0 + chunk < job->ngroups ? g0 + chunk : job->ngroups;
+        for (uint64_t g = g0; g < g1; ++g) {
+            uint32_t m = 0;
+            for (uint64_t l = job->group_off[g]; l < job->group_off[g + 1]; ++l) {
+                const uint8_t* line = job->aa + job->line_off[l];
+                const uint32_t n = (uint32_t)(job->line_off[l + 1] - job->line_off[l]);
+                uint32_t start = 0;
+                for (uint32_t i = 0; i <= n; ++i) {
+                    int cut = 0;
+                    uint32_t end = i;
+                    if (i == n) cut = 1;
+                    else if (line[i] == '*') cut = 1;
+                    else if ((line[i] == 'K' || line[i] == 'R') && i + 1 < n && line[i + 1] != 'P') { cut = 1; end = i + 1; }
+                    if (!cut) continue;
+                    const uint32_t len = end - start;
+                    if (len && (int)len >= o->minlen && (int)len <= o->maxlen && pep_passes_sets(line + start, len, o->keep, o->drop)) {
+                        uint64_t v;
+                        ++lookups;
+                        if (ref_fst_get(job->img, job->img_size, line + start, len, &v)) {
+                            if (m + 1 > kept_cap) { kept_cap *= 2; kept = (uint32_t*)realloc(kept, kept_cap * sizeof(uint32_t)); }
+                            kept[m++] = (uint32_t)v;
+                            ++hits;
+                        }
+                    }
+                    start = (i < n && line[i] == '*') ? i + 1 : end;
+                }
+            }
+            uint32_t res = 0xFFFFFFFFu; /* a group without lines has no record */
+            if (job->group_off[g + 1] > job->group_off[g]) {
+                uint32_t bad = 0;
+                res = aggregate_record(job->tax, &s, kept, m, o->strategy, o->factor, o->lower_bound, o->ranked_only, &bad);
+                if (res == 0xFFFFFFFEu) { job->error = 1; job->bad = bad; res = 0xFFFFFFFFu; }
+            }
+            job->out[g] = res;
+        }
+    }
+    pthread_mutex_lock(job->mu);
+    job->lookups += lookups;
+    job->hits += hits;
+    pthread_mutex_unlock(job->mu);
+    free(s.keys); free(s.vals); free(s.nodes); free(s.queue); free(kept);
+    return NULL;
+}
+
+int ref_classify_peptides(const uint8_t* img, uint64_t img_size, const void* tax, const RefTrypOpts* opts, const uint8_t* aa,
+                          const uint64_t* line_off, const uint64_t* group_off, uint64_t ngroups, uint32_t* out, int threads,
+                          uint64_t* n_lookups, uint64_t* n_hits, uint32_t* bad_taxon) {
+    PepJob job;
+    memset(&job, 0, sizeof job);
+    pthread_mutex_t mu;
+    pthread_mutex_init(&mu, NULL);
+    job.img = img; job.img_size = img_size; job.tax = (const RefTax*)tax; job.o = *opts;
+    job.aa = aa; job.line_off = line_off; job.group_off = group_off; job.ngroups = ngroups; job.out = out; job.mu = &mu;
+    if (threads < 1) threads = 1;
+    pthread_t* th = (pthread_t*)malloc(threads * sizeof(pthread_t));
+    for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, pep_worker, &job);
+    for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+    free(th);
+    pthread_mutex_destroy(&mu);
+    if (n_lookups) *n_lookups = job.lookups;
+    if (n_hits) *n_hits = job.hits;
+    if (job.error) { if (bad_taxon) *bad_taxon = job.bad; return -4; }
+    return 0;
+}
+
+/* ------------------------------------------------------------- the reference's process structure */
+/* scripts/umgap-analyse.sh:276-290 runs five processes connected by pipes: translate -a | prot2kmer2lca -o
+ * | seedextend | uniq -d / | taxa2agg.  Only the lookups are multi-threaded (rayon over 240-record chunks,
+ * prot2kmer2lca.rs:163-166); every stage parses FASTA text and prints FASTA text (io/fasta.rs:30-67,164-180).
+ * ref_pipeline_staged runs the same five stages one after the other over in-memory text, each as the
+ * reference structures it, and reports the seconds each took: as concurrent processes the pipeline moves at
+ * the pace of its slowest stage. */
+#include <stdio.h>
+#include <time.h>
+
+typedef struct { char* p; size_t n, cap; } Buf;
+static void buf_need(Buf* b, size_t extra) {
+    if (b->n + extra > b->cap) {
+        while (b->n + extra > b->cap) b->cap = b->cap ? b->cap * 2 : (1u << 20);
+        b->p = (char*)realloc(b->p, b->cap);
+    }
+}
+static void buf_put(Buf* b, const char* s, size_t n) { buf_need(b, n); memcpy(b->p + b->n, s, n); b->n += n; }
+static void buf_putc(Buf* b, char c) { buf_need(b, 1); b->p[b->n++] = c; }
+static void buf_put_u32(Buf* b, uint32_t v) {
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    buf_need(b, (size_t)n);
+    while (n) b->p[b->n++] = tmp[--n];
+}
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+/* one record of a FASTA stream: header [h, h+hn), item lines [body, body_end) (fasta.rs:38-67) */
+typedef struct { const char* h; size_t hn; const char* body; const char* body_end; } Rec;
+static const char* next_record(const char* p, const char* end, Rec* r) {
+    const char* e = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* hend = e ? e : end;
+    r->h = p + 1;
+    r->hn = (size_t)(hend - p - 1);
+    p = e ? e + 1 : end;
+    r->body = p;
+    while (p < end && *p != '>') {
+        const char* le = (const char*)memchr(p, '\n', (size_t)(end - p));
+        p = le ? le + 1 : end;
+    }
+    r->body_end = p;
+    return p;
+}
+
+typedef struct {
+    const uint8_t* img; uint64_t img_size; int k;
+    const Rec* recs; uint64_t nrecs; uint64_t next; pthread_mutex_t* mu;
+    Buf* outs; /* one per chunk, concatenated in order afterwards */
+    uint64_t lookups;
+} KJob;
+static void* k_worker(void* arg) {
+    KJob* j = (KJob*)arg;
+    uint64_t lookups = 0;
+    for (;;) {
+        pthread_mutex_lock(j->mu);
+        const uint64_t c = j->next++;
+        pthread_mutex_unlock(j->mu);
+        const uint64_t r0 = c * 240;
+        if (r0 >= j->nrecs) break;
+        const uint64_t r1 = r0 + 240 < j->nrecs ? r0 + 240 : j->nrecs;
+        Buf* o = &j->outs[c];
+        for (uint64_t r = r0; r < r1; ++r) {
+            const Rec* rc = &j->recs[r];
+            /* unwrap = true: the item lines concatenated; translate prints one line, so it is the line itself */
+            const char* s = rc->body;
+            size_t n = (size_t)(rc->body_end - rc->body);
+            while (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) --n;
+            if (n < (size_t)j->k) continue;                           /* :172 */
+            buf_putc(o, '>'); buf_put(o, rc->h, rc->hn); buf_putc(o, '\n');
+            for (size_t i = 0; i + (size_t)j->k <= n; ++i) {
+                uint64_t v = 0;
+                ++lookups;
+                if (!ref_fst_get(j->img, j->img_size, (const uint8_t*)s + i, (uint32_t)j->k, &v)) v = 0;   /* -o */
+                buf_put_u32(o, (uint32_t)v); buf_putc(o, '\n');
+            }
+        }
+    }
+    pthread_mutex_lock(j->mu);
+    j->lookups += lookups;
+    pthread_mutex_unlock(j->mu);
+    return NULL;
+}
+
+static uint32_t parse_ids(const Rec* r, uint32_t** ids, uint32_t* cap) {
+    uint32_t n = 0;
+    const char* p = r->body;
+    while (p < r->body_end) {
+        uint32_t v = 0;
+        while (p < r->body_end && *p >= '0' && *p <= '9') v = v * 10 + (uint32_t)(*p++ - '0');
+        while (p < r->body_end && (*p == '\n' || *p == '\r')) ++p;
+        if (n + 2 > *cap) { *cap = 2 * (*cap) + 64; *ids = (uint32_t*)realloc(*ids, *cap * sizeof(uint32_t)); }
+        (*ids)[n++] = v;
+    }
+    return n;
+}
+
+/* fasta: `>h1\nACGT...\n>h2\n...`; out_taxa receives one taxon per uniq group (as many as it has room for);
+ * stage_s[5] = seconds of translate, prot2kmer2lca, seedextend, uniq, taxa2agg.  Returns the number of groups,
+ * or a negative error. */
+int64_t ref_pipeline_staged(const uint8_t* img, uint64_t img_size, const void* taxp, const RefOpts* o, const char* fasta,
+                            uint64_t fasta_len, int threads, uint32_t* out_taxa, uint64_t out_cap, double* stage_s,
+                            uint64_t* n_lookups) {
+    const RefTax* tax = (const RefTax*)taxp;
+    const char* starts;
+    const char* aas = table_aas(o->table, &starts);
+    if (!aas) return -1;
+    uint8_t lut[65];
+    for (int i = 0; i < 64; ++i) lut[i] = (o->methionine && starts[i] == 'M') ? 'M' : (uint8_t)aas[i];
+    lut[64] = '-';
+    /* ---- translate -a (single thread) */
+    double t0 = now_s();
+    Buf tb = {0, 0, 0};
+    {
+        const char* p = fasta;
+        const char* end = fasta + fasta_len;
+        uint8_t* pep = (uint8_t*)malloc(1 << 16);
+        while (p < end) {
+            Rec r;
+            p = next_record(p, end, &r);
+            const char* s = r.body;
+            size_t n = (size_t)(r.body_end - r.body);
+            while (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) --n;
+            for (int fr = 0; fr < 6; ++fr) {
+                const uint32_t plen = translate_frame(lut, (const uint8_t*)s, (uint32_t)n, fr >= 3, (uint32_t)(fr % 3), pep);
+                buf_putc(&tb, '>'); buf_put(&tb, r.h, r.hn); buf_putc(&tb, '\n');
+                if (plen) { buf_put(&tb, (const char*)pep, plen); buf_putc(&tb, '\n'); }
+            }
+        }
+        free(pep);
+    }
+    stage_s[0] = now_s() - t0;
+    /* ---- prot2kmer2lca -o (reader single-threaded, 240-record chunks over `threads` threads, output in order) */
+    t0 = now_s();
+    Buf kb = {0, 0, 0};
+    {
+        uint64_t nrecs = 0, cap = 1 << 16;
+        Rec* recs = (Rec*)malloc(cap * sizeof(Rec));
+        const char* p = tb.p;
+        const char* end = tb.p + tb.n;
+        while (p < end) {
+            if (nrecs == cap) { cap *= 2; recs = (Rec*)realloc(recs, cap * sizeof(Rec)); }
+            p = next_record(p, end, &recs[nrecs++]);
+        }
+        const uint64_t nchunks = (nrecs + 239) / 240;
+        KJob job;
+        memset(&job, 0, sizeof job);
+        pthread_mutex_t mu;
+        pthread_mutex_init(&mu, NULL);
+        job.img = img; job.img_size = img_size; job.k = o->k; job.recs = recs; job.nrecs = nrecs; job.mu = &mu;
+        job.outs = (Buf*)calloc(nchunks ? nchunks : 1, sizeof(Buf));
+        if (threads < 1) threads = 1;
+        pthread_t* th = (pthread_t*)malloc((size_t)threads * sizeof(pthread_t));
+        for (int i = 0; i < threads; ++i) pthread_create(&th[i], NULL, k_worker, &job);
+        for (int i = 0; i < threads; ++i) pthread_join(th[i], NULL);
+        for (uint64_t c = 0; c < nchunks; ++c) { buf_put(&kb, job.outs[c].p, job.outs[c].n); free(job.outs[c].p); }
+        if (n_lookups) *n_lookups = job.lookups;
+        free(th); free(job.outs); free(recs);
+        pthread_mutex_destroy(&mu);
+    }
+    stage_s[1] = now_s() - t0;
+    free(tb.p);
+    /* ---- seedextend (single thread) */
+    t0 = now_s();
+    Buf sb = {0, 0, 0};
+    Buf* cur = &kb;
+    uint32_t idcap = 256, *ids = (uint32_t*)malloc(idcap * sizeof(uint32_t)), *sel = NULL, selcap = 0;
+    if (o->seedextend) {
+        const char* p = kb.p;
+        const char* end = kb.p + kb.n;
+        while (p < end) {
+            Rec r;
+            p = next_record(p, end, &r);
+            uint32_t n = parse_ids(&r, &ids, &idcap);
+            ids[n] = 0;
+            if (n + 2 > selcap) { selcap = 2 * n + 64; sel = (uint32_t*)realloc(sel, selcap * sizeof(uint32_t)); }
+            const uint32_t m = seedextend(ids, n + 1, (uint32_t)o->min_seed_size, (uint32_t)o->max_gap_size, sel, 0);
+            buf_putc(&sb, '>'); buf_put(&sb, r.h, r.hn); buf_putc(&sb, '\n');
+            for (uint32_t i = 0; i < m; ++i) { buf_put_u32(&sb, sel[i]); buf_putc(&sb, '\n'); }
+        }
+        cur = &sb;
+    }
+    stage_s[2] = now_s() - t0;
+    /* ---- uniq -d / (single thread) */
+    t0 = now_s();
+    Buf ub = {0, 0, 0};
+    {
+        const char* p = cur->p;
+        const char* end = cur->p + cur->n;
+        const char* last = NULL;
+        size_t lastn = 0;
+        while (p < end) {
+            Rec r;
+            p = next_record(p, end, &r);
+            const char* d = (const char*)memchr(r.h, '/', r.hn);
+            const size_t hn = d ? (size_t)(d - r.h) : r.hn;
+            if (!last || lastn != hn || memcmp(last, r.h, hn) != 0) {
+                buf_putc(&ub, '>'); buf_put(&ub, r.h, hn); buf_putc(&ub, '\n');
+                last = r.h;   /* points into cur, which outlives this loop */
+                lastn = hn;
+            }
+            buf_put(&ub, r.body, (size_t)(r.body_end - r.body));
+        }
+    }
+    stage_s[3] = now_s() - t0;
+    free(kb.p); free(sb.p);
+    /* ---- taxa2agg (single thread) */
+    t0 = now_s();
+    int64_t ngroups = 0;
+    int err = 0;
+    {
+        AggScratch s;
+        memset(&s, 0, sizeof s);
+        s.nodes_cap = 256;
+        s.nodes = (TNode*)malloc(s.nodes_cap * sizeof(TNode));
+        Buf ab = {0, 0, 0};
+        const char* p = ub.p;
+        const char* end = ub.p + ub.n;
+        while (p < end) {
+            Rec r;
+            p = next_record(p, end, &r);
+            const uint32_t n = parse_ids(&r, &ids, &idcap);
+            uint32_t bad = 0;
+            const uint32_t res = aggregate_record(tax, &s, ids, n, o->strategy, o->factor, o->lower_bound, o->ranked_only, &bad);
+            if (res == 0xFFFFFFFEu) { err = 1; break; }
+            buf_putc(&ab, '>'); buf_put(&ab, r.h, r.hn); buf_putc(&ab, '\n'); buf_put_u32(&ab, res); buf_putc(&ab, '\n');
+            if ((uint64_t)ngroups < out_cap) out_taxa[ngroups] = res;
+            ++ngroups;
+        }
+        free(ab.p);
+        free(s.keys); free(s.vals); free(s.nodes); free(s.queue);
+    }
+    stage_s[4] = now_s() - t0;
+    free(ub.p); free(ids); free(sel);
+    return err ? -4 : ngroups;
 }

@@ -131,3 +131,40 @@ def classify(img: FstImage, tax: RefTaxonomy, opts: RefOpts, nt: np.ndarray, rea
     if rc != 0:
         raise ValueError("Unknown table")
     return out[:ng], nl.value, nh.value
+
+
+class RefTrypOpts(C.Structure):
+    _fields_ = [("minlen", C.c_int), ("maxlen", C.c_int), ("keep", C.c_char_p), ("drop", C.c_char_p), ("strategy", C.c_int),
+                ("factor", C.c_float), ("lower_bound", C.c_float), ("ranked_only", C.c_int)]
+
+
+def classify_peptides(img: FstImage, tax: RefTaxonomy, opts: RefTrypOpts, aa: np.ndarray, line_off: np.ndarray,
+                      group_off: np.ndarray, threads: int = 1):
+    """prot2tryp2lca | uniq -d / | taxa2agg per group of peptide lines: (taxon per group, lookups, hits)."""
+    aa = np.ascontiguousarray(aa, dtype=np.uint8)
+    line_off = np.ascontiguousarray(line_off, dtype=np.uint64)
+    group_off = np.ascontiguousarray(group_off, dtype=np.uint64)
+    ng = len(group_off) - 1
+    out = np.zeros(max(ng, 1), dtype=np.uint32)
+    nl, nh, bad = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    rc = lib().ref_classify_peptides(_p(img.data), C.c_uint64(len(img.data)), tax._h, C.byref(opts), _p(aa), _p(line_off),
+                                     _p(group_off), C.c_uint64(ng), _p(out), C.c_int(threads), C.byref(nl), C.byref(nh),
+                                     C.byref(bad))
+    if rc == -4:
+        raise KeyError(f"Unknown Taxon ID: {bad.value}")
+    return out[:ng], nl.value, nh.value
+
+
+def pipeline_staged(img: FstImage, tax: RefTaxonomy, opts: RefOpts, fasta: bytes, threads: int = 1):
+    """The reference's five-process structure over in-memory text (ref_pipeline_staged): returns
+    (taxon per uniq group, seconds per stage [translate, prot2kmer2lca, seedextend, uniq, taxa2agg], lookups)."""
+    cap = fasta.count(b">") + 1
+    out = np.zeros(cap, dtype=np.uint32)
+    stage = (C.c_double * 5)()
+    nl = C.c_uint64()
+    lib().ref_pipeline_staged.restype = C.c_int64
+    n = lib().ref_pipeline_staged(_p(img.data), C.c_uint64(len(img.data)), tax._h, C.byref(opts), C.c_char_p(fasta),
+                                  C.c_uint64(len(fasta)), C.c_int(threads), _p(out), C.c_uint64(cap), stage, C.byref(nl))
+    if n < 0:
+        raise ValueError(f"ref_pipeline_staged failed: {n}")
+    return out[:n], [float(x) for x in stage], nl.value

@@ -136,3 +136,77 @@ def test_pipeline_matches_python_oracle(world):
             else:
                 assert int(got[gi]) == 0xFFFFFFFF
         assert nl == sum(2 * (len(r[1]) - 26) for r in reads if len(r[1]) >= 27) and nh > 0
+
+
+def test_peptide_pipeline_matches_python_oracle(world):
+    """ref_classify_peptides (the CPU baseline of the tryptic presets) against the oracle's text pipeline
+    prot2tryp2lca | uniq -d / | taxa2agg, with the digest's edge cases (KP, trailing K, '*', empty lines)."""
+    import random
+    rng = random.Random(91)
+    tryp = {}
+    ids = [t[0] for t in world["taxa"]]
+    for p in world["proteins"]:
+        for pep in olookup.tryptic_filter(olookup.tryptic_digest(p), 5, 50):
+            tryp.setdefault(pep.encode(), rng.choice(ids))
+    items = sorted(tryp.items())
+    img = cport.FstImage(cport.fst_build([k for k, _ in items], [v for _, v in items]))
+    lines, heads = [], []
+    for i, p in enumerate(world["proteins"][:50]):
+        a = rng.randrange(0, len(p) // 2)
+        for m, piece in enumerate((p[a:a + 70], p[a + 20:a + 110]), 1):
+            heads.append(f"g{i}/{m}")
+            lines.append(piece)
+    extra = ["", "K", "KP", "AAAAKPAAAAK", "*K*", "AAAAAK*RRRRRP", "PEPTIDEK" * 9]
+    for j, e in enumerate(extra):
+        heads.append(f"x{j}/1")
+        lines.append(e)
+    text = "".join(f">{h}\n{l}\n" if l else f">{h}\n" for h, l in zip(heads, lines))
+    # groups as uniq -d / forms them; a record without item lines contributes no line (fasta.rs:38-67)
+    keep_lines = list(zip(heads, lines))
+    ne_lines = [l for l in lines if l]
+    aa = np.frombuffer("".join(ne_lines).encode(), dtype=np.uint8)
+    off = np.zeros(len(ne_lines) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(l) for l in ne_lines])
+    group_names, goff, cnt = [], [0], 0
+    for h, l in keep_lines:
+        g = h.split("/")[0]
+        if not group_names or group_names[-1] != g:
+            if group_names:
+                goff.append(cnt)
+            group_names.append(g)
+        cnt += 1 if l else 0
+    goff.append(cnt)
+    goff = np.array(goff, dtype=np.uint64)
+    for minlen, maxlen, strategy, lb, keep, drop in [(5, 50, 2, 1.0, b"", b""), (9, 45, 2, 1.0, b"", b""), (9, 45, 2, 5.0, b"", b""),
+                                                     (5, 50, 1, 0.0, b"L", b"W"), (5, 50, 0, 0.0, b"", b"")]:
+        opts = cport.RefTrypOpts(minlen=minlen, maxlen=maxlen, keep=keep, drop=drop, strategy=strategy, factor=0.25,
+                                 lower_bound=lb, ranked_only=0)
+        got, nl, nh = cport.classify_peptides(img, world["ctax"], opts, aa, off, goff, threads=3)
+        t = opipe.prot2tryp2lca_text(text, olookup.DictIndex(tryp), False, minlen, maxlen, keep.decode(), drop.decode())
+        want = opipe.taxa2agg_sets(opipe.uniq_text(t, "/"), world["otax"], strategy, 0.25, lb)
+        assert [h for h, _ in want] == group_names
+        for gi, (h, adm) in enumerate(want):
+            if goff[gi + 1] == goff[gi]:
+                assert adm == {1}    # the reference prints the root for a record without peptides
+                continue
+            assert int(got[gi]) in adm, (h, int(got[gi]), adm)
+        assert nh > 20
+
+
+def test_staged_text_pipeline_matches_python_oracle(world):
+    """ref_pipeline_staged (the reference's five-process structure: text between the stages, only the lookups
+    multi-threaded -- the `reference_structure` CPU figure of bench.py) prints what the oracle's text pipeline prints."""
+    reads = datagen.make_reads(world["proteins"], 150, seed=45) + [("s0/1", "ACGT"), ("s0/2", "ACG" * 9), ("s1/1", "N" * 40)]
+    items = sorted(world["index"].items())
+    img = cport.FstImage(cport.fst_build([k for k, _ in items], [v for _, v in items]))
+    fa = "".join(f">{h}\n{s}\n" for h, s in reads).encode()
+    for strategy, s, g, lb in [(1, 3, 0, 0.0), (2, 2, 1, 1.0), (0, 3, 1, 2.0)]:
+        opts = cport.RefOpts(table=1, methionine=0, one_on_one=1, seedextend=1, min_seed_size=s, max_gap_size=g,
+                             strategy=strategy, factor=0.25, lower_bound=lb, ranked_only=0, k=9)
+        out, stage_s, nl = cport.pipeline_staged(img, world["ctax"], opts, fa, threads=3)
+        want = opipe.classify_reads(reads, olookup.DictIndex(world["index"]), world["otax"], min_seed_size=s, max_gap_size=g,
+                                    strategy=strategy, factor=0.25, lower_bound=lb)
+        assert len(out) == len(want) and len(stage_s) == 5
+        for (h, adm), o in zip(want, out):
+            assert int(o) in adm, (h, int(o), adm)
+        assert nl == sum(2 * (len(r[1]) - 26) for r in reads if len(r[1]) >= 27)
