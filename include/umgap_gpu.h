@@ -226,19 +226,22 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
                              const uint64_t* group_off_dev, uint64_t ngroups,
                              uint32_t* taxon_out_dev, void* stream);
 
-/* Packed host form of the reads: 2 bits per nucleotide plus one N flag, a quarter (N rare) to three eighths of
- * the bytes umgap_classify_reads moves over PCIe -- the form a FASTA parser can emit directly (the `umgap classify`
- * block parser does).  Nucleotide x of the concatenated reads sits at bits 2 (x % 16) of codes[x / 16] with
- * A, C, G, T = 0, 1, 2, 3; bit x % 16 of nmask[x / 16] is up when the byte was none of those four letters
- * (lower case included: N, dna/mod.rs:34-44).  Both arrays hold umgap_packed_words(total_nt) words; read_off stays
- * in nucleotides.  umgap_pack_reads fills them from the bytes on `threads` host threads (<= 0: all).  nmask may
- * be NULL when no read holds an N.  Results are those of umgap_classify_reads on the same reads.              */
+/* Packed host form of the reads: 2 bits per nucleotide plus a short list of the words that hold an N -- a quarter
+ * of the bytes umgap_classify_reads moves over PCIe, and a form a FASTA parser can emit directly.  Nucleotide x of
+ * the concatenated reads sits at bits 2 (x % 16) of codes[x / 16] with A, C, G, T = 0, 1, 2, 3
+ * (umgap_packed_words(total_nt) words).  Every 16-nucleotide word that holds a byte which is none of those four
+ * letters (lower case included: N, dna/mod.rs:34-44) has one entry in n_entries: word index << 16 | flags, bit
+ * x % 16 of flags up for each such nucleotide; the entries ascend by word index.  read_off stays in nucleotides.
+ * umgap_pack_reads fills both from the bytes on `threads` host threads (<= 0: all); it sets *n_count and fails with
+ * UMGAP_ERR_CAPACITY when n_entries (n_cap entries) is too small (umgap_packed_words(total_nt) always suffices).
+ * Results are those of umgap_classify_reads on the same reads.                                                  */
 uint64_t umgap_packed_words(uint64_t total_nt);
-int umgap_pack_reads(const uint8_t* nt, uint64_t total_nt, uint32_t* codes, uint16_t* nmask, int threads);
+int umgap_pack_reads(const uint8_t* nt, uint64_t total_nt, uint32_t* codes, uint64_t* n_entries, uint64_t n_cap,
+                     uint64_t* n_count, int threads);
 int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
-                                const uint32_t* codes, const uint16_t* nmask, const uint64_t* read_off,
-                                uint64_t nreads, const uint64_t* group_off, uint64_t ngroups,
-                                uint32_t* taxon_out, uint64_t* n_lookups);
+                                const uint32_t* codes, const uint64_t* n_entries, uint64_t n_count,
+                                const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
+                                uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups);
 
 /* Stage kernels on device-resident data, used by the benchmark to time the lookup kernel in
  * isolation: ids_dev receives 2*total_nt entries (position-major, both strands).           */

@@ -856,15 +856,15 @@ def test_sampled_lookup_ragged_batches(capi, world, s, g, strategy):
 
 
 def test_packed_reads_match_byte_form(capi, world, monkeypatch):
-    """umgap_classify_reads_packed (2-bit nucleotides + N flags, packed on the host by umgap_pack_reads) against
-    umgap_classify_reads and the oracle: ragged reads with N, lower case and other bytes, chunk seams that fall
-    inside a 16-nucleotide word (UMGAP_CHUNK_NT), the sampled and the every-position kernels, a read longer than
-    a sampled batch."""
+    """umgap_classify_reads_packed (2-bit nucleotides + the list of words holding an N, packed on the host by
+    umgap_pack_reads) against umgap_classify_reads and the oracle: ragged reads with N, lower case and other bytes,
+    chunk seams that fall inside a 16-nucleotide word (UMGAP_CHUNK_NT), the sampled and the every-position kernels,
+    a read longer than a sampled batch."""
     rng = random.Random(77)
     prots = world["proteins"]
     reads = []
     for L in (100, 149, 150, 151, 301):
-        reads += datagen.make_reads(prots, 40, seed=900 + L, read_len=L, hit_frac=0.8)
+        reads += [(f"L{L}{h}", sq) for h, sq in datagen.make_reads(prots, 40, seed=900 + L, read_len=L, hit_frac=0.8)]
     long_nt = "".join(rng.choice(datagen.CODONS.get(a, ["GCT"])) for p in prots[:5] for a in p)
     odd = _random_reads(rng, 40) + [long_nt[:1500]]
     for i, sq in enumerate(odd):
@@ -872,7 +872,8 @@ def test_packed_reads_match_byte_form(capi, world, monkeypatch):
     nt, off = capi.pack_strings([r[1].encode() for r in reads])
     heads = [h.split("/")[0] for h, _ in reads]
     goff = np.array([0] + [i for i in range(1, len(reads) + 1) if i == len(reads) or heads[i] != heads[i - 1]], dtype=np.uint64)
-    codes, nmask = capi.pack_reads(nt)
+    codes, entries = capi.pack_reads(nt)
+    assert len(entries) > 10 and np.all(np.diff(entries >> np.uint64(16)) > 0)
     oidx = olookup.DictIndex(world["index"])
     for chunk_nt in ("0", "777", "5000"):
         monkeypatch.setenv("UMGAP_CHUNK_NT", chunk_nt)
@@ -881,7 +882,7 @@ def test_packed_reads_match_byte_form(capi, world, monkeypatch):
                    dict(seedextend=0, one_on_one=0, strategy=capi.AGG_LCA_STAR)):
             opts = capi.default_opts(**kw)
             want, nl = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, goff)
-            got, nl2 = capi.classify_reads_packed(world["gidx"], world["gtax"], opts, codes, nmask, off, goff)
+            got, nl2 = capi.classify_reads_packed(world["gidx"], world["gtax"], opts, codes, entries, off, goff)
             assert nl == nl2
             assert np.array_equal(want, got), (chunk_nt, kw)
             if chunk_nt == "777" and kw["strategy"] == capi.AGG_LCA_STAR:
@@ -890,11 +891,11 @@ def test_packed_reads_match_byte_form(capi, world, monkeypatch):
                     h = heads[int(goff[k])]
                     assert (int(got[k]) in ref[h]) if h in ref else int(got[k]) == capi.ABSENT, h
     monkeypatch.delenv("UMGAP_CHUNK_NT")
-    # no N flags array: every byte is taken as one of A, C, G, T
+    # no N entries: every byte is one of A, C, G, T
     clean = np.frombuffer(bytes(nt).translate(bytes.maketrans(b"NacgtRY*", b"AACGTAAA")), dtype=np.uint8)
-    c2, m2 = capi.pack_reads(clean)
-    assert not m2[: (len(clean) + 15) // 16 - 1].any()
+    c2, e2 = capi.pack_reads(clean)
+    assert len(e2) == (1 if len(clean) % 16 else 0)   # only the padding of the last word
     opts = capi.default_opts(seedextend=1, min_seed_size=3)
     a, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, clean, off, goff)
-    b, _ = capi.classify_reads_packed(world["gidx"], world["gtax"], opts, c2, None if len(clean) % 16 == 0 else m2, off, goff)
+    b, _ = capi.classify_reads_packed(world["gidx"], world["gtax"], opts, c2, None, off, goff)
     assert np.array_equal(a, b)

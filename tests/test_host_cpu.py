@@ -272,3 +272,35 @@ def test_oracle_ranked_seedextend_and_rank_score_ladder():
     assert ose.seedextend_ranked(ids, tax, 2, 0, 9) == [4, 4, 4, 4]
     assert ose.seedextend_ranked(ids, tax, 2, 0, 10) == [4, 4, 4, 4]
     assert ose.seedextend_ranked([1, 2, 3], tax, 2, 0, 5) == []
+
+
+def test_pack_reads_host_packer():
+    """umgap_pack_reads (host only): 2-bit codes (A, C, G, T = 0..3) and one ascending entry per 16-nucleotide word
+    that holds any other byte -- lower case, N, IUPAC, NUL and 0xFF included (dna/mod.rs:34-44) -- plus the padding of
+    the last word; capacity errors."""
+    import numpy as np
+    from umgap_b200 import capi
+    rng = np.random.default_rng(0)
+    alphabet = np.frombuffer(b"ACGTNacgtRYKM*-\x00\xff", dtype=np.uint8)
+    p = np.array([0.2495] * 4 + [0.002 / (len(alphabet) - 4)] * (len(alphabet) - 4))
+    lut = np.full(256, 4, dtype=np.uint8)
+    for i, c in enumerate(b"ACGT"):
+        lut[c] = i
+    for n in (0, 1, 15, 16, 17, 1000, 100003, 2_100_000):
+        nt = alphabet[rng.choice(len(alphabet), size=n, p=p / p.sum())]
+        codes, ent = capi.pack_reads(nt, threads=3)
+        nw = (n + 15) // 16
+        pad = np.full(nw * 16, 4, dtype=np.uint8)
+        pad[:n] = lut[nt]
+        pad = pad.reshape(nw, 16)
+        want_mask = np.zeros(nw, dtype=np.uint64)
+        for j in range(16):
+            want_mask |= (pad[:, j] == 4).astype(np.uint64) << np.uint64(j)
+            ok = pad[:, j] != 4
+            assert np.array_equal(((codes[:nw].astype(np.uint64) >> np.uint64(2 * j)) & np.uint64(3))[ok], pad[:, j][ok].astype(np.uint64))
+        nzw = np.nonzero(want_mask)[0].astype(np.uint64)
+        assert np.array_equal(ent, (nzw << np.uint64(16)) | want_mask[nzw]), n
+    nt = np.frombuffer(b"ACGTN" * 100, dtype=np.uint8)
+    with pytest.raises(capi.UmgapError) as e:
+        capi.pack_reads(nt, entries=np.zeros(3, dtype=np.uint64))
+    assert e.value.code == -5   # UMGAP_ERR_CAPACITY

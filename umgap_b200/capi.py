@@ -428,23 +428,27 @@ def classify_reads(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarr
     return out[:ngroups], (nl.value if count_lookups else None)
 
 
-def pack_reads(nt: np.ndarray, threads: int = 0, pinned=None):
-    """umgap_pack_reads: nucleotide bytes -> (codes uint32[], nmask uint16[]), 16 nucleotides per word.  `pinned`:
-    optional (codes, nmask) arrays to fill (e.g. views of page-locked memory)."""
+def pack_reads(nt: np.ndarray, threads: int = 0, codes: Optional[np.ndarray] = None, entries: Optional[np.ndarray] = None):
+    """umgap_pack_reads: nucleotide bytes -> (codes uint32[words], N entries uint64[count]), 16 nucleotides per word.
+    `codes` / `entries`: optional arrays to fill (e.g. views of page-locked memory)."""
     lib = load_library()
     lib.umgap_packed_words.restype = C.c_uint64
     nt = _arr(nt, np.uint8)
     nw = int(lib.umgap_packed_words(C.c_uint64(len(nt))))
-    codes, nmask = pinned if pinned is not None else (np.zeros(max(nw, 1), dtype=np.uint32), np.zeros(max(nw, 1), dtype=np.uint16))
-    assert len(codes) >= nw and len(nmask) >= nw
-    _check(lib.umgap_pack_reads(_p(nt), C.c_uint64(len(nt)), _p(codes), _p(nmask), C.c_int(threads)))
-    return codes, nmask
+    if codes is None:
+        codes = np.zeros(max(nw, 1), dtype=np.uint32)
+    if entries is None:
+        entries = np.zeros(max(nw, 1), dtype=np.uint64)
+    assert len(codes) >= nw
+    n = C.c_uint64()
+    _check(lib.umgap_pack_reads(_p(nt), C.c_uint64(len(nt)), _p(codes), _p(entries), C.c_uint64(len(entries)), C.byref(n), C.c_int(threads)))
+    return codes, entries[: n.value]
 
 
-def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes: np.ndarray, nmask: Optional[np.ndarray],
+def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes: np.ndarray, entries: Optional[np.ndarray],
                           read_off: np.ndarray, group_off: np.ndarray, count_lookups: bool = True,
                           out: Optional[np.ndarray] = None):
-    """umgap_classify_reads_packed (host buffers, 2-bit nucleotides + N flags)."""
+    """umgap_classify_reads_packed (host buffers, 2-bit nucleotides + the list of words holding an N)."""
     lib = load_library()
     read_off = _arr(read_off, np.uint64)
     group_off = _arr(group_off, np.uint64)
@@ -452,9 +456,10 @@ def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes
     if out is None:
         out = np.zeros(max(ngroups, 1), dtype=np.uint32)
     nl = C.c_uint64()
-    _check(lib.umgap_classify_reads_packed(index._h, tax._h, C.byref(opts), _p(codes), _p(nmask), _p(read_off),
-                                           C.c_uint64(len(read_off) - 1), _p(group_off), C.c_uint64(ngroups), _p(out),
-                                           C.byref(nl) if count_lookups else None))
+    ne = 0 if entries is None else len(entries)
+    _check(lib.umgap_classify_reads_packed(index._h, tax._h, C.byref(opts), _p(codes), _p(entries) if ne else None, C.c_uint64(ne),
+                                           _p(read_off), C.c_uint64(len(read_off) - 1), _p(group_off), C.c_uint64(ngroups),
+                                           _p(out), C.byref(nl) if count_lookups else None))
     return out[:ngroups], (nl.value if count_lookups else None)
 
 

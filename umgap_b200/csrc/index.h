@@ -35,30 +35,12 @@ struct umgap_taxonomy {
     std::vector<void*> dev_allocs;
     // host copies (error reporting, synthetic generators, tests)
     std::vector<uint64_t> ids, parents;  // as given
+    std::vector<uint8_t> ranks, valids;  // as given (umgap_taxonomy_replicate)
     std::vector<uint32_t> h_dense_of, h_id_of, h_parent;
     std::vector<uint8_t> h_depth;
     uint64_t root = 0, max_id = 0;
     uint32_t max_depth = 0;
 };
-
-namespace umgap {
-// Pinned host staging of one chunk stream of the host-buffer path (grow-only, lives with the handle).
-struct PinnedStage {
-    uint64_t* p = nullptr;
-    size_t cap = 0;
-    cudaEvent_t used = nullptr;  // the last copy out of this buffer
-    uint64_t* get(size_t n) {
-        if (used) UMGAP_CUDA(cudaEventSynchronize(used));
-        if (n > cap) {
-            if (p) cudaFreeHost(p);
-            p = nullptr;
-            cap = n > (1u << 16) ? n : (1u << 16);
-            UMGAP_CUDA(cudaHostAlloc((void**)&p, cap * sizeof(uint64_t), cudaHostAllocDefault));
-        }
-        return p;
-    }
-};
-}  // namespace umgap
 
 struct umgap_index {
     int device = 0;
@@ -87,7 +69,6 @@ struct umgap_index {
     // streams + events of the chunked host-buffer path
     mutable cudaStream_t chunk_stream[6] = {};
     mutable cudaEvent_t chunk_done[6] = {};
-    mutable umgap::PinnedStage host_stage[6];
 
     umgap::TableView view() const {
         umgap::TableView v{};

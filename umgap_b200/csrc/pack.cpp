@@ -35,17 +35,20 @@ inline void pack16(const uint8_t* p, uint32_t& codes, uint16_t& flags) {
     flags = (uint16_t)f;
 }
 
-void pack_range(const uint8_t* nt, uint64_t total_nt, uint64_t w_begin, uint64_t w_end, uint32_t* codes, uint16_t* nmask) {
+void pack_range(const uint8_t* nt, uint64_t total_nt, uint64_t w_begin, uint64_t w_end, uint32_t* codes,
+                std::vector<uint64_t>* entries) {
     for (uint64_t w = w_begin; w < w_end; ++w) {
         const uint64_t x0 = 16 * w;
+        uint16_t flags;
         if (x0 + 16 <= total_nt) {
-            pack16(nt + x0, codes[w], nmask[w]);
+            pack16(nt + x0, codes[w], flags);
         } else {  // the last word: the positions past the end are N
             uint8_t tmp[16];
             memset(tmp, 'N', sizeof tmp);
             memcpy(tmp, nt + x0, total_nt - x0);
-            pack16(tmp, codes[w], nmask[w]);
+            pack16(tmp, codes[w], flags);
         }
+        if (flags) entries->push_back((w << 16) | flags);
     }
 }
 
@@ -55,20 +58,31 @@ extern "C" {
 
 uint64_t umgap_packed_words(uint64_t total_nt) { return (total_nt + 15) / 16; }
 
-int umgap_pack_reads(const uint8_t* nt, uint64_t total_nt, uint32_t* codes, uint16_t* nmask, int threads) {
+int umgap_pack_reads(const uint8_t* nt, uint64_t total_nt, uint32_t* codes, uint64_t* n_entries, uint64_t n_cap,
+                     uint64_t* n_count, int threads) {
     return umgap::guarded([&] {
-        if (total_nt && (!nt || !codes || !nmask)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if ((total_nt && (!nt || !codes)) || !n_count || (n_cap && !n_entries)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         const uint64_t nw = umgap_packed_words(total_nt);
         int t = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
         t = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(1, t), nw / (1u << 16) + 1));
+        std::vector<std::vector<uint64_t>> found((size_t)t);
         if (t == 1) {
-            pack_range(nt, total_nt, 0, nw, codes, nmask);
-            return;
+            pack_range(nt, total_nt, 0, nw, codes, &found[0]);
+        } else {
+            std::vector<std::thread> pool;
+            for (int i = 0; i < t; ++i)
+                pool.emplace_back(pack_range, nt, total_nt, nw * i / t, nw * (i + 1) / t, codes, &found[(size_t)i]);
+            for (std::thread& th : pool) th.join();
         }
-        std::vector<std::thread> pool;
-        for (int i = 0; i < t; ++i)
-            pool.emplace_back(pack_range, nt, total_nt, nw * i / t, nw * (i + 1) / t, codes, nmask);
-        for (std::thread& th : pool) th.join();
+        uint64_t n = 0;
+        for (const auto& f : found) n += f.size();
+        *n_count = n;
+        if (n > n_cap) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "%llu words hold an N, room for %llu", (unsigned long long)n, (unsigned long long)n_cap);
+        uint64_t at = 0;
+        for (const auto& f : found) {
+            if (!f.empty()) memcpy(n_entries + at, f.data(), f.size() * sizeof(uint64_t));
+            at += f.size();
+        }
     });
 }
 

@@ -1866,15 +1866,16 @@ int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
 extern "C++" {
 namespace {
 // N flags of a packed chunk that travel as (word index << 16 | flags) entries when few words hold an N.
-__global__ void nmask_scatter_kernel(uint16_t* nmask, const uint64_t* entries, uint64_t n) {
+__global__ void nmask_scatter_kernel(uint16_t* nmask, const uint64_t* entries, uint64_t n, uint64_t first_word) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) nmask[entries[i] >> 16] = (uint16_t)(entries[i] & 0xFFFFu);
+    if (i < n) nmask[(entries[i] >> 16) - first_word] = (uint16_t)(entries[i] & 0xFFFFu);
 }
 
 struct HostReads {  // one of the two host forms of a batch's nucleotides
     const uint8_t* nt = nullptr;       // bytes as received
     const uint32_t* codes = nullptr;   // packed: 2 bits per nucleotide ...
-    const uint16_t* nmask = nullptr;   // ... and one N flag each (NULL: no N anywhere)
+    const uint64_t* n_entries = nullptr;  // ... and the words that hold an N: word index << 16 | flags, ascending
+    uint64_t n_count = 0;
 };
 
 }  // namespace
@@ -1931,7 +1932,6 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
     auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
     uint64_t g0 = 0;
     int buf = 0, prev = -1;
-    PinnedStage* stage = idx->host_stage;
     try {
         int chunk_no = 0;
         while (g0 < ngroups) {
@@ -1975,30 +1975,18 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
                 uint64_t* d_entries = (uint64_t*)(base + ((cap_w * 6 + 63) & ~63ull));
                 UMGAP_CUDA(cudaMemcpyAsync(d_codes, hr.codes + w0, nw * 4, cudaMemcpyHostToDevice, s));
                 moved = nw * 4;
-                if (hr.nmask) {
-                    // words with an N are rare (0.1 % N: one word in 60): they travel as entries unless there are many
-                    uint64_t* e = stage[buf].get(nw / 4 + 1);
-                    uint64_t ne = 0;
-                    const uint16_t* m = hr.nmask + w0;
-                    for (uint64_t w = 0; w < nw && ne <= nw / 4; ++w)
-                        if (m[w]) e[ne++] = (w << 16) | m[w];
-                    if (ne <= nw / 4) {
-                        UMGAP_CUDA(cudaMemsetAsync(d_nmask, 0, nw * 2, s));
-                        if (ne) {
-                            UMGAP_CUDA(cudaMemcpyAsync(d_entries, e, ne * 8, cudaMemcpyHostToDevice, s));
-                            nmask_scatter_kernel<<<(unsigned)ceil_div(ne, 256), 256, 0, s>>>(d_nmask, d_entries, ne);
-                            UMGAP_CUDA(cudaGetLastError());
-                            ++g_launch_count;
-                        }
-                        if (!stage[buf].used) UMGAP_CUDA(cudaEventCreateWithFlags(&stage[buf].used, cudaEventDisableTiming));
-                        UMGAP_CUDA(cudaEventRecord(stage[buf].used, s));
-                        moved += ne * 8;
-                    } else {
-                        UMGAP_CUDA(cudaMemcpyAsync(d_nmask, m, nw * 2, cudaMemcpyHostToDevice, s));
-                        moved += nw * 2;
-                    }
-                } else {
-                    UMGAP_CUDA(cudaMemsetAsync(d_nmask, 0, nw * 2, s));
+                UMGAP_CUDA(cudaMemsetAsync(d_nmask, 0, nw * 2, s));
+                // the chunk's share of the N entries (ascending word index): found by bisection, uploaded as they are
+                const uint64_t* e_lo = std::lower_bound(hr.n_entries, hr.n_entries + hr.n_count, w0 << 16);
+                const uint64_t* e_hi = std::lower_bound(e_lo, hr.n_entries + hr.n_count, (w0 + nw) << 16);
+                const uint64_t ne = (uint64_t)(e_hi - e_lo);
+                if (ne > cap_w) UMGAP_FAIL(UMGAP_ERR_INVALID, "N entries are not strictly ascending by word index");
+                if (ne) {
+                    UMGAP_CUDA(cudaMemcpyAsync(d_entries, e_lo, ne * 8, cudaMemcpyHostToDevice, s));
+                    nmask_scatter_kernel<<<(unsigned)ceil_div(ne, 256), 256, 0, s>>>(d_nmask, d_entries, ne, w0);
+                    UMGAP_CUDA(cudaGetLastError());
+                    ++g_launch_count;
+                    moved += ne * 8;
                 }
                 nv.codes = d_codes;
                 nv.nmask = d_nmask;
@@ -2044,13 +2032,15 @@ int umgap_classify_reads(const umgap_index* idx, const umgap_taxonomy* tax,
 }
 
 int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
-                                const uint32_t* codes, const uint16_t* nmask, const uint64_t* read_off, uint64_t nreads,
-                                const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+                                const uint32_t* codes, const uint64_t* n_entries, uint64_t n_count, const uint64_t* read_off,
+                                uint64_t nreads, const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out,
+                                uint64_t* n_lookups) {
     return guarded([&] {
-        if (nreads && !codes) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if ((nreads && !codes) || (n_count && !n_entries)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         HostReads hr;
         hr.codes = codes;
-        hr.nmask = nmask;
+        hr.n_entries = n_entries;
+        hr.n_count = n_count;
         classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
     });
 }

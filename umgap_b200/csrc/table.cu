@@ -464,10 +464,44 @@ void umgap_index_free(umgap_index* idx) {
     for (int i = 0; i < 6; ++i) {
         if (idx->chunk_stream[i]) cudaStreamDestroy(idx->chunk_stream[i]);
         if (idx->chunk_done[i]) cudaEventDestroy(idx->chunk_done[i]);
-        if (idx->host_stage[i].used) cudaEventDestroy(idx->host_stage[i].used);
-        if (idx->host_stage[i].p) cudaFreeHost(idx->host_stage[i].p);
     }
     delete idx;
+}
+
+// A replica of a fixed-length table on another device (multi-GPU mode 1: index replicated, reads partitioned):
+// the levels are copied device to device (NVLink when the GPUs are peers) instead of streaming the file again.
+int umgap_index_replicate(const umgap_index* src, int device, umgap_index** out) {
+    umgap_index* idx = nullptr;
+    int rc = guarded([&] {
+        if (!src || !out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (src->k <= 0 || src->var_table) UMGAP_FAIL(UMGAP_ERR_INVALID, "only fixed-length k-mer tables can be replicated");
+        if (src->nshards > 1) UMGAP_FAIL(UMGAP_ERR_INVALID, "a shard of a key-range-sharded index cannot be replicated");
+        use_device(device);
+        idx = new umgap_index();
+        idx->device = device;
+        idx->k = src->k;
+        idx->nlevels = src->nlevels;
+        memcpy(idx->code_of_byte, src->code_of_byte, sizeof idx->code_of_byte);
+        idx->alphabet_size = src->alphabet_size;
+        idx->n_keys = src->n_keys;
+        idx->n_skipped = src->n_skipped;
+        idx->n_flagged = src->n_flagged;
+        idx->n_displaced = src->n_displaced;
+        idx->max_probe = src->max_probe;
+        idx->bytes = src->bytes;
+        idx->load_factor = src->load_factor;
+        idx->region_bytes = src->region_bytes;
+        for (int i = 0; i < src->nlevels; ++i) {
+            const size_t bytes = (size_t)src->level_nlines[i] * 128;
+            idx->level_nlines[i] = src->level_nlines[i];
+            UMGAP_CUDA(cudaMalloc((void**)&idx->level_dev[i], bytes));
+            UMGAP_CUDA(cudaMemcpyPeer(idx->level_dev[i], device, src->level_dev[i], src->device, bytes));
+        }
+        UMGAP_CUDA(cudaDeviceSynchronize());
+        *out = idx;
+    });
+    if (rc != UMGAP_OK && idx) umgap_index_free(idx);
+    return rc;
 }
 
 int umgap_index_get_info(const umgap_index* idx, umgap_index_info* info) {

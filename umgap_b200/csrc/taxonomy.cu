@@ -150,6 +150,8 @@ static void build(umgap_taxonomy* tax, const std::vector<uint64_t>& ids,
 
     tax->ids = ids;
     tax->parents = parents;
+    tax->ranks = rank;
+    tax->valids = valid;
     tax->root = root;
     tax->max_id = max_id;
     tax->max_depth = max_depth;
@@ -193,6 +195,15 @@ int umgap_taxonomy_from_arrays(const uint64_t* ids, const uint64_t* parents, con
     });
     if (rc != UMGAP_OK && tax) umgap_taxonomy_free(tax);
     return rc;
+}
+
+int umgap_taxonomy_replicate(const umgap_taxonomy* src, int device, umgap_taxonomy** out) {
+    if (!src || !out) {
+        set_error("null argument");
+        return UMGAP_ERR_INVALID;
+    }
+    return umgap_taxonomy_from_arrays(src->ids.data(), src->parents.data(), src->ranks.data(), src->valids.data(),
+                                      src->ids.size(), device, out);
 }
 
 int umgap_taxonomy_load(const char* tsv_path, int device, umgap_taxonomy** out) {
