@@ -60,7 +60,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=1_000_000)
     ap.add_argument("--index-keys", type=float, default=1e9, help="synthetic index size (9-mer windows)")
-    ap.add_argument("--cpu-index-keys", type=float, default=2e7, help="index size of the host-resident CPU legs")
+    ap.add_argument("--cpu-index-keys", type=float, default=1e8, help="index size of the host-resident CPU legs")
+    ap.add_argument("--legs", default="all", help="extra legs after the headline: all | none | comma list of every_position,parity,sharded,large_index,tryptic,loader")
+    ap.add_argument("--large-index-keys", type=float, default=6.12e9, help="windows of the large-index leg (6.12e9 -> a 100 GB table)")
     ap.add_argument("--load-factor", type=float, default=0.0, help="table load factor (0 = library default policy)")
     ap.add_argument("--sharded", action="store_true", help="key-range-shard the index over the GPUs (peer-memory lookups) instead of replicating it")
     ap.add_argument("--peer-loads", action="store_true", help="with --sharded: read remote shards through IPC peer mappings instead of the all-to-all exchange")
@@ -93,64 +95,90 @@ def pipeline_config(args, extra=None):
 
 # ----------------------------------------------------------------------------------------- CPU legs
 
-def cpu_instance(n_keys: float):
-    """Host-resident instance of the same generator: taxonomy, fst image, and a reads() closure."""
+def cpu_instance(n_keys: float, threads: int):
+    """Host-resident instance of the same generator (oracle/c mirror of the device generator): taxonomy, fst image
+    of the proteome's 9-mer index, and a reads() closure."""
     import datagen
     from oracle import cport, synth
     taxa = datagen.make_taxonomy(N_TAXA, seed=1)
     pre = synth.Preorder(taxa)
     n_prot = max(1, int(n_keys // (PROTEIN_LEN - 8)))
-    keys, vals = synth.build_index(2, n_prot, PROTEIN_LEN, 70, 20, pre)
-    img = cport.FstImage(cport.fst_build_blob(keys.reshape(-1), np.arange(0, 9 * len(keys) + 1, 9, dtype=np.uint64), vals))
+    t0 = time.perf_counter()
+    data, nkeys = cport.synth_fst(2, n_prot, PROTEIN_LEN, 70, 20, pre, threads=threads)
+    build_s = time.perf_counter() - t0
+    img = cport.FstImage(data)
     ctax = cport.RefTaxonomy(taxa)
     opts = cport.RefOpts(table=1, methionine=0, one_on_one=1, seedextend=1, min_seed_size=3, max_gap_size=0,
                          strategy=1, factor=0.25, lower_bound=0.0, ranked_only=0, k=K)
 
     def reads(first_pair: int, npairs: int):
-        parts = [synth.reads(2, n_prot, PROTEIN_LEN, 3, first_pair + c, min(50_000, npairs - c), READ_LEN, HIT_PCT)
-                 for c in range(0, npairs, 50_000)]
-        nt = np.concatenate(parts).reshape(-1)
+        nt = cport.synth_reads(2, n_prot, PROTEIN_LEN, 3, first_pair, npairs, READ_LEN, HIT_PCT, threads=threads).reshape(-1)
         off = np.arange(0, len(nt) + 1, READ_LEN, dtype=np.uint64)
         goff = np.arange(0, 2 * npairs + 1, 2, dtype=np.uint64)
         return nt, off, goff
 
-    return dict(img=img, tax=ctax, opts=opts, reads=reads, n_keys=len(keys), fst_bytes=len(img.data))
+    return dict(img=img, tax=ctax, taxa=taxa, opts=opts, reads=reads, n_keys=int(nkeys), n_prot=n_prot, fst_bytes=len(img.data),
+                fst_build_s=build_s, raw=data)
 
 
-def cpu_run(inst, first_pair: int, npairs: int, threads: int):
+def cpu_run(inst, first_pair: int, npairs: int, threads: int, lookups_only: bool = False):
     from oracle import cport
     nt, off, goff = inst["reads"](first_pair, npairs)
     t0 = time.perf_counter()
-    out, nl, nh = cport.classify(inst["img"], inst["tax"], inst["opts"], nt, off, goff, threads=threads)
+    out, nl, nh = cport.classify(inst["img"], inst["tax"], inst["opts"], nt, off, goff, threads=threads, lookups_only=lookups_only)
     dt = time.perf_counter() - t0
     return dt, nl, out
 
 
-def cpu_baseline(args, budget_s: float = 12.0):
+def cpu_staged(inst, first_pair: int, npairs: int, threads: int):
+    """The reference's own structure (scripts/umgap-analyse.sh:276-311): five stages with FASTA text between them, only
+    prot2kmer2lca multi-threaded (prot2kmer2lca.rs:163-166).  The stages run one after another here; as concurrent
+    processes the pipe's rate is that of its slowest stage."""
+    from oracle import cport
+    nt, off, _ = inst["reads"](first_pair, npairs)
+    rows = nt.reshape(-1, READ_LEN)
+    fa = b"".join(b">r%d/%d\n%s\n" % (first_pair + i // 2, 1 + (i & 1), rows[i].tobytes()) for i in range(len(rows)))
+    out, stage_s, nl = cport.pipeline_staged(inst["img"], inst["tax"], inst["opts"], fa, threads=threads)
+    names = ("translate", "prot2kmer2lca", "seedextend", "uniq", "taxa2agg")
+    nreads = 2 * npairs
+    return {"reads_per_second_stages_in_sequence": nreads / sum(stage_s),
+            "reads_per_second_as_concurrent_pipe": nreads / max(stage_s),
+            "stage_seconds": {n: round(s, 4) for n, s in zip(names, stage_s)}, "pairs": npairs,
+            "what": "ref_pipeline_staged: FASTA text between the stages, prot2kmer2lca on all threads in 240-record chunks, "
+                    "every other stage single-threaded (the reference's process structure)"}
+
+
+def cpu_baseline(args, inst=None, budget_s: float = 12.0):
     threads = os.cpu_count() or 1
-    inst = cpu_instance(args.cpu_index_keys)
+    inst = inst or cpu_instance(args.cpu_index_keys, threads)
     dt, _, _ = cpu_run(inst, 0, 2000, threads)  # calibration, also warms the image
     npairs = int(min(400_000, max(2000, 2000 * budget_s / max(dt, 1e-4))))
     dt, nl, _ = cpu_run(inst, 10_000_000, npairs, threads)
+    dl, nll, _ = cpu_run(inst, 10_000_000, npairs, threads, lookups_only=True)
+    staged = cpu_staged(inst, 11_000_000, max(1000, npairs // 10), threads)
     return {
         "value": 2 * npairs / dt,
         "unit": UNIT,
         "lookups_per_second": nl / dt,
+        "lookup_stage_alone_lookups_per_second": nll / dl,
         "cores": threads,
         "kind": "port",
         "sample": f"{npairs} pairs of the same generator against a host-resident fst image of {inst['n_keys']} keys "
-                  f"({inst['fst_bytes'] / 1e6:.0f} MB; the 1e9-key index is built on the device only), whole pipeline "
-                  f"chunk-parallel over {threads} threads, {dt:.1f} s",
+                  f"({inst['fst_bytes'] / 1e6:.0f} MB, built in {inst['fst_build_s']:.0f} s; the 1e9-key index is built on the device only), "
+                  f"whole pipeline chunk-parallel over {threads} threads (best-effort CPU: more parallel than the reference's "
+                  f"process pipeline, no text between the stages), {dt:.1f} s",
+        "reference_structure": staged,
     }
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference pipeline on every host thread."""
+    """Reference arm: the CPU restatement of the reference pipeline on every host thread, on our arm's config; each
+    step is a bounded sample of the step's 1 M pairs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    inst = cpu_instance(args.cpu_index_keys)
+    inst = cpu_instance(args.cpu_index_keys, threads)
     dt, _, _ = cpu_run(inst, 0, 2000, threads)
     # bounded sample per step: the whole run (warmup + steps) stays around a minute
     per_step = int(min(args.pairs_per_step, 100_000, max(1000, 2000 * (60.0 / max(1, args.steps + args.warmup)) / max(dt, 1e-4))))
@@ -162,16 +190,18 @@ def run_reference(args):
         total_t += dt
         total_l += nl
     value = 2 * per_step * args.steps / total_t
-    sample = (f"{per_step} pairs per step against a host-resident fst image of {inst['n_keys']} keys "
-              f"({inst['fst_bytes'] / 1e6:.0f} MB), {threads} threads")
+    staged = cpu_staged(inst, 30_000_000, max(1000, per_step // 10), threads)
+    sample = (f"{per_step} pairs per step (a bounded sample of the step's {args.pairs_per_step} pairs) against a host-resident fst image of "
+              f"{inst['n_keys']} keys ({inst['fst_bytes'] / 1e6:.0f} MB; the arm's 1e9-key index lives on the device only), {threads} threads; "
+              "C restatement of the reference algorithm (the Rust binary cannot be built here: no cargo/rustc), whole chain chunk-parallel")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
         "lookups_per_second": total_l / total_t,
-        "config": pipeline_config(args, {"pairs_per_step": per_step, "note": "C restatement of the reference algorithm "
-                                         "(the Rust binary cannot be built here: no cargo/rustc); " + sample}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": pipeline_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "pairs_per_step_sampled": per_step, "index_keys": inst["n_keys"], "reference_structure": staged},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,6 +262,347 @@ class ClockSampler:
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
+
+
+# --------------------------------------------------------------------------------------------- legs
+# Extra measurements after the headline (BASELINE.json configs[2..4], the every-position kernel, parity checks); each
+# returns a dict for the JSON line.  A leg that fails reports {"error": ...} instead of taking the headline down.
+
+class Ctx:
+    pass
+
+
+def timed_steps(ctx, fn, steps, warmup=2):
+    """CUDA events on the current stream around `steps` calls of fn(i), max over ranks; lookup / classify brackets."""
+    torch, capi = ctx.torch, ctx.capi
+    for w in range(warmup):
+        fn(w)
+    ctx.barrier()
+    capi.kernel_timing(True)
+    capi.kernel_times()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    lookup_ms, lookup_n, classify_ms, _ = capi.kernel_times()
+    capi.kernel_timing(False)
+    if ctx.world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=ctx.dev)
+        ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, lookup_ms / steps, classify_ms / steps
+
+
+def all_ranks_true(ctx, ok: bool) -> bool:
+    if ctx.world == 1:
+        return bool(ok)
+    t = ctx.torch.tensor([1 if ok else 0], dtype=ctx.torch.int32, device=ctx.dev)
+    ctx.dist.all_reduce(t, op=ctx.dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def leg_every_position(ctx, gidx, peak):
+    """The plain kernel (translate_lookup_kernel: every k-mer position probed, the path of configs[0], of pipelines
+    without seedextend / -o, and of k != 9) on the headline workload: umgap_pipeline_sampling(0)."""
+    capi = ctx.capi
+    before = capi.pipeline_sampling(0)
+    try:
+        steps = max(3, min(5, ctx.args.steps))
+        step_ms, lookup_ms, classify_ms = timed_steps(
+            ctx, lambda i: capi.classify_reads_dev(gidx, ctx.gtax, ctx.opts, ctx.batches[i % len(ctx.batches)].data_ptr(), ctx.roff.data_ptr(),
+                                                   ctx.nreads, ctx.total_nt, ctx.goff.data_ptr(), ctx.B, ctx.out_b.data_ptr(), ctx.stream), steps)
+    finally:
+        capi.pipeline_sampling(before)
+    alg = ctx.nreads * LOOKUPS_PER_READ * BYTES_PER_LOOKUP
+    return {"value": ctx.world * ctx.nreads / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+            "lookup_stage_ms": lookup_ms, "classify_ms": classify_ms,
+            "roofline_frac": alg / (lookup_ms * 1e-3) / 1e9 / peak, "lookups_per_second_kernel": ctx.nreads * LOOKUPS_PER_READ / (lookup_ms * 1e-3),
+            "kernel": "translate_lookup_kernel<9,TableView> (all 248 positions of a read probed)"}
+
+
+def leg_parity_device(ctx, gidx):
+    """Bit-equality on batch 0 of every rank: the sampled lookups against every position probed (seedextend sees the
+    same extended seeds), and the packed host form against the device-resident form."""
+    capi, torch = ctx.capi, ctx.torch
+    def run():
+        capi.classify_reads_dev(gidx, ctx.gtax, ctx.opts, ctx.batches[0].data_ptr(), ctx.roff.data_ptr(), ctx.nreads, ctx.total_nt,
+                                ctx.goff.data_ptr(), ctx.B, ctx.out_b.data_ptr(), ctx.stream)
+        torch.cuda.synchronize()
+        return ctx.out_b.clone()
+    sampled = run()
+    before = capi.pipeline_sampling(0)
+    try:
+        plain = run()
+    finally:
+        capi.pipeline_sampling(before)
+    ctx.replicated_out0 = sampled
+    return {"sampled_equals_every_position": all_ranks_true(ctx, bool(torch.equal(sampled, plain))),
+            "groups_compared_per_rank": int(ctx.B)}
+
+
+def leg_sharded(ctx, gidx_repl):
+    """BASELINE configs[4]: the index key-range-sharded over the GPUs, lookups routed to their owners (the exchange
+    step), on the headline workload; results compared with the replicated table's on every rank."""
+    capi, torch, dist = ctx.capi, ctx.torch, ctx.dist
+    from umgap_b200 import sharded
+    args = ctx.args
+    t0 = time.perf_counter()
+    sidx = capi.Index.build_synthetic(ctx.spec, ctx.gtax, device=ctx.local, load_factor=args.load_factor, shard=ctx.rank, nshards=ctx.world)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    routed = sharded.RoutedClassifier(sidx, ctx.gtax, dist, ctx.total_nt, lanes=args.routed_lanes)
+    def step(i):
+        routed.classify(ctx.opts, ctx.batches[i % len(ctx.batches)], ctx.roff, ctx.goff, ctx.out_b, ctx.total_nt)
+    step(0)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(ctx.out_b, ctx.replicated_out0)) if getattr(ctx, "replicated_out0", None) is not None else None
+    overflow = routed.overflowed()
+    steps = max(3, min(5, args.steps))
+    step_ms, lookup_ms, classify_ms = timed_steps(ctx, step, steps)
+    routed.profile = True
+    routed.stage_ms = {}
+    for i in range(2):
+        step(i)
+    routed.profile = False
+    stages = {k: round(v / 2, 3) for k, v in routed.stage_ms.items()}
+    res = {"value": ctx.world * ctx.nreads / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+           "local_shard_lookup_ms": lookup_ms, "classify_ms": classify_ms, "routed_stages_ms_per_step": stages,
+           "lookups_routed_per_step_per_rank": routed.lookups_routed, "bucket_overflow": bool(overflow),
+           "shard_build_s": build_s, "shard_bytes": int(sidx.info().bytes),
+           "equals_replicated": None if same is None else all_ranks_true(ctx, same and not overflow),
+           "what": "index key-range-sharded over the GPUs; two exchange rounds per batch (sampled positions, then the live frames)"}
+    del routed
+    sidx.close()
+    return res
+
+
+def leg_large_index(ctx, peak):
+    """BASELINE configs[3]: a ~100 GB table replicated per GPU, reads partitioned (every rank classifies its own batches)."""
+    capi, torch = ctx.capi, ctx.torch
+    args = ctx.args
+    n_prot = max(1, int(args.large_index_keys // (PROTEIN_LEN - 8)))
+    spec = capi.SynthSpec(seed=2, n_proteins=n_prot, protein_len=PROTEIN_LEN, home_pct=70, ancestor_pct=20)
+    free_b, _ = torch.cuda.mem_get_info()
+    need = int(args.large_index_keys * 16.6) + 24 * ctx.total_nt * 4
+    if free_b < need:
+        return {"skipped": f"needs ~{need / 1e9:.0f} GB of free HBM, {free_b / 1e9:.0f} GB free"}
+    t0 = time.perf_counter()
+    big = capi.Index.build_synthetic(spec, ctx.gtax, device=ctx.local, load_factor=args.load_factor or 0.5)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    info = big.info()
+    nb = 3
+    batches = []
+    for b in range(nb):
+        nt = torch.empty(ctx.total_nt, dtype=torch.uint8, device=ctx.dev)
+        capi.synth_reads_dev(spec, 3, (ctx.rank * 64 + b) * ctx.B, ctx.B, READ_LEN, HIT_PCT, nt.data_ptr())
+        batches.append(nt)
+    torch.cuda.synchronize()
+    def step(i):
+        capi.classify_reads_dev(big, ctx.gtax, ctx.opts, batches[i % nb].data_ptr(), ctx.roff.data_ptr(), ctx.nreads, ctx.total_nt,
+                                ctx.goff.data_ptr(), ctx.B, ctx.out_b.data_ptr(), ctx.stream)
+    steps = max(3, min(5, args.steps))
+    step_ms, lookup_ms, classify_ms = timed_steps(ctx, step, steps)
+    sampled = ctx.out_b.clone()
+    classified = float((ctx.out_b != 1).float().mean().item())
+    before = capi.pipeline_sampling(0)
+    try:
+        step(steps - 1)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(sampled, ctx.out_b))
+    finally:
+        capi.pipeline_sampling(before)
+    region = 60 << 30
+    alg = ctx.nreads * LOOKUPS_PER_READ * BYTES_PER_LOOKUP
+    res = {"value": ctx.world * ctx.nreads / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+           "lookup_stage_ms": lookup_ms, "classify_ms": classify_ms, "index_bytes": int(info.bytes), "index_keys_resident": int(info.n_keys),
+           "index_build_s": build_s, "index_load_factor": info.load_factor,
+           "probe_regions": int(max(1, -(-int(info.bytes) // region))), "roofline_frac": alg / (lookup_ms * 1e-3) / 1e9 / peak,
+           "classified_below_root_frac": classified, "sampled_equals_every_position": all_ranks_true(ctx, same),
+           "what": "replicated per GPU, reads partitioned; level 0 probed one <= 60 GiB hash-prefix region per launch (address-translation reach)"}
+    del batches
+    big.close()
+    return res
+
+
+def tryptic_instance(n_prot: int, npairs: int, frag: int, taxa, seed: int = 5):
+    """Synthetic proteome -> tryptic peptides of 9..45 residues valued with the protein's taxon (keys sorted, first value
+    of a duplicate kept), and predicted-gene style fragments in pairs (70 % windows of one protein, 30 % random residues)."""
+    rng = np.random.default_rng(seed)
+    L = 400
+    ids = np.array([t[0] for t in taxa], dtype=np.uint64)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    freq = np.array([8.3, 1.4, 5.5, 6.8, 3.9, 7.1, 2.3, 5.9, 5.8, 9.7, 2.4, 4.1, 4.7, 3.9, 5.5, 6.6, 5.4, 6.9, 1.1, 2.9])
+    prot = letters[rng.choice(20, size=(n_prot, L), p=freq / freq.sum())]
+    home = ids[rng.integers(0, len(ids), n_prot)]
+    flat = prot.reshape(-1)
+    prev = np.empty_like(flat)
+    prev[1:] = flat[:-1]
+    prev[0] = 0
+    start = ((prev == ord("K")) | (prev == ord("R"))) & (flat != ord("P"))
+    start[::L] = True
+    pos = np.flatnonzero(start)
+    nxt = np.empty_like(pos)
+    nxt[:-1] = pos[1:]
+    nxt[-1] = flat.size
+    end = np.minimum(nxt, (pos // L + 1) * L)
+    ln = end - pos
+    keep = (ln >= 9) & (ln <= 45)
+    kpos, klen = pos[keep], ln[keep]
+    peps = {}
+    fb = flat.tobytes()
+    for p0, l0 in zip(kpos.tolist(), klen.tolist()):
+        peps.setdefault(fb[p0:p0 + l0], int(home[p0 // L]))
+    keys = sorted(peps)
+    vals = np.array([peps[k] for k in keys], dtype=np.uint64)
+    koff = np.zeros(len(keys) + 1, dtype=np.uint64)
+    np.cumsum(np.fromiter((len(k) for k in keys), dtype=np.uint64, count=len(keys)), out=koff[1:])
+    blob = np.frombuffer(b"".join(keys), dtype=np.uint8)
+    nlines = 2 * npairs
+    src = rng.integers(0, n_prot, npairs)
+    hit = rng.random(npairs) < 0.7
+    a = rng.integers(0, L - frag, nlines)
+    lines = prot[np.repeat(src, 2)[:, None], (a[:, None] + np.arange(frag)[None, :])]
+    noise = letters[rng.integers(0, 20, size=(nlines, frag))]
+    lines = np.where(np.repeat(hit, 2)[:, None], lines, noise)
+    aa = np.ascontiguousarray(lines.reshape(-1))
+    loff = np.arange(nlines + 1, dtype=np.uint64) * frag
+    goff = np.arange(0, nlines + 1, 2, dtype=np.uint64)
+    return dict(blob=blob, koff=koff, vals=vals, aa=aa, loff=loff, goff=goff, n_keys=len(keys), nlines=nlines, frag=frag)
+
+
+def leg_tryptic(ctx, taxa):
+    """BASELINE configs[2]: prot2tryp2lca -l9 -L45 | uniq -d / | taxa2agg -l1 -a mrtl (the tryptic presets of
+    scripts/umgap-analyse.sh:291-300) through umgap_classify_peptides[_dev]; the C port of the same chain as the CPU
+    baseline, and a parity sample of the device results against it."""
+    capi, torch = ctx.capi, ctx.torch
+    from oracle import cport
+    npairs, frag = 1_000_000, 50
+    t0 = time.perf_counter()
+    inst = tryptic_instance(250_000, npairs, frag, taxa)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    tidx = capi.Index.from_blob(inst["blob"], inst["koff"], inst["vals"], k=0, device=ctx.local)
+    build_s = time.perf_counter() - t0
+    opts = capi.tryp_opts(minlen=9, maxlen=45, strategy=capi.AGG_MRTL, lower_bound=1.0)
+    aa, loff, goff, nlines = inst["aa"], inst["loff"], inst["goff"], inst["nlines"]
+    d_aa = torch.from_numpy(aa).to(ctx.dev)
+    d_loff = torch.from_numpy(loff.astype(np.int64)).to(ctx.dev)
+    d_goff = torch.from_numpy(goff.astype(np.int64)).to(ctx.dev)
+    d_out = torch.zeros(npairs, dtype=torch.int32, device=ctx.dev)
+    def run(_i=0):
+        capi.classify_peptides_dev(tidx, ctx.gtax, opts, d_aa.data_ptr(), d_loff.data_ptr(), nlines, aa.size, d_goff.data_ptr(), npairs,
+                                   d_out.data_ptr(), ctx.stream)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    dev_out = d_out.cpu().numpy().view(np.uint32)
+    # end to end from pinned host buffers
+    def pin(a):
+        t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).pin_memory()
+        return t.numpy().view(a.dtype), t
+    h_aa, _k1 = pin(aa)
+    h_loff, _k2 = pin(loff)
+    h_goff, _k3 = pin(goff)
+    host_out = capi.classify_peptides(tidx, ctx.gtax, opts, h_aa, h_loff, h_goff)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        host_out = capi.classify_peptides(tidx, ctx.gtax, opts, h_aa, h_loff, h_goff)
+    e2e_s = (time.perf_counter() - t0) / 3
+    # CPU baseline + parity: the C port on the same peptides against an fst image of the same keys
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    img = cport.FstImage(cport.fst_build_blob(inst["blob"], inst["koff"], inst["vals"]))
+    fst_s = time.perf_counter() - t0
+    copts = cport.RefTrypOpts(minlen=9, maxlen=45, keep=b"", drop=b"", strategy=2, factor=0.25, lower_bound=1.0, ranked_only=0)
+    ns = npairs
+    sub_aa, sub_loff, sub_goff = aa[: 2 * ns * frag], loff[: 2 * ns + 1], goff[: ns + 1]
+    ctax = cport.RefTaxonomy(taxa)
+    cport.classify_peptides(img, ctax, copts, sub_aa[: 2000 * frag], sub_loff[:2001], sub_goff[:1001], threads=threads)  # warm
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        want, nl, nh = cport.classify_peptides(img, ctax, copts, sub_aa, sub_loff, sub_goff, threads=threads)
+    cpu_s = (time.perf_counter() - t0) / reps
+    # MRTL ties (equal maxima) are broken by HashMap order in the reference: count agreement, and require that a
+    # disagreement is a tie (both answers have a hit and differ) -- never root-vs-taxon
+    agree = float((want == dev_out[:ns]).mean())
+    hard = int(((want != dev_out[:ns]) & ((want == 1) | (dev_out[:ns] == 1))).sum())
+    res = {"workload": "tryptic presets: prot2tryp2lca -l9 -L45 | uniq -d / | taxa2agg -l1 -a mrtl on pairs of 50-residue predicted-gene "
+                       "fragments (70 % from the indexed proteome), tryptic index of the synthetic proteome",
+           "value": nlines / (ms * 1e-3), "unit": "peptide lines/s", "pairs_per_second": npairs / (ms * 1e-3), "ms_per_step": ms,
+           "pairs_per_step": npairs, "index_keys_resident": int(tidx.info().n_keys), "index_bytes": int(tidx.info().bytes),
+           "index_build_s": build_s, "instance_generation_s": gen_s,
+           "e2e": {"value": nlines / e2e_s, "unit": "peptide lines/s", "ms_per_step": 1e3 * e2e_s, "h2d_bytes_per_step": int(aa.nbytes + loff.nbytes + goff.nbytes),
+                   "d2h_bytes_per_step": int(4 * npairs), "entry_point": "umgap_classify_peptides: pinned host arrays"},
+           "host_equals_device": bool(np.array_equal(host_out, dev_out)),
+           "cpu_baseline": {"value": 2 * ns / cpu_s, "unit": "peptide lines/s", "cores": threads, "kind": "port", "lookups_per_second": nl / cpu_s,
+                            "sample": f"{reps} x {ns} pairs, ref_classify_peptides (oracle/c) on {threads} threads against an fst image of the same "
+                                      f"{inst['n_keys']} peptides (built in {fst_s:.1f} s), {cpu_s * reps:.1f} s"},
+           "parity_vs_c_port": {"groups": ns, "equal_frac": agree, "root_vs_taxon_disagreements": hard,
+                                "note": "differences are MRTL ties (rmq/rtl.rs:52-55 breaks them by HashMap order)"},
+           "classified_below_root_frac": float((dev_out != 1).mean())}
+    tidx.close()
+    return res
+
+
+def leg_cpu_parity_and_loader(ctx, inst):
+    """(1) The fst loader: the CPU legs' image (1e8 keys) written to a file and streamed into a device table by
+    umgap_index_load_fst -- keys/s of the loader.  (2) Parity against the oracle on the same index: a 2 000-pair slice
+    through umgap_classify_reads against oracle/c (LCA*: no ties, must be equal; hybrid: equal or a tie) and 300 pairs
+    against the line-by-line Python oracle's admissible sets, which also gives the fraction of reads with a tie."""
+    capi, torch = ctx.capi, ctx.torch
+    from oracle import cport, lookup as olookup, pipeline as opipe
+    from oracle.taxonomy import Taxonomy as OTaxonomy
+    import tempfile
+    res = {}
+    with tempfile.NamedTemporaryFile(suffix=".fst", dir="/tmp") as f:
+        f.write(inst["raw"])
+        f.flush()
+        t0 = time.perf_counter()
+        lidx = capi.Index.load_fst(f.name, k=9, device=ctx.local)
+        torch.cuda.synchronize()
+        load_s = time.perf_counter() - t0
+    info = lidx.info()
+    res["fst_loader"] = {"index_load_s": load_s, "keys": int(info.n_keys), "keys_per_second": info.n_keys / load_s,
+                         "fst_bytes": inst["fst_bytes"], "bytes_per_second": inst["fst_bytes"] / load_s,
+                         "what": "umgap_index_load_fst on the CPU legs' fst image (page cache warm)"}
+    npairs = 2000
+    nt, off, goff = inst["reads"](40_000_000, npairs)
+    checks = {}
+    for name, strategy in (("lca_star", 0), ("hybrid", 1)):
+        o = capi.default_opts(min_seed_size=3, max_gap_size=0, strategy=strategy, factor=0.25)
+        got, _ = capi.classify_reads(lidx, ctx.gtax, o, nt, off, goff)
+        inst["opts"].strategy = strategy
+        want, _, _ = cport.classify(inst["img"], inst["tax"], inst["opts"], nt, off, goff, threads=os.cpu_count() or 1)
+        checks[name] = {"groups": npairs, "equal": int((got == want).sum())}
+    inst["opts"].strategy = 1
+    # the line-by-line oracle on the first 300 pairs: admissible sets (ties of tree/mix.rs:52-55)
+    ns = 300
+    otax = OTaxonomy(inst["taxa"])
+    rows = nt.reshape(-1, READ_LEN)
+    reads = [(f"r{i // 2}/{1 + (i & 1)}", rows[i].tobytes().decode()) for i in range(2 * ns)]
+    sets = opipe.classify_reads(reads, inst["img"], otax, min_seed_size=3, max_gap_size=0, strategy=1, factor=0.25)
+    o = capi.default_opts(min_seed_size=3, max_gap_size=0, strategy=capi.AGG_HYBRID, factor=0.25)
+    got, _ = capi.classify_reads(lidx, ctx.gtax, o, nt[: 2 * ns * READ_LEN], off[: 2 * ns + 1], goff[: ns + 1])
+    inside = sum(int(g) in adm for g, (_, adm) in zip(got, sets))
+    ties = sum(len(adm) > 1 for _, adm in sets)
+    checks["hybrid_vs_python_oracle_sets"] = {"groups": ns, "inside_admissible_set": inside, "groups_with_a_tie": ties}
+    res["oracle_slice"] = checks
+    res["tie_fraction"] = ties / ns
+    res["ok"] = (checks["lca_star"]["equal"] == npairs and inside == ns)
+    lidx.close()
+    return res
 
 
 # --------------------------------------------------------------------------------------------- ours
@@ -428,18 +799,78 @@ def run_ours(args):
         e2e["pack_reads_threads"] = os.cpu_count()
         e2e["byte_form"] = e2e_bytes
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (translate_lookup_kernel)
+    was_routed = routed is not None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"])
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    # ---- legs beyond the headline: every rank takes part in the device legs, rank 0 alone runs the CPU-side ones
+    want = {"every_position", "parity", "sharded", "large_index", "tryptic", "loader"} if args.legs == "all" else \
+        set() if args.legs == "none" else set(args.legs.split(","))
+    ctx = Ctx()
+    ctx.torch, ctx.capi, ctx.dist, ctx.args = torch, capi, dist, args
+    ctx.rank, ctx.world, ctx.local, ctx.dev, ctx.barrier = rank, world, local, dev, barrier
+    ctx.gtax, ctx.spec, ctx.opts, ctx.batches, ctx.roff, ctx.goff = gtax, spec, opts, batches, roff, goff
+    ctx.nreads, ctx.total_nt, ctx.B, ctx.stream = nreads, total_nt, B, stream
+    ctx.out_b = torch.zeros(B, dtype=torch.int32, device=dev)
+    ctx.replicated_out0 = None
+    legs = {}
+
+    def leg(name, fn, *a):
+        if name not in want:
+            return
+        t0 = time.perf_counter()
+        try:
+            legs[name] = fn(*a)
+        except Exception as e:  # a failed leg is reported, the headline stands
+            legs[name] = {"error": f"{type(e).__name__}: {e}"}
+        if isinstance(legs[name], dict):
+            legs[name]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+        barrier()
+
+    if not shard_mode:
+        leg("every_position", leg_every_position, ctx, gidx, peak)
+        leg("parity", leg_parity_device, ctx, gidx)
+        if world > 1:
+            leg("sharded", leg_sharded, ctx, gidx)
+    # the large table needs the HBM the headline instance holds
+    routed = None
+    del batches
+    ctx.batches = None
+    gidx.close()
+    torch.cuda.empty_cache()
+    if not shard_mode:
+        leg("large_index", leg_large_index, ctx, peak)
+    torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()   # rank 0's CPU-side legs
+            dist.destroy_process_group()
+        return
+
+    leg_inst = None
+    if "tryptic" in want:
+        t0 = time.perf_counter()
+        try:
+            legs["tryptic"] = leg_tryptic(ctx, taxa)
+        except Exception as e:
+            legs["tryptic"] = {"error": f"{type(e).__name__}: {e}"}
+        legs["tryptic"]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+    if not args.no_cpu_baseline:
+        leg_inst = cpu_instance(args.cpu_index_keys, os.cpu_count() or 1)
+    if "loader" in want and leg_inst is not None:
+        t0 = time.perf_counter()
+        try:
+            legs["oracle_parity_and_loader"] = leg_cpu_parity_and_loader(ctx, leg_inst)
+        except Exception as e:
+            legs["oracle_parity_and_loader"] = {"error": f"{type(e).__name__}: {e}"}
+        legs["oracle_parity_and_loader"]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+
+    # ---- roofline of the dominant kernel (lookup stage)
     lookups_per_launch = nreads * LOOKUPS_PER_READ
     # a step's lookup stage = the once-per-batch bracket plus one bracket per slice (routed mode: one launch per exchange round)
     avg_ms = max(lookup_ms / max(1, args.steps), 1e-9)   # routed mode: the local-shard lookups of both exchange rounds
@@ -455,8 +886,8 @@ def run_ours(args):
     if os.path.exists(tpath) and traffic:
         lines = tj.get("lookup_kernel_dram_bytes_per_launch", traffic) / 128.0 / nreads
     alg_bytes = lookups_per_launch * BYTES_PER_LOOKUP
-    if routed is not None or slices == 1:
-        use_ms = avg_ms if routed is not None else max(lookup_ms / max(1, lookup_n), 1e-9)
+    if was_routed or slices == 1:
+        use_ms = avg_ms if was_routed else max(lookup_ms / max(1, lookup_n), 1e-9)
         mode = "CUDA-event brackets around every launch of the lookup stage in the timed region, on its stream"
     else:
         # In the timed region a step is cut into slices whose lookup kernels run beside the previous slice's classify
@@ -466,16 +897,18 @@ def run_ours(args):
         # measured in this run right after the timed region; the in-region bracket sum is reported beside it.
         use_ms, mode = alone_ms, "lookup stage timed alone on the timed region's batches (umgap_pipeline_slices(1)), CUDA events on its stream"
     achieved = alg_bytes / (use_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if routed is not None
+    roofline = {"bound": "hbm", "kernel": "lookup_hashes_kernel (local shard)" if was_routed
                 else "lookup stage = lookup_sampled_kernel<9,TableView,3,0> (translation inside the kernel; + the long-read pass of translate_lookup_kernel), one event bracket",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "timing": mode,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": None if not traffic else "committed ncu --set full capture, not measured in this run: " + str(tj.get("source", ""))[:160],
+                "peak_source": peak_src, "timing": mode,
                 "note": "algorithmic bytes = 248 k-mers x 32 B per read (SURVEY 8(d)); in front of seedextend -s3 the kernel probes every "
                         "third position first and the rest only for frames with a hit (bit-identical output), so the HBM actually moves "
                         "`traffic` bytes: 128-byte line fills at the random-line ceiling (profiles/README.md)",
                 "dram_lines_per_read": lines,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": use_ms,
-                "classify_kernel_ms_alone": alone_classify_ms / alone_steps if routed is None else None,
+                "classify_kernel_ms_alone": alone_classify_ms / alone_steps if not was_routed else None,
                 "in_timed_region": {"slices_per_step": slices, "lookup_bracket_sum_ms_per_step": avg_ms,
                                     "classify_bracket_sum_ms_per_step": classify_ms / args.steps,
                                     "step_ms": ms / args.steps,
@@ -490,24 +923,35 @@ def run_ours(args):
                     "frac_effective_lookups": lookups_per_launch / (use_ms * 1e-3) / rand_sectors_per_s},
                 "kernel_share_of_step": min(1.0, use_ms / (ms / args.steps)) if ms else None,
                 "lookups_per_second_kernel": lookups_per_launch / (use_ms * 1e-3)}
-    cb = None if args.no_cpu_baseline else cpu_baseline(args)
+    cb = None if args.no_cpu_baseline else cpu_baseline(args, leg_inst)
     reads_total = world * nreads * args.steps
     line = {
         "metric": METRIC, "value": reads_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
         "lookups_per_second": reads_total * LOOKUPS_PER_READ / (ms * 1e-3),
-        "config": pipeline_config(args, {"index_keys_resident": int(info.n_keys), "index_bytes": int(info.bytes),
-                                         "index_build_s": build_s, "index_load_factor": info.load_factor, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
-                                         "classified_below_root_frac": classified, "kmer_hit_rate": kmer_hit_rate}),
+        "config": pipeline_config(args),
+        "workload_stats": {"index_keys_resident": int(info.n_keys), "index_bytes": int(info.bytes), "index_build_s": build_s,
+                           "index_load_factor": info.load_factor, "flagged_sector_frac": info.n_flagged / max(1, info.n_buckets),
+                           "classified_below_root_frac": classified, "kmer_hit_rate": kmer_hit_rate,
+                           "tie_fraction": (legs.get("oracle_parity_and_loader") or {}).get("tie_fraction")},
         "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches),
         "kernel_ms": {"translate_lookup": lookup_ms, "classify": classify_ms},
     }
     if routed_stages is not None:
         line["routed_stages_ms_per_step"] = routed_stages
+    line.update({("parity_check" if k == "parity" else k): v for k, v in legs.items()})
+    if "parity_check" in line and isinstance(line["parity_check"], dict):
+        pc = line["parity_check"]
+        if isinstance(line.get("sharded"), dict):
+            pc["sharded_equals_replicated"] = line["sharded"].get("equals_replicated")
+        if isinstance(line.get("oracle_parity_and_loader"), dict):
+            pc["oracle_slice"] = line["oracle_parity_and_loader"].get("oracle_slice")
+            pc["oracle_slice_ok"] = line["oracle_parity_and_loader"].get("ok")
     emit(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

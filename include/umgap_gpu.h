@@ -243,6 +243,26 @@ int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* ta
                                 const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
                                 uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups);
 
+/* ---- multi-GPU, replicated index (SURVEY 8(e) mode 1: reads are independent units, index and taxonomy
+ * replicated per GPU, no collective on the data path) inside one process -- what the reference gets from running
+ * several pipelines side by side.  umgap_index_replicate / umgap_taxonomy_replicate copy a loaded table / tree to
+ * another device (device to device, NVLink between peers) instead of streaming the file again.
+ * umgap_classify_reads_multi cuts the groups of a batch into one contiguous, nucleotide-balanced range per replica
+ * (never inside a uniq group, uniq.rs:56-84) and drives each replica's chunked host-buffer path from its own host
+ * thread; results are those of umgap_classify_reads, in input order.  idx[i] and tax[i] must live on the same
+ * device; a replica may not appear twice.                                                                      */
+int umgap_index_replicate(const umgap_index* src, int device, umgap_index** out);
+int umgap_taxonomy_replicate(const umgap_taxonomy* src, int device, umgap_taxonomy** out);
+int umgap_classify_reads_multi(const umgap_index* const* idx, const umgap_taxonomy* const* tax, int ngpus,
+                               const umgap_pipeline_opts* opts, const uint8_t* nt, const uint64_t* read_off,
+                               uint64_t nreads, const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out,
+                               uint64_t* n_lookups);
+int umgap_classify_reads_packed_multi(const umgap_index* const* idx, const umgap_taxonomy* const* tax, int ngpus,
+                                      const umgap_pipeline_opts* opts, const uint32_t* codes, const uint64_t* n_entries,
+                                      uint64_t n_count, const uint64_t* read_off, uint64_t nreads,
+                                      const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out,
+                                      uint64_t* n_lookups);
+
 /* Stage kernels on device-resident data, used by the benchmark to time the lookup kernel in
  * isolation: ids_dev receives 2*total_nt entries (position-major, both strands).           */
 int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts* opts,

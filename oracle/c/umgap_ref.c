@@ -1089,3 +1089,225 @@ int64_t ref_pipeline_staged(const uint8_t* img, uint64_t img_size, const void* t
     free(ub.p); free(ids); free(sel);
     return err ? -4 : ngroups;
 }
+
+/* ------------------------------------------------------------ synthetic workload (bench aid) ----
+ * C mirror of oracle/synth.py (itself the numpy mirror of umgap_b200/csrc/synth.cu, checked bit for bit
+ * against the device generator): the counter-based proteome, its 9-mer index as an fst image, and the
+ * reads.  Lets bench.py's CPU legs hold an index of 1e8+ keys without minutes of numpy.  Not part of
+ * the reference. */
+
+static inline uint64_t sm64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline uint64_t rnd3(uint64_t seed, uint64_t a, uint64_t b) { return sm64(sm64(seed ^ (a * 0xD6E8FEB86659FD93ull)) ^ b); }
+static const uint32_t SYN_CUM[20] = {5407, 6305, 9877, 14300, 16830, 21463, 22951, 26832, 30638, 36969,
+                                     38548, 41209, 44309, 46884, 50510, 54855, 58361, 62858, 63572, 65535};
+static const char SYN_AAS[] = "ACDEFGHIKLMNPQRSTVWY";
+static const char SYN_TABLE1[] = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG";
+#define SYN_K_TAXON 0x7461786F6Eull
+#define SYN_K_VALUE 0x76616C7565ull
+#define SYN_K_MUT 0x6D7574ull
+#define SYN_K_CODON 0x636F646F6Eull
+static inline uint32_t syn_residue(uint64_t seed, uint64_t j, uint64_t p) {
+    const uint32_t u = (uint32_t)(rnd3(seed, j, p) & 0xFFFF);
+    uint32_t c = 0;
+    for (int i = 0; i < 19; ++i) c += u > SYN_CUM[i];
+    return c;
+}
+
+typedef struct {
+    uint64_t seed, j0, j1; uint32_t plen, home_pct, anc_pct, ntax;
+    const uint32_t* depth; const uint32_t* parent_dense;
+    uint64_t* out; /* (key45 << 16 | dense) per window */
+} SynGen;
+static void* syn_gen_worker(void* arg) {
+    SynGen* g = (SynGen*)arg;
+    const uint32_t wpp = g->plen - 8;
+    uint8_t* res = (uint8_t*)malloc(g->plen);
+    for (uint64_t j = g->j0; j < g->j1; ++j) {
+        for (uint32_t p = 0; p < g->plen; ++p) res[p] = (uint8_t)syn_residue(g->seed, j, p);
+        const uint32_t home = (uint32_t)(rnd3(g->seed ^ SYN_K_TAXON, j, 0) % g->ntax);
+        uint64_t key = 0;
+        for (uint32_t p = 0; p < 8; ++p) key = key << 5 | res[p];
+        for (uint32_t p = 0; p < wpp; ++p) {
+            key = (key << 5 | res[p + 8]) & ((1ull << 45) - 1);
+            const uint64_t rv = rnd3(g->seed ^ SYN_K_VALUE, j, p);
+            const uint32_t u = (uint32_t)(rv % 100);
+            const uint64_t hi = rv >> 32;
+            uint32_t dense = home;
+            if (u >= g->home_pct && u < g->home_pct + g->anc_pct) {
+                const uint32_t d = (uint32_t)(hi % (g->depth[home] + 1ull));
+                while (g->depth[dense] > d) dense = g->parent_dense[dense];
+            } else if (u >= g->home_pct + g->anc_pct) {
+                dense = (uint32_t)(hi % g->ntax);
+            }
+            g->out[(j - g->j0) * wpp + p] = key << 16 | dense;
+        }
+    }
+    free(res);
+    return NULL;
+}
+
+static void radix_sort_u64(uint64_t* a, uint64_t* tmp, uint64_t n, int lo_bit, int hi_bit) {
+    uint64_t *src = a, *dst = tmp;
+    for (int b = lo_bit; b < hi_bit; b += 8) {
+        uint64_t cnt[257] = {0};
+        for (uint64_t i = 0; i < n; ++i) cnt[((src[i] >> b) & 255) + 1]++;
+        for (int i = 0; i < 256; ++i) cnt[i + 1] += cnt[i];
+        for (uint64_t i = 0; i < n; ++i) dst[cnt[(src[i] >> b) & 255]++] = src[i];
+        uint64_t* t = src; src = dst; dst = t;
+    }
+    if (src != a) memcpy(a, src, n * sizeof(uint64_t));
+}
+typedef struct { uint64_t* a; uint64_t* tmp; const uint64_t* start; int* next; pthread_mutex_t* mu; } SynSort;
+static void* syn_sort_worker(void* arg) {
+    SynSort* s = (SynSort*)arg;
+    for (;;) {
+        pthread_mutex_lock(s->mu);
+        const int b = (*s->next)++;
+        pthread_mutex_unlock(s->mu);
+        if (b >= 256) break;
+        radix_sort_u64(s->a + s->start[b], s->tmp + s->start[b], s->start[b + 1] - s->start[b], 16, 53);
+    }
+    return NULL;
+}
+
+/* All 9-mer windows of the proteome, sorted, equal k-mers merged by LCA, as an fst Map image (malloc'ed; ref_free).
+ * id_of / depth / parent_dense: the taxonomy in the library's preorder numbering (oracle/synth.py: Preorder). */
+uint8_t* ref_synth_fst(uint64_t seed, uint64_t n_prot, uint32_t plen, uint32_t home_pct, uint32_t anc_pct,
+                       const uint64_t* id_of, const uint32_t* depth, const uint32_t* parent_dense, uint32_t ntax,
+                       int threads, uint64_t* out_size, uint64_t* out_nkeys) {
+    *out_size = 0;
+    if (plen < 9 || ntax == 0 || ntax > 65536 || n_prot == 0) return NULL;
+    if (threads < 1) threads = 1;
+    const uint64_t wpp = plen - 8, n = n_prot * wpp;
+    uint64_t* a = (uint64_t*)malloc(n * sizeof(uint64_t));
+    uint64_t* tmp = (uint64_t*)malloc(n * sizeof(uint64_t));
+    if (!a || !tmp) { free(a); free(tmp); return NULL; }
+    pthread_t* th = (pthread_t*)malloc(threads * sizeof(pthread_t));
+    SynGen* gs = (SynGen*)calloc(threads, sizeof(SynGen));
+    for (int t = 0; t < threads; ++t) {
+        SynGen g = {seed, n_prot * t / threads, n_prot * (t + 1) / threads, plen, home_pct, anc_pct, ntax, depth, parent_dense, NULL};
+        g.out = a + g.j0 * wpp;
+        gs[t] = g;
+        pthread_create(&th[t], NULL, syn_gen_worker, &gs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(gs);
+    /* partition by the top 8 key bits, then sort the 256 parts on the threads */
+    uint64_t start[257] = {0};
+    for (uint64_t i = 0; i < n; ++i) start[(a[i] >> 53) + 1]++;
+    for (int i = 0; i < 256; ++i) start[i + 1] += start[i];
+    {
+        uint64_t fill[256];
+        memcpy(fill, start, sizeof fill);
+        for (uint64_t i = 0; i < n; ++i) tmp[fill[a[i] >> 53]++] = a[i];
+        uint64_t* t = a; a = tmp; tmp = t;
+    }
+    pthread_mutex_t mu;
+    pthread_mutex_init(&mu, NULL);
+    int next = 0;
+    SynSort ss = {a, tmp, start, &next, &mu};
+    for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, syn_sort_worker, &ss);
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&mu);
+    free(th);
+    free(tmp);
+    Builder b;
+    memset(&b, 0, sizeof b);
+    b.stack_cap = 64;
+    b.stack = (BNode*)calloc(b.stack_cap, sizeof(BNode));
+    b_put_int(&b, 2, 8);
+    b_put_int(&b, 0, 8);
+    uint64_t i = 0;
+    while (i < n && !b.error) {
+        const uint64_t key = a[i] >> 16;
+        uint32_t x = (uint32_t)(a[i] & 0xFFFF);
+        for (++i; i < n && (a[i] >> 16) == key; ++i) { /* equal k-mers: LCA of their values */
+            uint32_t y = (uint32_t)(a[i] & 0xFFFF);
+            while (x != y) { if (depth[x] >= depth[y]) x = parent_dense[x]; else y = parent_dense[y]; }
+        }
+        uint8_t kb[9];
+        for (int c = 0; c < 9; ++c) kb[c] = (uint8_t)SYN_AAS[(key >> (5 * (8 - c))) & 31];
+        builder_insert(&b, kb, 9, id_of[x]);
+    }
+    free(a);
+    uint8_t* result = NULL;
+    if (!b.error) {
+        compile_from(&b, 0);
+        const uint64_t root = emit_node(&b, &b.stack[0]);
+        b_put_int(&b, b.nkeys, 8);
+        b_put_int(&b, root, 8);
+        result = b.buf;
+        *out_size = b.len;
+        if (out_nkeys) *out_nkeys = b.nkeys;
+    } else {
+        free(b.buf);
+    }
+    for (int k = 0; k < b.stack_cap; ++k) free(b.stack[k].tr);
+    free(b.stack);
+    free(b.prev);
+    return result;
+}
+
+typedef struct {
+    uint64_t seed, n_prot, read_seed, first_pair, r0, r1; uint32_t plen, read_len, hit_pct;
+    uint8_t* out; const uint8_t (*codon_tab)[6]; const uint8_t* ncodon;
+} SynReads;
+static void* syn_reads_worker(void* arg) {
+    SynReads* s = (SynReads*)arg;
+    const uint32_t L = s->read_len, ncod = L / 3;
+    static const uint8_t base_of_tcag[4] = {3, 1, 0, 2};
+    for (uint64_t r = s->r0; r < s->r1; ++r) {
+        const uint64_t pair = s->first_pair + r / 2, mate = r & 1, rid = pair * 2 + mate;
+        const uint64_t rp = rnd3(s->read_seed, pair, 0);
+        const int hit = (rp % 100) < s->hit_pct && s->plen >= ncod;
+        const uint64_t j = (rp >> 8) % s->n_prot;
+        const uint64_t rm = rnd3(s->read_seed, pair, 1 + mate);
+        const uint64_t o = hit ? rm % (s->plen - ncod + 1) : 0;
+        const uint32_t sh = (uint32_t)((rm >> 32) % 3);
+        uint8_t* dst = s->out + r * L;
+        for (uint32_t x = 0; x < L; ++x) {
+            const uint64_t rx = rnd3(s->read_seed ^ SYN_K_MUT, rid, x);
+            uint32_t base = (uint32_t)((rx >> 16) & 3);
+            if (hit && x >= sh && (x - sh) / 3 < (L - sh) / 3 && ((rx & 0xFFFF) % 100) != 0) {
+                const uint32_t q = (x - sh) / 3, ph = (x - sh) % 3;
+                const uint32_t aa = syn_residue(s->seed, j, o + q);
+                const uint64_t rc = rnd3(s->read_seed ^ SYN_K_CODON, rid, q);
+                const uint32_t codon = s->codon_tab[aa][rc % s->ncodon[aa]];
+                base = base_of_tcag[(codon >> (2 * (2 - ph))) & 3];
+            }
+            const int is_n = ((rx >> 32) % 1000) == 0;
+            if (mate) dst[L - 1 - x] = is_n ? 'N' : (uint8_t)"ACGT"[3 - base];
+            else dst[x] = is_n ? 'N' : (uint8_t)"ACGT"[base];
+        }
+    }
+    return NULL;
+}
+/* npairs * 2 reads of read_len nucleotides (mate 2 reverse-complemented) into out. */
+void ref_synth_reads(uint64_t seed, uint64_t n_prot, uint32_t plen, uint64_t read_seed, uint64_t first_pair, uint64_t npairs,
+                     uint32_t read_len, uint32_t hit_pct, uint8_t* out, int threads) {
+    uint8_t codon_tab[20][6];
+    uint8_t ncodon[20];
+    memset(codon_tab, 0, sizeof codon_tab);
+    for (int a = 0; a < 20; ++a) {
+        ncodon[a] = 0;
+        for (int c = 0; c < 64; ++c) if (SYN_TABLE1[c] == SYN_AAS[a]) codon_tab[a][ncodon[a]++] = (uint8_t)c;
+    }
+    if (threads < 1) threads = 1;
+    pthread_t* th = (pthread_t*)malloc(threads * sizeof(pthread_t));
+    SynReads* ss = (SynReads*)calloc(threads, sizeof(SynReads));
+    const uint64_t nreads = 2 * npairs;
+    for (int t = 0; t < threads; ++t) {
+        SynReads s = {seed, n_prot, read_seed, first_pair, nreads * t / threads, nreads * (t + 1) / threads, plen, read_len, hit_pct,
+                      out, (const uint8_t (*)[6])codon_tab, ncodon};
+        ss[t] = s;
+        pthread_create(&th[t], NULL, syn_reads_worker, &ss[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(ss);
+    free(th);
+}

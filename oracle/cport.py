@@ -168,3 +168,32 @@ def pipeline_staged(img: FstImage, tax: RefTaxonomy, opts: RefOpts, fasta: bytes
     if n < 0:
         raise ValueError(f"ref_pipeline_staged failed: {n}")
     return out[:n], [float(x) for x in stage], nl.value
+
+
+def synth_fst(seed: int, n_proteins: int, protein_len: int, home_pct: int, ancestor_pct: int, pre, threads: int = 0):
+    """ref_synth_fst: the fst image of the synthetic proteome's 9-mer index (what oracle.synth.build_index +
+    fst_build_blob give, generated, sorted and merged in C).  `pre`: oracle.synth.Preorder.  Returns (bytes, n_keys)."""
+    size, nkeys = C.c_uint64(), C.c_uint64()
+    id_of = np.ascontiguousarray(pre.id_arr, dtype=np.uint64)
+    depth = np.asarray(pre.depth, dtype=np.uint32)
+    parent = np.asarray(pre.parent_dense, dtype=np.uint32)
+    lib().ref_synth_fst.restype = C.c_void_p
+    ptr = lib().ref_synth_fst(C.c_uint64(seed), C.c_uint64(n_proteins), C.c_uint32(protein_len), C.c_uint32(home_pct),
+                              C.c_uint32(ancestor_pct), _p(id_of), _p(depth), _p(parent), C.c_uint32(pre.n),
+                              C.c_int(threads or (os.cpu_count() or 1)), C.byref(size), C.byref(nkeys))
+    if not ptr:
+        raise ValueError("ref_synth_fst failed")
+    try:
+        return C.string_at(ptr, size.value), nkeys.value
+    finally:
+        lib().ref_free(C.c_void_p(ptr))
+
+
+def synth_reads(seed: int, n_proteins: int, protein_len: int, read_seed: int, first_pair: int, npairs: int, read_len: int,
+                hit_pct: int, threads: int = 0) -> np.ndarray:
+    """ref_synth_reads: uint8 [npairs*2, read_len], the C mirror of oracle.synth.reads."""
+    out = np.empty((2 * npairs, read_len), dtype=np.uint8)
+    lib().ref_synth_reads(C.c_uint64(seed), C.c_uint64(n_proteins), C.c_uint32(protein_len), C.c_uint64(read_seed),
+                          C.c_uint64(first_pair), C.c_uint64(npairs), C.c_uint32(read_len), C.c_uint32(hit_pct), _p(out),
+                          C.c_int(threads or (os.cpu_count() or 1)))
+    return out

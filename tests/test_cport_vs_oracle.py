@@ -210,3 +210,18 @@ def test_staged_text_pipeline_matches_python_oracle(world):
         for (h, adm), o in zip(want, out):
             assert int(o) in adm, (h, int(o), adm)
         assert nl == sum(2 * (len(r[1]) - 26) for r in reads if len(r[1]) >= 27)
+
+
+def test_c_workload_generator_matches_numpy_mirror():
+    """ref_synth_fst / ref_synth_reads (bench.py's CPU legs) against oracle/synth.py, which the GPU tests compare with the
+    device generator bit for bit: the same fst image (keys, LCA-merged values) and the same reads."""
+    from oracle import synth
+    taxa = datagen.make_taxonomy(500, seed=1)
+    pre = synth.Preorder(taxa)
+    for n_prot, plen in ((700, 408), (40, 60)):
+        keys, vals = synth.build_index(2, n_prot, plen, 70, 20, pre)
+        want = cport.fst_build_blob(keys.reshape(-1), np.arange(0, 9 * len(keys) + 1, 9, dtype=np.uint64), vals)
+        got, nkeys = cport.synth_fst(2, n_prot, plen, 70, 20, pre, threads=3)
+        assert nkeys == len(keys) and got == want
+    for first, n, L, pct in ((0, 64, 150, 70), (12345, 33, 101, 50), (7, 5, 27, 100)):
+        assert np.array_equal(synth.reads(2, 700, 408, 3, first, n, L, pct), cport.synth_reads(2, 700, 408, 3, first, n, L, pct, threads=3))

@@ -867,8 +867,10 @@ def test_packed_reads_match_byte_form(capi, world, monkeypatch):
         reads += [(f"L{L}{h}", sq) for h, sq in datagen.make_reads(prots, 40, seed=900 + L, read_len=L, hit_frac=0.8)]
     long_nt = "".join(rng.choice(datagen.CODONS.get(a, ["GCT"])) for p in prots[:5] for a in p)
     odd = _random_reads(rng, 40) + [long_nt[:1500]]
+    groups = [reads[i:i + 2] for i in range(0, len(reads), 2)]   # single reads go between the pairs, never inside one
     for i, sq in enumerate(odd):
-        reads.insert(rng.randrange(0, len(reads) // 2) * 2, (f"odd{i}/1", sq))
+        groups.insert(rng.randrange(0, len(groups)), [(f"odd{i}/1", sq)])
+    reads = [r for g in groups for r in g]
     nt, off = capi.pack_strings([r[1].encode() for r in reads])
     heads = [h.split("/")[0] for h, _ in reads]
     goff = np.array([0] + [i for i in range(1, len(reads) + 1) if i == len(reads) or heads[i] != heads[i - 1]], dtype=np.uint64)

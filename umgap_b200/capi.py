@@ -32,6 +32,7 @@ SYMBOLS = [
     "umgap_kmer_lookup_bound", "umgap_kmer_lookup",
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
     "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate",
+    "umgap_index_replicate", "umgap_taxonomy_replicate", "umgap_classify_reads_multi", "umgap_classify_reads_packed_multi",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
     "umgap_translate_lookup_dev",
@@ -460,6 +461,45 @@ def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes
     _check(lib.umgap_classify_reads_packed(index._h, tax._h, C.byref(opts), _p(codes), _p(entries) if ne else None, C.c_uint64(ne),
                                            _p(read_off), C.c_uint64(len(read_off) - 1), _p(group_off), C.c_uint64(ngroups),
                                            _p(out), C.byref(nl) if count_lookups else None))
+    return out[:ngroups], (nl.value if count_lookups else None)
+
+
+def replicate(index: Index, tax: Taxonomy, devices: Sequence[int]):
+    """Replicas of a loaded table and taxonomy on `devices` (umgap_index_replicate / umgap_taxonomy_replicate)."""
+    lib = load_library()
+    out = []
+    for d in devices:
+        hi, ht = C.c_void_p(), C.c_void_p()
+        _check(lib.umgap_index_replicate(index._h, C.c_int(d), C.byref(hi)))
+        _check(lib.umgap_taxonomy_replicate(tax._h, C.c_int(d), C.byref(ht)))
+        out.append((Index(hi), Taxonomy(ht)))
+    return out
+
+
+def classify_reads_multi(replicas, opts: PipelineOpts, nt: np.ndarray, read_off: np.ndarray, group_off: np.ndarray,
+                         count_lookups: bool = True, out: Optional[np.ndarray] = None, packed=None):
+    """umgap_classify_reads_multi over [(Index, Taxonomy), ...] (one pair per GPU); packed = (codes, entries) selects
+    umgap_classify_reads_packed_multi."""
+    lib = load_library()
+    read_off = _arr(read_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    n = len(replicas)
+    ih = (C.c_void_p * n)(*[i._h for i, _ in replicas])
+    th = (C.c_void_p * n)(*[t._h for _, t in replicas])
+    nl = C.c_uint64()
+    if packed is None:
+        nt = _arr(nt, np.uint8)
+        _check(lib.umgap_classify_reads_multi(ih, th, C.c_int(n), C.byref(opts), _p(nt), _p(read_off), C.c_uint64(len(read_off) - 1),
+                                              _p(group_off), C.c_uint64(ngroups), _p(out), C.byref(nl) if count_lookups else None))
+    else:
+        codes, entries = packed
+        ne = 0 if entries is None else len(entries)
+        _check(lib.umgap_classify_reads_packed_multi(ih, th, C.c_int(n), C.byref(opts), _p(codes), _p(entries) if ne else None,
+                                                     C.c_uint64(ne), _p(read_off), C.c_uint64(len(read_off) - 1), _p(group_off),
+                                                     C.c_uint64(ngroups), _p(out), C.byref(nl) if count_lookups else None))
     return out[:ngroups], (nl.value if count_lookups else None)
 
 

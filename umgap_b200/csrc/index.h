@@ -112,6 +112,7 @@ void check_shard(int shard, int nshards, int k);  // table.cu
 struct TimedLaunch {
     cudaEvent_t a, b;
     int kind;
+    int dev;
 };
 struct LaunchTimer {
     cudaStream_t st;

@@ -8,6 +8,10 @@
 //   translate_kernel, kmer_lookup_kernel, seedextend_kernel, aggregate_kernel: the same stages
 //                            one at a time, behind the per-command entry points.
 #include <algorithm>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <thread>
 
 #include "index.h"
 #include "warp_agg.cuh"
@@ -1358,8 +1362,10 @@ static void check_opts(const umgap_index* idx, const umgap_taxonomy* tax, const 
 
 // ---- optional per-launch timing (umgap_kernel_timing), shared with route.cu -----------------------
 namespace umgap {
-static uint64_t g_launch_count = 0;  // kernels launched by the fused path
-static uint64_t g_h2d_bytes = 0, g_d2h_bytes = 0;  // bytes umgap_classify_reads moved over PCIe
+// Process-wide counters and the timing aid; several host threads may drive different GPUs at once
+// (umgap_classify_reads_multi), so the counters are atomic and the event lists are guarded.
+static std::atomic<uint64_t> g_launch_count{0};  // kernels launched by the fused path
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // bytes umgap_classify_reads moved over PCIe
 static bool g_sampling = getenv("UMGAP_NO_SAMPLING") == nullptr;  // sampled lookups in front of seedextend (umgap_pipeline_sampling)
 static int g_slices = [] {           // slices of the device-buffer entry point (umgap_pipeline_slices)
     const char* e = getenv("UMGAP_SLICES");
@@ -1368,12 +1374,17 @@ static int g_slices = [] {           // slices of the device-buffer entry point 
 }();
 bool g_timing = false;
 std::vector<TimedLaunch> g_launches;
-static std::vector<cudaEvent_t> g_event_pool;
-static cudaEvent_t take_event() {
-    if (!g_event_pool.empty()) {
-        cudaEvent_t e = g_event_pool.back();
-        g_event_pool.pop_back();
-        return e;
+static std::mutex g_timing_mu;
+static std::map<int, std::vector<cudaEvent_t>> g_event_pool;  // per device: an event records only on its own device's streams
+static cudaEvent_t take_event(int dev) {
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        std::vector<cudaEvent_t>& pool = g_event_pool[dev];
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
     }
     cudaEvent_t e;
     UMGAP_CUDA(cudaEventCreate(&e));
@@ -1381,20 +1392,23 @@ static cudaEvent_t take_event() {
 }
 LaunchTimer::LaunchTimer(int kind, cudaStream_t s, bool enabled) : st(s), on(g_timing && enabled) {
     if (!on) return;
+    UMGAP_CUDA(cudaGetDevice(&t.dev));
     t.kind = kind;
-    t.a = take_event();
-    t.b = take_event();
+    t.a = take_event(t.dev);
+    t.b = take_event(t.dev);
     UMGAP_CUDA(cudaEventRecord(t.a, st));
 }
 void LaunchTimer::cancel() {
     if (!on) return;
-    g_event_pool.push_back(t.a);
-    g_event_pool.push_back(t.b);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_event_pool[t.dev].push_back(t.a);
+    g_event_pool[t.dev].push_back(t.b);
     on = false;
 }
 void LaunchTimer::stop() {
     if (!on) return;
     UMGAP_CUDA(cudaEventRecord(t.b, st));
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     g_launches.push_back(t);
 }
 }  // namespace umgap
@@ -1685,14 +1699,15 @@ int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* cla
     return guarded([&] {
         double ms[2] = {0, 0};
         uint64_t cnt[2] = {0, 0};
+        std::lock_guard<std::mutex> lk(g_timing_mu);
         for (TimedLaunch& t : g_launches) {
             UMGAP_CUDA(cudaEventSynchronize(t.b));
             float e = 0;
             UMGAP_CUDA(cudaEventElapsedTime(&e, t.a, t.b));
             ms[t.kind] += e;
             cnt[t.kind]++;
-            g_event_pool.push_back(t.a);
-            g_event_pool.push_back(t.b);
+            g_event_pool[t.dev].push_back(t.a);
+            g_event_pool[t.dev].push_back(t.b);
         }
         g_launches.clear();
         if (lookup_ms) *lookup_ms = ms[0];
@@ -1880,9 +1895,11 @@ struct HostReads {  // one of the two host forms of a batch's nucleotides
 
 }  // namespace
 
+// Groups [g_begin, g_end) of the batch (the whole batch by default; umgap_classify_reads_multi hands every GPU its range).
 static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
                           const HostReads& hr, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
-                          uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+                          uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups, uint64_t g_begin = 0,
+                          uint64_t g_end = ~0ull) {
     check_opts(idx, tax, opts);
     if (!tax) UMGAP_FAIL(UMGAP_ERR_INVALID, "null taxonomy");
     const bool packed = hr.codes != nullptr;
@@ -1930,16 +1947,17 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
     UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
     // nucleotides before group g (monotone in g): chunk ends are found by bisection
     auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
-    uint64_t g0 = 0;
+    g_end = std::min(g_end, ngroups);
+    uint64_t g0 = g_begin;
     int buf = 0, prev = -1;
     try {
         int chunk_no = 0;
-        while (g0 < ngroups) {
+        while (g0 < g_end) {
             const uint64_t nt0 = nt_before(g0);
             // the first chunks are short so that the kernels start early: 1/8, 1/4, 1/2 of a chunk, then full ones
             const uint64_t limit = chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
             ++chunk_no;
-            uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
+            uint64_t lo = g0 + 1, hi = g_end;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
             while (lo < hi) {
                 const uint64_t mid = lo + (hi - lo + 1) / 2;
                 if (nt_before(mid) - nt0 <= limit) lo = mid; else hi = mid - 1;
@@ -2042,6 +2060,84 @@ int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* ta
         hr.n_entries = n_entries;
         hr.n_count = n_count;
         classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
+    });
+}
+
+
+extern "C++" {
+// Replicated index, reads partitioned (SURVEY 8(e) mode 1) inside one process: the groups are cut into one contiguous,
+// nucleotide-balanced range per GPU (never inside a uniq group) and one host thread per GPU drives the chunked
+// host-buffer path of its replica; the ranges write disjoint parts of taxon_out.  No collective, no device-to-device traffic.
+static void classify_host_multi(const umgap_index* const* idx, const umgap_taxonomy* const* tax, int ngpus,
+                                const umgap_pipeline_opts* opts, const HostReads& hr, const uint64_t* read_off, uint64_t nreads,
+                                const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+    if (ngpus < 1 || !idx || !tax) UMGAP_FAIL(UMGAP_ERR_INVALID, "umgap_classify_reads_multi needs at least one index / taxonomy replica");
+    for (int i = 0; i < ngpus; ++i) {
+        if (!idx[i] || !tax[i]) UMGAP_FAIL(UMGAP_ERR_INVALID, "null replica %d", i);
+        if (tax[i]->device != idx[i]->device) UMGAP_FAIL(UMGAP_ERR_INVALID, "replica %d: index and taxonomy live on different devices", i);
+        for (int j = 0; j < i; ++j)
+            if (idx[j] == idx[i]) UMGAP_FAIL(UMGAP_ERR_INVALID, "replica %d given twice (one in-flight call per handle)", i);
+    }
+    if (ngpus == 1 || ngroups == 0) {
+        classify_host(idx[0], tax[0], opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
+        return;
+    }
+    if ((nreads && !read_off) || !group_off) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+    if (group_off[ngroups] != nreads || group_off[0] != 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off must cover reads 0..nreads");
+    std::vector<uint64_t> cut(ngpus + 1, ngroups);
+    cut[0] = 0;
+    const uint64_t total = read_off[nreads];
+    for (int i = 1; i < ngpus; ++i) {  // first group that starts at or after the i-th share of the nucleotides
+        const uint64_t want = total / ngpus * i;
+        uint64_t lo = cut[i - 1], hi = ngroups;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (read_off[group_off[mid]] < want) lo = mid + 1; else hi = mid;
+        }
+        cut[i] = lo;
+    }
+    std::vector<int> rc(ngpus, UMGAP_OK);
+    std::vector<std::string> msg(ngpus);
+    auto run = [&](int i) {
+        rc[i] = guarded([&] {
+            classify_host(idx[i], tax[i], opts, hr, read_off, nreads, group_off, ngroups, taxon_out, i == 0 ? n_lookups : nullptr,
+                          cut[i], cut[i + 1]);
+        });
+        if (rc[i] != UMGAP_OK) msg[i] = get_error();  // the error text is per thread: hand it to the caller
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < ngpus; ++i) th.emplace_back(run, i);
+    run(0);
+    for (std::thread& t : th) t.join();
+    for (int i = 0; i < ngpus; ++i)
+        if (rc[i] != UMGAP_OK) {
+            set_error("GPU %d: %s", idx[i]->device, msg[i].c_str());
+            throw StatusError{rc[i]};
+        }
+}
+}  // extern "C++"
+
+int umgap_classify_reads_multi(const umgap_index* const* idx, const umgap_taxonomy* const* tax, int ngpus,
+                               const umgap_pipeline_opts* opts, const uint8_t* nt, const uint64_t* read_off, uint64_t nreads,
+                               const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+    return guarded([&] {
+        HostReads hr;
+        hr.nt = nt;
+        classify_host_multi(idx, tax, ngpus, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
+    });
+}
+
+int umgap_classify_reads_packed_multi(const umgap_index* const* idx, const umgap_taxonomy* const* tax, int ngpus,
+                                      const umgap_pipeline_opts* opts, const uint32_t* codes, const uint64_t* n_entries,
+                                      uint64_t n_count, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
+                                      uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups) {
+    return guarded([&] {
+        if ((nreads && !codes) || (n_count && !n_entries)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        HostReads hr;
+        hr.codes = codes;
+        hr.n_entries = n_entries;
+        hr.n_count = n_count;
+        classify_host_multi(idx, tax, ngpus, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
     });
 }
 
