@@ -901,3 +901,41 @@ def test_packed_reads_match_byte_form(capi, world, monkeypatch):
     a, _ = capi.classify_reads(world["gidx"], world["gtax"], opts, clean, off, goff)
     b, _ = capi.classify_reads_packed(world["gidx"], world["gtax"], opts, c2, None, off, goff)
     assert np.array_equal(a, b)
+
+
+def test_multi_replica_classification_matches_single(capi, world):
+    """umgap_classify_reads_multi (index and taxonomy replicated, the groups of a batch cut into one range per replica,
+    one host thread each) returns what umgap_classify_reads returns: two and three replicas (on this box's GPUs, or all
+    on device 0 when it has one), ragged reads, the byte and the packed form, and an error raised inside one range."""
+    rng = random.Random(31)
+    reads = []
+    for L in (100, 150, 151, 301):
+        reads += [(f"L{L}{h}", sq) for h, sq in datagen.make_reads(world["proteins"], 60, seed=700 + L, read_len=L, hit_frac=0.8)]
+    groups = [reads[i:i + 2] for i in range(0, len(reads), 2)]
+    for i, sq in enumerate(_random_reads(rng, 30)):
+        groups.insert(rng.randrange(0, len(groups)), [(f"odd{i}/1", sq)])
+    reads = [r for g in groups for r in g]
+    nt, off = capi.pack_strings([r[1].encode() for r in reads])
+    heads = [h.split("/")[0] for h, _ in reads]
+    goff = np.array([0] + [i for i in range(1, len(reads) + 1) if i == len(reads) or heads[i] != heads[i - 1]], dtype=np.uint64)
+    ndev = capi.device_count()
+    codes, entries = capi.pack_reads(nt)
+    for nrep in (2, 3):
+        reps = [(world["gidx"], world["gtax"])] + capi.replicate(world["gidx"], world["gtax"], [(i + 1) % ndev for i in range(nrep - 1)])
+        for kw in (dict(seedextend=1, min_seed_size=3, strategy=capi.AGG_HYBRID), dict(seedextend=0, one_on_one=0, strategy=capi.AGG_LCA_STAR)):
+            opts = capi.default_opts(**kw)
+            want, nl = capi.classify_reads(world["gidx"], world["gtax"], opts, nt, off, goff)
+            got, nl2 = capi.classify_reads_multi(reps, opts, nt, off, goff)
+            assert nl == nl2 and np.array_equal(want, got), (nrep, kw)
+            got, _ = capi.classify_reads_multi(reps, opts, None, off, goff, packed=(codes, entries))
+            assert np.array_equal(want, got), (nrep, kw, "packed")
+        # fewer groups than replicas, and none
+        got, _ = capi.classify_reads_multi(reps, opts, nt, off[:3], np.array([0, 2], dtype=np.uint64))
+        assert np.array_equal(got, want[:1])
+        got, _ = capi.classify_reads_multi(reps, opts, nt, off[:1], np.array([0], dtype=np.uint64))
+        assert len(got) == 0
+        for i, t in reps[1:]:
+            i.close()
+            t.close()
+    with pytest.raises(capi.UmgapError):
+        capi.classify_reads_multi([(world["gidx"], world["gtax"]), (world["gidx"], world["gtax"])], opts, nt, off, goff)

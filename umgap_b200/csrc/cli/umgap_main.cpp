@@ -18,6 +18,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -762,12 +763,171 @@ int cmd_fastq2fasta(int argc, char** argv) {
 }
 
 // ---- classify: the whole preset in one process (extension) ---------------------------------------
+// Host side of the fused command.  The stream is cut into blocks of whole uniq groups; K parser threads turn blocks
+// into the arrays the library takes (no per-record strings; fasta.rs:38-67 with unwrap: a record is its header line
+// and the concatenation of the lines up to the next line that starts with '>'); one thread per GPU classifies parsed
+// blocks on its replica of the index (--gpus / UMGAP_DEVICES: index and taxonomy replicated, reads partitioned,
+// SURVEY 8(e) mode 1); the writer prints the blocks in input order.
+namespace classify_cli {
+
+struct Batch {
+    std::string nt, harena;
+    std::vector<uint64_t> roff, goff, hoff;  // hoff[g] .. hoff[g+1]: header of group g in harena
+    void reset() {
+        nt.clear();
+        harena.clear();
+        roff.assign(1, 0);
+        goff.clear();
+        hoff.assign(1, 0);
+    }
+    size_t groups() const { return hoff.size() - 1; }
+};
+
+struct Job {
+    std::vector<char> text;
+    size_t len = 0;
+    uint64_t seq = 0;
+    Batch batch;
+    std::vector<uint32_t> res;
+    std::string out;
+};
+
+template <class T>
+class Queue {  // unbounded FIFO; the number of jobs in flight bounds it
+  public:
+    void push(T v) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(v);
+        }
+        cv_.notify_one();
+    }
+    bool pop(T& v) {  // false once closed and drained
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = q_.front();
+        q_.erase(q_.begin());
+        return true;
+    }
+    void close() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            closed_ = true;
+        }
+        cv_.notify_all();
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<T> q_;
+    bool closed_ = false;
+};
+
+// Start of the record that ends at `end` (the position of a '>' that follows a '\n', or the end of the data).
+inline size_t record_start(const char* buf, size_t end) {
+    for (size_t q = end; q > 0;) {
+        const void* m = memrchr(buf, '>', q);
+        if (!m) break;
+        const size_t at = (const char*)m - buf;
+        if (at == 0 || buf[at - 1] == '\n') return at;
+        q = at;
+    }
+    return 0;
+}
+// Header (truncated at the uniq delimiter) and sequence length of the record in [rs, re).
+inline void record_view(const char* buf, size_t rs, size_t re, const std::string& delim, const char*& hs, size_t& hl, size_t& seq_len) {
+    const char* e = (const char*)memchr(buf + rs, '\n', re - rs);
+    const char* hend = e ? e : buf + re;
+    hs = buf + rs + 1;
+    hl = hend - hs;
+    if (hl && hs[hl - 1] == '\r') --hl;
+    if (!delim.empty()) {
+        const void* m = memmem(hs, hl, delim.data(), delim.size());
+        if (m) hl = (const char*)m - hs;
+    }
+    seq_len = 0;
+    for (const char* p = e ? e + 1 : buf + re; p < buf + re; ++p) seq_len += (*p != '\n' && *p != '\r');
+}
+// Where to cut [0, len): the start of a complete record that takes part in uniq's grouping (long enough for a frame,
+// prot2kmer2lca.rs:172) and whose group differs from that of the last such record before it -- so that no uniq
+// group (uniq.rs:56-84) spans two blocks.  0: no such place in the buffer yet.
+size_t find_cut(const char* buf, size_t len, const std::string& delim, size_t span) {
+    size_t r_end = record_start(buf, len);  // the last record may be incomplete: it stays behind the cut
+    while (r_end > 0) {
+        const size_t at = record_start(buf, r_end);
+        const char *h2, *h1;
+        size_t l2, l1, n2, n1;
+        record_view(buf, at, r_end, delim, h2, l2, n2);
+        if (n2 >= span) {
+            bool joined = false;
+            for (size_t pe = at; pe > 0;) {  // the last grouped record before the candidate
+                const size_t ps = record_start(buf, pe);
+                record_view(buf, ps, pe, delim, h1, l1, n1);
+                if (n1 >= span) {
+                    joined = l1 == l2 && memcmp(h1, h2, l1) == 0;
+                    break;
+                }
+                pe = ps;
+            }
+            if (!joined && at > 0) return at;
+        }
+        r_end = at;
+    }
+    return 0;
+}
+
+void parse_block(const char* p, const char* end, const std::string& delim, size_t span, Batch* B) {
+    B->reset();
+    B->nt.reserve(end - p);
+    while (p < end) {
+        const char* e = (const char*)memchr(p, '\n', end - p);  // header line
+        const char* hend = e ? e : end;
+        const char* hs = p + 1;
+        size_t hl = hend - hs;
+        if (hl && hs[hl - 1] == '\r') --hl;
+        p = e ? e + 1 : end;
+        const size_t nt0 = B->nt.size();
+        while (p < end && *p != '>') {  // sequence lines
+            const char* le = (const char*)memchr(p, '\n', end - p);
+            const char* lend = le ? le : end;
+            size_t ll = lend - p;
+            if (ll && p[ll - 1] == '\r') --ll;
+            B->nt.append(p, ll);
+            p = le ? le + 1 : end;
+        }
+        // reads too short for any frame emit no record at all and so do not take part in uniq's grouping
+        // (prot2kmer2lca.rs:172 drops them before uniq sees them)
+        if (B->nt.size() - nt0 < span) {
+            B->nt.resize(nt0);
+            continue;
+        }
+        if (!delim.empty()) {  // uniq -d: the header up to the first occurrence of the delimiter (uniq.rs:61-68)
+            const void* m = memmem(hs, hl, delim.data(), delim.size());
+            if (m) hl = (const char*)m - hs;
+        }
+        const size_t ng = B->groups();
+        const bool same = ng && B->hoff[ng] - B->hoff[ng - 1] == hl && memcmp(B->harena.data() + B->hoff[ng - 1], hs, hl) == 0;
+        if (!same) {
+            B->goff.push_back(B->roff.size() - 1);
+            B->harena.append(hs, hl);
+            B->hoff.push_back(B->harena.size());
+        }
+        B->roff.push_back(B->nt.size());
+    }
+    B->goff.push_back(B->roff.size() - 1);
+}
+
+}  // namespace classify_cli
+
 int cmd_classify(int argc, char** argv) {
+    using namespace classify_cli;
     Args a = parse(argc, argv, 2, {{'t', "table", true}, {'M', "methionine", false}, {'k', "length", true}, {'O', "omit-misses", false},
                                    {'S', "no-seedextend", false}, {'s', "min-seed-size", true}, {'g', "max-gap-size", true},
                                    {'d', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
-                                   {'f', "factor", true}, {'l', "lower-bound", true}});
-    if (a.pos.size() != 2) fail("usage: umgap classify [flags] <fst-file> <taxon-file> < reads.fa");
+                                   {'f', "factor", true}, {'l', "lower-bound", true}, {'G', "gpus", true}, {'P', "parser-threads", true}});
+    if (a.pos.size() != 2) fail("usage: umgap classify [flags] [--gpus N] <fst-file> <taxon-file> < reads.fa");
     umgap_pipeline_opts o;
     umgap_pipeline_opts_default(&o);
     o.table = (int)parse_usize(a.get("table", "1"));
@@ -782,193 +942,193 @@ int cmd_classify(int argc, char** argv) {
     o.ranked_only = a.has("ranked");
     const std::string delim = a.get("delimiter", "/");  // the presets join the mates with `uniq -d /`
     const int k = (int)parse_usize(a.get("length", "9"));
-    IndexHandle idx;
-    TaxHandle tax;
-    check(umgap_index_load_fst(a.pos[0].c_str(), k, 0, 0.0, &idx.p));
-    check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
-    // Host side of the fused command: the stream is parsed a block at a time straight into the arrays the library
-    // takes (no per-record strings; fasta.rs:38-67 with unwrap: a record is its header line and the concatenation of
-    // the lines up to the next line that starts with '>'), and a second thread classifies and prints batch i while
-    // this one parses batch i + 1.
-    struct Batch {
-        std::string nt, harena;
-        std::vector<uint64_t> roff, goff, hoff;  // hoff[g] .. hoff[g+1]: header of group g in harena
-        void reset() {
-            nt.clear();
-            harena.clear();
-            roff.assign(1, 0);
-            goff.clear();
-            hoff.assign(1, 0);
+    // devices: UMGAP_DEVICES=0,2,3 or --gpus N (devices 0..N-1); one by default
+    std::vector<int> devices;
+    if (const char* e = getenv("UMGAP_DEVICES")) {
+        for (const char* p = e; *p;) {
+            char* q = nullptr;
+            devices.push_back((int)strtol(p, &q, 10));
+            if (q == p) fail("UMGAP_DEVICES: expected a comma-separated list of device numbers");
+            p = *q == ',' ? q + 1 : q;
         }
-        size_t groups() const { return hoff.size() - 1; }
-    };
-    // groups per library call (UMGAP_CLI_BATCH overrides it, for tests of the batch seam)
-    const size_t batch_groups = getenv("UMGAP_CLI_BATCH") ? std::max<size_t>(1, strtoull(getenv("UMGAP_CLI_BATCH"), nullptr, 10)) : (size_t)1 << 19;
-    Batch batches[2];
-    std::mutex mu;
-    std::condition_variable cv;
-    int ready[2] = {0, 0};  // 0: free for the parser, 1: full, waiting for the classifier
-    bool done = false;
-    std::string worker_error;
-    std::thread worker([&] {
-        std::string out;
-        std::vector<uint32_t> res;
-        try {
-            for (int b = 0;; b ^= 1) {
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return ready[b] == 1 || done; });
-                    if (ready[b] != 1) break;
-                }
-                Batch& B = batches[b];
-                const size_t ng = B.groups();
-                if (ng) {
-                    res.resize(ng);
-                    B.goff.push_back(B.roff.size() - 1);
-                    check(umgap_classify_reads(idx.p, tax.p, &o, (const uint8_t*)B.nt.data(), B.roff.data(), B.roff.size() - 1,
-                                               B.goff.data(), ng, res.data(), nullptr));
-                    out.clear();
-                    char num[16];
-                    for (size_t g = 0; g < ng; ++g) {
-                        if (res[g] == UMGAP_ABSENT) continue;
-                        out += '>';
-                        out.append(B.harena, B.hoff[g], B.hoff[g + 1] - B.hoff[g]);
-                        out += '\n';
-                        const int n = snprintf(num, sizeof num, "%u", res[g]);
-                        out.append(num, n);
-                        out += '\n';
-                    }
-                    put(stdout, out);
-                }
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    ready[b] = 0;
-                }
-                cv.notify_all();
-            }
-        } catch (const std::exception& e) {
-            std::lock_guard<std::mutex> lk(mu);
-            worker_error = e.what();
-            ready[0] = ready[1] = 0;
-            cv.notify_all();
-        }
-    });
-    int cur = 0;
-    auto acquire = [&](int b) {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return ready[b] == 0; });
-        batches[b].reset();
-    };
-    auto submit = [&](int b) {
+    }
+    if (a.has("gpus")) {
+        const int n = (int)parse_usize(a.get("gpus", "1"));
+        if (n < 1) fail("--gpus needs a positive number");
+        if (devices.empty()) for (int i = 0; i < n; ++i) devices.push_back(i);
+        devices.resize(std::min<size_t>(devices.size(), n));
+    }
+    if (devices.empty()) devices.push_back(0);
+    const size_t G = devices.size();
+    std::vector<IndexHandle> idx(G);
+    std::vector<TaxHandle> tax(G);
+    check(umgap_index_load_fst(a.pos[0].c_str(), k, devices[0], 0.0, &idx[0].p));
+    check(umgap_taxonomy_load(a.pos[1].c_str(), devices[0], &tax[0].p));
+    for (size_t g = 1; g < G; ++g) {
+        check(umgap_index_replicate(idx[0].p, devices[g], &idx[g].p));
+        check(umgap_taxonomy_replicate(tax[0].p, devices[g], &tax[g].p));
+    }
+    // block size in bytes (UMGAP_CLI_BLOCK overrides it, for tests of the block seams)
+    const size_t block = getenv("UMGAP_CLI_BLOCK") ? std::max<size_t>(16, strtoull(getenv("UMGAP_CLI_BLOCK"), nullptr, 10)) : (size_t)32 << 20;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t P = a.has("parser-threads") ? std::max<size_t>(1, parse_usize(a.get("parser-threads", "1"))) : std::min<size_t>(std::max(2u, hw - 2), 12);
+    const size_t njobs = 2 * (P + G) + 2;
+    const size_t span = 3 * (size_t)k;
+
+    std::vector<std::unique_ptr<Job>> jobs(njobs);
+    Queue<Job*> free_q, parse_q, classify_q;
+    for (auto& j : jobs) {
+        j.reset(new Job());
+        free_q.push(j.get());
+    }
+    std::mutex mu;  // guards done / error
+    std::condition_variable done_cv;
+    std::map<uint64_t, Job*> done;
+    std::string error;
+    bool reader_finished = false;
+    uint64_t total_blocks = 0;
+    auto set_error = [&](const std::string& m) {
         {
             std::lock_guard<std::mutex> lk(mu);
-            ready[b] = 1;
+            if (error.empty()) error = m;
         }
-        cv.notify_all();
+        done_cv.notify_all();
+        free_q.close();
+        parse_q.close();
+        classify_q.close();
     };
-    std::string parse_error;
-    try {
-        acquire(cur);
-        Batch* B = &batches[cur];
-        const size_t span = 3 * (size_t)k;
-        std::vector<char> buf(64u << 20);
-        size_t have = 0;
-        bool eof = false, first = true;
-        while (!eof || have) {
-            if (!eof) {
-                if (have == buf.size()) buf.resize(buf.size() * 2);  // one record larger than the block
-                const size_t n = fread(buf.data() + have, 1, buf.size() - have, stdin);
-                if (n == 0) eof = true;
-                have += n;
+
+    std::vector<std::thread> parsers, classifiers;
+    std::atomic<size_t> parsers_left{P}, classifiers_left{G};
+    for (size_t t = 0; t < P; ++t)
+        parsers.emplace_back([&] {
+            Job* j;
+            while (parse_q.pop(j)) {
+                try {
+                    parse_block(j->text.data(), j->text.data() + j->len, delim, span, &j->batch);
+                    classify_q.push(j);
+                } catch (const std::exception& e) {
+                    set_error(e.what());
+                    break;
+                }
             }
-            if (first && have) {
-                if (buf[0] != '>') fail("Expected > at beginning of fasta header.");
-                first = false;
-            }
-            // records that are complete: everything before the last line that starts with '>' (all of it at the end)
-            size_t limit = have;
-            if (!eof) {
-                limit = 0;
-                for (size_t q = have; q > 1;) {
-                    const void* m = memrchr(buf.data(), '>', q);
-                    if (!m) break;
-                    const size_t at = (const char*)m - buf.data();
-                    if (at > 0 && buf[at - 1] == '\n') {
-                        limit = at;
-                        break;
+            if (--parsers_left == 0) classify_q.close();
+        });
+    for (size_t g = 0; g < G; ++g)
+        classifiers.emplace_back([&, g] {
+            Job* j;
+            while (classify_q.pop(j)) {
+                try {
+                    Batch& B = j->batch;
+                    const size_t ng = B.groups();
+                    j->out.clear();
+                    if (ng) {
+                        j->res.resize(ng);
+                        check(umgap_classify_reads(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.data(), B.roff.data(), B.roff.size() - 1,
+                                                   B.goff.data(), ng, j->res.data(), nullptr));
+                        j->out.reserve(B.harena.size() + 12 * ng);
+                        for (size_t x = 0; x < ng; ++x) {
+                            if (j->res[x] == UMGAP_ABSENT) continue;
+                            j->out += '>';
+                            j->out.append(B.harena, B.hoff[x], B.hoff[x + 1] - B.hoff[x]);
+                            j->out += '\n';
+                            append_u32(j->out, j->res[x]);
+                            j->out += '\n';
+                        }
                     }
-                    q = at;
-                }
-                if (limit == 0) {
-                    if (have == buf.size()) continue;   // grow the buffer and read on
-                    if (!eof) continue;
-                }
-            }
-            const char* p = buf.data();
-            const char* const end = buf.data() + limit;
-            while (p < end) {
-                // header line
-                const char* e = (const char*)memchr(p, '\n', end - p);
-                const char* hend = e ? e : end;
-                const char* hs = p + 1;
-                size_t hl = hend - hs;
-                if (hl && hs[hl - 1] == '\r') --hl;
-                p = e ? e + 1 : end;
-                const size_t nt0 = B->nt.size();
-                while (p < end && *p != '>') {  // sequence lines
-                    const char* le = (const char*)memchr(p, '\n', end - p);
-                    const char* lend = le ? le : end;
-                    size_t ll = lend - p;
-                    if (ll && p[ll - 1] == '\r') --ll;
-                    B->nt.append(p, ll);
-                    p = le ? le + 1 : end;
-                }
-                // reads too short for any frame emit no record at all and so do not take part in uniq's
-                // grouping (prot2kmer2lca.rs:172 drops them before uniq sees them)
-                if (B->nt.size() - nt0 < span) {
-                    B->nt.resize(nt0);
-                    continue;
-                }
-                if (!delim.empty()) {  // uniq -d: the header up to the first occurrence of the delimiter (uniq.rs:61-68)
-                    const void* m = memmem(hs, hl, delim.data(), delim.size());
-                    if (m) hl = (const char*)m - hs;
-                }
-                const size_t ng = B->groups();
-                const bool same = ng && B->hoff[ng] - B->hoff[ng - 1] == hl && memcmp(B->harena.data() + B->hoff[ng - 1], hs, hl) == 0;
-                if (!same) {
-                    if (ng >= batch_groups) {  // a new group starts: the batch can go
-                        std::string tail(B->nt, nt0);   // this read belongs to the next batch
-                        B->nt.resize(nt0);
-                        submit(cur);
-                        cur ^= 1;
-                        acquire(cur);
-                        if (!worker_error.empty()) fail(worker_error);
-                        B = &batches[cur];
-                        B->nt = tail;
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        done[j->seq] = j;
                     }
-                    B->goff.push_back(B->roff.size() - 1);
-                    B->harena.append(hs, hl);
-                    B->hoff.push_back(B->harena.size());
+                    done_cv.notify_all();
+                } catch (const std::exception& e) {
+                    set_error(e.what());
+                    break;
                 }
-                B->roff.push_back(B->nt.size());
             }
-            memmove(buf.data(), buf.data() + limit, have - limit);
-            have -= limit;
-            if (eof && limit == 0 && have) fail("Expected > at beginning of fasta header.");
+            --classifiers_left;
+            done_cv.notify_all();
+        });
+    std::thread writer([&] {
+        uint64_t next = 0;
+        for (;;) {
+            Job* j = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                done_cv.wait(lk, [&] { return !error.empty() || done.count(next) || (reader_finished && next >= total_blocks); });
+                if (!error.empty() || !done.count(next)) return;
+                j = done[next];
+                done.erase(next);
+            }
+            try {
+                put(stdout, j->out);
+            } catch (const std::exception& e) {
+                set_error(e.what());
+                return;
+            }
+            ++next;
+            free_q.push(j);
         }
-        submit(cur);
+    });
+
+    // reader: this thread
+    try {
+        std::vector<char> carry;  // what the previous block left behind its cut
+        bool eof = false, first = true;
+        uint64_t seq = 0;
+        while (!eof || !carry.empty()) {
+            Job* j;
+            if (!free_q.pop(j)) break;  // closed: an error elsewhere
+            if (j->text.size() < block + carry.size()) j->text.resize(block + carry.size());
+            memcpy(j->text.data(), carry.data(), carry.size());
+            size_t have = carry.size();
+            carry.clear();
+            size_t cut = 0;
+            for (;;) {
+                while (!eof && have < j->text.size()) {
+                    const ssize_t n = read(0, j->text.data() + have, j->text.size() - have);
+                    if (n < 0) {
+                        if (errno == EINTR) continue;
+                        fail("failed reading input");
+                    }
+                    if (n == 0) eof = true;
+                    have += (size_t)n;
+                }
+                if (first && have) {
+                    if (j->text[0] != '>') fail("Expected > at beginning of fasta header.");  // fasta.rs:44-49
+                    first = false;
+                }
+                if (eof) {
+                    cut = have;
+                    break;
+                }
+                cut = find_cut(j->text.data(), have, delim, span);
+                if (cut) break;
+                j->text.resize(j->text.size() * 2);  // one group larger than the block: read on
+            }
+            carry.assign(j->text.data() + cut, j->text.data() + have);
+            j->len = cut;
+            if (cut == 0) {
+                free_q.push(j);
+                continue;
+            }
+            j->seq = seq++;
+            parse_q.push(j);
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            total_blocks = seq;
+            reader_finished = true;
+        }
+        done_cv.notify_all();
+        parse_q.close();
     } catch (const std::exception& e) {
-        parse_error = e.what();
+        set_error(e.what());
     }
-    {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return (ready[0] == 0 && ready[1] == 0) || !worker_error.empty(); });
-        done = true;
-    }
-    cv.notify_all();
-    worker.join();
-    if (!parse_error.empty()) fail(parse_error);
-    if (!worker_error.empty()) fail(worker_error);
+    for (auto& t : parsers) t.join();
+    for (auto& t : classifiers) t.join();
+    writer.join();
+    if (!error.empty()) fail(error);
     return 0;
 }
 

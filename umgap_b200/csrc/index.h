@@ -108,6 +108,21 @@ struct TableBuilder {
 
 void check_shard(int shard, int nshards, int k);  // table.cu
 
+// The exchange step of the key-range-sharded mode (route.cu, pipeline.cu, exchange.cu): where the pack kernels put the
+// hashes bound for shard o -- a bucket in this rank's memory that the host sends (NCCL), or the owner's inbox, stored
+// to directly over NVLink peer mappings.
+
+struct BucketPtrs {
+    uint64_t* p[kMaxShards];
+};
+void route_pack_sampled(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
+                        const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap, const BucketPtrs& hp,
+                        uint32_t* send_pos_dev, uint64_t* cursors_dev, uint8_t* frame_hits_dev, uint32_t* ids_dev,
+                        const uint64_t* group_off_dev, uint64_t g_lo, uint64_t g_hi, int slot, cudaStream_t st);
+void route_pack_all(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev, const uint64_t* read_off_dev,
+                    uint64_t nreads, uint64_t total_nt, uint64_t cap, const BucketPtrs& hp, uint32_t* send_pos_dev,
+                    uint64_t* cursors_dev, uint32_t* ids_dev, cudaStream_t st);
+
 // Per-launch timing of the hot kernels (pipeline.cu): kind 0 = lookup, 1 = classify.
 struct TimedLaunch {
     cudaEvent_t a, b;

@@ -519,7 +519,7 @@ __device__ __forceinline__ uint32_t drain_round(const TV& t, uint64_t* q, uint32
 // Routed (key-range-sharded) mode: where the sampled kernel's lookups go instead of the local table -- the bucket of
 // the shard that owns the hash (route.cu; the ranks swap the buckets by NCCL and answer them from their own shard).
 struct RouteSink {
-    uint64_t* send_h = nullptr;             // [nshards][cap] hashes
+    BucketPtrs h;                           // per owner: its bucket of `cap` hashes (local memory, or the owner's inbox over NVLink)
     uint32_t* send_pos = nullptr;           // [nshards][cap] where the answer belongs (phase 1: read * 8 + frame, phase 2: ids index)
     unsigned long long* cursors = nullptr;  // [nshards] bucket fills, then [nshards] overflow flags
     uint64_t cap = 0;
@@ -564,7 +564,7 @@ __device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t*
         if (active) {
             const unsigned long long at = base + before;
             if (at < rs.cap) {
-                rs.send_h[(uint64_t)owner * rs.cap + at] = h;
+                rs.h.p[owner][at] = h;
                 rs.send_pos[(uint64_t)owner * rs.cap + at] = pos((uint32_t)(e >> 50));
             } else {
                 rs.cursors[rs.nshards + owner] = 1;  // bucket overflow: the host retries with a larger capacity
@@ -1779,7 +1779,7 @@ int umgap_classify_ids_masked_dev(const umgap_index* idx, const umgap_taxonomy* 
 extern "C++" {
 namespace umgap {
 void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
-                            const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
+                            const uint64_t* read_off_dev, uint64_t cap, const BucketPtrs& hp, uint32_t* send_pos_dev,
                             uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
                             const uint64_t* group_off_dev, uint64_t g_lo, cudaStream_t st);  // route.cu
 }
@@ -1789,14 +1789,15 @@ int umgap_route_sampled_applies(const umgap_index* idx, const umgap_pipeline_opt
     return idx && o && g_sampling && o->seedextend && o->one_on_one && o->min_seed_size >= 2 && idx->k == 9 ? 1 : 0;
 }
 
-int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
+extern "C++" void umgap::route_pack_sampled(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
                                  const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
-                                 uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev,
+                                 const BucketPtrs& hp, uint32_t* send_pos_dev, uint64_t* cursors_dev,
                                  uint8_t* frame_hits_dev, uint32_t* ids_dev, const uint64_t* group_off_dev, uint64_t g_lo,
-                                 uint64_t g_hi, int slot, void* stream) {
-    return guarded([&] {
-        if (!idx || !opts || !send_h_dev || !send_pos_dev || !cursors_dev || !ids_dev || !frame_hits_dev)
+                                 uint64_t g_hi, int slot, cudaStream_t st) {
+    {
+        if (!idx || !opts || !send_pos_dev || !cursors_dev || !ids_dev || !frame_hits_dev)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->nshards > kMaxShards) UMGAP_FAIL(UMGAP_ERR_INVALID, "the exchange step supports at most %d shards", kMaxShards);
         if (!umgap_route_sampled_applies(idx, opts))
             UMGAP_FAIL(UMGAP_ERR_INVALID, "sampled routing needs k = 9, -o and seedextend -s >= 2 (umgap_route_sampled_applies)");
         if (phase != 1 && phase != 2) UMGAP_FAIL(UMGAP_ERR_INVALID, "phase must be 1 or 2");
@@ -1804,7 +1805,6 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         if (2 * total_nt >= (1ull << 32) || nreads >= (1ull << 28)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large for 32-bit positions");
         if (((uintptr_t)nt_dev & 15u) || ((uintptr_t)frame_hits_dev & 3u)) UMGAP_FAIL(UMGAP_ERR_INVALID, "nt_dev must be 16-byte, frame_hits_dev 4-byte aligned");
         use_device(idx->device);
-        cudaStream_t st = (cudaStream_t)stream;
         UMGAP_CUDA(cudaMemsetAsync(cursors_dev, 0, 2 * (size_t)idx->nshards * sizeof(uint64_t), st));
         // 64 long-read counters, 64 unit counters, then the list of the reads longer than a warp batch (filled by phase 1)
         uint32_t* counters = (uint32_t*)idx->ws.get(WS_LONG + slot, (128 + nreads) * sizeof(uint32_t));
@@ -1819,7 +1819,7 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         CodonLut lut{};
         make_code_lut(idx, opts->table, opts->methionine, lut);
         RouteSink rs;
-        rs.send_h = send_h_dev;
+        rs.h = hp;
         rs.send_pos = send_pos_dev;
         rs.cursors = reinterpret_cast<unsigned long long*>(cursors_dev);
         rs.cap = cap;
@@ -1849,12 +1849,28 @@ int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_op
         UMGAP_CUDA(cudaGetLastError());
         ++g_launch_count;
         if (phase == 2) {  // every position of the reads longer than a warp batch
-            launch_route_pack_list(idx, opts, nt_dev, read_off_dev, cap, send_h_dev, send_pos_dev, cursors_dev, ids_dev, counters + 128,
+            launch_route_pack_list(idx, opts, nt_dev, read_off_dev, cap, hp, send_pos_dev, cursors_dev, ids_dev, counters + 128,
                                    counters, group_off_dev, g_lo, st);
             ++g_launch_count;
         }
+    }
+}
+
+int umgap_route_pack_sampled_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, int phase, const uint8_t* nt_dev,
+                                 const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
+                                 uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev,
+                                 uint8_t* frame_hits_dev, uint32_t* ids_dev, const uint64_t* group_off_dev, uint64_t g_lo,
+                                 uint64_t g_hi, int slot, void* stream) {
+    return guarded([&] {
+        if (!idx || !send_h_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->nshards > kMaxShards) UMGAP_FAIL(UMGAP_ERR_INVALID, "the exchange step supports at most %d shards", kMaxShards);
+        BucketPtrs hp{};
+        for (int o = 0; o < idx->nshards; ++o) hp.p[o] = send_h_dev + (uint64_t)o * cap;  // the buckets of this rank, sent by the host
+        route_pack_sampled(idx, opts, phase, nt_dev, read_off_dev, nreads, total_nt, cap, hp, send_pos_dev, cursors_dev, frame_hits_dev,
+                           ids_dev, group_off_dev, g_lo, g_hi, slot, (cudaStream_t)stream);
     });
 }
+
 
 int umgap_classify_reads_dev(const umgap_index* idx, const umgap_taxonomy* tax,
                              const umgap_pipeline_opts* opts, const uint8_t* nt_dev,

@@ -31,7 +31,7 @@ template <int K>
 __global__ void __launch_bounds__(kRouteWarps * 32)
 route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ nt,
                   const uint64_t* __restrict__ read_off, uint64_t nreads, uint64_t cap,
-                  uint64_t* __restrict__ send_h, uint32_t* __restrict__ send_pos,
+                  const BucketPtrs hp, uint32_t* __restrict__ send_pos,
                   unsigned long long* __restrict__ cursors /* [nshards] + [nshards]: overflow flag */,
                   uint32_t* __restrict__ ids, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count,
                   const uint64_t* __restrict__ group_off, uint64_t g_lo) {
@@ -104,7 +104,7 @@ route_pack_kernel(CodonLut72 lut, uint32_t nshards, const uint8_t* __restrict__ 
                         base = __shfl_sync(peers, base, leader);
                         const unsigned long long at = base + __popc(peers & lt_mask);
                         if (at < cap) {
-                            send_h[(uint64_t)owner * cap + at] = h;
+                            hp.p[owner][at] = h;
                             send_pos[(uint64_t)owner * cap + at] = (uint32_t)(2 * off + pos);
                         } else {
                             cursors[nshards + owner] = 1;  // bucket overflow: the host retries with a larger capacity
@@ -181,12 +181,12 @@ __global__ void route_scatter_hits_kernel(const uint32_t* __restrict__ ans, cons
 
 // The plain pack kernel over a device work list (pipeline.cu: umgap_route_pack_sampled_dev, phase 2).
 void launch_route_pack_list(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
-                            const uint64_t* read_off_dev, uint64_t cap, uint64_t* send_h_dev, uint32_t* send_pos_dev,
+                            const uint64_t* read_off_dev, uint64_t cap, const BucketPtrs& hp, uint32_t* send_pos_dev,
                             uint64_t* cursors_dev, uint32_t* ids_dev, const uint32_t* list, const uint32_t* list_count,
                             const uint64_t* group_off_dev, uint64_t g_lo, cudaStream_t st) {
     CodonLut72 lut{};
     make_code_lut_public(idx, opts->table, opts->methionine, lut.v);
-    route_pack_kernel<9><<<148, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, 0, cap, send_h_dev,
+    route_pack_kernel<9><<<148, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, 0, cap, hp,
                                                           send_pos_dev, reinterpret_cast<unsigned long long*>(cursors_dev),
                                                           ids_dev, list, list_count, group_off_dev, g_lo);
     UMGAP_CUDA(cudaGetLastError());
@@ -198,26 +198,39 @@ using namespace umgap;
 
 extern "C" {
 
-int umgap_route_pack_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+extern "C++" void umgap::route_pack_all(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
                          const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
-                         uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev, uint32_t* ids_dev,
-                         void* stream) {
-    return guarded([&] {
-        if (!idx || !opts || !send_h_dev || !send_pos_dev || !cursors_dev || !ids_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+                         const BucketPtrs& hp, uint32_t* send_pos_dev, uint64_t* cursors_dev, uint32_t* ids_dev,
+                         cudaStream_t st) {
+    {
+        if (!idx || !opts || !send_pos_dev || !cursors_dev || !ids_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         if (idx->k != 9) UMGAP_FAIL(UMGAP_ERR_INVALID, "the routed path is built for k = 9");
+        if (idx->nshards > kMaxShards) UMGAP_FAIL(UMGAP_ERR_INVALID, "the exchange step supports at most %d shards", kMaxShards);
         if (2 * total_nt >= (1ull << 32)) UMGAP_FAIL(UMGAP_ERR_INVALID, "batch too large for 32-bit ids positions");
         use_device(idx->device);
-        cudaStream_t st = (cudaStream_t)stream;
         UMGAP_CUDA(cudaMemsetAsync(cursors_dev, 0, 2 * (size_t)idx->nshards * sizeof(uint64_t), st));
         if (!nreads) return;
         CodonLut72 lut{};
         make_code_lut_public(idx, opts->table, opts->methionine, lut.v);
         const unsigned blocks = (unsigned)std::min<uint64_t>(ceil_div(nreads, kRouteWarps), 148ull * 32);
         route_pack_kernel<9><<<blocks, kRouteWarps * 32, 0, st>>>(lut, (uint32_t)idx->nshards, nt_dev, read_off_dev, nreads, cap,
-                                                                 send_h_dev, send_pos_dev,
+                                                                 hp, send_pos_dev,
                                                                  reinterpret_cast<unsigned long long*>(cursors_dev), ids_dev,
                                                                  nullptr, nullptr, nullptr, 0);
         UMGAP_CUDA(cudaGetLastError());
+    }
+}
+
+int umgap_route_pack_dev(const umgap_index* idx, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                         const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt, uint64_t cap,
+                         uint64_t* send_h_dev, uint32_t* send_pos_dev, uint64_t* cursors_dev, uint32_t* ids_dev,
+                         void* stream) {
+    return guarded([&] {
+        if (!idx || !send_h_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (idx->nshards > kMaxShards) UMGAP_FAIL(UMGAP_ERR_INVALID, "the exchange step supports at most %d shards", kMaxShards);
+        BucketPtrs hp{};
+        for (int o = 0; o < idx->nshards; ++o) hp.p[o] = send_h_dev + (uint64_t)o * cap;
+        route_pack_all(idx, opts, nt_dev, read_off_dev, nreads, total_nt, cap, hp, send_pos_dev, cursors_dev, ids_dev, (cudaStream_t)stream);
     });
 }
 
