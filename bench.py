@@ -344,38 +344,98 @@ def leg_parity_device(ctx, gidx):
 
 
 def leg_sharded(ctx, gidx_repl):
-    """BASELINE configs[4]: the index key-range-sharded over the GPUs, lookups routed to their owners (the exchange
-    step), on the headline workload; results compared with the replicated table's on every rank."""
+    """BASELINE configs[4]: the index key-range-sharded over the GPUs, every lookup answered by the GPU that owns the
+    hash.  The exchange step runs inside the kernels (exchange.cu: the pack kernels store hashes into the owners'
+    inboxes over NVLink peer mappings, the lookup kernels store the answers back; epoch flags order the rounds) --
+    no collective library and no host synchronisation inside a batch.  One process drives all the GPUs through
+    umgap_sharded (the form the CLI / a Rust host uses): rank 0 does, the other ranks wait on the host."""
     capi, torch, dist = ctx.capi, ctx.torch, ctx.dist
-    from umgap_b200 import sharded
     args = ctx.args
+    if ctx.rank != 0:
+        dist.barrier(group=ctx.gloo)
+        return None
+    res = None
+    try:
+        res = _sharded_rank0(ctx, gidx_repl)
+    finally:
+        torch.cuda.set_device(ctx.local)
+        dist.barrier(group=ctx.gloo)
+    return res
+
+
+def _sharded_rank0(ctx, gidx_repl):
+    import datagen
+    capi, torch = ctx.capi, ctx.torch
+    args = ctx.args
+    G = ctx.world
+    taxa_arrays = datagen.taxonomy_arrays(datagen.make_taxonomy(N_TAXA, seed=1))
     t0 = time.perf_counter()
-    sidx = capi.Index.build_synthetic(ctx.spec, ctx.gtax, device=ctx.local, load_factor=args.load_factor, shard=ctx.rank, nshards=ctx.world)
-    torch.cuda.synchronize()
+    gtax, shards = [], []
+    for d in range(G):
+        gtax.append(capi.Taxonomy.from_arrays(*taxa_arrays, device=d))
+        shards.append(capi.Index.build_synthetic(ctx.spec, gtax[d], device=d, load_factor=args.load_factor, shard=d, nshards=G))
     build_s = time.perf_counter() - t0
-    routed = sharded.RoutedClassifier(sidx, ctx.gtax, dist, ctx.total_nt, lanes=args.routed_lanes)
+    nb = 3
+    batches, roffs, goffs, outs = [], [], [], []
+    for d in range(G):
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            bs = []
+            for b in range(nb):
+                nt = torch.empty(ctx.total_nt, dtype=torch.uint8, device=dev)
+                capi.synth_reads_dev(ctx.spec, 3, (d * 64 + b) * ctx.B, ctx.B, READ_LEN, HIT_PCT, nt.data_ptr())
+                bs.append(nt)
+            batches.append(bs)
+            roffs.append(torch.arange(0, ctx.nreads + 1, dtype=torch.int64, device=dev) * READ_LEN)
+            goffs.append(torch.arange(0, ctx.nreads + 1, 2, dtype=torch.int64, device=dev))
+            outs.append(torch.zeros(ctx.B, dtype=torch.int32, device=dev))
+            torch.cuda.synchronize()
+    S = capi.Sharded(shards, gtax, ctx.total_nt)
+
     def step(i):
-        routed.classify(ctx.opts, ctx.batches[i % len(ctx.batches)], ctx.roff, ctx.goff, ctx.out_b, ctx.total_nt)
+        S.classify_reads_dev(ctx.opts, [batches[d][i % nb].data_ptr() for d in range(G)], [r.data_ptr() for r in roffs],
+                             [ctx.nreads] * G, [ctx.total_nt] * G, [g.data_ptr() for g in goffs], [ctx.B] * G,
+                             [o.data_ptr() for o in outs])
+
+    # parity: batch 0 of every GPU against the replicated table (rank 0's replica)
     step(0)
-    torch.cuda.synchronize()
-    same = bool(torch.equal(ctx.out_b, ctx.replicated_out0)) if getattr(ctx, "replicated_out0", None) is not None else None
-    overflow = routed.overflowed()
+    routed0 = S.sync()
+    same = True
+    torch.cuda.set_device(ctx.local)
+    for d in range(G):
+        nt0 = batches[d][0].to(ctx.dev)
+        capi.classify_reads_dev(gidx_repl, ctx.gtax, ctx.opts, nt0.data_ptr(), ctx.roff.data_ptr(), ctx.nreads, ctx.total_nt,
+                                ctx.goff.data_ptr(), ctx.B, ctx.out_b.data_ptr(), ctx.stream)
+        torch.cuda.synchronize()
+        same = same and bool(torch.equal(ctx.out_b, outs[d].to(ctx.dev)))
+        del nt0
     steps = max(3, min(5, args.steps))
-    step_ms, lookup_ms, classify_ms = timed_steps(ctx, step, steps)
-    routed.profile = True
-    routed.stage_ms = {}
     for i in range(2):
         step(i)
-    routed.profile = False
-    stages = {k: round(v / 2, 3) for k, v in routed.stage_ms.items()}
-    res = {"value": ctx.world * ctx.nreads / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
-           "local_shard_lookup_ms": lookup_ms, "classify_ms": classify_ms, "routed_stages_ms_per_step": stages,
-           "lookups_routed_per_step_per_rank": routed.lookups_routed, "bucket_overflow": bool(overflow),
-           "shard_build_s": build_s, "shard_bytes": int(sidx.info().bytes),
-           "equals_replicated": None if same is None else all_ranks_true(ctx, same and not overflow),
+    S.sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    S.sync()
+    step_ms = 1e3 * (time.perf_counter() - t0) / steps
+    # where the time goes: CUDA-event brackets around the stages of two more batches, averaged over the GPUs
+    capi.kernel_timing(True)
+    capi.kernel_times_ex()
+    for i in range(2):
+        step(i)
+    S.sync()
+    stages = {k: round(ms / (2 * G), 3) for k, (ms, _) in capi.kernel_times_ex().items()}
+    capi.kernel_timing(False)
+    res = {"value": G * ctx.nreads / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+           "timing": "wall clock between umgap_sharded_sync calls around the timed batches (one process enqueues for every GPU; nothing "
+                     "synchronises inside)",
+           "stages_ms_per_step_per_gpu": stages, "lookups_routed_per_step": int(routed0),
+           "shard_build_s_all": build_s, "shard_bytes": int(shards[0].info().bytes), "equals_replicated": bool(same),
+           "exchange": "in-kernel: peer stores over NVLink (8 B per lookup out, 4 B back), epoch flags, no NCCL, no host read-back",
            "what": "index key-range-sharded over the GPUs; two exchange rounds per batch (sampled positions, then the live frames)"}
-    del routed
-    sidx.close()
+    S.close()
+    for x in shards + gtax:
+        x.close()
     return res
 
 
@@ -619,8 +679,10 @@ def run_ours(args):
     if capi.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: " + capi.load_library().umgap_last_error().decode())
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")   # host-side waits that keep the GPUs free (the sharded leg)
 
     def barrier():
         if world > 1:
@@ -817,6 +879,7 @@ def run_ours(args):
     ctx.nreads, ctx.total_nt, ctx.B, ctx.stream = nreads, total_nt, B, stream
     ctx.out_b = torch.zeros(B, dtype=torch.int32, device=dev)
     ctx.replicated_out0 = None
+    ctx.gloo = gloo
     legs = {}
 
     def leg(name, fn, *a):
@@ -829,6 +892,8 @@ def run_ours(args):
             legs[name] = {"error": f"{type(e).__name__}: {e}"}
         if isinstance(legs[name], dict):
             legs[name]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+        else:
+            legs.pop(name)
         barrier()
 
     if not shard_mode:

@@ -98,6 +98,19 @@ int umgap_index_attach_shards(umgap_index* idx, const umgap_shard_desc* descs, i
  * handles, in shard order; peer access is enabled as needed.                                    */
 int umgap_index_attach_shards_local(umgap_index* idx, umgap_index* const* shards, int nshards);
 
+/* ---- buildindex / printindex: the index FILE itself (host only; buildindex.rs:32-48, printindex.rs:38-51).
+ * umgap_fst_writer_*: fst::MapBuilder -- keys in strictly increasing byte order, each with its u64 value; writes an
+ * `fst` format-v2 Map file to `path` (NULL or "-": stdout).  No suffix sharing: larger than the crate's files, same
+ * content.  finish() and abort() release the writer.  umgap_fst_stream: fst::Map::stream -- calls fn for every key in
+ * order (a non-zero return stops with UMGAP_ERR_IO); *n_keys receives the count stored in the file's footer.      */
+typedef struct umgap_fst_writer umgap_fst_writer;
+int umgap_fst_writer_open(const char* path, umgap_fst_writer** out);
+int umgap_fst_writer_insert(umgap_fst_writer* w, const uint8_t* key, size_t len, uint64_t value);
+int umgap_fst_writer_finish(umgap_fst_writer* w);
+void umgap_fst_writer_abort(umgap_fst_writer* w);
+typedef int (*umgap_fst_key_fn)(const uint8_t* key, size_t len, uint64_t value, void* user);
+int umgap_fst_stream(const char* path, umgap_fst_key_fn fn, void* user, uint64_t* n_keys);
+
 typedef struct umgap_index_info {
     uint64_t n_keys;        /* distinct keys resident                                      */
     uint64_t n_buckets;     /* 32-byte buckets                                             */
@@ -348,12 +361,56 @@ int umgap_classify_ids_masked_dev(const umgap_index* idx, const umgap_taxonomy* 
                                   const uint64_t* group_off_dev, uint64_t ngroups, const uint8_t* frame_hits_dev,
                                   int frame_major, uint32_t* taxon_out_dev, void* stream);
 
+/* ---- the exchange step with the kernels doing the transfers (exchange.cu): no collective library, no host in the
+ * loop.  Every rank owns a shard and an *exchange region* of umgap_exchange_region_bytes() in its HBM that every other
+ * rank maps (peer access inside one process; cuMem / IPC / symmetric-memory mappings across processes -- the library
+ * takes the mapped pointers, however they were made).  The pack kernels store each k-mer hash straight into the
+ * owner's inbox over NVLink, epoch flags order the rounds, the owner's lookup kernel stores the answers straight into
+ * the requester's answer box; one batch = two rounds behind `-o | seedextend -s S` (S >= 2), else one, then the
+ * classify kernel -- all enqueued on one stream without a host synchronisation.  Every rank needs a GPU of its own
+ * (the ranks' kernels wait on each other).  regions[o] = this rank's mapping of rank o's region (zero-initialised by
+ * its owner before the first batch); every rank calls umgap_exchange_classify_dev for every batch (a rank without
+ * reads passes nreads = ngroups = 0).  umgap_exchange_status (after the caller synchronised the stream) raises bucket
+ * overflow (UMGAP_ERR_CAPACITY), a peer that never answered (UMGAP_ERR_CUDA) and Unknown Taxon ID.               */
+typedef struct umgap_exchange umgap_exchange;
+uint64_t umgap_exchange_bucket_cap(int nranks, uint64_t max_total_nt);
+uint64_t umgap_exchange_region_bytes(int nranks, uint64_t max_total_nt);
+int umgap_exchange_create(const umgap_index* shard, const umgap_taxonomy* tax, int rank, int nranks, uint64_t max_total_nt,
+                          void* const* regions, umgap_exchange** out);
+void umgap_exchange_free(umgap_exchange* ex);
+int umgap_exchange_classify_dev(umgap_exchange* ex, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
+                                const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,
+                                const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, void* stream);
+int umgap_exchange_status(umgap_exchange* ex, uint64_t* lookups_routed);
+
+/* One process driving every shard (the CLI, a Rust host with one thread): shards[i] is shard i of n, each on its own
+ * GPU; peer access is enabled and the regions allocated here.  umgap_classify_reads_sharded takes host buffers like
+ * umgap_classify_reads (the groups cut into one range per GPU, as many passes as the per-GPU buffers of max_total_nt
+ * nucleotides require); the _dev form takes one device-resident batch per shard and returns at once --
+ * umgap_sharded_sync waits and raises what umgap_exchange_status raises.                                          */
+typedef struct umgap_sharded umgap_sharded;
+int umgap_sharded_create(const umgap_index* const* shards, const umgap_taxonomy* const* tax, int n, uint64_t max_total_nt,
+                         umgap_sharded** out);
+void umgap_sharded_free(umgap_sharded* s);
+int umgap_classify_reads_sharded_dev(umgap_sharded* s, const umgap_pipeline_opts* opts, const uint8_t* const* nt_dev,
+                                     const uint64_t* const* read_off_dev, const uint64_t* nreads, const uint64_t* total_nt,
+                                     const uint64_t* const* group_off_dev, const uint64_t* ngroups,
+                                     uint32_t* const* taxon_out_dev);
+int umgap_sharded_sync(umgap_sharded* s, uint64_t* lookups_routed);
+int umgap_classify_reads_sharded(umgap_sharded* s, const umgap_pipeline_opts* opts, const uint8_t* nt,
+                                 const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off, uint64_t ngroups,
+                                 uint32_t* taxon_out, uint64_t* n_lookups);
+
 /* ---- measurement aid: when enabled, every launch of the two hot-path kernels is bracketed by CUDA
  * events on the stream it is launched on.  umgap_kernel_times() waits for the recorded launches,
  * returns the summed durations (ms) and launch counts since the last call, and clears them.      */
 int umgap_kernel_timing(int enable);
 int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
                        uint64_t* classify_launches);
+/* The same with the brackets of the exchange step: kind 0 lookup, 1 classify, 2 pack (hashes stored into the owners'
+ * inboxes), 3 the time the wait kernels spun for peers (exposed transfers and skew), 4 scatter; nkinds <= 8, summed
+ * over every device this process drives.                                                                        */
+int umgap_kernel_times_ex(double* ms, uint64_t* launches, int nkinds);
 /* Number of kernels the fused path (umgap_classify_reads[_dev], umgap_translate_lookup_dev,
  * umgap_classify_ids_dev) has launched in this process; the lookup stage is up to three launches
  * (residue-code pre-pass, sampled lookup kernel, long-read pass).                                  */

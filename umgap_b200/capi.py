@@ -32,6 +32,10 @@ SYMBOLS = [
     "umgap_kmer_lookup_bound", "umgap_kmer_lookup",
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
     "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate",
+    "umgap_fst_writer_open", "umgap_fst_writer_insert", "umgap_fst_writer_finish", "umgap_fst_writer_abort", "umgap_fst_stream",
+    "umgap_kernel_times_ex", "umgap_exchange_bucket_cap", "umgap_exchange_region_bytes", "umgap_exchange_create", "umgap_exchange_free",
+    "umgap_exchange_classify_dev", "umgap_exchange_status", "umgap_sharded_create", "umgap_sharded_free",
+    "umgap_classify_reads_sharded_dev", "umgap_sharded_sync", "umgap_classify_reads_sharded",
     "umgap_index_replicate", "umgap_taxonomy_replicate", "umgap_classify_reads_multi", "umgap_classify_reads_packed_multi",
     "umgap_pipeline_opts_default", "umgap_classify_reads", "umgap_classify_reads_dev",
     "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
@@ -264,6 +268,35 @@ class Index:
             self.close()
         except Exception:
             pass
+
+
+def fst_write(path: str, items) -> None:
+    """umgap_fst_writer_*: (key bytes, value) pairs in strictly increasing key order -> an fst Map file."""
+    lib = load_library()
+    w = C.c_void_p()
+    _check(lib.umgap_fst_writer_open(path.encode(), C.byref(w)))
+    try:
+        for k, v in items:
+            _check(lib.umgap_fst_writer_insert(w, C.c_char_p(bytes(k)), C.c_size_t(len(k)), C.c_uint64(int(v))))
+    except Exception:
+        lib.umgap_fst_writer_abort(w)
+        raise
+    _check(lib.umgap_fst_writer_finish(w))
+
+
+def fst_items(path: str):
+    """umgap_fst_stream: the (key, value) pairs of an fst Map file, in order."""
+    out = []
+    CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_uint64, C.c_void_p)
+
+    def cb(key, n, value, _user):
+        out.append((bytes(key[:n]), int(value)))
+        return 0
+
+    n = C.c_uint64()
+    _check(load_library().umgap_fst_stream(path.encode(), CB(cb), None, C.byref(n)))
+    assert n.value == len(out)
+    return out
 
 
 def default_opts(**kw) -> PipelineOpts:
@@ -503,6 +536,60 @@ def classify_reads_multi(replicas, opts: PipelineOpts, nt: np.ndarray, read_off:
     return out[:ngroups], (nl.value if count_lookups else None)
 
 
+class Sharded:
+    """umgap_sharded: one process driving every shard of a key-range-sharded index; the exchange step runs in the
+    kernels over NVLink peer mappings (exchange.cu).  shards[i] = shard i of n on its own GPU, taxa[i] on the same GPU."""
+
+    def __init__(self, shards: Sequence[Index], taxa: Sequence[Taxonomy], max_total_nt: int):
+        n = len(shards)
+        self.n = n
+        self._keep = (list(shards), list(taxa))
+        ih = (C.c_void_p * n)(*[i._h for i in shards])
+        th = (C.c_void_p * n)(*[t._h for t in taxa])
+        h = C.c_void_p()
+        _check(load_library().umgap_sharded_create(ih, th, C.c_int(n), C.c_uint64(max_total_nt), C.byref(h)))
+        self._h = h
+
+    def classify_reads(self, opts: PipelineOpts, nt: np.ndarray, read_off: np.ndarray, group_off: np.ndarray,
+                       count_lookups: bool = True):
+        nt = _arr(nt, np.uint8)
+        read_off = _arr(read_off, np.uint64)
+        group_off = _arr(group_off, np.uint64)
+        ngroups = len(group_off) - 1
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+        nl = C.c_uint64()
+        _check(load_library().umgap_classify_reads_sharded(self._h, C.byref(opts), _p(nt), _p(read_off), C.c_uint64(len(read_off) - 1),
+                                                           _p(group_off), C.c_uint64(ngroups), _p(out),
+                                                           C.byref(nl) if count_lookups else None))
+        return out[:ngroups], (nl.value if count_lookups else None)
+
+    def classify_reads_dev(self, opts: PipelineOpts, nt_ptrs, read_off_ptrs, nreads, total_nt, group_off_ptrs, ngroups, out_ptrs) -> None:
+        """One device-resident batch per shard (lists of raw device addresses and counts); returns at once."""
+        n = self.n
+        vp = lambda xs: (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in xs])
+        u64 = lambda xs: (C.c_uint64 * n)(*[int(x) for x in xs])
+        _check(load_library().umgap_classify_reads_sharded_dev(self._h, C.byref(opts), vp(nt_ptrs), vp(read_off_ptrs), u64(nreads),
+                                                               u64(total_nt), vp(group_off_ptrs), u64(ngroups), vp(out_ptrs)))
+
+    def sync(self) -> int:
+        """Waits for the enqueued batches; raises on bucket overflow / a silent peer / Unknown Taxon ID.  Returns the
+        number of lookups routed since the last call."""
+        r = C.c_uint64()
+        _check(load_library().umgap_sharded_sync(self._h, C.byref(r)))
+        return r.value
+
+    def close(self):
+        if self._h:
+            load_library().umgap_sharded_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def classify_reads_dev(index: Index, tax: Taxonomy, opts: PipelineOpts, nt_ptr: int,
                        read_off_ptr: int, nreads: int, total_nt: int, group_off_ptr: int,
                        ngroups: int, out_ptr: int, stream: int = 0) -> None:
@@ -537,6 +624,15 @@ def kernel_times():
     na, nb = C.c_uint64(), C.c_uint64()
     _check(load_library().umgap_kernel_times(C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
     return a.value, na.value, b.value, nb.value
+
+
+def kernel_times_ex():
+    """umgap_kernel_times_ex: dict stage -> (ms, launches) since the last call."""
+    ms = (C.c_double * 8)()
+    cnt = (C.c_uint64 * 8)()
+    _check(load_library().umgap_kernel_times_ex(ms, cnt, C.c_int(8)))
+    names = ("lookup", "classify", "pack", "wait_for_peers", "scatter")
+    return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
 
 def pipeline_slices(slices: int = 0) -> int:

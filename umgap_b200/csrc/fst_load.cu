@@ -1,6 +1,10 @@
 // umgap_index_load_fst: streams an fst Map file once into the device table (replaces
 // fst::Map::from_path / from_bytes at prot2kmer2lca.rs:109-114 and prot2tryp2lca.rs:89-94).
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "index.h"
 
@@ -53,6 +57,232 @@ struct KmerSink : FstSink {
     }
 };
 
+
+// ---- the same load on several host threads -----------------------------------------------------------------------
+// The file is cut below its first three key bytes into independent subtrees (FstFile::split); worker threads walk
+// them and pack the k-byte keys into pinned batches; this thread uploads full batches (cudaMemcpyAsync on a ring of
+// streams, each with its own device buffers) and launches the inserts, so the walk, the copies and the insert
+// kernels overlap.  The residue alphabet is fixed before the workers start: the bytes met on the first three levels,
+// in walk order (a deterministic function of the file, hence the same on every rank of a sharded load).  A key with a
+// byte first met deeper than that makes the load start over on the serial path above.
+struct PinnedBatch {
+    uint64_t* k = nullptr;
+    uint32_t* v = nullptr;
+    size_t n = 0;
+};
+constexpr size_t kPBatch = 1u << 20;
+
+struct BatchQueues {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<PinnedBatch*> free_, full_;
+    bool stop = false;
+    PinnedBatch* take_free() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !free_.empty() || stop; });
+        if (free_.empty()) return nullptr;
+        PinnedBatch* b = free_.back();
+        free_.pop_back();
+        return b;
+    }
+    void give_free(PinnedBatch* b) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            b->n = 0;
+            free_.push_back(b);
+        }
+        cv.notify_all();
+    }
+    void give_full(PinnedBatch* b) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            full_.push_back(b);
+        }
+        cv.notify_all();
+    }
+};
+
+struct WorkerSink : FstSink {
+    const uint8_t* code_of_byte;
+    const size_t k;
+    BatchQueues& q;
+    PinnedBatch* cur = nullptr;
+    uint64_t skipped = 0;
+    bool unknown_byte = false, bad_value = false;
+    WorkerSink(const uint8_t* codes, size_t kk, BatchQueues& queues) : code_of_byte(codes), k(kk), q(queues) {}
+    void on_key(const uint8_t* key, size_t len, uint64_t value) override {
+        if (len != k) {
+            ++skipped;
+            return;
+        }
+        uint64_t code = 0;
+        for (size_t i = 0; i < k; ++i) {
+            const uint8_t c = code_of_byte[key[i]];
+            if (c == 0xFF) {
+                unknown_byte = true;
+                return;
+            }
+            code = (code << 5) | c;
+        }
+        if (value >= 0xFFFFFFFFull) {
+            bad_value = true;
+            return;
+        }
+        if (!cur) cur = q.take_free();
+        if (!cur) return;  // the load was stopped
+        cur->k[cur->n] = code;
+        cur->v[cur->n] = (uint32_t)value;
+        if (++cur->n == kPBatch) {
+            q.give_full(cur);
+            cur = nullptr;
+        }
+    }
+    void finish() {
+        if (cur && cur->n) q.give_full(cur);
+        else if (cur) q.give_free(cur);
+        cur = nullptr;
+    }
+};
+
+// Returns false when the file needs the serial path (a residue byte outside the alphabet of the first levels).
+bool load_parallel(const char* path, TableBuilder& b, umgap_index* idx, int threads) {
+    FstFile file(path);
+    const size_t k = (size_t)idx->k;
+    std::vector<FstTask> tasks;
+    std::vector<uint8_t> seen;
+    // keys of up to min(3, k - 1) bytes end inside the split: none of them has k bytes, they only count as skipped
+    struct Shallow : FstSink {
+        uint64_t n = 0;
+        void on_key(const uint8_t*, size_t, uint64_t) override { ++n; }
+    } shallow;
+    const size_t depth = std::min<size_t>(3, k - 1);
+    if (depth == 0) return false;
+    file.split(depth, tasks, shallow, seen);
+    for (uint8_t byte : seen)
+        if (b.code_for(byte) < 0) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "index keys use more than 32 distinct byte values");
+    idx->n_skipped += shallow.n;
+    if (tasks.empty()) return true;
+
+    const int kRing = 4;
+    const int nbatches = threads + kRing + 2;
+    std::vector<PinnedBatch> store(nbatches);
+    BatchQueues q;
+    cudaStream_t st[kRing] = {};
+    cudaEvent_t ev[kRing] = {};
+    PinnedBatch* inflight[kRing] = {};
+    DevBuf<uint64_t> dk[kRing];
+    DevBuf<uint32_t> dv[kRing];
+    std::vector<std::thread> workers;
+    std::vector<WorkerSink*> sinks;
+    std::atomic<size_t> next_task{0};
+    std::atomic<int> running{threads};
+    std::atomic<bool> failed{false};
+    std::string worker_error;
+    int worker_rc = UMGAP_OK;
+    auto cleanup = [&] {
+        {
+            std::lock_guard<std::mutex> lk(q.mu);
+            q.stop = true;
+        }
+        q.cv.notify_all();
+        for (std::thread& t : workers) t.join();
+        for (WorkerSink* s : sinks) delete s;
+        cudaDeviceSynchronize();
+        for (int i = 0; i < kRing; ++i) {
+            if (st[i]) cudaStreamDestroy(st[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        for (PinnedBatch& pb : store) {
+            if (pb.k) cudaFreeHost(pb.k);
+            if (pb.v) cudaFreeHost(pb.v);
+        }
+    };
+    try {
+        for (PinnedBatch& pb : store) {
+            UMGAP_CUDA(cudaHostAlloc((void**)&pb.k, kPBatch * 8, cudaHostAllocDefault));
+            UMGAP_CUDA(cudaHostAlloc((void**)&pb.v, kPBatch * 4, cudaHostAllocDefault));
+            q.free_.push_back(&pb);
+        }
+        for (int i = 0; i < kRing; ++i) {
+            UMGAP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            UMGAP_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            dk[i].alloc(kPBatch);
+            dv[i].alloc(kPBatch);
+        }
+        UMGAP_CUDA(cudaDeviceSynchronize());  // the table's memsets (legacy stream) before inserts on the ring's streams
+        std::mutex err_mu;
+        for (int t = 0; t < threads; ++t) {
+            WorkerSink* sink = new WorkerSink(idx->code_of_byte, k, q);
+            sinks.push_back(sink);
+            workers.emplace_back([&, sink] {
+                const int rc = guarded([&] {
+                    for (;;) {
+                        const size_t i = next_task.fetch_add(1);
+                        if (i >= tasks.size() || failed.load() || sink->unknown_byte || sink->bad_value) break;
+                        file.stream(tasks[i], *sink);
+                    }
+                    sink->finish();
+                });
+                if (rc != UMGAP_OK) {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    if (worker_rc == UMGAP_OK) {
+                        worker_rc = rc;
+                        worker_error = get_error();
+                    }
+                    failed = true;
+                }
+                if (sink->unknown_byte || sink->bad_value) failed = true;
+                {
+                    std::lock_guard<std::mutex> lk(q.mu);
+                    --running;
+                }
+                q.cv.notify_all();
+            });
+        }
+        // uploader
+        uint64_t seq = 0;
+        for (;;) {
+            PinnedBatch* pb = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(q.mu);
+                q.cv.wait(lk, [&] { return !q.full_.empty() || running.load() == 0; });
+                if (q.full_.empty()) break;
+                pb = q.full_.back();
+                q.full_.pop_back();
+            }
+            const int slot = (int)(seq++ % kRing);
+            if (inflight[slot]) {
+                UMGAP_CUDA(cudaEventSynchronize(ev[slot]));
+                q.give_free(inflight[slot]);
+                inflight[slot] = nullptr;
+            }
+            UMGAP_CUDA(cudaMemcpyAsync(dk[slot].p, pb->k, pb->n * 8, cudaMemcpyHostToDevice, st[slot]));
+            UMGAP_CUDA(cudaMemcpyAsync(dv[slot].p, pb->v, pb->n * 4, cudaMemcpyHostToDevice, st[slot]));
+            b.insert_dev(dk[slot].p, dv[slot].p, pb->n, st[slot]);
+            UMGAP_CUDA(cudaEventRecord(ev[slot], st[slot]));
+            inflight[slot] = pb;
+        }
+        UMGAP_CUDA(cudaDeviceSynchronize());
+    } catch (...) {
+        failed = true;
+        cleanup();
+        throw;
+    }
+    bool unknown = false, bad = false;
+    for (WorkerSink* s : sinks) {
+        unknown |= s->unknown_byte;
+        bad |= s->bad_value;
+        idx->n_skipped += s->skipped;
+    }
+    cleanup();
+    if (worker_rc != UMGAP_OK) {
+        set_error("%s", worker_error.c_str());
+        throw StatusError{worker_rc};
+    }
+    if (bad) UMGAP_FAIL(UMGAP_ERR_CAPACITY, "an index value does not fit 32 bits");
+    return !unknown;
+}
+
 }  // namespace
 }  // namespace umgap
 
@@ -85,16 +315,47 @@ extern "C" int umgap_index_load_fst_shard(const char* path, int k, int device, d
             return;
         }
         const uint64_t n = fst_file_len(path);
-        TableBuilder b;
-        try {
-            b.begin(idx, n, load_factor);
-            KmerSink sink(b, idx);
-            fst_stream_file(path, sink, nullptr);
-            sink.flush();
-            b.finish();
-        } catch (...) {
-            b.abort();
-            throw;
+        // host threads of the walk (UMGAP_LOAD_THREADS; 1 = the serial path)
+        const char* te = getenv("UMGAP_LOAD_THREADS");
+        int threads = te ? atoi(te) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n < (1u << 16)) threads = std::min(threads, 2);
+        bool done = false;
+        if (threads > 1) {
+            TableBuilder b;
+            try {
+                b.begin(idx, n, load_factor);
+                done = load_parallel(path, b, idx, threads);
+                if (done) b.finish();
+                else b.abort();
+            } catch (...) {
+                b.abort();
+                throw;
+            }
+            if (!done) {  // start over on one thread: free the half-built table, forget the alphabet
+                for (int i = 0; i < kMaxLevels; ++i) {
+                    if (idx->level_dev[i]) cudaFree(idx->level_dev[i]);
+                    idx->level_dev[i] = nullptr;
+                    idx->level_nlines[i] = 0;
+                }
+                idx->nlevels = 0;
+                idx->bytes = 0;
+                idx->n_skipped = 0;
+                idx->alphabet_size = 0;
+                memset(idx->code_of_byte, 0xFF, sizeof idx->code_of_byte);
+            }
+        }
+        if (!done) {
+            TableBuilder b;
+            try {
+                b.begin(idx, n, load_factor);
+                KmerSink sink(b, idx);
+                fst_stream_file(path, sink, nullptr);
+                sink.flush();
+                b.finish();
+            } catch (...) {
+                b.abort();
+                throw;
+            }
         }
         *out = idx;
     });

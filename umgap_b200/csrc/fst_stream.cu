@@ -150,27 +150,25 @@ uint64_t fst_file_len(const char* path) {
     return len;
 }
 
-void fst_stream_file(const char* path, FstSink& sink, uint64_t* n_keys_footer) {
-    Mapped m(path);
-    uint64_t len, root;
-    check_header(m, len, root);
-    if (n_keys_footer) *n_keys_footer = len;
-    if (m.size == 32) return;  // empty fst
-    const uint64_t node_limit = m.size - 16;
-    struct Frame {
-        Node node;
-        uint32_t next;
-        uint64_t out;
-    };
+namespace {
+struct Frame {
+    Node node;
+    uint32_t next;
+    uint64_t out;
+};
+
+// Depth-first walk below `start` (reached by `key` with outputs summing to `out`), at most max_depth more bytes:
+// keys go to the sink; with `cut`, nodes at max_depth are not entered but recorded as tasks.
+void walk(const uint8_t* data, uint64_t node_limit, uint64_t start, uint64_t out0, std::vector<uint8_t>& key, FstSink& sink,
+          size_t max_depth, std::vector<FstTask>* cut, std::vector<uint8_t>* bytes_seen) {
+    const size_t base = key.size();
     std::vector<Frame> stack;
-    std::vector<uint8_t> key;
-    stack.push_back(Frame{Node(m.data, root, node_limit), 0, 0});
-    if (stack.back().node.final_) sink.on_key(key.data(), 0, stack.back().node.final_output);
+    stack.push_back(Frame{Node(data, start, node_limit), 0, out0});
     while (!stack.empty()) {
         Frame& f = stack.back();
         if (f.next >= f.node.ntrans) {
             stack.pop_back();
-            if (!key.empty()) key.pop_back();
+            if (key.size() > base) key.pop_back();
             continue;
         }
         uint8_t input;
@@ -178,15 +176,66 @@ void fst_stream_file(const char* path, FstSink& sink, uint64_t* n_keys_footer) {
         f.node.trans(f.next++, input, output, target);
         const uint64_t out = f.out + output;
         key.push_back(input);
+        if (bytes_seen) bytes_seen->push_back(input);
         if (key.size() > 4096) UMGAP_FAIL(UMGAP_ERR_IO, "fst: key longer than 4096 bytes (cycle?)");
-        Node child(m.data, target, node_limit);
+        Node child(data, target, node_limit);
         if (child.final_) sink.on_key(key.data(), key.size(), out + child.final_output);
         if (child.ntrans == 0) {
             key.pop_back();
             continue;
         }
+        if (cut && key.size() - base >= max_depth) {
+            FstTask t;
+            t.addr = target;
+            t.out = out;
+            t.plen = (uint8_t)key.size();
+            memcpy(t.prefix, key.data(), key.size());
+            cut->push_back(t);
+            key.pop_back();
+            continue;
+        }
         stack.push_back(Frame{child, 0, out});
     }
+}
+}  // namespace
+
+void fst_stream_file(const char* path, FstSink& sink, uint64_t* n_keys_footer) {
+    Mapped m(path);
+    uint64_t len, root;
+    check_header(m, len, root);
+    if (n_keys_footer) *n_keys_footer = len;
+    if (m.size == 32) return;  // empty fst
+    const uint64_t node_limit = m.size - 16;
+    std::vector<uint8_t> key;
+    Node r(m.data, root, node_limit);
+    if (r.final_) sink.on_key(key.data(), 0, r.final_output);
+    walk(m.data, node_limit, root, 0, key, sink, 0, nullptr, nullptr);
+}
+
+// ---- the same file walked by several threads: the top `depth` levels once (their keys go to `shallow`, the input
+// bytes seen there to `bytes_seen` in walk order), the subtrees below as independent tasks ------------------------
+struct FstFile::Impl {
+    Mapped m;
+    uint64_t len = 0, root = 0;
+    explicit Impl(const char* path) : m(path) { check_header(m, len, root); }
+};
+FstFile::FstFile(const char* path) : impl_(new Impl(path)) {}
+FstFile::~FstFile() { delete impl_; }
+uint64_t FstFile::len() const { return impl_->len; }
+void FstFile::split(size_t depth, std::vector<FstTask>& tasks, FstSink& shallow, std::vector<uint8_t>& bytes_seen) const {
+    const Mapped& m = impl_->m;
+    if (m.size == 32) return;
+    if (depth > sizeof(FstTask().prefix)) depth = sizeof(FstTask().prefix);
+    const uint64_t node_limit = m.size - 16;
+    std::vector<uint8_t> key;
+    Node r(m.data, impl_->root, node_limit);
+    if (r.final_) shallow.on_key(key.data(), 0, r.final_output);
+    walk(m.data, node_limit, impl_->root, 0, key, shallow, depth, &tasks, &bytes_seen);
+}
+void FstFile::stream(const FstTask& t, FstSink& sink) const {
+    const Mapped& m = impl_->m;
+    std::vector<uint8_t> key(t.prefix, t.prefix + t.plen);
+    walk(m.data, m.size - 16, t.addr, t.out, key, sink, 0, nullptr, nullptr);
 }
 
 }  // namespace umgap

@@ -144,6 +144,26 @@ struct FstSink {
     virtual ~FstSink() {}
 };
 void fst_stream_file(const char* path, FstSink& sink, uint64_t* n_keys_footer);
+// The same walk cut into independent subtrees (fst_load.cu walks them on several threads).
+struct FstTask {
+    uint64_t addr, out;   // node below the prefix, outputs summed along the prefix
+    uint8_t prefix[7];
+    uint8_t plen;
+};
+class FstFile {
+  public:
+    explicit FstFile(const char* path);
+    ~FstFile();
+    uint64_t len() const;
+    void split(size_t depth, std::vector<FstTask>& tasks, FstSink& shallow, std::vector<uint8_t>& bytes_seen) const;
+    void stream(const FstTask& t, FstSink& sink) const;
+    FstFile(const FstFile&) = delete;
+    FstFile& operator=(const FstFile&) = delete;
+
+  private:
+    struct Impl;
+    Impl* impl_;
+};
 uint64_t fst_file_len(const char* path);  // number of keys recorded in the footer
 
 }  // namespace umgap

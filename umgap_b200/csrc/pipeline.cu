@@ -1657,6 +1657,24 @@ static void raise_dev_error(const DevError& e) {
     if (e.flag) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", e.taxon);
 }
 
+namespace umgap {
+// The workspaces the pack and classify kernels of a batch of this size take from the handle, allocated now: a launch
+// path that allocates synchronises the device, which the exchange step (exchange.cu) must never do inside a batch.
+void pipeline_reserve(const umgap_index* idx, uint64_t nreads, uint64_t total_nt) {
+    use_device(idx->device);
+    idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
+    idx->ws.get(WS_ERR, sizeof(DevError));
+    idx->ws.get(WS_LONG, (128 + nreads) * sizeof(uint32_t));
+}
+// Raises the error the classify kernel of the last *_dev call left behind (Unknown Taxon ID); the caller has synchronised.
+void pipeline_take_error(const umgap_index* idx) {
+    use_device(idx->device);
+    DevError he;
+    UMGAP_CUDA(cudaMemcpy(&he, idx->ws.get(WS_ERR, sizeof(DevError)), sizeof he, cudaMemcpyDeviceToHost));
+    raise_dev_error(he);
+}
+}  // namespace umgap
+
 extern "C" {
 
 int umgap_index_set_probe_region(umgap_index* idx, uint64_t bytes) {
@@ -1694,27 +1712,39 @@ int umgap_kernel_timing(int enable) {
     return UMGAP_OK;
 }
 
-int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
-                       uint64_t* classify_launches) {
+int umgap_kernel_times_ex(double* ms_out, uint64_t* launches_out, int nkinds) {
     return guarded([&] {
-        double ms[2] = {0, 0};
-        uint64_t cnt[2] = {0, 0};
+        double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint64_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         std::lock_guard<std::mutex> lk(g_timing_mu);
         for (TimedLaunch& t : g_launches) {
             UMGAP_CUDA(cudaEventSynchronize(t.b));
             float e = 0;
             UMGAP_CUDA(cudaEventElapsedTime(&e, t.a, t.b));
-            ms[t.kind] += e;
-            cnt[t.kind]++;
+            ms[t.kind & 7] += e;
+            cnt[t.kind & 7]++;
             g_event_pool[t.dev].push_back(t.a);
             g_event_pool[t.dev].push_back(t.b);
         }
         g_launches.clear();
-        if (lookup_ms) *lookup_ms = ms[0];
-        if (lookup_launches) *lookup_launches = cnt[0];
-        if (classify_ms) *classify_ms = ms[1];
-        if (classify_launches) *classify_launches = cnt[1];
+        for (int i = 0; i < nkinds && i < 8; ++i) {
+            if (ms_out) ms_out[i] = ms[i];
+            if (launches_out) launches_out[i] = cnt[i];
+        }
     });
+}
+
+int umgap_kernel_times(double* lookup_ms, uint64_t* lookup_launches, double* classify_ms,
+                       uint64_t* classify_launches) {
+    double ms[8];
+    uint64_t cnt[8];
+    const int rc = umgap_kernel_times_ex(ms, cnt, 8);
+    if (rc != UMGAP_OK) return rc;
+    if (lookup_ms) *lookup_ms = ms[0];
+    if (lookup_launches) *lookup_launches = cnt[0];
+    if (classify_ms) *classify_ms = ms[1];
+    if (classify_launches) *classify_launches = cnt[1];
+    return UMGAP_OK;
 }
 
 void umgap_pipeline_opts_default(umgap_pipeline_opts* o) {
