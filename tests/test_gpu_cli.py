@@ -200,6 +200,16 @@ def test_fused_cli_block_parser_edge_cases(files):
         assert p.returncode == 0, p.stderr.decode()
         assert p.stdout.decode() == want_odd, block
     assert want.count(">") >= 80
+    # the same stream from a regular file: the command maps it and cuts the blocks in place
+    (d / "edge.fa").write_text(text)
+    for block in (None, "16", "300", "70000"):
+        env = dict(os.environ)
+        if block:
+            env["UMGAP_CLI_BLOCK"] = block
+        with open(d / "edge.fa", "rb") as fh:
+            p = subprocess.run([UMGAP] + args, stdin=fh, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout.decode() == want, ("file", block)
     rc, out, err = run(args, "ACGT\n>r\nACGT\n")
     assert rc == 1 and "Expected > at beginning of fasta header." in err
     rc, out, err = run(args, "")

@@ -304,3 +304,115 @@ def test_pack_reads_host_packer():
     with pytest.raises(capi.UmgapError) as e:
         capi.pack_reads(nt, entries=np.zeros(3, dtype=np.uint64))
     assert e.value.code == -5   # UMGAP_ERR_CAPACITY
+
+
+def test_cli_buildindex_printindex_roundtrip(built, tmp_path):
+    """`umgap buildindex` (buildindex.rs:32-48) and `umgap printindex` (printindex.rs:38-51) on the host: the doc example
+    round trip, the bytes of the doc example against the oracle's codec, and a larger TSV written by the product's
+    writer and read back by the three independent readers (product, oracle/fstv2.py, oracle/c)."""
+    import random
+    from oracle import cport, fstv2
+    tsv = b"AAAAA\t2759\nBBBBBB\t9153\n"
+    fst = tmp_path / "tiny.index"
+    p = subprocess.run([UMGAP, "buildindex"], input=tsv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0
+    fst.write_bytes(p.stdout)
+    assert p.stdout == fstv2.build([(b"AAAAA", 2759), (b"BBBBBB", 9153)])
+    rc, out, err = _run(["printindex", str(fst)])
+    assert rc == 0 and out == tsv.decode(), err
+    rng = random.Random(3)
+    items = {}
+    for _ in range(30000):
+        L = rng.choice([1, 2, 3, 5, 9, 9, 9, 9, 15, 40])
+        items[bytes(rng.choice(b"ACDEFGHIKLMNPQRSTVWY") for _ in range(L))] = rng.choice([0, 1, 7, 300, 2 ** 31, 2 ** 40 + 3, 2759])
+    for a in range(33, 127):
+        if a != ord('"'):
+            items[bytes([ord("Z"), a])] = a      # a node with more than 32 transitions
+    items = sorted(items.items())
+    big_tsv = b"".join(k + b"\t" + str(v).encode() + b"\n" for k, v in items)
+    p = subprocess.run([UMGAP, "buildindex"], input=big_tsv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    big = tmp_path / "big.index"
+    big.write_bytes(p.stdout)
+    assert list(fstv2.Fst(p.stdout).stream()) == items
+    img = cport.FstImage(p.stdout)
+    assert all(img.get(k) == v for k, v in rng.sample(items, 3000))
+    rc, out, err = _run(["printindex", str(big)])
+    assert rc == 0 and out.encode() == big_tsv, err
+    # files of the oracle's two writers (fstv2.build minimises: shared suffixes) through printindex
+    for data in (fstv2.build(items), cport.fst_build([k for k, _ in items], [v for _, v in items])):
+        big.write_bytes(data)
+        rc, out, _ = _run(["printindex", str(big)])
+        assert rc == 0 and out.encode() == big_tsv
+    rc, _, err = _run(["buildindex"], b"B\t1\nA\t2\n")
+    assert rc == 1 and "out of order" in err
+    rc, _, err = _run(["buildindex"], b"A\t1\nA\t2\n")
+    assert rc == 1 and "duplicate" in err
+    rc, _, err = _run(["buildindex"], b"A 1\n")
+    assert rc == 1
+
+
+def test_cli_reporting_commands_match_oracle(built, tmp_path):
+    """snaptaxon (snaptaxon.rs:66-108), taxa2freq (taxa2freq.rs:86-169) and bestof (bestof.rs:50-79) against their
+    line-by-line restatements (oracle/reporting.py) on a synthetic taxonomy."""
+    import random
+    from oracle import reporting as orep
+    from oracle.taxonomy import Taxonomy as OTaxonomy, format_taxon
+    import datagen
+    taxa = datagen.make_taxonomy(300, seed=5)
+    otax = OTaxonomy(taxa)
+    tfile = tmp_path / "taxons.tsv"
+    tfile.write_bytes(("\n".join(format_taxon(t) for t in taxa) + "\n").encode("latin-1"))
+    rng = random.Random(9)
+    ids = [t[0] for t in taxa]
+    lines = []
+    for i in range(400):
+        if i % 7 == 0:
+            lines.append(f">read{i}")
+        lines.append(str(rng.choice(ids)))
+    text = "\n".join(lines) + "\n"
+    picks = rng.sample(ids, 5)
+    for flags, kw in ((["-r", "genus"], dict(rank="genus")), (["-r", "species", "-i"], dict(rank="species", invalid=True)),
+                      (["-t", str(picks[0]), "-t", str(picks[1])], dict(taxons=picks[:2])),
+                      (["-r", "family", "-t", str(picks[2])], dict(rank="family", taxons=picks[2:3])), ([], {})):
+        rc, out, err = _run(["snaptaxon", str(tfile)] + flags, text.encode())
+        assert rc == 0, err
+        assert out == orep.snaptaxon_text(text, otax, **kw), flags
+    rc, _, err = _run(["snaptaxon", str(tfile), "-r", "no rank"], text.encode())
+    assert rc == 1
+    rc, _, err = _run(["snaptaxon", str(tfile), "-r", "genus"], b"notanumber\n")
+    assert rc == 1 and "invalid digit" in err
+    # taxa2freq: stdin and two files; rows ordered by descending total, equal totals in any order (HashMap order there)
+    other = "".join(str(rng.choice(ids)) + "\n" for _ in range(300))
+    (tmp_path / "a.txt").write_text(text)
+    (tmp_path / "b.txt").write_text(other)
+    for rank, minf in (("species", 1), ("genus", 0), ("phylum", 3)):
+        for files, inputs in (([], [text]), ([str(tmp_path / "a.txt"), str(tmp_path / "b.txt")], [text, other])):
+            rc, out, err = _run(["taxa2freq", "-r", rank, "-f", str(minf), str(tfile)] + files, text.encode() if not files else b"")
+            assert rc == 0, err
+            rows, _ = orep.taxa2freq_rows(inputs, otax, rank, minf)
+            got = out.split("\n")
+            assert got[0] == "taxon id,taxon name," + (",".join(files) if files else "stdin") and got[-1] == ""
+            got_rows = [g.split(",") for g in got[1:-1]]
+            assert sorted((int(g[0]), g[1], [int(x) for x in g[2:]]) for g in got_rows) == sorted(rows)
+            totals = [sum(int(x) for x in g[2:]) for g in got_rows]
+            assert totals == sorted(totals, reverse=True)
+    rc, _, err = _run(["taxa2freq", "-r", "no rank", str(tfile)], b"")
+    assert rc == 1 and "Snap to an actual rank." in err
+    # bestof: groups of six frame records (and of three), ids 0 and 1 do not count, ties go to the later record
+    recs = []
+    for i in range(50):
+        for fr in range(6):
+            n = rng.choice([0, 1, 3, 3, 8])
+            recs.append((f"r{i}|{fr}", [str(rng.choice([0, 1, 1, rng.choice(ids)])) for _ in range(n)]))
+    btext = "".join(f">{h}\n" + "".join(x + "\n" for x in s) for h, s in recs)
+    for frames in (6, 3, 2):
+        rc, out, err = _run(["bestof", "-f", str(frames)], btext.encode())
+        assert rc == 0, err
+        assert out == orep.bestof_text(btext, frames), frames
+    # the doc example of bestof.rs:24-41 (frames 1, 2, 3, 1R, 2R, 3R of one read): frame 1 wins
+    doc = (">header1|1\n" + "\n".join("9606 9606 2759 9606 9606 9606 9606 9606 9606 9606 8287".split()) + "\n>header1|2\n" +
+           "\n".join("2026807 888268 186802 1598 1883".split()) + "\n>header1|3\n1883\n>header1|1R\n" +
+           "\n".join("27342 2759 155619 1133106 38033 2".split()) + "\n>header1|2R\n>header1|3R\n2951\n")
+    rc, out, _ = _run(["bestof"], doc.encode())
+    assert rc == 0 and out == ">header1|1\n" + "\n".join("9606 9606 2759 9606 9606 9606 9606 9606 9606 9606 8287".split()) + "\n"

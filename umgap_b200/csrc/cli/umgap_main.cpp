@@ -8,12 +8,20 @@
 //   taxa2agg       src/commands/taxa2agg.rs:61-183       -> umgap_taxonomy_load + umgap_aggregate
 //   uniq           src/commands/uniq.rs:41-84            (host only)
 //   fastq2fasta    src/commands/fastq2fasta.rs:55-84     (host only)
-//   classify       the fused preset pipeline (extension) -> umgap_classify_reads
+//   buildindex     src/commands/buildindex.rs:32-48      -> umgap_fst_writer_* (host only)
+//   printindex     src/commands/printindex.rs:38-51      -> umgap_fst_stream (host only)
+//   snaptaxon      src/commands/snaptaxon.rs:66-108      (host only)
+//   taxa2freq      src/commands/taxa2freq.rs:86-169      (host only)
+//   bestof         src/commands/bestof.rs:50-79          (host only)
+//   classify       the fused preset pipeline (extension) -> umgap_classify_reads, one replica per GPU
 //
 // Stream rules follow src/io/fasta.rs:30-67,164-180.  Errors go to stderr as `Error: ...`, exit 1
 // (quick_main!, src/main.rs:8).  The host does parsing and formatting only; every stage's
 // arithmetic runs on the GPU through the C ABI.
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
+#include <sys/stat.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -785,6 +793,7 @@ struct Batch {
 
 struct Job {
     std::vector<char> text;
+    const char* view = nullptr;  // the block's bytes: text.data(), or a window of the memory-mapped input file
     size_t len = 0;
     uint64_t seq = 0;
     Batch batch;
@@ -1005,7 +1014,7 @@ int cmd_classify(int argc, char** argv) {
             Job* j;
             while (parse_q.pop(j)) {
                 try {
-                    parse_block(j->text.data(), j->text.data() + j->len, delim, span, &j->batch);
+                    parse_block(j->view, j->view + j->len, delim, span, &j->batch);
                     classify_q.push(j);
                 } catch (const std::exception& e) {
                     set_error(e.what());
@@ -1071,49 +1080,89 @@ int cmd_classify(int argc, char** argv) {
         }
     });
 
-    // reader: this thread
+    // reader: this thread.  A regular file on stdin is mapped and cut in place (the parser threads read the file's pages
+    // themselves); anything else (a pipe) is read block by block into the jobs' buffers.
     try {
-        std::vector<char> carry;  // what the previous block left behind its cut
-        bool eof = false, first = true;
         uint64_t seq = 0;
-        while (!eof || !carry.empty()) {
-            Job* j;
-            if (!free_q.pop(j)) break;  // closed: an error elsewhere
-            if (j->text.size() < block + carry.size()) j->text.resize(block + carry.size());
-            memcpy(j->text.data(), carry.data(), carry.size());
-            size_t have = carry.size();
-            carry.clear();
-            size_t cut = 0;
-            for (;;) {
-                while (!eof && have < j->text.size()) {
-                    const ssize_t n = read(0, j->text.data() + have, j->text.size() - have);
-                    if (n < 0) {
-                        if (errno == EINTR) continue;
-                        fail("failed reading input");
+        struct stat sb;
+        const char* map = nullptr;
+        size_t map_len = 0;
+        if (fstat(0, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0 && !getenv("UMGAP_CLI_NO_MMAP")) {
+            const off_t at = lseek(0, 0, SEEK_CUR);
+            void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, 0, 0);
+            if (m != MAP_FAILED && at >= 0 && at < sb.st_size) {
+                map = (const char*)m + at;
+                map_len = (size_t)(sb.st_size - at);
+            }
+        }
+        if (map) {
+            if (map[0] != '>') fail("Expected > at beginning of fasta header.");  // fasta.rs:44-49
+            size_t pos = 0;
+            while (pos < map_len) {
+                size_t want = block, cut = 0;
+                for (;;) {
+                    if (pos + want >= map_len) {
+                        cut = map_len - pos;
+                        break;
                     }
-                    if (n == 0) eof = true;
-                    have += (size_t)n;
+                    cut = find_cut(map + pos, want, delim, span);
+                    if (cut) break;
+                    want *= 2;  // one group larger than the block
                 }
-                if (first && have) {
-                    if (j->text[0] != '>') fail("Expected > at beginning of fasta header.");  // fasta.rs:44-49
-                    first = false;
-                }
-                if (eof) {
-                    cut = have;
-                    break;
-                }
-                cut = find_cut(j->text.data(), have, delim, span);
-                if (cut) break;
-                j->text.resize(j->text.size() * 2);  // one group larger than the block: read on
+                Job* j;
+                if (!free_q.pop(j)) break;
+                j->view = map + pos;
+                j->len = cut;
+                j->seq = seq++;
+                parse_q.push(j);
+                pos += cut;
             }
-            carry.assign(j->text.data() + cut, j->text.data() + have);
-            j->len = cut;
-            if (cut == 0) {
-                free_q.push(j);
-                continue;
+        } else {
+#ifdef F_SETPIPE_SZ
+            (void)fcntl(0, F_SETPIPE_SZ, 1 << 20);  // a larger pipe buffer, where stdin is a pipe and the kernel allows it
+#endif
+            std::vector<char> carry;  // what the previous block left behind its cut
+            bool eof = false, first = true;
+            while (!eof || !carry.empty()) {
+                Job* j;
+                if (!free_q.pop(j)) break;  // closed: an error elsewhere
+                if (j->text.size() < block + carry.size()) j->text.resize(block + carry.size());
+                memcpy(j->text.data(), carry.data(), carry.size());
+                size_t have = carry.size();
+                carry.clear();
+                size_t cut = 0;
+                for (;;) {
+                    while (!eof && have < j->text.size()) {
+                        const ssize_t n = read(0, j->text.data() + have, j->text.size() - have);
+                        if (n < 0) {
+                            if (errno == EINTR) continue;
+                            fail("failed reading input");
+                        }
+                        if (n == 0) eof = true;
+                        have += (size_t)n;
+                    }
+                    if (first && have) {
+                        if (j->text[0] != '>') fail("Expected > at beginning of fasta header.");  // fasta.rs:44-49
+                        first = false;
+                    }
+                    if (eof) {
+                        cut = have;
+                        break;
+                    }
+                    cut = find_cut(j->text.data(), have, delim, span);
+                    if (cut) break;
+                    j->text.resize(j->text.size() * 2);  // one group larger than the block: read on
+                }
+                carry.assign(j->text.data() + cut, j->text.data() + have);
+                j->view = j->text.data();
+                j->len = cut;
+                if (cut == 0) {
+                    free_q.push(j);
+                    continue;
+                }
+                j->seq = seq++;
+                parse_q.push(j);
             }
-            j->seq = seq++;
-            parse_q.push(j);
         }
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -1222,11 +1271,371 @@ void usage(FILE* f) {
           "    uniq             Joins consecutive FASTA records with the same header\n"
           "    taxa2agg         Aggregates taxon ids per record (lca*, hybrid, mrtl)\n"
           "    fastq2fasta      Interleaves FASTQ files into FASTA\n"
-          "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process\n"
+          "    buildindex       Writes an fst index from sorted `key<TAB>taxon id` lines\n"
+          "    printindex       Prints the key/value pairs of an fst index\n"
+          "    snaptaxon        Snaps taxon ids to a rank or to listed taxa\n"
+          "    taxa2freq        Counts taxon ids per ranked ancestor (CSV)\n"
+          "    bestof           Picks the best record of every group of frames\n"
+          "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process [--gpus N]\n"
           "    classify-peptides  prot2tryp2lca | uniq | taxa2agg in one process\n", f);
 }
 
+// Lines of a stream without their line ends, as (pointer, length) views that stay valid until the next call.
+class BlockLines {
+  public:
+    explicit BlockLines(FILE* f) : src_(f) {}
+    bool next(const char*& ls, size_t& ll) {
+        if (!src_.next(line_)) return false;
+        ls = line_.data();
+        ll = line_.size();
+        return true;
+    }
+
+  private:
+    LineSource src_;
+    std::string line_;
+};
+
+// ---- buildindex / printindex (host only) ----------------------------------------------------------------------------
+// buildindex.rs:32-48: TSV `key \t taxon id` on stdin, ordered by key, to an fst Map on stdout.
+int cmd_buildindex(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {});
+    if (!a.pos.empty()) fail("Found argument '" + a.pos[0] + "' which wasn't expected, or isn't valid in this context");
+    umgap_fst_writer* w = nullptr;
+    check(umgap_fst_writer_open(nullptr, &w));
+    try {
+        BlockLines lines(stdin);
+        const char* ls;
+        size_t ll;
+        while (lines.next(ls, ll)) {
+            const char* tab = (const char*)memchr(ls, '\t', ll);
+            if (!tab || memchr(tab + 1, '\t', ll - (tab + 1 - ls))) fail("CSV deserialize error: expected two tab-separated fields (key, taxon id)");
+            const uint64_t v = parse_usize(std::string(tab + 1, ls + ll - (tab + 1)));
+            check(umgap_fst_writer_insert(w, (const uint8_t*)ls, (size_t)(tab - ls), v));
+        }
+    } catch (...) {
+        umgap_fst_writer_abort(w);
+        throw;
+    }
+    check(umgap_fst_writer_finish(w));
+    return 0;
+}
+
+// printindex.rs:38-51: every key of the index with its value, TSV.
+int cmd_printindex(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {});
+    if (a.pos.size() != 1) fail("The following required arguments were not provided:\n    <fst-file>");
+    std::string out;
+    struct Ctx {
+        std::string* out;
+    } ctx{&out};
+    check(umgap_fst_stream(a.pos[0].c_str(),
+                           [](const uint8_t* key, size_t len, uint64_t value, void* user) -> int {
+                               std::string& o = *((Ctx*)user)->out;
+                               // csv::Writer quotes a field that holds the delimiter, a quote or a line break
+                               bool quote = len == 0;
+                               for (size_t i = 0; i < len; ++i) quote |= key[i] == '\t' || key[i] == '"' || key[i] == '\n' || key[i] == '\r';
+                               if (quote) {
+                                   o += '"';
+                                   for (size_t i = 0; i < len; ++i) {
+                                       if (key[i] == '"') o += '"';
+                                       o += (char)key[i];
+                                   }
+                                   o += '"';
+                               } else {
+                                   o.append((const char*)key, len);
+                               }
+                               o += '\t';
+                               o += std::to_string(value);
+                               o += '\n';
+                               if (o.size() > (1u << 20)) {
+                                   if (fwrite(o.data(), 1, o.size(), stdout) != o.size()) return 1;
+                                   o.clear();
+                               }
+                               return 0;
+                           },
+                           &ctx, nullptr));
+    put(stdout, out);
+    return 0;
+}
+
+// ---- reporting commands on the host: snaptaxon, taxa2freq, bestof ---------------------------------------------------
+// The taxonomy as these commands use it (taxon.rs:89-163, 224-301): the TSV, the children map, and filter_ancestors.
+struct HostTaxonomy {
+    struct Taxon {
+        uint64_t id, parent;
+        int rank;
+        bool valid;
+        std::string name;
+    };
+    std::vector<Taxon> taxa;
+    std::vector<int64_t> row_of;  // by id; -1 = no such taxon
+    uint64_t root = 0, max_id = 0;
+
+    static int rank_index(const std::string& s) {
+        static const char* names[] = {"no rank", "superkingdom", "domain", "realm", "kingdom", "subkingdom", "superphylum", "phylum",
+                                      "subphylum", "superclass", "class", "subclass", "infraclass", "superorder", "order", "suborder",
+                                      "infraorder", "parvorder", "superfamily", "family", "subfamily", "tribe", "subtribe", "genus",
+                                      "subgenus", "species group", "species subgroup", "species", "subspecies", "varietas", "forma", "strain"};
+        for (int i = 0; i < 32; ++i)
+            if (s == names[i]) return i;
+        return -1;
+    }
+    explicit HostTaxonomy(const std::string& path) {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) fail("Failed opening taxon file.");
+        BlockLines lines(f);
+        const char* ls;
+        size_t ll;
+        while (lines.next(ls, ll)) {
+            std::string line(ls, ll);
+            while (!line.empty() && isspace((unsigned char)line.back())) line.pop_back();  // trim_end (taxon.rs:89)
+            std::vector<std::string> col;
+            size_t p = 0;
+            for (;;) {
+                const size_t t = line.find('\t', p);
+                col.push_back(line.substr(p, t == std::string::npos ? std::string::npos : t - p));
+                if (t == std::string::npos) break;
+                p = t + 1;
+            }
+            // trim_end also eats a trailing "\x00"?  No: NUL is not whitespace; the valid byte survives it.
+            if (col.size() != 5) {
+                fclose(f);
+                fail("Taxon requires five fields");
+            }
+            Taxon t;
+            t.id = parse_usize(col[0]);
+            t.name = col[1];
+            t.rank = rank_index(col[2]);
+            if (t.rank < 0) {
+                fclose(f);
+                fail("Matching variant not found");
+            }
+            t.parent = parse_usize(col[3]);
+            if (col[4] == "\x01") t.valid = true;
+            else if (col[4] == std::string(1, '\0')) t.valid = false;
+            else {
+                fclose(f);
+                fail("Couldn't parse the valid byte");
+            }
+            taxa.push_back(t);
+        }
+        fclose(f);
+        if (taxa.empty()) fail("There's no root!");
+        for (const Taxon& t : taxa) max_id = std::max(max_id, t.id);
+        row_of.assign(max_id + 1, -1);
+        std::vector<bool> is_child(max_id + 1, false);
+        for (size_t i = 0; i < taxa.size(); ++i) {
+            row_of[taxa[i].id] = (int64_t)i;
+            if (taxa[i].id != taxa[i].parent) is_child[taxa[i].id] = true;
+        }
+        // TaxonTree::new (taxon.rs:224-247): the ids never listed with another parent; exactly one may remain
+        int nroots = 0;
+        std::vector<bool> seen(max_id + 1, false);
+        for (const Taxon& t : taxa)
+            if (!is_child[t.id] && !seen[t.id]) {
+                seen[t.id] = true;
+                if (nroots++ == 0) root = t.id;
+            }
+        if (nroots > 1) fail("More than one root!");
+        if (nroots == 0) fail("There's no root!");
+    }
+    // TaxonTree::filter_ancestors (taxon.rs:251-286): by id, the nearest ancestor-or-self that passes; the walk starts at
+    // the root with Some(root); ids the walk does not reach stay None (-1).
+    template <class F>
+    std::vector<int64_t> filter_ancestors(F pass) const {
+        std::vector<std::vector<uint64_t>> children(max_id + 1);
+        for (const Taxon& t : taxa)
+            if (t.id != t.parent && t.parent <= max_id) children[t.parent].push_back(t.id);
+        std::vector<int64_t> out(max_id + 1, -1);
+        std::vector<std::pair<uint64_t, int64_t>> stack{{root, (int64_t)root}};
+        std::vector<bool> done(max_id + 1, false);
+        while (!stack.empty()) {
+            auto [cur, anc] = stack.back();
+            stack.pop_back();
+            if (done[cur]) continue;
+            done[cur] = true;
+            const int64_t mine = pass(cur) ? (int64_t)cur : anc;
+            out[cur] = mine;
+            for (uint64_t c : children[cur]) stack.push_back({c, mine});
+        }
+        return out;
+    }
+};
+
+// snaptaxon.rs:66-108
+int cmd_snaptaxon(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'r', "rank", true}, {'t', "taxons", true}, {'i', "invalid", false}});
+    // `-t 1239 2`: structopt's Vec option takes every following value, so bare numbers after -t are taxa as well
+    std::vector<uint64_t> wanted;
+    if (a.has("taxons"))
+        for (const std::string& v : a.opt["taxons"]) wanted.push_back(parse_usize(v));
+    std::string taxon_file;
+    for (const std::string& p : a.pos) {
+        const bool numeric = !p.empty() && p.find_first_not_of("0123456789") == std::string::npos;
+        if (numeric && a.has("taxons") && !taxon_file.empty()) wanted.push_back(parse_usize(p));
+        else if (taxon_file.empty()) taxon_file = p;
+        else fail("Found argument '" + p + "' which wasn't expected, or isn't valid in this context");
+    }
+    if (taxon_file.empty()) fail("The following required arguments were not provided:\n    <taxon-file>");
+    int rank = -1;
+    if (a.has("rank")) {
+        rank = HostTaxonomy::rank_index(a.get("rank", ""));
+        if (rank < 0) fail("'" + a.get("rank", "") + "' isn't a valid value for '--rank <rank>'");
+        if (rank == 0) fail("Snap to an actual rank.");
+    }
+    HostTaxonomy tax(taxon_file);
+    const bool invalid = a.has("invalid");
+    const std::vector<int64_t> snap = tax.filter_ancestors([&](uint64_t tid) {
+        if (std::find(wanted.begin(), wanted.end(), tid) != wanted.end()) return true;
+        const HostTaxonomy::Taxon& t = tax.taxa[tax.row_of[tid]];
+        return (invalid || t.valid) && rank >= 0 && t.rank == rank;
+    });
+    BlockLines lines(stdin);
+    const char* ls;
+    size_t ll;
+    std::string out;
+    while (lines.next(ls, ll)) {
+        if (ll && ls[0] == '>') {
+            out.append(ls, ll);
+        } else {
+            const uint64_t t = parse_usize(std::string(ls, ll));
+            if (t >= snap.size()) fail("index out of bounds: the len is " + std::to_string(snap.size()) + " but the index is " + std::to_string(t));
+            out += std::to_string(snap[t] < 0 ? 0 : snap[t]);
+        }
+        out += '\n';
+        if (out.size() > (1u << 20)) {
+            put(stdout, out);
+            out.clear();
+        }
+    }
+    put(stdout, out);
+    return 0;
+}
+
+// taxa2freq.rs:86-169
+int cmd_taxa2freq(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'r', "rank", true}, {'f', "frequency", true}});
+    if (a.pos.empty()) fail("The following required arguments were not provided:\n    <taxon-file>");
+    const int rank = HostTaxonomy::rank_index(a.get("rank", "species"));
+    if (rank < 0) fail("'" + a.get("rank", "") + "' isn't a valid value for '--rank <rank>'");
+    if (rank == 0) fail("Snap to an actual rank.");
+    const uint64_t min_frequency = parse_usize(a.get("frequency", "1"));
+    HostTaxonomy tax(a.pos[0]);
+    const std::vector<std::string> files(a.pos.begin() + 1, a.pos.end());
+    const size_t ncol = std::max<size_t>(1, files.size());
+    const std::vector<int64_t> snap = tax.filter_ancestors([&](uint64_t tid) { return tax.taxa[tax.row_of[tid]].rank == rank; });
+    std::string out = "taxon id,taxon name";
+    if (files.empty()) out += ",stdin";
+    for (const std::string& f : files) out += "," + f;
+    out += '\n';
+    std::map<uint64_t, std::vector<uint64_t>> counts;
+    auto count_file = [&](FILE* f, size_t col) {
+        BlockLines lines(f);
+        const char* ls;
+        size_t ll;
+        while (lines.next(ls, ll)) {
+            // lines that do not parse as a taxon id (FASTA headers) are skipped (taxa2freq.rs:160)
+            size_t i = (ll && ls[0] == '+') ? 1 : 0;
+            if (i >= ll) continue;
+            uint64_t v = 0;
+            bool ok = true;
+            for (; i < ll && ok; ++i) {
+                const unsigned d = (unsigned)(ls[i] - '0');
+                ok = d <= 9 && v <= (UINT64_MAX - d) / 10;
+                v = v * 10 + d;
+            }
+            if (!ok) continue;
+            if (v >= snap.size()) fail("index out of bounds: the len is " + std::to_string(snap.size()) + " but the index is " + std::to_string(v));
+            std::vector<uint64_t>& row = counts[snap[v] < 0 ? 0 : (uint64_t)snap[v]];
+            if (row.empty()) row.assign(ncol, 0);
+            row[col]++;
+        }
+    };
+    if (files.empty()) {
+        count_file(stdin, 0);
+    } else {
+        for (size_t i = 0; i < files.size(); ++i) {
+            FILE* f = fopen(files[i].c_str(), "rb");
+            if (!f) fail("No such file or directory (os error 2)");
+            count_file(f, i);
+            fclose(f);
+        }
+    }
+    // rows by descending sum; the reference sorts a HashMap's entries by the sum (stable) and prints them reversed, so
+    // rows with equal sums come in hash order there -- here by descending taxon id, a fixed choice among those orders
+    std::vector<std::pair<uint64_t, std::vector<uint64_t>>> rows(counts.begin(), counts.end());
+    auto total = [](const std::vector<uint64_t>& r) {
+        uint64_t s = 0;
+        for (uint64_t x : r) s += x;
+        return s;
+    };
+    std::stable_sort(rows.begin(), rows.end(), [&](const auto& x, const auto& y) { return total(x.second) < total(y.second); });
+    for (size_t i = rows.size(); i-- > 0;) {
+        const uint64_t tid = rows[i].first;
+        if (tid > tax.max_id || tax.row_of[tid] < 0) fail("LCA taxon id not in taxon list. Check compatibility with index.");
+        if (total(rows[i].second) > min_frequency) {  // strictly greater, as written (taxa2freq.rs:141)
+            const HostTaxonomy::Taxon& t = tax.taxa[tax.row_of[tid]];
+            out += std::to_string(t.id) + "," + t.name;
+            for (uint64_t c : rows[i].second) out += "," + std::to_string(c);
+            out += '\n';
+        }
+    }
+    put(stdout, out);
+    return 0;
+}
+
+// bestof.rs:50-79: of every `frames` consecutive records the one with the most ids other than 0 and 1 (the last of
+// equal maxima, Iterator::max_by_key).  As written, a group is emitted when its last record arrives and only the
+// frames - 1 records before it are candidates: the record that completes the group is read but never pushed.
+int cmd_bestof(int argc, char** argv) {
+    Args a = parse(argc, argv, 2, {{'f', "frames", true}});
+    const uint64_t frames = parse_usize(a.get("frames", "6"));
+    if (frames == 0) fail("attempt to subtract with overflow");
+    FastaReader rd(stdin, false);
+    std::vector<Record> chunk;
+    Record r;
+    std::string out;
+    while (rd.next(r)) {
+        if (chunk.size() < frames - 1) {
+            chunk.push_back(r);
+            continue;
+        }
+        if (chunk.empty()) fail("called `Option::unwrap()` on a `None` value");  // -f 1: max_by_key of nothing
+        size_t best = 0, best_n = 0;
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            size_t n = 0;
+            for (const std::string& tid : chunk[i].seq) {
+                // tid.parse::<TaxonId>().unwrap_or(0), then everything but 0 and 1 counts
+                bool ok = !tid.empty();
+                size_t k = (ok && tid[0] == '+') ? 1 : 0;
+                ok = ok && k < tid.size();
+                unsigned __int128 v = 0;
+                for (; ok && k < tid.size(); ++k) {
+                    ok = tid[k] >= '0' && tid[k] <= '9';
+                    v = v * 10 + (unsigned)(tid[k] - '0');
+                    if (v > (unsigned __int128)UINT64_MAX) ok = false;
+                }
+                if (ok && v != 0 && v != 1) ++n;
+            }
+            if (n >= best_n) {
+                best = i;
+                best_n = n;
+            }
+        }
+        write_record(out, chunk[best].header, chunk[best].seq, "\n", false);
+        chunk.clear();
+        if (out.size() > (1u << 20)) {
+            put(stdout, out);
+            out.clear();
+        }
+    }
+    put(stdout, out);
+    return 0;
+}
+
 }  // namespace
+
 
 int main(int argc, char** argv) {
     try {
@@ -1250,6 +1659,11 @@ int main(int argc, char** argv) {
         if (sub == "taxa2agg") return cmd_taxa2agg(argc, argv);
         if (sub == "uniq") return cmd_uniq(argc, argv);
         if (sub == "fastq2fasta") return cmd_fastq2fasta(argc, argv);
+        if (sub == "buildindex") return cmd_buildindex(argc, argv);
+        if (sub == "printindex") return cmd_printindex(argc, argv);
+        if (sub == "snaptaxon") return cmd_snaptaxon(argc, argv);
+        if (sub == "taxa2freq") return cmd_taxa2freq(argc, argv);
+        if (sub == "bestof") return cmd_bestof(argc, argv);
         if (sub == "classify") return cmd_classify(argc, argv);
         if (sub == "classify-peptides") return cmd_classify_peptides(argc, argv);
         fail("Found argument '" + sub + "' which wasn't expected, or isn't valid in this context");

@@ -2,6 +2,7 @@
 // fst::Map::from_path / from_bytes at prot2kmer2lca.rs:109-114 and prot2tryp2lca.rs:89-94).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -320,13 +321,21 @@ extern "C" int umgap_index_load_fst_shard(const char* path, int k, int device, d
         int threads = te ? atoi(te) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
         if (n < (1u << 16)) threads = std::min(threads, 2);
         bool done = false;
+        const bool verbose = getenv("UMGAP_LOAD_VERBOSE") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         if (threads > 1) {
             TableBuilder b;
             try {
+                const double t0 = now();
                 b.begin(idx, n, load_factor);
+                const double t1 = now();
                 done = load_parallel(path, b, idx, threads);
+                const double t2 = now();
                 if (done) b.finish();
                 else b.abort();
+                if (verbose)
+                    fprintf(stderr, "umgap_index_load_fst: %llu keys, %d threads: table allocation %.3f s, walk + upload + insert %.3f s, "
+                            "overflow levels + statistics %.3f s\n", (unsigned long long)n, threads, t1 - t0, t2 - t1, now() - t2);
             } catch (...) {
                 b.abort();
                 throw;
