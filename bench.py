@@ -388,14 +388,14 @@ def _sharded_rank0(ctx, gidx_repl):
             batches.append(bs)
             roffs.append(torch.arange(0, ctx.nreads + 1, dtype=torch.int64, device=dev) * READ_LEN)
             goffs.append(torch.arange(0, ctx.nreads + 1, 2, dtype=torch.int64, device=dev))
-            outs.append(torch.zeros(ctx.B, dtype=torch.int32, device=dev))
+            outs.append([torch.zeros(ctx.B, dtype=torch.int32, device=dev) for _ in range(2)])   # consecutive batches are in flight together
             torch.cuda.synchronize()
     S = capi.Sharded(shards, gtax, ctx.total_nt)
 
     def step(i):
         S.classify_reads_dev(ctx.opts, [batches[d][i % nb].data_ptr() for d in range(G)], [r.data_ptr() for r in roffs],
                              [ctx.nreads] * G, [ctx.total_nt] * G, [g.data_ptr() for g in goffs], [ctx.B] * G,
-                             [o.data_ptr() for o in outs])
+                             [o[i % 2].data_ptr() for o in outs])
 
     # parity: batch 0 of every GPU against the replicated table (rank 0's replica)
     step(0)
@@ -407,7 +407,7 @@ def _sharded_rank0(ctx, gidx_repl):
         capi.classify_reads_dev(gidx_repl, ctx.gtax, ctx.opts, nt0.data_ptr(), ctx.roff.data_ptr(), ctx.nreads, ctx.total_nt,
                                 ctx.goff.data_ptr(), ctx.B, ctx.out_b.data_ptr(), ctx.stream)
         torch.cuda.synchronize()
-        same = same and bool(torch.equal(ctx.out_b, outs[d].to(ctx.dev)))
+        same = same and bool(torch.equal(ctx.out_b, outs[d][0].to(ctx.dev)))
         del nt0
     steps = max(3, min(5, args.steps))
     for i in range(2):
@@ -432,6 +432,7 @@ def _sharded_rank0(ctx, gidx_repl):
            "stages_ms_per_step_per_gpu": stages, "lookups_routed_per_step": int(routed0),
            "shard_build_s_all": build_s, "shard_bytes": int(shards[0].info().bytes), "equals_replicated": bool(same),
            "exchange": "in-kernel: peer stores over NVLink (8 B per lookup out, 4 B back), epoch flags, no NCCL, no host read-back",
+           "lanes": int(os.environ.get("UMGAP_SHARDED_LANES", "2")),
            "what": "index key-range-sharded over the GPUs; two exchange rounds per batch (sampled positions, then the live frames)"}
     S.close()
     for x in shards + gtax:

@@ -377,6 +377,10 @@ uint64_t umgap_exchange_bucket_cap(int nranks, uint64_t max_total_nt);
 uint64_t umgap_exchange_region_bytes(int nranks, uint64_t max_total_nt);
 int umgap_exchange_create(const umgap_index* shard, const umgap_taxonomy* tax, int rank, int nranks, uint64_t max_total_nt,
                           void* const* regions, umgap_exchange** out);
+/* A rank that keeps several batches in flight makes one context per lane (0..5), each with regions of its own: the
+ * lanes use separate workspace sets of the shard's handle.                                                         */
+int umgap_exchange_create_lane(const umgap_index* shard, const umgap_taxonomy* tax, int rank, int nranks,
+                               uint64_t max_total_nt, void* const* regions, int lane, umgap_exchange** out);
 void umgap_exchange_free(umgap_exchange* ex);
 int umgap_exchange_classify_dev(umgap_exchange* ex, const umgap_pipeline_opts* opts, const uint8_t* nt_dev,
                                 const uint64_t* read_off_dev, uint64_t nreads, uint64_t total_nt,

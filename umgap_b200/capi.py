@@ -33,7 +33,7 @@ SYMBOLS = [
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
     "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate",
     "umgap_fst_writer_open", "umgap_fst_writer_insert", "umgap_fst_writer_finish", "umgap_fst_writer_abort", "umgap_fst_stream",
-    "umgap_kernel_times_ex", "umgap_exchange_bucket_cap", "umgap_exchange_region_bytes", "umgap_exchange_create", "umgap_exchange_free",
+    "umgap_kernel_times_ex", "umgap_exchange_bucket_cap", "umgap_exchange_region_bytes", "umgap_exchange_create", "umgap_exchange_create_lane", "umgap_exchange_free",
     "umgap_exchange_classify_dev", "umgap_exchange_status", "umgap_sharded_create", "umgap_sharded_free",
     "umgap_classify_reads_sharded_dev", "umgap_sharded_sync", "umgap_classify_reads_sharded",
     "umgap_index_replicate", "umgap_taxonomy_replicate", "umgap_classify_reads_multi", "umgap_classify_reads_packed_multi",

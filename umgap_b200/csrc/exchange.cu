@@ -27,8 +27,11 @@
 
 namespace umgap {
 
-void pipeline_reserve(const umgap_index* idx, uint64_t nreads, uint64_t total_nt);  // pipeline.cu
+void pipeline_reserve(const umgap_index* idx, uint64_t nreads, uint64_t total_nt, int buf);  // pipeline.cu
 void pipeline_take_error(const umgap_index* idx);
+void classify_ids_buf(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts, const uint32_t* ids_dev,
+                      const uint64_t* read_off_dev, uint64_t total_nt, const uint64_t* group_off_dev, uint64_t ngroups,
+                      const uint8_t* frame_hits_dev, bool frame_major, uint32_t* taxon_out_dev, int buf, cudaStream_t st);
 
 struct RegionLayout {
     uint64_t inbox_h, ansbox, inbox_cnt, flag_h, flag_a, bytes;
@@ -128,6 +131,7 @@ struct umgap_exchange {
     const umgap_index* shard = nullptr;
     const umgap_taxonomy* tax = nullptr;
     int rank = 0, n = 1, device = 0;
+    int lane = 0;  // workspace set of the shard's handle this context uses (contexts that run side by side on one shard differ in it)
     uint64_t cap = 0, max_total_nt = 0, max_reads = 0;
     uint8_t* region[kMaxShards] = {};  // this rank's mapping of every rank's exchange region
     uint32_t* send_pos = nullptr;
@@ -216,7 +220,7 @@ void exchange_classify(umgap_exchange* ex, const umgap_pipeline_opts* opts, cons
             {
                 LaunchTimer timer(2, st);
                 route_pack_sampled(ex->shard, opts, phase, nt_dev, read_off_dev, nreads, total_nt, ex->cap, hp, ex->send_pos, ex->cursors,
-                                   ex->frame_hits, ex->ids, nullptr, 0, 0, 0, st);
+                                   ex->frame_hits, ex->ids, nullptr, 0, 0, ex->lane, st);
                 timer.stop();
             }
             exchange_round(ex, st);
@@ -228,14 +232,15 @@ void exchange_classify(umgap_exchange* ex, const umgap_pipeline_opts* opts, cons
             timer.stop();
         }
         if (ngroups)
-            check_rc(umgap_classify_ids_masked_dev(ex->shard, ex->tax, opts, ex->ids, read_off_dev, total_nt, group_off_dev, ngroups,
-                                                   ex->frame_hits, 1, out_dev, st));
+            classify_ids_buf(ex->shard, ex->tax, opts, ex->ids, read_off_dev, total_nt, group_off_dev, ngroups, ex->frame_hits, true, out_dev,
+                             ex->lane, st);
     } else {
         route_pack_all(ex->shard, opts, nt_dev, read_off_dev, nreads, total_nt, ex->cap, hp, ex->send_pos, ex->cursors, ex->ids, st);
         exchange_round(ex, st);
         check_rc(umgap_route_scatter_dev(ex->shard, ansbox, ex->send_pos, ex->cursors, ex->cap, ex->ids, st));
         if (ngroups)
-            check_rc(umgap_classify_ids_dev(ex->shard, ex->tax, opts, ex->ids, read_off_dev, total_nt, group_off_dev, ngroups, out_dev, st));
+            classify_ids_buf(ex->shard, ex->tax, opts, ex->ids, read_off_dev, total_nt, group_off_dev, ngroups, nullptr, false, out_dev,
+                             ex->lane, st);
     }
 }
 
@@ -256,8 +261,14 @@ uint64_t umgap_exchange_region_bytes(int nranks, uint64_t max_total_nt) {
 
 int umgap_exchange_create(const umgap_index* shard, const umgap_taxonomy* tax, int rank, int nranks, uint64_t max_total_nt,
                           void* const* regions, umgap_exchange** out) {
+    return umgap_exchange_create_lane(shard, tax, rank, nranks, max_total_nt, regions, 0, out);
+}
+
+int umgap_exchange_create_lane(const umgap_index* shard, const umgap_taxonomy* tax, int rank, int nranks, uint64_t max_total_nt,
+                               void* const* regions, int lane, umgap_exchange** out) {
     umgap_exchange* ex = nullptr;
     int rc = guarded([&] {
+        if (lane < 0 || lane > 5) UMGAP_FAIL(UMGAP_ERR_INVALID, "lane must be in 0..5");
         if (!shard || !tax || !regions || !out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
         if (nranks < 1 || nranks > kMaxShards || rank < 0 || rank >= nranks) UMGAP_FAIL(UMGAP_ERR_INVALID, "rank %d of %d", rank, nranks);
         if (shard->nshards != nranks || shard->shard != rank)
@@ -272,6 +283,7 @@ int umgap_exchange_create(const umgap_index* shard, const umgap_taxonomy* tax, i
         ex->rank = rank;
         ex->n = nranks;
         ex->device = shard->device;
+        ex->lane = lane;
         ex->max_total_nt = max_total_nt;
         ex->max_reads = max_total_nt / 27 + 1;
         ex->cap = umgap_exchange_bucket_cap(nranks, max_total_nt);
@@ -290,7 +302,7 @@ int umgap_exchange_create(const umgap_index* shard, const umgap_taxonomy* tax, i
         UMGAP_CUDA(cudaMemset(ex->cursors, 0, 2 * kMaxShards * 8));
         // the workspaces of the pack and classify kernels, so that no launch of a batch allocates (an allocation
         // synchronises the device, and a device may be spinning in a wait kernel for a peer that is enqueued later)
-        pipeline_reserve(shard, ex->max_reads, max_total_nt);
+        pipeline_reserve(shard, ex->max_reads, max_total_nt, lane);
         UMGAP_CUDA(cudaDeviceSynchronize());
         *out = ex;
     });
@@ -340,11 +352,15 @@ int umgap_exchange_status(umgap_exchange* ex, uint64_t* lookups_routed) {
 // ---- one process driving all the shards (the CLI, a Rust host): peer access between the GPUs, regions from cudaMalloc ----
 struct umgap_sharded {
     int n = 0;
+    // lanes: complete sets of exchange contexts (regions, buckets, streams) that consecutive batches alternate between, so
+    // that one batch's pack kernels run beside the previous batch's lookup kernels (UMGAP_SHARDED_LANES, default 2)
+    int nlanes = 1;
+    uint64_t calls = 0;
     uint64_t max_total_nt = 0;
-    std::vector<umgap_exchange*> ex;
-    std::vector<void*> region;
+    std::vector<umgap_exchange*> ex;     // [lane * n + i]
+    std::vector<void*> region;           // [lane * n + i]
     std::vector<int> device;
-    std::vector<cudaStream_t> stream;
+    std::vector<cudaStream_t> stream;    // [lane * n + i]
     // staging of the host-buffer entry point, per GPU
     std::vector<uint8_t*> d_nt;
     std::vector<uint64_t*> d_roff, d_goff;
@@ -356,11 +372,17 @@ extern "C" {
 
 void umgap_sharded_free(umgap_sharded* s) {
     if (!s) return;
-    for (int i = 0; i < s->n; ++i) {
-        if (i < (int)s->ex.size()) umgap_exchange_free(s->ex[i]);
+    for (umgap_exchange* e : s->ex) umgap_exchange_free(e);
+    for (size_t x = 0; x < s->region.size(); ++x) {
+        cudaSetDevice(s->device[x % s->n]);
+        cudaFree(s->region[x]);
+    }
+    for (size_t x = 0; x < s->stream.size(); ++x) {
+        cudaSetDevice(s->device[x % s->n]);
+        if (s->stream[x]) cudaStreamDestroy(s->stream[x]);
+    }
+    for (int i = 0; i < s->n && i < (int)s->device.size(); ++i) {
         cudaSetDevice(s->device[i]);
-        if (i < (int)s->region.size()) cudaFree(s->region[i]);
-        if (i < (int)s->stream.size() && s->stream[i]) cudaStreamDestroy(s->stream[i]);
         if (i < (int)s->d_nt.size()) {
             cudaFree(s->d_nt[i]);
             cudaFree(s->d_roff[i]);
@@ -387,6 +409,11 @@ int umgap_sharded_create(const umgap_index* const* shards, const umgap_taxonomy*
                 if (s->device[j] == s->device[i]) UMGAP_FAIL(UMGAP_ERR_INVALID, "shards %d and %d share device %d: the exchange step needs a GPU per shard", j, i, s->device[i]);
         }
         const uint64_t bytes = umgap_exchange_region_bytes(n, max_total_nt);
+        {
+            const char* e = getenv("UMGAP_SHARDED_LANES");
+            const int v = e ? atoi(e) : 2;
+            s->nlanes = std::max(1, std::min(v, 4));
+        }
         for (int i = 0; i < n; ++i) {
             use_device(s->device[i]);
             for (int j = 0; j < n; ++j) {
@@ -398,19 +425,24 @@ int umgap_sharded_create(const umgap_index* const* shards, const umgap_taxonomy*
                 if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
                 else UMGAP_CUDA(e);
             }
-            void* r = nullptr;
-            UMGAP_CUDA(cudaMalloc(&r, bytes));
-            UMGAP_CUDA(cudaMemset(r, 0, bytes));
-            s->region.push_back(r);
-            cudaStream_t st;
-            UMGAP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            s->stream.push_back(st);
         }
-        for (int i = 0; i < n; ++i) {
-            umgap_exchange* ex = nullptr;
-            check_rc(umgap_exchange_create(shards[i], tax[i], i, n, max_total_nt, s->region.data(), &ex));
-            s->ex.push_back(ex);
-        }
+        for (int lane = 0; lane < s->nlanes; ++lane)
+            for (int i = 0; i < n; ++i) {
+                use_device(s->device[i]);
+                void* r = nullptr;
+                UMGAP_CUDA(cudaMalloc(&r, bytes));
+                UMGAP_CUDA(cudaMemset(r, 0, bytes));
+                s->region.push_back(r);
+                cudaStream_t st;
+                UMGAP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                s->stream.push_back(st);
+            }
+        for (int lane = 0; lane < s->nlanes; ++lane)
+            for (int i = 0; i < n; ++i) {
+                umgap_exchange* ex = nullptr;
+                check_rc(umgap_exchange_create_lane(shards[i], tax[i], i, n, max_total_nt, s->region.data() + (size_t)lane * n, lane, &ex));
+                s->ex.push_back(ex);
+            }
         s->d_nt.assign(n, nullptr);
         s->d_roff.assign(n, nullptr);
         s->d_goff.assign(n, nullptr);
@@ -436,10 +468,11 @@ int umgap_classify_reads_sharded_dev(umgap_sharded* s, const umgap_pipeline_opts
         // the GPUs must not share an enqueuing thread.
         std::vector<int> rc(s->n, UMGAP_OK);
         std::vector<std::string> msg(s->n);
+        const size_t lane0 = (size_t)(s->calls++ % s->nlanes) * s->n;
         auto run = [&](int i) {
             rc[i] = guarded([&] {
-                exchange_classify(s->ex[i], opts, nt_dev[i], read_off_dev[i], nreads[i], total_nt[i], group_off_dev[i], ngroups[i],
-                                  taxon_out_dev[i], s->stream[i]);
+                exchange_classify(s->ex[lane0 + i], opts, nt_dev[i], read_off_dev[i], nreads[i], total_nt[i], group_off_dev[i], ngroups[i],
+                                  taxon_out_dev[i], s->stream[lane0 + i]);
             });
             if (rc[i] != UMGAP_OK) msg[i] = get_error();
         };
@@ -458,14 +491,14 @@ int umgap_classify_reads_sharded_dev(umgap_sharded* s, const umgap_pipeline_opts
 int umgap_sharded_sync(umgap_sharded* s, uint64_t* lookups_routed) {
     return guarded([&] {
         if (!s) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
-        for (int i = 0; i < s->n; ++i) {
-            use_device(s->device[i]);
-            UMGAP_CUDA(cudaStreamSynchronize(s->stream[i]));
+        for (size_t x = 0; x < s->stream.size(); ++x) {
+            use_device(s->device[x % s->n]);
+            UMGAP_CUDA(cudaStreamSynchronize(s->stream[x]));
         }
         uint64_t sum = 0;
         int first_rc = UMGAP_OK;
         std::string msg;
-        for (int i = 0; i < s->n; ++i) {
+        for (size_t i = 0; i < s->ex.size(); ++i) {
             uint64_t r = 0;
             const int rc = umgap_exchange_status(s->ex[i], &r);
             sum += r;

@@ -66,7 +66,7 @@ struct KmerSink : FstSink {
 // kernels overlap.  The residue alphabet is fixed before the workers start: the bytes met on the first three levels,
 // in walk order (a deterministic function of the file, hence the same on every rank of a sharded load).  A key with a
 // byte first met deeper than that makes the load start over on the serial path above.
-struct PinnedBatch {
+struct alignas(64) PinnedBatch {   // a cache line of its own: the workers fill neighbouring batches
     uint64_t* k = nullptr;
     uint32_t* v = nullptr;
     size_t n = 0;
@@ -103,14 +103,17 @@ struct BatchQueues {
     }
 };
 
-struct WorkerSink : FstSink {
-    const uint8_t* code_of_byte;
+struct alignas(64) WorkerSink : FstSink {
+    uint8_t code_of_byte[256];  // a private copy of the alphabet
     const size_t k;
     BatchQueues& q;
     PinnedBatch* cur = nullptr;
+    uint64_t* ck = nullptr;     // the current batch's arrays and fill, kept here while it is being filled
+    uint32_t* cv = nullptr;
+    size_t cn = 0;
     uint64_t skipped = 0;
     bool unknown_byte = false, bad_value = false;
-    WorkerSink(const uint8_t* codes, size_t kk, BatchQueues& queues) : code_of_byte(codes), k(kk), q(queues) {}
+    WorkerSink(const uint8_t* codes, size_t kk, BatchQueues& queues) : k(kk), q(queues) { memcpy(code_of_byte, codes, 256); }
     void on_key(const uint8_t* key, size_t len, uint64_t value) override {
         if (len != k) {
             ++skipped;
@@ -129,18 +132,27 @@ struct WorkerSink : FstSink {
             bad_value = true;
             return;
         }
-        if (!cur) cur = q.take_free();
-        if (!cur) return;  // the load was stopped
-        cur->k[cur->n] = code;
-        cur->v[cur->n] = (uint32_t)value;
-        if (++cur->n == kPBatch) {
+        if (!cur) {
+            cur = q.take_free();
+            if (!cur) return;  // the load was stopped
+            ck = cur->k;
+            cv = cur->v;
+            cn = 0;
+        }
+        ck[cn] = code;
+        cv[cn] = (uint32_t)value;
+        if (++cn == kPBatch) {
+            cur->n = cn;
             q.give_full(cur);
             cur = nullptr;
         }
     }
     void finish() {
-        if (cur && cur->n) q.give_full(cur);
-        else if (cur) q.give_free(cur);
+        if (cur) {
+            cur->n = cn;
+            if (cn) q.give_full(cur);
+            else q.give_free(cur);
+        }
         cur = nullptr;
     }
 };

@@ -429,10 +429,13 @@ struct SampledSmem {
     uint64_t q[kSQueue];          // hash | distance << 45 | level << 48 | tag << 50
     uint32_t roff[kSReads + 1];   // read starts relative to the batch
     uint32_t mask[kSReads];       // frame hit masks
-    uint32_t val[kSValRows][32];  // answer of sampled position s < kSValRows of the record walked by lane l: val[s][l]
+    // answer of sampled position s < kSValRows of the record walked by lane l: val[s][l]; the routed modes, which keep no
+    // answers here, order the queue by owner in this space (route_flush)
+    alignas(8) uint32_t val[kSValRows][32];
     uint16_t item[kSItems];       // second phase: frame record | segment << 5
 };
 constexpr uint32_t kSRevOff = sizeof(uint4) * ((kSSpan + 32) / 16);  // byte distance from f[] to r[]
+static_assert(kSQueue * 12 <= kSValRows * 32 * 4, "route_flush orders a full queue (hash + position per entry) in val[]");
 
 // Re-probes the queued lookups until all are answered; done(tag, value) receives each answer.
 template <class TV, class Done>
@@ -527,12 +530,17 @@ struct RouteSink {
 };
 
 // Appends the queued lookups (hash | tag << 50) to their owners' buckets.  One atomic per owner and flush: lane o
-// counts the queue's entries bound for shard o, claims that many consecutive slots of bucket o, and hands them out
-// chunk by chunk (a claim per 32-entry chunk was measured: the two or eight cursors are same-address atomics, 10 M of
-// them per 1 M pairs, and the pack kernels ran at a third of their speed).  pos(tag) = the send_pos value.
+// counts the queue's entries bound for shard o and claims that many consecutive slots of bucket o (a claim per
+// 32-entry chunk was measured: the two or eight cursors are same-address atomics, 10 M of them per 1 M pairs, and the
+// pack kernels ran at a third of their speed).  The entries are first ordered by owner in shared memory (`scratch`:
+// kSQueue hashes + kSQueue positions), so that the stores of a flush form one contiguous run per owner -- buckets that
+// live in another GPU's memory (exchange.cu) then receive a few long NVLink writes per flush instead of a 32-byte
+// piece per owner and chunk (eight owners: pack kernels 11 ms -> see profiles/README.md).  pos(tag) = the send_pos value.
 template <class Pos>
-__device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t* q, uint32_t qn, int lane, Pos pos) {
+__device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t* q, uint32_t qn, int lane, Pos pos, uint32_t* scratch) {
     const unsigned lt_mask = (1u << lane) - 1;
+    uint64_t* sh = reinterpret_cast<uint64_t*>(scratch);
+    uint32_t* sp = scratch + 2 * kSQueue;
     __syncwarp();
     uint32_t mine = 0;  // lane o: entries bound for shard o
 #pragma unroll 1
@@ -545,8 +553,10 @@ __device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t*
             if ((uint32_t)lane == o) mine += __popc(m);
         }
     }
-    unsigned long long next = 0;  // lane o: next free slot of bucket o
-    if ((uint32_t)lane < rs.nshards && mine) next = atomicAdd(&rs.cursors[lane], (unsigned long long)mine);
+    const uint32_t start = warp_incl_scan(mine, lane) - mine;  // lane o: where owner o's run begins in the ordered queue
+    unsigned long long base = 0;  // lane o: first claimed slot of bucket o
+    if ((uint32_t)lane < rs.nshards && mine) base = atomicAdd(&rs.cursors[lane], (unsigned long long)mine);
+    uint32_t fill = start;
 #pragma unroll 1
     for (uint32_t c = 0; c < qn; c += 32) {
         const bool active = c + lane < qn;
@@ -554,20 +564,35 @@ __device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t*
         const uint64_t h = e & kKeyMask;
         uint32_t local32;
         const uint32_t owner = active ? shard_split(h, rs.nshards, local32) : 0xFFFFFFFFu;
-        const unsigned long long base = __shfl_sync(0xffffffffu, next, active ? (int)owner : 0);
+        const uint32_t at = __shfl_sync(0xffffffffu, fill, active ? (int)owner : 0);
         uint32_t before = 0;  // entries of this chunk bound for the same shard in lower lanes
         for (uint32_t o = 0; o < rs.nshards; ++o) {
             const unsigned m = __ballot_sync(0xffffffffu, owner == o);
             if (owner == o) before = __popc(m & lt_mask);
-            if ((uint32_t)lane == o) next += __popc(m);
+            if ((uint32_t)lane == o) fill += __popc(m);
         }
         if (active) {
-            const unsigned long long at = base + before;
+            sh[at + before] = h;
+            sp[at + before] = pos((uint32_t)(e >> 50));
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t c = 0; c < qn; c += 32) {
+        const uint32_t i = c + lane;
+        const bool active = i < qn;
+        const uint64_t h = active ? sh[i] : 0ull;
+        uint32_t local32;
+        const uint32_t owner = active ? shard_split(h, rs.nshards, local32) : 0u;
+        const uint32_t st = __shfl_sync(0xffffffffu, start, (int)owner);
+        const unsigned long long b0 = __shfl_sync(0xffffffffu, base, (int)owner);
+        if (active) {
+            const unsigned long long at = b0 + (i - st);
             if (at < rs.cap) {
                 rs.h.p[owner][at] = h;
-                rs.send_pos[(uint64_t)owner * rs.cap + at] = pos((uint32_t)(e >> 50));
+                rs.send_pos[(uint64_t)owner * rs.cap + at] = sp[i];
             } else {
-                rs.cursors[rs.nshards + owner] = 1;  // bucket overflow: the host retries with a larger capacity
+                rs.cursors[rs.nshards + owner] = 1;  // bucket overflow: raised by umgap_exchange_status / RoutedClassifier.overflowed
             }
         }
     }
@@ -577,7 +602,7 @@ __device__ __forceinline__ void route_flush(const RouteSink& rs, const uint64_t*
 // Makes room in (all = false) or empties (all = true) the per-warp queue of the sampled kernel, by its mode.
 template <int MODE, class TV, class Done, class Pos>
 __device__ __forceinline__ uint32_t service_queue(const TV& t, const RouteSink& rs, uint64_t* q, uint32_t qn, int lane, bool all,
-                                                  uint32_t room, Done done, Pos pos) {
+                                                  uint32_t room, Done done, Pos pos, uint32_t* scratch) {
     if (MODE == 0) {
         drain_queue(t, q, qn, lane, done);
         return 0;
@@ -591,7 +616,7 @@ __device__ __forceinline__ uint32_t service_queue(const TV& t, const RouteSink& 
         }
         return qn;
     }
-    route_flush(rs, q, qn, lane, pos);
+    route_flush(rs, q, qn, lane, pos, scratch);
     return 0;
 }
 
@@ -743,7 +768,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                 const uint32_t max_cs = __reduce_max_sync(0xffffffffu, cs);
 #pragma unroll 1
                 for (uint32_t s0 = 0; s0 < max_cs; s0 += kSU) {
-                    if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done1, pos1);
+                    if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done1, pos1, &sm.val[0][0]);
                     uint64_t h[kSU];
                     ulonglong4 sec[kSU];
                     bool valid[kSU];
@@ -789,7 +814,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     }
                 }
             }
-            qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done1, pos1);
+            qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done1, pos1, &sm.val[0][0]);
             __syncwarp();
             if (MODE == 0 && (uint32_t)lane < nb) frame_hits[cur + lane] = (uint8_t)sm.mask[lane];
             if (MODE == 1) {  // the masks accumulate over the region passes; phase 2 is another launch
@@ -847,7 +872,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                     const uint32_t max_cnt = __reduce_max_sync(0xffffffffu, cnt);
 #pragma unroll 1
                     for (uint32_t s0 = 0; s0 < max_cnt; s0 += kSU) {
-                        if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done2, pos2);
+                        if (qn + 32 * kSU > (uint32_t)kSQueue) qn = service_queue<MODE>(t, rs, sm.q, qn, lane, false, 32 * kSU, done2, pos2, &sm.val[0][0]);
                         uint64_t h[kSU];
                         ulonglong4 sec[kSU];
                         uint32_t v[kSU];
@@ -899,7 +924,7 @@ lookup_sampled_kernel(const __grid_constant__ TV t, const __grid_constant__ Codo
                         }
                     }
                 }
-                qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done2, pos2);
+                qn = service_queue<MODE>(t, rs, sm.q, qn, lane, true, 0, done2, pos2, &sm.val[0][0]);
             }
             __syncwarp();
             cur += nb;
@@ -1660,17 +1685,33 @@ static void raise_dev_error(const DevError& e) {
 namespace umgap {
 // The workspaces the pack and classify kernels of a batch of this size take from the handle, allocated now: a launch
 // path that allocates synchronises the device, which the exchange step (exchange.cu) must never do inside a batch.
-void pipeline_reserve(const umgap_index* idx, uint64_t nreads, uint64_t total_nt) {
+void pipeline_reserve(const umgap_index* idx, uint64_t nreads, uint64_t total_nt, int buf) {
     use_device(idx->device);
-    idx->ws.get(WS_SCRATCH, (12 * total_nt + 64) * sizeof(uint32_t));
-    idx->ws.get(WS_ERR, sizeof(DevError));
-    idx->ws.get(WS_LONG, (128 + nreads) * sizeof(uint32_t));
+    idx->ws.get(WS_SCRATCH + buf, (12 * total_nt + 64) * sizeof(uint32_t));
+    UMGAP_CUDA(cudaMemset(idx->ws.get(WS_ERR, sizeof(DevError)), 0, sizeof(DevError)));
+    idx->ws.get(WS_LONG + buf, (128 + nreads) * sizeof(uint32_t));
+}
+// umgap_classify_ids[_masked]_dev with the workspace set `buf` (0 .. kMaxBufs - 1): batches in flight at the same time
+// on one handle (the lanes of the exchange step) must not share the scratch of the groups with many distinct taxa.
+void classify_ids_buf(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts, const uint32_t* ids_dev,
+                      const uint64_t* read_off_dev, uint64_t total_nt, const uint64_t* group_off_dev, uint64_t ngroups,
+                      const uint8_t* frame_hits_dev, bool frame_major, uint32_t* taxon_out_dev, int buf, cudaStream_t st) {
+    check_opts(idx, tax, opts);
+    if (!tax || !ids_dev) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+    if (buf < 0 || buf >= kMaxBufs) UMGAP_FAIL(UMGAP_ERR_INVALID, "workspace set out of range");
+    use_device(idx->device);
+    uint32_t* scratch = (uint32_t*)idx->ws.get(WS_SCRATCH + buf, (12 * total_nt + 64) * sizeof(uint32_t));
+    DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
+    launch_classify(idx, tax, opts, ids_dev, read_off_dev, group_off_dev, 0, ngroups, frame_hits_dev, scratch, taxon_out_dev, err, st,
+                    frame_major);
 }
 // Raises the error the classify kernel of the last *_dev call left behind (Unknown Taxon ID); the caller has synchronised.
 void pipeline_take_error(const umgap_index* idx) {
     use_device(idx->device);
     DevError he;
-    UMGAP_CUDA(cudaMemcpy(&he, idx->ws.get(WS_ERR, sizeof(DevError)), sizeof he, cudaMemcpyDeviceToHost));
+    void* err = idx->ws.get(WS_ERR, sizeof(DevError));
+    UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
+    UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
     raise_dev_error(he);
 }
 }  // namespace umgap
