@@ -92,7 +92,11 @@ def main():
     for lane in tiny.lanes:
         lane.cap = 64
     d_out = torch.zeros(len(goff) - 1, dtype=torch.int32, device="cuda")
-    tiny.classify(capi.default_opts(seedextend=1, min_seed_size=3), d_nt[:total_nt], d_roff, d_goff, d_out, total_nt)
+    try:   # every rank learns of the overflow in the same exchange and raises: none is left behind in a collective
+        tiny.classify(capi.default_opts(seedextend=1, min_seed_size=3), d_nt[:total_nt], d_roff, d_goff, d_out, total_nt)
+        raise AssertionError("a bucket overflow went unreported")
+    except RuntimeError as e:
+        assert "overflowed" in str(e)
     assert tiny.overflowed()
     dist.barrier()
     torch.cuda.synchronize()

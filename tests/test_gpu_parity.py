@@ -476,6 +476,8 @@ def test_tryptic_lookup_matches_oracle(capi, world, tmp_path):
     (1, 0.0, 5, 50, "", "", False),     # command defaults, hybrid
     (0, 0.0, 5, 50, "", "CW", True),    # drop set, ranked snapping, LCA*
     (1, 2.0, 6, 30, "L", "", False),    # keep set
+    (1, 0.0, 1, 50, "", "", False),     # -l 1 and -l 3: one slot of the per-group hit array per residue / per two residues
+    (2, 1.0, 3, 50, "", "", False),
 ])
 def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, strategy, lb, mn, mx, keep, drop, ranked):
     """umgap_classify_peptides (digest + lookup + uniq join + aggregation on the device) against the oracle's text

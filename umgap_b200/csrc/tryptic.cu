@@ -163,7 +163,7 @@ constexpr int kPepThreads = 128;
 
 __device__ __forceinline__ void tryp_probe(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
                                            const uint8_t* __restrict__ aa, uint64_t h, uint64_t start, uint32_t len,
-                                           uint32_t* __restrict__ out) {
+                                           uint32_t* __restrict__ out, uint32_t shift) {
     uint64_t s = __umul64hi(h, nslots);
     for (;;) {
         const VarSlot sl = slots[s];
@@ -173,7 +173,7 @@ __device__ __forceinline__ void tryp_probe(const VarSlot* __restrict__ slots, ui
             bool same = true;
             for (uint32_t q = 0; q < len; ++q) same &= k[q] == aa[start + q];
             if (same) {
-                out[start] = sl.value;
+                out[start >> shift] = sl.value;
                 return;
             }
         }
@@ -184,7 +184,7 @@ __device__ __forceinline__ void tryp_probe(const VarSlot* __restrict__ slots, ui
 __global__ void __launch_bounds__(kPepThreads)
 tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, const uint8_t* __restrict__ pool,
                          const uint8_t* __restrict__ aa, uint64_t total_aa, const uint64_t* __restrict__ line_off, uint64_t nlines,
-                         TrypParams tp, const uint8_t* __restrict__ set_lut, uint32_t* __restrict__ out) {
+                         TrypParams tp, const uint8_t* __restrict__ set_lut, uint32_t* __restrict__ out, uint32_t shift) {
     __shared__ uint8_t s_lut[256];
     __shared__ uint64_t s_hash[kPepList][kPepThreads];
     __shared__ uint64_t s_where[kPepList][kPepThreads];  // start << 8 | length
@@ -199,7 +199,7 @@ tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, con
         bool dropped = false, too_long = false, prev_kr = false;
         auto flush = [&]() {
             for (uint32_t p = 0; p < npend; ++p)
-                tryp_probe(slots, nslots, pool, aa, s_hash[p][t], s_where[p][t] >> 8, (uint32_t)(s_where[p][t] & 0xFF), out);
+                tryp_probe(slots, nslots, pool, aa, s_hash[p][t], s_where[p][t] >> 8, (uint32_t)(s_where[p][t] & 0xFF), out, shift);
             npend = 0;
         };
         auto finish = [&]() {  // the peptide [pstart, pstart + len) is complete
@@ -254,11 +254,16 @@ tryp_lookup_lines_kernel(const VarSlot* __restrict__ slots, uint64_t nslots, con
     }
 }
 
-// rec_off[g] = line_off[group_off[g]]: the byte range of the lines `uniq` joins into group g
+// rec_off[g] = line_off[group_off[g]] >> shift: the range of `out` that holds the kept peptides of the lines `uniq` joins
+// into group g.  A kept peptide has at least minlen >= 2^shift residues and peptides do not overlap, so start >> shift is a
+// slot of its own, and a kept peptide of group g starts at least 2^shift bytes before the group's end: its slot lies below
+// the first slot of group g + 1.  (shift 2 for -l >= 4 -- the presets use -l 9: a quarter of the zeroed array to clear and
+// to aggregate over.)
 __global__ void group_bytes_kernel(const uint64_t* __restrict__ line_off, const uint64_t* __restrict__ group_off, uint64_t ngroups,
-                                   uint64_t* __restrict__ rec_off) {
+                                   uint64_t* __restrict__ rec_off, uint32_t shift) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= ngroups; g += stride) rec_off[g] = line_off[group_off[g]];
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= ngroups; g += stride)
+        rec_off[g] = line_off[group_off[g]] >> shift;
 }
 
 __global__ void line_of_byte_kernel(const uint64_t* __restrict__ line_off, uint64_t nlines, uint32_t* __restrict__ lob) {
@@ -397,15 +402,17 @@ static void classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* 
     UMGAP_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(unsigned int), st));
     if (!ngroups) return;
     UMGAP_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
-    UMGAP_CUDA(cudaMemsetAsync(d_out, 0, (total_aa + 1) * sizeof(uint32_t), st));
+    const uint32_t minlen = std::max<uint32_t>(1, tp.minlen);
+    const uint32_t shift = minlen >= 4 ? 2 : minlen >= 2 ? 1 : 0;  // one slot of `out` per 2^shift residues (group_bytes_kernel)
+    UMGAP_CUDA(cudaMemsetAsync(d_out, 0, ((total_aa >> shift) + 1) * sizeof(uint32_t), st));
     if (nlines && total_aa) {
         if (((uintptr_t)aa_dev & 7u) != 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "aa_dev must be 8-byte aligned");
         tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, kPepThreads), 148 * 16), kPepThreads, 0, st>>>(
-            t->slots, t->nslots, t->pool, aa_dev, total_aa, line_off_dev, nlines, tp, d_lut, d_out);
+            t->slots, t->nslots, t->pool, aa_dev, total_aa, line_off_dev, nlines, tp, d_lut, d_out, shift);
         UMGAP_CUDA(cudaGetLastError());
     }
     group_bytes_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(ngroups + 1, 256), 148 * 8), 256, 0, st>>>(line_off_dev, group_off_dev,
-                                                                                                        ngroups, d_rec);
+                                                                                                        ngroups, d_rec, shift);
     UMGAP_CUDA(cudaGetLastError());
     launch_aggregate(tax, o->strategy, o->factor, o->lower_bound, o->ranked_only, d_out, d_rec, ngroups, d_scratch, taxon_out_dev,
                      d_err, st);

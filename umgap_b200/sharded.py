@@ -109,9 +109,19 @@ class RoutedClassifier:
         with torch.cuda.stream(stream):
             lane.overflow |= lane.cursors[G:].any()
             lane.fills = lane.cursors[:G].clamp(max=cap)
-            dist.all_to_all_single(lane.recv_counts, lane.fills)                       # bucket fills
-            both = torch.stack([lane.fills, lane.recv_counts]).cpu()                   # the one host read of a round
+            # bucket fills, and beside each this rank's overflow flag: every rank learns of an overflow anywhere in the
+            # same exchange, so that all of them raise together (one rank leaving a collective alone would hang the rest)
+            send = torch.stack([lane.fills, lane.overflow.to(torch.int64).expand(G)], dim=1).contiguous()
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send)
+            lane.recv_counts.copy_(recv[:, 0])
+            both = torch.stack([lane.fills, recv[:, 0], recv[:, 1]]).cpu()             # the one host read of a round
             sc, rc = both[0].tolist(), both[1].tolist()
+            if any(both[2].tolist()):
+                # a pack kernel dropped the lookups that did not fit: the results would silently miss k-mers
+                bad = [r for r, f in enumerate(both[2].tolist()) if f]
+                raise RuntimeError(f"RoutedClassifier: a bucket overflowed on rank(s) {bad} (capacity {cap} lookups per owner; key skew "
+                                   "beyond the slack) -- construct it with a larger `slack`")
             self.lookups_routed += sum(sc)
             self._mark("counts")
             works = self._swap(lane, lane.send_h, sc, lane.recv_h, rc)                 # hashes: 8 B per lookup
