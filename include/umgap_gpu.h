@@ -57,6 +57,12 @@ const char* umgap_last_error(void);
 int umgap_abi_version(void);
 int umgap_device_count(void); /* number of CUDA devices, or negative status */
 
+/* Page-locked host memory for the buffers handed to the host-buffer entry points (the read buffer of a parser):
+ * copies out of it run asynchronously at full PCIe rate, copies out of pageable memory are staged and serialise.
+ * Needs a CUDA device; NULL on failure (umgap_last_error).                                                      */
+void* umgap_host_alloc(size_t bytes);
+void umgap_host_free(void* p);
+
 /* ---- index: replaces fst::Map::{from_path,from_bytes} + Map::get ------------------------
  * call sites prot2kmer2lca.rs:109-114,176; prot2tryp2lca.rs:89-94,130.                      */
 

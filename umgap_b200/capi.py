@@ -21,7 +21,7 @@ AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
 
 # every symbol include/umgap_gpu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
-    "umgap_last_error", "umgap_abi_version", "umgap_device_count",
+    "umgap_last_error", "umgap_abi_version", "umgap_device_count", "umgap_host_alloc", "umgap_host_free",
     "umgap_index_load_fst", "umgap_index_from_pairs", "umgap_index_free", "umgap_index_get_info",
     "umgap_index_set_probe_region", "umgap_index_build_from_proteins",
     "umgap_index_load_fst_shard", "umgap_index_from_pairs_shard", "umgap_index_shard_desc",

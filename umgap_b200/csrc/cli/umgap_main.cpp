@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -778,8 +779,33 @@ int cmd_fastq2fasta(int argc, char** argv) {
 // SURVEY 8(e) mode 1); the writer prints the blocks in input order.
 namespace classify_cli {
 
+// The nucleotides of a block, in page-locked memory (umgap_host_alloc): the library copies them to the GPU asynchronously.
+struct PinnedBytes {
+    char* p = nullptr;
+    size_t n = 0, cap = 0;
+    ~PinnedBytes() { umgap_host_free(p); }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    void resize(size_t m) { n = m; }  // shrink only
+    void reserve(size_t m) {
+        if (m <= cap) return;
+        char* q = (char*)umgap_host_alloc(m + m / 8 + 64);
+        if (!q) fail(umgap_last_error());
+        if (n) memcpy(q, p, n);
+        umgap_host_free(p);
+        p = q;
+        cap = m + m / 8 + 64;
+    }
+    void append(const char* src, size_t len) {
+        if (n + len > cap) reserve(n + len);
+        memcpy(p + n, src, len);
+        n += len;
+    }
+};
+
 struct Batch {
-    std::string nt, harena;
+    PinnedBytes nt;
+    std::string harena;
     std::vector<uint64_t> roff, goff, hoff;  // hoff[g] .. hoff[g+1]: header of group g in harena
     void reset() {
         nt.clear();
@@ -796,6 +822,7 @@ struct Job {
     const char* view = nullptr;  // the block's bytes: text.data(), or a window of the memory-mapped input file
     size_t len = 0;
     uint64_t seq = 0;
+    int stage = 0;  // what the pool threads do with it next: 0 parse, 1 format the classified groups
     Batch batch;
     std::vector<uint32_t> res;
     std::string out;
@@ -977,6 +1004,8 @@ int cmd_classify(int argc, char** argv) {
         check(umgap_index_replicate(idx[0].p, devices[g], &idx[g].p));
         check(umgap_taxonomy_replicate(tax[0].p, devices[g], &tax[g].p));
     }
+    const auto t_loaded = std::chrono::steady_clock::now();
+    std::atomic<uint64_t> n_reads{0}, n_bytes{0};
     // block size in bytes (UMGAP_CLI_BLOCK overrides it, for tests of the block seams)
     const size_t block = getenv("UMGAP_CLI_BLOCK") ? std::max<size_t>(16, strtoull(getenv("UMGAP_CLI_BLOCK"), nullptr, 10)) : (size_t)32 << 20;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1008,20 +1037,43 @@ int cmd_classify(int argc, char** argv) {
     };
 
     std::vector<std::thread> parsers, classifiers;
-    std::atomic<size_t> parsers_left{P}, classifiers_left{G};
+    // pool threads: parse a block, or format the groups of a classified one (both are text work; the classifier
+    // threads only drive their GPU)
+    auto format_job = [&](Job* j) {
+        Batch& B = j->batch;
+        const size_t ng = B.groups();
+        j->out.clear();
+        j->out.reserve(B.harena.size() + 12 * ng);
+        for (size_t x = 0; x < ng; ++x) {
+            if (j->res[x] == UMGAP_ABSENT) continue;
+            j->out += '>';
+            j->out.append(B.harena, B.hoff[x], B.hoff[x + 1] - B.hoff[x]);
+            j->out += '\n';
+            append_u32(j->out, j->res[x]);
+            j->out += '\n';
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            done[j->seq] = j;
+        }
+        done_cv.notify_all();
+    };
     for (size_t t = 0; t < P; ++t)
         parsers.emplace_back([&] {
             Job* j;
             while (parse_q.pop(j)) {
                 try {
-                    parse_block(j->view, j->view + j->len, delim, span, &j->batch);
-                    classify_q.push(j);
+                    if (j->stage == 0) {
+                        parse_block(j->view, j->view + j->len, delim, span, &j->batch);
+                        classify_q.push(j);
+                    } else {
+                        format_job(j);
+                    }
                 } catch (const std::exception& e) {
                     set_error(e.what());
                     break;
                 }
             }
-            if (--parsers_left == 0) classify_q.close();
         });
     for (size_t g = 0; g < G; ++g)
         classifiers.emplace_back([&, g] {
@@ -1030,33 +1082,19 @@ int cmd_classify(int argc, char** argv) {
                 try {
                     Batch& B = j->batch;
                     const size_t ng = B.groups();
-                    j->out.clear();
-                    if (ng) {
-                        j->res.resize(ng);
-                        check(umgap_classify_reads(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.data(), B.roff.data(), B.roff.size() - 1,
+                    j->res.resize(ng);
+                    if (ng)
+                        check(umgap_classify_reads(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.p, B.roff.data(), B.roff.size() - 1,
                                                    B.goff.data(), ng, j->res.data(), nullptr));
-                        j->out.reserve(B.harena.size() + 12 * ng);
-                        for (size_t x = 0; x < ng; ++x) {
-                            if (j->res[x] == UMGAP_ABSENT) continue;
-                            j->out += '>';
-                            j->out.append(B.harena, B.hoff[x], B.hoff[x + 1] - B.hoff[x]);
-                            j->out += '\n';
-                            append_u32(j->out, j->res[x]);
-                            j->out += '\n';
-                        }
-                    }
-                    {
-                        std::lock_guard<std::mutex> lk(mu);
-                        done[j->seq] = j;
-                    }
-                    done_cv.notify_all();
+                    n_reads += B.roff.size() - 1;
+                    n_bytes += j->len;
+                    j->stage = 1;
+                    parse_q.push(j);
                 } catch (const std::exception& e) {
                     set_error(e.what());
                     break;
                 }
             }
-            --classifiers_left;
-            done_cv.notify_all();
         });
     std::thread writer([&] {
         uint64_t next = 0;
@@ -1065,7 +1103,13 @@ int cmd_classify(int argc, char** argv) {
             {
                 std::unique_lock<std::mutex> lk(mu);
                 done_cv.wait(lk, [&] { return !error.empty() || done.count(next) || (reader_finished && next >= total_blocks); });
-                if (!error.empty() || !done.count(next)) return;
+                if (!error.empty()) return;
+                if (!done.count(next)) {  // every block is written: the pool and the classifiers can go
+                    lk.unlock();
+                    parse_q.close();
+                    classify_q.close();
+                    return;
+                }
                 j = done[next];
                 done.erase(next);
             }
@@ -1111,6 +1155,7 @@ int cmd_classify(int argc, char** argv) {
                 }
                 Job* j;
                 if (!free_q.pop(j)) break;
+                j->stage = 0;
                 j->view = map + pos;
                 j->len = cut;
                 j->seq = seq++;
@@ -1126,6 +1171,7 @@ int cmd_classify(int argc, char** argv) {
             while (!eof || !carry.empty()) {
                 Job* j;
                 if (!free_q.pop(j)) break;  // closed: an error elsewhere
+                j->stage = 0;
                 if (j->text.size() < block + carry.size()) j->text.resize(block + carry.size());
                 memcpy(j->text.data(), carry.data(), carry.size());
                 size_t have = carry.size();
@@ -1170,7 +1216,6 @@ int cmd_classify(int argc, char** argv) {
             reader_finished = true;
         }
         done_cv.notify_all();
-        parse_q.close();
     } catch (const std::exception& e) {
         set_error(e.what());
     }
@@ -1178,6 +1223,12 @@ int cmd_classify(int argc, char** argv) {
     for (auto& t : classifiers) t.join();
     writer.join();
     if (!error.empty()) fail(error);
+    if (getenv("UMGAP_CLI_VERBOSE")) {  // the stream's own rate, start-up (CUDA context, index and taxonomy load) left out
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loaded).count();
+        fprintf(stderr, "umgap classify: %llu reads, %llu bytes of FASTA in %.3f s after the index was loaded: %.2f M reads/s, %.2f GB/s "
+                "(%zu parser threads, %zu GPU(s))\n", (unsigned long long)n_reads.load(), (unsigned long long)n_bytes.load(), dt,
+                n_reads.load() / dt / 1e6, n_bytes.load() / dt / 1e9, P, G);
+    }
     return 0;
 }
 

@@ -55,6 +55,19 @@ void Workspace::release() {
 extern "C" {
 const char* umgap_last_error(void) { return umgap::get_error(); }
 int umgap_abi_version(void) { return UMGAP_ABI_VERSION; }
+void* umgap_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        umgap::set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+void umgap_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 int umgap_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
