@@ -262,6 +262,24 @@ int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* ta
                                 const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
                                 uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups);
 
+/* Asynchronous forms of the two host-buffer calls: the batch is enqueued on the index's internal streams and the call
+ * returns; umgap_pending_wait blocks until taxon_out holds the batch's results, raises what the batch raised
+ * (Unknown Taxon ID) and releases the ticket.  A host that hands over batch i + 1 before it waits for batch i keeps
+ * the GPU busy across the seam: the uploads and first kernels of one batch run in the tail of the other (one batch at
+ * a time leaves ~0.5 ms per 1 M pairs idle).  All host arrays of a batch -- page-locked, else the copies are not
+ * asynchronous -- stay valid and unchanged until its wait returns; batches complete in the order they were enqueued;
+ * at most 32 in flight per index; calls on one index come from one thread at a time.  The reference's stages are
+ * synchronous filters; this is the shape of its pipe (one stage reads while the next computes).                  */
+typedef struct umgap_pending umgap_pending;
+int umgap_classify_reads_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                               const uint8_t* nt, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
+                               uint64_t ngroups, uint32_t* taxon_out, umgap_pending** out);
+int umgap_classify_reads_packed_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                                      const uint32_t* codes, const uint64_t* n_entries, uint64_t n_count,
+                                      const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off, uint64_t ngroups,
+                                      uint32_t* taxon_out, umgap_pending** out);
+int umgap_pending_wait(umgap_pending* p);
+
 /* ---- multi-GPU, replicated index (SURVEY 8(e) mode 1: reads are independent units, index and taxonomy
  * replicated per GPU, no collective on the data path) inside one process -- what the reference gets from running
  * several pipelines side by side.  umgap_index_replicate / umgap_taxonomy_replicate copy a loaded table / tree to

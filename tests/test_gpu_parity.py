@@ -941,3 +941,71 @@ def test_multi_replica_classification_matches_single(capi, world):
             t.close()
     with pytest.raises(capi.UmgapError):
         capi.classify_reads_multi([(world["gidx"], world["gtax"]), (world["gidx"], world["gtax"])], opts, nt, off, goff)
+
+
+def test_async_host_calls_match_the_synchronous_ones(capi, world):
+    """umgap_classify_reads_async / _packed_async + umgap_pending_wait: several batches in flight on one index (their
+    chunks share the index's streams and workspaces in stream order) give what the synchronous calls give, complete in
+    order, keep each batch's error to that batch (Unknown Taxon ID is raised by the wait of the batch that held it and
+    by no other), and the 33rd batch in flight is refused."""
+    prots = world["proteins"]
+    gidx, gtax = world["gidx"], world["gtax"]
+    batches = []
+    for b, L in enumerate((150, 100, 251, 150, 301, 120)):
+        reads = datagen.make_reads(prots, 40 + 10 * b, seed=7700 + b, read_len=L, hit_frac=0.8)
+        nt, off = capi.pack_strings([r[1].encode() for r in reads])
+        goff = np.arange(0, len(reads) + 1, 2, dtype=np.uint64)
+        batches.append((nt, off, goff, capi.pack_reads(nt)))
+    for kw in (dict(min_seed_size=3, strategy=capi.AGG_HYBRID), dict(seedextend=0, strategy=capi.AGG_MRTL),
+               dict(min_seed_size=2, max_gap_size=1, strategy=capi.AGG_LCA_STAR, lower_bound=2.0)):
+        opts = capi.default_opts(**kw)
+        want = [capi.classify_reads(gidx, gtax, opts, nt, off, goff)[0].copy() for nt, off, goff, _ in batches]
+        for chunk_nt in (None, "3000"):  # several chunks per batch: the seams of consecutive batches interleave
+            if chunk_nt:
+                os.environ["UMGAP_CHUNK_NT"] = chunk_nt
+            try:
+                tickets = [capi.classify_reads_async(gidx, gtax, opts, nt, off, goff) if i % 2 == 0 else
+                           capi.classify_reads_packed_async(gidx, gtax, opts, pk[0], pk[1], off, goff)
+                           for i, (nt, off, goff, pk) in enumerate(batches)]
+                for i in reversed(range(len(tickets))):  # waiting out of order is allowed
+                    assert np.array_equal(tickets[i].wait(), want[i]), (kw, chunk_nt, i)
+            finally:
+                os.environ.pop("UMGAP_CHUNK_NT", None)
+    # an index value the taxonomy does not hold: only the batch that meets it fails
+    nt0, off0 = batches[0][0], batches[0][1]
+    nt1, off1 = batches[1][0], batches[1][1]
+    in_batch1 = set()
+    for r in range(len(off1) - 1):
+        for _, pep in otr.translate_record(bytes(nt1[int(off1[r]):int(off1[r + 1])]).decode(), 1, False):
+            in_batch1.update(pep[i:i + 9] for i in range(len(pep) - 8))
+    probe = None
+    for r in range(len(off0) - 1):
+        pep = otr.translate_record(bytes(nt0[int(off0[r]):int(off0[r + 1])]).decode(), 1, False, ["1"])[0][1][:9]
+        if len(pep) == 9 and "*" not in pep and "-" not in pep and pep not in in_batch1:
+            probe = pep.encode()
+            break
+    assert probe is not None
+    idx_map = dict(world["index"])
+    idx_map[probe] = 4_000_000_000
+    k2 = sorted(idx_map)
+    bidx = capi.Index.from_pairs(k2, [idx_map[k] for k in k2], k=9)
+    try:
+        opts = capi.default_opts(seedextend=0, strategy=capi.AGG_LCA_STAR)
+        # batch 1 (reads of another length and seed) does not hold the probe k-mer
+        clean = capi.classify_reads(gidx, gtax, opts, *batches[1][:3])[0].copy()
+        t0 = capi.classify_reads_async(bidx, gtax, opts, *batches[1][:3])
+        t1 = capi.classify_reads_async(bidx, gtax, opts, *batches[0][:3])
+        t2 = capi.classify_reads_async(bidx, gtax, opts, *batches[1][:3])
+        assert np.array_equal(t0.wait(), clean)
+        with pytest.raises(capi.UmgapError) as e:
+            t1.wait()
+        assert "Unknown Taxon ID: 4000000000" in str(e.value)
+        assert np.array_equal(t2.wait(), clean)
+    finally:
+        bidx.close()
+    tickets = [capi.classify_reads_async(gidx, gtax, capi.default_opts(), *batches[0][:3]) for _ in range(32)]
+    with pytest.raises(capi.UmgapError):
+        capi.classify_reads_async(gidx, gtax, capi.default_opts(), *batches[0][:3])
+    for t in tickets:
+        t.wait()
+    capi.classify_reads_async(gidx, gtax, capi.default_opts(), *batches[0][:3]).wait()

@@ -41,6 +41,7 @@ SYMBOLS = [
     "umgap_tryp_opts_default", "umgap_classify_peptides", "umgap_classify_peptides_dev",
     "umgap_translate_lookup_dev",
     "umgap_packed_words", "umgap_pack_reads", "umgap_classify_reads_packed",
+    "umgap_classify_reads_async", "umgap_classify_reads_packed_async", "umgap_pending_wait",
     "umgap_route_pack_dev", "umgap_lookup_hashes_dev", "umgap_route_scatter_dev", "umgap_classify_ids_dev",
     "umgap_route_sampled_applies", "umgap_route_pack_sampled_dev", "umgap_route_scatter_hits_dev", "umgap_classify_ids_masked_dev",
     "umgap_kernel_timing", "umgap_kernel_times", "umgap_kernel_launch_count", "umgap_transfer_bytes", "umgap_pipeline_slices", "umgap_pipeline_sampling",
@@ -495,6 +496,60 @@ def classify_reads_packed(index: Index, tax: Taxonomy, opts: PipelineOpts, codes
                                            _p(read_off), C.c_uint64(len(read_off) - 1), _p(group_off), C.c_uint64(ngroups),
                                            _p(out), C.byref(nl) if count_lookups else None))
     return out[:ngroups], (nl.value if count_lookups else None)
+
+
+class Pending:
+    """A batch enqueued by classify_reads_async / classify_reads_packed_async; wait() completes it and returns the
+    per-group taxa.  Keeps the host arrays of the batch alive until then."""
+
+    def __init__(self, handle, out, ngroups, keep):
+        self._h, self._out, self._n, self._keep = handle, out, ngroups, keep
+
+    def wait(self) -> np.ndarray:
+        h, self._h = self._h, None
+        if h is not None:
+            self._keep = None
+            _check(load_library().umgap_pending_wait(h))
+        return self._out[: self._n]
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None:
+            try:
+                load_library().umgap_pending_wait(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def classify_reads_async(index: Index, tax: Taxonomy, opts: PipelineOpts, nt: np.ndarray, read_off: np.ndarray,
+                         group_off: np.ndarray, out: Optional[np.ndarray] = None) -> Pending:
+    """umgap_classify_reads_async: enqueue the batch, return at once (page-locked arrays make the copies asynchronous)."""
+    nt = _arr(nt, np.uint8)
+    read_off = _arr(read_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    h = C.c_void_p()
+    _check(load_library().umgap_classify_reads_async(index._h, tax._h, C.byref(opts), _p(nt), _p(read_off), C.c_uint64(len(read_off) - 1),
+                                                     _p(group_off), C.c_uint64(ngroups), _p(out), C.byref(h)))
+    return Pending(h, out, ngroups, (nt, read_off, group_off, opts))
+
+
+def classify_reads_packed_async(index: Index, tax: Taxonomy, opts: PipelineOpts, codes: np.ndarray, entries: Optional[np.ndarray],
+                                read_off: np.ndarray, group_off: np.ndarray, out: Optional[np.ndarray] = None) -> Pending:
+    """umgap_classify_reads_packed_async."""
+    read_off = _arr(read_off, np.uint64)
+    group_off = _arr(group_off, np.uint64)
+    ngroups = len(group_off) - 1
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    ne = 0 if entries is None else len(entries)
+    h = C.c_void_p()
+    _check(load_library().umgap_classify_reads_packed_async(index._h, tax._h, C.byref(opts), _p(codes), _p(entries) if ne else None,
+                                                            C.c_uint64(ne), _p(read_off), C.c_uint64(len(read_off) - 1), _p(group_off),
+                                                            C.c_uint64(ngroups), _p(out), C.byref(h)))
+    return Pending(h, out, ngroups, (codes, entries, read_off, group_off, opts))
 
 
 def replicate(index: Index, tax: Taxonomy, devices: Sequence[int]):

@@ -69,6 +69,9 @@ struct umgap_index {
     // streams + events of the chunked host-buffer path
     mutable cudaStream_t chunk_stream[6] = {};
     mutable cudaEvent_t chunk_done[6] = {};
+    // batches enqueued by the asynchronous host-buffer calls and not yet waited for; their device error slots
+    mutable uint32_t pending = 0, errq_next = 0, chunk_next = 0;
+    mutable bool errq_ready = false;
 
     umgap::TableView view() const {
         umgap::TableView v{};

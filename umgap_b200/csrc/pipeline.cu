@@ -1359,7 +1359,9 @@ using namespace umgap;
 constexpr int kMaxBufs = 6;  // chunk streams of the host-buffer path, each with its own set of buffers
 enum { WS_ERR = 0, WS_NT = 1, WS_ROFF = WS_NT + kMaxBufs, WS_GOFF = WS_ROFF + kMaxBufs, WS_OUT = WS_GOFF + kMaxBufs, WS_HITS = WS_OUT + kMaxBufs,
        WS_IDS = WS_HITS + kMaxBufs, WS_SCRATCH = WS_IDS + kMaxBufs, WS_LONG = WS_SCRATCH + kMaxBufs,
-       WS_END = WS_LONG + kMaxBufs };
+       WS_ERRQ = WS_LONG + kMaxBufs, WS_END = WS_ERRQ + 1 };
+constexpr uint32_t kErrRing = 64;  // device error slots of the batches in flight (umgap_classify_reads*_async)
+constexpr uint32_t kMaxPending = 32;
 static_assert(WS_END <= Workspace::kSlots, "workspace slots");
 
 static ClassifyParams make_params(const umgap_index* idx, const umgap_pipeline_opts* o) {
@@ -1982,11 +1984,23 @@ struct HostReads {  // one of the two host forms of a batch's nucleotides
 
 }  // namespace
 
+}  // extern "C++"
+// A batch enqueued by umgap_classify_reads[_packed]_async: one event per chunk stream behind its last operation, and
+// the device slot its classify kernels report an unknown taxon to.
+struct umgap_pending {
+    const umgap_index* idx = nullptr;
+    cudaEvent_t ev[kMaxBufs] = {};
+    int nev = 0;
+    DevError* err = nullptr;
+};
+extern "C++" {
+
 // Groups [g_begin, g_end) of the batch (the whole batch by default; umgap_classify_reads_multi hands every GPU its range).
+// pend != nullptr: the call returns once everything is enqueued (umgap_pending_wait completes it).
 static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
                           const HostReads& hr, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
                           uint64_t ngroups, uint32_t* taxon_out, uint64_t* n_lookups, uint64_t g_begin = 0,
-                          uint64_t g_end = ~0ull) {
+                          uint64_t g_end = ~0ull, umgap_pending* pend = nullptr) {
     check_opts(idx, tax, opts);
     if (!tax) UMGAP_FAIL(UMGAP_ERR_INVALID, "null taxonomy");
     const bool packed = hr.codes != nullptr;
@@ -2008,15 +2022,28 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
     // Chunked and software-pipelined over kBufs streams: while the kernels of chunk c run, the
     // nucleotides and offsets of the next chunks upload and the results of the previous one
     // download.  Offsets are uploaded as given and rebased on the device.
-    // nucleotides per chunk (measured best of 6..96 MiB x 3..6 streams: profiles/r01_e2e_chunk_sweep.log; UMGAP_CHUNK_MB, or
-    // UMGAP_CHUNK_NT in nucleotides, override it -- read per call, so that tests can move the chunk seams)
-    const uint64_t kChunkNt = []() -> uint64_t {
+    // nucleotides per chunk.  One batch at a time (profiles/r01_e2e_chunk_sweep.log, r02_async_chunk_sweep.log): 16 M for
+    // the byte form, 32 M for the packed form, which moves a quarter of the bytes (6.03 -> 5.87 ms per 1 M pairs); the
+    // first chunks are shorter so that the kernels start early.  Asynchronous batches overlap each other, so their chunks
+    // are as large as the workspaces should get -- equal parts of at most 64 M (5.58 ms; 16 M: 5.94 ms; device-resident:
+    // 5.41 ms).  UMGAP_CHUNK_MB, or UMGAP_CHUNK_NT in nucleotides, override it -- read per call, so that tests can move
+    // the chunk seams.
+    bool chunk_env = false;
+    const uint64_t kChunkNt = [&]() -> uint64_t {
         const char* n = getenv("UMGAP_CHUNK_NT");
+        chunk_env = true;
         if (n && strtoull(n, nullptr, 10)) return std::max<uint64_t>(512, strtoull(n, nullptr, 10));
         const char* e = getenv("UMGAP_CHUNK_MB");
         const uint64_t mb = e ? strtoull(e, nullptr, 10) : 0;
-        return (uint64_t)((mb ? mb : 16ull) << 20);
+        if (mb) return mb << 20;
+        chunk_env = false;
+        if (pend) {
+            const uint64_t total = nreads ? read_off[nreads] - read_off[0] : 0, cap = 64ull << 20;
+            return std::max<uint64_t>(1ull << 20, ceil_div(total, std::max<uint64_t>(1, ceil_div(total, cap))) + 4096);
+        }
+        return (hr.codes ? 32ull : 16ull) << 20;
     }();
+    const bool ramp = !pend || chunk_env;  // short first chunks
     static const int kBufs = [] {  // chunks in flight (streams); UMGAP_CHUNK_STREAMS overrides
         const char* e = getenv("UMGAP_CHUNK_STREAMS");
         const int v = e ? atoi(e) : 0;
@@ -2030,19 +2057,31 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
         }
     cudaStream_t* st = idx->chunk_stream;
     cudaEvent_t* done = idx->chunk_done;
-    DevError* err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
-    UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
+    DevError* err;
+    if (pend) {  // a slot of the ring: zero when handed out (cleared once here, and again by the wait that found it set)
+        DevError* ring = (DevError*)idx->ws.get(WS_ERRQ, kErrRing * sizeof(DevError));
+        if (!idx->errq_ready) {
+            UMGAP_CUDA(cudaMemset(ring, 0, kErrRing * sizeof(DevError)));
+            idx->errq_ready = true;
+        }
+        err = ring + (idx->errq_next++ % kErrRing);
+        pend->err = err;
+    } else {
+        err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
+        UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
+    }
     // nucleotides before group g (monotone in g): chunk ends are found by bisection
     auto nt_before = [&](uint64_t g) { return read_off[group_off[g]]; };
     g_end = std::min(g_end, ngroups);
     uint64_t g0 = g_begin;
-    int buf = 0, prev = -1;
+    // asynchronous batches continue the rotation over the chunk streams where the previous batch left it
+    int buf = pend ? (int)(idx->chunk_next % (uint32_t)kBufs) : 0, prev = -1;
     try {
         int chunk_no = 0;
         while (g0 < g_end) {
             const uint64_t nt0 = nt_before(g0);
             // the first chunks are short so that the kernels start early: 1/8, 1/4, 1/2 of a chunk, then full ones
-            const uint64_t limit = chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
+            const uint64_t limit = ramp && chunk_no < 3 ? kChunkNt >> (3 - chunk_no) : kChunkNt;
             ++chunk_no;
             uint64_t lo = g0 + 1, hi = g_end;  // largest g1 with nt_before(g1) - nt0 <= limit, at least g0 + 1
             while (lo < hi) {
@@ -2114,6 +2153,15 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
             buf = (buf + 1) % kBufs;
             g0 = g1;
         }
+        if (pend) {  // the results are complete when every chunk stream has passed this point
+            idx->chunk_next = (uint32_t)buf;
+            for (int i = 0; i < kBufs; ++i) {
+                UMGAP_CUDA(cudaEventCreateWithFlags(&pend->ev[pend->nev], cudaEventDisableTiming));
+                ++pend->nev;
+                UMGAP_CUDA(cudaEventRecord(pend->ev[pend->nev - 1], st[i]));
+            }
+            return;
+        }
         for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
         DevError he;
         UMGAP_CUDA(cudaMemcpy(&he, err, sizeof he, cudaMemcpyDeviceToHost));
@@ -2148,6 +2196,68 @@ int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* ta
         hr.n_count = n_count;
         classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, n_lookups);
     });
+}
+
+// The asynchronous forms: everything of the batch is enqueued on the handle's chunk streams and the call returns; the
+// next batch can be handed over while this one runs, so that its uploads and first kernels fill the tail of this one.
+extern "C++" static int classify_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts, const HostReads& hr,
+                          const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out,
+                          umgap_pending** out) {
+    umgap_pending* p = nullptr;
+    const int rc = guarded([&] {
+        if (!out) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        *out = nullptr;
+        if (!idx) UMGAP_FAIL(UMGAP_ERR_INVALID, "null index");
+        if (idx->pending >= kMaxPending) UMGAP_FAIL(UMGAP_ERR_INVALID, "more than %u batches in flight on one index", kMaxPending);
+        p = new umgap_pending();
+        p->idx = idx;
+        classify_host(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, nullptr, 0, ~0ull, p);
+        ++idx->pending;
+        *out = p;
+    });
+    if (rc != UMGAP_OK && p) {
+        for (int i = 0; i < p->nev; ++i) cudaEventDestroy(p->ev[i]);
+        delete p;
+    }
+    return rc;
+}
+
+int umgap_classify_reads_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts, const uint8_t* nt,
+                               const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off, uint64_t ngroups,
+                               uint32_t* taxon_out, umgap_pending** out) {
+    HostReads hr;
+    hr.nt = nt;
+    return classify_async(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, out);
+}
+
+int umgap_classify_reads_packed_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
+                                      const uint32_t* codes, const uint64_t* n_entries, uint64_t n_count, const uint64_t* read_off,
+                                      uint64_t nreads, const uint64_t* group_off, uint64_t ngroups, uint32_t* taxon_out,
+                                      umgap_pending** out) {
+    if ((nreads && !codes) || (n_count && !n_entries)) return guarded([&] { UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument"); });
+    HostReads hr;
+    hr.codes = codes;
+    hr.n_entries = n_entries;
+    hr.n_count = n_count;
+    return classify_async(idx, tax, opts, hr, read_off, nreads, group_off, ngroups, taxon_out, out);
+}
+
+int umgap_pending_wait(umgap_pending* p) {
+    if (!p) return UMGAP_OK;
+    const int rc = guarded([&] {
+        use_device(p->idx->device);
+        for (int i = 0; i < p->nev; ++i) UMGAP_CUDA(cudaEventSynchronize(p->ev[i]));
+        DevError he{};
+        if (p->err) {
+            UMGAP_CUDA(cudaMemcpy(&he, p->err, sizeof he, cudaMemcpyDeviceToHost));
+            if (he.flag) UMGAP_CUDA(cudaMemset(p->err, 0, sizeof(DevError)));
+        }
+        raise_dev_error(he);
+    });
+    for (int i = 0; i < p->nev; ++i) cudaEventDestroy(p->ev[i]);
+    if (p->idx->pending) --p->idx->pending;
+    delete p;
+    return rc;
 }
 
 
