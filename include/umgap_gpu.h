@@ -210,6 +210,14 @@ int umgap_seedextend_ranked(const umgap_taxonomy* tax, const uint32_t* taxa, con
 int umgap_aggregate(const umgap_taxonomy* tax, const uint32_t* taxa, const uint64_t* rec_off,
                     uint64_t nrecs, int strategy, float factor, float lower_bound,
                     int ranked_only, uint32_t* taxon_out);
+/* taxa2agg -s (taxa2agg.rs:141-148, 162-170): every id carries an f32 score ("taxon=score"); a taxon's weight is the sum
+ * of its scores in input order, the lower bound applies to the sums, and every later f32 addition follows the
+ * reference's order (rmq/rtl.rs:43-46 walking up; tree/mod.rs:75-80 and 95-96 with a node's children in ascending
+ * taxon id, one of the HashSet orders the reference can take).  An unknown taxon raises only when it survives the
+ * lower bound.  One thread per record: the mode is used by no preset of scripts/umgap-analyse.sh.                 */
+int umgap_aggregate_scored(const umgap_taxonomy* tax, const uint32_t* taxa, const float* scores, const uint64_t* rec_off,
+                           uint64_t nrecs, int strategy, float factor, float lower_bound, int ranked_only,
+                           uint32_t* taxon_out);
 
 /* ---- fused path: translate -a | prot2kmer2lca [-o] | [seedextend] | uniq -d | taxa2agg
  * (scripts/umgap-analyse.sh:276-311) without materialising text between the stages.       */

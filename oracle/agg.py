@@ -33,6 +33,14 @@ def count(ids: Iterable[int]) -> Dict[int, np.float32]:
     return c
 
 
+def count_scored(pairs: Iterable[Tuple[int, float]]) -> Dict[int, np.float32]:
+    """agg/mod.rs:27-36 with the scored parser (taxa2agg.rs:141-148): a taxon's f32 scores added in input order."""
+    c: Dict[int, np.float32] = {}
+    for t, sc in pairs:
+        c[t] = f32(c.get(t, f32(0.0)) + f32(sc))
+    return c
+
+
 def filter_counts(c: Dict[int, np.float32], lower_bound: float) -> Dict[int, np.float32]:
     """agg/mod.rs:39-44."""
     lb = f32(lower_bound)
@@ -48,8 +56,9 @@ class _Tree:
         self.children = children
 
 
-def _tree_new(tax: Taxonomy, taxons: Dict[int, np.float32]) -> _Tree:
-    """tree/mod.rs:29-67."""
+def _tree_new(tax: Taxonomy, taxons: Dict[int, np.float32], order=sorted) -> _Tree:
+    """tree/mod.rs:29-67.  `order` arranges a node's children (a HashSet in the reference: any order can occur;
+    it matters only to the rounding of f32 sums of scored input)."""
     tree: Dict[int, Set[int]] = {}
     queue = list(taxons.keys())
     qi = 0
@@ -65,7 +74,7 @@ def _tree_new(tax: Taxonomy, taxons: Dict[int, np.float32]) -> _Tree:
 
     def create(root: int) -> _Tree:
         return _Tree(root, taxons.get(root, f32(0.0)),
-                     [create(c) for c in sorted(tree.get(root, ()))])
+                     [create(c) for c in order(tree.get(root, ()))])
 
     import sys
     sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
@@ -91,19 +100,19 @@ def _aggregate(t: _Tree) -> _Tree:
     return _Tree(t.root, value, children)
 
 
-def lca_star(tax: Taxonomy, taxons: Dict[int, np.float32]) -> int:
+def lca_star(tax: Taxonomy, taxons: Dict[int, np.float32], order=sorted) -> int:
     """tree/lca.rs:34-40.  Deterministic."""
     if not taxons:
         raise EmptyInput()
-    return _collapse(_tree_new(tax, taxons)).root
+    return _collapse(_tree_new(tax, taxons, order)).root
 
 
-def hybrid(tax: Taxonomy, taxons: Dict[int, np.float32], factor: float) -> Set[int]:
+def hybrid(tax: Taxonomy, taxons: Dict[int, np.float32], factor: float, order=sorted) -> Set[int]:
     """tree/mix.rs:43-64.  Returns every answer reachable through tied maxima."""
     if not taxons:
         raise EmptyInput()
     fac = f32(factor)
-    subtree = _aggregate(_collapse(_tree_new(tax, taxons)))
+    subtree = _aggregate(_collapse(_tree_new(tax, taxons, order)))
     results: Set[int] = set()
 
     def descend(base: _Tree):
@@ -174,4 +183,31 @@ def taxa2agg_record(tax: Taxonomy, snapping: Sequence[Optional[int]], ids: Seque
         if s is None:
             raise UnknownTaxon(a)   # `.unwrap()` panic in the reference (:178)
         out.add(s)
+    return out
+
+
+def taxa2agg_record_scored(tax: Taxonomy, snapping: Sequence[Optional[int]], pairs: Sequence[Tuple[int, float]],
+                           strategy: int, factor: float = 0.25, lower_bound: float = 0.0, orders=(sorted,)) -> Set[int]:
+    """taxa2agg.rs:159-181 with -s for one record of (taxon, score) pairs.  `orders`: the child orders under which the
+    induced tree is summed (the reference iterates a HashSet; `sorted` = ascending taxon id is the order of the device
+    kernel); the result is the union over them and over tied maxima."""
+    counts = filter_counts(count_scored((t, sc) for t, sc in pairs if t != 0), lower_bound)
+    if not counts:
+        return {1}
+    res: Set[int] = set()
+    if strategy == LCA_STAR:
+        res = {lca_star(tax, counts)}
+    elif strategy == HYBRID:
+        for o in orders:
+            res |= hybrid(tax, counts, factor, o)
+    elif strategy == MRTL:
+        res = mrtl(tax, counts)
+    else:
+        raise ValueError("unknown strategy")
+    out = set()
+    for a in res:
+        sn = snapping[a]
+        if sn is None:
+            raise UnknownTaxon(a)
+        out.add(sn)
     return out

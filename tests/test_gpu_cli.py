@@ -78,6 +78,21 @@ def test_stagewise_pipeline_matches_oracle_text(files):
         assert len(got) == len(want)
         for (gh, gs), (wh, ws) in zip(got, want):
             assert gh == wh and len(gs) == 1 and int(gs[0]) in ws, (gh, gs, ws)
+    # taxa2agg -s: "taxon=score" lines (taxa2agg.rs:141-148); scores derived from the ids, short decimals
+    scored_in = "".join(f">{h}\n" + "".join(f"{t}={(int(t) % 7 + 1) / 4}\n" for t in seq) for h, seq in ofasta.read_records(u_out, False))
+    from oracle import agg as oagg
+    for flags, strategy, lb in [(["-s", "-a", "lca*", "-l", "1.5"], 0, 1.5), (["-s"], 1, 0.0), (["-s", "-m", "rmq", "-a", "mrtl", "-l", "0.5"], 2, 0.5)]:
+        rc, a_out, err = run(["taxa2agg"] + flags + [str(d / "taxons.tsv")], scored_in)
+        assert rc == 0, err
+        got = list(ofasta.read_records(a_out, False))
+        recs = list(ofasta.read_records(scored_in, False))
+        assert len(got) == len(recs)
+        snapping = files["otax"].snapping(False)
+        for (gh, gs), (wh, ws) in zip(got, recs):
+            pairs = [(int(x.split("=")[0]), float(x.split("=")[1])) for x in ws]
+            assert gh == wh and len(gs) == 1 and int(gs[0]) in oagg.taxa2agg_record_scored(files["otax"], snapping, pairs, strategy, 0.25, lb), gh
+    rc, out, err = run(["taxa2agg", "-s", str(d / "taxons.tsv")], ">r\n5\n")
+    assert rc == 1 and "Taxon without score" in err
     # the fused command prints what the five-stage pipe prints
     rc, c_out, err = run(["classify", "-s", "3", "-a", "lca*", str(d / "nine.fst"), str(d / "taxons.tsv")], files["fasta"])
     assert rc == 0, err

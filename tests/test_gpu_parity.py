@@ -1009,3 +1009,66 @@ def test_async_host_calls_match_the_synchronous_ones(capi, world):
     for t in tickets:
         t.wait()
     capi.classify_reads_async(gidx, gtax, capi.default_opts(), *batches[0][:3]).wait()
+
+
+def test_scored_aggregation_matches_oracle(capi, world):
+    """umgap_aggregate_scored (taxa2agg -s, taxa2agg.rs:141-148): f32 scores summed in the reference's orders.  Against the
+    oracle's literal restatement: equality where its answer is unique, membership in the set of tied maxima / child
+    orders otherwise; with all scores 1.0 the unscored kernels' answers; an unknown taxon raises only when its sum
+    reaches the lower bound (the reference filters before the aggregator sees it, taxa2agg.rs:169-170), in both kernels."""
+    rng = random.Random(515)
+    otax = world["otax"]
+    ids = [t[0] for t in otax.by_id if t is not None]
+    recs = [[], [(0, 1.5)], [(ids[3], 0.25)], [(ids[3], 0.1)] * 7]
+    for _ in range(400):
+        home = rng.choice(ids)
+        path = otax.root_path(home)
+        r = []
+        for _ in range(rng.choice([1, 2, 3, 6, 12, 40, 150])):
+            u = rng.random()
+            t = 0 if u < 0.15 else home if u < 0.5 else rng.choice(path) if u < 0.8 else rng.choice(ids)
+            sc = rng.choice([1.0, 0.5, 0.1, 0.3, 2.75, float(np.float32(rng.random())), float(np.float32(rng.random() * 1e-3)), 1e6 + 0.5])
+            r.append((t, sc))
+        recs.append(r)
+    flat = np.array([t for r in recs for t, _ in r] or [0], dtype=np.uint32)
+    sc = np.array([s for r in recs for _, s in r] or [0], dtype=np.float32)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    np.cumsum([len(r) for r in recs], out=off[1:])
+    shuffles = [sorted] + [(lambda seed: (lambda xs: random.Random(seed).sample(sorted(xs), len(xs))))(k) for k in range(3)]
+    unique = 0
+    for strategy in (capi.AGG_LCA_STAR, capi.AGG_HYBRID, capi.AGG_MRTL):
+        for factor in ((0.25, 0.0, 0.5, 1.0) if strategy == capi.AGG_HYBRID else (0.25,)):
+            for lb in (0.0, 0.75, 2.0):
+                for ranked in (False, True):
+                    got = capi.aggregate_scored(world["gtax"], flat, sc, off, strategy, factor, lb, ranked)
+                    snapping = otax.snapping(ranked)
+                    for i, r in enumerate(recs):
+                        mine = oagg.taxa2agg_record_scored(otax, snapping, r, strategy, factor, lb)          # the kernel's child order
+                        anyorder = oagg.taxa2agg_record_scored(otax, snapping, r, strategy, factor, lb, shuffles)
+                        assert int(got[i]) in mine and mine <= anyorder, (strategy, factor, lb, ranked, r, int(got[i]), mine)
+                        unique += len(anyorder) == 1
+    assert unique > 5000
+    # scores of 1.0 are the unscored input (taxa2agg.rs:150-152)
+    ones = np.ones_like(sc)
+    for strategy in (capi.AGG_LCA_STAR, capi.AGG_HYBRID, capi.AGG_MRTL):
+        a = capi.aggregate_scored(world["gtax"], flat, ones, off, strategy, 0.25, 1.0)
+        b = capi.aggregate(world["gtax"], flat, off, strategy, 0.25, 1.0)
+        assert np.array_equal(a, b), strategy
+    # an id the tree does not hold: filtered away below the lower bound, an error when it survives
+    unknown = max(ids) + 77
+    rec_t = np.array([ids[5], ids[5], unknown, ids[9], ids[9]], dtype=np.uint32)
+    rec_s = np.array([1.0, 1.0, 1.0, 1.0, 1.0], dtype=np.float32)
+    o2 = np.array([0, 5], dtype=np.uint64)
+    want = oagg.taxa2agg_record(otax, otax.snapping(False), [int(x) for x in rec_t], oagg.LCA_STAR, 0.25, 2.0)
+    assert int(capi.aggregate_scored(world["gtax"], rec_t, rec_s, o2, capi.AGG_LCA_STAR, 0.25, 2.0)[0]) in want
+    assert int(capi.aggregate(world["gtax"], rec_t, o2, capi.AGG_LCA_STAR, 0.25, 2.0)[0]) in want
+    big = np.array([ids[5], ids[5], unknown] + [ids[k] for k in range(10, 60)] * 2, dtype=np.uint32)   # the list path of the warp kernel
+    o3 = np.array([0, len(big)], dtype=np.uint64)
+    want = oagg.taxa2agg_record(otax, otax.snapping(False), [int(x) for x in big], oagg.MRTL, 0.25, 2.0)
+    assert int(capi.aggregate(world["gtax"], big, o3, capi.AGG_MRTL, 0.25, 2.0)[0]) in want
+    for fn in (lambda: capi.aggregate_scored(world["gtax"], rec_t, rec_s, o2, capi.AGG_LCA_STAR, 0.25, 1.0),
+               lambda: capi.aggregate(world["gtax"], rec_t, o2, capi.AGG_LCA_STAR, 0.25, 1.0),
+               lambda: capi.aggregate(world["gtax"], big, o3, capi.AGG_MRTL, 0.25, 1.0)):
+        with pytest.raises(capi.UmgapError) as e:
+            fn()
+        assert f"Unknown Taxon ID: {unknown}" in str(e.value)

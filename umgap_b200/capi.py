@@ -31,7 +31,7 @@ SYMBOLS = [
     "umgap_translate_bound", "umgap_translate",
     "umgap_kmer_lookup_bound", "umgap_kmer_lookup",
     "umgap_tryp_lookup_bound", "umgap_tryp_lookup",
-    "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate",
+    "umgap_seedextend", "umgap_seedextend_ranked", "umgap_aggregate", "umgap_aggregate_scored",
     "umgap_fst_writer_open", "umgap_fst_writer_insert", "umgap_fst_writer_finish", "umgap_fst_writer_abort", "umgap_fst_stream",
     "umgap_kernel_times_ex", "umgap_exchange_bucket_cap", "umgap_exchange_region_bytes", "umgap_exchange_create", "umgap_exchange_create_lane", "umgap_exchange_free",
     "umgap_exchange_classify_dev", "umgap_exchange_status", "umgap_sharded_create", "umgap_sharded_free",
@@ -408,6 +408,19 @@ def aggregate(tax: Taxonomy, taxa: np.ndarray, rec_off: np.ndarray, strategy: in
     _check(lib.umgap_aggregate(tax._h, _p(taxa), _p(rec_off), C.c_uint64(nrecs), C.c_int(strategy),
                                C.c_float(factor), C.c_float(lower_bound),
                                C.c_int(int(ranked_only)), _p(out)))
+    return out[:nrecs]
+
+
+def aggregate_scored(tax: Taxonomy, taxa: np.ndarray, scores: np.ndarray, rec_off: np.ndarray, strategy: int,
+                     factor: float = 0.25, lower_bound: float = 0.0, ranked_only: bool = False):
+    """umgap_aggregate_scored (taxa2agg -s)."""
+    taxa = _arr(taxa, np.uint32)
+    scores = _arr(scores, np.float32)
+    rec_off = _arr(rec_off, np.uint64)
+    nrecs = len(rec_off) - 1
+    out = np.zeros(max(nrecs, 1), dtype=np.uint32)
+    _check(load_library().umgap_aggregate_scored(tax._h, _p(taxa), _p(scores), _p(rec_off), C.c_uint64(nrecs), C.c_int(strategy),
+                                                 C.c_float(factor), C.c_float(lower_bound), C.c_int(int(ranked_only)), _p(out)))
     return out[:nrecs]
 
 

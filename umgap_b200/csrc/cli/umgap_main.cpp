@@ -655,11 +655,57 @@ int cmd_taxa2agg(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'s', "scored", false}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
                                    {'f', "factor", true}, {'l', "lower-bound", true}});
     if (a.pos.size() != 1) fail("The following required arguments were not provided:\n    <taxon-file>");
-    if (a.has("scored")) fail("taxa2agg --scored is not implemented on the GPU path");
     const int st = parse_strategy(a.get("method", "tree"), a.get("aggregate", "hybrid"));
     const float factor = parse_f32(a.get("factor", "0.25")), lb = parse_f32(a.get("lower-bound", "0"));
     TaxHandle tax;
     check(umgap_taxonomy_load(a.pos[0].c_str(), 0, &tax.p));
+    if (a.has("scored")) {  // -s: every line is "taxon=score" (taxa2agg.rs:141-148) -> umgap_aggregate_scored
+        FastaReader rd(stdin, false);
+        Record r;
+        std::vector<std::string> heads;
+        std::vector<uint32_t> ids, res;
+        std::vector<float> scores;
+        std::vector<uint64_t> off{0};
+        std::string out;
+        auto flush = [&]() {
+            if (heads.empty()) return;
+            res.assign(heads.size(), 0);
+            ids.push_back(0);
+            scores.push_back(0);
+            check(umgap_aggregate_scored(tax.p, ids.data(), scores.data(), off.data(), heads.size(), st, factor, lb, a.has("ranked"), res.data()));
+            out.clear();
+            for (size_t i = 0; i < heads.size(); ++i) {
+                out += '>';
+                out += heads[i];
+                out += '\n';
+                append_u32(out, res[i]);
+                out += '\n';
+            }
+            put(stdout, out);
+            heads.clear();
+            ids.clear();
+            scores.clear();
+            off.assign(1, 0);
+        };
+        while (rd.next(r)) {
+            for (const std::string& pair : r.seq) {
+                const size_t eq = pair.find('=');
+                if (eq == std::string::npos || pair.find('=', eq + 1) != std::string::npos) fail("Taxon without score");
+                const std::string t = pair.substr(0, eq);
+                if (t.empty() || t.find_first_not_of("0123456789") != std::string::npos) fail("invalid digit found in string");
+                errno = 0;
+                const unsigned long long v = strtoull(t.c_str(), nullptr, 10);
+                if (errno || v >= 0xFFFFFFFFull) fail("taxon id out of range: " + t);
+                ids.push_back((uint32_t)v);
+                scores.push_back(parse_f32(pair.substr(eq + 1)));
+            }
+            off.push_back(ids.size());
+            heads.push_back(r.header);
+            if (heads.size() >= kBatchRecords) flush();
+        }
+        flush();
+        return 0;
+    }
     BlockReader br(stdin);
     IdBatch b;
     std::vector<uint32_t> res;

@@ -254,6 +254,187 @@ void launch_aggregate(const umgap_taxonomy* tax, int strategy, float factor, flo
     UMGAP_CUDA(cudaGetLastError());
 }
 
+
+// ---- taxa2agg -s: scored input (taxa2agg.rs:141-148: "taxon=score" pairs) ------------------------------------------
+// The weights are f32 sums, so the ORDER of every addition is part of the result.  One thread per record, the
+// reference's own orders: a taxon's score is summed in input order (agg/mod.rs:31-34); MRTL adds the ancestors' sums
+// walking up from the taxon (rmq/rtl.rs:43-46); the induced tree sums a chain of single children top-down
+// (tree/mod.rs:75-80) and a node's children after its own value (tree/mod.rs:95-96) -- in HashSet order there, in
+// ascending taxon id here (= preorder of the sorted member list: taxonomy.cu numbers siblings by ascending id), one of
+// the orders the reference can take.  Ties as in the unscored kernels: the first maximum in preorder.  An unknown taxon
+// raises only if it survives the lower bound (it never reaches the aggregator otherwise, taxa2agg.rs:169-170).
+// Scratch per record: its slice of A (u32) and W (f32), as long as the record.
+struct ScoredRec {
+    const TaxView& tv;
+    const uint32_t* A;  // distinct kept members: dense index, ascending
+    const float* W;     // their summed scores
+};
+
+__device__ uint32_t scored_lca(const TaxView& tv, uint32_t x, uint32_t y) {  // dense x <= y
+    if (x == y || __ldg(tv.last + x) >= y) return x;
+    uint32_t best = 0;
+    const uint32_t dmax = min((uint32_t)__ldg(tv.depth + x), (uint32_t)__ldg(tv.depth + y));
+    for (uint32_t d = 0; d <= dmax; ++d) {
+        const uint32_t ax = __ldg(tv.anc + (uint64_t)x * tv.stride + d);
+        if (ax != __ldg(tv.anc + (uint64_t)y * tv.stride + d)) break;
+        best = ax;
+    }
+    return best;
+}
+// End of the child group that starts at member j: the members below the same child (depth cd) of the node.
+__device__ uint32_t scored_group_end(const ScoredRec& r, uint32_t j, uint32_t hi, uint32_t cd) {
+    const uint32_t ch = __ldg(r.tv.anc + (uint64_t)r.A[j] * r.tv.stride + cd);
+    uint32_t e = j + 1;
+    while (e < hi && __ldg(r.tv.anc + (uint64_t)r.A[e] * r.tv.stride + cd) == ch) ++e;
+    return e;
+}
+// The collapsed node (tree/mod.rs:71-86) over members [lo, hi), all inside one subtree: its root and chain value;
+// on return [lo, hi) are the members below it and nk says whether it has children (0, or >= 2).
+__device__ void scored_node(const ScoredRec& r, uint32_t& lo, uint32_t hi, uint32_t& root, float& value, uint32_t& nk) {
+    value = 0.0f;  // T::default() of the nodes that are not members (tree/mod.rs:58)
+    for (;;) {
+        const uint32_t c = scored_lca(r.tv, r.A[lo], r.A[hi - 1]);
+        if (r.A[lo] == c) value = value + r.W[lo++];  // the node itself is a member; a chain adds top-down
+        root = c;
+        nk = 0;
+        if (lo >= hi) return;  // a leaf of the induced tree
+        const uint32_t cd = (uint32_t)__ldg(r.tv.depth + c) + 1;
+        nk = scored_group_end(r, lo, hi, cd) == hi ? 1u : 2u;
+        if (nk != 1) return;  // a fork ends the chain of single children
+    }
+}
+// Aggregated value (tree/mod.rs:90-101) of the collapsed subtree over members [lo, hi): the node's own value, then its
+// children's aggregated values in order.  Depth-first with an explicit stack (one frame per nested fork).
+constexpr int kScoredDepth = 256;  // depths are 8-bit
+__device__ float scored_subtree(const ScoredRec& r, uint32_t lo, uint32_t hi) {
+    uint32_t fj[kScoredDepth], fhi[kScoredDepth], fcd[kScoredDepth];
+    float fv[kScoredDepth];
+    int sp = 0;
+    uint32_t root, nk;
+    scored_node(r, lo, hi, root, fv[0], nk);
+    fj[0] = lo;
+    fhi[0] = hi;
+    fcd[0] = (uint32_t)__ldg(r.tv.depth + root) + 1;
+    for (;;) {
+        if (fj[sp] >= fhi[sp]) {  // every child added
+            const float v = fv[sp];
+            if (sp == 0) return v;
+            --sp;
+            fv[sp] = fv[sp] + v;
+            continue;
+        }
+        uint32_t clo = fj[sp];
+        const uint32_t chi = scored_group_end(r, clo, fhi[sp], fcd[sp]);
+        fj[sp] = chi;
+        ++sp;  // nested forks are strictly deeper: sp < 256
+        scored_node(r, clo, chi, root, fv[sp], nk);
+        fj[sp] = clo;
+        fhi[sp] = chi;
+        fcd[sp] = (uint32_t)__ldg(r.tv.depth + root) + 1;
+    }
+}
+
+__global__ void aggregate_scored_kernel(const TaxView tv, AggParams ap, const uint32_t* __restrict__ taxa, const float* __restrict__ scores,
+                                        const uint64_t* __restrict__ rec_off, uint64_t nrecs, uint32_t* __restrict__ sa,
+                                        float* __restrict__ sw, uint32_t* __restrict__ out, unsigned int* __restrict__ err) {
+    const uint64_t rec = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= nrecs) return;
+    const uint64_t lo = rec_off[rec], hi = rec_off[rec + 1];
+    uint32_t* A = sa + lo;
+    float* W = sw + lo;
+    // count (agg/mod.rs:27-36): first sight appends, later sights add in input order; zeros are dropped (taxa2agg.rs:169)
+    uint32_t m = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t id = taxa[i];
+        if (id == 0) continue;
+        uint32_t j = 0;
+        while (j < m && A[j] != id) ++j;
+        if (j == m) {
+            A[m] = id;
+            W[m] = 0.0f;
+            ++m;
+        }
+        W[j] = W[j] + scores[i];
+    }
+    // filter (agg/mod.rs:39-44)
+    uint32_t kept = 0;
+    for (uint32_t j = 0; j < m; ++j)
+        if (W[j] >= ap.lower_bound) {
+            A[kept] = A[j];
+            W[kept] = W[j];
+            ++kept;
+        }
+    m = kept;
+    if (m == 0) {
+        out[rec] = 1u;  // taxa2agg.rs:174-175
+        return;
+    }
+    // dense indices, ascending (insertion sort: records are short)
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t id = A[j];
+        const uint32_t d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
+        if (d == kNoTaxon) {
+            if (atomicCAS(&err[0], 0u, 1u) == 0u) err[1] = id;
+            out[rec] = UMGAP_ABSENT;
+            return;
+        }
+        const float w = W[j];
+        uint32_t k = j;
+        while (k > 0 && A[k - 1] > d) {
+            A[k] = A[k - 1];
+            W[k] = W[k - 1];
+            --k;
+        }
+        A[k] = d;
+        W[k] = w;
+    }
+    const ScoredRec r{tv, A, W};
+    uint32_t result;
+    if (ap.strategy == UMGAP_AGG_MRTL) {
+        float best = 0.0f;
+        uint32_t best_j = 0;
+        for (uint32_t j = 0; j < m; ++j) {
+            float w = W[j];
+            for (uint32_t i = j; i-- > 0;)  // the ancestors among the members, deepest first (rmq/rtl.rs:43-46)
+                if (__ldg(tv.last + A[i]) >= A[j]) w = w + W[i];
+            if (j == 0 || w > best) {
+                best = w;
+                best_j = j;
+            }
+        }
+        result = A[best_j];
+    } else {
+        uint32_t lo2 = 0, hi2 = m, root, nk;
+        float v;
+        float bval = ap.strategy == UMGAP_AGG_HYBRID ? scored_subtree(r, 0, m) : 0.0f;
+        scored_node(r, lo2, hi2, root, v, nk);  // LCA* = the root of the collapsed tree (tree/lca.rs:34-40)
+        if (ap.strategy == UMGAP_AGG_HYBRID) {
+            while (nk) {  // no children: stop (tree/mix.rs:51)
+                const uint32_t cd = (uint32_t)__ldg(tv.depth + root) + 1;
+                uint32_t bl = 0, bh = 0;
+                float best = 0.0f;
+                for (uint32_t j = lo2; j < hi2;) {  // the heaviest child, the first in order among equals
+                    const uint32_t e = scored_group_end(r, j, hi2, cd);
+                    const float sv = scored_subtree(r, j, e);
+                    if (j == lo2 || sv > best) {
+                        best = sv;
+                        bl = j;
+                        bh = e;
+                    }
+                    j = e;
+                }
+                if (__fdiv_rn(best, bval) < ap.factor) break;  // tree/mix.rs:57
+                lo2 = bl;
+                hi2 = bh;
+                bval = best;
+                scored_node(r, lo2, hi2, root, v, nk);
+            }
+        }
+        result = root;
+    }
+    out[rec] = ap.ranked_only ? __ldg(tv.snap_ranked + result) : __ldg(tv.snap_valid + result);
+}
+
 }  // namespace umgap
 
 using namespace umgap;
@@ -439,6 +620,37 @@ int umgap_aggregate(const umgap_taxonomy* tax, const uint32_t* taxa, const uint6
         AggParams ap{strategy, factor, lower_bound, ranked_only};
         aggregate_kernel<<<grid_for(nrecs, kStageAggWarps), kStageAggWarps * 32>>>(
             tax->view, ap, d_in.p, d_off.p, nrecs, d_scratch.p, d_out.p, d_err.p);
+        UMGAP_CUDA(cudaGetLastError());
+        unsigned int he[2];
+        UMGAP_CUDA(cudaMemcpy(he, d_err.p, 8, cudaMemcpyDeviceToHost));
+        UMGAP_CUDA(cudaMemcpy(taxon_out, d_out.p, nrecs * 4, cudaMemcpyDeviceToHost));
+        if (he[0]) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", he[1]);
+    });
+}
+
+int umgap_aggregate_scored(const umgap_taxonomy* tax, const uint32_t* taxa, const float* scores, const uint64_t* rec_off,
+                           uint64_t nrecs, int strategy, float factor, float lower_bound, int ranked_only, uint32_t* taxon_out) {
+    return guarded([&] {
+        if (!tax || !rec_off || (nrecs && !taxon_out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        if (strategy < UMGAP_AGG_LCA_STAR || strategy > UMGAP_AGG_MRTL)
+            UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", strategy);
+        if (!nrecs) return;
+        const uint64_t total = rec_off[nrecs];
+        if (total && (!taxa || !scores)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
+        use_device(tax->device);
+        DevBuf<uint32_t> d_in(total + 1), d_a(total + 1), d_out(nrecs);
+        DevBuf<float> d_sc(total + 1), d_w(total + 1);
+        DevBuf<uint64_t> d_off(nrecs + 1);
+        DevBuf<unsigned int> d_err(2);
+        if (total) {
+            UMGAP_CUDA(cudaMemcpy(d_in.p, taxa, total * 4, cudaMemcpyHostToDevice));
+            UMGAP_CUDA(cudaMemcpy(d_sc.p, scores, total * 4, cudaMemcpyHostToDevice));
+        }
+        UMGAP_CUDA(cudaMemcpy(d_off.p, rec_off, (nrecs + 1) * 8, cudaMemcpyHostToDevice));
+        UMGAP_CUDA(cudaMemset(d_err.p, 0, 8));
+        AggParams ap{strategy, factor, lower_bound, ranked_only};
+        aggregate_scored_kernel<<<(unsigned)ceil_div(nrecs, 64), 64>>>(tax->view, ap, d_in.p, d_sc.p, d_off.p, nrecs, d_a.p, d_w.p, d_out.p,
+                                                                       d_err.p);
         UMGAP_CUDA(cudaGetLastError());
         unsigned int he[2];
         UMGAP_CUDA(cudaMemcpy(he, d_err.p, 8, cudaMemcpyDeviceToHost));

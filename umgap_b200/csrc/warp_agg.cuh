@@ -262,19 +262,16 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
                                                    uint32_t* L, uint32_t n, const AggParams& ap,
                                                    int lane, uint32_t* bad_id) {
     if (n == 0) return 1u;
-    // 1. taxon id -> preorder index
-    bool bad = false;
+    // 1. taxon id -> preorder index.  An id the tree does not hold raises only if it survives the lower bound -- the
+    //    reference filters the counts before the aggregator sees them (taxa2agg.rs:169-170) -- so it is counted like
+    //    any other, under a marked value that sorts behind every index (ids that differ only in bit 31 would share it)
+    constexpr uint32_t kUnknownMark = 0x80000000u;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t id = A[i];
         const uint32_t d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
-        if (d == kNoTaxon) {
-            bad = true;
-            *bad_id = id;
-        }
-        A[i] = d;
+        A[i] = d == kNoTaxon ? (kUnknownMark | id) : d;
     }
     __syncwarp();
-    if (__any_sync(0xffffffffu, bad)) return kAggUnknown;
     // 2. sort, 3. distinct + run starts
     warp_sort<KV>(A, C, n, lane);
     uint32_t occurrences = n;
@@ -338,6 +335,13 @@ __device__ __forceinline__ uint32_t warp_aggregate(const TaxView& tv, uint32_t* 
     }
     m = kept;
     if (m == 0) return 1u;  // everything filtered: the literal "1"
+    {
+        const uint32_t tail = A[m - 1];  // marked values sort last
+        if (tail & kUnknownMark) {
+            *bad_id = tail & ~kUnknownMark;
+            return kAggUnknown;
+        }
+    }
     if (lane == 0) P[m] = running;
     for (uint32_t j = lane; j < m; j += 32) L[j] = __ldg(tv.last + A[j]);
     __syncwarp();
@@ -425,14 +429,13 @@ __device__ __forceinline__ uint32_t warp_aggregate_distinct(const TaxView& tv, u
     if (n == 0) return 1u;
     const bool have = (uint32_t)lane < n;
     uint32_t d = kNoTaxon;
-    if (have) {
-        d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
-        if (d == kNoTaxon) *bad_id = id;
-    }
-    if (__any_sync(0xffffffffu, have && d == kNoTaxon)) return kAggUnknown;
+    if (have) d = id <= tv.max_id ? __ldg(tv.dense_of + id) : kNoTaxon;
     // lower-bound filter first (agg/mod.rs:39-44, f32 compare), then a rank sort of the kept members: the dozen
     // members of a typical record take a dozen shuffles, a sorting network over all 32 lanes takes 15 steps of two
     const bool keep = have && (float)cnt >= ap.lower_bound;
+    // an id the tree does not hold raises only if it survives the filter (taxa2agg.rs:169-170 filters first)
+    if (keep && d == kNoTaxon) *bad_id = id;
+    if (__any_sync(0xffffffffu, keep && d == kNoTaxon)) return kAggUnknown;
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const uint32_t m = (uint32_t)__popc(mask);
     if (m == 0) return 1u;  // everything filtered: the literal "1"
