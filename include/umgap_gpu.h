@@ -50,7 +50,8 @@ typedef struct umgap_index umgap_index;       /* GPU-resident key -> taxon table
 typedef struct umgap_taxonomy umgap_taxonomy; /* GPU-resident tree: ancestor matrix etc.    */
 
 /* Aggregation strategies of `taxa2agg -a` (taxa2agg.rs:111-139, 186-221). */
-enum { UMGAP_AGG_LCA_STAR = 0, UMGAP_AGG_HYBRID = 1, UMGAP_AGG_MRTL = 2 };
+enum { UMGAP_AGG_LCA_STAR = 0, UMGAP_AGG_HYBRID = 1, UMGAP_AGG_MRTL = 2,
+       UMGAP_AGG_RMQ_HYBRID = 3 /* `-m rmq -a hybrid`, the LCA / MRTL mix of rmq/mix.rs:56-93: umgap_aggregate_scored only */ };
 
 /* ---- errors / device ------------------------------------------------------------------ */
 const char* umgap_last_error(void);
@@ -214,7 +215,8 @@ int umgap_aggregate(const umgap_taxonomy* tax, const uint32_t* taxa, const uint6
  * of its scores in input order, the lower bound applies to the sums, and every later f32 addition follows the
  * reference's order (rmq/rtl.rs:43-46 walking up; tree/mod.rs:75-80 and 95-96 with a node's children in ascending
  * taxon id, one of the HashSet orders the reference can take).  An unknown taxon raises only when it survives the
- * lower bound.  One thread per record: the mode is used by no preset of scripts/umgap-analyse.sh.                 */
+ * lower bound.  One thread per record: the mode is used by no preset of scripts/umgap-analyse.sh.  Also takes
+ * UMGAP_AGG_RMQ_HYBRID (taxa2agg -m rmq -a hybrid, rmq/mix.rs:56-93; unscored input = scores of 1.0).            */
 int umgap_aggregate_scored(const umgap_taxonomy* tax, const uint32_t* taxa, const float* scores, const uint64_t* rec_off,
                            uint64_t nrecs, int strategy, float factor, float lower_bound, int ranked_only,
                            uint32_t* taxon_out);

@@ -160,7 +160,45 @@ def mrtl(tax: Taxonomy, taxons: Dict[int, np.float32]) -> Set[int]:
     return {t for t, v in rtl.items() if v == m}
 
 
-LCA_STAR, HYBRID, MRTL = 0, 1, 2
+def _lca(tax: Taxonomy, a: int, b: int) -> int:
+    """The plain LCA of two taxa (what rmq/lca.rs:42-47 computes through the Euler tour: the shallowest node between
+    their first occurrences is their lowest common ancestor whichever of equal minima the RMQ returns)."""
+    pa, pb = tax.root_path(a), tax.root_path(b)
+    j = 0
+    while j < min(len(pa), len(pb)) and pa[j] == pb[j]:
+        j += 1
+    return pa[j - 1]
+
+
+def rmq_mix(tax: Taxonomy, taxons: Dict[int, np.float32], factor: float) -> Set[int]:
+    """rmq/mix.rs:56-93 (`-m rmq -a hybrid`).  Returns the set of arg-maxima (max_by_key over a HashMap)."""
+    fac = f32(factor)
+    weights: Dict[int, List[np.float32]] = {}
+    queue = list(taxons.keys())
+    qi = 0
+    while qi < len(queue):
+        left = queue[qi]
+        qi += 1
+        if left in weights:
+            continue
+        for right, cnt in taxons.items():
+            lca = _lca(tax, left, right)      # :71 (UnknownTaxon from first_occurence)
+            if lca == left or lca == right:
+                w = weights.setdefault(left, [f32(0.0), f32(0.0)])
+                if lca == left:
+                    w[0] = f32(w[0] + cnt)    # weight.lca
+                if lca == right:
+                    w[1] = f32(w[1] + cnt)    # weight.rtl
+            else:
+                queue.append(lca)
+    if not weights:
+        raise EmptyInput()
+    val = {t: f32(f32(w[0] * fac) + f32(w[1] * f32(f32(1.0) - fac))) for t, w in weights.items()}   # :49-51
+    m = max(val.values())
+    return {t for t, v in val.items() if v == m}
+
+
+LCA_STAR, HYBRID, MRTL, RMQ_HYBRID = 0, 1, 2, 3
 
 
 def taxa2agg_record(tax: Taxonomy, snapping: Sequence[Optional[int]], ids: Sequence[int],
@@ -202,6 +240,8 @@ def taxa2agg_record_scored(tax: Taxonomy, snapping: Sequence[Optional[int]], pai
             res |= hybrid(tax, counts, factor, o)
     elif strategy == MRTL:
         res = mrtl(tax, counts)
+    elif strategy == RMQ_HYBRID:
+        res = rmq_mix(tax, counts, factor)
     else:
         raise ValueError("unknown strategy")
     out = set()

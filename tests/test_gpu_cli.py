@@ -91,6 +91,11 @@ def test_stagewise_pipeline_matches_oracle_text(files):
         for (gh, gs), (wh, ws) in zip(got, recs):
             pairs = [(int(x.split("=")[0]), float(x.split("=")[1])) for x in ws]
             assert gh == wh and len(gs) == 1 and int(gs[0]) in oagg.taxa2agg_record_scored(files["otax"], snapping, pairs, strategy, 0.25, lb), gh
+    rc, a_out, err = run(["taxa2agg", "-m", "rmq", "-a", "hybrid", "-f", "0.5", str(d / "taxons.tsv")], u_out)   # rmq/mix.rs
+    assert rc == 0 and "Warning: this is a hybrid between LCA/MRTL" in err
+    snapping = files["otax"].snapping(False)
+    for (gh, gs), (wh, ws) in zip(ofasta.read_records(a_out, False), ofasta.read_records(u_out, False)):
+        assert gh == wh and int(gs[0]) in oagg.taxa2agg_record_scored(files["otax"], snapping, [(int(x), 1.0) for x in ws], oagg.RMQ_HYBRID, 0.5), gh
     rc, out, err = run(["taxa2agg", "-s", str(d / "taxons.tsv")], ">r\n5\n")
     assert rc == 1 and "Taxon without score" in err
     # the fused command prints what the five-stage pipe prints

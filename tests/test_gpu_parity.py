@@ -1036,6 +1036,32 @@ def test_scored_aggregation_matches_oracle(capi, world):
     np.cumsum([len(r) for r in recs], out=off[1:])
     shuffles = [sorted] + [(lambda seed: (lambda xs: random.Random(seed).sample(sorted(xs), len(xs))))(k) for k in range(3)]
     unique = 0
+    # `-m rmq -a hybrid` (rmq/mix.rs:56-93) through the same entry point: unscored input and dyadic scores (its sums run
+    # in HashMap order in the reference: exact sums make every order agree), incl. the reference's own vectors
+    fx = [(1, "root", 0, 1, True), (2, "Bacteria", 1, 1, True), (10239, "Viruses", 1, 1, True), (12884, "Viroids", 1, 1, True),
+          (185751, "Pospiviroidae", 19, 12884, True), (185752, "Avsunviroidae", 19, 12884, True)]
+    ftax = capi.Taxonomy.from_arrays(*datagen.taxonomy_arrays(fx))
+    def mix(idl, f):
+        a = np.array(idl, dtype=np.uint32)
+        return int(capi.aggregate_scored(ftax, a, np.ones(len(idl), dtype=np.float32), np.array([0, len(idl)], dtype=np.uint64), capi.AGG_RMQ_HYBRID, f)[0])
+    assert mix([12884, 185751], 0.0) == 185751 and mix([12884, 185751, 185752, 185752], 0.0) == 185752
+    assert mix([1, 1, 10239, 10239, 10239, 12884, 185751, 185752], 0.0) == 10239
+    assert mix([12884, 185751], 1.0) == 12884 and mix([1, 1, 10239, 10239, 10239, 12884, 185751, 185752], 1.0) == 1
+    assert mix([12884, 12884, 185751], 0.5) == 12884 and mix([12884, 185751, 185751], 0.5) == 185751
+    assert mix([1, 12884, 12884, 185751, 185752], 0.5) == 12884
+    ftax.close()
+    dyadic = np.array([float(int(x * 8) % 5 + 1) / 4 for x in sc], dtype=np.float32)
+    for scores in (np.ones_like(sc), dyadic):
+        for factor in (0.25, 0.0, 0.5, 1.0):
+            for lb in (0.0, 1.0):
+                got = capi.aggregate_scored(world["gtax"], flat, scores, off, capi.AGG_RMQ_HYBRID, factor, lb)
+                snapping = otax.snapping(False)
+                k = 0
+                for i, r in enumerate(recs):
+                    pairs = [(t, float(scores[k + j])) for j, (t, _) in enumerate(r)]
+                    k += len(r)
+                    want = oagg.taxa2agg_record_scored(otax, snapping, pairs, oagg.RMQ_HYBRID, factor, lb)
+                    assert int(got[i]) in want, (factor, lb, pairs, int(got[i]), want)
     for strategy in (capi.AGG_LCA_STAR, capi.AGG_HYBRID, capi.AGG_MRTL):
         for factor in ((0.25, 0.0, 0.5, 1.0) if strategy == capi.AGG_HYBRID else (0.25,)):
             for lb in (0.0, 0.75, 2.0):

@@ -251,6 +251,35 @@ def test_mrtl_vectors(tax):
     assert M([1, 1, 185752, 185751, 1]) == {185751, 185752}
 
 
+# ---- rmq/mix.rs:102-126 (`-m rmq -a hybrid`)
+def test_rmq_mix_vectors(tax):
+    X = lambda ids, f: agg.rmq_mix(tax, cagg(ids), f)
+    assert X([12884, 185751], 0.0) == {185751}
+    assert X([12884, 185751, 185752, 185752], 0.0) == {185752}
+    assert X([1, 1, 10239, 10239, 10239, 12884, 185751, 185752], 0.0) == {10239}
+    assert X([12884, 185751], 1.0) == {12884}
+    assert X([12884, 185751, 185752, 185752], 1.0) == {12884}
+    assert X([1, 1, 10239, 10239, 10239, 12884, 185751, 185752], 1.0) == {1}
+    assert X([12884, 12884, 185751], 0.5) == {12884}
+    assert X([12884, 185751, 185751], 0.5) == {185751}
+    assert X([1, 12884, 12884, 185751, 185752], 0.5) == {12884}   # 3.5 against 2.5: no tie, whatever rmq/mix.rs:119 fears
+    with pytest.raises(agg.EmptyInput):
+        agg.rmq_mix(tax, {}, 0.5)
+
+
+# ---- taxa2agg -s (taxa2agg.rs:141-148, agg/mod.rs:27-44)
+def test_scored_counts_and_filter(tax):
+    c = agg.count_scored([(185751, 0.5), (12884, 0.25), (185751, 0.75), (0, 9.0)])
+    assert c[185751] == agg.f32(1.25) and c[12884] == agg.f32(0.25)
+    snap = tax.snapping(False)
+    rec = [(185751, 0.5), (185752, 0.25), (185751, 0.75), (0, 9.0)]
+    assert agg.taxa2agg_record_scored(tax, snap, rec, agg.LCA_STAR) == {12884}
+    assert agg.taxa2agg_record_scored(tax, snap, rec, agg.LCA_STAR, lower_bound=1.0) == {185751}   # 185752 sums to 0.25
+    assert agg.taxa2agg_record_scored(tax, snap, rec, agg.LCA_STAR, lower_bound=2.0) == {1}       # nothing left: literal 1
+    assert agg.taxa2agg_record_scored(tax, snap, rec, agg.MRTL) == {185751}
+    assert agg.taxa2agg_record_scored(tax, snap, [(t, 1.0) for t in (12884, 185751)], agg.HYBRID, 0.0) == {185751}
+
+
 # ---- commands/taxa2agg.rs:159-181
 def test_taxa2agg_record_loop(tax):
     out = pipeline.taxa2agg_sets(">a\n185751\n0\n185751\n12884\n>b\n0\n0\n>c\n", tax, agg.LCA_STAR)

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("UMGAP_GPU_LIB") or os.path.join(_HERE, "lib", "libumg
 MISS = 0xFFFFFFFF
 ABSENT = 0xFFFFFFFF
 AGG_LCA_STAR, AGG_HYBRID, AGG_MRTL = 0, 1, 2
+AGG_RMQ_HYBRID = 3
 
 # every symbol include/umgap_gpu.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [

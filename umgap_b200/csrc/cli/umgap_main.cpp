@@ -646,8 +646,12 @@ int parse_strategy(const std::string& method, const std::string& strategy) {
     else fail("Invalid strategy: " + strategy);
     if (tree && st == UMGAP_AGG_MRTL)  // taxa2agg.rs:134-138
         fail("Invalid invocation: Tree and MaximumRootToLeafPath cannot be combined");
+    if (rmq && st == UMGAP_AGG_HYBRID) {  // taxa2agg.rs:117-124
+        fputs("Warning: this is a hybrid between LCA/MRTL, not LCA*/MRTL\n", stderr);
+        return UMGAP_AGG_RMQ_HYBRID;
+    }
     if (rmq && st != UMGAP_AGG_MRTL)
-        fail("-m rmq -a " + strategy + " (the RMQ variants of lca*/hybrid) is not implemented on the GPU path; use -m tree");
+        fail("-m rmq -a lca* (an order-dependent fold over Euler-tour positions, rmq/lca.rs:60-90) is not implemented on the GPU path; use -m tree");
     return st;
 }
 
@@ -709,12 +713,18 @@ int cmd_taxa2agg(int argc, char** argv) {
     BlockReader br(stdin);
     IdBatch b;
     std::vector<uint32_t> res;
+    std::vector<float> ones;
     std::string out;
     auto flush = [&]() {
         if (!b.size()) return;
         res.assign(b.size(), 0);
         b.ids.push_back(0);
-        check(umgap_aggregate(tax.p, b.ids.data(), b.off.data(), b.size(), st, factor, lb, a.has("ranked"), res.data()));
+        if (st == UMGAP_AGG_RMQ_HYBRID) {  // the serial kernel of the scored mode, every score 1.0 (taxa2agg.rs:150-152)
+            ones.assign(b.ids.size(), 1.0f);
+            check(umgap_aggregate_scored(tax.p, b.ids.data(), ones.data(), b.off.data(), b.size(), st, factor, lb, a.has("ranked"), res.data()));
+        } else {
+            check(umgap_aggregate(tax.p, b.ids.data(), b.off.data(), b.size(), st, factor, lb, a.has("ranked"), res.data()));
+        }
         out.clear();
         for (size_t i = 0; i < b.size(); ++i) {
             out += '>';

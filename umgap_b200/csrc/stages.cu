@@ -390,7 +390,29 @@ __global__ void aggregate_scored_kernel(const TaxView tv, AggParams ap, const ui
     }
     const ScoredRec r{tv, A, W};
     uint32_t result;
-    if (ap.strategy == UMGAP_AGG_MRTL) {
+    if (ap.strategy == UMGAP_AGG_RMQ_HYBRID) {
+        // rmq/mix.rs:56-93: every taxon of the closure of the members under pairwise LCA -- the members and the LCAs of
+        // neighbours in preorder -- weighs  lca * factor + rtl * (1 - factor),  lca = the summed counts of the members at or
+        // below it, rtl = those of the members at or above it; the heaviest wins (the first in preorder among equals;
+        // the reference takes the last in HashMap order).  Sums run in ascending preorder.
+        const float inv = __fsub_rn(1.0f, ap.factor);
+        float best = 0.0f;
+        result = kNoTaxon;
+        for (uint32_t c = 0; c < 2 * m - 1; ++c) {
+            const uint32_t t = (c & 1u) ? scored_lca(tv, A[c >> 1], A[(c >> 1) + 1]) : A[c >> 1];
+            const uint32_t tl = __ldg(tv.last + t);
+            float wl = 0.0f, wr = 0.0f;
+            for (uint32_t i = 0; i < m; ++i) {
+                if (A[i] >= t && A[i] <= tl) wl = wl + W[i];
+                if (A[i] <= t && __ldg(tv.last + A[i]) >= t) wr = wr + W[i];
+            }
+            const float val = __fadd_rn(__fmul_rn(wl, ap.factor), __fmul_rn(wr, inv));
+            if (result == kNoTaxon || val > best || (val == best && t < result)) {
+                best = val;
+                result = t;
+            }
+        }
+    } else if (ap.strategy == UMGAP_AGG_MRTL) {
         float best = 0.0f;
         uint32_t best_j = 0;
         for (uint32_t j = 0; j < m; ++j) {
@@ -632,7 +654,7 @@ int umgap_aggregate_scored(const umgap_taxonomy* tax, const uint32_t* taxa, cons
                            uint64_t nrecs, int strategy, float factor, float lower_bound, int ranked_only, uint32_t* taxon_out) {
     return guarded([&] {
         if (!tax || !rec_off || (nrecs && !taxon_out)) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
-        if (strategy < UMGAP_AGG_LCA_STAR || strategy > UMGAP_AGG_MRTL)
+        if (strategy < UMGAP_AGG_LCA_STAR || strategy > UMGAP_AGG_RMQ_HYBRID)
             UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", strategy);
         if (!nrecs) return;
         const uint64_t total = rec_off[nrecs];
