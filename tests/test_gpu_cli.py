@@ -91,6 +91,16 @@ def test_stagewise_pipeline_matches_oracle_text(files):
         for (gh, gs), (wh, ws) in zip(got, recs):
             pairs = [(int(x.split("=")[0]), float(x.split("=")[1])) for x in ws]
             assert gh == wh and len(gs) == 1 and int(gs[0]) in oagg.taxa2agg_record_scored(files["otax"], snapping, pairs, strategy, 0.25, lb), gh
+    # -m rmq -a lca*: the fold of rmq/lca.rs:60-90 over the record's distinct taxa, restated with its Euler tour and RMQ
+    from oracle import rmq as ormq
+    calc = ormq.LCACalculator(files["otax"])
+    rc, a_out, err = run(["taxa2agg", "-m", "rmq", "-a", "lca*", "-l", "2", str(d / "taxons.tsv")], u_out)
+    assert rc == 0, err
+    snapping = files["otax"].snapping(False)
+    for (gh, gs), (wh, ws) in zip(ofasta.read_records(a_out, False), ofasta.read_records(u_out, False)):
+        counts = oagg.filter_counts(oagg.count(int(x) for x in ws if int(x) != 0), 2.0)
+        want = snapping[calc.aggregate(list(counts))] if counts else 1
+        assert gh == wh and int(gs[0]) == want, gh
     rc, a_out, err = run(["taxa2agg", "-m", "rmq", "-a", "hybrid", "-f", "0.5", str(d / "taxons.tsv")], u_out)   # rmq/mix.rs
     assert rc == 0 and "Warning: this is a hybrid between LCA/MRTL" in err
     snapping = files["otax"].snapping(False)

@@ -1,6 +1,7 @@
 """Pins the oracle against every in-scope known-answer vector the reference holds
 (SURVEY Appendix E): unit tests and doc-comment examples, cited per test."""
 import itertools
+import random
 
 import pytest
 
@@ -265,6 +266,55 @@ def test_rmq_mix_vectors(tax):
     assert X([1, 12884, 12884, 185751, 185752], 0.5) == {12884}   # 3.5 against 2.5: no tie, whatever rmq/mix.rs:119 fears
     with pytest.raises(agg.EmptyInput):
         agg.rmq_mix(tax, {}, 0.5)
+
+
+# ---- rmq/mod.rs:171-260, rmq/lca.rs:105-172 (`-m rmq -a lca*`)
+def test_rmq_structure_and_fold_vectors(tax):
+    from oracle import rmq
+    arr = [12, 17, 23, 2, 20, 4, 8, 27, 26, 19, 31, 22, 28, 16, 24, 14, 5, 29, 32, 11, 7, 9, 25, 30, 21, 13, 6, 18, 15, 33, 10, 3, 33, 1]
+    assert rmq.RMQ(arr).block_min == [33]                     # rmq/mod.rs:177-182 on a 64-bit usize
+    assert rmq.euler_tour(tax) == [(1, 0), (2, 1), (1, 0), (10239, 1), (1, 0), (12884, 1), (185751, 2), (12884, 1), (185752, 2),
+                                   (12884, 1), (1, 0)]            # taxon.rs:433-446
+    rng = random.Random(3)
+    for _ in range(100):                                      # query returns a position of the range's minimum
+        a = [rng.randrange(0, 5) for _ in range(rng.randrange(1, 300))]
+        R = rmq.RMQ(a)
+        for _ in range(100):
+            i, j = rng.randrange(len(a)), rng.randrange(len(a))
+            q = R.query(i, j)
+            assert min(i, j) <= q <= max(i, j) and a[q] == min(a[min(i, j):max(i, j) + 1])
+    calc = rmq.LCACalculator(tax)
+    A = lambda ids: calc.aggregate(list(dict.fromkeys(ids)))
+    assert A([12884, 185752]) == 185752 and A([185752, 12884]) == 185752 and A([1, 2]) == 2 and A([2, 1]) == 2
+    assert A([2, 10239]) == 1 and A([10239, 2]) == 1 and A([185751, 185752]) == 12884 and A([185752, 185751]) == 12884
+    for p in itertools.permutations([12884, 185751, 185752]):
+        assert A(list(p)) == 12884
+    large = taxonomy.Taxonomy([(i, "", 0, p, True) for i, p in [(1, 1), (2, 1), (5, 2), (6, 2), (3, 1), (7, 3), (10, 7), (13, 10), (14, 13),
+                                                              (15, 3), (8, 3), (11, 8), (12, 8), (9, 3), (4, 1)]])
+    lc = rmq.LCACalculator(large)
+    assert lc.aggregate([9, 7]) == 3 and lc.aggregate([9, 10]) == 3 and lc.aggregate([7, 9]) == 3 and lc.aggregate([14, 8]) == 3
+
+
+def test_rmq_fold_is_the_tree_form_lca_star():
+    """Why the product answers `-m rmq -a lca*` with the kernel of `-m tree -a lca*`: over every order of a record's
+    distinct taxa (the reference folds HashMap keys) the fold of rmq/lca.rs:60-90, restated with its RMQ as written,
+    gives one answer, and it is tree/lca.rs:34-40's."""
+    from oracle import rmq
+    import datagen
+    rng = random.Random(77)
+    checked = 0
+    for seed in range(24):
+        taxa = datagen.make_taxonomy(rng.choice([8, 30, 120, 400]), seed=100 + seed)
+        tx = taxonomy.Taxonomy(taxa)
+        calc = rmq.LCACalculator(tx)
+        ids = [t[0] for t in taxa]
+        for _ in range(40):
+            path = tx.root_path(rng.choice(ids))
+            keys = list({rng.choice(path) if rng.random() < 0.6 else rng.choice(ids) for _ in range(rng.randrange(1, 7))})
+            got = {calc.aggregate(list(p)) for p in itertools.permutations(keys)}
+            assert got == {agg.lca_star(tx, {t: agg.f32(1) for t in keys})}, keys
+            checked += 1
+    assert checked == 960
 
 
 # ---- taxa2agg -s (taxa2agg.rs:141-148, agg/mod.rs:27-44)

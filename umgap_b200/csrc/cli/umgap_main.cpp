@@ -650,8 +650,8 @@ int parse_strategy(const std::string& method, const std::string& strategy) {
         fputs("Warning: this is a hybrid between LCA/MRTL, not LCA*/MRTL\n", stderr);
         return UMGAP_AGG_RMQ_HYBRID;
     }
-    if (rmq && st != UMGAP_AGG_MRTL)
-        fail("-m rmq -a lca* (an order-dependent fold over Euler-tour positions, rmq/lca.rs:60-90) is not implemented on the GPU path; use -m tree");
+    // -m rmq -a lca*: the fold of rmq/lca.rs:60-90 gives tree/lca.rs:34-40's answer in every order of the record's taxa
+    // (oracle/rmq.py restates it with its Euler tour and RMQ; tests/test_oracle_golden.py checks all orders): same kernel
     return st;
 }
 
