@@ -278,8 +278,9 @@ int umgap_classify_reads_packed(const umgap_index* idx, const umgap_taxonomy* ta
  * the GPU busy across the seam: the uploads and first kernels of one batch run in the tail of the other (one batch at
  * a time leaves ~0.5 ms per 1 M pairs idle).  All host arrays of a batch -- page-locked, else the copies are not
  * asynchronous -- stay valid and unchanged until its wait returns; batches complete in the order they were enqueued;
- * at most 32 in flight per index; calls on one index come from one thread at a time.  The reference's stages are
- * synchronous filters; this is the shape of its pipe (one stage reads while the next computes).                  */
+ * at most 32 in flight per index; calls on one index come from one thread at a time; every ticket is waited for
+ * before its index is freed.  The reference's stages are synchronous filters; this is the shape of its pipe (one
+ * stage reads while the next computes).                                                                          */
 typedef struct umgap_pending umgap_pending;
 int umgap_classify_reads_async(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_pipeline_opts* opts,
                                const uint8_t* nt, const uint64_t* read_off, uint64_t nreads, const uint64_t* group_off,
