@@ -431,7 +431,7 @@ def _sharded_rank0(ctx, gidx_repl):
         torch.cuda.synchronize()
         same = same and bool(torch.equal(ctx.out_b, outs[d][0].to(ctx.dev)))
         del nt0
-    steps = max(3, min(5, args.steps))
+    steps = max(3, min(20, 2 * args.steps))   # consecutive batches overlap (lanes): enough of them for the steady state
     for i in range(2):
         step(i)
     S.sync()

@@ -184,7 +184,15 @@ void exchange_round(umgap_exchange* ex, cudaStream_t st) {
     }
     {
         LaunchTimer timer(0, st);
-        exchange_lookup_kernel<<<148 * 8, 256, 0, st>>>(ex->shard->view(), reinterpret_cast<const uint64_t*>(mine + L.inbox_h),
+        // CTAs per SM of the lookup kernel (UMGAP_XLOOKUP_CTAS): four probe chains per thread reach the random-request
+        // ceiling with a fraction of the SM's threads, and what it leaves free runs the other lane's pack / scatter /
+        // classify kernels beside it
+        static const unsigned per_sm = [] {
+            const char* e = getenv("UMGAP_XLOOKUP_CTAS");
+            const int v = e ? atoi(e) : 0;
+            return (unsigned)(v > 0 ? std::min(v, 16) : 8);
+        }();
+        exchange_lookup_kernel<<<148 * per_sm, 256, 0, st>>>(ex->shard->view(), reinterpret_cast<const uint64_t*>(mine + L.inbox_h),
                                                        reinterpret_cast<const unsigned long long*>(mine + L.inbox_cnt), (uint32_t)ex->n,
                                                        ex->cap, ans);
         timer.stop();
