@@ -19,9 +19,10 @@ __device__ __forceinline__ uint64_t sm64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-enum { V_NC_NA_256 = 0, V_NC_256, V_PLAIN_256, V_NC_2x128, V_NC_NA_64, V_NC_4x64, V_CG_2x128, V_LU_256, V_NC_NA_EF_256, V_COUNT };
+enum { V_NC_NA_256 = 0, V_NC_256, V_PLAIN_256, V_NC_2x128, V_NC_NA_64, V_NC_4x64, V_CG_2x128, V_LU_256, V_NC_NA_EF_256, V_NC_NA_L2_64B, V_NC_NA_L2_128B, V_NC_NA_L2_256B, V_COUNT };
 static const char* kNames[] = {"nc.L1no_alloc.v4u64", "nc.v4u64", "plain.v4u64", "nc.2x v2u64", "nc.L1no_alloc.u64 (8B)",
-                               "nc.4x u64", "cg.2x v2u64", "lu.v4u64", "nc.na.L2evict_first.v4u64"};
+                               "nc.4x u64", "cg.2x v2u64", "lu.v4u64", "nc.na.L2evict_first.v4u64", "nc.na.L2::64B.v4u64",
+                               "nc.na.L2::128B.v4u64", "nc.na.L2::256B.v4u64"};
 
 template <int V>
 __device__ __forceinline__ uint64_t ld(const char* p, uint64_t pol) {
@@ -46,6 +47,10 @@ __device__ __forceinline__ uint64_t ld(const char* p, uint64_t pol) {
     }
     if (V == V_LU_256) asm volatile("ld.global.lu.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     if (V == V_NC_NA_EF_256) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+    // prefetch-size qualifiers (SASS: LDG.E.NA.ENL2.LTC64B/LTC128B/LTC256B.256.CONSTANT): do they set the fill size of an L2 miss?
+    if (V == V_NC_NA_L2_64B) asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    if (V == V_NC_NA_L2_128B) asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    if (V == V_NC_NA_L2_256B) asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     return a ^ b ^ c ^ d;
 }
 
@@ -135,6 +140,6 @@ int main(int argc, char** argv) {
     const bool all = !strcmp(var, "all");
     const int v = atoi(var);
 #define RUN(V) if (all || v == V) run<V>(t, bytes, wbytes, n, sink);
-    RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8)
+    RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11)
     return 0;
 }

@@ -165,6 +165,96 @@ def test_socket_server_mode(files, tmp_path):
         srv.wait()
 
 
+NC_STANDIN = """#!/usr/bin/env python3
+# stand-in for `nc -NU <socket>` (scripts/umgap-analyse.sh:279): stdin -> Unix socket, half-close at EOF, socket -> stdout
+import socket, sys, threading
+c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+c.connect(sys.argv[-1])
+def up():
+    while True:
+        b = sys.stdin.buffer.read(1 << 16)
+        if not b:
+            break
+        c.sendall(b)
+    c.shutdown(socket.SHUT_WR)
+t = threading.Thread(target=up)
+t.start()
+while True:
+    b = c.recv(1 << 16)
+    if not b:
+        break
+    sys.stdout.buffer.write(b)
+sys.stdout.buffer.flush()
+t.join()
+"""
+
+
+def test_analyse_script_presets_through_the_socket_server(files, tmp_path):
+    """The pipeline section of scripts/umgap-analyse.sh (:257-264 the index server, :276-311 the six case arms), arm by arm
+    as shell pipes of `umgap` commands, with stand-ins for what the image lacks: `nc -NU` (a Python socket client) and
+    FGSpp (gene prediction: its output is a FASTA of predicted peptides, here fragments of the proteome).  Every arm's
+    text is the oracle's text pipeline on the same input (ties of hybrid / mrtl: membership)."""
+    d = files["dir"]
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    (bindir / "nc").write_text(NC_STANDIN)
+    os.chmod(bindir / "nc", 0o755)
+    os.symlink(UMGAP, bindir / "umgap")
+    env = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ.get("PATH", ""))
+    sock = str(tmp_path / "socket")
+    taxons, ninemers, tryptics = str(d / "taxons.tsv"), str(d / "nine.fst"), str(d / "tryp.fst")
+    genes = []   # what FGSpp prints for paired reads: >header/mate_start_end_strand, one predicted peptide each
+    for i, p in enumerate(files["proteins"][:40]):
+        genes.append((f"r{i}/1_1_150_+", p[:50]))
+        genes.append((f"r{i}/2_4_150_-", p[60:108] + ("*" if i % 5 == 0 else "")))
+    genes += [("lone/1_1_30_+", "MKRW"), ("none/1_1_30_+", "")]
+    (tmp_path / "genes.fa").write_text("".join(f">{h}\n" + (f"{s}\n" if s else "") for h, s in genes))
+    (tmp_path / "reads.fa").write_text(files["fasta"])
+    srv = subprocess.Popen(["umgap", "prot2kmer2lca", "-m", "-o", "-s", sock, ninemers], stdout=subprocess.DEVNULL, env=env)
+    try:
+        for _ in range(600):   # `while [ ! -S "$socket" ] && sleep 1` of the script
+            if os.path.exists(sock):
+                break
+            time.sleep(0.1)
+        assert os.path.exists(sock)
+        arms = {
+            "max-sensitivity": ("reads.fa", "umgap translate -a | nc -NU $socket | umgap seedextend -g1 -s2 | umgap uniq -d / | umgap taxa2agg -l1 -m rmq -a mrtl $taxons"),
+            "high-sensitivity": ("reads.fa", "umgap translate -a | nc -NU $socket | umgap seedextend -g1 -s3 | umgap uniq -d / | umgap taxa2agg -l1 -a hybrid -f 0.25 $taxons"),
+            "tryptic-sensitivity": ("genes.fa", "cat | umgap prot2tryp2lca -l9 -L45 $tryptics | umgap uniq -d / | umgap taxa2agg -l1 -m rmq -a mrtl $taxons"),
+            "tryptic-precision": ("genes.fa", "cat | umgap prot2tryp2lca -l9 -L45 $tryptics | umgap uniq -d / | umgap taxa2agg -l5 -m rmq -a mrtl $taxons"),
+            "high-precision": ("genes.fa", "cat | nc -NU $socket | umgap seedextend -g1 -s3 | umgap uniq -d / | umgap taxa2agg -l2 -a lca\\* $taxons"),
+            "max-precision": ("genes.fa", "cat | nc -NU $socket | umgap seedextend -g1 -s4 | umgap uniq -d / | umgap taxa2agg -l5 -a lca\\* $taxons"),
+        }
+        nine, tryp = olookup.DictIndex(files["index"]), olookup.DictIndex(files["tryp"])
+        otax = files["otax"]
+        below_root = 0
+        for name, (infile, pipe) in arms.items():
+            cmd = f"set -o pipefail; socket={sock}; taxons={taxons}; tryptics={tryptics}; {pipe} < {tmp_path / infile}"
+            p = subprocess.run(["bash", "-c", cmd], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+            assert p.returncode == 0, (name, p.stderr.decode())
+            text = (tmp_path / infile).read_text()
+            if name.endswith("sensitivity") and infile == "reads.fa":
+                text = opipe.translate_text(text)
+            if name.startswith("tryptic"):
+                ids = opipe.prot2tryp2lca_text(text, tryp, False, 9, 45)
+            else:
+                g, s = {"max-sensitivity": (1, 2), "high-sensitivity": (1, 3), "high-precision": (1, 3), "max-precision": (1, 4)}[name]
+                ids = opipe.seedextend_text(opipe.prot2kmer2lca_text(text, nine, 9, True), s, g)
+            joined = opipe.uniq_text(ids, "/")
+            strategy, lb = {"max-sensitivity": (2, 1.0), "high-sensitivity": (1, 1.0), "tryptic-sensitivity": (2, 1.0),
+                            "tryptic-precision": (2, 5.0), "high-precision": (0, 2.0), "max-precision": (0, 5.0)}[name]
+            want = opipe.taxa2agg_sets(joined, otax, strategy, 0.25, lb, False)
+            got = list(ofasta.read_records(p.stdout.decode(), False))
+            assert len(got) == len(want) and len(got) > 0, name
+            for (gh, gs), (wh, ws) in zip(got, want):
+                assert gh == wh and len(gs) == 1 and int(gs[0]) in ws, (name, gh, gs, ws)
+                below_root += int(gs[0]) != 1
+        assert below_root > 50
+    finally:
+        srv.kill()
+        srv.wait()
+
+
 def test_fused_peptide_cli_matches_the_three_stage_pipe(files):
     """`umgap classify-peptides` prints what `prot2tryp2lca | uniq -d / | taxa2agg` prints (tryptic presets)."""
     d = files["dir"]

@@ -352,7 +352,10 @@ constexpr int kSSpan = 256 * kSReads;  // five reads of up to 256 nt fill 30 lan
 #endif
 constexpr int kSU = UMGAP_S_UNROLL;     // lookups in flight per lane
 constexpr int kSQueue = 64 * kSU;
-constexpr int kSWarps = 4;
+#ifndef UMGAP_S_WARPS
+#define UMGAP_S_WARPS 4
+#endif
+constexpr int kSWarps = UMGAP_S_WARPS;
 constexpr int kSBlocks = UMGAP_S_BLOCKS;  // CTAs per SM the launch bounds ask for
 constexpr int kSItems = 32 + 6 * kSReads;
 constexpr int kSValRows = 16;
@@ -411,8 +414,7 @@ __device__ __forceinline__ void translate_chunk16_packed(uint64_t codes, uint32_
 // (complement = 3 - code); [64] = a codon holding an N.  lut.v is in T,C,A,G order (translation.rs:20).  Threads
 // 0..64 of the CTA fill it; the caller synchronises.
 __device__ __forceinline__ void fill_pair_lut(const CodonLut& lut, uint16_t* pair) {
-    if (threadIdx.x < 65) {
-        const uint32_t i = threadIdx.x;
+    for (uint32_t i = threadIdx.x; i < 65; i += blockDim.x) {  // any block size
         if (i == 64) {
             pair[64] = (uint16_t)(lut.v[64] | (uint32_t)lut.v[64] << 8);
         } else {

@@ -101,10 +101,15 @@ __device__ __forceinline__ uint32_t num_levels(const ShardedView& t, uint64_t h)
     return (uint32_t)t.nlevels[shard_split(h, (uint32_t)t.nshards, local32)];
 }
 
-// 256-bit read-only load of one sector: a single LDG.E.256.
+// 256-bit read-only load of one sector: a single LDG.E.256.  UMGAP_PROBE_FILL (".L2::64B" / ".L2::128B", SASS LTC64B /
+// LTC128B) is a measurement knob: an L2 miss of the plain form fills the whole 128-byte line, `.L2::64B` fills 64 bytes
+// (bench/randsector variants 9-11: half the DRAM bytes at the same request rate).
+#ifndef UMGAP_PROBE_FILL
+#define UMGAP_PROBE_FILL ""
+#endif
 __device__ __forceinline__ ulonglong4 load_sector(const ulonglong4* p) {
     ulonglong4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate" UMGAP_PROBE_FILL ".v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w)
                  : "l"(p));
     return r;
