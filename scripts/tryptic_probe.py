@@ -95,6 +95,23 @@ for _ in range(3):
 dt = (time.perf_counter() - t0) / 3
 assert np.array_equal(h, out)
 print(f"host buffers (pageable, H2D + D2H inside): {dt * 1e3:.2f} ms = {nlines / dt / 1e6:.1f} M peptide lines/s", flush=True)
+def pin(x):
+    t = torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).pin_memory()
+    return t.numpy().view(x.dtype), t
+p_aa, _k1 = pin(aa)
+p_loff, _k2 = pin(loff)
+p_out, _k4 = pin(np.zeros(npairs, dtype=np.uint32))
+p_goff, _k3 = pin(goff)
+for chunk in (sys.argv[4].split(",") if len(sys.argv) > 4 else ["4194304", "16777216", "67108864", "1073741824"]):
+    os.environ["UMGAP_PEP_CHUNK_BYTES"] = chunk
+    h = capi.classify_peptides(gidx, gtax, opts, p_aa, p_loff, p_goff, out=p_out)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        h = capi.classify_peptides(gidx, gtax, opts, p_aa, p_loff, p_goff, out=p_out)
+    dt = (time.perf_counter() - t0) / 5
+    assert np.array_equal(h, out)
+    print(f"host buffers (pinned), ranges of {int(chunk) >> 20} MB: {dt * 1e3:.2f} ms = {nlines / dt / 1e6:.1f} M peptide lines/s", flush=True)
+os.environ.pop("UMGAP_PEP_CHUNK_BYTES")
 # property: the answer of a group is the root or the snapped taxon of its protein (= the aggregate of that taxon alone)
 want = capi.aggregate(gtax, home[src].astype(np.uint32), np.arange(npairs + 1, dtype=np.uint64), capi.AGG_MRTL)
 ok = (out == 1) | (out == want)

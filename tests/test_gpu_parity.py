@@ -479,7 +479,7 @@ def test_tryptic_lookup_matches_oracle(capi, world, tmp_path):
     (1, 0.0, 1, 50, "", "", False),     # -l 1 and -l 3: one slot of the per-group hit array per residue / per two residues
     (2, 1.0, 3, 50, "", "", False),
 ])
-def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, strategy, lb, mn, mx, keep, drop, ranked):
+def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, monkeypatch, strategy, lb, mn, mx, keep, drop, ranked):
     """umgap_classify_peptides (digest + lookup + uniq join + aggregation on the device) against the oracle's text
     stages `prot2tryp2lca | uniq -d / | taxa2agg` (scripts/umgap-analyse.sh:291-300), and the device-buffer entry
     point against the host-buffer one."""
@@ -521,6 +521,11 @@ def test_fused_peptide_path_matches_oracle_text_pipeline(capi, world, strategy, 
         assert int(g_) in adm, (h, int(g_), adm)
         below += int(g_) != 1
     assert below > (100 if lb < 5 else 10)
+    # the host-buffer call sends the batch in ranges of whole groups on rotating streams: move the seams
+    for chunk in ("64", "777", "5000"):
+        monkeypatch.setenv("UMGAP_PEP_CHUNK_BYTES", chunk)
+        assert np.array_equal(capi.classify_peptides(gidx, world["gtax"], opts, aa, off, goff), got), chunk
+    monkeypatch.delenv("UMGAP_PEP_CHUNK_BYTES")
     # device-buffer entry point, asynchronous on the current stream
     import torch
     d_aa = torch.from_numpy(aa).cuda()

@@ -439,13 +439,15 @@ def tryp_opts(**kw) -> TrypOpts:
 
 
 def classify_peptides(index: Index, tax: Taxonomy, opts: TrypOpts, aa: np.ndarray, line_off: np.ndarray,
-                      group_off: np.ndarray) -> np.ndarray:
-    """umgap_classify_peptides (host buffers): prot2tryp2lca | uniq | taxa2agg, one taxon per group of lines."""
+                      group_off: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """umgap_classify_peptides (host buffers): prot2tryp2lca | uniq | taxa2agg, one taxon per group of lines.
+    `out` may be a caller-provided (page-locked) uint32 array of at least ngroups entries."""
     aa = _arr(aa, np.uint8)
     line_off = _arr(line_off, np.uint64)
     group_off = _arr(group_off, np.uint64)
     ngroups = len(group_off) - 1
-    out = np.zeros(max(ngroups, 1), dtype=np.uint32)
+    if out is None:
+        out = np.zeros(max(ngroups, 1), dtype=np.uint32)
     _check(load_library().umgap_classify_peptides(index._h, tax._h, C.byref(opts), _p(aa), _p(line_off),
                                                   C.c_uint64(len(line_off) - 1), _p(group_off), C.c_uint64(ngroups), _p(out)))
     return out[:ngroups]

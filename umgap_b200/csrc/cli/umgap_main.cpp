@@ -1291,6 +1291,28 @@ int cmd_classify(int argc, char** argv) {
 // ---- classify-peptides: the tryptic presets in one process (extension) -----------------------------
 // prot2tryp2lca | uniq -d / | taxa2agg (scripts/umgap-analyse.sh:291-300) behind the gene predictor: peptide records
 // on stdin, `>header\n<taxon>\n` per group of records on stdout.
+// Page-locked vectors (umgap_host_alloc): the library's copies of the ranges of a batch overlap its kernels only from
+// and into such memory.
+template <class T>
+struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U>
+    PinnedAlloc(const PinnedAlloc<U>&) {}
+    T* allocate(size_t n) {
+        void* p = umgap_host_alloc(n * sizeof(T));
+        if (!p) throw std::bad_alloc();
+        return (T*)p;
+    }
+    void deallocate(T* p, size_t) { umgap_host_free(p); }
+    template <class U>
+    bool operator==(const PinnedAlloc<U>&) const { return true; }
+    template <class U>
+    bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+template <class T>
+using PinnedVec = std::vector<T, PinnedAlloc<T>>;
+
 int cmd_classify_peptides(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'l', "minlen", true}, {'L', "maxlen", true}, {'k', "keep", true}, {'d', "drop", true},
                                    {'D', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
@@ -1313,9 +1335,14 @@ int cmd_classify_peptides(int argc, char** argv) {
     check(umgap_index_load_fst(a.pos[0].c_str(), 0, 0, 0.0, &idx.p));
     check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
     BlockReader br(stdin);
-    std::string aa, harena, out;
-    std::vector<uint64_t> loff{0}, goff, hoff{0};
-    std::vector<uint32_t> res;
+    std::string harena, out;
+    PinnedVec<char> aa;
+    PinnedVec<uint64_t> loff{0}, goff;
+    std::vector<uint64_t> hoff{0};
+    PinnedVec<uint32_t> res;
+    aa.reserve(64u << 20);
+    loff.reserve(2 * kBatchRecords * 4 + 16);
+    goff.reserve(kBatchRecords * 4 + 16);
     auto flush = [&]() {
         const size_t ng = hoff.size() - 1;
         if (!ng) return;
@@ -1360,7 +1387,7 @@ int cmd_classify_peptides(int argc, char** argv) {
             }
             while (p < end && *p != '>') {  // one item per physical line (prot2tryp2lca.rs:105-118)
                 take_line(p, end, ls, ll);
-                aa.append(ls, ll);
+                aa.insert(aa.end(), ls, ls + ll);
                 loff.push_back(aa.size());
             }
         }

@@ -381,41 +381,73 @@ void launch_aggregate(const umgap_taxonomy* tax, int strategy, float factor, flo
 // workspace slots of a peptide-table handle (a k = 0 index never runs the k-mer pipeline, whose slots these overlap)
 enum { TWS_LUT = 0, TWS_OUT = 1, TWS_REC = 2, TWS_SCRATCH = 3, TWS_ERR = 4, TWS_AA = 5, TWS_LOFF = 6, TWS_GOFF = 7, TWS_RES = 8 };
 
-static void classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* o,
-                                  const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines, uint64_t total_aa,
-                                  const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, unsigned int** err_out,
-                                  cudaStream_t st) {
+// What the launches of a range of groups need: set up once per call by peptides_prepare.
+struct PepRun {
+    const VarTable* t;
+    TrypParams tp;
+    uint32_t shift;  // one slot of `out` per 2^shift residues (group_bytes_kernel)
+    uint8_t* d_lut;
+    uint32_t* d_out;
+    uint64_t* d_rec;
+    uint32_t* d_scratch;
+    unsigned int* d_err;
+};
+
+// Checks, workspace, the cleared error slot and the keep / drop table, all on `st`.
+static PepRun peptides_prepare(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* o, uint64_t total_aa,
+                               uint64_t ngroups, cudaStream_t st) {
     if (!idx || !tax || !o) UMGAP_FAIL(UMGAP_ERR_INVALID, "null argument");
     if (idx->k != 0 || !idx->var_table) UMGAP_FAIL(UMGAP_ERR_INVALID, "index is not a variable-length peptide table");
     if (tax->device != idx->device) UMGAP_FAIL(UMGAP_ERR_INVALID, "index and taxonomy live on different devices");
     if (o->strategy < UMGAP_AGG_LCA_STAR || o->strategy > UMGAP_AGG_MRTL) UMGAP_FAIL(UMGAP_ERR_INVALID, "unknown aggregation strategy %d", o->strategy);
     uint8_t lut[256] = {};
-    const TrypParams tp = make_tryp_params(o->minlen, o->maxlen, o->keep, o->drop, lut);
+    PepRun r{};
+    r.tp = make_tryp_params(o->minlen, o->maxlen, o->keep, o->drop, lut);
     use_device(idx->device);
-    const VarTable* t = (const VarTable*)idx->var_table;
-    uint8_t* d_lut = (uint8_t*)idx->ws.get(TWS_LUT, 256);
-    uint32_t* d_out = (uint32_t*)idx->ws.get(TWS_OUT, (total_aa + 1) * sizeof(uint32_t));
-    uint64_t* d_rec = (uint64_t*)idx->ws.get(TWS_REC, (ngroups + 1) * sizeof(uint64_t));
-    uint32_t* d_scratch = (uint32_t*)idx->ws.get(TWS_SCRATCH, (3 * total_aa + ngroups + 8) * sizeof(uint32_t));
-    unsigned int* d_err = (unsigned int*)idx->ws.get(TWS_ERR, 2 * sizeof(unsigned int));
-    if (err_out) *err_out = d_err;
-    UMGAP_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(unsigned int), st));
-    if (!ngroups) return;
-    UMGAP_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
-    const uint32_t minlen = std::max<uint32_t>(1, tp.minlen);
-    const uint32_t shift = minlen >= 4 ? 2 : minlen >= 2 ? 1 : 0;  // one slot of `out` per 2^shift residues (group_bytes_kernel)
-    UMGAP_CUDA(cudaMemsetAsync(d_out, 0, ((total_aa >> shift) + 1) * sizeof(uint32_t), st));
-    if (nlines && total_aa) {
-        if (((uintptr_t)aa_dev & 7u) != 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "aa_dev must be 8-byte aligned");
-        tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(nlines, kPepThreads), 148 * 16), kPepThreads, 0, st>>>(
-            t->slots, t->nslots, t->pool, aa_dev, total_aa, line_off_dev, nlines, tp, d_lut, d_out, shift);
+    r.t = (const VarTable*)idx->var_table;
+    r.d_lut = (uint8_t*)idx->ws.get(TWS_LUT, 256);
+    r.d_out = (uint32_t*)idx->ws.get(TWS_OUT, (total_aa + 1) * sizeof(uint32_t));
+    r.d_rec = (uint64_t*)idx->ws.get(TWS_REC, (ngroups + 1) * sizeof(uint64_t));
+    r.d_scratch = (uint32_t*)idx->ws.get(TWS_SCRATCH, (3 * total_aa + ngroups + 8) * sizeof(uint32_t));
+    r.d_err = (unsigned int*)idx->ws.get(TWS_ERR, 2 * sizeof(unsigned int));
+    UMGAP_CUDA(cudaMemsetAsync(r.d_err, 0, 2 * sizeof(unsigned int), st));
+    UMGAP_CUDA(cudaMemcpyAsync(r.d_lut, lut, 256, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    const uint32_t minlen = std::max<uint32_t>(1, r.tp.minlen);
+    r.shift = minlen >= 4 ? 2 : minlen >= 2 ? 1 : 0;
+    return r;
+}
+
+// Groups [g0, g1) = lines [l0, l1) = bytes [b0, b1) of the batch, on `st`.  Offsets and slots are those of the whole
+// batch (aa_dev, line_off_dev, group_off_dev and the workspace are indexed absolutely), so ranges on different streams
+// touch disjoint parts: a kept peptide of the range starts in [b0, b1 - 2^shift], its slot lies in
+// [b0 >> shift, b1 >> shift) (group_bytes_kernel), and the scratch of record g is A = scratch + 3 * rec_off[g] + g.
+// The walk never loads a byte at or beyond b1 (`total_aa` of the kernel), so a range can run while the next one is
+// still on its way to the device.
+static void peptides_range(const PepRun& r, const umgap_taxonomy* tax, const umgap_tryp_opts* o, const uint8_t* aa_dev,
+                           const uint64_t* line_off_dev, const uint64_t* group_off_dev, uint64_t g0, uint64_t g1, uint64_t l0,
+                           uint64_t l1, uint64_t b0, uint64_t b1, bool last, uint32_t* taxon_out_dev, cudaStream_t st) {
+    if (g1 <= g0) return;
+    const uint64_t s0 = b0 >> r.shift, s1 = (b1 >> r.shift) + (last ? 1 : 0);
+    if (s1 > s0) UMGAP_CUDA(cudaMemsetAsync(r.d_out + s0, 0, (s1 - s0) * sizeof(uint32_t), st));
+    if (l1 > l0 && b1 > b0) {
+        tryp_lookup_lines_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(l1 - l0, kPepThreads), 148 * 16), kPepThreads, 0, st>>>(
+            r.t->slots, r.t->nslots, r.t->pool, aa_dev, b1, line_off_dev + l0, l1 - l0, r.tp, r.d_lut, r.d_out, r.shift);
         UMGAP_CUDA(cudaGetLastError());
     }
-    group_bytes_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(ngroups + 1, 256), 148 * 8), 256, 0, st>>>(line_off_dev, group_off_dev,
-                                                                                                        ngroups, d_rec, shift);
+    group_bytes_kernel<<<(unsigned)std::min<uint64_t>(ceil_div(g1 - g0 + 1, 256), 148 * 8), 256, 0, st>>>(line_off_dev, group_off_dev + g0,
+                                                                                                        g1 - g0, r.d_rec + g0, r.shift);
     UMGAP_CUDA(cudaGetLastError());
-    launch_aggregate(tax, o->strategy, o->factor, o->lower_bound, o->ranked_only, d_out, d_rec, ngroups, d_scratch, taxon_out_dev,
-                     d_err, st);
+    launch_aggregate(tax, o->strategy, o->factor, o->lower_bound, o->ranked_only, r.d_out, r.d_rec + g0, g1 - g0, r.d_scratch + g0,
+                     taxon_out_dev + g0, r.d_err, st);
+}
+
+static void classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* tax, const umgap_tryp_opts* o,
+                                  const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines, uint64_t total_aa,
+                                  const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, cudaStream_t st) {
+    const PepRun r = peptides_prepare(idx, tax, o, total_aa, ngroups, st);
+    if (!ngroups) return;
+    if (nlines && total_aa && ((uintptr_t)aa_dev & 7u) != 0) UMGAP_FAIL(UMGAP_ERR_INVALID, "aa_dev must be 8-byte aligned");
+    peptides_range(r, tax, o, aa_dev, line_off_dev, group_off_dev, 0, ngroups, 0, nlines, 0, total_aa, true, taxon_out_dev, st);
 }
 
 extern "C" {
@@ -436,7 +468,7 @@ int umgap_classify_peptides_dev(const umgap_index* idx, const umgap_taxonomy* ta
                                 const uint8_t* aa_dev, const uint64_t* line_off_dev, uint64_t nlines, uint64_t total_aa,
                                 const uint64_t* group_off_dev, uint64_t ngroups, uint32_t* taxon_out_dev, void* stream) {
     return guarded([&] {
-        classify_peptides_dev(idx, tax, opts, aa_dev, line_off_dev, nlines, total_aa, group_off_dev, ngroups, taxon_out_dev, nullptr,
+        classify_peptides_dev(idx, tax, opts, aa_dev, line_off_dev, nlines, total_aa, group_off_dev, ngroups, taxon_out_dev,
                               (cudaStream_t)stream);
     });
 }
@@ -455,18 +487,60 @@ int umgap_classify_peptides(const umgap_index* idx, const umgap_taxonomy* tax, c
         uint64_t* d_loff = (uint64_t*)idx->ws.get(TWS_LOFF, (nlines + 1) * sizeof(uint64_t));
         uint64_t* d_goff = (uint64_t*)idx->ws.get(TWS_GOFF, (ngroups + 1) * sizeof(uint64_t));
         uint32_t* d_res = (uint32_t*)idx->ws.get(TWS_RES, ngroups * sizeof(uint32_t));
-        if (total) UMGAP_CUDA(cudaMemcpyAsync(d_aa, aa, total, cudaMemcpyHostToDevice, 0));
-        UMGAP_CUDA(cudaMemcpyAsync(d_loff, line_off, (nlines + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, 0));
-        UMGAP_CUDA(cudaMemcpyAsync(d_goff, group_off, (ngroups + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, 0));
-        unsigned int* d_err = nullptr;
-        classify_peptides_dev(idx, tax, opts, d_aa, d_loff, nlines, total, d_goff, ngroups, d_res, &d_err, 0);
+        // The batch goes over in ranges of whole groups of about 16 MB of residues (UMGAP_PEP_CHUNK_BYTES; the first ones
+        // 1/8, 1/4, 1/2 of that), rotating over the handle's chunk streams: each range's bytes and offsets are copied
+        // to their places in the batch-sized device arrays, its kernels run behind its own copy and beside the next
+        // range's, its results go back on the same stream.  The ranges overlap only when `taxon_out` (and the
+        // inputs) are page-locked (umgap_host_alloc): a copy into pageable memory holds the host until the range is done.
+        // (One copy of everything, then the kernels, then the results: 4.8 ms per 1 M pairs of 50-residue lines, of
+        // which PCIe needs 2.3.)
+        const char* e = getenv("UMGAP_PEP_CHUNK_BYTES");  // read per call, so that tests can move the seams
+        const uint64_t chunk = std::max<uint64_t>(64, e && atoll(e) > 0 ? (uint64_t)atoll(e) : 8ull << 20);
+        const int kStreams = 4;
+        if (!idx->chunk_stream[0])
+            for (int i = 0; i < 6; ++i) {
+                UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->chunk_stream[i], cudaStreamNonBlocking));
+                UMGAP_CUDA(cudaEventCreateWithFlags(&idx->chunk_done[i], cudaEventDisableTiming));
+            }
+        cudaStream_t* st = idx->chunk_stream;
+        const PepRun r = peptides_prepare(idx, tax, opts, total, ngroups, st[0]);
+        UMGAP_CUDA(cudaEventRecord(idx->chunk_done[0], st[0]));
+        for (int i = 1; i < kStreams; ++i) UMGAP_CUDA(cudaStreamWaitEvent(st[i], idx->chunk_done[0], 0));
+        auto bytes_before = [&](uint64_t g) {
+            if (group_off[g] > nlines) UMGAP_FAIL(UMGAP_ERR_INVALID, "group_off exceeds the number of lines");
+            return line_off[group_off[g]];
+        };
+        std::vector<uint64_t> empty;  // groups without lines, found while the device works on the range
+        try {
+            uint64_t g0 = 0;
+            for (int c = 0; g0 < ngroups; ++c) {
+                const uint64_t b0 = bytes_before(g0), limit = c < 3 ? chunk >> (3 - c) : chunk;
+                uint64_t lo = g0 + 1, hi = ngroups;  // largest g1 with at most `limit` bytes in [g0, g1), at least g0 + 1
+                while (lo < hi) {
+                    const uint64_t mid = lo + (hi - lo + 1) / 2;
+                    if (bytes_before(mid) - b0 <= limit) lo = mid; else hi = mid - 1;
+                }
+                const uint64_t g1 = lo, l0 = group_off[g0], l1 = group_off[g1], b1 = line_off[l1];
+                if (l1 < l0 || b1 < b0) UMGAP_FAIL(UMGAP_ERR_INVALID, "offsets are not ascending");
+                cudaStream_t s = st[c % kStreams];
+                if (b1 > b0) UMGAP_CUDA(cudaMemcpyAsync(d_aa + b0, aa + b0, b1 - b0, cudaMemcpyHostToDevice, s));
+                UMGAP_CUDA(cudaMemcpyAsync(d_loff + l0, line_off + l0, (l1 - l0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+                UMGAP_CUDA(cudaMemcpyAsync(d_goff + g0, group_off + g0, (g1 - g0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+                peptides_range(r, tax, opts, d_aa, d_loff, d_goff, g0, g1, l0, l1, b0, b1, g1 == ngroups, d_res, s);
+                UMGAP_CUDA(cudaMemcpyAsync(taxon_out + g0, d_res + g0, (g1 - g0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                for (uint64_t g = g0; g < g1; ++g)
+                    if (group_off[g + 1] == group_off[g]) empty.push_back(g);
+                g0 = g1;
+            }
+            for (int i = 0; i < kStreams; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
+        } catch (...) {
+            cudaDeviceSynchronize();
+            throw;
+        }
         unsigned int he[2] = {0, 0};
-        UMGAP_CUDA(cudaMemcpyAsync(taxon_out, d_res, ngroups * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));
-        UMGAP_CUDA(cudaMemcpyAsync(he, d_err, sizeof he, cudaMemcpyDeviceToHost, 0));
-        UMGAP_CUDA(cudaStreamSynchronize(0));
+        UMGAP_CUDA(cudaMemcpy(he, r.d_err, sizeof he, cudaMemcpyDeviceToHost));
         if (he[0]) UMGAP_FAIL(UMGAP_ERR_UNKNOWN_TAXON, "Unknown Taxon ID: %u", he[1]);
-        for (uint64_t g = 0; g < ngroups; ++g)   // a group without lines has no record in the reference
-            if (group_off[g + 1] == group_off[g]) taxon_out[g] = UMGAP_ABSENT;
+        for (uint64_t g : empty) taxon_out[g] = UMGAP_ABSENT;  // a group without lines has no record in the reference
     });
 }
 
