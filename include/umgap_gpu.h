@@ -323,7 +323,9 @@ int umgap_translate_lookup_dev(const umgap_index* idx, const umgap_pipeline_opts
  * Lines l in [group_off[g], group_off[g+1]) are the records `uniq` joins.  Every peptide line is digested
  * (prot2tryp2lca.rs:112-117), the peptides of minlen..maxlen bytes that pass the keep / drop sets are looked up
  * in the variable-length table `idx` (k = 0), and the taxa of a group are aggregated (zeros dropped,
- * taxa2agg.rs:169; a group without a hit yields 1, :174-175; a group without lines UMGAP_ABSENT).   */
+ * taxa2agg.rs:169; a group without a hit yields 1, :174-175; a group without lines UMGAP_ABSENT).
+ * The host-buffer call sends the batch in ranges of whole groups on rotating streams; the ranges overlap (copy in,
+ * kernels, results out) when aa, the offset arrays and taxon_out are page-locked (umgap_host_alloc).   */
 typedef struct umgap_tryp_opts {
     int minlen;         /* prot2tryp2lca -l, default 5                                     */
     int maxlen;         /* prot2tryp2lca -L, default 50                                    */

@@ -229,7 +229,7 @@ def test_analyse_script_presets_through_the_socket_server(files, tmp_path):
         otax = files["otax"]
         below_root = 0
         for name, (infile, pipe) in arms.items():
-            cmd = f"set -o pipefail; socket={sock}; taxons={taxons}; tryptics={tryptics}; {pipe} < {tmp_path / infile}"
+            cmd = f"set -o pipefail; socket={sock}; taxons={taxons}; tryptics={tryptics}; {{ {pipe}; }} < {tmp_path / infile}"
             p = subprocess.run(["bash", "-c", cmd], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
             assert p.returncode == 0, (name, p.stderr.decode())
             text = (tmp_path / infile).read_text()
