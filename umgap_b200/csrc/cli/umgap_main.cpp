@@ -833,6 +833,28 @@ int cmd_fastq2fasta(int argc, char** argv) {
 // and the concatenation of the lines up to the next line that starts with '>'); one thread per GPU classifies parsed
 // blocks on its replica of the index (--gpus / UMGAP_DEVICES: index and taxonomy replicated, reads partitioned,
 // SURVEY 8(e) mode 1); the writer prints the blocks in input order.
+// Page-locked vectors (umgap_host_alloc): the library's copies of the ranges of a batch overlap its kernels only from
+// and into such memory.
+template <class T>
+struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U>
+    PinnedAlloc(const PinnedAlloc<U>&) {}
+    T* allocate(size_t n) {
+        void* p = umgap_host_alloc(n * sizeof(T));
+        if (!p) throw std::bad_alloc();
+        return (T*)p;
+    }
+    void deallocate(T* p, size_t) { umgap_host_free(p); }
+    template <class U>
+    bool operator==(const PinnedAlloc<U>&) const { return true; }
+    template <class U>
+    bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+template <class T>
+using PinnedVec = std::vector<T, PinnedAlloc<T>>;
+
 namespace classify_cli {
 
 // The nucleotides of a block, in page-locked memory (umgap_host_alloc): the library copies them to the GPU asynchronously.
@@ -862,7 +884,8 @@ struct PinnedBytes {
 struct Batch {
     PinnedBytes nt;
     std::string harena;
-    std::vector<uint64_t> roff, goff, hoff;  // hoff[g] .. hoff[g+1]: header of group g in harena
+    PinnedVec<uint64_t> roff, goff;  // page-locked like nt: an asynchronous batch is copied from where it lies
+    std::vector<uint64_t> hoff;      // hoff[g] .. hoff[g+1]: header of group g in harena
     void reset() {
         nt.clear();
         harena.clear();
@@ -879,8 +902,9 @@ struct Job {
     size_t len = 0;
     uint64_t seq = 0;
     int stage = 0;  // what the pool threads do with it next: 0 parse, 1 format the classified groups
+    off_t file_off = -1;  // >= 0: the block is read from the input file at this offset into `text` by the thread that parses it
     Batch batch;
-    std::vector<uint32_t> res;
+    PinnedVec<uint32_t> res;
     std::string out;
 };
 
@@ -897,6 +921,13 @@ class Queue {  // unbounded FIFO; the number of jobs in flight bounds it
     bool pop(T& v) {  // false once closed and drained
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = q_.front();
+        q_.erase(q_.begin());
+        return true;
+    }
+    bool try_pop(T& v) {  // false when nothing is queued right now
+        std::lock_guard<std::mutex> lk(mu_);
         if (q_.empty()) return false;
         v = q_.front();
         q_.erase(q_.begin());
@@ -973,6 +1004,10 @@ size_t find_cut(const char* buf, size_t len, const std::string& delim, size_t sp
 void parse_block(const char* p, const char* end, const std::string& delim, size_t span, Batch* B) {
     B->reset();
     B->nt.reserve(end - p);
+    if (B->roff.capacity() < (size_t)(end - p) / 48 + 16) {  // page-locked vectors grow dearly: sized once for blocks of short reads
+        B->roff.reserve((size_t)(end - p) / 48 + 16);
+        B->goff.reserve((size_t)(end - p) / 48 + 16);
+    }
     while (p < end) {
         const char* e = (const char*)memchr(p, '\n', end - p);  // header line
         const char* hend = e ? e : end;
@@ -1062,11 +1097,25 @@ int cmd_classify(int argc, char** argv) {
     }
     const auto t_loaded = std::chrono::steady_clock::now();
     std::atomic<uint64_t> n_reads{0}, n_bytes{0};
+    // the steady state's own clock: from the moment every job's buffers have been through one block (page-locked
+    // allocations and first-touch page faults behind it) -- reads counted as they are classified
+    std::chrono::steady_clock::time_point t_warm{};
+    uint64_t warm_reads = 0, warm_blocks = 0;
     // block size in bytes (UMGAP_CLI_BLOCK overrides it, for tests of the block seams)
-    const size_t block = getenv("UMGAP_CLI_BLOCK") ? std::max<size_t>(16, strtoull(getenv("UMGAP_CLI_BLOCK"), nullptr, 10)) : (size_t)32 << 20;
+    // 4 MB: a block's text and nucleotides stay in its parser thread's cache (8 MB blocks ran at 60-160 M reads/s from one run
+    // to the next, 32 MB blocks at 47-69 M, 4 MB blocks at 150-185 M: profiles/r02_cli_probe*.log)
+    const size_t block = getenv("UMGAP_CLI_BLOCK") ? std::max<size_t>(16, strtoull(getenv("UMGAP_CLI_BLOCK"), nullptr, 10)) : (size_t)4 << 20;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t P = a.has("parser-threads") ? std::max<size_t>(1, parse_usize(a.get("parser-threads", "1"))) : std::min<size_t>(std::max(2u, hw - 2), 12);
-    const size_t njobs = 2 * (P + G) + 2;
+    // blocks in flight per GPU (UMGAP_CLI_DEPTH), and how the parser threads get at a mapped input file's bytes
+    // (UMGAP_CLI_READ): populate = madvise(MADV_POPULATE_READ) on the block, then parse in place (a fault per page, twelve
+    // threads on one address space: 103 M reads/s against 153 M); pread = into the job's own buffer (80 M); mmap = as it
+    // comes.  Measured in profiles/README.md section 8.
+    const size_t depth = getenv("UMGAP_CLI_DEPTH") ? std::max<size_t>(1, std::min<size_t>(8, strtoull(getenv("UMGAP_CLI_DEPTH"), nullptr, 10))) : 2;
+    const std::string read_mode = getenv("UMGAP_CLI_READ") ? getenv("UMGAP_CLI_READ") : "populate";
+    const bool populate = read_mode == "populate";
+    (void)populate;
+    const size_t njobs = P + P / 2 + (depth + 1) * G + 2;
     const size_t span = 3 * (size_t)k;
 
     std::vector<std::unique_ptr<Job>> jobs(njobs);
@@ -1120,6 +1169,22 @@ int cmd_classify(int argc, char** argv) {
             while (parse_q.pop(j)) {
                 try {
                     if (j->stage == 0) {
+                        if (j->file_off >= 0) {  // the block's bytes, read by the thread that parses them
+                            if (j->text.size() < j->len) j->text.resize(j->len);
+                            for (size_t have = 0; have < j->len;) {
+                                const ssize_t n = pread(0, j->text.data() + have, j->len - have, j->file_off + (off_t)have);
+                                if (n < 0 && errno == EINTR) continue;
+                                if (n <= 0) fail("failed reading input");
+                                have += (size_t)n;
+                            }
+                            j->view = j->text.data();
+                        }
+#ifdef MADV_POPULATE_READ
+                        else if (populate) {  // a mapped block: its pages in one call instead of a fault per page
+                            const uintptr_t lo = (uintptr_t)j->view & ~(uintptr_t)4095;
+                            (void)madvise((void*)lo, (uintptr_t)j->view + j->len - lo, MADV_POPULATE_READ);
+                        }
+#endif
                         parse_block(j->view, j->view + j->len, delim, span, &j->batch);
                         classify_q.push(j);
                     } else {
@@ -1131,25 +1196,43 @@ int cmd_classify(int argc, char** argv) {
                 }
             }
         });
+    // classifier threads: one per GPU, `depth` blocks in flight (the next block's upload and first kernels run in the
+    // tail of the one before it: umgap_classify_reads_async)
     for (size_t g = 0; g < G; ++g)
         classifiers.emplace_back([&, g] {
-            Job* j;
-            while (classify_q.pop(j)) {
-                try {
+            std::vector<std::pair<Job*, umgap_pending*>> fl;
+            auto finish = [&]() {
+                Job* j = fl.front().first;
+                umgap_pending* t = fl.front().second;
+                fl.erase(fl.begin());
+                if (t) check(umgap_pending_wait(t));
+                n_reads += j->batch.roff.size() - 1;
+                n_bytes += j->len;
+                j->stage = 1;
+                parse_q.push(j);
+            };
+            try {
+                for (;;) {
+                    Job* j = nullptr;
+                    const bool got = fl.size() >= depth ? false : fl.empty() ? classify_q.pop(j) : classify_q.try_pop(j);
+                    if (!got) {
+                        if (fl.empty()) break;  // closed and drained
+                        finish();
+                        continue;
+                    }
                     Batch& B = j->batch;
                     const size_t ng = B.groups();
                     j->res.resize(ng);
+                    umgap_pending* t = nullptr;
                     if (ng)
-                        check(umgap_classify_reads(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.p, B.roff.data(), B.roff.size() - 1,
-                                                   B.goff.data(), ng, j->res.data(), nullptr));
-                    n_reads += B.roff.size() - 1;
-                    n_bytes += j->len;
-                    j->stage = 1;
-                    parse_q.push(j);
-                } catch (const std::exception& e) {
-                    set_error(e.what());
-                    break;
+                        check(umgap_classify_reads_async(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.p, B.roff.data(), B.roff.size() - 1,
+                                                         B.goff.data(), ng, j->res.data(), &t));
+                    fl.emplace_back(j, t);
                 }
+            } catch (const std::exception& e) {
+                for (auto& f : fl)  // every ticket is waited for before its index goes
+                    if (f.second) (void)umgap_pending_wait(f.second);
+                set_error(e.what());
             }
         });
     std::thread writer([&] {
@@ -1176,6 +1259,11 @@ int cmd_classify(int argc, char** argv) {
                 return;
             }
             ++next;
+            if (next == 2 * njobs) {
+                t_warm = std::chrono::steady_clock::now();
+                warm_reads = n_reads.load();
+                warm_blocks = next;
+            }
             free_q.push(j);
         }
     });
@@ -1187,12 +1275,14 @@ int cmd_classify(int argc, char** argv) {
         struct stat sb;
         const char* map = nullptr;
         size_t map_len = 0;
+        off_t map_at = 0;
         if (fstat(0, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0 && !getenv("UMGAP_CLI_NO_MMAP")) {
             const off_t at = lseek(0, 0, SEEK_CUR);
             void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, 0, 0);
             if (m != MAP_FAILED && at >= 0 && at < sb.st_size) {
                 map = (const char*)m + at;
                 map_len = (size_t)(sb.st_size - at);
+                map_at = at;
             }
         }
         if (map) {
@@ -1213,6 +1303,7 @@ int cmd_classify(int argc, char** argv) {
                 if (!free_q.pop(j)) break;
                 j->stage = 0;
                 j->view = map + pos;
+                j->file_off = read_mode == "pread" ? map_at + (off_t)pos : (off_t)-1;
                 j->len = cut;
                 j->seq = seq++;
                 parse_q.push(j);
@@ -1228,6 +1319,7 @@ int cmd_classify(int argc, char** argv) {
                 Job* j;
                 if (!free_q.pop(j)) break;  // closed: an error elsewhere
                 j->stage = 0;
+                j->file_off = -1;
                 if (j->text.size() < block + carry.size()) j->text.resize(block + carry.size());
                 memcpy(j->text.data(), carry.data(), carry.size());
                 size_t have = carry.size();
@@ -1284,6 +1376,11 @@ int cmd_classify(int argc, char** argv) {
         fprintf(stderr, "umgap classify: %llu reads, %llu bytes of FASTA in %.3f s after the index was loaded: %.2f M reads/s, %.2f GB/s "
                 "(%zu parser threads, %zu GPU(s))\n", (unsigned long long)n_reads.load(), (unsigned long long)n_bytes.load(), dt,
                 n_reads.load() / dt / 1e6, n_bytes.load() / dt / 1e9, P, G);
+        if (warm_blocks) {
+            const double ds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_warm).count();
+            fprintf(stderr, "umgap classify steady state: %.2f M reads/s over the %.3f s after the first %llu blocks\n",
+                    (n_reads.load() - warm_reads) / ds / 1e6, ds, (unsigned long long)warm_blocks);
+        }
     }
     return 0;
 }
@@ -1291,28 +1388,6 @@ int cmd_classify(int argc, char** argv) {
 // ---- classify-peptides: the tryptic presets in one process (extension) -----------------------------
 // prot2tryp2lca | uniq -d / | taxa2agg (scripts/umgap-analyse.sh:291-300) behind the gene predictor: peptide records
 // on stdin, `>header\n<taxon>\n` per group of records on stdout.
-// Page-locked vectors (umgap_host_alloc): the library's copies of the ranges of a batch overlap its kernels only from
-// and into such memory.
-template <class T>
-struct PinnedAlloc {
-    using value_type = T;
-    PinnedAlloc() = default;
-    template <class U>
-    PinnedAlloc(const PinnedAlloc<U>&) {}
-    T* allocate(size_t n) {
-        void* p = umgap_host_alloc(n * sizeof(T));
-        if (!p) throw std::bad_alloc();
-        return (T*)p;
-    }
-    void deallocate(T* p, size_t) { umgap_host_free(p); }
-    template <class U>
-    bool operator==(const PinnedAlloc<U>&) const { return true; }
-    template <class U>
-    bool operator!=(const PinnedAlloc<U>&) const { return false; }
-};
-template <class T>
-using PinnedVec = std::vector<T, PinnedAlloc<T>>;
-
 int cmd_classify_peptides(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'l', "minlen", true}, {'L', "maxlen", true}, {'k', "keep", true}, {'d', "drop", true},
                                    {'D', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
