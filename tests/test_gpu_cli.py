@@ -276,6 +276,22 @@ def test_fused_peptide_cli_matches_the_three_stage_pipe(files):
         assert rc == 0, err
         assert got == want, (tflags, aflags)
         assert got.count(">") == 42 and sum(l != "1" for l in got.split("\n")[1::2]) > 10
+        # the command parses blocks of whole groups on several threads: seams at every place, from a pipe and from a file
+        # (mapped and cut in place), CRLF line ends, no final newline, two classifier threads
+        odd = text.replace("\n", "\r\n", 30).rstrip("\n")
+        (d / "pep.fa").write_text(odd)
+        for block, devices, extra in (("16", None, ["-P", "1"]), ("300", "0,0", ["-P", "3"]), ("5000", None, [])):
+            env = dict(os.environ, UMGAP_CLI_BLOCK=block)
+            if devices:
+                env["UMGAP_DEVICES"] = devices
+            cmd = [UMGAP, "classify-peptides"] + extra + fused_flags + [str(d / "tryp.fst"), str(d / "taxons.tsv")]
+            p = subprocess.run(cmd, input=odd.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+            assert p.returncode == 0, p.stderr.decode()
+            assert p.stdout.decode() == want, (block, devices)
+            with open(d / "pep.fa", "rb") as f:
+                p = subprocess.run(cmd, stdin=f, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+            assert p.returncode == 0, p.stderr.decode()
+            assert p.stdout.decode() == want, (block, devices, "file")
 
 
 def test_fused_cli_block_parser_edge_cases(files):
@@ -305,6 +321,18 @@ def test_fused_cli_block_parser_edge_cases(files):
                            timeout=300, env=env)
         assert p.returncode == 0, p.stderr.decode()
         assert p.stdout.decode() == want, (block, devices)
+    # a regular file on stdin is mapped and cut in place; the parser threads populate, read or fault their blocks' pages
+    (d / "edge.fa").write_text(text)
+    for block, mode in ((None, None), ("16", "populate"), ("300", "pread"), ("2000", "mmap"), ("70000", "populate")):
+        env = dict(os.environ)
+        if block:
+            env["UMGAP_CLI_BLOCK"] = block
+        if mode:
+            env["UMGAP_CLI_READ"] = mode
+        with open(d / "edge.fa", "rb") as f:
+            p = subprocess.run([UMGAP] + args, stdin=f, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout.decode() == want, (block, mode, "file")
     # a short read between the mates of a pair is dropped before uniq sees it (prot2kmer2lca.rs:172): the mates still join,
     # also when a block seam falls next to it
     lines = text.split("\n>")

@@ -1046,29 +1046,67 @@ void parse_block(const char* p, const char* end, const std::string& delim, size_
     B->goff.push_back(B->roff.size() - 1);
 }
 
+// Peptide records (what the gene predictor prints): every physical line is an item of its record
+// (prot2tryp2lca.rs:105-118), records with the same header up to the delimiter form a group; nt = the residues,
+// roff = line offsets, goff = lines before each group.  A record without lines still names its group.
+void parse_peptide_block(const char* p, const char* end, const std::string& delim, Batch* B) {
+    B->reset();
+    B->nt.reserve(end - p);
+    if (B->roff.capacity() < (size_t)(end - p) / 16 + 16) {
+        B->roff.reserve((size_t)(end - p) / 16 + 16);
+        B->goff.reserve((size_t)(end - p) / 16 + 16);
+    }
+    while (p < end) {
+        const char* e = (const char*)memchr(p, '\n', end - p);  // header line
+        const char* hend = e ? e : end;
+        const char* hs = p + 1;
+        size_t hl = hend - hs;
+        if (hl && hs[hl - 1] == '\r') --hl;
+        p = e ? e + 1 : end;
+        if (!delim.empty()) {
+            const void* m = memmem(hs, hl, delim.data(), delim.size());
+            if (m) hl = (const char*)m - hs;
+        }
+        const size_t ng = B->groups();
+        const bool same = ng && B->hoff[ng] - B->hoff[ng - 1] == hl && memcmp(B->harena.data() + B->hoff[ng - 1], hs, hl) == 0;
+        if (!same) {
+            B->goff.push_back(B->roff.size() - 1);
+            B->harena.append(hs, hl);
+            B->hoff.push_back(B->harena.size());
+        }
+        while (p < end && *p != '>') {
+            const char* le = (const char*)memchr(p, '\n', end - p);
+            const char* lend = le ? le : end;
+            size_t ll = lend - p;
+            if (ll && p[ll - 1] == '\r') --ll;
+            B->nt.append(p, ll);
+            B->roff.push_back(B->nt.size());
+            p = le ? le + 1 : end;
+        }
+    }
+    B->goff.push_back(B->roff.size() - 1);
+}
+
 }  // namespace classify_cli
 
-int cmd_classify(int argc, char** argv) {
-    using namespace classify_cli;
-    Args a = parse(argc, argv, 2, {{'t', "table", true}, {'M', "methionine", false}, {'k', "length", true}, {'O', "omit-misses", false},
-                                   {'S', "no-seedextend", false}, {'s', "min-seed-size", true}, {'g', "max-gap-size", true},
-                                   {'d', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
-                                   {'f', "factor", true}, {'l', "lower-bound", true}, {'G', "gpus", true}, {'P', "parser-threads", true}});
-    if (a.pos.size() != 2) fail("usage: umgap classify [flags] [--gpus N] <fst-file> <taxon-file> < reads.fa");
+// What the block pipeline below runs: reads (translate | prot2kmer2lca | seedextend | uniq | taxa2agg) or peptide
+// records (prot2tryp2lca | uniq | taxa2agg).
+struct BlockPipeline {
+    bool peptides = false;
     umgap_pipeline_opts o;
-    umgap_pipeline_opts_default(&o);
-    o.table = (int)parse_usize(a.get("table", "1"));
-    o.methionine = a.has("methionine");
-    o.one_on_one = !a.has("omit-misses");
-    o.seedextend = !a.has("no-seedextend");
-    o.min_seed_size = (int)parse_usize(a.get("min-seed-size", "2"));
-    o.max_gap_size = (int)parse_usize(a.get("max-gap-size", "0"));
-    o.strategy = parse_strategy(a.get("method", a.get("aggregate", "hybrid") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "hybrid"));
-    o.factor = parse_f32(a.get("factor", "0.25"));
-    o.lower_bound = parse_f32(a.get("lower-bound", "0"));
-    o.ranked_only = a.has("ranked");
-    const std::string delim = a.get("delimiter", "/");  // the presets join the mates with `uniq -d /`
-    const int k = (int)parse_usize(a.get("length", "9"));
+    umgap_tryp_opts to;
+    std::string delim;
+    int k = 9;
+};
+
+// Blocks of whole uniq groups cut from stdin, parsed on K threads straight into the library's arrays, classified on
+// one thread per GPU, formatted on the pool threads, printed in input order.
+int run_block_pipeline(const Args& a, const BlockPipeline& cfg) {
+    using namespace classify_cli;
+    const umgap_pipeline_opts& o = cfg.o;
+    const std::string& delim = cfg.delim;
+    const int k = cfg.k;
+    const bool peptides = cfg.peptides;
     // devices: UMGAP_DEVICES=0,2,3 or --gpus N (devices 0..N-1); one by default
     std::vector<int> devices;
     if (const char* e = getenv("UMGAP_DEVICES")) {
@@ -1092,7 +1130,8 @@ int cmd_classify(int argc, char** argv) {
     check(umgap_index_load_fst(a.pos[0].c_str(), k, devices[0], 0.0, &idx[0].p));
     check(umgap_taxonomy_load(a.pos[1].c_str(), devices[0], &tax[0].p));
     for (size_t g = 1; g < G; ++g) {
-        check(umgap_index_replicate(idx[0].p, devices[g], &idx[g].p));
+        if (peptides) check(umgap_index_load_fst(a.pos[0].c_str(), 0, devices[g], 0.0, &idx[g].p));  // a peptide table is streamed again
+        else check(umgap_index_replicate(idx[0].p, devices[g], &idx[g].p));
         check(umgap_taxonomy_replicate(tax[0].p, devices[g], &tax[g].p));
     }
     const auto t_loaded = std::chrono::steady_clock::now();
@@ -1116,7 +1155,7 @@ int cmd_classify(int argc, char** argv) {
     const bool populate = read_mode == "populate";
     (void)populate;
     const size_t njobs = P + P / 2 + (depth + 1) * G + 2;
-    const size_t span = 3 * (size_t)k;
+    const size_t span = peptides ? 0 : 3 * (size_t)k;  // every peptide record takes part in uniq's grouping
 
     std::vector<std::unique_ptr<Job>> jobs(njobs);
     Queue<Job*> free_q, parse_q, classify_q;
@@ -1150,11 +1189,11 @@ int cmd_classify(int argc, char** argv) {
         j->out.clear();
         j->out.reserve(B.harena.size() + 12 * ng);
         for (size_t x = 0; x < ng; ++x) {
-            if (j->res[x] == UMGAP_ABSENT) continue;
+            if (j->res[x] == UMGAP_ABSENT && !peptides) continue;
             j->out += '>';
             j->out.append(B.harena, B.hoff[x], B.hoff[x + 1] - B.hoff[x]);
             j->out += '\n';
-            append_u32(j->out, j->res[x]);
+            append_u32(j->out, j->res[x] == UMGAP_ABSENT ? 1u : j->res[x]);  // a peptide record without lines aggregates to the literal 1
             j->out += '\n';
         }
         {
@@ -1185,7 +1224,8 @@ int cmd_classify(int argc, char** argv) {
                             (void)madvise((void*)lo, (uintptr_t)j->view + j->len - lo, MADV_POPULATE_READ);
                         }
 #endif
-                        parse_block(j->view, j->view + j->len, delim, span, &j->batch);
+                        if (peptides) parse_peptide_block(j->view, j->view + j->len, delim, &j->batch);
+                        else parse_block(j->view, j->view + j->len, delim, span, &j->batch);
                         classify_q.push(j);
                     } else {
                         format_job(j);
@@ -1224,7 +1264,10 @@ int cmd_classify(int argc, char** argv) {
                     const size_t ng = B.groups();
                     j->res.resize(ng);
                     umgap_pending* t = nullptr;
-                    if (ng)
+                    if (ng && peptides)  // ranges of the batch overlap inside the call
+                        check(umgap_classify_peptides(idx[g].p, tax[g].p, &cfg.to, (const uint8_t*)B.nt.p, B.roff.data(), B.roff.size() - 1,
+                                                      B.goff.data(), ng, j->res.data()));
+                    else if (ng)
                         check(umgap_classify_reads_async(idx[g].p, tax[g].p, &o, (const uint8_t*)B.nt.p, B.roff.data(), B.roff.size() - 1,
                                                          B.goff.data(), ng, j->res.data(), &t));
                     fl.emplace_back(j, t);
@@ -1385,89 +1428,58 @@ int cmd_classify(int argc, char** argv) {
     return 0;
 }
 
+int cmd_classify(int argc, char** argv) {
+    using namespace classify_cli;
+    Args a = parse(argc, argv, 2, {{'t', "table", true}, {'M', "methionine", false}, {'k', "length", true}, {'O', "omit-misses", false},
+                                   {'S', "no-seedextend", false}, {'s', "min-seed-size", true}, {'g', "max-gap-size", true},
+                                   {'d', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
+                                   {'f', "factor", true}, {'l', "lower-bound", true}, {'G', "gpus", true}, {'P', "parser-threads", true}});
+    if (a.pos.size() != 2) fail("usage: umgap classify [flags] [--gpus N] <fst-file> <taxon-file> < reads.fa");
+    umgap_pipeline_opts o;
+    umgap_pipeline_opts_default(&o);
+    o.table = (int)parse_usize(a.get("table", "1"));
+    o.methionine = a.has("methionine");
+    o.one_on_one = !a.has("omit-misses");
+    o.seedextend = !a.has("no-seedextend");
+    o.min_seed_size = (int)parse_usize(a.get("min-seed-size", "2"));
+    o.max_gap_size = (int)parse_usize(a.get("max-gap-size", "0"));
+    o.strategy = parse_strategy(a.get("method", a.get("aggregate", "hybrid") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "hybrid"));
+    o.factor = parse_f32(a.get("factor", "0.25"));
+    o.lower_bound = parse_f32(a.get("lower-bound", "0"));
+    o.ranked_only = a.has("ranked");
+    const std::string delim = a.get("delimiter", "/");  // the presets join the mates with `uniq -d /`
+    const int k = (int)parse_usize(a.get("length", "9"));
+    BlockPipeline cfg;
+    cfg.o = o;
+    cfg.delim = delim;
+    cfg.k = k;
+    return run_block_pipeline(a, cfg);
+}
+
 // ---- classify-peptides: the tryptic presets in one process (extension) -----------------------------
 // prot2tryp2lca | uniq -d / | taxa2agg (scripts/umgap-analyse.sh:291-300) behind the gene predictor: peptide records
 // on stdin, `>header\n<taxon>\n` per group of records on stdout.
 int cmd_classify_peptides(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {{'l', "minlen", true}, {'L', "maxlen", true}, {'k', "keep", true}, {'d', "drop", true},
                                    {'D', "delimiter", true}, {'r', "ranked", false}, {'m', "method", true}, {'a', "aggregate", true},
-                                   {'f', "factor", true}, {'b', "lower-bound", true}});
-    if (a.pos.size() != 2) fail("usage: umgap classify-peptides [flags] <tryptic-fst-file> <taxon-file> < peptides.fa");
-    umgap_tryp_opts o;
-    umgap_tryp_opts_default(&o);
-    o.minlen = (int)parse_usize(a.get("minlen", "5"));
-    o.maxlen = (int)parse_usize(a.get("maxlen", "50"));
+                                   {'f', "factor", true}, {'b', "lower-bound", true}, {'G', "gpus", true}, {'P', "parser-threads", true}});
+    if (a.pos.size() != 2) fail("usage: umgap classify-peptides [flags] [--gpus N] <tryptic-fst-file> <taxon-file> < peptides.fa");
+    BlockPipeline cfg;
+    cfg.peptides = true;
+    umgap_pipeline_opts_default(&cfg.o);
+    umgap_tryp_opts_default(&cfg.to);
+    cfg.to.minlen = (int)parse_usize(a.get("minlen", "5"));
+    cfg.to.maxlen = (int)parse_usize(a.get("maxlen", "50"));
     const std::string keep = a.get("keep", ""), drop = a.get("drop", "");
-    o.keep = keep.c_str();
-    o.drop = drop.c_str();
-    o.strategy = parse_strategy(a.get("method", a.get("aggregate", "mrtl") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "mrtl"));
-    o.factor = parse_f32(a.get("factor", "0.25"));
-    o.lower_bound = parse_f32(a.get("lower-bound", "0"));
-    o.ranked_only = a.has("ranked");
-    const std::string delim = a.get("delimiter", "/");
-    IndexHandle idx;
-    TaxHandle tax;
-    check(umgap_index_load_fst(a.pos[0].c_str(), 0, 0, 0.0, &idx.p));
-    check(umgap_taxonomy_load(a.pos[1].c_str(), 0, &tax.p));
-    BlockReader br(stdin);
-    std::string harena, out;
-    PinnedVec<char> aa;
-    PinnedVec<uint64_t> loff{0}, goff;
-    std::vector<uint64_t> hoff{0};
-    PinnedVec<uint32_t> res;
-    aa.reserve(64u << 20);
-    loff.reserve(2 * kBatchRecords * 4 + 16);
-    goff.reserve(kBatchRecords * 4 + 16);
-    auto flush = [&]() {
-        const size_t ng = hoff.size() - 1;
-        if (!ng) return;
-        goff.push_back(loff.size() - 1);
-        res.assign(ng, 0);
-        aa.reserve(aa.size() + 16);
-        check(umgap_classify_peptides(idx.p, tax.p, &o, (const uint8_t*)aa.data(), loff.data(), loff.size() - 1, goff.data(), ng, res.data()));
-        out.clear();
-        for (size_t g = 0; g < ng; ++g) {
-            out += '>';
-            out.append(harena, hoff[g], hoff[g + 1] - hoff[g]);
-            out += '\n';
-            append_u32(out, res[g] == UMGAP_ABSENT ? 1u : res[g]);  // a record without lines aggregates to the literal 1
-            out += '\n';
-        }
-        put(stdout, out);
-        aa.clear();
-        harena.clear();
-        loff.assign(1, 0);
-        goff.clear();
-        hoff.assign(1, 0);
-    };
-    const char *p, *end;
-    while (br.next(p, end))
-        while (p < end) {
-            const char* ls;
-            size_t ll;
-            take_line(p, end, ls, ll);
-            const char* hs = ls + 1;
-            size_t hl = ll - 1;
-            if (!delim.empty()) {
-                const void* m = memmem(hs, hl, delim.data(), delim.size());
-                if (m) hl = (const char*)m - hs;
-            }
-            const size_t ng = hoff.size() - 1;
-            const bool same = ng && hoff[ng] - hoff[ng - 1] == hl && memcmp(harena.data() + hoff[ng - 1], hs, hl) == 0;
-            if (!same) {
-                if (ng >= kBatchRecords * 4) flush();
-                goff.push_back(loff.size() - 1);
-                harena.append(hs, hl);
-                hoff.push_back(harena.size());
-            }
-            while (p < end && *p != '>') {  // one item per physical line (prot2tryp2lca.rs:105-118)
-                take_line(p, end, ls, ll);
-                aa.insert(aa.end(), ls, ls + ll);
-                loff.push_back(aa.size());
-            }
-        }
-    flush();
-    return 0;
+    cfg.to.keep = keep.c_str();
+    cfg.to.drop = drop.c_str();
+    cfg.to.strategy = parse_strategy(a.get("method", a.get("aggregate", "mrtl") == "mrtl" ? "rmq" : "tree"), a.get("aggregate", "mrtl"));
+    cfg.to.factor = parse_f32(a.get("factor", "0.25"));
+    cfg.to.lower_bound = parse_f32(a.get("lower-bound", "0"));
+    cfg.to.ranked_only = a.has("ranked");
+    cfg.delim = a.get("delimiter", "/");
+    cfg.k = 0;
+    return run_block_pipeline(a, cfg);
 }
 
 void usage(FILE* f) {
@@ -1486,7 +1498,7 @@ void usage(FILE* f) {
           "    taxa2freq        Counts taxon ids per ranked ancestor (CSV)\n"
           "    bestof           Picks the best record of every group of frames\n"
           "    classify         translate | prot2kmer2lca | seedextend | uniq | taxa2agg in one process [--gpus N]\n"
-          "    classify-peptides  prot2tryp2lca | uniq | taxa2agg in one process\n", f);
+          "    classify-peptides  prot2tryp2lca | uniq | taxa2agg in one process [--gpus N]\n", f);
 }
 
 // Lines of a stream without their line ends, as (pointer, length) views that stay valid until the next call.
