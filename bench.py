@@ -875,8 +875,8 @@ def run_ours(args):
         e2e_bytes = timed_e2e(lambda: capi.classify_reads(gidx, gtax, opts, nt_np, h_roff, h_goff, count_lookups=False, out=h_out))
         e2e_bytes["entry_point"] = "umgap_classify_reads: pinned host arrays, one byte per nucleotide"
         e2e_bytes["host_input_bytes_per_step"] = int(total_nt + h_roff.nbytes + h_goff.nbytes)
-        # (b) the packed form (umgap_classify_reads_packed): 2 bits per nucleotide + N flags, what the CLI's block parser
-        #     emits; the packing (umgap_pack_reads) is timed beside it, not inside: it is the parser's job, once per read
+        # (b) the packed form (umgap_classify_reads_packed): 2 bits per nucleotide + N flags, a form a parser can
+        #     emit; the packing (umgap_pack_reads) is timed beside it, not inside: it is the parser's job, once per read
         nw = (total_nt + 15) // 16
         p_codes = torch.empty(nw, dtype=torch.int32).pin_memory()
         p_entries = torch.empty(max(1, nw // 8), dtype=torch.int64).pin_memory()
@@ -928,6 +928,68 @@ def run_ours(args):
         e2e["pack_reads_ms_per_step_untimed"] = 1e3 * pack_s
         e2e["pack_reads_threads"] = os.cpu_count()
         e2e["byte_form"] = e2e_bytes
+        if world == 1:
+            # (d) from bytes with the packing inside the timed region: umgap_pack_reads (all host threads) into one of three
+            #     page-locked sets, the packed batch handed over asynchronously, the batch that used the set before waited
+            #     for first -- the host packs batch i while the GPU classifies batch i - 1
+            sets = [(codes_np, p_entries.numpy().view(np.uint64))]
+            _keep = []
+            for _ in range(2):
+                c_t, e_t = torch.empty(nw, dtype=torch.int32).pin_memory(), torch.empty(max(1, nw // 8), dtype=torch.int64).pin_memory()
+                _keep.append((c_t, e_t))
+                sets.append((c_t.numpy().view(np.uint32), e_t.numpy().view(np.uint64)))
+            outs3 = [h_out, h_out2, pinned(np.zeros(B, dtype=np.uint32))[0]]
+            pack_in_s = [0.0, 0.0, 0.0]
+            pack_threads = int(os.environ.get("UMGAP_BENCH_PACK_THREADS", "0"))
+
+            def from_bytes():
+                # a packer thread (umgap_pack_reads spreads over the host threads itself) and this thread, which hands the
+                # packed sets over and waits for their results: the structure of a streaming host (the CLI's parser and
+                # classifier threads)
+                import queue
+                import threading
+                free_q, ready_q = queue.Queue(), queue.Queue()
+                for k_ in range(3):
+                    free_q.put(k_)
+
+                def packer():
+                    for _i in range(n_pipe):
+                        k_ = free_q.get()
+                        t_s = time.perf_counter()
+                        c_, e_ = capi.pack_reads(nt_np, pack_threads, codes=sets[k_][0], entries=sets[k_][1])
+                        pack_in_s[0] += time.perf_counter() - t_s
+                        ready_q.put((k_, c_, e_))
+
+                th = threading.Thread(target=packer)
+                th.start()
+                pend = []
+                for _i in range(n_pipe):
+                    k_, c_, e_ = ready_q.get()
+                    t_p = time.perf_counter()
+                    pend.append((k_, capi.classify_reads_packed_async(gidx, gtax, opts, c_, e_, h_roff, h_goff, out=outs3[k_])))
+                    t_w = time.perf_counter()
+                    pack_in_s[2] += t_w - t_p
+                    if len(pend) >= 2:
+                        k0, p0 = pend.pop(0)
+                        p0.wait()
+                        free_q.put(k0)
+                    pack_in_s[1] += time.perf_counter() - t_w
+                for k0, p0 in pend:
+                    p0.wait()
+                th.join()
+
+            from_bytes()
+            if not all(np.array_equal(o_, dev_out) for o_ in outs3):
+                raise SystemExit("the packed-on-the-fly path and the device-resident entry point disagree")
+            pack_in_s[:] = [0.0, 0.0, 0.0]
+            fb = timed_e2e(from_bytes, calls=1, steps_per_call=n_pipe)
+            fb["pack_ms_per_step_inside"] = 1e3 * pack_in_s[0] / n_pipe
+            fb["host_wait_ms_per_step"] = 1e3 * pack_in_s[1] / n_pipe
+            fb["host_submit_ms_per_step"] = 1e3 * pack_in_s[2] / n_pipe
+            fb["entry_point"] = ("umgap_pack_reads (bytes -> 2-bit codes + N words, all host threads) on a packer thread + "
+                                 "umgap_classify_reads_packed_async on this one, three page-locked sets, two batches in flight: the host "
+                                 "packs a batch while the GPU classifies the ones before it")
+            e2e["from_bytes_packed_on_the_fly"] = fb
 
     was_routed = routed is not None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -72,6 +72,10 @@ struct umgap_index {
     // batches enqueued by the asynchronous host-buffer calls and not yet waited for; their device error slots
     mutable uint32_t pending = 0, errq_next = 0, chunk_next = 0;
     mutable bool errq_ready = false;
+    // page-locked mirror of the error slots: a batch's slot is copied into it behind its last kernel, on a stream of
+    // its own, so that the wait reads host memory instead of issuing a copy
+    mutable void* errq_host = nullptr;
+    mutable cudaStream_t errq_stream = nullptr;
 
     umgap::TableView view() const {
         umgap::TableView v{};

@@ -1991,9 +1991,10 @@ struct HostReads {  // one of the two host forms of a batch's nucleotides
 // the device slot its classify kernels report an unknown taxon to.
 struct umgap_pending {
     const umgap_index* idx = nullptr;
-    cudaEvent_t ev[kMaxBufs] = {};
+    cudaEvent_t ev[kMaxBufs + 1] = {};
     int nev = 0;
-    DevError* err = nullptr;
+    DevError* err = nullptr;       // the batch's device slot
+    DevError* err_host = nullptr;  // its page-locked mirror, valid behind the last event
 };
 extern "C++" {
 
@@ -2064,10 +2065,15 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
         DevError* ring = (DevError*)idx->ws.get(WS_ERRQ, kErrRing * sizeof(DevError));
         if (!idx->errq_ready) {
             UMGAP_CUDA(cudaMemset(ring, 0, kErrRing * sizeof(DevError)));
+            UMGAP_CUDA(cudaHostAlloc(&idx->errq_host, kErrRing * sizeof(DevError), cudaHostAllocDefault));
+            memset(idx->errq_host, 0, kErrRing * sizeof(DevError));
+            UMGAP_CUDA(cudaStreamCreateWithFlags(&idx->errq_stream, cudaStreamNonBlocking));
             idx->errq_ready = true;
         }
-        err = ring + (idx->errq_next++ % kErrRing);
+        const uint32_t slot = idx->errq_next++ % kErrRing;
+        err = ring + slot;
         pend->err = err;
+        pend->err_host = (DevError*)idx->errq_host + slot;
     } else {
         err = (DevError*)idx->ws.get(WS_ERR, sizeof(DevError));
         UMGAP_CUDA(cudaMemset(err, 0, sizeof(DevError)));
@@ -2161,7 +2167,15 @@ static void classify_host(const umgap_index* idx, const umgap_taxonomy* tax, con
                 UMGAP_CUDA(cudaEventCreateWithFlags(&pend->ev[pend->nev], cudaEventDisableTiming));
                 ++pend->nev;
                 UMGAP_CUDA(cudaEventRecord(pend->ev[pend->nev - 1], st[i]));
+                UMGAP_CUDA(cudaStreamWaitEvent(idx->errq_stream, pend->ev[pend->nev - 1], 0));
             }
+            // the error slot goes to its page-locked mirror behind every chunk stream, on a stream of its own (the chunk
+            // streams stay independent of each other); the wait then reads host memory (a synchronous copy per batch
+            // held the waiting thread for 2.5 ms beside a batch in flight)
+            UMGAP_CUDA(cudaMemcpyAsync(pend->err_host, err, sizeof(DevError), cudaMemcpyDeviceToHost, idx->errq_stream));
+            UMGAP_CUDA(cudaEventCreateWithFlags(&pend->ev[pend->nev], cudaEventDisableTiming));
+            ++pend->nev;
+            UMGAP_CUDA(cudaEventRecord(pend->ev[pend->nev - 1], idx->errq_stream));
             return;
         }
         for (int i = 0; i < kBufs; ++i) UMGAP_CUDA(cudaStreamSynchronize(st[i]));
@@ -2250,9 +2264,12 @@ int umgap_pending_wait(umgap_pending* p) {
         use_device(p->idx->device);
         for (int i = 0; i < p->nev; ++i) UMGAP_CUDA(cudaEventSynchronize(p->ev[i]));
         DevError he{};
-        if (p->err) {
-            UMGAP_CUDA(cudaMemcpy(&he, p->err, sizeof he, cudaMemcpyDeviceToHost));
-            if (he.flag) UMGAP_CUDA(cudaMemset(p->err, 0, sizeof(DevError)));
+        if (p->err_host) {
+            he = *p->err_host;
+            if (he.flag) {  // the slot is zero again when the ring comes back to it
+                UMGAP_CUDA(cudaMemset(p->err, 0, sizeof(DevError)));
+                *p->err_host = DevError{};
+            }
         }
         raise_dev_error(he);
     });

@@ -465,6 +465,8 @@ void umgap_index_free(umgap_index* idx) {
         if (idx->chunk_stream[i]) cudaStreamDestroy(idx->chunk_stream[i]);
         if (idx->chunk_done[i]) cudaEventDestroy(idx->chunk_done[i]);
     }
+    if (idx->errq_stream) cudaStreamDestroy(idx->errq_stream);
+    if (idx->errq_host) cudaFreeHost(idx->errq_host);
     delete idx;
 }
 
