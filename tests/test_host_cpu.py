@@ -304,6 +304,22 @@ def test_pack_reads_host_packer():
     with pytest.raises(capi.UmgapError) as e:
         capi.pack_reads(nt, entries=np.zeros(3, dtype=np.uint64))
     assert e.value.code == -5   # UMGAP_ERR_CAPACITY
+    # the packer takes 32 nucleotides per step where the host has AVX2 and 8 otherwise (chosen once per process):
+    # the other form, in a process of its own, packs the same words
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from umgap_b200 import capi; "
+            "rng = np.random.default_rng(3); a = np.frombuffer(b'ACGTNacgtRY\\x00\\xff', dtype=np.uint8); "
+            "nt = a[rng.choice(len(a), size=200003, p=[0.24] * 4 + [0.04 / 9] * 9)]; c, e = capi.pack_reads(nt, threads=2); "
+            "print(int(c.sum(dtype=np.uint64)), len(e), int(e.sum(dtype=np.uint64)))" % ROOT)
+    outs = []
+    for scalar in (False, True):
+        env = dict(os.environ)
+        env.pop("UMGAP_PACK_SCALAR", None)
+        if scalar:
+            env["UMGAP_PACK_SCALAR"] = "1"
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, check=True, stdout=subprocess.PIPE).stdout)
+    assert outs[0] == outs[1] and len(outs[0].split()) == 3
 
 
 def test_cli_buildindex_printindex_roundtrip(built, tmp_path):

@@ -1152,8 +1152,9 @@ int run_block_pipeline(const Args& a, const BlockPipeline& cfg) {
     // comes.  Measured in profiles/README.md section 8.
     const size_t depth = getenv("UMGAP_CLI_DEPTH") ? std::max<size_t>(1, std::min<size_t>(8, strtoull(getenv("UMGAP_CLI_DEPTH"), nullptr, 10))) : 2;
     const std::string read_mode = getenv("UMGAP_CLI_READ") ? getenv("UMGAP_CLI_READ") : "populate";
+#ifdef MADV_POPULATE_READ
     const bool populate = read_mode == "populate";
-    (void)populate;
+#endif
     const size_t njobs = P + P / 2 + (depth + 1) * G + 2;
     const size_t span = peptides ? 0 : 3 * (size_t)k;  // every peptide record takes part in uniq's grouping
 
