@@ -1,6 +1,6 @@
 """Steady-state rate of `umgap classify` from a FASTA file under its measurement knobs (UMGAP_CLI_READ, UMGAP_CLI_DEPTH,
 --parser-threads): the reads of tests/test_gpu_cli.py::test_cli_wall_clock_through_pipes, many times over.
-  python scripts/cli_probe.py [reps] [variant,variant,...]     variant = read:depth:parsers, e.g. pread:2:12
+  python tests/cli_probe.py [reps] [variant,variant,...]     variant = read:depth:parsers, e.g. pread:2:12
 """
 import os
 import subprocess
@@ -10,7 +10,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # datagen
 import numpy as np
 import datagen
 from oracle import cport, synth

@@ -1,5 +1,5 @@
 """Wall clock of every stage of the five-stage pipe on its own (files in, files out), and of the pipe: where the
-stage-wise CLI spends its time.  python scripts/stage_probe.py [npairs]"""
+stage-wise CLI spends its time.  python tests/cli_stage_probe.py [npairs]"""
 import os
 import subprocess
 import sys
@@ -8,7 +8,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # datagen
 import numpy as np
 import datagen
 from oracle import cport, synth
