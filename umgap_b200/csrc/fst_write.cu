@@ -47,6 +47,14 @@ struct Pending {             // a node on the unfrozen path
     bool open = false;       // the transition the path continues on (target not known yet)
     uint8_t open_input = 0;
     uint64_t open_output = 0;
+    void reset() {           // a node of the path is reused with the room its transitions already have
+        final_ = false;
+        final_output = 0;
+        arcs.clear();
+        open = false;
+        open_input = 0;
+        open_output = 0;
+    }
 };
 
 }  // namespace
@@ -60,12 +68,24 @@ struct umgap_fst_writer {
     uint64_t pos = 0;          // bytes written so far
     uint64_t last_addr = 0;    // address of the node written last
     uint64_t nkeys = 0;
-    std::vector<Pending> path; // path[i] is reached by the first i bytes of the last key
+    std::vector<Pending> path; // path[i], i < plen, is reached by the first i bytes of the last key; the rest is spare
+    size_t plen = 0;
     std::string last_key;
     bool any = false;
+    std::vector<uint8_t> buf;  // bytes not yet handed to the file (nodes are a few bytes each)
 
+    void push_node() {
+        if (plen == path.size()) path.emplace_back();
+        else path[plen].reset();
+        ++plen;
+    }
+    void flush_buf() {
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) UMGAP_FAIL(UMGAP_ERR_IO, "failed writing the fst");
+        buf.clear();
+    }
     void put(const void* p, size_t n) {
-        if (n && fwrite(p, 1, n, f) != n) UMGAP_FAIL(UMGAP_ERR_IO, "failed writing the fst");
+        if (buf.size() + n > (1u << 20)) flush_buf();
+        buf.insert(buf.end(), (const uint8_t*)p, (const uint8_t*)p + n);
         pos += n;
     }
     void put_le(uint64_t v, unsigned n) {
@@ -134,12 +154,12 @@ struct umgap_fst_writer {
     }
     // Freezes path[keep + 1 ..]: deepest first, each linked into its parent's open transition.
     void freeze_below(size_t keep) {
-        while (path.size() > keep + 1) {
-            Pending& nd = path.back();
+        while (plen > keep + 1) {
+            Pending& nd = path[plen - 1];
             const uint64_t addr = emit(nd);
             if (addr) last_addr = addr;
-            path.pop_back();
-            Pending& parent = path.back();
+            --plen;
+            Pending& parent = path[plen - 1];
             parent.arcs.push_back(Arc{parent.open_input, parent.open_output, addr});
             parent.open = false;
         }
@@ -160,9 +180,10 @@ int umgap_fst_writer_open(const char* path, umgap_fst_writer** out) {
         } else {
             w->f = stdout;
         }
+        w->buf.reserve((1u << 20) + 512);
         w->put_le(2, 8);
         w->put_le(0, 8);
-        w->path.emplace_back();
+        w->push_node();
         *out = w;
     });
     if (rc != UMGAP_OK && w) {
@@ -187,7 +208,7 @@ int umgap_fst_writer_insert(umgap_fst_writer* w, const uint8_t* key, size_t len,
         // walk the common prefix, leaving on each shared transition the part of its output the new value also has
         size_t p = 0;
         uint64_t rest = value;
-        while (p < len && p + 1 < w->path.size() && w->path[p].open && w->path[p].open_input == key[p]) {
+        while (p < len && p + 1 < w->plen && w->path[p].open && w->path[p].open_input == key[p]) {
             Pending& nd = w->path[p];
             const uint64_t common = std::min(nd.open_output, rest);
             const uint64_t push = nd.open_output - common;
@@ -211,9 +232,9 @@ int umgap_fst_writer_insert(umgap_fst_writer* w, const uint8_t* key, size_t len,
                 nd.open = true;
                 nd.open_input = key[i];
                 nd.open_output = i == p ? rest : 0;
-                w->path.emplace_back();
+                w->push_node();
             }
-            w->path.back().final_ = true;
+            w->path[w->plen - 1].final_ = true;
         }
         w->last_key.assign((const char*)key, len);
         w->any = true;
@@ -228,6 +249,7 @@ int umgap_fst_writer_finish(umgap_fst_writer* w) {
         const uint64_t root = w->emit(w->path[0]);
         w->put_le(w->nkeys, 8);
         w->put_le(root, 8);
+        w->flush_buf();
         if (fflush(w->f) != 0) UMGAP_FAIL(UMGAP_ERR_IO, "failed writing the fst");
     });
     if (w->owns && w->f) fclose(w->f);
