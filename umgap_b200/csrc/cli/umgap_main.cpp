@@ -197,7 +197,7 @@ inline void take_line(const char*& p, const char* end, const char*& ls, size_t& 
     const char* le = e ? e : end;
     ls = p;
     ll = le - p;
-    if (ll && ls[ll - 1] == '\r') --ll;
+    if (e && ll && ls[ll - 1] == '\r') --ll;  // "\r\n" is a line end, a "\r" before the end of the stream is not
     p = e ? e + 1 : end;
 }
 
@@ -752,6 +752,53 @@ int cmd_uniq(int argc, char** argv) {
     const std::string sep = a.get("separator", "\n");
     const bool wrap = a.has("wrap"), has_delim = a.has("delimiter");
     const std::string delim = a.get("delimiter", "");
+    if (sep == "\n" && !wrap && !getenv("UMGAP_UNIQ_RECORDS")) {
+        // The form every pipeline uses (items stay one per line): the stream is joined in place, block by block.  A group's
+        // text is ">header\n", its items joined by "\n", and a final "\n" unless the joined string is empty
+        // (fasta.rs:164-180) -- one item that is empty, or none.
+        BlockReader br(stdin);
+        std::string last, out;
+        bool have_last = false, nonempty = false;
+        size_t nitems = 0;
+        const char *p, *end;
+        while (br.next(p, end)) {
+            while (p < end) {
+                const char* ls;
+                size_t ll;
+                take_line(p, end, ls, ll);
+                const char* hs = ls + 1;
+                size_t hl = ll - 1;
+                if (has_delim) {  // the header up to the first occurrence of the delimiter (uniq.rs:61-68)
+                    const void* m = delim.empty() ? hs : memmem(hs, hl, delim.data(), delim.size());
+                    if (m) hl = (const char*)m - hs;
+                }
+                if (!(have_last && last.size() == hl && memcmp(last.data(), hs, hl) == 0)) {
+                    if (have_last && (nitems >= 2 || nonempty)) out += '\n';
+                    out += '>';
+                    out.append(hs, hl);
+                    out += '\n';
+                    last.assign(hs, hl);
+                    have_last = true;
+                    nitems = 0;
+                    nonempty = false;
+                }
+                while (p < end && *p != '>') {
+                    take_line(p, end, ls, ll);
+                    if (nitems) out += '\n';
+                    out.append(ls, ll);
+                    ++nitems;
+                    nonempty |= ll > 0;
+                }
+                if (out.size() > (1 << 20)) {
+                    put(stdout, out);
+                    out.clear();
+                }
+            }
+        }
+        if (have_last && (nitems >= 2 || nonempty)) out += '\n';
+        put(stdout, out);
+        return 0;
+    }
     FastaReader rd(stdin, false);
     Record r, last;
     bool have_last = false;
@@ -965,7 +1012,7 @@ inline void record_view(const char* buf, size_t rs, size_t re, const std::string
     const char* hend = e ? e : buf + re;
     hs = buf + rs + 1;
     hl = hend - hs;
-    if (hl && hs[hl - 1] == '\r') --hl;
+    if (e && hl && hs[hl - 1] == '\r') --hl;
     if (!delim.empty()) {
         const void* m = memmem(hs, hl, delim.data(), delim.size());
         if (m) hl = (const char*)m - hs;
@@ -1013,14 +1060,14 @@ void parse_block(const char* p, const char* end, const std::string& delim, size_
         const char* hend = e ? e : end;
         const char* hs = p + 1;
         size_t hl = hend - hs;
-        if (hl && hs[hl - 1] == '\r') --hl;
+        if (e && hl && hs[hl - 1] == '\r') --hl;
         p = e ? e + 1 : end;
         const size_t nt0 = B->nt.size();
         while (p < end && *p != '>') {  // sequence lines
             const char* le = (const char*)memchr(p, '\n', end - p);
             const char* lend = le ? le : end;
             size_t ll = lend - p;
-            if (ll && p[ll - 1] == '\r') --ll;
+            if (le && ll && p[ll - 1] == '\r') --ll;
             B->nt.append(p, ll);
             p = le ? le + 1 : end;
         }
@@ -1061,7 +1108,7 @@ void parse_peptide_block(const char* p, const char* end, const std::string& deli
         const char* hend = e ? e : end;
         const char* hs = p + 1;
         size_t hl = hend - hs;
-        if (hl && hs[hl - 1] == '\r') --hl;
+        if (e && hl && hs[hl - 1] == '\r') --hl;
         p = e ? e + 1 : end;
         if (!delim.empty()) {
             const void* m = memmem(hs, hl, delim.data(), delim.size());
@@ -1078,7 +1125,7 @@ void parse_peptide_block(const char* p, const char* end, const std::string& deli
             const char* le = (const char*)memchr(p, '\n', end - p);
             const char* lend = le ? le : end;
             size_t ll = lend - p;
-            if (ll && p[ll - 1] == '\r') --ll;
+            if (le && ll && p[ll - 1] == '\r') --ll;
             B->nt.append(p, ll);
             B->roff.push_back(B->nt.size());
             p = le ? le + 1 : end;
