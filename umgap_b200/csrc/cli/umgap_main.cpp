@@ -825,45 +825,87 @@ int cmd_uniq(int argc, char** argv) {
     return 0;
 }
 
-struct FastqReader {  // src/io/fastq.rs:26-87
-    LineSource src;
-    explicit FastqReader(FILE* f) : src(f) {}
-    bool next(std::string& header, std::string& seq) {
-        std::string line;
-        if (!src.next(line)) return false;
-        if (line.empty() || line[0] != '@') fail("Expected @ at beginning of fastq header.");
-        header.assign(line, 1, std::string::npos);
-        seq.clear();
-        size_t n = 0;
-        bool got;
-        while ((got = src.next(line)) && !(line.size() && line[0] == '+')) {
-            seq += line;
-            ++n;
+// Lines of a FASTQ stream as views into a refilled buffer (valid until the next call), "\n" / "\r\n" stripped.
+class FastqLines {
+  public:
+    explicit FastqLines(FILE* f) : f_(f), buf_(4u << 20) {}
+    bool next(const char*& ls, size_t& ll) {
+        for (;;) {
+            const char* nl = (const char*)memchr(buf_.data() + pos_, '\n', len_ - pos_);
+            if (nl) {
+                ls = buf_.data() + pos_;
+                ll = nl - ls;
+                pos_ = (nl - buf_.data()) + 1;
+                if (ll && ls[ll - 1] == '\r') --ll;
+                return true;
+            }
+            if (eof_) {  // the last line has no line end
+                if (pos_ == len_) return false;
+                ls = buf_.data() + pos_;
+                ll = len_ - pos_;
+                pos_ = len_;
+                return true;
+            }
+            memmove(buf_.data(), buf_.data() + pos_, len_ - pos_);
+            len_ -= pos_;
+            pos_ = 0;
+            if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);  // one line longer than the buffer
+            const size_t n = fread(buf_.data() + len_, 1, buf_.size() - len_, f_);
+            if (n == 0) eof_ = true;
+            len_ += n;
         }
-        for (size_t i = 0; i < n; ++i)
-            if (!src.next(line)) fail("Expected as many quality lines as sequence lines.");
-        return true;
     }
+
+  private:
+    FILE* f_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+    bool eof_ = false;
 };
+
+// The next record of a FASTQ stream (src/io/fastq.rs:26-87) appended to `out` as fasta::Writer prints it with an empty
+// separator (fasta.rs:164-180): ">header\n", the sequence lines joined, "\n" unless the sequence is empty.  The quality
+// lines -- as many as there were sequence lines -- are skipped.  False when the stream is exhausted.
+bool fastq_record_to_fasta(FastqLines& src, std::string& out) {
+    const char* ls;
+    size_t ll;
+    if (!src.next(ls, ll)) return false;
+    if (ll == 0 || ls[0] != '@') fail("Expected @ at beginning of fastq header.");
+    out += '>';
+    out.append(ls + 1, ll - 1);
+    out += '\n';
+    size_t n = 0, seq = 0;
+    while (src.next(ls, ll) && !(ll && ls[0] == '+')) {
+        out.append(ls, ll);
+        seq += ll;
+        ++n;
+    }
+    if (seq) out += '\n';
+    for (size_t i = 0; i < n; ++i)
+        if (!src.next(ls, ll)) fail("Expected as many quality lines as sequence lines.");
+    return true;
+}
 
 int cmd_fastq2fasta(int argc, char** argv) {
     Args a = parse(argc, argv, 2, {});
     if (a.pos.empty()) fail("The following required arguments were not provided:\n    <input>...");
     std::vector<FILE*> files;
-    std::vector<std::unique_ptr<FastqReader>> rd;
+    std::vector<std::unique_ptr<FastqLines>> rd;
     for (auto& p : a.pos) {
         FILE* f = fopen(p.c_str(), "r");
         if (!f) fail(p + ": " + strerror(errno));
         files.push_back(f);
-        rd.emplace_back(new FastqReader(f));
+        rd.emplace_back(new FastqLines(f));
     }
     std::string out;
     for (;;) {  // one record from every file, stop when any is exhausted (fastq2fasta.rs:62-84)
-        std::vector<std::pair<std::string, std::string>> row(rd.size());
+        const size_t row = out.size();
         bool ok = true;
-        for (size_t i = 0; i < rd.size() && ok; ++i) ok = rd[i]->next(row[i].first, row[i].second);
-        if (!ok) break;
-        for (auto& r : row) write_record(out, r.first, {r.second}, "", false);
+        for (size_t i = 0; i < rd.size() && ok; ++i) ok = fastq_record_to_fasta(*rd[i], out);
+        if (!ok) {
+            out.resize(row);  // a row with a file short of a record is not written
+            break;
+        }
         if (out.size() > (1 << 20)) {
             put(stdout, out);
             out.clear();
