@@ -226,6 +226,57 @@ inline void append_u32(std::string& out, uint32_t v) {
     while (n) out += tmp[--n];
 }
 
+// Decimal digits of v at w (room for 10), two at a time; returns the end.
+inline char* put_u32(char* w, uint32_t v) {
+    static const char kPairs[201] =
+        "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+    if (v < 10) {
+        *w = (char)('0' + v);
+        return w + 1;
+    }
+    char tmp[10];
+    int n = 10;
+    while (v >= 100) {
+        const uint32_t q = v / 100, r = v - q * 100;
+        tmp[--n] = kPairs[2 * r + 1];
+        tmp[--n] = kPairs[2 * r];
+        v = q;
+    }
+    if (v >= 10) {
+        tmp[--n] = kPairs[2 * v + 1];
+        tmp[--n] = kPairs[2 * v];
+    } else {
+        tmp[--n] = (char)('0' + v);
+    }
+    memcpy(w, tmp + n, 10 - n);
+    return w + (10 - n);
+}
+
+// The records of a block with their sequence lines joined (fasta::Reader with unwrap, fasta.rs:38-67): the sequences
+// one after the other in `seq`, off[i] .. off[i + 1] the i-th, the headers as views into the block.
+struct UnwrappedBlock {
+    std::string seq;
+    std::vector<uint64_t> off;
+    std::vector<std::pair<const char*, size_t>> heads;
+    void parse(const char* p, const char* end) {
+        seq.clear();
+        off.assign(1, 0);
+        heads.clear();
+        while (p < end) {
+            const char* ls;
+            size_t ll;
+            take_line(p, end, ls, ll);
+            heads.emplace_back(ls + 1, ll - 1);
+            while (p < end && *p != '>') {
+                take_line(p, end, ls, ll);
+                seq.append(ls, ll);
+            }
+            off.push_back(seq.size());
+        }
+    }
+    size_t size() const { return heads.size(); }
+};
+
 // A batch of records whose items are taxon ids, one per line (the streams between prot2kmer2lca, seedextend, uniq
 // and taxa2agg): headers in one arena, ids flattened, CSR offsets.
 struct IdBatch {
@@ -422,10 +473,6 @@ int cmd_translate(int argc, char** argv) {
     int slot_of[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0, s = 0; i < 6; ++i)
         if (mask >> i & 1) slot_of[i] = s++;
-    FastaReader rd(stdin, true);
-    std::vector<Record> recs;
-    Record r;
-    bool more = true;
     // an unknown table is an error even on empty input (translate.rs:79)
     {
         const uint64_t z[1] = {0};
@@ -433,66 +480,83 @@ int cmd_translate(int argc, char** argv) {
         uint8_t dummy[1];
         check(umgap_translate(0, dummy, z, 0, table, meth, 1, dummy, ao));
     }
-    while (more) {
-        recs.clear();
-        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
-        if (recs.empty()) break;
-        std::string out;
-        if (nsel) {
-            std::string nt;
-            std::vector<uint64_t> off(recs.size() + 1, 0);
-            for (size_t i = 0; i < recs.size(); ++i) {
-                nt += recs[i].seq[0];
-                off[i + 1] = nt.size();
-            }
-            std::vector<uint8_t> aa(umgap_translate_bound(nt.size(), recs.size(), mask));
-            std::vector<uint64_t> aoff(recs.size() * nsel + 1);
-            check(umgap_translate(0, (const uint8_t*)nt.data(), off.data(), recs.size(), table, meth, mask, aa.data(), aoff.data()));
-            for (size_t i = 0; i < recs.size(); ++i)
-                for (int k : order) {
-                    const size_t j = i * nsel + slot_of[k];
-                    std::string h = recs[i].header;
-                    if (a.has("append-name")) h += std::string("|") + names[k];
-                    write_record(out, h, {std::string((const char*)aa.data() + aoff[j], aoff[j + 1] - aoff[j])}, "", false);
+    // blocks of whole records parsed in place, one call per block, the text of the block formatted into one buffer
+    BlockReader br(stdin, 8u << 20);
+    UnwrappedBlock B;
+    std::vector<uint8_t> aa;
+    std::vector<uint64_t> aoff;
+    std::vector<char> out;
+    const bool named = a.has("append-name");
+    const char *p, *end;
+    while (br.next(p, end)) {
+        B.parse(p, end);
+        const size_t n = B.size();
+        if (!nsel || !n) continue;
+        aa.resize(umgap_translate_bound(B.seq.size(), n, mask));
+        aoff.resize(n * nsel + 1);
+        check(umgap_translate(0, (const uint8_t*)B.seq.data(), B.off.data(), n, table, meth, mask, aa.data(), aoff.data()));
+        size_t need = 0;
+        for (size_t i = 0; i < n; ++i) need += order.size() * (B.heads[i].second + 6);
+        for (int k : order)
+            for (size_t i = 0; i < n; ++i) need += aoff[i * nsel + slot_of[k] + 1] - aoff[i * nsel + slot_of[k]];
+        out.resize(need);
+        char* w = out.data();
+        for (size_t i = 0; i < n; ++i)
+            for (int k : order) {  // fasta::Writer, empty separator (fasta.rs:164-180)
+                const size_t j = i * nsel + slot_of[k];
+                *w++ = '>';
+                memcpy(w, B.heads[i].first, B.heads[i].second);
+                w += B.heads[i].second;
+                if (named) {
+                    *w++ = '|';
+                    for (const char* q = names[k]; *q; ++q) *w++ = *q;
                 }
-        }
-        put(stdout, out);
+                *w++ = '\n';
+                const size_t len = aoff[j + 1] - aoff[j];
+                memcpy(w, aa.data() + aoff[j], len);
+                w += len;
+                if (len) *w++ = '\n';
+            }
+        if (w != out.data() && fwrite(out.data(), 1, w - out.data(), stdout) != (size_t)(w - out.data())) fail("failed writing output");
     }
     return 0;
 }
 
 // ---- prot2kmer2lca ------------------------------------------------------------------------------
 void stream_prot2kmer2lca(FILE* in, FILE* out_f, const umgap_index* idx, bool one_on_one) {
-    FastaReader rd(in, true);
-    std::vector<Record> recs;
-    Record r;
-    bool more = true;
-    while (more) {
-        recs.clear();
-        while (recs.size() < kBatchRecords && (more = rd.next(r))) recs.push_back(r);
-        if (recs.empty()) break;
-        std::string aa;
-        std::vector<uint64_t> off(recs.size() + 1, 0);
-        for (size_t i = 0; i < recs.size(); ++i) {
-            aa += recs[i].seq[0];
-            off[i + 1] = aa.size();
-        }
-        std::vector<uint32_t> taxa(umgap_kmer_lookup_bound(aa.size(), recs.size()));
-        std::vector<uint64_t> toff(recs.size() + 1);
-        std::vector<uint8_t> kept(recs.size() + 1);
-        check(umgap_kmer_lookup(idx, (const uint8_t*)aa.data(), off.data(), recs.size(), one_on_one, taxa.data(), toff.data(), kept.data()));
-        std::string out;
-        for (size_t i = 0; i < recs.size(); ++i) {
+    // blocks of whole records parsed in place, one lookup call per block, the ids printed into one buffer
+    BlockReader br(in, 8u << 20);
+    UnwrappedBlock B;
+    std::vector<uint32_t> taxa;
+    std::vector<uint64_t> toff;
+    std::vector<uint8_t> kept;
+    std::vector<char> out;
+    const char *p, *end;
+    while (br.next(p, end)) {
+        B.parse(p, end);
+        const size_t n = B.size();
+        if (!n) continue;
+        taxa.resize(umgap_kmer_lookup_bound(B.seq.size(), n));
+        toff.resize(n + 1);
+        kept.resize(n + 1);
+        check(umgap_kmer_lookup(idx, (const uint8_t*)B.seq.data(), B.off.data(), n, one_on_one, taxa.data(), toff.data(), kept.data()));
+        size_t need = 11 * toff[n];
+        for (size_t i = 0; i < n; ++i)
+            if (kept[i]) need += B.heads[i].second + 2;
+        out.resize(need);
+        char* w = out.data();
+        for (size_t i = 0; i < n; ++i) {
             if (!kept[i]) continue;  // prot2kmer2lca.rs:172
-            out += '>';
-            out += recs[i].header;
-            out += '\n';
+            *w++ = '>';
+            memcpy(w, B.heads[i].first, B.heads[i].second);
+            w += B.heads[i].second;
+            *w++ = '\n';
             for (uint64_t j = toff[i]; j < toff[i + 1]; ++j) {
-                append_u32(out, taxa[j]);
-                out += '\n';
+                w = put_u32(w, taxa[j]);
+                *w++ = '\n';
             }
         }
-        put(out_f, out);
+        if (w != out.data() && fwrite(out.data(), 1, w - out.data(), out_f) != (size_t)(w - out.data())) fail("failed writing output");
         fflush(out_f);
     }
 }
